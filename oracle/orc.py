@@ -1,0 +1,383 @@
+"""ctypes bindings of the parity oracle -- TEST INFRASTRUCTURE, not product code.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` leg
+may import this module. It wraps
+
+* ``oracle/liboracle.so``            -- the plain-C restatement (oracle/sb_oracle.c), and
+* ``oracle/_ref/libref_solvers.so``  -- the reference's own solver headers compiled verbatim
+  (oracle/ref_build/ref_solvers.cpp), when it has been built (needs /root/reference at build
+  time only; the built file travels to the GPU box).
+
+Both are built by ``make -C oracle`` (``__graft_entry__.build()`` runs it).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+REF_LIB_PATH = os.path.join(HERE, "_ref", "libref_solvers.so")
+REF_MESH_TOOL = os.path.join(HERE, "_ref", "ref_mesh_tool")
+
+RED_SEQ, RED_TREE = 0, 1
+COL_PAD = -(2**31)
+
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+
+APPLY_FN = C.CFUNCTYPE(None, C.c_void_p, _f64p, _f64p, C.c_size_t)
+
+
+def build(ref: bool | None = None) -> None:
+    """Run the oracle Makefile (liboracle.so always; _ref/ when the reference is mounted)."""
+    target = "all" if ref is None else ("ref" if ref else "oracle")
+    subprocess.run(["make", "-C", HERE, target], check=True, capture_output=True)
+
+
+class FaceOpStruct(C.Structure):
+    _fields_ = [
+        ("n_cells", C.c_int64), ("n_faces", C.c_int64),
+        ("face_cell", _i32p), ("face_area", _f64p), ("face_dist", _f64p), ("cell_vol", _f64p),
+        ("n_bfaces", C.c_int64),
+        ("bface_cell", _i32p), ("bface_area", _f64p), ("bface_dist", _f64p),
+        ("prefill", C.c_int32), ("dt", C.c_double),
+    ]
+
+
+class SolverOpts(C.Structure):
+    _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
+                ("reduction_mode", C.c_int32)]
+
+
+class SolverReport(C.Structure):
+    _fields_ = [("converged", C.c_int32), ("iterations", C.c_int64), ("abs_err", C.c_double),
+                ("rel_err", C.c_double), ("n_hist", C.c_int64), ("n_trace", C.c_int64)]
+
+
+class RefOpts(C.Structure):
+    _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
+                ("num_inner_iterations", C.c_int64), ("reduction_mode", C.c_int32),
+                ("relaxation_factor", C.c_double)]
+
+
+class RefReport(C.Structure):
+    _fields_ = [("converged", C.c_int32), ("iterations", C.c_int64), ("abs_err", C.c_double),
+                ("rel_err", C.c_double), ("n_hist", C.c_int64), ("n_trace", C.c_int64),
+                ("n_apply", C.c_int64)]
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build(ref=False)
+        L = C.CDLL(LIB_PATH)
+        L.orc_apply_faces.argtypes = [C.POINTER(FaceOpStruct), _f64p, _f64p]
+        L.orc_apply_faces.restype = None
+        L.orc_rows_width.argtypes = [C.POINTER(FaceOpStruct)]
+        L.orc_rows_width.restype = C.c_int
+        L.orc_build_rows.argtypes = [C.POINTER(FaceOpStruct), C.c_int, C.c_int64, _i32p, _i64p]
+        L.orc_build_rows.restype = None
+        L.orc_rows_faithful.argtypes = [C.POINTER(FaceOpStruct), C.c_int, C.c_int64, _i64p, _f64p, _f64p]
+        L.orc_rows_faithful.restype = None
+        L.orc_apply_rows_faithful.argtypes = [C.c_int64, C.c_int, C.c_int64, _i32p, _f64p, _f64p,
+                                              C.c_int32, C.c_double, _f64p, _f64p]
+        L.orc_apply_rows_faithful.restype = None
+        L.orc_rows_coef.argtypes = [C.POINTER(FaceOpStruct), C.c_int, C.c_int64, _i32p, _i64p, _i32p,
+                                    _f64p, _f64p]
+        L.orc_rows_coef.restype = None
+        L.orc_apply_rows_coef.argtypes = [C.c_int64, C.c_int, C.c_int64, _i32p, _f64p, _f64p, _f64p, _f64p]
+        L.orc_apply_rows_coef.restype = None
+        L.orc_dot.argtypes = [C.c_int64, _f64p, _f64p, C.c_int]
+        L.orc_dot.restype = C.c_double
+        L.orc_norm2.argtypes = [C.c_int64, _f64p, C.c_int]
+        L.orc_norm2.restype = C.c_double
+        L.orc_safe_divide.argtypes = [C.c_double, C.c_double]
+        L.orc_safe_divide.restype = C.c_double
+        for name in ("orc_cg", "orc_bicgstab"):
+            fn = getattr(L, name)
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, _f64p, _f64p, C.POINTER(SolverOpts),
+                           C.POINTER(SolverReport), _f64p, C.c_int64, _f64p, C.c_int64]
+            fn.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_LIB_PATH)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        if not have_ref():
+            raise FileNotFoundError(
+                f"{REF_LIB_PATH} not built (needs /root/reference; run `make -C oracle ref`)")
+        R = C.CDLL(REF_LIB_PATH)
+        R.ref_solve.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, _f64p, _f64p,
+                                C.POINTER(RefOpts), C.POINTER(RefReport), _f64p, C.c_int64, _f64p,
+                                C.c_int64]
+        R.ref_solve.restype = C.c_int
+        R.ref_reset_rng.restype = None
+        R.ref_fill_randomly_generic.argtypes = [C.c_size_t, _f64p]
+        R.ref_fill_randomly_generic.restype = None
+        R.ref_dot.argtypes = [C.c_size_t, _f64p, _f64p]
+        R.ref_dot.restype = C.c_double
+        R.ref_norm2.argtypes = [C.c_size_t, _f64p]
+        R.ref_norm2.restype = C.c_double
+        R.ref_build_info.restype = C.c_char_p
+        _ref = R
+    return _ref
+
+
+def _p(a, typ):
+    return a.ctypes.data_as(typ)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+@dataclass
+class FaceMesh:
+    """Face-list SoA of one mesh (the arrays sb_mesh_soa / orc_face_op point at)."""
+    n_cells: int
+    face_cell: np.ndarray   # int32 [F,2] inner, outer
+    face_area: np.ndarray   # f64 [F]
+    face_dist: np.ndarray   # f64 [F]
+    cell_vol: np.ndarray    # f64 [N]
+    bface_cell: np.ndarray  # int32 [B]
+    bface_area: np.ndarray  # f64 [B]
+    bface_dist: np.ndarray  # f64 [B]
+
+    @property
+    def n_faces(self) -> int:
+        return int(self.face_area.shape[0])
+
+    @property
+    def n_bfaces(self) -> int:
+        return int(self.bface_area.shape[0])
+
+    def without_boundary(self) -> "FaceMesh":
+        e = np.zeros(0)
+        return FaceMesh(self.n_cells, self.face_cell, self.face_area, self.face_dist, self.cell_vol,
+                        np.zeros(0, np.int32), e, e.copy())
+
+
+class FaceOp:
+    """y = prefill(x) + dt * div grad x over a FaceMesh (see sb_oracle.h: orc_face_op)."""
+
+    def __init__(self, mesh: FaceMesh, prefill: int, dt: float, dirichlet: bool = False):
+        self.mesh = mesh
+        self.prefill, self.dt = int(prefill), float(dt)
+        self._keep = [np.ascontiguousarray(mesh.face_cell, np.int32).reshape(-1), _f64(mesh.face_area),
+                      _f64(mesh.face_dist), _f64(mesh.cell_vol),
+                      np.ascontiguousarray(mesh.bface_cell, np.int32), _f64(mesh.bface_area),
+                      _f64(mesh.bface_dist)]
+        k = self._keep
+        nb = mesh.n_bfaces if dirichlet else 0
+        self.struct = FaceOpStruct(mesh.n_cells, mesh.n_faces, _p(k[0], _i32p), _p(k[1], _f64p),
+                                   _p(k[2], _f64p), _p(k[3], _f64p), nb, _p(k[4], _i32p),
+                                   _p(k[5], _f64p), _p(k[6], _f64p), self.prefill, self.dt)
+        self.n = mesh.n_cells
+
+    # --- face loop ---------------------------------------------------------------------------
+    def apply(self, x):
+        x = _f64(x)
+        y = np.empty(self.n)
+        lib().orc_apply_faces(C.byref(self.struct), _p(x, _f64p), _p(y, _f64p))
+        return y
+
+    @property
+    def callback(self):
+        """(function pointer, user pointer) pair for orc_cg / ref_solve."""
+        return C.cast(lib().orc_apply_faces_cb, C.c_void_p), C.cast(C.pointer(self.struct), C.c_void_p)
+
+    # --- cell rows ---------------------------------------------------------------------------
+    def rows(self, ld: int | None = None):
+        L = lib()
+        w = L.orc_rows_width(C.byref(self.struct))
+        ld = self.n if ld is None else int(ld)
+        col = np.empty((w, ld), np.int32)
+        face = np.empty((w, ld), np.int64)
+        L.orc_build_rows(C.byref(self.struct), w, ld, _p(col, _i32p), _p(face, _i64p))
+        return w, ld, col, face
+
+    def rows_faithful(self, ld: int | None = None):
+        w, ld, col, face = self.rows(ld)
+        g = np.empty((w, ld))
+        d = np.empty((w, ld))
+        lib().orc_rows_faithful(C.byref(self.struct), w, ld, _p(face, _i64p), _p(g, _f64p), _p(d, _f64p))
+        return w, ld, col, g, d
+
+    def rows_coef(self, ld: int | None = None):
+        w, ld, col, face = self.rows(ld)
+        col_out = np.empty((w, ld), np.int32)
+        a = np.empty((w, ld))
+        diag = np.empty(ld)
+        lib().orc_rows_coef(C.byref(self.struct), w, ld, _p(col, _i32p), _p(face, _i64p),
+                            _p(col_out, _i32p), _p(a, _f64p), _p(diag, _f64p))
+        return w, ld, col_out, a, diag
+
+    def apply_rows_faithful(self, x, rows=None):
+        w, ld, col, g, d = rows or self.rows_faithful()
+        x = _f64(x)
+        y = np.empty(self.n)
+        lib().orc_apply_rows_faithful(self.n, w, ld, _p(col, _i32p), _p(g, _f64p), _p(d, _f64p),
+                                      self.prefill, self.dt, _p(x, _f64p), _p(y, _f64p))
+        return y
+
+    def apply_rows_coef(self, x, rows=None):
+        w, ld, col, a, diag = rows or self.rows_coef()
+        x = _f64(x)
+        y = np.empty(self.n)
+        lib().orc_apply_rows_coef(self.n, w, ld, _p(col, _i32p), _p(a, _f64p), _p(diag, _f64p),
+                                  _p(x, _f64p), _p(y, _f64p))
+        return y
+
+
+class CallbackOp:
+    """Wrap a Python callable y = f(x) as an (fn, user) pair (slow; small cases only)."""
+
+    def __init__(self, f, n):
+        self.n = n
+
+        def _cb(user, y, x, n_):
+            xv = np.ctypeslib.as_array(x, shape=(n_,))
+            yv = np.ctypeslib.as_array(y, shape=(n_,))
+            yv[:] = f(xv.copy())
+
+        self._cfn = APPLY_FN(_cb)
+
+    @property
+    def callback(self):
+        return C.cast(self._cfn, C.c_void_p), C.c_void_p(None)
+
+
+def dot(a, b, mode=RED_SEQ) -> float:
+    a, b = _f64(a), _f64(b)
+    return float(lib().orc_dot(a.shape[0], _p(a, _f64p), _p(b, _f64p), mode))
+
+
+def norm2(a, mode=RED_SEQ) -> float:
+    a = _f64(a)
+    return float(lib().orc_norm2(a.shape[0], _p(a, _f64p), mode))
+
+
+@dataclass
+class SolveResult:
+    x: np.ndarray
+    converged: bool
+    iterations: int
+    abs_err: float
+    rel_err: float
+    hist: np.ndarray    # hist[0] initial residual, hist[k] after iteration k
+    trace: np.ndarray   # every dot/norm result in call order
+    n_apply: int = -1
+
+
+def solve(solver: str, op, b, x0=None, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6,
+          mode=RED_SEQ) -> SolveResult:
+    """Plain-C restated solvers (oracle/sb_oracle.c): 'cg' | 'bicgstab'."""
+    L = lib()
+    fn = {"cg": L.orc_cg, "bicgstab": L.orc_bicgstab}[solver]
+    b = _f64(b)
+    n = b.shape[0]
+    x = np.zeros(n) if x0 is None else _f64(x0).copy()
+    cap_h = num_iterations + 2
+    cap_t = 8 * num_iterations + 16
+    hist, trace = np.zeros(cap_h), np.zeros(cap_t)
+    opts = SolverOpts(num_iterations, abs_tol, rel_tol, mode)
+    rep = SolverReport()
+    f, u = op.callback
+    rc = fn(f, u, n, _p(b, _f64p), _p(x, _f64p), C.byref(opts), C.byref(rep), _p(hist, _f64p), cap_h,
+            _p(trace, _f64p), cap_t)
+    assert rc == 0
+    return SolveResult(x, bool(rep.converged), rep.iterations, rep.abs_err, rep.rel_err,
+                       hist[:rep.n_hist].copy(), trace[:min(rep.n_trace, cap_t)].copy())
+
+
+REF_SOLVERS = ("cg", "cgs", "bicgstab", "bicgstabl", "gmres", "fgmres", "tfqmr", "tfqmr1", "idrs",
+               "richardson")
+
+
+def ref_solve(solver: str, op, b, x0=None, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6,
+              num_inner=0, mode=RED_SEQ, relaxation_factor=0.0, reset_rng=True,
+              trace_cap=None) -> SolveResult:
+    """The reference's own solver headers (oracle/_ref), on a host vector."""
+    R = ref()
+    if reset_rng:
+        R.ref_reset_rng()
+    b = _f64(b)
+    n = b.shape[0]
+    x = np.zeros(n) if x0 is None else _f64(x0).copy()
+    cap_h = num_iterations + 2
+    cap_t = trace_cap or (64 * num_iterations + 256)
+    hist, trace = np.zeros(cap_h), np.zeros(cap_t)
+    opts = RefOpts(num_iterations, abs_tol, rel_tol, num_inner, mode, relaxation_factor)
+    rep = RefReport()
+    f, u = op.callback
+    rc = R.ref_solve(solver.encode(), n, f, u, _p(b, _f64p), _p(x, _f64p), C.byref(opts), C.byref(rep),
+                     _p(hist, _f64p), cap_h, _p(trace, _f64p), cap_t)
+    if rc != 0:
+        raise ValueError(f"ref_solve: unknown solver {solver!r}")
+    return SolveResult(x, bool(rep.converged), rep.iterations, rep.abs_err, rep.rel_err,
+                       hist[:rep.n_hist].copy(), trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)
+
+
+# ---- reading the binary dumps of oracle/_ref/ref_mesh_tool ------------------------------------
+class _Reader:
+    def __init__(self, path):
+        with open(path, "rb") as f:
+            self.buf = f.read()
+        self.off = 0
+
+    def i64(self):
+        v = struct.unpack_from("<q", self.buf, self.off)[0]
+        self.off += 8
+        return v
+
+    def f64(self):
+        v = struct.unpack_from("<d", self.buf, self.off)[0]
+        self.off += 8
+        return v
+
+    def arr(self, dtype):
+        n = self.i64()
+        a = np.frombuffer(self.buf, dtype=dtype, count=n, offset=self.off).copy()
+        self.off += n * np.dtype(dtype).itemsize
+        return a
+
+
+def read_mesh_export(path):
+    r = _Reader(path)
+    n_cells, n_nodes, n_faces_total, n_labels = r.i64(), r.i64(), r.i64(), r.i64()
+    face_cell = r.arr(np.int32).reshape(-1, 2)
+    face_area, face_dist = r.arr(np.float64), r.arr(np.float64)
+    bface_cell, bface_area, bface_dist, bface_label = (r.arr(np.int32), r.arr(np.float64),
+                                                       r.arr(np.float64), r.arr(np.int32))
+    cell_vol, cx, cy = r.arr(np.float64), r.arr(np.float64), r.arr(np.float64)
+    mesh = FaceMesh(n_cells, face_cell, face_area, face_dist, cell_vol, bface_cell, bface_area, bface_dist)
+    extra = dict(n_nodes=n_nodes, n_faces_total=n_faces_total, n_face_labels=n_labels,
+                 bface_label=bface_label, cell_center=np.stack([cx, cy], 1))
+    return mesh, extra
+
+
+def read_cg_dump(path):
+    r = _Reader(path)
+    n, conv, it = r.i64(), r.i64(), r.i64()
+    abs_err, rel_err = r.f64(), r.f64()
+    b, x, hist = r.arr(np.float64), r.arr(np.float64), r.arr(np.float64)
+    return dict(n=n, converged=bool(conv), iterations=it, abs_err=abs_err, rel_err=rel_err, b=b, x=x,
+                hist=hist)
