@@ -1,0 +1,233 @@
+/*
+ * stormb200.h -- C ABI of the B200-native Krylov hot path for StormRuler.
+ *
+ * This is the drop-in boundary. The reference (Jhuighuy/StormRuler) is a header-only C++
+ * template library with no FFI of its own; its extension points for this path are
+ *   - the `legacy_vector_like` vector concept          source/Storm/Solvers/Operator.hpp:39-45
+ *   - `Operator<Vector>::mul` (virtual)                source/Storm/Solvers/Operator.hpp:66-74
+ *   - the Bittern free functions / operators found by overload resolution on the vector type
+ *                                                      source/Storm/Bittern/MatrixAlgorithms.hpp,
+ *                                                      MatrixMath.hpp, MatrixTarget.hpp
+ * The C++23 host header stormruler_b200/host/Storm/B200/DeviceVector.hpp implements those on top
+ * of the functions below; g++ compiles it together with the unmodified reference solver headers,
+ * nvcc compiles this library for sm_100a (nvcc 12.9 cannot parse C++23, hence the C boundary).
+ * INTEGRATION.md shows the binding a StormRuler maintainer would add.
+ *
+ * Conventions: opaque handles; every function returns an int status (0 = SB_OK, negative =
+ * error) and never throws; sb_last_error() returns a thread-local message for the last failure.
+ * Pointers are DEVICE pointers unless their name starts with h_. All device vectors must come
+ * from sb_vec_alloc (it pads the capacity so kernels can use unguarded 128-bit accesses).
+ * One context = one device = one host thread at a time (the reference is single-threaded,
+ * SURVEY.md 8b). There is no CPU fallback: without a CUDA device every entry point that touches
+ * the device fails with SB_ERR_CUDA.
+ */
+#ifndef STORMB200_H
+#define STORMB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_API __attribute__((visibility("default")))
+
+#define SB_OK 0
+#define SB_ERR_INVALID (-1) /* bad argument */
+#define SB_ERR_CUDA (-2)    /* CUDA runtime failure (sticky: the context is unusable afterwards) */
+#define SB_ERR_NOMEM (-3)
+#define SB_ERR_NCCL (-4)
+#define SB_ERR_STATE (-5)   /* call not valid in this state (e.g. comm not initialised) */
+
+typedef struct sb_ctx sb_ctx;
+typedef struct sb_op sb_op;
+
+SB_API const char* sb_last_error(void);
+SB_API int sb_version(void);
+
+/* ---- context ---------------------------------------------------------------------------------
+ * Owns the device, one compute stream, reduction scratch and pinned staging memory. */
+SB_API int sb_ctx_create(int device, sb_ctx** out);
+SB_API int sb_ctx_destroy(sb_ctx* ctx);
+SB_API int sb_sync(sb_ctx* ctx);
+/* cudaStream_t of the compute stream (for CUDA-event timing by the caller). */
+SB_API void* sb_ctx_stream(sb_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+SB_API int64_t sb_ctx_launch_count(sb_ctx* ctx);
+
+/* ---- vectors: replaces the storage of Feathers/Field.hpp:60-114 (CellField, the solvers' Vector)
+ * sb_vec_alloc zero-fills, like Field::assign (Field.hpp:82-84) which IDR(s) relies on. */
+SB_API int sb_vec_alloc(sb_ctx* ctx, size_t n, double** d_out);
+SB_API int sb_vec_free(sb_ctx* ctx, double* d);
+SB_API int sb_vec_upload(sb_ctx* ctx, double* d, const double* h_src, size_t n);
+SB_API int sb_vec_download(sb_ctx* ctx, const double* d, double* h_dst, size_t n);
+
+/* ---- operator: replaces the face loop of source_apps/playground/Playground.cpp:115-131 driven
+ * through FunctionalOperator::mul (Operator.hpp:156-158), plus the boundary-ghost pattern of
+ * Feathers/ConvectionScheme.hpp:95-106.
+ *
+ *   y = prefill(x);  for interior faces f (ascending): flux = dt*(x[outer]-x[inner])/dist_f;
+ *                    y[inner] += (area_f/vol_inner)*flux;  y[outer] -= (area_f/vol_outer)*flux;
+ *                    for Dirichlet boundary faces b (ascending, after all interior faces):
+ *                    flux = dt*((-x[c]) - x[c])/bdist_b;  y[c] += (barea_b/vol_c)*flux.
+ *
+ * The face list is uploaded once and turned into a cell-row (ELL) layout on the device side:
+ * rows ordered by cell, entries of a row in ascending face index (the CPU's summation order). */
+typedef struct sb_mesh_soa {
+  int64_t n_cells;
+  int64_t n_faces;           /* interior faces, reference face order */
+  const int32_t* face_cell;  /* h_ [2*n_faces] inner, outer  (Mesh.hpp:269-280) */
+  const double* face_area;   /* h_ [n_faces] */
+  const double* face_dist;   /* h_ [n_faces] ||centre_outer - centre_inner|| */
+  const double* cell_vol;    /* h_ [n_cells] */
+  int64_t n_bfaces;          /* Dirichlet (mirror ghost) boundary faces; 0 = pure Neumann */
+  const int32_t* bface_cell; /* h_ [n_bfaces] */
+  const double* bface_area;  /* h_ [n_bfaces] */
+  const double* bface_dist;  /* h_ [n_bfaces] ||ghost centre - cell centre|| */
+} sb_mesh_soa;
+
+#define SB_FORM_FAITHFUL 0 /* per entry (col, area/vol, dist): bit-identical to the face loop */
+#define SB_FORM_COEF 1     /* per entry (col, coef) + diagonal: the 12 B/entry streaming form  */
+
+typedef struct sb_op_desc {
+  int32_t form;    /* SB_FORM_* */
+  int32_t prefill; /* 0: y starts from 0; 1: y starts from x (`c_hat <<= c_in`, Playground.cpp:162) */
+  double dt;       /* the dt argument of stormDivGrad, verbatim */
+} sb_op_desc;
+
+typedef struct sb_op_info {
+  int64_t n_cells;
+  int64_t n_entries;      /* stored off-diagonal entries (ghosts included in the faithful form) */
+  int32_t width;          /* ELL width */
+  int64_t ld;             /* leading dimension (padded rows) */
+  int32_t form;
+  int64_t device_bytes;   /* bytes of operator data resident in HBM */
+  int64_t algorithmic_bytes_per_apply; /* 24*N + 12*entries (coef form) */
+} sb_op_info;
+
+SB_API int sb_op_create(sb_ctx* ctx, const sb_mesh_soa* h_mesh, const sb_op_desc* desc, sb_op** out);
+SB_API int sb_op_destroy(sb_ctx* ctx, sb_op* op);
+SB_API int sb_op_get_info(const sb_op* op, sb_op_info* info);
+/* Copy the row layout back to the host for bit-exact comparison with the oracle:
+ * h_col [width*ld] int32, h_val0 [width*ld] (coef, or area/vol), h_val1 [width*ld] (dist; faithful
+ * form only, may be NULL), h_diag [ld] (coef form only, may be NULL). */
+SB_API int sb_op_download_rows(sb_ctx* ctx, const sb_op* op, int32_t* h_col, double* h_val0,
+                               double* h_val1, double* h_diag);
+/* y <- A(x): Operator::mul (Operator.hpp:74). x and y must not alias. */
+SB_API int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y);
+
+/* ---- mesh ingestion (host side, no GPU needed): replaces what the playground gets from
+ * read_mesh_from_tetgen + UnstructuredMesh (Mallard/IoTetgen.hpp:44-235, MeshUnstructured.hpp:350-425,
+ * 464-500, 509-554) for the hot path, in 3-D (the reference mesh layer is 2-D only):
+ * a cell soup is turned into the face-list SoA above. Conventions follow the reference:
+ *   - local faces of a tetrahedron / hexahedron as in Mallard/Shape.hpp:559-606 / 803-843;
+ *   - a face is created by the first cell (in cell order, local-face order) that touches it; that
+ *     cell is its inner cell, the second one its outer cell (MeshUnstructured.hpp:509-554);
+ *   - faces are ordered by creation, interior faces (label 0) first (MeshUnstructured.hpp:464-500);
+ *   - triangle area = |cross|/2, quadrangle = two triangles (n1,n2,n3)+(n3,n4,n1), cell centre =
+ *     barycentre (simple shapes: node mean; hexahedron: volume-weighted over its 5 tetrahedral
+ *     pieces), Shape.hpp:170-215,310-334,395-402,845-852; tetrahedron volume = |triple product|/6.
+ * All integer results (face order, inner/outer, permutations, partitions, halo maps) are
+ * deterministic and checked bit for bit against the independent C restatement in oracle/. */
+typedef struct sb_mesh sb_mesh;
+#define SB_CELL_TET 0
+#define SB_CELL_HEX 1
+
+/* Box [0,1]^3 of nx*ny*nz hexahedra, optionally split into 6 Kuhn tetrahedra each (SB_CELL_TET).
+ * Interior nodes are displaced by U(-jitter*h, jitter*h) per coordinate (std::mt19937_64(seed_jitter),
+ * node order, x then y then z); if shuffle != 0 the cell order is randomly permuted
+ * (Fisher-Yates, std::mt19937_64(seed_shuffle)) so that renumbering has something to do. */
+SB_API int sb_mesh_generate_box(int cell_kind, int nx, int ny, int nz, double jitter, uint64_t seed_jitter,
+                                int shuffle, uint64_t seed_shuffle, sb_mesh** out);
+/* General ingestion: h_xyz [3*n_nodes], h_cell_nodes [n_cells * (4 | 8)]. */
+SB_API int sb_mesh_from_cells(int cell_kind, int64_t n_nodes, const double* h_xyz, int64_t n_cells,
+                              const int32_t* h_cell_nodes, sb_mesh** out);
+SB_API int sb_mesh_destroy(sb_mesh* mesh);
+/* Reverse Cuthill-McKee renumbering of the cells over the face adjacency graph; faces are rebuilt
+ * for the new cell order. h_perm (may be NULL) receives perm[new] = old (Utils/Permutations.hpp:77-103). */
+SB_API int sb_mesh_renumber_rcm(sb_mesh* mesh, int32_t* h_perm);
+/* Apply an arbitrary cell permutation perm[new] = old (bijection check included). */
+SB_API int sb_mesh_permute_cells(sb_mesh* mesh, const int32_t* h_perm);
+/* Fill `soa` with pointers into the mesh (valid until the mesh is modified or destroyed). Boundary
+ * faces: every face with a single adjacent cell; bface_dist = 2*|face centre - cell centre|. */
+SB_API int sb_mesh_get_soa(const sb_mesh* mesh, sb_mesh_soa* soa);
+SB_API int sb_mesh_cell_centers(const sb_mesh* mesh, double* h_xyz /* [3*n_cells] */);
+/* Bandwidth of the cell graph, max |inner - outer| over interior faces (renumbering quality). */
+SB_API int64_t sb_mesh_bandwidth(const sb_mesh* mesh);
+
+/* ---- BLAS-1: replaces Bittern's lazy expressions + assignment operators
+ * (MatrixMath.hpp:233-301, MatrixTarget.hpp:96-119, MatrixAlgorithms.hpp:95-135) for the vector.
+ * An expression is a postfix program over <= SB_EXPR_MAX_VEC vector operands and
+ * <= SB_EXPR_MAX_SCAL scalars, evaluated per element in exactly the order written (each
+ * operation rounded separately, no FMA contraction), e.g. r + beta*(p - omega*v) is
+ *   V0 S0 V1 S1 V2 MUL SUB MUL ADD.   The target may alias any operand. */
+#define SB_EXPR_MAX_OPS 24
+#define SB_EXPR_MAX_VEC 4
+#define SB_EXPR_MAX_SCAL 4
+enum {
+  SB_OP_VEC0 = 0, SB_OP_VEC1, SB_OP_VEC2, SB_OP_VEC3,
+  SB_OP_SCAL0 = 8, SB_OP_SCAL1, SB_OP_SCAL2, SB_OP_SCAL3,
+  SB_OP_ADD = 16, SB_OP_SUB, SB_OP_MUL, SB_OP_DIV, SB_OP_NEG
+};
+typedef struct sb_expr {
+  int32_t n_ops;
+  uint8_t ops[SB_EXPR_MAX_OPS];
+  const double* vec[SB_EXPR_MAX_VEC];
+  double scal[SB_EXPR_MAX_SCAL];
+} sb_expr;
+enum { SB_ASSIGN = 0, SB_ADD_ASSIGN = 1, SB_SUB_ASSIGN = 2, SB_MUL_ASSIGN = 3, SB_DIV_ASSIGN = 4 };
+/* y (op)= expr, element-wise over n elements. */
+SB_API int sb_eval(sb_ctx* ctx, double* y, size_t n, int assign_op, const sb_expr* expr);
+SB_API int sb_fill(sb_ctx* ctx, double* y, size_t n, double value);
+SB_API int sb_copy(sb_ctx* ctx, double* y, const double* x, size_t n);
+
+/* dot_product (MatrixAlgorithms.hpp:310-317) and the square of norm_2 (:262-270) with the fixed
+ * reduction tree "SB_TREE v1" (DESIGN.md): run-to-run and grid-size independent. Results are
+ * returned on the host (one stream synchronisation per call). sb_dot_batch evaluates m dot
+ * products with one synchronisation. */
+SB_API int sb_dot(sb_ctx* ctx, const double* a, const double* b, size_t n, double* h_out);
+SB_API int sb_norm2(sb_ctx* ctx, const double* a, size_t n, double* h_out);
+SB_API int sb_dot_batch(sb_ctx* ctx, int m, const double* const* h_a, const double* const* h_b, size_t n,
+                        double* h_out);
+
+/* ---- fused solvers: CgSolver (SolverCg.hpp:54-126) and BiCgStabSolver (SolverBiCgStab.hpp:59-165)
+ * driven as IterativeSolver::solve (Solver.hpp:116-147), no preconditioner. Same statements, same
+ * per-element operation order and the same stopping rule as the reference; scalars stay on the
+ * device and each dot/norm is fused into the kernel that produces its operand. */
+typedef struct sb_solver_opts {
+  int64_t num_iterations; /* Solver.hpp:67 (default 2000) */
+  double abs_tol;         /* Solver.hpp:71 (default 1e-6); <= 0 disables */
+  double rel_tol;         /* Solver.hpp:72 (default 1e-6); <= 0 disables */
+  int32_t check_every;    /* host polls the device convergence flag every this many iterations (0 = 32) */
+  int32_t use_graph;      /* 1: replay one captured CUDA graph per iteration */
+} sb_solver_opts;
+
+typedef struct sb_solver_report {
+  int32_t converged;
+  int64_t iterations;  /* IterativeSolver::iteration after solve() */
+  double initial_err;
+  double abs_err;      /* IterativeSolver::absolute_error */
+  double rel_err;      /* IterativeSolver::relative_error */
+  int64_t n_hist;      /* entries written to h_hist: [0] initial, [k] after iteration k */
+  int64_t n_trace;     /* entries written to h_trace: every reduction result, reference call order */
+  double solve_ms;     /* device time of the solve (CUDA events) */
+  int64_t launches;    /* kernels launched by this solve */
+} sb_solver_report;
+
+SB_API int sb_cg_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b,
+                       const sb_solver_opts* opts, sb_solver_report* report, double* h_hist,
+                       int64_t hist_cap, double* h_trace, int64_t trace_cap);
+SB_API int sb_bicgstab_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b,
+                             const sb_solver_opts* opts, sb_solver_report* report, double* h_hist,
+                             int64_t hist_cap, double* h_trace, int64_t trace_cap);
+/* Same, with HOST buffers for x (in: initial guess, out: solution) and b: the copies are part
+ * of the call (bench.py's e2e figure). solver: "cg" | "bicgstab". */
+SB_API int sb_solve_host(sb_ctx* ctx, const sb_op* op, const char* solver, double* h_x,
+                         const double* h_b, const sb_solver_opts* opts, sb_solver_report* report,
+                         double* h_hist, int64_t hist_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STORMB200_H */

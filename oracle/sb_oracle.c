@@ -192,9 +192,9 @@ void orc_apply_rows_coef(int64_t n, int width, int64_t ld, const int32_t* col, c
  *   element e belongs to CTA tile c = e / 2048, warp w = (e % 2048) / 256, sub-iteration
  *   j = (e % 256) / 64, lane l = (e % 64) / 2. Lane accumulates its 8 products sequentially
  *   from +0.0 (j ascending, even element first); lanes combine with an xor butterfly (16,8,4,2,1);
- *   the 8 warp sums are added left to right -> partial[c]. Final stage: 1024 "threads", thread t
- *   sums partial[t], partial[t+1024], ... sequentially from +0.0; butterfly inside each warp; the
- *   32 warp sums are butterflied again. Out-of-range elements contribute +0.0.
+ *   the 8 warp sums are added left to right -> partial[c]. Final stage: one CTA of 256 threads,
+ *   thread t sums partial[t], partial[t+256], ... sequentially from +0.0; butterfly inside each
+ *   warp; the 8 warp sums are added left to right. Out-of-range elements contribute +0.0.
  * ---------------------------------------------------------------------------------------------- */
 static void butterfly32(double v[32]) {
   for (int m = 16; m >= 1; m >>= 1) {
@@ -229,21 +229,23 @@ static double tree_dot(int64_t n, const double* a, const double* b) {
     for (int w = 1; w < 8; ++w) s = s + ws[w];
     partial[c] = s;
   }
-  double wsum[32];
-  for (int w = 0; w < 32; ++w) {
+  /* final stage: one 256-thread CTA */
+  double wsum[8];
+  for (int w = 0; w < 8; ++w) {
     double lane[32];
     for (int l = 0; l < 32; ++l) {
       const int t = w * 32 + l;
       double s = 0.0;
-      for (int64_t q = t; q < n_tiles; q += 1024) s = s + partial[q];
+      for (int64_t q = t; q < n_tiles; q += 256) s = s + partial[q];
       lane[l] = s;
     }
     butterfly32(lane);
     wsum[w] = lane[0];
   }
-  butterfly32(wsum);
+  double total = wsum[0];
+  for (int w = 1; w < 8; ++w) total = total + wsum[w];
   free(partial);
-  return wsum[0];
+  return total;
 }
 
 double orc_dot(int64_t n, const double* a, const double* b, int mode) {

