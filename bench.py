@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- Krylov iterations/s and HBM roofline fraction of the StormRuler hot path on B200.
+
+Metric (BASELINE.json): Krylov iterations/s & HBM GB/s (% of roofline) at 10 M cells.
+Workload at N=1 (BASELINE.json configs[1]): BiCGStab on a 3-D FVM Poisson
+problem, synthetic jittered tetrahedral box mesh (119^3 hexes x 6 Kuhn tets = 10 110 954 cells),
+homogeneous-Dirichlet mirror ghosts, cells shuffled then RCM-renumbered, fp64.
+A "step" is one BiCGStab iteration = 2 operator applies + 5 fused reductions + 5 vector updates.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--solver cg|bicgstab]
+                    [--n N_PER_AXIS] [--cell tet|hex]
+
+Own arm: W untimed iterations, then exactly K iterations timed with CUDA events on the solver's
+stream (tolerances disabled so the count is fixed; the per-iteration working set of ~1.2 GB is far
+larger than the 126 MB L2, so no flush is needed between iterations). Prints ONE JSON line.
+`--impl reference` times the reference's own CPU solver (oracle/_ref: the unmodified StormRuler
+headers; falls back to the oracle's C port) on the same mesh and right-hand side on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def build_problem(args):
+    """Mesh (host) + exact solution + names. Shared by both arms so they see the same arrays."""
+    from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh
+    t0 = time.time()
+    kind = CELL_TET if args.cell == "tet" else CELL_HEX
+    mesh = Mesh.box(kind, args.n, jitter=0.2, seed_jitter=42, shuffle=True, seed_shuffle=43)
+    t1 = time.time()
+    bw0 = mesh.bandwidth
+    mesh.renumber_rcm()
+    t2 = time.time()
+    log(f"[bench] mesh: {mesh.n_cells} {args.cell} cells, {mesh.n_faces} interior faces, {mesh.n_bfaces} boundary "
+        f"faces; generate {t1 - t0:.1f}s, RCM {t2 - t1:.1f}s (bandwidth {bw0} -> {mesh.bandwidth})")
+    c = mesh.cell_centers()
+    x_star = np.sin(np.pi * c[:, 0]) * np.sin(np.pi * c[:, 1]) * np.sin(np.pi * c[:, 2])
+    return mesh, x_star
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, reasons, sm_max = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                sm_max = float(r[1])
+                for k, nm in enumerate(names):
+                    if r[4 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        busy = [v for v in sm if sm_max and v > 0.3 * sm_max] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": sm_max,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_rate(mesh, x_star, solver, budget_s=20.0, max_iters=None):
+    """Reference CPU solver on the same SoA arrays and right-hand side, 1 core (the reference is
+    single-threaded by construction). Returns (it/s, kind, iterations run, seconds)."""
+    from oracle import orc
+    fm = orc.FaceMesh(mesh.n_cells, mesh.face_cell, mesh.face_area, mesh.face_dist, mesh.cell_vol,
+                      mesh.bface_cell, mesh.bface_area, mesh.bface_dist)
+    op = orc.FaceOp(fm, prefill=0, dt=-1.0, dirichlet=True)
+    b = op.apply(x_star)
+    kind = "reference" if orc.have_ref() else "port"
+
+    def run(iters):
+        t = time.perf_counter()
+        if kind == "reference":
+            r = orc.ref_solve(solver, op, b, num_iterations=iters, abs_tol=0.0, rel_tol=0.0, trace_cap=16)
+        else:
+            r = orc.solve(solver, op, b, num_iterations=iters, abs_tol=0.0, rel_tol=0.0)
+        assert r.iterations == iters
+        return time.perf_counter() - t
+
+    t1 = run(1)                       # init + 1 iteration: calibrates the budget
+    per_it = max(t1 / 2.0, 1e-6)
+    iters = int(max(2, min(budget_s / per_it, 2000)))
+    if max_iters is not None:
+        iters = max(2, min(iters, max_iters))
+    t_n = run(iters)
+    rate = (iters - 1) / max(t_n - t1, 1e-9)   # subtract the initialisation (residual + first iteration)
+    return rate, kind, iters, t_n
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mesh, x_star = build_problem(args)
+    t0 = time.perf_counter()
+    from oracle import orc
+    fm = orc.FaceMesh(mesh.n_cells, mesh.face_cell, mesh.face_area, mesh.face_dist, mesh.cell_vol,
+                      mesh.bface_cell, mesh.bface_area, mesh.bface_dist)
+    op = orc.FaceOp(fm, prefill=0, dt=-1.0, dirichlet=True)
+    b = op.apply(x_star)
+    kind = "reference" if orc.have_ref() else "port"
+    solve = (lambda it: orc.ref_solve(args.solver, op, b, num_iterations=it, abs_tol=0.0, rel_tol=0.0, trace_cap=16)) \
+        if kind == "reference" else (lambda it: orc.solve(args.solver, op, b, num_iterations=it, abs_tol=0.0, rel_tol=0.0))
+    # warm-up iterations are part of the same solve: time W+K and W iterations and subtract
+    tw0 = time.perf_counter(); solve(args.warmup); tw = time.perf_counter() - tw0
+    tk0 = time.perf_counter(); r = solve(args.warmup + args.steps); tk = time.perf_counter() - tk0
+    dt = max(tk - tw, 1e-9)
+    value = args.steps / dt
+    line = {
+        "impl": "reference", "metric": "krylov_iterations_per_sec", "value": value, "unit": "it/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, mesh),
+        "cpu_baseline": {"value": value, "unit": "it/s", "cores": 1, "kind": kind,
+                         "sample": f"{args.steps} {args.solver} iterations at full size (after {args.warmup} warm-up "
+                                   f"iterations), reference solver headers on a host vector + face-loop operator, "
+                                   f"g++ -O2 -ffp-contract=off, single thread (the reference has no threading)"},
+        "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "residual_after": r.abs_err, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, mesh):
+    return {"workload": f"{args.solver} on 3-D FVM Poisson (Dirichlet mirror ghosts), synthetic jittered "
+                        f"{'Kuhn-tetrahedral' if args.cell == 'tet' else 'hexahedral'} box mesh {args.n}^3, "
+                        f"RCM-renumbered",
+            "cells": int(mesh.n_cells), "interior_faces": int(mesh.n_faces), "boundary_faces": int(mesh.n_bfaces),
+            "solver": args.solver, "operator_form": "coef (12 B/entry ELL + diagonal)",
+            "l2_policy": "inputs_larger_than_L2 (per-iteration working set >> 126 MB)"}
+
+
+def run_own_arm(args):
+    import stormruler_b200 as sb
+    from stormruler_b200 import capi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from stormruler_b200 import multigpu
+        return multigpu.bench_main(args, build_problem, workload_config, peaks, ClockSampler)
+    mesh, x_star = build_problem(args)
+    ctx = sb.Context(local_rank)
+    t0 = time.time()
+    op = sb.FvmOperator(ctx, mesh, prefill=0, dt=-1.0, form=sb.FORM_COEF, dirichlet=True)
+    log(f"[bench] operator upload: {time.time() - t0:.1f}s, width {op.info.width}, "
+        f"{op.info.device_bytes / 1e6:.0f} MB in HBM, {op.info.algorithmic_bytes_per_apply / mesh.n_cells:.1f} B/cell/apply")
+    n = mesh.n_cells
+    xs = ctx.vector(x_star)
+    b = ctx.zeros(n)
+    op.mul(b, xs)                                   # b = A x*
+    Solver = sb.BiCgStabSolver if args.solver == "bicgstab" else sb.CgSolver
+    applies_per_it, passes_per_it = (2, 15) if args.solver == "bicgstab" else (1, 9)
+
+    def solve(iters, **kw):
+        s = Solver(num_iterations=iters, absolute_error_tolerance=0.0, relative_error_tolerance=0.0,
+                   record=False, **kw)
+        x = ctx.zeros(n)
+        s.solve(x, b, op)
+        assert s.iteration == iters, (s.iteration, iters)
+        return s, x
+
+    sampler = ClockSampler(local_rank).start()
+    solve(max(args.warmup, 3), use_graph=True)                       # warm-up (untimed)
+    launches0 = ctx.launch_count
+    s, x = solve(args.steps, use_graph=True)                         # timed: exactly K iterations
+    gpu_launches = s.launches
+    rep_ms = _iter_ms(s)
+    value = args.steps / (rep_ms * 1e-3)
+    # per-kernel breakdown of the same K iterations (events around every launch, no graph)
+    sp, _ = solve(args.steps, profile=True)
+    clocks = sampler.stop()
+    kms = _kernel_ms(sp)
+    err = np.linalg.norm(x.numpy() - x_star) / np.linalg.norm(x_star)
+
+    # ---- roofline of the dominant kernel: the operator apply ----
+    peak, peak_src = peaks()
+    alg_apply = op.info.algorithmic_bytes_per_apply
+    slots = {"bicgstab": ["direction", "apply+dot", "half_update", "apply+2dots", "final_update+2dots"],
+             "cg": ["apply+dot", "update+dot", "direction"]}[args.solver]
+    apply_slots = [k for k, nm in enumerate(slots) if nm.startswith("apply")]
+    apply_ms = sum(kms[k] for k in apply_slots) / (len(apply_slots) * args.steps)   # avg per launch
+    achieved = alg_apply / (apply_ms * 1e-3) / 1e9
+    alg_iter = applies_per_it * alg_apply + passes_per_it * 8 * n
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "apply_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- e2e: the reference-facing C-ABI call with HOST buffers (copies inside the timed region) ----
+    import torch
+    hx = torch.zeros(n, dtype=torch.float64).pin_memory()
+    hb = torch.from_numpy(b.numpy()).pin_memory()
+    hxn, hbn = hx.numpy(), hb.numpy()
+    sb.solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=3, abs_tol=0.0, rel_tol=0.0, use_graph=True)
+    hxn[:] = 0.0
+    ctx.sync()
+    t = time.perf_counter()
+    rep = sb.solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=args.steps, abs_tol=0.0, rel_tol=0.0,
+                        use_graph=True)
+    e2e_s = time.perf_counter() - t
+    assert rep.iterations == args.steps
+    e2e_value = args.steps / e2e_s
+
+    # ---- CPU baseline beside it (bounded sample of the same workload) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        rate, kind, iters, secs = cpu_reference_rate(mesh, x_star, args.solver, budget_s=args.cpu_budget)
+        cpu = {"value": rate, "unit": "it/s", "cores": 1, "kind": kind,
+               "sample": f"{iters} {args.solver} iterations of the same {n}-cell problem ({secs:.1f} s), reference "
+                         f"solver headers + face-loop operator, g++ -O2 -ffp-contract=off, 1 thread "
+                         f"(the reference is single-threaded by construction)"}
+
+    line = {
+        "metric": "krylov_iterations_per_sec", "value": value, "unit": "it/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": rep_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, mesh),
+        "roofline": {"bound": "hbm", "kernel": "operator apply + fused dot(s) (sb::apply_kernel)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(alg_apply), "avg_launch_ms": apply_ms,
+                     "share_of_step": sum(kms[k] for k in apply_slots) / sum(kms[:len(slots)])},
+        "iteration_roofline": {"algorithmic_bytes_per_iteration": int(alg_iter),
+                               "achieved_gbs": alg_iter * value / 1e9, "frac_of_measured_peak": alg_iter * value / 1e9 / peak,
+                               "frac_of_nominal_8TBs": alg_iter * value / 8e12},
+        "kernel_ms_per_iteration": {nm: kms[k] / args.steps for k, nm in enumerate(slots)},
+        "applies_per_sec": applies_per_it * value,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": 16 * n / args.steps,
+                "d2h_bytes_per_step": 8 * n / args.steps,
+                "note": f"one sb_solve_host call = H2D(x0,b) + init + {args.steps} iterations + D2H(x), pinned host buffers"},
+        "gpu_launches": int(gpu_launches), "clocks": clocks,
+        "rel_error_vs_exact_after_steps": float(err), "residual_after_steps": float(s.absolute_error),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _iter_ms(s):
+    return float(s.iter_ms)
+
+
+def _kernel_ms(s):
+    return list(s.kernel_ms)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--solver", default="bicgstab", choices=["cg", "bicgstab"])
+    ap.add_argument("--n", type=int, default=119, help="hexes per axis (119 -> 10.1 M tets)")
+    ap.add_argument("--cell", default="tet", choices=["tet", "hex"])
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -201,7 +201,11 @@ typedef struct sb_solver_opts {
   double rel_tol;         /* Solver.hpp:72 (default 1e-6); <= 0 disables */
   int32_t check_every;    /* host polls the device convergence flag every this many iterations (0 = 32) */
   int32_t use_graph;      /* 1: replay one captured CUDA graph per iteration */
+  int32_t profile;        /* 1: bracket every kernel of the iteration with CUDA events (no graph) and
+                             report the accumulated time per kernel slot in sb_solver_report.kernel_ms */
 } sb_solver_opts;
+
+#define SB_MAX_KERNEL_SLOTS 8
 
 typedef struct sb_solver_report {
   int32_t converged;
@@ -211,8 +215,13 @@ typedef struct sb_solver_report {
   double rel_err;      /* IterativeSolver::relative_error */
   int64_t n_hist;      /* entries written to h_hist: [0] initial, [k] after iteration k */
   int64_t n_trace;     /* entries written to h_trace: every reduction result, reference call order */
-  double solve_ms;     /* device time of the solve (CUDA events) */
+  double solve_ms;     /* device time of the whole solve incl. initialisation (CUDA events) */
+  double iter_ms;      /* device time of the iteration loop only */
   int64_t launches;    /* kernels launched by this solve */
+  int32_t n_kernel_slots;               /* kernels per iteration (CG 3, BiCGStab 5) */
+  double kernel_ms[SB_MAX_KERNEL_SLOTS]; /* profile=1: total device time per kernel slot, in launch order
+                                            (CG: apply+dot, update+dot, direction; BiCGStab: direction,
+                                            apply+dot, half update, apply+2 dots, final update+2 dots) */
 } sb_solver_report;
 
 SB_API int sb_cg_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b,

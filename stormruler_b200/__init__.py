@@ -264,10 +264,13 @@ class _FusedSolver:
     relative_error: float = 0.0
     check_every: int = 0
     use_graph: bool = False
+    profile: bool = False
     record: bool = True
     history: np.ndarray = field(default_factory=lambda: np.zeros(0))
     trace: np.ndarray = field(default_factory=lambda: np.zeros(0))
     solve_ms: float = 0.0
+    iter_ms: float = 0.0
+    kernel_ms: tuple = ()
     launches: int = 0
     _entry = ""
     _trace_per_iter = 2
@@ -276,7 +279,7 @@ class _FusedSolver:
         lib = op.ctx.lib
         opts = capi.SolverOpts(int(self.num_iterations), float(self.absolute_error_tolerance),
                                float(self.relative_error_tolerance), int(self.check_every),
-                               int(bool(self.use_graph)))
+                               int(bool(self.use_graph)), int(bool(self.profile)))
         rep = capi.SolverReport()
         cap_h = self.num_iterations + 2 if self.record else 0
         cap_t = self._trace_per_iter * self.num_iterations + 8 if self.record else 0
@@ -288,7 +291,8 @@ class _FusedSolver:
         self.iteration = int(rep.iterations)
         self.absolute_error, self.relative_error = rep.abs_err, rep.rel_err
         self.history, self.trace = hist[:rep.n_hist].copy(), trace[:rep.n_trace].copy()
-        self.solve_ms, self.launches = rep.solve_ms, int(rep.launches)
+        self.solve_ms, self.iter_ms, self.launches = rep.solve_ms, rep.iter_ms, int(rep.launches)
+        self.kernel_ms = tuple(rep.kernel_ms[k] for k in range(rep.n_kernel_slots))
         return bool(rep.converged)
 
 
@@ -309,7 +313,7 @@ def solve_host(ctx: Context, op: FvmOperator, solver: str, x_host: np.ndarray, b
     """sb_solve_host: host buffers in/out, copies inside the call. x_host is updated in place."""
     assert x_host.dtype == np.float64 and x_host.flags.c_contiguous
     b_host = _f64(b_host)
-    opts = capi.SolverOpts(int(num_iterations), float(abs_tol), float(rel_tol), int(check_every), int(use_graph))
+    opts = capi.SolverOpts(int(num_iterations), float(abs_tol), float(rel_tol), int(check_every), int(use_graph), 0)
     rep = capi.SolverReport()
     capi.check(ctx.lib.sb_solve_host(ctx.handle, op.handle, solver.encode(), x_host.ctypes.data_as(capi.f64p),
                                      b_host.ctypes.data_as(capi.f64p), C.byref(opts), C.byref(rep), None, 0))

@@ -47,13 +47,14 @@ class Expr(C.Structure):
 
 class SolverOpts(C.Structure):
     _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
-                ("check_every", C.c_int32), ("use_graph", C.c_int32)]
+                ("check_every", C.c_int32), ("use_graph", C.c_int32), ("profile", C.c_int32)]
 
 
 class SolverReport(C.Structure):
     _fields_ = [("converged", C.c_int32), ("iterations", C.c_int64), ("initial_err", C.c_double),
                 ("abs_err", C.c_double), ("rel_err", C.c_double), ("n_hist", C.c_int64),
-                ("n_trace", C.c_int64), ("solve_ms", C.c_double), ("launches", C.c_int64)]
+                ("n_trace", C.c_int64), ("solve_ms", C.c_double), ("iter_ms", C.c_double),
+                ("launches", C.c_int64), ("n_kernel_slots", C.c_int32), ("kernel_ms", C.c_double * 8)]
 
 
 # name -> (restype, argtypes); the keys are exactly the SB_API symbols of include/stormb200.h

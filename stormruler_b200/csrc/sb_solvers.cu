@@ -315,6 +315,17 @@ struct Solve {
   Recorder rec;
   const int* done;
   double *p, *r, *z, *rt, *t, *v;
+  std::vector<cudaEvent_t>* prof = nullptr; // profile=1: one event before every kernel + one per iteration end
+
+  int mark() {
+    if (prof != nullptr) {
+      cudaEvent_t e;
+      SB_CUDA(cudaEventCreate(&e));
+      SB_CUDA(cudaEventRecord(e, ctx->stream));
+      prof->push_back(e);
+    }
+    return SB_OK;
+  }
 
   int init(Kind kind) {
     // r <- b - A x fused with <r,r>  (Operator::Residual, Operator.hpp:95-99)
@@ -332,16 +343,25 @@ struct Solve {
   int iterate(Kind kind) {
     const SolverState* st = rec.st;
     if (kind == Kind::Cg) {
+      SB_TRY(mark());
       SB_TRY((launch_apply<1, false>(ctx, op, p, z, EpiXY{}, CgAlphaFinal{rec}, done)));
+      SB_TRY(mark());
       SB_TRY((launch_ew<1>(ctx, n, CgUpdateBody{st, x, r, p, z}, CgBetaFinal{rec}, done)));
+      SB_TRY(mark());
       SB_TRY((launch_ew<0>(ctx, n, CgDirectionBody{st, p, r}, NoFinal{}, done)));
     } else {
+      SB_TRY(mark());
       SB_TRY((launch_ew<0>(ctx, n, BiDirectionBody{st, p, r, v}, NoFinal{}, done)));
+      SB_TRY(mark());
       SB_TRY((launch_apply<1, false>(ctx, op, p, v, EpiUY{rt}, BiAlphaFinal{rec}, done)));
+      SB_TRY(mark());
       SB_TRY((launch_ew<0>(ctx, n, BiHalfBody{st, r, v}, NoFinal{}, done)));
+      SB_TRY(mark());
       SB_TRY((launch_apply<2, false>(ctx, op, r, t, EpiYYandYX{}, BiOmegaFinal{rec}, done)));
+      SB_TRY(mark());
       SB_TRY((launch_ew<2>(ctx, n, BiEndBody{st, x, r, p, t, rt}, BiEndFinal{rec}, done)));
     }
+    SB_TRY(mark());
     return SB_OK;
   }
 };
@@ -381,6 +401,11 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   const int64_t launches0 = ctx->launches;
   SB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   SB_TRY(S.init(kind));
+  cudaEvent_t ev_mid;
+  SB_CUDA(cudaEventCreate(&ev_mid));
+  SB_CUDA(cudaEventRecord(ev_mid, ctx->stream));
+  std::vector<cudaEvent_t> prof_events;
+  const bool profile = opts->profile != 0 && !opts->use_graph;
 
   // One captured graph per iteration: the kernel arguments never change (scalars are read from the
   // device state), so the same graph is replayed; this removes the per-kernel launch cost that
@@ -419,6 +444,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
         SB_CUDA(cudaGraphLaunch(graph_exec, ctx->stream));
         ctx->launches += per_iter;
       } else {
+        if (profile) S.prof = &prof_events;
         SB_TRY(S.iterate(kind));
       }
     }
@@ -440,8 +466,24 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   cudaEventDestroy(evs[1]);
   if (graph_exec != nullptr) cudaGraphExecDestroy(graph_exec);
   const SolverState out = *pinned_state;
-  float ms = 0.f;
+  float ms = 0.f, ms_iter = 0.f;
   SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  SB_CUDA(cudaEventElapsedTime(&ms_iter, ev_mid, ctx->ev1));
+  cudaEventDestroy(ev_mid);
+  report->iter_ms = ms_iter;
+  report->n_kernel_slots = per_iter;
+  for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->kernel_ms[k] = 0.0;
+  if (profile) {
+    // events come in groups of per_iter + 1 per iteration
+    const size_t group = (size_t) per_iter + 1;
+    for (size_t g = 0; g + group <= prof_events.size(); g += group)
+      for (int k = 0; k < per_iter; ++k) {
+        float dt = 0.f;
+        cudaEventElapsedTime(&dt, prof_events[g + k], prof_events[g + k + 1]);
+        report->kernel_ms[k] += dt;
+      }
+    for (cudaEvent_t e : prof_events) cudaEventDestroy(e);
+  }
   report->converged = out.converged;
   report->iterations = out.iteration;
   report->initial_err = out.initial_err;

@@ -1,0 +1,82 @@
+"""Host-side mesh handle (sb_mesh): synthetic box meshes, cell-soup ingestion, RCM renumbering.
+Pure host code in libstormb200.so -- works without a GPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+CELL_TET, CELL_HEX = 0, 1
+
+
+class Mesh:
+    def __init__(self, handle):
+        self.lib = capi.load()
+        self.handle = handle
+        self._refresh()
+
+    # -- constructors -----------------------------------------------------------------------------
+    @staticmethod
+    def box(kind: int, nx: int, ny: int | None = None, nz: int | None = None, jitter: float = 0.2,
+            seed_jitter: int = 42, shuffle: bool = True, seed_shuffle: int = 43) -> "Mesh":
+        """SURVEY.md 8d config 2/4 geometry: [0,1]^3, nx*ny*nz hexes (x6 Kuhn tets for CELL_TET)."""
+        lib = capi.load()
+        h = C.c_void_p()
+        ny, nz = ny or nx, nz or nx
+        capi.check(lib.sb_mesh_generate_box(kind, nx, ny, nz, jitter, seed_jitter, int(shuffle), seed_shuffle,
+                                            C.byref(h)))
+        return Mesh(h)
+
+    @staticmethod
+    def from_cells(kind: int, xyz: np.ndarray, cells: np.ndarray) -> "Mesh":
+        lib = capi.load()
+        xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+        cells = np.ascontiguousarray(cells, np.int32)
+        h = C.c_void_p()
+        capi.check(lib.sb_mesh_from_cells(kind, xyz.shape[0], xyz.ctypes.data_as(capi.f64p), cells.shape[0],
+                                          cells.ctypes.data_as(capi.i32p), C.byref(h)))
+        return Mesh(h)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.sb_mesh_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # -- views (zero-copy numpy views of the library-owned SoA) -----------------------------------
+    def _refresh(self):
+        soa = capi.MeshSoa()
+        capi.check(self.lib.sb_mesh_get_soa(self.handle, C.byref(soa)))
+        self.soa = soa
+        self.n_cells, self.n_faces, self.n_bfaces = int(soa.n_cells), int(soa.n_faces), int(soa.n_bfaces)
+        view = lambda p, n: np.ctypeslib.as_array(p, shape=(n,)) if n > 0 else np.zeros(0)  # noqa: E731
+        self.face_cell = view(soa.face_cell, 2 * self.n_faces).reshape(-1, 2) if self.n_faces else np.zeros((0, 2), np.int32)
+        self.face_area, self.face_dist = view(soa.face_area, self.n_faces), view(soa.face_dist, self.n_faces)
+        self.cell_vol = view(soa.cell_vol, self.n_cells)
+        self.bface_cell = view(soa.bface_cell, self.n_bfaces) if self.n_bfaces else np.zeros(0, np.int32)
+        self.bface_area, self.bface_dist = view(soa.bface_area, self.n_bfaces), view(soa.bface_dist, self.n_bfaces)
+
+    def renumber_rcm(self) -> np.ndarray:
+        """Reverse Cuthill-McKee; returns perm with perm[new] = old."""
+        perm = np.empty(self.n_cells, np.int32)
+        capi.check(self.lib.sb_mesh_renumber_rcm(self.handle, perm.ctypes.data_as(capi.i32p)))
+        self._refresh()
+        return perm
+
+    def permute_cells(self, perm: np.ndarray):
+        perm = np.ascontiguousarray(perm, np.int32)
+        capi.check(self.lib.sb_mesh_permute_cells(self.handle, perm.ctypes.data_as(capi.i32p)))
+        self._refresh()
+
+    def cell_centers(self) -> np.ndarray:
+        out = np.empty((self.n_cells, 3))
+        capi.check(self.lib.sb_mesh_cell_centers(self.handle, out.ctypes.data_as(capi.f64p)))
+        return out
+
+    @property
+    def bandwidth(self) -> int:
+        return int(self.lib.sb_mesh_bandwidth(self.handle))
