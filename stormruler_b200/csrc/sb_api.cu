@@ -28,7 +28,7 @@ int ensure_red_scratch(sb_ctx* ctx, int64_t n) {
   return SB_OK;
 }
 
-static RedPtrs red_ptrs(const sb_ctx* ctx) { return RedPtrs{ctx->red.partials, ctx->red.cap_tiles, ctx->red.ticket}; }
+static RedPtrs red_ptrs(const sb_ctx* ctx) { return RedPtrs{ctx->red.partials, ctx->red.cap_tiles}; }
 
 } // namespace sb
 
@@ -50,8 +50,6 @@ int sb_ctx_create(int device, sb_ctx** out) {
   ctx->device = device;
   SB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   SB_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
-  SB_CUDA(cudaMalloc(&ctx->red.ticket, sizeof(unsigned int)));
-  SB_CUDA(cudaMemsetAsync(ctx->red.ticket, 0, sizeof(unsigned int), ctx->stream));
   SB_CUDA(cudaMalloc(&ctx->red.result, sizeof(double) * 64));
   ctx->pinned_doubles = 4096;
   SB_CUDA(cudaMallocHost(&ctx->h_pinned, sizeof(double) * ctx->pinned_doubles));
@@ -72,7 +70,6 @@ int sb_ctx_destroy(sb_ctx* ctx) {
   cudaFree(ctx->d_hist);
   cudaFree(ctx->d_trace);
   cudaFree(ctx->red.partials);
-  cudaFree(ctx->red.ticket);
   cudaFree(ctx->red.result);
   cudaFreeHost(ctx->h_pinned);
   cudaEventDestroy(ctx->ev0);
@@ -138,8 +135,7 @@ int launch_eval(sb_ctx* ctx, double* y, size_t n, const sb_expr* e, const Prog& 
   for (int k = 0; k < SB_EXPR_MAX_SCAL; ++k) body.sc[k] = e->scal[k];
   body.prog = prog;
   const unsigned grid = (unsigned) num_tiles((int64_t) n);
-  ew_kernel<0, EvalBody<NV, AOP, Prog>, NoFinal>
-      <<<grid, kThreads, 0, ctx->stream>>>((int64_t) n, body, RedPtrs{}, NoFinal{}, nullptr);
+  ew_kernel<0, EvalBody<NV, AOP, Prog>><<<grid, kThreads, 0, ctx->stream>>>((int64_t) n, body, RedPtrs{}, nullptr);
   ctx->launches++;
   SB_CUDA(cudaGetLastError());
   return SB_OK;
@@ -253,8 +249,8 @@ int sb_fill(sb_ctx* ctx, double* y, size_t n, double value) {
   SB_REQUIRE(ctx != nullptr && y != nullptr, "null argument");
   if (n == 0) return SB_OK;
   FillBody body{y, value};
-  ew_kernel<0, FillBody, NoFinal><<<(unsigned) num_tiles((int64_t) n), kThreads, 0, ctx->stream>>>(
-      (int64_t) n, body, RedPtrs{}, NoFinal{}, nullptr);
+  ew_kernel<0, FillBody><<<(unsigned) num_tiles((int64_t) n), kThreads, 0, ctx->stream>>>((int64_t) n, body, RedPtrs{},
+                                                                                     nullptr);
   ctx->launches++;
   SB_CUDA(cudaGetLastError());
   return SB_OK;
@@ -276,11 +272,11 @@ int launch_dots(sb_ctx* ctx, const double* const* a, const double* const* b, siz
   DotBody<M> body;
   for (int k = 0; k < M; ++k) body.a[k] = a[k], body.b[k] = b[k];
   SB_TRY(ensure_red_scratch(ctx, (int64_t) n));
-  ew_kernel<M, DotBody<M>, StoreFinal<M>><<<(unsigned) num_tiles((int64_t) n), kThreads, 0, ctx->stream>>>(
-      (int64_t) n, body, red_ptrs(ctx), StoreFinal<M>{d_out}, nullptr);
+  ew_kernel<M, DotBody<M>><<<(unsigned) num_tiles((int64_t) n), kThreads, 0, ctx->stream>>>((int64_t) n, body,
+                                                                                          red_ptrs(ctx), nullptr);
   ctx->launches++;
   SB_CUDA(cudaGetLastError());
-  return SB_OK;
+  return launch_final<M>(ctx, (int64_t) n, StoreFinal<M>{d_out}, nullptr);
 }
 } // namespace
 

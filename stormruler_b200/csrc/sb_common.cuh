@@ -53,13 +53,11 @@ void set_error(const char* fmt, ...);
     if (_rc != SB_OK) return _rc; \
   } while (0)
 
-// Device-resident reduction scratch: per-tile partial sums, a ticket counter for the
-// "last CTA finishes" pattern and the output slots.
+// Device-resident reduction scratch: per-tile partial sums and the output slots.
 struct RedScratch {
   double* partials = nullptr; // [kMaxDots][cap_tiles]
   int64_t cap_tiles = 0;
-  unsigned int* ticket = nullptr; // zero between launches (the last CTA resets it)
-  double* result = nullptr;       // [64] result slots of the stand-alone dots
+  double* result = nullptr;   // [64] result slots of the stand-alone dots
 };
 
 } // namespace sb

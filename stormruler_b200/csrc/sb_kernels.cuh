@@ -18,7 +18,6 @@ namespace sb {
 struct RedPtrs {
   double* partials;      // [kMaxDots][cap_tiles]
   int64_t cap_tiles;
-  unsigned int* ticket;
 };
 
 __device__ __forceinline__ double2 ld2(const double* p, int64_t e) {
@@ -41,12 +40,15 @@ __device__ __forceinline__ int64_t lane_elem(int j) {
   return (int64_t) blockIdx.x * kTile + warp * (kTile / kWarps) + j * 64 + 2 * lane;
 }
 
-// CTA-level combine + "last CTA reduces the partials" (SB_TREE v1). `fin(sums)` runs on one thread
-// of the last CTA after all ND totals are known; it is where solver scalars are updated.
-template<int ND, class Final>
-__device__ __forceinline__ void block_reduce_finalize(double (&acc)[ND], const RedPtrs& red, Final& fin) {
+// CTA-level combine of SB_TREE v1: warp butterflies, then the 8 warp sums are added left to right and
+// stored as partial[tile]. No fence, no atomics: the totals are produced by final_reduce_kernel, a
+// one-CTA launch that follows in stream order. (An earlier version let the last CTA finish the
+// reduction behind a __threadfence + ticket atomic; ncu/CUDA-event timing showed that the fence, which
+// must wait for the CTA's outstanding y stores, stretched every CTA's lifetime and cost ~25 us per
+// reducing kernel at 10 M cells, against ~2 us for the extra launch.)
+template<int ND>
+__device__ __forceinline__ void block_reduce_partials(double (&acc)[ND], const RedPtrs& red) {
   __shared__ double s_w[ND][kWarps];
-  __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int d = 0; d < ND; ++d) {
@@ -60,23 +62,46 @@ __device__ __forceinline__ void block_reduce_finalize(double (&acc)[ND], const R
 #pragma unroll
     for (int w = 1; w < kWarps; ++w) s = __dadd_rn(s, s_w[d][w]);
     red.partials[(int64_t) d * red.cap_tiles + blockIdx.x] = s;
-    __threadfence();
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(red.ticket, 1u);
-    s_last = (t == gridDim.x - 1);
+}
+
+// Final stage of SB_TREE v1: one CTA of 256 threads. Thread t adds partial[t], partial[t+256], ...
+// in that order (loads of a batch are independent and issued together; only the additions are
+// sequential), butterfly per warp, the 8 warp sums added left to right. `fin(sums)` then runs on one
+// thread: that is where the solver scalars (alpha, beta, residual, stop flag) are updated.
+template<int ND, class Final>
+__global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles, RedPtrs red, Final fin,
+                                                                const int* __restrict__ done) {
+  if (done != nullptr && *done != 0) return;
+  __shared__ double s_w[ND][kWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kBatch = 8;
+  double s[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) s[d] = 0.0;
+  for (int64_t q0 = threadIdx.x; q0 < n_tiles; q0 += (int64_t) kBatch * kThreads) {
+    double v[ND][kBatch];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const double* part = red.partials + (int64_t) d * red.cap_tiles;
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int64_t q = q0 + (int64_t) b * kThreads;
+        v[d][b] = (q < n_tiles) ? __ldcg(part + q) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int64_t q = q0 + (int64_t) b * kThreads;
+        s[d] = (q < n_tiles) ? __dadd_rn(s[d], v[d][b]) : s[d];
+      }
+    }
   }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int64_t n_tiles = gridDim.x;
 #pragma unroll
   for (int d = 0; d < ND; ++d) {
-    const double* part = red.partials + (int64_t) d * red.cap_tiles;
-    double s = 0.0;
-    for (int64_t q = threadIdx.x; q < n_tiles; q += kThreads) s = __dadd_rn(s, __ldcg(part + q));
-    const double v = warp_butterfly(s);
+    const double v = warp_butterfly(s[d]);
     if (lane == 0) s_w[d][warp] = v;
   }
   __syncthreads();
@@ -84,14 +109,23 @@ __device__ __forceinline__ void block_reduce_finalize(double (&acc)[ND], const R
     double sums[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
-      double s = s_w[d][0];
+      double t = s_w[d][0];
 #pragma unroll
-      for (int w = 1; w < kWarps; ++w) s = __dadd_rn(s, s_w[d][w]);
-      sums[d] = s;
+      for (int w = 1; w < kWarps; ++w) t = __dadd_rn(t, s_w[d][w]);
+      sums[d] = t;
     }
-    *red.ticket = 0u;
     fin(sums);
   }
+}
+
+// Launch helper shared by all reducing kernels: the one-CTA final stage, right behind the producer.
+template<int ND, class Final>
+inline int launch_final(sb_ctx* ctx, int64_t n, const Final& fin, const int* done) {
+  const RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
+  final_reduce_kernel<ND, Final><<<1, kThreads, 0, ctx->stream>>>(num_tiles(n), red, fin, done);
+  ctx->launches++;
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
 }
 
 struct NoFinal {
@@ -102,8 +136,8 @@ struct NoFinal {
 //   struct Regs; void load(int64_t e0, Regs&) const; void run(int64_t e0, int64_t n, Regs&, double (&acc)[max(ND,1)]) const;
 // `done` (may be null) is the solver's device-side stop flag: once set, later launches are no-ops, so
 // the iterate stays exactly what the reference returns at that iteration (DESIGN.md "stopping").
-template<int ND, class Body, class Final>
-__global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, Body body, RedPtrs red, Final fin,
+template<int ND, class Body>
+__global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, Body body, RedPtrs red,
                                                       const int* __restrict__ done) {
   if (done != nullptr && *done != 0) return;
   typename Body::Regs r[kSub];
@@ -114,7 +148,7 @@ __global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, Body body, RedP
   for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
 #pragma unroll
   for (int j = 0; j < kSub; ++j) body.run(lane_elem(j), n, r[j], acc);
-  if constexpr (ND > 0) block_reduce_finalize<ND>(acc, red, fin);
+  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red);
 }
 
 // masked accumulation: out-of-range elements contribute +0.0 (SB_TREE v1)

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <memory>
+#include <thread>
 
 using namespace sb;
 
@@ -108,11 +109,37 @@ int sb_op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, sb_o
   op->d.n = m->n_cells, op->d.ld = R.ld, op->d.width = R.width, op->d.form = desc->form;
   op->d.prefill = desc->prefill, op->d.dt = desc->dt;
   op->n_entries = R.entries;
+  if (const char* dbg = std::getenv("SB_DEBUG")) op->d.debug = std::atoi(dbg);
   SB_CUDA(cudaSetDevice(ctx->device));
-  SB_TRY(upload(ctx, R.col, &op->buffers[0], op->device_bytes));
-  SB_TRY(upload(ctx, R.v0, &op->buffers[1], op->device_bytes));
-  SB_TRY(upload(ctx, R.v1, &op->buffers[2], op->device_bytes));
-  SB_TRY(upload(ctx, R.diag, &op->buffers[3], op->device_bytes));
+  std::vector<unsigned char> blk;
+  if (desc->form == SB_FORM_COEF && !apply_v1_forced()) {
+    // blocked layout: slice record = [col[W][64] | coef[W][64] | diag[64]]
+    const int W = R.width;
+    const int64_t slice_bytes = 768 * (int64_t) W + 512, n_slices = R.ld / 64;
+    blk.resize((size_t) (slice_bytes * n_slices));
+    auto pack = [&](int64_t lo, int64_t hi) {
+      for (int64_t sl = lo; sl < hi; ++sl) {
+        unsigned char* rec = blk.data() + sl * slice_bytes;
+        for (int k = 0; k < W; ++k) {
+          std::memcpy(rec + k * 256, &R.col[(size_t) k * R.ld + sl * 64], 256);
+          std::memcpy(rec + W * 256 + k * 512, &R.v0[(size_t) k * R.ld + sl * 64], 512);
+        }
+        std::memcpy(rec + W * 768, &R.diag[(size_t) sl * 64], 512);
+      }
+    };
+    const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t) th.emplace_back(pack, n_slices * t / T, n_slices * (t + 1) / T);
+    for (auto& x : th) x.join();
+    SB_TRY(upload(ctx, blk, &op->buffers[4], op->device_bytes));
+    op->d.blk = (const unsigned char*) op->buffers[4];
+    op->d.slice_bytes = (int32_t) slice_bytes;
+  } else {
+    SB_TRY(upload(ctx, R.col, &op->buffers[0], op->device_bytes));
+    SB_TRY(upload(ctx, R.v0, &op->buffers[1], op->device_bytes));
+    SB_TRY(upload(ctx, R.v1, &op->buffers[2], op->device_bytes));
+    SB_TRY(upload(ctx, R.diag, &op->buffers[3], op->device_bytes));
+  }
   SB_CUDA(cudaStreamSynchronize(ctx->stream));
   op->d.col = (const int32_t*) op->buffers[0];
   op->d.v0 = (const double*) op->buffers[1];
@@ -148,6 +175,23 @@ int sb_op_download_rows(sb_ctx* ctx, const sb_op* op, int32_t* h_col, double* h_
                         double* h_diag) {
   SB_REQUIRE(ctx != nullptr && op != nullptr, "null argument");
   const size_t wl = (size_t) op->d.width * (size_t) op->d.ld;
+  if (op->d.blk != nullptr) {
+    // blocked layout: fetch the records and unpack them into the canonical [W][ld] arrays
+    const int W = op->d.width;
+    const int64_t sb_ = op->d.slice_bytes, n_slices = op->d.ld / 64, ld = op->d.ld;
+    std::vector<unsigned char> blk((size_t) (sb_ * n_slices));
+    SB_CUDA(cudaMemcpyAsync(blk.data(), op->d.blk, blk.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t sl = 0; sl < n_slices; ++sl) {
+      const unsigned char* rec = blk.data() + sl * sb_;
+      for (int k = 0; k < W; ++k) {
+        if (h_col) std::memcpy(h_col + (size_t) k * ld + sl * 64, rec + k * 256, 256);
+        if (h_val0) std::memcpy(h_val0 + (size_t) k * ld + sl * 64, rec + W * 256 + k * 512, 512);
+      }
+      if (h_diag) std::memcpy(h_diag + sl * 64, rec + W * 768, 512);
+    }
+    return SB_OK;
+  }
   if (h_col) SB_CUDA(cudaMemcpyAsync(h_col, op->d.col, sizeof(int32_t) * wl, cudaMemcpyDeviceToHost, ctx->stream));
   if (h_val0) SB_CUDA(cudaMemcpyAsync(h_val0, op->d.v0, sizeof(double) * wl, cudaMemcpyDeviceToHost, ctx->stream));
   if (h_val1 && op->d.v1)

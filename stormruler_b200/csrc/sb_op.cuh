@@ -17,6 +17,8 @@
 
 #include "sb_kernels.cuh"
 
+#include <cstdlib>
+
 namespace sb {
 
 struct OpDev {
@@ -27,11 +29,19 @@ struct OpDev {
   const double* v0 = nullptr;
   const double* v1 = nullptr;
   const double* diag = nullptr;
+  // coef form, blocked layout ("SELL-64"): one record per 64-row slice,
+  //   [ col[W][64] int32 | coef[W][64] fp64 | diag[64] fp64 ]  = 768*W + 512 bytes, contiguous,
+  // so a warp stage is ONE bulk copy and the whole operator is a single sequential HBM stream.
+  const unsigned char* blk = nullptr;
+  int32_t slice_bytes = 0;
+  int32_t debug = 0; // experiments only (SB_DEBUG env): bit0 = skip the gathers
 };
 
 // Epilogues fuse dot products into the apply: they see the input pair x[e0..e0+1] and the freshly
 // computed output pair, so <x,Ax>-style reductions cost no extra vector pass.
 struct NoEpi {
+  static constexpr bool kExtra = false;
+  __device__ __forceinline__ const double* extra() const { return nullptr; }
   struct Regs {};
   __device__ __forceinline__ void load(int64_t, Regs&) const {}
   __device__ __forceinline__ void run(int64_t, int64_t, double2, double2, Regs&, double (&)[1]) const {}
@@ -39,6 +49,8 @@ struct NoEpi {
 
 // acc[0] += x.y
 struct EpiXY {
+  static constexpr bool kExtra = false;
+  __device__ __forceinline__ const double* extra() const { return nullptr; }
   struct Regs {};
   __device__ __forceinline__ void load(int64_t, Regs&) const {}
   __device__ __forceinline__ void run(int64_t e0, int64_t n, double2 x, double2 y, Regs&, double (&acc)[1]) const {
@@ -49,10 +61,13 @@ struct EpiXY {
 // acc[0] += u.y  (u: a third vector, e.g. r~ in BiCGStab)
 struct EpiUY {
   const double* u;
+  static constexpr bool kExtra = true;
+  __device__ __forceinline__ const double* extra() const { return u; }
   struct Regs {
     double2 u;
   };
   __device__ __forceinline__ void load(int64_t e0, Regs& r) const { r.u = ld2(u, e0); }
+  __device__ __forceinline__ void from_stage(Regs& r, double2 v) const { r.u = v; }
   __device__ __forceinline__ void run(int64_t e0, int64_t n, double2, double2 y, Regs& r, double (&acc)[1]) const {
     acc_pair(acc[0], e0, n, __dmul_rn(r.u.x, y.x), __dmul_rn(r.u.y, y.y));
   }
@@ -60,6 +75,8 @@ struct EpiUY {
 
 // acc[0] += y.y ; acc[1] += y.x   (BiCGStab: <t,t>, <t,r>)
 struct EpiYYandYX {
+  static constexpr bool kExtra = false;
+  __device__ __forceinline__ const double* extra() const { return nullptr; }
   struct Regs {};
   __device__ __forceinline__ void load(int64_t, Regs&) const {}
   __device__ __forceinline__ void run(int64_t e0, int64_t n, double2 x, double2 y, Regs&, double (&acc)[2]) const {
@@ -72,10 +89,13 @@ struct EpiYYandYX {
 // The kernel stores the value returned through `out`.
 struct EpiResidual {
   const double* b;
+  static constexpr bool kExtra = true;
+  __device__ __forceinline__ const double* extra() const { return b; }
   struct Regs {
     double2 b;
   };
   __device__ __forceinline__ void load(int64_t e0, Regs& r) const { r.b = ld2(b, e0); }
+  __device__ __forceinline__ void from_stage(Regs& r, double2 v) const { r.b = v; }
 };
 
 template<int FORM, int W>
@@ -134,10 +154,9 @@ __device__ __forceinline__ double2 apply_rows(const OpDev& op, const double* __r
 }
 
 // y <- A x with a fused reduction epilogue. RESID: store b - A x instead (and reduce <r,r>).
-template<int FORM, int W, int ND, bool RESID, class Epi, class Final>
+template<int FORM, int W, int ND, bool RESID, class Epi>
 __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double* __restrict__ x, double* __restrict__ y,
-                                                         Epi epi, RedPtrs red, Final fin,
-                                                         const int* __restrict__ done) {
+                                                         Epi epi, RedPtrs red, const int* __restrict__ done) {
   if (done != nullptr && *done != 0) return;
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
@@ -157,7 +176,150 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double*
     st2(y, e0, out);
     if constexpr (!RESID) epi.run(e0, op.n, xo, out, er, acc);
   }
-  if constexpr (ND > 0) block_reduce_finalize<ND>(acc, red, fin);
+  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red);
+}
+
+
+// ---- apply kernel v2: warp-private TMA (bulk-copy) staging of the streamed operands ----------------
+// ncu on v1 (profiles/r01_apply_v1_ncu_details.txt): DRAM traffic equals the algorithmic bytes but only
+// ~60 % of peak bandwidth is reached; warps sit on long-scoreboard stalls because the column indices
+// must arrive before the dependent gathers can even be issued. Here the streamed operands of a warp's
+// 64-row stage (W index slices, W coefficient slices, diagonal, own x, optional epilogue vector: all
+// contiguous runs) are fetched by cp.async.bulk into a per-warp shared-memory ring, completion tracked
+// by a per-warp mbarrier. The operator itself is stored blocked (one contiguous record per 64-row
+// slice, see OpDev::blk), so a stage is 2-3 bulk copies issued by one elected lane and the kernel
+// reads 3-4 sequential HBM streams instead of 12 (measured: more concurrent streams = lower DRAM
+// efficiency). No registers are held by loads in flight, so two stages per warp and three
+// CTAs per SM keep ~200 KB in flight per SM, and the L1 is left entirely to the gathered x.
+// The row->lane mapping, operation order and reduction tree are identical to v1 (bit-identical output).
+constexpr int kStages = 2;
+
+template<int W, bool EXTRA>
+struct StageLayout {
+  static constexpr int col = 0;              // W slices of 64 int32   } one slice record of the
+  static constexpr int coef = W * 256;       // W slices of 64 fp64    } blocked operator layout,
+  static constexpr int diag = coef + W * 512; //                        } fetched by ONE bulk copy
+  static constexpr int slice = diag + 512;
+  static constexpr int xown = slice;
+  static constexpr int extra = xown + 512;
+  static constexpr int bytes = extra + (EXTRA ? 512 : 0);
+  static constexpr int cta_bytes = bytes * kStages * kWarps;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap(); // a lost bulk copy must fail loudly, never hang the device
+}
+
+template<int W, int ND, bool RESID, class Epi>
+__global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const double* __restrict__ x,
+                                                            double* __restrict__ y, Epi epi, RedPtrs red,
+                                                            const int* __restrict__ done) {
+  using L = StageLayout<W, Epi::kExtra>;
+  extern __shared__ __align__(128) unsigned char sb_smem[];
+  __shared__ __align__(8) uint64_t bars[kWarps][kStages];
+  if (done != nullptr && *done != 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* wbase = sb_smem + (size_t) warp * kStages * L::bytes;
+  const int64_t row0 = (int64_t) blockIdx.x * kTile + warp * (kTile / kWarps);
+
+  auto issue = [&](int j) { // elected lane: fetch stage j (64 rows) into ring slot j % kStages
+    const int s = j % kStages;
+    unsigned char* dst = wbase + s * L::bytes;
+    uint64_t* bar = &bars[warp][s];
+    const int64_t r = row0 + j * 64;
+    mbar_expect_tx(bar, (uint32_t) L::bytes);
+    bulk_g2s(dst, op.blk + (r >> 6) * (int64_t) L::slice, L::slice, bar);
+    bulk_g2s(dst + L::xown, x + r, 512, bar);
+    if constexpr (Epi::kExtra) bulk_g2s(dst + L::extra, epi.extra() + r, 512, bar);
+  };
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < kStages; ++j) issue(j);
+  }
+  __syncwarp();
+
+  double acc[ND > 0 ? ND : 1];
+#pragma unroll
+  for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+
+#pragma unroll
+  for (int j = 0; j < kSub; ++j) {
+    const int s = j % kStages;
+    mbar_wait(&bars[warp][s], (uint32_t) ((j / kStages) & 1));
+    const unsigned char* src = wbase + s * L::bytes;
+    int2 c[W];
+    double2 a[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      c[k] = reinterpret_cast<const int2*>(src + L::col + k * 256)[lane];
+      a[k] = reinterpret_cast<const double2*>(src + L::coef + k * 512)[lane];
+    }
+    const double2 dg = reinterpret_cast<const double2*>(src + L::diag)[lane];
+    const double2 xo = reinterpret_cast<const double2*>(src + L::xown)[lane];
+    typename Epi::Regs er;
+    if constexpr (Epi::kExtra) epi.from_stage(er, reinterpret_cast<const double2*>(src + L::extra)[lane]);
+    __syncwarp(); // every lane has copied its slice out of the ring slot
+    if (lane == 0 && j + kStages < kSub) issue(j + kStages);
+
+    double g0[W], g1[W];
+    if (op.debug & 1) {
+#pragma unroll
+      for (int k = 0; k < W; ++k) g0[k] = xo.x, g1[k] = xo.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        g0[k] = (c[k].x >= 0) ? __ldg(x + c[k].x) : 0.0;
+        g1[k] = (c[k].y >= 0) ? __ldg(x + c[k].y) : 0.0;
+      }
+    }
+    double u0 = __dmul_rn(dg.x, xo.x), u1 = __dmul_rn(dg.y, xo.y);
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      const double t0 = __dadd_rn(u0, __dmul_rn(a[k].x, g0[k]));
+      const double t1 = __dadd_rn(u1, __dmul_rn(a[k].y, g1[k]));
+      u0 = (c[k].x >= 0) ? t0 : u0;
+      u1 = (c[k].y >= 0) ? t1 : u1;
+    }
+    double2 out = make_double2(u0, u1);
+    const int64_t e0 = row0 + j * 64 + 2 * lane;
+    if constexpr (RESID) {
+      out.x = __dsub_rn(er.b.x, out.x);
+      out.y = __dsub_rn(er.b.y, out.y);
+      acc_pair(acc[0], e0, op.n, __dmul_rn(out.x, out.x), __dmul_rn(out.y, out.y));
+    }
+    st2(y, e0, out);
+    if constexpr (!RESID) epi.run(e0, op.n, xo, out, er, acc);
+  }
+  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red);
 }
 
 } // namespace sb
@@ -166,10 +328,19 @@ struct sb_op {
   sb::OpDev d;
   int64_t n_entries = 0;
   int64_t device_bytes = 0;
-  void* buffers[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* buffers[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace sb {
+
+// SB_APPLY_V1=1 selects the register-staged kernel (v1) for A/B measurements.
+inline bool apply_v1_forced() {
+  static const bool forced = [] {
+    const char* e = std::getenv("SB_APPLY_V1");
+    return e != nullptr && e[0] == '1';
+  }();
+  return forced;
+}
 
 // Launch y <- A x (+ epilogue) on the context's stream, dispatching on form and ELL width.
 template<int ND, bool RESID, class Epi, class Final>
@@ -180,9 +351,9 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
   if constexpr (ND > 0) {
     SB_TRY(ensure_red_scratch(ctx, d.n));
   }
-  const RedPtrs red{ctx->red.partials, ctx->red.cap_tiles, ctx->red.ticket};
+  const RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
 #define SB_LAUNCH(FORM, W)                                                                       \
-  apply_kernel<FORM, W, ND, RESID, Epi, Final><<<grid, kThreads, 0, ctx->stream>>>(d, x, y, epi, red, fin, done)
+  apply_kernel<FORM, W, ND, RESID, Epi><<<grid, kThreads, 0, ctx->stream>>>(d, x, y, epi, red, done)
 #define SB_WIDTHS(FORM)                   \
   switch (d.width) {                      \
     case 0: case 1: SB_LAUNCH(FORM, 1); break; \
@@ -197,7 +368,33 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
       set_error("operator width %d not supported (max 8)", d.width); \
       return SB_ERR_INVALID;              \
   }
-  if (d.form == SB_FORM_COEF) {
+  if (d.form == SB_FORM_COEF && d.blk != nullptr) {
+#define SB_LAUNCH_TMA(W)                                                                                        \
+  {                                                                                                             \
+    auto kern = apply_kernel_tma<W, ND, RESID, Epi>;                                                     \
+    constexpr int smem = StageLayout<W, Epi::kExtra>::cta_bytes;                                                \
+    static bool configured = false;                                                                             \
+    if (!configured) {                                                                                          \
+      SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
+      configured = true;                                                                                        \
+    }                                                                                                           \
+    kern<<<grid, kThreads, smem, ctx->stream>>>(d, x, y, epi, red, done);                                  \
+  }
+    switch (d.width) {
+      case 0: case 1: SB_LAUNCH_TMA(1) break;
+      case 2: SB_LAUNCH_TMA(2) break;
+      case 3: SB_LAUNCH_TMA(3) break;
+      case 4: SB_LAUNCH_TMA(4) break;
+      case 5: SB_LAUNCH_TMA(5) break;
+      case 6: SB_LAUNCH_TMA(6) break;
+      case 7: SB_LAUNCH_TMA(7) break;
+      case 8: SB_LAUNCH_TMA(8) break;
+      default:
+        set_error("operator width %d not supported (max 8)", d.width);
+        return SB_ERR_INVALID;
+    }
+#undef SB_LAUNCH_TMA
+  } else if (d.form == SB_FORM_COEF) {
     SB_WIDTHS(SB_FORM_COEF)
   } else {
     SB_WIDTHS(SB_FORM_FAITHFUL)
@@ -206,6 +403,7 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
 #undef SB_LAUNCH
   ctx->launches++;
   SB_CUDA(cudaGetLastError());
+  if constexpr (ND > 0) return launch_final<ND>(ctx, d.n, fin, done);
   return SB_OK;
 }
 

@@ -264,10 +264,11 @@ struct BiEndBody { // x = (x + alpha*p) + omega*r ; r -= omega*t ; acc0 += r.r ;
 // ---- host side ------------------------------------------------------------------------------------
 template<int ND, class Body, class Final>
 int launch_ew(sb_ctx* ctx, int64_t n, const Body& body, const Final& fin, const int* done) {
-  RedPtrs red{ctx->red.partials, ctx->red.cap_tiles, ctx->red.ticket};
-  ew_kernel<ND, Body, Final><<<(unsigned) num_tiles(n), kThreads, 0, ctx->stream>>>(n, body, red, fin, done);
+  RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
+  ew_kernel<ND, Body><<<(unsigned) num_tiles(n), kThreads, 0, ctx->stream>>>(n, body, red, done);
   ctx->launches++;
   SB_CUDA(cudaGetLastError());
+  if constexpr (ND > 0) return launch_final<ND>(ctx, n, fin, done);
   return SB_OK;
 }
 
@@ -423,7 +424,8 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
     SB_CUDA(cudaGraphInstantiate(&graph_exec, graph, 0));
     SB_CUDA(cudaGraphDestroy(graph));
   }
-  const int per_iter = (kind == Kind::Cg) ? 3 : 5;
+  const int per_iter = (kind == Kind::Cg) ? 3 : 5;       // profiled kernel slots (each includes its final stage)
+  const int launches_per_iter = (kind == Kind::Cg) ? 5 : 8; // + one-CTA final-reduce launches
 
   // Convergence polling: a flag copy is queued every `check` iterations and examined one batch later,
   // so the host never drains the stream while it still has work to enqueue.
@@ -442,7 +444,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
     for (; it < batch_end; ++it) {
       if (graph_exec != nullptr) {
         SB_CUDA(cudaGraphLaunch(graph_exec, ctx->stream));
-        ctx->launches += per_iter;
+        ctx->launches += launches_per_iter;
       } else {
         if (profile) S.prof = &prof_events;
         SB_TRY(S.iterate(kind));
