@@ -1,0 +1,89 @@
+"""ctypes access to libstorm_dropin.so: StormRuler's own solver templates instantiated on
+Storm::DeviceVector (stormruler_b200/host/dropin.cpp). Built by `make -C stormruler_b200/host` where the
+reference tree is available; the built library travels to the GPU box. Test/bench plumbing only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "host", "libstorm_dropin.so")
+
+GENERIC_SOLVERS = ("cg", "cgs", "bicgstab", "bicgstabl", "gmres", "fgmres", "tfqmr", "tfqmr1", "idrs",
+                   "richardson")
+FUSED_SOLVERS = ("fused_cg", "fused_bicgstab")
+
+
+class Opts(C.Structure):
+    _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
+                ("num_inner_iterations", C.c_int64), ("relaxation_factor", C.c_double),
+                ("use_graph", C.c_int32)]
+
+
+class Report(C.Structure):
+    _fields_ = [("converged", C.c_int32), ("iterations", C.c_int64), ("abs_err", C.c_double),
+                ("rel_err", C.c_double), ("n_hist", C.c_int64), ("n_trace", C.c_int64),
+                ("n_apply", C.c_int64)]
+
+
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        capi.load()  # libstormb200.so first (also found through the rpath)
+        if not available():
+            raise ImportError(f"{LIB_PATH} is missing: run `make -C stormruler_b200/host` where the "
+                              "StormRuler sources are available")
+        L = C.CDLL(LIB_PATH)
+        L.dropin_solve.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                   C.POINTER(Opts), C.POINTER(Report), capi.f64p, C.c_int64, capi.f64p,
+                                   C.c_int64]
+        L.dropin_solve.restype = C.c_int
+        L.dropin_last_error.restype = C.c_char_p
+        L.dropin_reset_rng.restype = None
+        L.dropin_selftest_errors.argtypes = [C.c_void_p]
+        L.dropin_selftest_errors.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+@dataclass
+class Result:
+    converged: bool
+    iterations: int
+    abs_err: float
+    rel_err: float
+    hist: np.ndarray
+    trace: np.ndarray
+    n_apply: int
+
+
+def solve(name: str, op, x, b, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6, num_inner=0,
+          relaxation_factor=0.0, use_graph=True, reset_rng=True, trace_cap=None) -> Result:
+    """Run solver `name` on DeviceVectors x (in/out) and b through the C++ drop-in."""
+    L = load()
+    if reset_rng:
+        L.dropin_reset_rng()
+    cap_h = num_iterations + 2
+    cap_t = trace_cap or (64 * num_iterations + 256)
+    hist, trace = np.zeros(cap_h), np.zeros(cap_t)
+    opts = Opts(num_iterations, abs_tol, rel_tol, num_inner, relaxation_factor, int(use_graph))
+    rep = Report()
+    rc = L.dropin_solve(name.encode(), op.ctx.handle, op.handle, x.ptr, b.ptr, x.n, C.byref(opts),
+                        C.byref(rep), hist.ctypes.data_as(capi.f64p), cap_h,
+                        trace.ctypes.data_as(capi.f64p), cap_t)
+    if rc != 0:
+        raise capi.StormB200Error(f"dropin_solve({name}) failed ({rc}): {L.dropin_last_error().decode()}")
+    return Result(bool(rep.converged), rep.iterations, rep.abs_err, rep.rel_err,
+                  hist[:min(rep.n_hist, cap_h)].copy(), trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)

@@ -1,0 +1,392 @@
+// Storm/B200/DeviceVector.hpp -- the C++23 drop-in: StormRuler's solver headers, unchanged, on a B200.
+//
+// StormRuler's extension point for the Krylov path is not an FFI but two C++ contracts
+// (SURVEY.md 8b):
+//   * the `legacy_vector_like` concept            Storm/Solvers/Operator.hpp:39-45
+//   * `Operator<Vector>::mul` (virtual)           Storm/Solvers/Operator.hpp:66-74
+// plus the Bittern free functions / operators that the solver bodies find by overload resolution
+// on the vector type (Storm/Bittern/MatrixAlgorithms.hpp, MatrixMath.hpp, MatrixTarget.hpp).
+// This header supplies a vector type whose storage lives in HBM (`Storm::DeviceVector`), the lazy
+// expression type its operators build (`Storm::DevExpr`, flattened to the postfix program of
+// sb_eval so the kernel evaluates in the reference's association order), the reductions, and an
+// `Operator<DeviceVector>` over an uploaded FVM operator (`Storm::FvmOperator`). With it,
+//     Storm::BiCgStabLSolver<Storm::DeviceVector> solver;   solver.solve(x, b, op);
+// compiles from the reference's own SolverBiCgStab.hpp and runs every vector statement as a
+// hand-written sm_100a kernel through the C ABI of libstormb200.so (include/stormb200.h). There
+// is no host fallback: every operation goes to the device or throws.
+//
+// Include order in a translation unit:
+//     -I<repo>/stormruler_b200/host/compat  (first: shadows Storm/Bittern/MatrixDense.hpp)
+//     #include <Storm/B200/DeviceVector.hpp>      // before any Storm/Solvers/Solver*.hpp
+//     #include <Storm/Solvers/SolverCg.hpp> ...
+//
+// Overload-resolution contract (SURVEY.md 8b "hazard", probed): the generic Bittern entry points
+// take forwarding references, which beat a `const DeviceVector&` parameter for non-const lvalues.
+// Therefore every vector-taking function below exists for all const / non-const lvalue
+// combinations as NON-template overloads; `DevExpr` is deliberately not a Storm::matrix (no
+// shape()), and DeviceVector is deliberately not a Storm::output_matrix (its element accessor
+// returns a by-value proxy that the scalar functors reject), so an accidental fall-through to the
+// per-element generic path is a compile error instead of a silently slow run.
+#pragma once
+
+#include <Storm/Bittern/Matrix.hpp>
+
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include "../../../../include/stormb200.h"
+
+namespace Storm {
+
+// ---- names the legacy solver headers expect but the tree no longer defines ------
+template<class R, class C>
+using MatrixShape = std::tuple<R, C>; // Solvers/MatrixDense.hpp:150
+template<class M>
+constexpr auto& fill_with(M& m, double s) { // Solver.hpp:281, SolverBiCgStab.hpp:224, SolverTfqmr.hpp:77
+  return fill(m, s);
+}
+constexpr auto make_diagonal_matrix(auto shape, auto s) { // Solvers/MatrixDense.hpp:174
+  return eye<double>(shape, double(s));
+}
+
+namespace B200 {
+
+/// Throws std::runtime_error carrying the library's message when a C-ABI call fails.
+inline void check(int rc, const char* what) {
+  if (rc != SB_OK) {
+    throw std::runtime_error(std::string{"stormb200: "} + what + " failed (" + std::to_string(rc) +
+                             "): " + sb_last_error());
+  }
+}
+
+/// Optional observer of every reduction result (dot_product / norm_2), in call order: the hook the
+/// parity tests use to compare the full scalar trace with the CPU reference.
+using ReductionObserver = void (*)(void* user, double value);
+inline ReductionObserver g_observer = nullptr;
+inline void* g_observer_user = nullptr;
+inline void observe(double v) {
+  if (g_observer != nullptr) g_observer(g_observer_user, v);
+}
+
+/// Engine behind fill_randomly(DeviceVector&): the reference's construction, a default-seeded
+/// std::mt19937_64 with a static lifetime (MatrixAlgorithms.hpp:140-153), made resettable.
+inline std::mt19937_64& random_engine() {
+  static std::mt19937_64 engine{};
+  return engine;
+}
+
+} // namespace B200
+
+class DeviceVector;
+
+/// By-value proxy returned by DeviceVector::operator(): explicit read only. Not arithmetic, not
+/// assignable: the generic per-element Bittern algorithms cannot be instantiated with it.
+struct DeviceElement {
+  double value;
+  double get() const noexcept { return value; }
+};
+
+/// Lazy vector expression: a postfix program over <= 4 distinct device vectors and <= 4 scalars
+/// (the sb_expr of include/stormb200.h). Stands in for Bittern's MapMatrixView trees
+/// (MatrixMath.hpp:44-87); evaluation order is exactly the order the C++ operators were applied.
+class DevExpr {
+public:
+
+  DevExpr() = default;
+  DevExpr(const DeviceVector& v); // NOLINT: implicit on purpose (a vector is an expression)
+
+  static DevExpr scalar(double s) {
+    DevExpr e;
+    e._e.scal[0] = s;
+    e._n_scal = 1;
+    e.push(SB_OP_SCAL0);
+    return e;
+  }
+
+  /// `lhs (op) rhs` with op in SB_OP_ADD..SB_OP_DIV.
+  static DevExpr binary(const DevExpr& lhs, const DevExpr& rhs, uint8_t op) {
+    DevExpr out = lhs;
+    if (out._ctx == nullptr) out._ctx = rhs._ctx, out._n = rhs._n;
+    if (lhs._ctx != nullptr && rhs._ctx != nullptr && (lhs._ctx != rhs._ctx || lhs._n != rhs._n)) {
+      throw std::runtime_error("stormb200: expression mixes vectors of different size or context");
+    }
+    int vmap[SB_EXPR_MAX_VEC], smap[SB_EXPR_MAX_SCAL];
+    for (int k = 0; k < rhs._n_vec; ++k) {
+      int slot = -1;
+      for (int q = 0; q < out._n_vec; ++q)
+        if (out._e.vec[q] == rhs._e.vec[k]) slot = q;
+      if (slot < 0) {
+        if (out._n_vec == SB_EXPR_MAX_VEC) throw std::runtime_error("stormb200: expression uses more than 4 vectors");
+        slot = out._n_vec++;
+        out._e.vec[slot] = rhs._e.vec[k];
+      }
+      vmap[k] = slot;
+    }
+    for (int k = 0; k < rhs._n_scal; ++k) {
+      if (out._n_scal == SB_EXPR_MAX_SCAL) throw std::runtime_error("stormb200: expression uses more than 4 scalars");
+      smap[k] = out._n_scal;
+      out._e.scal[out._n_scal++] = rhs._e.scal[k];
+    }
+    for (int k = 0; k < rhs._e.n_ops; ++k) {
+      const uint8_t o = rhs._e.ops[k];
+      if (o <= SB_OP_VEC3) out.push(uint8_t(SB_OP_VEC0 + vmap[o - SB_OP_VEC0]));
+      else if (o >= SB_OP_SCAL0 && o <= SB_OP_SCAL3) out.push(uint8_t(SB_OP_SCAL0 + smap[o - SB_OP_SCAL0]));
+      else out.push(o);
+    }
+    out.push(op);
+    return out;
+  }
+
+  DevExpr negated() const {
+    DevExpr out = *this;
+    out.push(SB_OP_NEG);
+    return out;
+  }
+
+  const sb_expr& program() const noexcept { return _e; }
+  sb_ctx* context() const noexcept { return _ctx; }
+  size_t size() const noexcept { return _n; }
+
+private:
+
+  void push(uint8_t op) {
+    if (_e.n_ops == SB_EXPR_MAX_OPS) throw std::runtime_error("stormb200: expression too long");
+    _e.ops[_e.n_ops++] = op;
+  }
+
+  sb_expr _e{};
+  int _n_vec = 0, _n_scal = 0;
+  sb_ctx* _ctx = nullptr;
+  size_t _n = 0;
+};
+
+/// Device-resident fp64 vector: the `Vector` of the solver templates on a B200. Replaces
+/// CellField (Feathers/Field.hpp:60-114): contiguous doubles, shape {n, 1} (rank 2, :77-79),
+/// assign() allocates ZERO-filled storage of the same shape (:82-84 -- IDR(s) relies on it).
+/// Move-only; std::swap is a pointer swap (SolverBiCgStab.hpp:84 etc.).
+class DeviceVector final {
+public:
+
+  DeviceVector() = default;
+  DeviceVector(sb_ctx* ctx, size_t n) { allocate(ctx, n); }
+  DeviceVector(sb_ctx* ctx, const std::vector<double>& host) {
+    allocate(ctx, host.size());
+    upload(host.data());
+  }
+  DeviceVector(const DeviceVector&) = delete;
+  DeviceVector& operator=(const DeviceVector&) = delete;
+  DeviceVector(DeviceVector&& o) noexcept : _ctx{o._ctx}, _d{o._d}, _n{o._n}, _owned{o._owned} {
+    o._d = nullptr, o._n = 0, o._owned = false;
+  }
+  DeviceVector& operator=(DeviceVector&& o) noexcept {
+    if (this != &o) {
+      release();
+      _ctx = o._ctx, _d = o._d, _n = o._n, _owned = o._owned;
+      o._d = nullptr, o._n = 0, o._owned = false;
+    }
+    return *this;
+  }
+  ~DeviceVector() { release(); }
+
+  /// Non-owning view of device memory that came from sb_vec_alloc elsewhere (e.g. Python).
+  static DeviceVector view(sb_ctx* ctx, double* d, size_t n) {
+    DeviceVector v;
+    v._ctx = ctx, v._d = d, v._n = n, v._owned = false;
+    return v;
+  }
+
+  // -- the legacy_vector_like surface (Operator.hpp:39-45) ---------------------------------------
+  auto shape() const noexcept { return std::array<size_t, 2>{_n, 1}; }
+  /// Debug accessor (one-element D2H copy). Exists so that Storm::matrix<DeviceVector> holds.
+  DeviceElement operator()(size_t row, size_t = 0) const {
+    double v = 0.0;
+    B200::check(sb_vec_download(_ctx, _d + row, &v, 1), "sb_vec_download");
+    return DeviceElement{v};
+  }
+  void assign(const DeviceVector& other, bool copy = true) {
+    if (&other == this) return;
+    release();
+    allocate(other._ctx, other._n); // zero-filled
+    if (copy && _n > 0) B200::check(sb_copy(_ctx, _d, other._d, _n), "sb_copy");
+  }
+
+  // -- storage -----------------------------------------------------------------------------------
+  sb_ctx* context() const noexcept { return _ctx; }
+  double* data() noexcept { return _d; }
+  const double* data() const noexcept { return _d; }
+  size_t size() const noexcept { return _n; }
+  void upload(const double* host) { B200::check(sb_vec_upload(_ctx, _d, host, _n), "sb_vec_upload"); }
+  void download(double* host) const { B200::check(sb_vec_download(_ctx, _d, host, _n), "sb_vec_download"); }
+  std::vector<double> to_host() const {
+    std::vector<double> h(_n);
+    if (_n > 0) download(h.data());
+    return h;
+  }
+
+  // -- assignment operators (MatrixTarget.hpp:96-119) ---------------------------------------------
+  DeviceVector& eval(int assign_op, const DevExpr& e) {
+    if (e.context() != nullptr && (e.context() != _ctx || e.size() != _n)) {
+      throw std::runtime_error("stormb200: assignment between vectors of different size or context");
+    }
+    B200::check(sb_eval(_ctx, _d, _n, assign_op, &e.program()), "sb_eval");
+    return *this;
+  }
+  DeviceVector& operator+=(const DevExpr& e) { return eval(SB_ADD_ASSIGN, e); }
+  DeviceVector& operator-=(const DevExpr& e) { return eval(SB_SUB_ASSIGN, e); }
+  DeviceVector& operator*=(double s) { return eval(SB_MUL_ASSIGN, DevExpr::scalar(s)); }
+  DeviceVector& operator/=(double s) { return eval(SB_DIV_ASSIGN, DevExpr::scalar(s)); }
+
+private:
+
+  void allocate(sb_ctx* ctx, size_t n) {
+    if (ctx == nullptr) throw std::runtime_error("stormb200: DeviceVector needs a context");
+    _ctx = ctx, _n = n, _owned = true;
+    B200::check(sb_vec_alloc(ctx, n, &_d), "sb_vec_alloc");
+  }
+  void release() noexcept {
+    if (_owned && _d != nullptr) sb_vec_free(_ctx, _d);
+    _d = nullptr, _n = 0, _owned = false;
+  }
+
+  sb_ctx* _ctx = nullptr;
+  double* _d = nullptr;
+  size_t _n = 0;
+  bool _owned = false;
+};
+
+inline DevExpr::DevExpr(const DeviceVector& v) : _n_vec{1}, _ctx{v.context()}, _n{v.size()} {
+  _e.vec[0] = v.data();
+  _e.ops[0] = SB_OP_VEC0;
+  _e.n_ops = 1;
+}
+
+// ---- y <<= expr (MatrixAlgorithms.hpp:120-124) ---------------------------------------------------
+inline DeviceVector& operator<<=(DeviceVector& y, const DevExpr& e) { return y.eval(SB_ASSIGN, e); }
+inline DeviceVector& operator<<=(DeviceVector& y, DeviceVector& x) { return y.eval(SB_ASSIGN, DevExpr{x}); }
+inline DeviceVector& operator<<=(DeviceVector& y, const DeviceVector& x) { return y.eval(SB_ASSIGN, DevExpr{x}); }
+
+// ---- expression builders (MatrixMath.hpp:233-301), all cv combinations ---------------------------
+#define STORM_B200_BINARY(OPNAME, CODE)                                                                          \
+  inline DevExpr OPNAME(const DevExpr& a, const DevExpr& b) { return DevExpr::binary(a, b, CODE); }              \
+  inline DevExpr OPNAME(DeviceVector& a, DeviceVector& b) { return DevExpr::binary(a, b, CODE); }                \
+  inline DevExpr OPNAME(DeviceVector& a, const DeviceVector& b) { return DevExpr::binary(a, b, CODE); }          \
+  inline DevExpr OPNAME(const DeviceVector& a, DeviceVector& b) { return DevExpr::binary(a, b, CODE); }          \
+  inline DevExpr OPNAME(const DeviceVector& a, const DeviceVector& b) { return DevExpr::binary(a, b, CODE); }    \
+  inline DevExpr OPNAME(DeviceVector& a, const DevExpr& b) { return DevExpr::binary(a, b, CODE); }               \
+  inline DevExpr OPNAME(const DeviceVector& a, const DevExpr& b) { return DevExpr::binary(a, b, CODE); }         \
+  inline DevExpr OPNAME(const DevExpr& a, DeviceVector& b) { return DevExpr::binary(a, b, CODE); }               \
+  inline DevExpr OPNAME(const DevExpr& a, const DeviceVector& b) { return DevExpr::binary(a, b, CODE); }
+STORM_B200_BINARY(operator+, SB_OP_ADD)
+STORM_B200_BINARY(operator-, SB_OP_SUB)
+#undef STORM_B200_BINARY
+
+// scal * mat, mat * scal (MatrixMath.hpp:247-257): element-wise scal * x (commutative in IEEE-754).
+inline DevExpr operator*(double s, const DevExpr& a) { return DevExpr::binary(DevExpr::scalar(s), a, SB_OP_MUL); }
+inline DevExpr operator*(double s, DeviceVector& a) { return s * DevExpr{a}; }
+inline DevExpr operator*(double s, const DeviceVector& a) { return s * DevExpr{a}; }
+inline DevExpr operator*(const DevExpr& a, double s) { return DevExpr::binary(a, DevExpr::scalar(s), SB_OP_MUL); }
+inline DevExpr operator*(DeviceVector& a, double s) { return DevExpr{a} * s; }
+inline DevExpr operator*(const DeviceVector& a, double s) { return DevExpr{a} * s; }
+// mat / scal (MatrixMath.hpp:266-270)
+inline DevExpr operator/(const DevExpr& a, double s) { return DevExpr::binary(a, DevExpr::scalar(s), SB_OP_DIV); }
+inline DevExpr operator/(DeviceVector& a, double s) { return DevExpr{a} / s; }
+inline DevExpr operator/(const DeviceVector& a, double s) { return DevExpr{a} / s; }
+// unary minus (MatrixMath.hpp:241-243)
+inline DevExpr operator-(const DevExpr& a) { return a.negated(); }
+inline DevExpr operator-(DeviceVector& a) { return DevExpr{a}.negated(); }
+inline DevExpr operator-(const DeviceVector& a) { return DevExpr{a}.negated(); }
+
+// ---- reductions (MatrixAlgorithms.hpp:262-270, 310-317): fixed tree SB_TREE v1, result on the host
+namespace B200 {
+inline double dot_impl(const DeviceVector& a, const DeviceVector& b) {
+  if (a.context() != b.context() || a.size() != b.size()) {
+    throw std::runtime_error("stormb200: dot_product of vectors of different size or context");
+  }
+  double v = 0.0;
+  check(sb_dot(a.context(), a.data(), b.data(), a.size(), &v), "sb_dot");
+  observe(v);
+  return v;
+}
+inline double norm_impl(const DeviceVector& a) {
+  double v = 0.0;
+  check(sb_norm2(a.context(), a.data(), a.size(), &v), "sb_norm2");
+  observe(v);
+  return v;
+}
+} // namespace B200
+inline double dot_product(DeviceVector& a, DeviceVector& b) { return B200::dot_impl(a, b); }
+inline double dot_product(DeviceVector& a, const DeviceVector& b) { return B200::dot_impl(a, b); }
+inline double dot_product(const DeviceVector& a, DeviceVector& b) { return B200::dot_impl(a, b); }
+inline double dot_product(const DeviceVector& a, const DeviceVector& b) { return B200::dot_impl(a, b); }
+inline double norm_2(DeviceVector& a) { return B200::norm_impl(a); }
+inline double norm_2(const DeviceVector& a) { return B200::norm_impl(a); }
+
+// ---- fills ---------------------------------------------------------------------------------------
+inline DeviceVector& fill_with(DeviceVector& y, double s) {
+  B200::check(sb_fill(y.context(), y.data(), y.size(), s), "sb_fill");
+  return y;
+}
+inline DeviceVector& fill(DeviceVector& y, double s) { return fill_with(y, s); }
+/// Uniform(0,1) numbers from the reference's engine construction, generated on the host in row
+/// order and uploaded: integer RNG state must be reproduced exactly.
+inline DeviceVector& fill_randomly(DeviceVector& y) {
+  std::uniform_real_distribution<double> distribution{0.0, 1.0};
+  std::vector<double> h(y.size());
+  for (double& v : h) v = distribution(B200::random_engine());
+  if (!h.empty()) y.upload(h.data());
+  return y;
+}
+
+} // namespace Storm
+
+#include <Storm/Solvers/Operator.hpp>
+
+namespace Storm {
+
+static_assert(matrix<DeviceVector>);
+static_assert(legacy_vector_like<DeviceVector>);
+static_assert(!output_matrix<DeviceVector>, "the generic per-element Bittern path must stay unreachable");
+
+/// The uploaded matrix-free FVM operator as an Operator<DeviceVector> (Operator.hpp:66-74): what the
+/// playground wraps in a FunctionalOperator around stormDivGrad (Playground.cpp:115-131,153-167).
+class FvmOperator final : public Operator<DeviceVector> {
+public:
+
+  /// Takes ownership of nothing: `op` must outlive this object (sb_op_create / sb_op_destroy).
+  FvmOperator(sb_ctx* ctx, const sb_op* op) : _ctx{ctx}, _op{op} {}
+
+  /// Upload a face-list mesh (sb_mesh_soa) and own the resulting device operator.
+  FvmOperator(sb_ctx* ctx, const sb_mesh_soa& mesh, const sb_op_desc& desc) : _ctx{ctx} {
+    B200::check(sb_op_create(ctx, &mesh, &desc, &_owned), "sb_op_create");
+    _op = _owned;
+  }
+  ~FvmOperator() override {
+    if (_owned != nullptr) sb_op_destroy(_ctx, _owned);
+  }
+
+  void mul(DeviceVector& y, const DeviceVector& x) const override {
+    B200::check(sb_apply(_ctx, _op, x.data(), y.data()), "sb_apply");
+    ++_num_applies;
+  }
+
+  sb_ctx* context() const noexcept { return _ctx; }
+  const sb_op* handle() const noexcept { return _op; }
+  size_t num_applies() const noexcept { return _num_applies; }
+
+private:
+
+  sb_ctx* _ctx = nullptr;
+  const sb_op* _op = nullptr;
+  sb_op* _owned = nullptr;
+  mutable size_t _num_applies = 0;
+};
+
+} // namespace Storm

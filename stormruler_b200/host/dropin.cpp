@@ -1,0 +1,209 @@
+// dropin.cpp -- the reference's solver templates instantiated on Storm::DeviceVector.
+//
+// This translation unit is what a StormRuler application does after switching its Vector type:
+// it includes the reference's OWN solver headers from where they lie (-I<reference>/source, nothing
+// copied) after Storm/B200/DeviceVector.hpp and instantiates every solver on the device vector:
+//   SolverCg.hpp, SolverCgs.hpp, SolverBiCgStab.hpp (BiCGStab, BiCGStab(l)), SolverGmres.hpp
+//   (GMRES, FGMRES), SolverTfqmr.hpp (TFQMR, TFQMR1), SolverIdrs.hpp, SolverRichardson.hpp,
+// all driven by IterativeSolver::solve (Solver.hpp:116-147), plus the two fused fast-path solvers
+// of Storm/B200/FusedSolvers.hpp. It is exported behind a small C entry point so the parity tests
+// (Python, ctypes) can run it on vectors they own; g++ -std=c++23 builds it, linking libstormb200.so.
+// The built libstorm_dropin.so travels to the GPU box (the reference tree does not exist there).
+#include <Storm/B200/FusedSolvers.hpp>
+
+#include <Storm/Solvers/SolverBiCgStab.hpp>
+#include <Storm/Solvers/SolverCg.hpp>
+#include <Storm/Solvers/SolverCgs.hpp>
+#include <Storm/Solvers/SolverGmres.hpp>
+#include <Storm/Solvers/SolverIdrs.hpp>
+#include <Storm/Solvers/SolverRichardson.hpp>
+#include <Storm/Solvers/SolverTfqmr.hpp>
+
+#include <cstring>
+#include <string>
+
+namespace {
+
+using Storm::DeviceVector;
+
+struct dropin_opts {
+  int64_t num_iterations;
+  double abs_tol;
+  double rel_tol;
+  int64_t num_inner_iterations; // <= 0: keep the solver's default (Solver.hpp:159)
+  double relaxation_factor;     // Richardson only; <= 0 keeps the default
+  int32_t use_graph;            // fused solvers only
+};
+
+struct dropin_report {
+  int32_t converged;
+  int64_t iterations;
+  double abs_err;
+  double rel_err;
+  int64_t n_hist;
+  int64_t n_trace;
+  int64_t n_apply;
+};
+
+thread_local std::string g_error;
+
+struct Trace {
+  double* data = nullptr;
+  int64_t cap = 0, count = 0;
+  static void push(void* user, double v) {
+    auto* t = static_cast<Trace*>(user);
+    if (t->data != nullptr && t->count < t->cap) t->data[t->count] = v;
+    ++t->count;
+  }
+};
+
+// Forwards to the FVM operator and samples the solver's public progress fields on every call
+// (residual-history capture, method (2) of SURVEY.md 8c -- same scheme as the CPU oracle harness).
+template<class SolverT>
+struct SamplingOperator final : Storm::Operator<DeviceVector> {
+  const Storm::FvmOperator* inner;
+  const SolverT* solver;
+  double* hist;
+  int64_t hist_cap;
+  mutable int64_t n_apply = 0;
+  void mul(DeviceVector& y, const DeviceVector& x) const override {
+    const int64_t it = (int64_t) solver->iteration;
+    if (hist != nullptr && it < hist_cap) hist[it] = solver->absolute_error;
+    inner->mul(y, x);
+    ++n_apply;
+  }
+};
+
+template<class SolverT>
+int run_generic(sb_ctx* ctx, const sb_op* op, double* d_x, const double* d_b, size_t n, const dropin_opts* o,
+                dropin_report* rep, double* hist, int64_t hist_cap, double* trace, int64_t trace_cap) {
+  SolverT solver{};
+  solver.num_iterations = (size_t) o->num_iterations;
+  solver.absolute_error_tolerance = o->abs_tol;
+  solver.relative_error_tolerance = o->rel_tol;
+  if constexpr (requires { solver.num_inner_iterations; }) {
+    if (o->num_inner_iterations > 0) solver.num_inner_iterations = (size_t) o->num_inner_iterations;
+  }
+  if constexpr (requires { solver.relaxation_factor; }) {
+    if (o->relaxation_factor > 0.0) solver.relaxation_factor = o->relaxation_factor;
+  }
+  DeviceVector x = DeviceVector::view(ctx, d_x, n);
+  const DeviceVector b = DeviceVector::view(ctx, const_cast<double*>(d_b), n);
+  Trace tr{trace, trace_cap, 0};
+  Storm::B200::g_observer = &Trace::push, Storm::B200::g_observer_user = &tr;
+  const Storm::FvmOperator fvm{ctx, op};
+  SamplingOperator<SolverT> sop;
+  sop.inner = &fvm, sop.solver = &solver, sop.hist = hist, sop.hist_cap = hist_cap;
+  bool converged = false;
+  try {
+    converged = solver.solve(x, b, sop);
+  } catch (...) {
+    Storm::B200::g_observer = nullptr;
+    throw;
+  }
+  Storm::B200::g_observer = nullptr;
+  const int64_t it = (int64_t) solver.iteration;
+  if (hist != nullptr && it < hist_cap) hist[it] = solver.absolute_error;
+  rep->converged = converged ? 1 : 0;
+  rep->iterations = it;
+  rep->abs_err = solver.absolute_error, rep->rel_err = solver.relative_error;
+  rep->n_hist = it + 1, rep->n_trace = tr.count, rep->n_apply = sop.n_apply;
+  return 0;
+}
+
+template<class SolverT>
+int run_fused(sb_ctx* ctx, const sb_op* op, double* d_x, const double* d_b, size_t n, const dropin_opts* o,
+              dropin_report* rep, double* hist, int64_t hist_cap, double* trace, int64_t trace_cap) {
+  SolverT solver{};
+  solver.num_iterations = (size_t) o->num_iterations;
+  solver.absolute_error_tolerance = o->abs_tol;
+  solver.relative_error_tolerance = o->rel_tol;
+  solver.use_graph = o->use_graph != 0;
+  solver.record_history = true;
+  DeviceVector x = DeviceVector::view(ctx, d_x, n);
+  const DeviceVector b = DeviceVector::view(ctx, const_cast<double*>(d_b), n);
+  const Storm::FvmOperator fvm{ctx, op};
+  Storm::Solver<DeviceVector>& as_base = solver; // called through the reference's abstract interface
+  const bool converged = as_base.solve(x, b, fvm);
+  rep->converged = converged ? 1 : 0;
+  rep->iterations = (int64_t) solver.iteration;
+  rep->abs_err = solver.absolute_error, rep->rel_err = solver.relative_error;
+  rep->n_hist = (int64_t) solver.residual_history.size();
+  rep->n_trace = (int64_t) solver.reduction_trace.size();
+  rep->n_apply = -1;
+  if (hist != nullptr)
+    std::memcpy(hist, solver.residual_history.data(), sizeof(double) * (size_t) std::min<int64_t>(rep->n_hist, hist_cap));
+  if (trace != nullptr)
+    std::memcpy(trace, solver.reduction_trace.data(), sizeof(double) * (size_t) std::min<int64_t>(rep->n_trace, trace_cap));
+  return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+#define DROPIN_API __attribute__((visibility("default")))
+
+DROPIN_API const char* dropin_last_error(void) { return g_error.c_str(); }
+
+// Solver names: cg cgs bicgstab bicgstabl gmres fgmres tfqmr tfqmr1 idrs richardson (the reference
+// templates on DeviceVector), fused_cg fused_bicgstab (Storm::B200 fast path).
+DROPIN_API int dropin_solve(const char* name, sb_ctx* ctx, const sb_op* op, double* d_x, const double* d_b,
+                            size_t n, const dropin_opts* o, dropin_report* rep, double* hist, int64_t hist_cap,
+                            double* trace, int64_t trace_cap) {
+  const std::string s{name};
+  try {
+#define DROPIN_CASE(key, T)                                                                              \
+  if (s == key)                                                                                          \
+    return run_generic<Storm::T<DeviceVector>>(ctx, op, d_x, d_b, n, o, rep, hist, hist_cap, trace, trace_cap)
+    DROPIN_CASE("cg", CgSolver);
+    DROPIN_CASE("cgs", CgsSolver);
+    DROPIN_CASE("bicgstab", BiCgStabSolver);
+    DROPIN_CASE("bicgstabl", BiCgStabLSolver);
+    DROPIN_CASE("gmres", GmresSolver);
+    DROPIN_CASE("fgmres", FgmresSolver);
+    DROPIN_CASE("tfqmr", TfqmrSolver);
+    DROPIN_CASE("tfqmr1", Tfqmr1Solver);
+    DROPIN_CASE("idrs", IdrsSolver);
+    DROPIN_CASE("richardson", RichardsonSolver);
+#undef DROPIN_CASE
+    if (s == "fused_cg")
+      return run_fused<Storm::B200::CgSolver>(ctx, op, d_x, d_b, n, o, rep, hist, hist_cap, trace, trace_cap);
+    if (s == "fused_bicgstab")
+      return run_fused<Storm::B200::BiCgStabSolver>(ctx, op, d_x, d_b, n, o, rep, hist, hist_cap, trace, trace_cap);
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -2;
+  }
+  g_error = "unknown solver name";
+  return -1;
+}
+
+// Reset the engine behind fill_randomly(DeviceVector&) to the reference's initial state.
+DROPIN_API void dropin_reset_rng(void) { Storm::B200::random_engine() = std::mt19937_64{}; }
+
+// Misuse checks exercised by the tests: mixing sizes must throw, not corrupt memory.
+DROPIN_API int dropin_selftest_errors(sb_ctx* ctx) {
+  int caught = 0;
+  try {
+    DeviceVector a{ctx, 10}, b{ctx, 11};
+    a += b;
+  } catch (const std::runtime_error&) {
+    ++caught;
+  }
+  try {
+    DeviceVector a{ctx, 10}, b{ctx, 11};
+    (void) Storm::dot_product(a, b);
+  } catch (const std::runtime_error&) {
+    ++caught;
+  }
+  try {
+    DeviceVector a{ctx, 8}, b{ctx, 8}, c{ctx, 8}, d{ctx, 8}, e{ctx, 8};
+    a <<= ((b + c) + (d + e)) + a; // five distinct vectors: over the evaluator's operand limit
+  } catch (const std::runtime_error&) {
+    ++caught;
+  }
+  return caught;
+}
+
+} // extern "C"

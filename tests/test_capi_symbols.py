@@ -57,3 +57,14 @@ def test_no_silent_cpu_fallback(lib):
         assert rc < 0 and h.value is None and len(lib.sb_last_error()) > 0
     assert lib.sb_ctx_create(10_000, C.byref(h)) < 0
     assert lib.sb_version() >= 100
+
+
+def test_dropin_library_loads_when_built():
+    """libstorm_dropin.so (reference solver templates on DeviceVector) is built wherever the reference
+    tree is mounted; it must load and export its entry points without a GPU."""
+    from stormruler_b200 import dropin
+    if not dropin.available():
+        pytest.skip("libstorm_dropin.so not built (needs the StormRuler sources at build time)")
+    L = dropin.load()
+    for name in ("dropin_solve", "dropin_last_error", "dropin_reset_rng", "dropin_selftest_errors"):
+        assert hasattr(L, name)
