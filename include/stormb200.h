@@ -156,6 +156,79 @@ SB_API int sb_mesh_cell_centers(const sb_mesh* mesh, double* h_xyz /* [3*n_cells
 /* Bandwidth of the cell graph, max |inner - outer| over interior faces (renumbering quality). */
 SB_API int64_t sb_mesh_bandwidth(const sb_mesh* mesh);
 
+/* ---- partitioning (host side, no GPU needed): new work specified by SURVEY.md 8e -- the reference has
+ * no partitioning or halo code. The cell graph (cells, one edge per interior face) is split into
+ * n_parts; each rank gets a local mesh in the numbering
+ *     [ interior owned | boundary owned | padding to a 2048 multiple | halo (by owner rank, then global id) ]
+ * whose face list keeps the GLOBAL ascending face order and inner/outer orientation, so every owned
+ * row of the distributed operator is bit-identical to the single-GPU row. All arrays are checked bit
+ * for bit against the numpy restatement in oracle/mesh_oracle.py. */
+typedef struct sb_part sb_part;
+#define SB_PART_METIS 0 /* METIS_PartGraphKway, default options (deterministic) */
+#define SB_PART_SLAB 1  /* contiguous blocks of the current cell order (use after RCM): <= 2 neighbours */
+
+typedef struct sb_part_info {
+  int32_t n_parts;
+  int64_t n_cells;
+  int64_t edge_cut;     /* interior faces whose cells belong to different parts */
+  int64_t max_owned, min_owned;
+  int64_t max_halo;
+  int64_t vec_capacity; /* max over ranks of pad2048(n_owned) + pad2048(n_halo): size of one pool vector */
+} sb_part_info;
+
+typedef struct sb_local_mesh {
+  int32_t rank, n_parts;
+  int64_t n_owned;      /* rows of this rank; local ids [0, n_owned) */
+  int64_t n_interior;   /* owned cells without a neighbour on another rank: local ids [0, n_interior) */
+  int64_t n_halo;       /* local ids [halo_base, halo_base + n_halo) */
+  int64_t halo_base;    /* n_owned rounded up to a multiple of 2048 */
+  const int32_t* local_to_global; /* h_ [n_owned + n_halo]: owned cells, then halo cells */
+  sb_mesh_soa soa;      /* local face list (n_cells = halo_base + n_halo), boundary faces of owned cells */
+  const int64_t* face_global;     /* h_ [soa.n_faces] global face index of each local face (ascending) */
+  int32_t n_nbr;
+  const int32_t* nbr_rank; /* h_ [n_nbr] ascending */
+  const int64_t* send_ptr; /* h_ [n_nbr+1] */
+  const int32_t* send_idx; /* h_ [send_ptr[n_nbr]] local ids of owned cells, ascending global id per neighbour */
+  const int64_t* recv_ptr; /* h_ [n_nbr+1] offsets into the halo block; group k holds cells owned by nbr_rank[k] */
+  const int64_t* send_dst; /* h_ [n_nbr] element offset in neighbour k's vectors where my block starts
+                              (= its halo_base + its recv_ptr for me) */
+} sb_local_mesh;
+
+SB_API int sb_part_create(const sb_mesh* mesh, int n_parts, int method, sb_part** out);
+SB_API int sb_part_from_array(const sb_mesh* mesh, int n_parts, const int32_t* h_part, sb_part** out);
+SB_API int sb_part_destroy(sb_part* part);
+SB_API int sb_part_get_info(sb_part* part, sb_part_info* info);
+SB_API int sb_part_get_array(const sb_part* part, const int32_t** h_part /* [n_cells], owned by part */);
+/* Local mesh of one rank (pointers stay valid until sb_part_destroy). */
+SB_API int sb_part_local(sb_part* part, int rank, sb_local_mesh* out);
+
+/* ---- multi-GPU communicator: one process per GPU. After sb_comm_prepare the context
+ * serves every vector (sb_vec_alloc and the solver workspaces) from a pool of n_vectors blocks of
+ * vec_capacity doubles inside one slab, so that vectors sit at the same offset on every rank.
+ *   SB_COMM_NCCL: halo exchange = grouped ncclSend/ncclRecv, reductions = ncclAllReduce (the
+ *                 torch-bundled or system libnccl.so.2 is loaded at run time);
+ *   SB_COMM_P2P:  the slab is shared with CUDA IPC; the pack kernel stores boundary values directly
+ *                 into the neighbours' halo tails over NVLink and the one-CTA final-reduce kernel
+ *                 exchanges its partial sums with all peers itself (summed in rank order: every rank
+ *                 gets bit-identical scalars). No host or library call on the critical path.
+ * Rendezvous: every rank calls sb_comm_prepare, the SB_COMM_BLOB_BYTES blobs are all-gathered out of
+ * band (bench.py: torch.distributed), every rank calls sb_comm_connect with the world*blob array, and
+ * the ranks synchronise once (a barrier) before the first collective call. */
+#define SB_COMM_NCCL 0
+#define SB_COMM_P2P 1
+#define SB_COMM_BLOB_BYTES 256
+#define SB_COMM_MAX_RANKS 8
+SB_API int sb_comm_prepare(sb_ctx* ctx, int rank, int world, int mode, int64_t vec_capacity, int32_t n_vectors,
+                           void* h_blob /* [SB_COMM_BLOB_BYTES] out */);
+SB_API int sb_comm_connect(sb_ctx* ctx, const void* h_all_blobs /* [world * SB_COMM_BLOB_BYTES] */);
+SB_API int sb_comm_destroy(sb_ctx* ctx);
+/* Device-side error word of the communicator (0 = fine); spin loops that give up set it and trap. */
+SB_API int sb_comm_status(sb_ctx* ctx, uint64_t* h_error);
+/* Distributed operator of this rank: rows for the owned cells of `local`, halo plan on the device.
+ * sb_apply / the fused solvers exchange halos inside the call; x must be a vector of this context
+ * (its halo tail is written by the neighbours). Vectors have n = local->n_owned logical elements. */
+SB_API int sb_dist_op_create(sb_ctx* ctx, const sb_local_mesh* local, const sb_op_desc* desc, sb_op** out);
+
 /* ---- BLAS-1: replaces Bittern's lazy expressions + assignment operators
  * (MatrixMath.hpp:233-301, MatrixTarget.hpp:96-119, MatrixAlgorithms.hpp:95-135) for the vector.
  * An expression is a postfix program over <= SB_EXPR_MAX_VEC vector operands and

@@ -25,7 +25,7 @@ LIB_PATH = os.path.join(HERE, "liboracle.so")
 REF_LIB_PATH = os.path.join(HERE, "_ref", "libref_solvers.so")
 REF_MESH_TOOL = os.path.join(HERE, "_ref", "ref_mesh_tool")
 
-RED_SEQ, RED_TREE = 0, 1
+RED_SEQ, RED_TREE, RED_TREE_SEG = 0, 1, 2
 COL_PAD = -(2**31)
 
 _f64p = C.POINTER(C.c_double)
@@ -103,6 +103,8 @@ def lib():
         L.orc_dot.restype = C.c_double
         L.orc_norm2.argtypes = [C.c_int64, _f64p, C.c_int]
         L.orc_norm2.restype = C.c_double
+        L.orc_set_segments.argtypes = [C.c_int, _i64p]
+        L.orc_set_segments.restype = None
         L.orc_safe_divide.argtypes = [C.c_double, C.c_double]
         L.orc_safe_divide.restype = C.c_double
         for name in ("orc_cg", "orc_bicgstab"):
@@ -263,6 +265,15 @@ class CallbackOp:
     @property
     def callback(self):
         return C.cast(self._cfn, C.c_void_p), C.c_void_p(None)
+
+
+def set_segments(seg_ptr) -> None:
+    """Rank-block boundaries for RED_TREE_SEG (the multi-GPU reduction order)."""
+    seg_ptr = np.ascontiguousarray(seg_ptr, np.int64)
+    lib().orc_set_segments(len(seg_ptr) - 1, _p(seg_ptr, _i64p))
+    if have_ref():  # the compiled reference harness links its own copy of the oracle reductions
+        ref().orc_set_segments.argtypes = [C.c_int, _i64p]
+        ref().orc_set_segments(len(seg_ptr) - 1, _p(seg_ptr, _i64p))
 
 
 def dot(a, b, mode=RED_SEQ) -> float:

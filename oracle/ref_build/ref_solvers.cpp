@@ -98,8 +98,8 @@ struct HostVec final : TargetMatrixInterface<HostVec> {
 // generic Bittern entry points take forwarding references (SURVEY.md 8b "overload hazard").
 inline double ref_dot_impl(const HostVec& a, const HostVec& b) {
   double v;
-  if (g_trace.mode == ORC_RED_TREE) {
-    v = orc_dot((int64_t) a.d.size(), a.d.data(), b.d.data(), ORC_RED_TREE);
+  if (g_trace.mode != ORC_RED_SEQ) {
+    v = orc_dot((int64_t) a.d.size(), a.d.data(), b.d.data(), g_trace.mode);
   } else {
     v = dot_product<const HostVec&, const HostVec&>(a, b); // the reference template
   }
@@ -108,8 +108,8 @@ inline double ref_dot_impl(const HostVec& a, const HostVec& b) {
 }
 inline double ref_norm_impl(const HostVec& a) {
   double v;
-  if (g_trace.mode == ORC_RED_TREE) {
-    v = orc_norm2((int64_t) a.d.size(), a.d.data(), ORC_RED_TREE);
+  if (g_trace.mode != ORC_RED_SEQ) {
+    v = orc_norm2((int64_t) a.d.size(), a.d.data(), g_trace.mode);
   } else {
     v = norm_2<const HostVec&>(a); // the reference template
   }

@@ -248,8 +248,29 @@ static double tree_dot(int64_t n, const double* a, const double* b) {
   return total;
 }
 
+/* ORC_RED_TREE_SEG: the multi-GPU reduction. The vector is the concatenation of the ranks' owned
+ * blocks (segment r = rank r's cells in its local order); each rank reduces its block with SB_TREE v1
+ * (tiles restart at the block start) and the rank sums are added in rank order 0..P-1
+ * (sb_comm.cuh: allreduce_p2p). */
+static int g_n_seg = 0;
+static int64_t g_seg_ptr[65];
+
+void orc_set_segments(int n_seg, const int64_t* seg_ptr) {
+  g_n_seg = n_seg < 64 ? n_seg : 64;
+  for (int k = 0; k <= g_n_seg; ++k) g_seg_ptr[k] = seg_ptr[k];
+}
+
+static double seg_tree_dot(int64_t n, const double* a, const double* b) {
+  if (g_n_seg <= 0 || g_seg_ptr[g_n_seg] != n) return tree_dot(n, a, b);
+  double total = tree_dot(g_seg_ptr[1] - g_seg_ptr[0], a + g_seg_ptr[0], b + g_seg_ptr[0]);
+  for (int r = 1; r < g_n_seg; ++r)
+    total = total + tree_dot(g_seg_ptr[r + 1] - g_seg_ptr[r], a + g_seg_ptr[r], b + g_seg_ptr[r]);
+  return total;
+}
+
 double orc_dot(int64_t n, const double* a, const double* b, int mode) {
   if (mode == ORC_RED_TREE) return tree_dot(n, a, b);
+  if (mode == ORC_RED_TREE_SEG) return seg_tree_dot(n, a, b);
   double init = 0.0;
   for (int64_t i = 0; i < n; ++i) init = init + a[i] * b[i];
   return init;

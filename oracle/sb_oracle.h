@@ -38,8 +38,11 @@ extern "C" {
 /* Reduction order used by dot/norm. */
 enum {
   ORC_RED_SEQ = 0,  /* the reference's order: left-to-right from 0.0 (MatrixAlgorithms.hpp:191-205) */
-  ORC_RED_TREE = 1  /* the GPU's fixed tree ("SB_TREE v1"), restated on the CPU */
+  ORC_RED_TREE = 1, /* the GPU's fixed tree ("SB_TREE v1"), restated on the CPU */
+  ORC_RED_TREE_SEG = 2 /* multi-GPU: SB_TREE v1 per rank block, rank sums added in rank order */
 };
+/* Segment boundaries for ORC_RED_TREE_SEG: seg_ptr[0..n_seg], seg_ptr[n_seg] = vector length. */
+void orc_set_segments(int n_seg, const int64_t* seg_ptr);
 
 /* Padding / ghost encodings of the ELL column array (shared with the product's documented layout). */
 #define ORC_COL_PAD INT32_MIN

@@ -19,8 +19,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libstormb200.so")
-SOURCES = ["sb_api.cu", "sb_op.cu", "sb_solvers.cu", "sb_mesh_host.cpp"]
-HEADERS = [os.path.join(CSRC, h) for h in ("sb_common.cuh", "sb_kernels.cuh", "sb_op.cuh")] + \
+SOURCES = ["sb_api.cu", "sb_op.cu", "sb_solvers.cu", "sb_comm.cu", "sb_mesh_host.cpp", "sb_part_host.cpp"]
+METIS = "/usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a"  # ships with the CUDA toolkit
+HEADERS = [os.path.join(CSRC, h) for h in ("sb_common.cuh", "sb_kernels.cuh", "sb_op.cuh", "sb_comm.cuh")] + \
     [os.path.join(HERE, "..", "include", "stormb200.h"), os.path.abspath(__file__)]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -56,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         list(ex.map(lambda s: _compile(s, verbose), todo))
     objs = [os.path.join(OBJ, os.path.splitext(s)[0] + ".o") for s in SOURCES]
     if todo or _stale(LIB, objs):
-        res = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-lpthread"], capture_output=True, text=True)
+        res = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + [METIS, "-lpthread", "-ldl"], capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError("link of libstormb200.so failed")

@@ -13,6 +13,9 @@ LIB_PATH = os.path.join(HERE, "libstormb200.so")
 
 SB_OK = 0
 FORM_FAITHFUL, FORM_COEF = 0, 1
+PART_METIS, PART_SLAB = 0, 1
+COMM_NCCL, COMM_P2P = 0, 1
+COMM_BLOB_BYTES = 256
 ASSIGN, ADD_ASSIGN, SUB_ASSIGN, MUL_ASSIGN, DIV_ASSIGN = range(5)
 OP_VEC0, OP_SCAL0 = 0, 8
 OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG = 16, 17, 18, 19, 20
@@ -28,6 +31,23 @@ class MeshSoa(C.Structure):
                 ("face_area", f64p), ("face_dist", f64p), ("cell_vol", f64p),
                 ("n_bfaces", C.c_int64), ("bface_cell", i32p), ("bface_area", f64p),
                 ("bface_dist", f64p)]
+
+
+i64p = C.POINTER(C.c_int64)
+
+
+class PartInfo(C.Structure):
+    _fields_ = [("n_parts", C.c_int32), ("n_cells", C.c_int64), ("edge_cut", C.c_int64),
+                ("max_owned", C.c_int64), ("min_owned", C.c_int64), ("max_halo", C.c_int64),
+                ("vec_capacity", C.c_int64)]
+
+
+class LocalMesh(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("n_parts", C.c_int32), ("n_owned", C.c_int64),
+                ("n_interior", C.c_int64), ("n_halo", C.c_int64), ("halo_base", C.c_int64),
+                ("local_to_global", i32p), ("soa", MeshSoa), ("face_global", i64p),
+                ("n_nbr", C.c_int32), ("nbr_rank", i32p), ("send_ptr", i64p), ("send_idx", i32p),
+                ("recv_ptr", i64p), ("send_dst", i64p)]
 
 
 class OpDesc(C.Structure):
@@ -84,6 +104,17 @@ SIGNATURES = {
     "sb_mesh_get_soa": (C.c_int, [C.c_void_p, C.POINTER(MeshSoa)]),
     "sb_mesh_cell_centers": (C.c_int, [C.c_void_p, f64p]),
     "sb_mesh_bandwidth": (C.c_int64, [C.c_void_p]),
+    "sb_part_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, vpp]),
+    "sb_part_from_array": (C.c_int, [C.c_void_p, C.c_int, i32p, vpp]),
+    "sb_part_destroy": (C.c_int, [C.c_void_p]),
+    "sb_part_get_info": (C.c_int, [C.c_void_p, C.POINTER(PartInfo)]),
+    "sb_part_get_array": (C.c_int, [C.c_void_p, C.POINTER(i32p)]),
+    "sb_part_local": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(LocalMesh)]),
+    "sb_comm_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int32, C.c_void_p]),
+    "sb_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "sb_comm_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "sb_dist_op_create": (C.c_int, [C.c_void_p, C.POINTER(LocalMesh), C.POINTER(OpDesc), vpp]),
     "sb_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Expr)]),
     "sb_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double]),
     "sb_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

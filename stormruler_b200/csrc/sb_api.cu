@@ -65,7 +65,9 @@ int sb_ctx_destroy(sb_ctx* ctx) {
   if (ctx == nullptr) return SB_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (double* w : ctx->work) cudaFree(w);
+  for (double* w : ctx->work) vec_free(ctx, w);
+  ctx->work.clear();
+  comm_teardown(ctx);
   cudaFree(ctx->d_state);
   cudaFree(ctx->d_hist);
   cudaFree(ctx->d_trace);
@@ -91,21 +93,12 @@ int64_t sb_ctx_launch_count(sb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 // ---- vectors ------------------------------------------------------------------------------------
 int sb_vec_alloc(sb_ctx* ctx, size_t n, double** d_out) {
   SB_REQUIRE(ctx != nullptr && d_out != nullptr, "null argument");
-  *d_out = nullptr;
-  const int64_t cap = pad_up((int64_t) n > 0 ? (int64_t) n : 1);
-  double* d = nullptr;
-  SB_CUDA(cudaMalloc(&d, sizeof(double) * cap));
-  SB_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * cap, ctx->stream));
-  *d_out = d;
-  return SB_OK;
+  return vec_alloc(ctx, n, d_out);
 }
 
 int sb_vec_free(sb_ctx* ctx, double* d) {
   SB_REQUIRE(ctx != nullptr, "ctx is null");
-  if (d == nullptr) return SB_OK;
-  SB_CUDA(cudaStreamSynchronize(ctx->stream));
-  SB_CUDA(cudaFree(d));
-  return SB_OK;
+  return vec_free(ctx, d);
 }
 
 int sb_vec_upload(sb_ctx* ctx, double* d, const double* h_src, size_t n) {

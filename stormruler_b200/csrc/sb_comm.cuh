@@ -1,0 +1,169 @@
+// sb_comm.cuh -- device side of the multi-GPU path: NVLink peer stores, sequence flags, and the
+// in-kernel all-reduce (DESIGN.md "Multi-GPU").
+//
+// P2P protocol (all state lives in each rank's CommCtrl, written by peers over NVLink):
+//   halo exchange, apply #s on every rank:
+//     pack kernel:   block 0 first tells each neighbour "I have finished reading the halos of apply
+//                    #s-1" (ack_flag, true by stream order); every CTA waits until each neighbour has
+//                    acked #s-1 (its halo tail may be overwritten), stores its share of boundary
+//                    values straight into the neighbours' halo tails, fences; the last CTA (ticket)
+//                    release-stores halo_flag[me] = s at every neighbour and bumps apply_seq.
+//     apply kernel:  CTAs of boundary tiles acquire halo_flag[q] >= apply_seq for every neighbour q
+//                    before their first gather; interior tiles (scheduled first) never wait.
+//   all-reduce #a (inside the one-CTA final-reduce kernel): thread (r, d) stores local sum d into
+//     rank r's mailbox ar_slot[a&1][me][d]; then spins on its own mailbox [a&1][r][d] until the value
+//     differs from the NaN sentinel, resets it, and thread 0 adds the P values in rank order.
+//     Two parities suffice: a rank can start all-reduce #a+2 only after every peer contributed to
+//     #a+1, i.e. after every peer has read (and reset) its #a mailboxes.
+// Every spin loop is bounded (SB_SPIN_TIMEOUT_NS, default 20 s): on expiry the kernel records the
+// reason in CommCtrl::error and traps, so a lost peer fails loudly instead of hanging the GPU.
+#pragma once
+
+#include "sb_common.cuh"
+
+namespace sb {
+
+constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+struct HaloDev {
+  int32_t n_nbr = 0;               // 0: operator is not distributed
+  int32_t first_boundary_tile = 0; // row tiles >= this one contain boundary cells
+  int32_t nbr_rank[kMaxRanks] = {};
+  int64_t send_ptr[kMaxRanks + 1] = {};
+  int64_t send_dst[kMaxRanks] = {}; // element offset inside neighbour k's vector
+  const int32_t* send_idx = nullptr; // device
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+static __device__ __noinline__ void comm_fail(CommCtrl* ctrl, unsigned long long code) {
+  ctrl->error = code;
+  __threadfence_system();
+  __trap();
+}
+
+// Spin until *flag >= want (acquire).
+__device__ __forceinline__ void wait_flag_ge(const unsigned long long* flag, unsigned long long want, CommCtrl* ctrl,
+                                             unsigned long long code) {
+  if (ld_acquire_sys(flag) >= want) return;
+  const unsigned long long t0 = globaltimer_ns();
+  while (ld_acquire_sys(flag) < want) {
+    __nanosleep(64);
+    if (globaltimer_ns() - t0 > kSpinTimeoutNs) comm_fail(ctrl, code);
+  }
+}
+
+// ---- halo pack, P2P: boundary values go straight into the neighbours' halo tails -------------------
+// x_off: byte offset of the vector inside the slab (identical on every rank).
+static __global__ void __launch_bounds__(kThreads) halo_pack_p2p_kernel(CommDev comm, HaloDev halo, const double* __restrict__ x,
+                                                                 int64_t x_off, const int* __restrict__ done) {
+  if (done != nullptr && *done != 0) return;
+  CommCtrl* me = comm.ctrl(comm.rank);
+  const unsigned long long seq = me->apply_seq + 1; // this apply's number (bumped by the last CTA below)
+  if (blockIdx.x == 0 && threadIdx.x < halo.n_nbr) {
+    // stream order: every earlier apply of this rank has completed -> its halos are free to overwrite
+    st_release_sys(&comm.ctrl(halo.nbr_rank[threadIdx.x])->ack_flag[comm.rank], seq - 1);
+  }
+  if (threadIdx.x < halo.n_nbr)
+    wait_flag_ge(&me->ack_flag[halo.nbr_rank[threadIdx.x]], seq - 1, me, 0xA000 + threadIdx.x);
+  __syncthreads();
+  const int64_t total = halo.send_ptr[halo.n_nbr];
+  for (int64_t i = (int64_t) blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t) gridDim.x * kThreads) {
+    int k = 0;
+#pragma unroll
+    for (int q = 1; q < kMaxRanks; ++q) k += (q < halo.n_nbr && i >= halo.send_ptr[q]) ? 1 : 0;
+    double* dst = reinterpret_cast<double*>(comm.base[halo.nbr_rank[k]] + x_off) + halo.send_dst[k] + (i - halo.send_ptr[k]);
+    *dst = x[halo.send_idx[i]];
+  }
+  __threadfence_system(); // my peer stores are performed before the ticket below is taken
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long ticket = atomicAdd(&me->pack_ticket, 1ull);
+    if (ticket == (unsigned long long) gridDim.x - 1) {
+      me->pack_ticket = 0;
+      __threadfence_system();
+      for (int k = 0; k < halo.n_nbr; ++k) st_release_sys(&comm.ctrl(halo.nbr_rank[k])->halo_flag[comm.rank], seq);
+      me->apply_seq = seq;
+    }
+  }
+}
+
+// NCCL mode: gather into a contiguous local send buffer.
+static __global__ void __launch_bounds__(kThreads) halo_pack_local_kernel(HaloDev halo, const double* __restrict__ x,
+                                                                   double* __restrict__ sendbuf,
+                                                                   const int* __restrict__ done) {
+  if (done != nullptr && *done != 0) return;
+  const int64_t total = halo.send_ptr[halo.n_nbr];
+  for (int64_t i = (int64_t) blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t) gridDim.x * kThreads)
+    sendbuf[i] = x[halo.send_idx[i]];
+}
+
+// Called by the CTAs of boundary tiles before their first gather (P2P mode).
+__device__ __forceinline__ void halo_wait(const CommDev& comm, const HaloDev& halo) {
+  CommCtrl* me = comm.ctrl(comm.rank);
+  if (threadIdx.x < halo.n_nbr)
+    wait_flag_ge(&me->halo_flag[halo.nbr_rank[threadIdx.x]], me->apply_seq, me, 0xB000 + threadIdx.x);
+  __syncthreads();
+}
+
+// ---- in-kernel all-reduce (P2P), called by all threads of the one-CTA final-reduce kernel ----------
+// `sums` valid in thread 0 on entry and on exit (rank-ordered total, bit-identical on every rank).
+template<int ND>
+__device__ __forceinline__ void allreduce_p2p(const CommDev& comm, double (&sums)[ND]) {
+  __shared__ double s_local[ND];
+  __shared__ double s_all[kMaxRanks][ND];
+  CommCtrl* me = comm.ctrl(comm.rank);
+  const unsigned long long par = me->ar_seq & 1ull;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int d = 0; d < ND; ++d) s_local[d] = sums[d];
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < comm.world * ND) {
+    const int r = t / ND, d = t % ND;
+    st_relaxed_sys(&comm.ctrl(r)->ar_slot[par][comm.rank][d], (unsigned long long) __double_as_longlong(s_local[d]));
+    unsigned long long* box = &me->ar_slot[par][r][d];
+    unsigned long long v = ld_relaxed_sys(box);
+    if (v == kArSentinel) {
+      const unsigned long long t0 = globaltimer_ns();
+      while ((v = ld_relaxed_sys(box)) == kArSentinel) {
+        if (globaltimer_ns() - t0 > kSpinTimeoutNs) comm_fail(me, 0xC000 + r);
+      }
+    }
+    st_relaxed_sys(box, kArSentinel);
+    s_all[r][d] = __longlong_as_double((long long) v);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      double tot = s_all[0][d];
+      for (int r = 1; r < comm.world; ++r) tot = __dadd_rn(tot, s_all[r][d]);
+      sums[d] = tot;
+    }
+    me->ar_seq = me->ar_seq + 1;
+  }
+}
+
+} // namespace sb

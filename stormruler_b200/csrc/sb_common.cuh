@@ -53,6 +53,37 @@ void set_error(const char* fmt, ...);
     if (_rc != SB_OK) return _rc; \
   } while (0)
 
+// ---- multi-GPU communicator (sb_comm.cu) ---------------------------------------------------------
+// One process per GPU. Every rank allocates ONE slab: a control block followed by a pool of
+// equally sized vector blocks. In P2P mode the slab is exported with CUDA IPC and mapped by every
+// peer, so a vector at offset o in my slab lives at offset o in each peer's slab ("symmetric" as long
+// as all ranks allocate in the same order, which SPMD solver code does) and kernels can store
+// straight into a neighbour's halo tail over NVLink.
+constexpr int kMaxRanks = 8;
+constexpr size_t kCtrlBytes = 64 * 1024;
+constexpr unsigned long long kArSentinel = 0xFFF8DEADBEEF0001ull; // a NaN payload arithmetic never produces
+
+// Control block at the start of every rank's slab (8-byte words; written by peers over NVLink).
+struct CommCtrl {
+  unsigned long long halo_flag[kMaxRanks]; // [src]: halo values of apply #seq from rank src have landed
+  unsigned long long ack_flag[kMaxRanks];  // [src]: rank src has finished reading the halos of apply #seq
+  unsigned long long apply_seq;            // applies issued so far by this rank (device-side: graph replay safe)
+  unsigned long long ar_seq;               // all-reduces completed so far by this rank
+  unsigned long long pack_ticket;          // last-CTA detection of the pack kernel
+  unsigned long long error;                // set before a spin loop gives up
+  unsigned long long pad[4];
+  unsigned long long ar_slot[2][kMaxRanks][4]; // all-reduce mailboxes (value is the flag), by seq parity
+};
+static_assert(sizeof(CommCtrl) <= kCtrlBytes, "control block too large");
+
+// What kernels need to reach the peers (passed by value).
+struct CommDev {
+  int32_t rank = 0, world = 1, mode = -1; // mode: -1 none, SB_COMM_NCCL, SB_COMM_P2P
+  int32_t pad = 0;
+  unsigned char* base[kMaxRanks] = {};    // mapped slab of every rank (base[rank] = my own)
+  __host__ __device__ CommCtrl* ctrl(int r) const { return reinterpret_cast<CommCtrl*>(base[r]); }
+};
+
 // Device-resident reduction scratch: per-tile partial sums and the output slots.
 struct RedScratch {
   double* partials = nullptr; // [kMaxDots][cap_tiles]
@@ -79,8 +110,23 @@ struct sb_ctx {
   double* d_trace = nullptr;
   int64_t trace_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // multi-GPU (sb_comm.cu); comm.mode < 0: single GPU
+  sb::CommDev comm;
+  unsigned char* slab = nullptr;
+  size_t slab_bytes = 0;
+  int64_t vec_capacity = 0; // doubles per pool block
+  std::vector<double*> pool_free; // LIFO free list of pool blocks
+  int32_t pool_blocks = 0;
+  void* nccl = nullptr;           // ncclComm_t
+  double* d_ar = nullptr;         // NCCL mode: all-reduce staging [4]
+  double* d_sendbuf = nullptr;    // NCCL mode: packed halo values
+  int64_t sendbuf_cap = 0;
 };
 
 namespace sb {
 int ensure_red_scratch(sb_ctx* ctx, int64_t n);
+// vector storage: pool block in multi-GPU mode, cudaMalloc otherwise (zero-filled either way)
+int vec_alloc(sb_ctx* ctx, size_t n, double** out);
+int vec_free(sb_ctx* ctx, double* d);
+int comm_teardown(sb_ctx* ctx);
 } // namespace sb

@@ -11,7 +11,7 @@
 // x86-64) rounds every operation separately.
 #pragma once
 
-#include "sb_common.cuh"
+#include "sb_comm.cuh"
 
 namespace sb {
 
@@ -70,7 +70,7 @@ __device__ __forceinline__ void block_reduce_partials(double (&acc)[ND], const R
 // sequential), butterfly per warp, the 8 warp sums added left to right. `fin(sums)` then runs on one
 // thread: that is where the solver scalars (alpha, beta, residual, stop flag) are updated.
 template<int ND, class Final>
-__global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles, RedPtrs red, Final fin,
+__global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles, RedPtrs red, Final fin, CommDev comm,
                                                                 const int* __restrict__ done) {
   if (done != nullptr && *done != 0) return;
   __shared__ double s_w[ND][kWarps];
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles,
     if (lane == 0) s_w[d][warp] = v;
   }
   __syncthreads();
+  double sums[ND];
   if (threadIdx.x == 0) {
-    double sums[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       double t = s_w[d][0];
@@ -114,15 +114,48 @@ __global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles,
       for (int w = 1; w < kWarps; ++w) t = __dadd_rn(t, s_w[d][w]);
       sums[d] = t;
     }
-    fin(sums);
   }
+  // multi-GPU, P2P mode: exchange the rank sums with every peer inside this kernel (rank-ordered total)
+  if (comm.mode == SB_COMM_P2P && comm.world > 1) allreduce_p2p<ND>(comm, sums);
+  if (threadIdx.x == 0) fin(sums);
 }
+
+template<int M>
+struct StoreFinal {
+  double* out;
+  __device__ void operator()(const double* sums) const {
+#pragma unroll
+    for (int k = 0; k < M; ++k) out[k] = sums[k];
+  }
+};
+
+// NCCL mode: the solver's scalar update runs after ncclAllReduce has combined the rank sums.
+template<int ND, class Final>
+__global__ void scalar_final_kernel(const double* __restrict__ sums, Final fin, const int* __restrict__ done) {
+  if (done != nullptr && *done != 0) return;
+  double s[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) s[d] = sums[d];
+  fin(s);
+}
+
+int nccl_allreduce_sum(sb_ctx* ctx, double* d_buf, int count); // sb_comm.cu
 
 // Launch helper shared by all reducing kernels: the one-CTA final stage, right behind the producer.
 template<int ND, class Final>
 inline int launch_final(sb_ctx* ctx, int64_t n, const Final& fin, const int* done) {
   const RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
-  final_reduce_kernel<ND, Final><<<1, kThreads, 0, ctx->stream>>>(num_tiles(n), red, fin, done);
+  if (ctx->comm.mode == SB_COMM_NCCL && ctx->comm.world > 1) {
+    final_reduce_kernel<ND, StoreFinal<ND>>
+        <<<1, kThreads, 0, ctx->stream>>>(num_tiles(n), red, StoreFinal<ND>{ctx->d_ar}, CommDev{}, done);
+    SB_CUDA(cudaGetLastError());
+    SB_TRY(nccl_allreduce_sum(ctx, ctx->d_ar, ND));
+    scalar_final_kernel<ND, Final><<<1, 1, 0, ctx->stream>>>(ctx->d_ar, fin, done);
+    ctx->launches += 2;
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+  }
+  final_reduce_kernel<ND, Final><<<1, kThreads, 0, ctx->stream>>>(num_tiles(n), red, fin, ctx->comm, done);
   ctx->launches++;
   SB_CUDA(cudaGetLastError());
   return SB_OK;
@@ -263,15 +296,6 @@ struct DotBody {
 #pragma unroll
     for (int k = 0; k < M; ++k)
       acc_pair(acc[k], e0, n, __dmul_rn(r.a[k].x, r.b[k].x), __dmul_rn(r.a[k].y, r.b[k].y));
-  }
-};
-
-template<int M>
-struct StoreFinal {
-  double* out;
-  __device__ void operator()(const double* sums) const {
-#pragma unroll
-    for (int k = 0; k < M; ++k) out[k] = sums[k];
   }
 };
 

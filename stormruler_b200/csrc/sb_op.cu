@@ -21,12 +21,14 @@ struct HostRows {
   std::vector<double> v0, v1, diag;
 };
 
-int build_rows(const sb_mesh_soa* m, const sb_op_desc* desc, HostRows& R) {
+// n_rows: rows are built for cells [0, n_rows) only (distributed operator: the owned cells; columns
+// may reference any cell < n_cells, i.e. the halo tail). n_rows == n_cells on a single GPU.
+int build_rows(const sb_mesh_soa* m, const sb_op_desc* desc, int64_t n_rows, HostRows& R) {
   const int64_t n = m->n_cells, F = m->n_faces, B = m->n_bfaces;
   for (int64_t f = 0; f < 2 * F; ++f)
     SB_REQUIRE(m->face_cell[f] >= 0 && m->face_cell[f] < n, "face_cell index out of range");
   for (int64_t b = 0; b < B; ++b)
-    SB_REQUIRE(m->bface_cell[b] >= 0 && m->bface_cell[b] < n, "bface_cell index out of range");
+    SB_REQUIRE(m->bface_cell[b] >= 0 && m->bface_cell[b] < n_rows, "bface_cell index out of range");
   const bool coef = desc->form == SB_FORM_COEF;
   // degrees: interior entries, plus ghost entries in the faithful form
   std::vector<int32_t> deg((size_t) n + 1, 0);
@@ -34,8 +36,8 @@ int build_rows(const sb_mesh_soa* m, const sb_op_desc* desc, HostRows& R) {
   if (!coef)
     for (int64_t b = 0; b < B; ++b) deg[m->bface_cell[b]]++;
   int32_t width = 1;
-  for (int64_t i = 0; i < n; ++i) width = std::max(width, deg[i]);
-  const int64_t ld = pad_up(n);
+  for (int64_t i = 0; i < n_rows; ++i) width = std::max(width, deg[i]);
+  const int64_t ld = pad_up(n_rows);
   R.width = width, R.ld = ld, R.entries = 0;
   R.col.assign((size_t) width * ld, kColPad);
   R.v0.assign((size_t) width * ld, 0.0);
@@ -44,8 +46,9 @@ int build_rows(const sb_mesh_soa* m, const sb_op_desc* desc, HostRows& R) {
   std::vector<int32_t> fill((size_t) n + 1, 0);
   const double dt = desc->dt;
   if (coef)
-    for (int64_t i = 0; i < n; ++i) R.diag[i] = desc->prefill ? 1.0 : 0.0;
+    for (int64_t i = 0; i < n_rows; ++i) R.diag[i] = desc->prefill ? 1.0 : 0.0;
   auto put = [&](int32_t row, int32_t c, double area, double dist) {
+    if (row >= n_rows) return; // a halo cell: its row lives on the owning rank
     const int64_t e = (int64_t) fill[row] * ld + row;
     if (coef) {
       const double a = ((area / m->cell_vol[row]) * dt) / dist;
@@ -89,9 +92,10 @@ int upload(sb_ctx* ctx, const std::vector<T>& h, void** d_out, int64_t& bytes) {
 
 extern "C" {
 
-int sb_op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, sb_op** out) {
+static int op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, int64_t n_rows, sb_op** out) {
   SB_REQUIRE(ctx != nullptr && m != nullptr && desc != nullptr && out != nullptr, "null argument");
   *out = nullptr;
+  SB_REQUIRE(n_rows > 0 && n_rows <= m->n_cells, "row count out of range");
   SB_REQUIRE(m->n_cells > 0 && m->n_cells < (int64_t) INT32_MAX - kTile, "n_cells out of range (int32 indices)");
   SB_REQUIRE(m->n_faces >= 0 && m->n_bfaces >= 0, "negative face count");
   SB_REQUIRE(m->n_faces == 0 || (m->face_cell && m->face_area && m->face_dist), "null face arrays");
@@ -103,10 +107,10 @@ int sb_op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, sb_o
   // subtracts interior coefficients and ghost terms in row order (interior first, then ghosts),
   // which is exactly the order of the two loops in build_rows.
   HostRows R;
-  SB_TRY(build_rows(m, desc, R));
+  SB_TRY(build_rows(m, desc, n_rows, R));
   SB_REQUIRE(R.width <= 8, "cells with more than 8 faces are not supported yet");
   std::unique_ptr<sb_op> op(new sb_op());
-  op->d.n = m->n_cells, op->d.ld = R.ld, op->d.width = R.width, op->d.form = desc->form;
+  op->d.n = n_rows, op->d.ld = R.ld, op->d.width = R.width, op->d.form = desc->form;
   op->d.prefill = desc->prefill, op->d.dt = desc->dt;
   op->n_entries = R.entries;
   if (const char* dbg = std::getenv("SB_DEBUG")) op->d.debug = std::atoi(dbg);
@@ -149,11 +153,52 @@ int sb_op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, sb_o
   return SB_OK;
 }
 
+int sb_op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, sb_op** out) {
+  SB_REQUIRE(m != nullptr, "null argument");
+  return op_create(ctx, m, desc, m->n_cells, out);
+}
+
+int sb_dist_op_create(sb_ctx* ctx, const sb_local_mesh* loc, const sb_op_desc* desc, sb_op** out) {
+  SB_REQUIRE(ctx != nullptr && loc != nullptr && desc != nullptr && out != nullptr, "null argument");
+  *out = nullptr;
+  if (ctx->comm.mode < 0) {
+    set_error("sb_dist_op_create needs a communicator (sb_comm_prepare / sb_comm_connect)");
+    return SB_ERR_STATE;
+  }
+  SB_REQUIRE(loc->rank == ctx->comm.rank && loc->n_parts == ctx->comm.world, "local mesh belongs to another rank / world size");
+  SB_REQUIRE(loc->n_nbr >= 0 && loc->n_nbr < kMaxRanks, "too many neighbours");
+  SB_REQUIRE(loc->halo_base == pad_up(loc->n_owned) && loc->soa.n_cells == loc->halo_base + loc->n_halo, "local mesh layout");
+  SB_REQUIRE(loc->halo_base + loc->n_halo <= ctx->vec_capacity, "local vector does not fit the pool block (vec_capacity)");
+  sb_op* op = nullptr;
+  SB_TRY(op_create(ctx, &loc->soa, desc, loc->n_owned, &op));
+  op->distributed = true;
+  op->halo_base = loc->halo_base, op->n_halo = loc->n_halo;
+  HaloDev& h = op->halo;
+  h.n_nbr = loc->n_nbr;
+  h.first_boundary_tile = (int32_t) (loc->n_interior / kTile);
+  const int64_t total = loc->n_nbr > 0 ? loc->send_ptr[loc->n_nbr] : 0;
+  for (int k = 0; k < loc->n_nbr; ++k) {
+    h.nbr_rank[k] = loc->nbr_rank[k], h.send_dst[k] = loc->send_dst[k];
+    SB_REQUIRE(loc->nbr_rank[k] >= 0 && loc->nbr_rank[k] < ctx->comm.world && loc->nbr_rank[k] != ctx->comm.rank, "bad neighbour rank");
+  }
+  for (int k = 0; k <= loc->n_nbr; ++k) h.send_ptr[k] = loc->send_ptr[k], op->recv_ptr[k] = loc->recv_ptr[k];
+  for (int64_t i = 0; i < total; ++i)
+    SB_REQUIRE(loc->send_idx[i] >= 0 && loc->send_idx[i] < loc->n_owned, "send_idx out of range");
+  if (total > 0) {
+    SB_CUDA(cudaMalloc(&op->d_send_idx, sizeof(int32_t) * (size_t) total));
+    SB_CUDA(cudaMemcpy(op->d_send_idx, loc->send_idx, sizeof(int32_t) * (size_t) total, cudaMemcpyHostToDevice));
+  }
+  h.send_idx = op->d_send_idx;
+  *out = op;
+  return SB_OK;
+}
+
 int sb_op_destroy(sb_ctx* ctx, sb_op* op) {
   SB_REQUIRE(ctx != nullptr, "ctx is null");
   if (op == nullptr) return SB_OK;
   SB_CUDA(cudaStreamSynchronize(ctx->stream));
   for (void* b : op->buffers) cudaFree(b);
+  cudaFree(op->d_send_idx);
   delete op;
   return SB_OK;
 }

@@ -37,6 +37,29 @@ struct OpDev {
   int32_t debug = 0; // experiments only (SB_DEBUG env): bit0 = skip the gathers
 };
 
+// Multi-GPU (P2P mode): what the apply kernel needs to wait for its halo. n_nbr == 0: no waiting.
+struct ApplyDist {
+  CommCtrl* ctrl = nullptr;        // this rank's control block
+  int32_t n_nbr = 0;
+  int32_t first_boundary_tile = 0; // row tiles >= this one contain boundary cells (they read the halo)
+  int32_t nbr_rank[kMaxRanks] = {};
+  int32_t coherent_gather = 0;     // 1: gather x with ld.global.ca instead of the read-only path
+};
+
+__device__ __forceinline__ void apply_halo_wait(const ApplyDist& ad) {
+  if (ad.n_nbr > 0 && (int) blockIdx.x >= ad.first_boundary_tile) {
+    if (threadIdx.x < ad.n_nbr)
+      wait_flag_ge(&ad.ctrl->halo_flag[ad.nbr_rank[threadIdx.x]], ad.ctrl->apply_seq, ad.ctrl, 0xB000 + threadIdx.x);
+    __syncthreads();
+  }
+}
+
+// Gathered x: read-only path on one GPU; in P2P mode the halo tail is written by peers while the
+// kernel runs, so the coherent path is used (the flag acquire above orders it).
+__device__ __forceinline__ double gather(const double* p, int coherent) {
+  return coherent ? __ldca(p) : __ldg(p);
+}
+
 // Epilogues fuse dot products into the apply: they see the input pair x[e0..e0+1] and the freshly
 // computed output pair, so <x,Ax>-style reductions cost no extra vector pass.
 struct NoEpi {
@@ -99,7 +122,8 @@ struct EpiResidual {
 };
 
 template<int FORM, int W>
-__device__ __forceinline__ double2 apply_rows(const OpDev& op, const double* __restrict__ x, int64_t e0, double2 xo) {
+__device__ __forceinline__ double2 apply_rows(const OpDev& op, const double* __restrict__ x, int64_t e0, double2 xo,
+                                              int coh) {
   const int64_t h = e0 >> 1, ldh = op.ld >> 1;
   const int2* __restrict__ col2 = reinterpret_cast<const int2*>(op.col);
   const double2* __restrict__ a2 = reinterpret_cast<const double2*>(op.v0);
@@ -113,8 +137,8 @@ __device__ __forceinline__ double2 apply_rows(const OpDev& op, const double* __r
     double g0[W], g1[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) {
-      g0[k] = (c[k].x >= 0) ? __ldg(x + c[k].x) : 0.0;
-      g1[k] = (c[k].y >= 0) ? __ldg(x + c[k].y) : 0.0;
+      g0[k] = (c[k].x >= 0) ? gather(x + c[k].x, coh) : 0.0;
+      g1[k] = (c[k].y >= 0) ? gather(x + c[k].y, coh) : 0.0;
     }
     double u0 = __dmul_rn(dg.x, xo.x), u1 = __dmul_rn(dg.y, xo.y);
 #pragma unroll
@@ -134,8 +158,8 @@ __device__ __forceinline__ double2 apply_rows(const OpDev& op, const double* __r
 #pragma unroll
     for (int k = 0; k < W; ++k) {
       // ghost entry (col == ~i): mirror state -x[i]; padding: skipped below
-      g0[k] = (c[k].x >= 0) ? __ldg(x + c[k].x) : -xo.x;
-      g1[k] = (c[k].y >= 0) ? __ldg(x + c[k].y) : -xo.y;
+      g0[k] = (c[k].x >= 0) ? gather(x + c[k].x, coh) : -xo.x;
+      g1[k] = (c[k].y >= 0) ? gather(x + c[k].y, coh) : -xo.y;
     }
     double u0 = op.prefill ? xo.x : 0.0, u1 = op.prefill ? xo.y : 0.0;
 #pragma unroll
@@ -156,8 +180,10 @@ __device__ __forceinline__ double2 apply_rows(const OpDev& op, const double* __r
 // y <- A x with a fused reduction epilogue. RESID: store b - A x instead (and reduce <r,r>).
 template<int FORM, int W, int ND, bool RESID, class Epi>
 __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double* __restrict__ x, double* __restrict__ y,
-                                                         Epi epi, RedPtrs red, const int* __restrict__ done) {
+                                                         Epi epi, RedPtrs red, ApplyDist ad,
+                                                         const int* __restrict__ done) {
   if (done != nullptr && *done != 0) return;
+  apply_halo_wait(ad);
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
   for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
@@ -167,7 +193,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double*
     const double2 xo = ld2(x, e0);
     typename Epi::Regs er;
     epi.load(e0, er);
-    double2 out = apply_rows<FORM, W>(op, x, e0, xo);
+    double2 out = apply_rows<FORM, W>(op, x, e0, xo, ad.coherent_gather);
     if constexpr (RESID) {
       out.x = __dsub_rn(er.b.x, out.x);
       out.y = __dsub_rn(er.b.y, out.y);
@@ -237,7 +263,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 template<int W, int ND, bool RESID, class Epi>
 __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const double* __restrict__ x,
                                                             double* __restrict__ y, Epi epi, RedPtrs red,
-                                                            const int* __restrict__ done) {
+                                                            ApplyDist ad, const int* __restrict__ done) {
   using L = StageLayout<W, Epi::kExtra>;
   extern __shared__ __align__(128) unsigned char sb_smem[];
   __shared__ __align__(8) uint64_t bars[kWarps][kStages];
@@ -266,6 +292,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     for (int j = 0; j < kStages; ++j) issue(j);
   }
   __syncwarp();
+  apply_halo_wait(ad); // the streamed operands are already in flight while boundary tiles wait
 
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
@@ -297,8 +324,8 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     } else {
 #pragma unroll
       for (int k = 0; k < W; ++k) {
-        g0[k] = (c[k].x >= 0) ? __ldg(x + c[k].x) : 0.0;
-        g1[k] = (c[k].y >= 0) ? __ldg(x + c[k].y) : 0.0;
+        g0[k] = (c[k].x >= 0) ? gather(x + c[k].x, ad.coherent_gather) : 0.0;
+        g1[k] = (c[k].y >= 0) ? gather(x + c[k].y, ad.coherent_gather) : 0.0;
       }
     }
     double u0 = __dmul_rn(dg.x, xo.x), u1 = __dmul_rn(dg.y, xo.y);
@@ -329,6 +356,12 @@ struct sb_op {
   int64_t n_entries = 0;
   int64_t device_bytes = 0;
   void* buffers[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // distributed operator (sb_dist_op_create): halo plan; halo.n_nbr == 0 otherwise
+  sb::HaloDev halo;
+  int64_t halo_base = 0, n_halo = 0;
+  int64_t recv_ptr[sb::kMaxRanks + 1] = {};
+  int32_t* d_send_idx = nullptr;
+  bool distributed = false;
 };
 
 namespace sb {
@@ -342,6 +375,8 @@ inline bool apply_v1_forced() {
   return forced;
 }
 
+int halo_exchange(sb_ctx* ctx, const sb_op* op, const double* x, const int* done); // sb_comm.cu
+
 // Launch y <- A x (+ epilogue) on the context's stream, dispatching on form and ELL width.
 template<int ND, bool RESID, class Epi, class Final>
 int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const Epi& epi, const Final& fin,
@@ -352,8 +387,18 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
     SB_TRY(ensure_red_scratch(ctx, d.n));
   }
   const RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
+  ApplyDist ad;
+  if (op->distributed && ctx->comm.world > 1) {
+    if (op->halo.n_nbr > 0) SB_TRY(halo_exchange(ctx, op, x, done));
+    if (ctx->comm.mode == SB_COMM_P2P && op->halo.n_nbr > 0) {
+      ad.ctrl = ctx->comm.ctrl(ctx->comm.rank);
+      ad.n_nbr = op->halo.n_nbr, ad.first_boundary_tile = op->halo.first_boundary_tile;
+      for (int k = 0; k < op->halo.n_nbr; ++k) ad.nbr_rank[k] = op->halo.nbr_rank[k];
+      ad.coherent_gather = 1;
+    }
+  }
 #define SB_LAUNCH(FORM, W)                                                                       \
-  apply_kernel<FORM, W, ND, RESID, Epi><<<grid, kThreads, 0, ctx->stream>>>(d, x, y, epi, red, done)
+  apply_kernel<FORM, W, ND, RESID, Epi><<<grid, kThreads, 0, ctx->stream>>>(d, x, y, epi, red, ad, done)
 #define SB_WIDTHS(FORM)                   \
   switch (d.width) {                      \
     case 0: case 1: SB_LAUNCH(FORM, 1); break; \
@@ -378,7 +423,7 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
       SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
       configured = true;                                                                                        \
     }                                                                                                           \
-    kern<<<grid, kThreads, smem, ctx->stream>>>(d, x, y, epi, red, done);                                  \
+    kern<<<grid, kThreads, smem, ctx->stream>>>(d, x, y, epi, red, ad, done);                                  \
   }
     switch (d.width) {
       case 0: case 1: SB_LAUNCH_TMA(1) break;

@@ -275,14 +275,13 @@ int launch_ew(sb_ctx* ctx, int64_t n, const Body& body, const Final& fin, const 
 static int ensure_work(sb_ctx* ctx, size_t n, size_t count) {
   if (ctx->work_n < n) {
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (double* w : ctx->work) cudaFree(w);
+    for (double* w : ctx->work) SB_TRY(vec_free(ctx, w));
     ctx->work.clear();
     ctx->work_n = n;
   }
   while (ctx->work.size() < count) {
     double* d = nullptr;
-    SB_CUDA(cudaMalloc(&d, sizeof(double) * pad_up((int64_t) ctx->work_n)));
-    SB_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * pad_up((int64_t) ctx->work_n), ctx->stream));
+    SB_TRY(vec_alloc(ctx, ctx->work_n, &d)); // pool block in multi-GPU mode (apply inputs need a halo tail)
     ctx->work.push_back(d);
   }
   return SB_OK;

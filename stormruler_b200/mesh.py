@@ -80,3 +80,71 @@ class Mesh:
     @property
     def bandwidth(self) -> int:
         return int(self.lib.sb_mesh_bandwidth(self.handle))
+
+
+class LocalView:
+    """One rank's local mesh (sb_local_mesh) as numpy views; duck-types the `mesh` argument of
+    FvmOperator / oracle FaceMesh (n_cells, face_cell, ...)."""
+
+    def __init__(self, part: "Partition", rank: int):
+        lm = capi.LocalMesh()
+        capi.check(part.lib.sb_part_local(part.handle, rank, C.byref(lm)))
+        self.struct, self._part = lm, part
+        self.rank, self.n_parts = int(lm.rank), int(lm.n_parts)
+        self.n_owned, self.n_interior = int(lm.n_owned), int(lm.n_interior)
+        self.n_halo, self.halo_base = int(lm.n_halo), int(lm.halo_base)
+        arr = lambda p, n, dt=None: (np.ctypeslib.as_array(p, shape=(n,)) if n > 0 else np.zeros(0, dt))  # noqa: E731
+        self.local_to_global = arr(lm.local_to_global, self.n_owned + self.n_halo, np.int32)
+        s = lm.soa
+        self.n_cells, self.n_faces, self.n_bfaces = int(s.n_cells), int(s.n_faces), int(s.n_bfaces)
+        self.face_cell = arr(s.face_cell, 2 * self.n_faces, np.int32).reshape(-1, 2)
+        self.face_area, self.face_dist = arr(s.face_area, self.n_faces), arr(s.face_dist, self.n_faces)
+        self.cell_vol = arr(s.cell_vol, self.n_cells)
+        self.bface_cell = arr(s.bface_cell, self.n_bfaces, np.int32)
+        self.bface_area, self.bface_dist = arr(s.bface_area, self.n_bfaces), arr(s.bface_dist, self.n_bfaces)
+        self.face_global = arr(lm.face_global, self.n_faces, np.int64)
+        self.n_nbr = int(lm.n_nbr)
+        self.nbr_rank = arr(lm.nbr_rank, self.n_nbr, np.int32)
+        self.send_ptr = arr(lm.send_ptr, self.n_nbr + 1, np.int64)
+        self.recv_ptr = arr(lm.recv_ptr, self.n_nbr + 1, np.int64)
+        self.send_idx = arr(lm.send_idx, int(self.send_ptr[-1]) if self.n_nbr else 0, np.int32)
+        self.send_dst = arr(lm.send_dst, self.n_nbr, np.int64)
+
+    @property
+    def owned_global(self) -> np.ndarray:
+        return self.local_to_global[:self.n_owned]
+
+    @property
+    def halo_global(self) -> np.ndarray:
+        return self.local_to_global[self.n_owned:]
+
+
+class Partition:
+    """sb_part: a split of the mesh's cell graph into n_parts (METIS k-way or RCM slabs)."""
+
+    def __init__(self, mesh: Mesh, n_parts: int, method: int = capi.PART_METIS, part=None):
+        self.lib, self.mesh = capi.load(), mesh   # the partition borrows the mesh arrays: keep it alive
+        h = C.c_void_p()
+        if part is not None:
+            part = np.ascontiguousarray(part, np.int32)
+            capi.check(self.lib.sb_part_from_array(mesh.handle, n_parts, part.ctypes.data_as(capi.i32p), C.byref(h)))
+        else:
+            capi.check(self.lib.sb_part_create(mesh.handle, n_parts, method, C.byref(h)))
+        self.handle, self.n_parts = h, n_parts
+        info = capi.PartInfo()
+        capi.check(self.lib.sb_part_get_info(h, C.byref(info)))
+        self.info = info
+        p = capi.i32p()
+        capi.check(self.lib.sb_part_get_array(h, C.byref(p)))
+        self.part = np.ctypeslib.as_array(p, shape=(mesh.n_cells,))
+
+    def local(self, rank: int) -> LocalView:
+        return LocalView(self, rank)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.sb_part_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

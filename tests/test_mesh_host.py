@@ -1,0 +1,160 @@
+"""Host-side integer work of the path (no GPU): cell soup -> face-list SoA, RCM renumbering,
+partitioning, halo maps. Bar (north_star): bit-exact. Oracle: the independent numpy restatement in
+oracle/mesh_oracle.py (conventions from the reference's mesh layer, cited there)."""
+import numpy as np
+import pytest
+
+from oracle import mesh_oracle as mo
+from oracle import orc
+from stormruler_b200 import capi
+from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh, Partition
+
+KIND = {"tet": CELL_TET, "hex": CELL_HEX}
+SOA_KEYS = ("face_cell", "face_area", "face_dist", "cell_vol", "bface_cell", "bface_area", "bface_dist")
+
+
+def assert_soa_equal(mesh, want):
+    assert mesh.n_cells == want["n_cells"]
+    for k in SOA_KEYS:
+        got = np.asarray(getattr(mesh, k))
+        assert got.shape == want[k].shape, k
+        assert np.array_equal(got, want[k]), f"{k} differs from the restatement"
+
+
+def test_mt19937_64_restatement_known_answers():
+    """std::mt19937_64 default seed: first output 14514284786278117030, 10000th 9981545732273789042
+    (the values the C++ standard itself requires, [rand.predef])."""
+    e = mo.MT19937_64()
+    first = e()
+    for _ in range(9998):
+        e()
+    assert first == 14514284786278117030 and e() == 9981545732273789042
+
+
+@pytest.mark.parametrize("kind,dims", [("tet", (5, 4, 3)), ("hex", (6, 5, 4)), ("tet", (1, 1, 1)), ("hex", (1, 1, 2))])
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_box_mesh_soa_bit_exact(kind, dims, shuffle):
+    mesh = Mesh.box(KIND[kind], *dims, jitter=0.2, seed_jitter=42, shuffle=shuffle, seed_shuffle=43)
+    xyz, cells = mo.box_cells(kind, *dims, jitter=0.2, seed_jitter=42, shuffle=shuffle, seed_shuffle=43)
+    want = mo.face_list(xyz, cells)
+    assert_soa_equal(mesh, want)
+    assert np.array_equal(mesh.cell_centers(), want["cell_ctr"])
+    # closedness: per cell, the area-weighted outward normals cancel <=> the Laplacian annihilates constants
+    n_faces_expected = {"tet": 4, "hex": 6}[kind] * mesh.n_cells
+    assert 2 * mesh.n_faces + mesh.n_bfaces == n_faces_expected
+
+
+@pytest.mark.parametrize("kind", ["tet", "hex"])
+def test_ingestion_from_cells_matches_generator(kind):
+    xyz, cells = mo.box_cells(kind, 4, 3, 3)
+    a = Mesh.from_cells(KIND[kind], xyz, cells)
+    b = Mesh.box(KIND[kind], 4, 3, 3)
+    for k in SOA_KEYS:
+        assert np.array_equal(getattr(a, k), getattr(b, k))
+    with pytest.raises(capi.StormB200Error):
+        bad = cells.copy()
+        bad[0, 0] = len(xyz)  # node index out of range
+        Mesh.from_cells(KIND[kind], xyz, bad)
+
+
+@pytest.mark.parametrize("kind,dims", [("tet", (6, 5, 4)), ("hex", (7, 6, 5))])
+def test_rcm_permutation_and_renumbered_mesh_bit_exact(kind, dims):
+    mesh = Mesh.box(KIND[kind], *dims)
+    xyz, cells = mo.box_cells(kind, *dims)
+    before = mo.face_list(xyz, cells)
+    bw0 = mesh.bandwidth
+    perm = mesh.renumber_rcm()
+    want_perm = mo.rcm(before["n_cells"], before["face_cell"])
+    assert np.array_equal(perm, want_perm), "RCM permutation differs from the restatement"
+    assert sorted(perm.tolist()) == list(range(mesh.n_cells))          # a bijection, perm[new] = old
+    assert_soa_equal(mesh, mo.face_list(*mo.permute(xyz, cells, want_perm)))
+    assert mesh.bandwidth < bw0 // 4                                    # and it does its job
+    # permuting back restores the original face list (Utils/Permutations.hpp semantics)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm), dtype=np.int32)
+    mesh.permute_cells(inv)
+    assert_soa_equal(mesh, before)
+    with pytest.raises(capi.StormB200Error):
+        mesh.permute_cells(np.zeros(mesh.n_cells, np.int32))            # not a permutation
+
+
+def as_dict(mesh):
+    d = {k: np.asarray(getattr(mesh, k)) for k in SOA_KEYS}
+    d["n_cells"] = mesh.n_cells
+    return d
+
+
+LOCAL_KEYS = ("local_to_global", "nbr_rank", "send_ptr", "recv_ptr", "send_idx", "send_dst", "face_global",
+              "face_cell", "face_area", "face_dist", "cell_vol", "bface_cell", "bface_area", "bface_dist")
+
+
+@pytest.mark.parametrize("method,n_parts", [(capi.PART_SLAB, 2), (capi.PART_SLAB, 5), (capi.PART_METIS, 2),
+                                            (capi.PART_METIS, 4), (capi.PART_METIS, 8)])
+def test_partition_local_meshes_and_halo_maps_bit_exact(method, n_parts):
+    mesh = Mesh.box(CELL_TET, 8, 7, 6)
+    mesh.renumber_rcm()
+    P = Partition(mesh, n_parts, method)
+    gd = as_dict(mesh)
+    if method == capi.PART_SLAB:
+        assert np.array_equal(P.part, mo.slab_partition(mesh.n_cells, n_parts))
+    else:
+        # METIS is a third-party black box: its output is pinned by determinism and validity
+        assert np.array_equal(P.part, Partition(mesh, n_parts, method).part)
+        counts = np.bincount(P.part, minlength=n_parts)
+        assert counts.min() > 0 and counts.max() <= 1.1 * mesh.n_cells / n_parts + 1
+    fc = gd["face_cell"]
+    assert P.info.edge_cut == int((P.part[fc[:, 0]] != P.part[fc[:, 1]]).sum())
+    cap = 0
+    for r in range(n_parts):
+        L, want = P.local(r), mo.local_maps(gd, P.part, r, n_parts)
+        for k in ("n_owned", "n_interior", "n_halo", "halo_base"):
+            assert getattr(L, k) == want[k], (r, k)
+        for k in LOCAL_KEYS:
+            got = np.asarray(getattr(L, k))
+            assert got.shape == want[k].shape and np.array_equal(got, want[k]), (r, k)
+        cap = max(cap, mo.pad_up(L.n_owned) + mo.pad_up(max(L.n_halo, 1)))
+    assert P.info.vec_capacity == cap
+    # every cell is owned exactly once; what a sends to b is what b expects from a, in the same order
+    owned = np.concatenate([P.local(r).owned_global for r in range(n_parts)])
+    assert sorted(owned.tolist()) == list(range(mesh.n_cells))
+    for a in range(n_parts):
+        La = P.local(a)
+        for k, b in enumerate(La.nbr_rank):
+            Lb = P.local(int(b))
+            kb = list(Lb.nbr_rank).index(a)
+            sent = La.local_to_global[La.send_idx[La.send_ptr[k]:La.send_ptr[k + 1]]]
+            expected = Lb.halo_global[Lb.recv_ptr[kb]:Lb.recv_ptr[kb + 1]]
+            assert np.array_equal(sent, expected)
+            assert La.send_dst[k] == Lb.halo_base + Lb.recv_ptr[kb]
+
+
+@pytest.mark.parametrize("method", [capi.PART_SLAB, capi.PART_METIS])
+def test_partitioned_apply_rows_are_bit_identical_to_global_rows(method):
+    """Emulated exchange (numpy): every owned row of every rank reproduces the global face loop bit for bit,
+    because the local face lists keep the global face order and orientation."""
+    mesh = Mesh.box(CELL_HEX, 7, 6, 5)
+    mesh.renumber_rcm()
+    gm = orc.FaceMesh(mesh.n_cells, mesh.face_cell, mesh.face_area, mesh.face_dist, mesh.cell_vol,
+                      mesh.bface_cell, mesh.bface_area, mesh.bface_dist)
+    x = np.cos(0.11 * np.arange(mesh.n_cells)) + 0.3
+    y = orc.FaceOp(gm, prefill=0, dt=-1.0, dirichlet=True).apply(x)
+    P = Partition(mesh, 3, method)
+    for r in range(3):
+        L = P.local(r)
+        xl = np.zeros(L.n_cells)
+        xl[:L.n_owned] = x[L.owned_global]
+        xl[L.halo_base:] = x[L.halo_global]            # what the neighbours' packs deliver
+        lm = orc.FaceMesh(L.n_cells, L.face_cell, L.face_area, L.face_dist, L.cell_vol, L.bface_cell, L.bface_area,
+                          L.bface_dist)
+        yl = orc.FaceOp(lm, prefill=0, dt=-1.0, dirichlet=True).apply(xl)
+        assert np.array_equal(yl[:L.n_owned], y[L.owned_global])
+
+
+def test_partition_rejects_bad_input():
+    mesh = Mesh.box(CELL_TET, 2, 2, 2)
+    with pytest.raises(capi.StormB200Error):
+        Partition(mesh, 2, part=np.full(mesh.n_cells, 5, np.int32))      # part id out of range
+    with pytest.raises(capi.StormB200Error):
+        Partition(mesh, 2, part=np.zeros(mesh.n_cells, np.int32))        # part 1 owns nothing
+    with pytest.raises(capi.StormB200Error):
+        Partition(mesh, 10 ** 6)                                         # more parts than cells
