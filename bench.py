@@ -308,6 +308,9 @@ def main():
     ap.add_argument("--cell", default="tet", choices=["tet", "hex"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: halo exchange + reductions by in-kernel NVLink peer stores (p2p) or NCCL send/recv + allreduce")
+    ap.add_argument("--partition", default="metis", choices=["metis", "slab"], help="N>1: METIS k-way or contiguous RCM slabs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

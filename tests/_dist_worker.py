@@ -1,0 +1,190 @@
+"""Worker of the world_size > 1 tests (launched by tests/test_multigpu.py through torch.distributed.run).
+
+    cpu mode (gloo, no GPU): the host-side logic of the N>1 path -- partition broadcast, local meshes,
+        halo maps -- is exercised end to end: the ranks exchange halo values with gloo send/recv following
+        send_idx / recv_ptr / send_dst exactly as the device code does, apply their local face lists with
+        the oracle, and every owned row must be bit-identical to the single-process result; the
+        rank-ordered segmented tree dot is checked against per-rank tree sums combined in rank order.
+    gpu mode (one rank per GPU): distributed apply / CG / BiCGStab through the C ABI, checked bit for bit
+        against the single-process oracle run in the ranks' concatenated cell order with the segmented
+        reduction tree (oracle RED_TREE_SEG).
+Exit code 0 = all checks passed on this rank.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import orc  # noqa: E402
+from stormruler_b200 import capi  # noqa: E402
+from stormruler_b200 import multigpu as mg  # noqa: E402
+from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh  # noqa: E402
+
+
+def face_mesh(m):
+    return orc.FaceMesh(m.n_cells, m.face_cell, m.face_area, m.face_dist, m.cell_vol, m.bface_cell, m.bface_area,
+                        m.bface_dist)
+
+
+def concat_order(part, world):
+    """Global ids in the ranks' concatenated local order + segment pointers."""
+    order, seg = [], [0]
+    for r in range(world):
+        L = part.local(r)
+        order.append(np.asarray(L.owned_global, np.int64))
+        seg.append(seg[-1] + L.n_owned)
+    return np.concatenate(order), np.asarray(seg, np.int64)
+
+
+def permuted_face_mesh(mesh, order):
+    """The global mesh with cells relabelled to the concatenated order; faces keep their global order, so
+    every cell still sums its face contributions in ascending global face index."""
+    g2c = np.empty(mesh.n_cells, np.int32)
+    g2c[order] = np.arange(mesh.n_cells, dtype=np.int32)
+    return orc.FaceMesh(mesh.n_cells, g2c[mesh.face_cell], mesh.face_area, mesh.face_dist, mesh.cell_vol[order],
+                        g2c[mesh.bface_cell] if mesh.n_bfaces else mesh.bface_cell, mesh.bface_area, mesh.bface_dist)
+
+
+def host_halo_exchange(dist, loc, x_local):
+    """What halo_pack + the peer stores do on the device, over gloo."""
+    import torch
+    reqs, recv_bufs = [], []
+    for k in range(loc.n_nbr):
+        q = int(loc.nbr_rank[k])
+        sb = torch.from_numpy(np.ascontiguousarray(x_local[loc.send_idx[loc.send_ptr[k]:loc.send_ptr[k + 1]]]))
+        rb = torch.empty(int(loc.recv_ptr[k + 1] - loc.recv_ptr[k]), dtype=torch.float64)
+        recv_bufs.append(rb)
+        reqs.append(dist.isend(sb, dst=q))
+        reqs.append(dist.irecv(rb, src=q))
+    for r in reqs:
+        r.wait()
+    for k in range(loc.n_nbr):
+        x_local[loc.halo_base + loc.recv_ptr[k]: loc.halo_base + loc.recv_ptr[k + 1]] = recv_bufs[k].numpy()
+
+
+def run_cpu(dist, rank, world):
+    import torch
+    for kind, dims, method in ((CELL_TET, (6, 5, 4), capi.PART_METIS), (CELL_HEX, (7, 6, 5), capi.PART_SLAB),
+                               (CELL_TET, (9, 3, 3), capi.PART_SLAB)):
+        mesh = Mesh.box(kind, *dims, jitter=0.2, seed_jitter=42, shuffle=True, seed_shuffle=43)
+        mesh.renumber_rcm()
+        part = mg.partition_mesh(mesh, world, method)
+        loc = part.local(rank)
+        n = mesh.n_cells
+        # every rank holds the same partition array
+        ref_part = mg.broadcast_array(np.asarray(part.part) if rank == 0 else None, (n,), np.int32)
+        assert np.array_equal(ref_part, part.part)
+        # send_dst is the neighbour's halo_base + its recv_ptr for me: ask the neighbours
+        mine = torch.zeros(world, dtype=torch.int64)
+        for k in range(loc.n_nbr):
+            mine[int(loc.nbr_rank[k])] = loc.halo_base + int(loc.recv_ptr[k])   # where nbr k's block starts in MY vectors
+        table = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(table, mine)
+        for k in range(loc.n_nbr):
+            q = int(loc.nbr_rank[k])
+            assert int(table[q][rank]) == int(loc.send_dst[k]), "send_dst disagrees with the neighbour's layout"
+        # distributed apply on the host = halo exchange + local face loop; owned rows bit-identical
+        rng = np.random.default_rng(7)
+        xg = rng.standard_normal(n)
+        gop = orc.FaceOp(face_mesh(mesh), prefill=1, dt=-0.05, dirichlet=True)
+        yg = gop.apply(xg)
+        xl = np.zeros(loc.n_cells)
+        xl[:loc.n_owned] = xg[loc.owned_global]
+        host_halo_exchange(dist, loc, xl)
+        assert np.array_equal(xl[loc.halo_base:loc.halo_base + loc.n_halo], xg[loc.halo_global]), "halo values"
+        lop = orc.FaceOp(face_mesh(loc), prefill=1, dt=-0.05, dirichlet=True)
+        yl = lop.apply(xl)
+        assert np.array_equal(yl[:loc.n_owned], yg[loc.owned_global]), "owned rows differ from the global apply"
+        assert np.array_equal(mg.gather_global(loc, yl[:loc.n_owned], n), yg)
+        # rank-ordered reduction: per-rank SB_TREE sums added in rank order == oracle RED_TREE_SEG
+        order, seg = concat_order(part, world)
+        orc.set_segments(seg)
+        want = orc.dot(xg[order], yg[order], orc.RED_TREE_SEG)
+        local_sum = torch.tensor([orc.dot(xl[:loc.n_owned], yl[:loc.n_owned], orc.RED_TREE)], dtype=torch.float64)
+        sums = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(sums, local_sum)
+        tot = float(sums[0][0])
+        for r in range(1, world):
+            tot = tot + float(sums[r][0])
+        assert tot == want, (tot, want)
+        assert mg.max_over_ranks(float(rank)) == world - 1 and mg.sum_over_ranks(1.0) == world
+    return 0
+
+
+def run_gpu(dist, rank, world, mode_name):
+    import stormruler_b200 as sb
+    mode = capi.COMM_NCCL if mode_name == "nccl" else capi.COMM_P2P
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cases = ((CELL_TET, (14, 12, 10), capi.PART_METIS), (CELL_HEX, (24, 20, 18), capi.PART_SLAB))
+    for kind, dims, method in cases:
+        mesh = Mesh.box(kind, *dims, jitter=0.2, seed_jitter=42, shuffle=True, seed_shuffle=43)
+        mesh.renumber_rcm()
+        part = mg.partition_mesh(mesh, world, method)
+        loc = part.local(rank)
+        n = mesh.n_cells
+        order, seg = concat_order(part, world)
+        orc.set_segments(seg)
+        pm = permuted_face_mesh(mesh, order)
+        ctx = mg.DistContext(local_rank, rank, world, part.info.vec_capacity, n_vectors=16, mode=mode)
+        rng = np.random.default_rng(11)
+        xg = rng.standard_normal(n)
+        bg = np.sin(0.37 * np.arange(n))
+        for form in (sb.FORM_FAITHFUL, sb.FORM_COEF):
+            op = mg.DistOperator(ctx, loc, prefill=1, dt=-0.05, form=form, dirichlet=True)
+            cpu = orc.FaceOp(pm, prefill=1, dt=-0.05, dirichlet=True)
+            # apply, several times in a row on alternating inputs (exercises the ack / sequence protocol)
+            x, y = ctx.vector(xg[loc.owned_global]), ctx.zeros(loc.n_owned)
+            if form == sb.FORM_FAITHFUL:
+                want = cpu.apply(xg[order])
+            else:
+                want = cpu.apply_rows_coef(xg[order])
+            for rep in range(5):
+                op.mul(y, x)
+                got = mg.gather_global(loc, y.numpy(), n)
+                assert np.array_equal(got[order], want), f"distributed apply differs (form {form}, repeat {rep})"
+            # ping-pong y = A x, x2 = A y: consecutive applies with different halo contents
+            x2 = ctx.zeros(loc.n_owned)
+            op.mul(x2, y)
+            want2 = cpu.apply(want) if form == sb.FORM_FAITHFUL else cpu.apply_rows_coef(want)
+            assert np.array_equal(mg.gather_global(loc, x2.numpy(), n)[order], want2)
+            # distributed dot
+            d = ctx.dot(x, y)
+            assert d == orc.dot(xg[order], want, orc.RED_TREE_SEG), "rank-ordered dot differs"
+            if form != sb.FORM_FAITHFUL:
+                del op, x, y, x2
+                continue
+            for name, Solver in (("cg", sb.CgSolver), ("bicgstab", sb.BiCgStabSolver)):
+                for use_graph in (False, True):
+                    s = Solver(num_iterations=60, absolute_error_tolerance=0.0, relative_error_tolerance=1e-9,
+                               use_graph=use_graph, check_every=7)
+                    xs = ctx.zeros(loc.n_owned)
+                    conv = s.solve(xs, ctx.vector(bg[loc.owned_global]), op)
+                    w = orc.solve(name, cpu, bg[order], num_iterations=60, abs_tol=0.0, rel_tol=1e-9, mode=orc.RED_TREE_SEG)
+                    assert conv == w.converged and s.iteration == w.iterations, (name, conv, s.iteration, w.iterations)
+                    assert np.array_equal(s.history, w.hist), f"{name}: residual history differs from the oracle"
+                    assert np.array_equal(mg.gather_global(loc, xs.numpy(), n)[order], w.x), f"{name}: solution differs"
+                    del xs
+            del op, x, y, x2
+        assert ctx.status() == 0
+        ctx.close()
+    return 0
+
+
+def main():
+    mode = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist = mg.init_process_group(cuda=(mode != "cpu"))
+    try:
+        rc = run_cpu(dist, rank, world) if mode == "cpu" else run_gpu(dist, rank, world, mode)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+    print(f"rank {rank}: OK", flush=True)
+    sys.exit(rc)
+
+
+if __name__ == "__main__":
+    main()
