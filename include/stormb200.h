@@ -109,6 +109,26 @@ typedef struct sb_op_info {
 SB_API int sb_op_create(sb_ctx* ctx, const sb_mesh_soa* h_mesh, const sb_op_desc* desc, sb_op** out);
 SB_API int sb_op_destroy(sb_ctx* ctx, sb_op* op);
 SB_API int sb_op_get_info(const sb_op* op, sb_op_info* info);
+/* Convection-diffusion operator  y = -nu div grad x + div(beta x)  with the first-order upwind face
+ * flux, written in the inner/outer face-loop pattern of UpwindConvectionScheme::operator()
+ * (Feathers/ConvectionScheme.hpp:83-106) -- SURVEY.md 8d config 3:
+ *   interior face f (inner i, outer o, un = beta . n_f, n_f pointing i -> o):
+ *       flux = max(un,0)*x[i] + min(un,0)*x[o] - nu*(x[o]-x[i])/dist_f
+ *       y[i] += (area_f/vol_i)*flux ;  y[o] -= (area_f/vol_o)*flux
+ *   Dirichlet boundary face b of cell c (mirror ghost -x[c], un = beta . n_b outward):
+ *       flux = max(un,0)*x[c] + min(un,0)*(-x[c]) - nu*((-x[c])-x[c])/bdist_b ;  y[c] += (barea_b/vol_c)*flux
+ * The rows are non-symmetric (two different coefficients per face); they are stored in the coefficient
+ * form (SB_FORM_COEF) and applied by the same kernels. Coefficient order of operations (restated in
+ * oracle/sb_oracle.c: orc_rows_convdiff): g = area/vol_row, kd = nu/dist, up = max(un,0), um = min(un,0);
+ *   inner row: a = g*(um - kd), diag += g*(up + kd);   outer row: a = g*((-up) - kd), diag += g*(kd - um);
+ *   boundary:  diag += g*((up - um) + (kd + kd));      diag accumulates in ascending face order from 0. */
+typedef struct sb_convdiff_desc {
+  double nu;
+  const double* face_un;  /* h_ [n_faces]  beta . n_f per interior face (a face-flux field) */
+  const double* bface_un; /* h_ [n_bfaces] beta . n_b per boundary face; may be NULL if n_bfaces == 0 */
+} sb_convdiff_desc;
+SB_API int sb_op_create_convdiff(sb_ctx* ctx, const sb_mesh_soa* h_mesh, const sb_convdiff_desc* desc, sb_op** out);
+
 /* Copy the row layout back to the host for bit-exact comparison with the oracle:
  * h_col [width*ld] int32, h_val0 [width*ld] (coef, or area/vol), h_val1 [width*ld] (dist; faithful
  * form only, may be NULL), h_diag [ld] (coef form only, may be NULL). */
@@ -153,6 +173,11 @@ SB_API int sb_mesh_permute_cells(sb_mesh* mesh, const int32_t* h_perm);
  * faces: every face with a single adjacent cell; bface_dist = 2*|face centre - cell centre|. */
 SB_API int sb_mesh_get_soa(const sb_mesh* mesh, sb_mesh_soa* soa);
 SB_API int sb_mesh_cell_centers(const sb_mesh* mesh, double* h_xyz /* [3*n_cells] */);
+/* Unit face normals (what FaceView::normal() is to the reference's flux schemes,
+ * Feathers/ConvectionScheme.hpp:87,100): h_fn [3*n_faces] oriented inner -> outer, h_bn [3*n_bfaces]
+ * oriented out of the domain; either may be NULL. Triangle: cross(v2-v1, v3-v1); quadrangle: cross of
+ * the diagonals; normalised, flipped if it points against (outer centre - inner centre). */
+SB_API int sb_mesh_face_normals(const sb_mesh* mesh, double* h_fn, double* h_bn);
 /* Bandwidth of the cell graph, max |inner - outer| over interior faces (renumbering quality). */
 SB_API int64_t sb_mesh_bandwidth(const sb_mesh* mesh);
 
@@ -192,6 +217,7 @@ typedef struct sb_local_mesh {
   const int64_t* recv_ptr; /* h_ [n_nbr+1] offsets into the halo block; group k holds cells owned by nbr_rank[k] */
   const int64_t* send_dst; /* h_ [n_nbr] element offset in neighbour k's vectors where my block starts
                               (= its halo_base + its recv_ptr for me) */
+  const int64_t* bface_global;    /* h_ [soa.n_bfaces] global boundary-face index of each local one */
 } sb_local_mesh;
 
 SB_API int sb_part_create(const sb_mesh* mesh, int n_parts, int method, sb_part** out);
@@ -228,6 +254,10 @@ SB_API int sb_comm_status(sb_ctx* ctx, uint64_t* h_error);
  * sb_apply / the fused solvers exchange halos inside the call; x must be a vector of this context
  * (its halo tail is written by the neighbours). Vectors have n = local->n_owned logical elements. */
 SB_API int sb_dist_op_create(sb_ctx* ctx, const sb_local_mesh* local, const sb_op_desc* desc, sb_op** out);
+/* Same for the convection-diffusion operator; desc->face_un / bface_un are indexed by LOCAL face
+ * (gather them with local->face_global / bface_global). */
+SB_API int sb_dist_op_create_convdiff(sb_ctx* ctx, const sb_local_mesh* local, const sb_convdiff_desc* desc,
+                                      sb_op** out);
 
 /* ---- BLAS-1: replaces Bittern's lazy expressions + assignment operators
  * (MatrixMath.hpp:233-301, MatrixTarget.hpp:96-119, MatrixAlgorithms.hpp:95-135) for the vector.

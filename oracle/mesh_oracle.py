@@ -190,7 +190,14 @@ def face_list(xyz, cells):
         fc = (a1[:, None] * _tri_center(v1, v2, v3) + a2[:, None] * _tri_center(v3, v4, v1)) / area[:, None]
     xi = ctr[creator]
     F = int(interior.sum())
+    # unit normals: triangle cross(v2-v1, v3-v1), quadrangle cross of the diagonals; oriented inner -> outer
+    # (boundary: along face centre - cell centre)
+    nrm = _cross(v2 - v1, v3 - v1) if npc == 4 else _cross(v3 - v1, v4 - v2)
+    nrm = nrm / _length(nrm)[:, None]
+    direction = np.where(interior[:, None], ctr[np.maximum(other, 0)] - xi, fc - xi)
+    nrm = np.where((_dot3(nrm, direction) < 0.0)[:, None], -nrm, nrm)
     return dict(
+        face_normal=nrm[:F], bface_normal=nrm[F:],
         n_cells=n, cell_vol=vol, cell_ctr=ctr,
         face_cell=np.stack([creator[:F], other[:F]], 1).astype(np.int32), face_area=area[:F],
         face_dist=_length(ctr[other[:F]] - xi[:F]),
@@ -301,5 +308,6 @@ def local_maps(mesh: dict, part, rank: int, n_parts: int):
         send_dst=np.array(send_dst, np.int64),
         face_global=np.flatnonzero(keep).astype(np.int64), face_cell=g2l[fc[keep]].astype(np.int32),
         face_area=mesh["face_area"][keep], face_dist=mesh["face_dist"][keep], cell_vol=cell_vol,
+        bface_global=np.flatnonzero(bkeep).astype(np.int64),
         bface_cell=g2l[mesh["bface_cell"][bkeep]].astype(np.int32), bface_area=mesh["bface_area"][bkeep],
         bface_dist=mesh["bface_dist"][bkeep])

@@ -51,6 +51,15 @@ class FaceOpStruct(C.Structure):
     ]
 
 
+class ConvDiffStruct(C.Structure):
+    _fields_ = [("base", FaceOpStruct), ("nu", C.c_double), ("face_un", _f64p), ("bface_un", _f64p)]
+
+
+class RowsOpStruct(C.Structure):
+    _fields_ = [("n", C.c_int64), ("width", C.c_int), ("ld", C.c_int64), ("col", _i32p), ("a", _f64p),
+                ("diag", _f64p)]
+
+
 class SolverOpts(C.Structure):
     _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
                 ("reduction_mode", C.c_int32)]
@@ -99,6 +108,10 @@ def lib():
         L.orc_rows_coef.restype = None
         L.orc_apply_rows_coef.argtypes = [C.c_int64, C.c_int, C.c_int64, _i32p, _f64p, _f64p, _f64p, _f64p]
         L.orc_apply_rows_coef.restype = None
+        L.orc_apply_convdiff_faces.argtypes = [C.POINTER(ConvDiffStruct), _f64p, _f64p]
+        L.orc_apply_convdiff_faces.restype = None
+        L.orc_rows_convdiff.argtypes = [C.POINTER(ConvDiffStruct), C.c_int, C.c_int64, _i32p, _f64p, _f64p]
+        L.orc_rows_convdiff.restype = None
         L.orc_dot.argtypes = [C.c_int64, _f64p, _f64p, C.c_int]
         L.orc_dot.restype = C.c_double
         L.orc_norm2.argtypes = [C.c_int64, _f64p, C.c_int]
@@ -247,6 +260,62 @@ class FaceOp:
         lib().orc_apply_rows_coef(self.n, w, ld, _p(col, _i32p), _p(a, _f64p), _p(diag, _f64p),
                                   _p(x, _f64p), _p(y, _f64p))
         return y
+
+
+class RowsOp:
+    """An operator given as coefficient rows (col, a, diag): y_i = diag_i x_i + sum_k a_ik x[col_ik]."""
+
+    def __init__(self, n, width, ld, col, a, diag):
+        self.n = int(n)
+        self._keep = [np.ascontiguousarray(col, np.int32), _f64(a), _f64(diag)]
+        k = self._keep
+        self.rows = (int(width), int(ld), k[0], k[1], k[2])
+        self.struct = RowsOpStruct(self.n, int(width), int(ld), _p(k[0], _i32p), _p(k[1], _f64p), _p(k[2], _f64p))
+
+    def apply(self, x):
+        x = _f64(x)
+        y = np.empty(self.n)
+        w, ld, col, a, diag = self.rows
+        lib().orc_apply_rows_coef(self.n, w, ld, _p(col, _i32p), _p(a, _f64p), _p(diag, _f64p), _p(x, _f64p),
+                                  _p(y, _f64p))
+        return y
+
+    @property
+    def callback(self):
+        return C.cast(lib().orc_apply_rows_cb, C.c_void_p), C.cast(C.pointer(self.struct), C.c_void_p)
+
+
+class ConvDiffOp:
+    """y = -nu div grad x + div(beta x), first-order upwind, Dirichlet mirror ghosts (sb_oracle.h:
+    orc_convdiff_op). `face_un` / `bface_un`: beta . n per interior / boundary face."""
+
+    def __init__(self, mesh: FaceMesh, nu: float, face_un, bface_un, dirichlet: bool = True):
+        self.mesh, self.nu, self.n = mesh, float(nu), mesh.n_cells
+        self._geo = FaceOp(mesh, prefill=0, dt=0.0, dirichlet=dirichlet)
+        self._un = [_f64(face_un), _f64(bface_un)]
+        assert self._un[0].shape[0] == mesh.n_faces and self._un[1].shape[0] == mesh.n_bfaces
+        self.struct = ConvDiffStruct(self._geo.struct, self.nu, _p(self._un[0], _f64p), _p(self._un[1], _f64p))
+
+    def apply(self, x):
+        x = _f64(x)
+        y = np.empty(self.n)
+        lib().orc_apply_convdiff_faces(C.byref(self.struct), _p(x, _f64p), _p(y, _f64p))
+        return y
+
+    @property
+    def callback(self):
+        return C.cast(lib().orc_apply_convdiff_faces_cb, C.c_void_p), C.cast(C.pointer(self.struct), C.c_void_p)
+
+    def rows_coef(self, ld: int | None = None) -> RowsOp:
+        """Row form in the product's layout contract (width from the interior faces only)."""
+        L = lib()
+        interior = FaceOpStruct.from_buffer_copy(self._geo.struct)
+        interior.n_bfaces = 0
+        w = max(1, L.orc_rows_width(C.byref(interior)))
+        ld = self.n if ld is None else int(ld)
+        col, a, diag = np.empty((w, ld), np.int32), np.empty((w, ld)), np.empty(ld)
+        L.orc_rows_convdiff(C.byref(self.struct), w, ld, _p(col, _i32p), _p(a, _f64p), _p(diag, _f64p))
+        return RowsOp(self.n, w, ld, col, a, diag)
 
 
 class CallbackOp:

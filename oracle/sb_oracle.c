@@ -185,6 +185,79 @@ void orc_apply_rows_coef(int64_t n, int width, int64_t ld, const int32_t* col, c
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Convection-diffusion (config 3): face loop and its row form.
+ * ---------------------------------------------------------------------------------------------- */
+void orc_apply_convdiff_faces(const orc_convdiff_op* op, const double* x, double* y) {
+  const orc_face_op* g = &op->base;
+  for (int64_t i = 0; i < g->n_cells; ++i) y[i] = 0.0;
+  for (int64_t f = 0; f < g->n_faces; ++f) {
+    const int32_t ci = g->face_cell[2 * f + 0], co = g->face_cell[2 * f + 1];
+    const double un = op->face_un[f];
+    const double up = un > 0.0 ? un : 0.0, um = un < 0.0 ? un : 0.0;
+    /* flux = flux_scheme(normal, u[outer], u[inner])   (ConvectionScheme.hpp:87-88) */
+    const double flux = (up * x[ci] + um * x[co]) - op->nu * (x[co] - x[ci]) / g->face_dist[f];
+    y[ci] += (g->face_area[f] / g->cell_vol[ci]) * flux; /* :89 */
+    y[co] -= (g->face_area[f] / g->cell_vol[co]) * flux; /* :90 */
+  }
+  for (int64_t b = 0; b < g->n_bfaces; ++b) {
+    const int32_t ci = g->bface_cell[b];
+    const double ghost = -x[ci]; /* bc->get_ghost_state (:98-99): homogeneous Dirichlet mirror */
+    const double un = op->bface_un[b];
+    const double up = un > 0.0 ? un : 0.0, um = un < 0.0 ? un : 0.0;
+    const double flux = (up * x[ci] + um * ghost) - op->nu * (ghost - x[ci]) / g->bface_dist[b];
+    y[ci] += (g->bface_area[b] / g->cell_vol[ci]) * flux; /* :103 */
+  }
+}
+
+void orc_apply_convdiff_faces_cb(void* user, double* y, const double* x, size_t n) {
+  (void) n;
+  orc_apply_convdiff_faces((const orc_convdiff_op*) user, x, y);
+}
+
+void orc_rows_convdiff(const orc_convdiff_op* op, int width, int64_t ld, int32_t* col, double* a, double* diag) {
+  const orc_face_op* g = &op->base;
+  const int64_t n = g->n_cells;
+  for (int64_t k = 0; k < (int64_t) width * ld; ++k) {
+    col[k] = ORC_COL_PAD;
+    a[k] = 0.0;
+  }
+  for (int64_t i = 0; i < ld; ++i) diag[i] = 0.0;
+  int32_t* fill = (int32_t*) calloc((size_t) n + 1, sizeof(int32_t));
+  for (int64_t f = 0; f < g->n_faces; ++f) {
+    const int32_t ci = g->face_cell[2 * f + 0], co = g->face_cell[2 * f + 1];
+    const double un = op->face_un[f];
+    const double up = un > 0.0 ? un : 0.0, um = un < 0.0 ? un : 0.0;
+    const double kd = op->nu / g->face_dist[f];
+    const double gi = g->face_area[f] / g->cell_vol[ci], go = g->face_area[f] / g->cell_vol[co];
+    int64_t e = (int64_t) fill[ci] * ld + ci;
+    col[e] = co;
+    a[e] = gi * (um - kd);
+    diag[ci] = diag[ci] + gi * (up + kd);
+    fill[ci]++;
+    e = (int64_t) fill[co] * ld + co;
+    col[e] = ci;
+    a[e] = go * ((-up) - kd);
+    diag[co] = diag[co] + go * (kd - um);
+    fill[co]++;
+  }
+  for (int64_t b = 0; b < g->n_bfaces; ++b) {
+    const int32_t ci = g->bface_cell[b];
+    const double un = op->bface_un[b];
+    const double up = un > 0.0 ? un : 0.0, um = un < 0.0 ? un : 0.0;
+    const double kd = op->nu / g->bface_dist[b];
+    const double gc = g->bface_area[b] / g->cell_vol[ci];
+    diag[ci] = diag[ci] + gc * ((up - um) + (kd + kd));
+  }
+  free(fill);
+}
+
+void orc_apply_rows_cb(void* user, double* y, const double* x, size_t n) {
+  const orc_rows_op* r = (const orc_rows_op*) user;
+  (void) n;
+  orc_apply_rows_coef(r->n, r->width, r->ld, r->col, r->a, r->diag, x, y);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Reductions.
  * ORC_RED_SEQ: Bittern `reduce` (MatrixAlgorithms.hpp:191-205): init = Result{} = 0.0, then
  *              init = init + a_i*b_i for ascending i.

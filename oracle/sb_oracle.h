@@ -72,6 +72,36 @@ void orc_apply_faces(const orc_face_op* op, const double* x, double* y);
 /* Same signature as the callback taken by oracle/_ref's ref_solve(): user = const orc_face_op*. */
 void orc_apply_faces_cb(void* user, double* y, const double* x, size_t n);
 
+/* Convection-diffusion operator  y = -nu div grad x + div(beta x), first-order upwind, in the face-loop
+ * pattern of UpwindConvectionScheme::operator() (Feathers/ConvectionScheme.hpp:83-106): interior faces
+ * add the flux to the inner cell and subtract it from the outer cell; boundary faces (ghost state from the
+ * boundary condition, here the homogeneous-Dirichlet mirror -x[c]) add it to the inner cell only.
+ * The reference's flux scheme is a functor argument (ConvectionScheme.hpp:64,87); for the scalar linear
+ * problem of SURVEY.md 8d config 3 it is  flux(n, u_outer, u_inner) = max(un,0)*u_inner + min(un,0)*u_outer
+ * - nu*(u_outer - u_inner)/dist,  un = beta . n.  face_un / bface_un hold un per face. */
+typedef struct {
+  orc_face_op base;       /* geometry (prefill and dt unused) */
+  double nu;
+  const double* face_un;  /* [n_faces] */
+  const double* bface_un; /* [n_bfaces] */
+} orc_convdiff_op;
+void orc_apply_convdiff_faces(const orc_convdiff_op* op, const double* x, double* y);
+void orc_apply_convdiff_faces_cb(void* user, double* y, const double* x, size_t n);
+/* Row (coefficient) form of the same operator, entry order from orc_build_rows(&op->base) with
+ * base.n_bfaces = 0 for the structure and the boundary faces folded into the diagonal. Operation order
+ * is part of the layout contract (include/stormb200.h: sb_convdiff_desc). */
+void orc_rows_convdiff(const orc_convdiff_op* op, int width, int64_t ld, int32_t* col, double* a, double* diag);
+/* orc_apply_rows_coef with a context: the callback form used by the solvers. */
+typedef struct {
+  int64_t n;
+  int width;
+  int64_t ld;
+  const int32_t* col;
+  const double* a;
+  const double* diag;
+} orc_rows_op;
+void orc_apply_rows_cb(void* user, double* y, const double* x, size_t n);
+
 /* Cell-row (ELL) form of the same operator.
  * width = max entries per row; ld = leading dimension (>= n_cells); entry k of row i at [k*ld + i].
  * Entries of a row are ordered exactly as the face loop visits the cell: interior faces by

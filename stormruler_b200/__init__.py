@@ -19,7 +19,7 @@ from . import capi
 from .capi import (ADD_ASSIGN, ASSIGN, DIV_ASSIGN, FORM_COEF, FORM_FAITHFUL, MUL_ASSIGN, SUB_ASSIGN,
                    StormB200Error)
 
-__all__ = ["Context", "DeviceVector", "FvmOperator", "CgSolver", "BiCgStabSolver", "StormB200Error",
+__all__ = ["Context", "DeviceVector", "FvmOperator", "ConvDiffOperator", "CgSolver", "BiCgStabSolver", "StormB200Error",
            "FORM_COEF", "FORM_FAITHFUL", "ASSIGN", "ADD_ASSIGN", "SUB_ASSIGN", "MUL_ASSIGN",
            "DIV_ASSIGN", "expr"]
 
@@ -251,6 +251,34 @@ class FvmOperator:
             v1.ctypes.data_as(capi.f64p) if faithful else None,
             None if faithful else diag.ctypes.data_as(capi.f64p)))
         return col, v0, v1, diag
+
+
+class ConvDiffOperator(FvmOperator):
+    """y = -nu div grad x + div(beta x), first-order upwind in the face-loop pattern of
+    UpwindConvectionScheme (Feathers/ConvectionScheme.hpp:83-106), Dirichlet mirror ghosts: non-symmetric
+    coefficient rows applied by the same kernels (sb_op_create_convdiff). `face_un` / `bface_un` = beta . n per
+    interior / boundary face (Mesh.face_flux)."""
+
+    def __init__(self, ctx: Context, mesh, nu: float, face_un, bface_un):
+        self.ctx = ctx
+        fc = np.ascontiguousarray(mesh.face_cell, np.int32).reshape(-1)
+        fa, fd, cv = _f64(mesh.face_area), _f64(mesh.face_dist), _f64(mesh.cell_vol)
+        bc = np.ascontiguousarray(mesh.bface_cell, np.int32)
+        ba, bd = _f64(mesh.bface_area), _f64(mesh.bface_dist)
+        fu, bu = _f64(face_un), _f64(bface_un)
+        assert fu.shape[0] == fa.shape[0] and bu.shape[0] == ba.shape[0]
+        soa = capi.MeshSoa(int(mesh.n_cells), int(fa.shape[0]), fc.ctypes.data_as(capi.i32p),
+                           fa.ctypes.data_as(capi.f64p), fd.ctypes.data_as(capi.f64p),
+                           cv.ctypes.data_as(capi.f64p), int(ba.shape[0]), bc.ctypes.data_as(capi.i32p),
+                           ba.ctypes.data_as(capi.f64p), bd.ctypes.data_as(capi.f64p))
+        desc = capi.ConvDiffDesc(float(nu), fu.ctypes.data_as(capi.f64p), bu.ctypes.data_as(capi.f64p))
+        h = C.c_void_p()
+        capi.check(ctx.lib.sb_op_create_convdiff(ctx.handle, C.byref(soa), C.byref(desc), C.byref(h)))
+        self.handle = h
+        info = capi.OpInfo()
+        capi.check(ctx.lib.sb_op_get_info(h, C.byref(info)))
+        self.info = info
+        self.n = int(info.n_cells)
 
 
 @dataclass

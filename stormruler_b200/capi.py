@@ -47,11 +47,15 @@ class LocalMesh(C.Structure):
                 ("n_interior", C.c_int64), ("n_halo", C.c_int64), ("halo_base", C.c_int64),
                 ("local_to_global", i32p), ("soa", MeshSoa), ("face_global", i64p),
                 ("n_nbr", C.c_int32), ("nbr_rank", i32p), ("send_ptr", i64p), ("send_idx", i32p),
-                ("recv_ptr", i64p), ("send_dst", i64p)]
+                ("recv_ptr", i64p), ("send_dst", i64p), ("bface_global", i64p)]
 
 
 class OpDesc(C.Structure):
     _fields_ = [("form", C.c_int32), ("prefill", C.c_int32), ("dt", C.c_double)]
+
+
+class ConvDiffDesc(C.Structure):
+    _fields_ = [("nu", C.c_double), ("face_un", f64p), ("bface_un", f64p)]
 
 
 class OpInfo(C.Structure):
@@ -91,6 +95,8 @@ SIGNATURES = {
     "sb_vec_upload": (C.c_int, [C.c_void_p, C.c_void_p, f64p, C.c_size_t]),
     "sb_vec_download": (C.c_int, [C.c_void_p, C.c_void_p, f64p, C.c_size_t]),
     "sb_op_create": (C.c_int, [C.c_void_p, C.POINTER(MeshSoa), C.POINTER(OpDesc), vpp]),
+    "sb_op_create_convdiff": (C.c_int, [C.c_void_p, C.POINTER(MeshSoa), C.POINTER(ConvDiffDesc), vpp]),
+    "sb_dist_op_create_convdiff": (C.c_int, [C.c_void_p, C.POINTER(LocalMesh), C.POINTER(ConvDiffDesc), vpp]),
     "sb_op_destroy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sb_op_get_info": (C.c_int, [C.c_void_p, C.POINTER(OpInfo)]),
     "sb_op_download_rows": (C.c_int, [C.c_void_p, C.c_void_p, i32p, f64p, f64p, f64p]),
@@ -103,6 +109,7 @@ SIGNATURES = {
     "sb_mesh_permute_cells": (C.c_int, [C.c_void_p, i32p]),
     "sb_mesh_get_soa": (C.c_int, [C.c_void_p, C.POINTER(MeshSoa)]),
     "sb_mesh_cell_centers": (C.c_int, [C.c_void_p, f64p]),
+    "sb_mesh_face_normals": (C.c_int, [C.c_void_p, f64p, f64p]),
     "sb_mesh_bandwidth": (C.c_int64, [C.c_void_p]),
     "sb_part_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, vpp]),
     "sb_part_from_array": (C.c_int, [C.c_void_p, C.c_int, i32p, vpp]),

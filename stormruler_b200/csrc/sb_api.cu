@@ -1,6 +1,7 @@
 // sb_api.cu -- context, vectors and BLAS-1 entry points of the C ABI (include/stormb200.h).
 #include "sb_kernels.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace sb {
@@ -48,6 +49,7 @@ int sb_ctx_create(int device, sb_ctx** out) {
   SB_CUDA(cudaSetDevice(device));
   sb_ctx* ctx = new sb_ctx();
   ctx->device = device;
+  if (const char* dbg = std::getenv("SB_DEBUG")) ctx->debug = std::atoi(dbg);
   SB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   SB_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   SB_CUDA(cudaMalloc(&ctx->red.result, sizeof(double) * 64));

@@ -121,6 +121,9 @@ struct sb_ctx {
   double* d_ar = nullptr;         // NCCL mode: all-reduce staging [4]
   double* d_sendbuf = nullptr;    // NCCL mode: packed halo values
   int64_t sendbuf_cap = 0;
+  // experiments only (SB_DEBUG env): bit1 = skip the halo exchange, bit2 = skip the cross-rank all-reduce
+  // (results are wrong on purpose; used to attribute multi-GPU time, never set in tests or bench lines)
+  int debug = 0;
 };
 
 namespace sb {

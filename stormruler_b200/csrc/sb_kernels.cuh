@@ -145,6 +145,12 @@ int nccl_allreduce_sum(sb_ctx* ctx, double* d_buf, int count); // sb_comm.cu
 template<int ND, class Final>
 inline int launch_final(sb_ctx* ctx, int64_t n, const Final& fin, const int* done) {
   const RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
+  if (ctx->debug & 4) { // experiment: rank-local sums only
+    final_reduce_kernel<ND, Final><<<1, kThreads, 0, ctx->stream>>>(num_tiles(n), red, fin, CommDev{}, done);
+    ctx->launches++;
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+  }
   if (ctx->comm.mode == SB_COMM_NCCL && ctx->comm.world > 1) {
     final_reduce_kernel<ND, StoreFinal<ND>>
         <<<1, kThreads, 0, ctx->stream>>>(num_tiles(n), red, StoreFinal<ND>{ctx->d_ar}, CommDev{}, done);

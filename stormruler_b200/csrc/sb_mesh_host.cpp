@@ -115,6 +115,7 @@ struct sb_mesh {
   std::vector<double> xyz;
   std::vector<int32_t> cells;
   std::vector<FacePair> pairs; // matched faces, numbering-independent except for the cell ids
+  std::vector<int64_t> face_order; // ordered face q (interior first, then boundary) -> index into pairs
   // derived SoA
   std::vector<double> cell_vol, cell_ctr;
   std::vector<int32_t> face_cell, bface_cell;
@@ -259,6 +260,48 @@ void order_faces(sb_mesh& m) {
         m.bface_cell[b] = ci;
         m.bface_area[b] = area;
         m.bface_dist[b] = 2.0 * length(sub(fc, xi)); // mirror ghost centre
+      }
+    }
+  });
+  m.face_order.swap(idx);
+}
+
+// Unit face normals, oriented inner -> outer (boundary faces: out of the domain), evaluated on demand.
+// Triangle: cross(v2-v1, v3-v1); quadrangle: cross of the diagonals (v3-v1) x (v4-v2); normalised by
+// its length; flipped when it points against (x_outer - x_inner) / (face centre - x_inner).
+void face_normals(const sb_mesh& m, double* fn, double* bn) {
+  const int64_t nf = (int64_t) m.face_order.size(), n_int = (int64_t) m.face_area.size();
+  parallel_for(nf, [&](int64_t lo, int64_t hi) {
+    for (int64_t q = lo; q < hi; ++q) {
+      const FacePair& p = m.pairs[(size_t) m.face_order[(size_t) q]];
+      const int32_t ci = p.cell[0];
+      const int32_t* nd = &m.cells[(size_t) ci * m.npc];
+      const int* lf = m.local_face(p.lf[0]);
+      const V3 v1 = m.node(nd[lf[0]]), v2 = m.node(nd[lf[1]]), v3 = m.node(nd[lf[2]]);
+      V3 nrm, fc;
+      if (lf[3] < 0) {
+        nrm = cross(sub(v2, v1), sub(v3, v1));
+        fc = tri_center(v1, v2, v3);
+      } else {
+        const V3 v4 = m.node(nd[lf[3]]);
+        nrm = cross(sub(v3, v1), sub(v4, v2));
+        const double a1 = tri_area(v1, v2, v3), a2 = tri_area(v3, v4, v1);
+        fc = divs(add(scale(a1, tri_center(v1, v2, v3)), scale(a2, tri_center(v3, v4, v1))), a1 + a2);
+      }
+      nrm = divs(nrm, length(nrm));
+      const V3 xi{m.cell_ctr[3 * (size_t) ci], m.cell_ctr[3 * (size_t) ci + 1], m.cell_ctr[3 * (size_t) ci + 2]};
+      V3 dir;
+      if (q < n_int) {
+        const int32_t co = p.cell[1];
+        dir = sub(V3{m.cell_ctr[3 * (size_t) co], m.cell_ctr[3 * (size_t) co + 1], m.cell_ctr[3 * (size_t) co + 2]}, xi);
+      } else {
+        dir = sub(fc, xi);
+      }
+      if (dot3(nrm, dir) < 0.0) nrm = V3{-nrm.x, -nrm.y, -nrm.z};
+      double* base = q < n_int ? fn : bn;
+      if (base != nullptr) {
+        double* out = base + 3 * (q < n_int ? q : q - n_int);
+        out[0] = nrm.x, out[1] = nrm.y, out[2] = nrm.z;
       }
     }
   });
@@ -495,6 +538,12 @@ int sb_mesh_get_soa(const sb_mesh* m, sb_mesh_soa* soa) {
 int sb_mesh_cell_centers(const sb_mesh* m, double* h_xyz) {
   SBM_REQUIRE(m != nullptr && h_xyz != nullptr, "null argument");
   std::memcpy(h_xyz, m->cell_ctr.data(), sizeof(double) * m->cell_ctr.size());
+  return SB_OK;
+}
+
+int sb_mesh_face_normals(const sb_mesh* m, double* h_fn, double* h_bn) {
+  SBM_REQUIRE(m != nullptr, "mesh is null");
+  face_normals(*m, h_fn, h_bn);
   return SB_OK;
 }
 

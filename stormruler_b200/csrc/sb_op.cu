@@ -78,6 +78,59 @@ int build_rows(const sb_mesh_soa* m, const sb_op_desc* desc, int64_t n_rows, Hos
   return SB_OK;
 }
 
+// Convection-diffusion rows (include/stormb200.h: sb_convdiff_desc). Same entry order as build_rows
+// (ascending face index per row); the coefficient arithmetic is restated operation by operation in
+// oracle/sb_oracle.c: orc_rows_convdiff.
+int build_rows_convdiff(const sb_mesh_soa* m, const sb_convdiff_desc* desc, int64_t n_rows, HostRows& R) {
+  const int64_t n = m->n_cells, F = m->n_faces, B = m->n_bfaces;
+  for (int64_t f = 0; f < 2 * F; ++f)
+    SB_REQUIRE(m->face_cell[f] >= 0 && m->face_cell[f] < n, "face_cell index out of range");
+  for (int64_t b = 0; b < B; ++b)
+    SB_REQUIRE(m->bface_cell[b] >= 0 && m->bface_cell[b] < n_rows, "bface_cell index out of range");
+  std::vector<int32_t> deg((size_t) n + 1, 0);
+  for (int64_t f = 0; f < F; ++f) deg[m->face_cell[2 * f]]++, deg[m->face_cell[2 * f + 1]]++;
+  int32_t width = 1;
+  for (int64_t i = 0; i < n_rows; ++i) width = std::max(width, deg[i]);
+  const int64_t ld = pad_up(n_rows);
+  R.width = width, R.ld = ld, R.entries = 0;
+  R.col.assign((size_t) width * ld, kColPad);
+  R.v0.assign((size_t) width * ld, 0.0);
+  R.diag.assign((size_t) ld, 0.0);
+  std::vector<int32_t> fill((size_t) n + 1, 0);
+  const double nu = desc->nu;
+  auto put = [&](int32_t row, int32_t c, double a, double dg) {
+    if (row >= n_rows) return;
+    const int64_t e = (int64_t) fill[row] * ld + row;
+    R.col[e] = c, R.v0[e] = a;
+    R.diag[row] = R.diag[row] + dg;
+    fill[row]++;
+    R.entries++;
+  };
+  for (int64_t f = 0; f < F; ++f) {
+    const int32_t ci = m->face_cell[2 * f], co = m->face_cell[2 * f + 1];
+    const double un = desc->face_un[f];
+    const double up = un > 0.0 ? un : 0.0, um = un < 0.0 ? un : 0.0;
+    const double kd = nu / m->face_dist[f];
+    if (ci < n_rows) {
+      const double g = m->face_area[f] / m->cell_vol[ci];
+      put(ci, co, g * (um - kd), g * (up + kd));
+    }
+    if (co < n_rows) {
+      const double g = m->face_area[f] / m->cell_vol[co];
+      put(co, ci, g * ((-up) - kd), g * (kd - um));
+    }
+  }
+  for (int64_t b = 0; b < B; ++b) {
+    const int32_t ci = m->bface_cell[b];
+    const double un = desc->bface_un[b];
+    const double up = un > 0.0 ? un : 0.0, um = un < 0.0 ? un : 0.0;
+    const double kd = nu / m->bface_dist[b];
+    const double g = m->bface_area[b] / m->cell_vol[ci];
+    R.diag[ci] = R.diag[ci] + g * ((up - um) + (kd + kd));
+  }
+  return SB_OK;
+}
+
 template<class T>
 int upload(sb_ctx* ctx, const std::vector<T>& h, void** d_out, int64_t& bytes) {
   *d_out = nullptr;
@@ -92,8 +145,8 @@ int upload(sb_ctx* ctx, const std::vector<T>& h, void** d_out, int64_t& bytes) {
 
 extern "C" {
 
-static int op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, int64_t n_rows, sb_op** out) {
-  SB_REQUIRE(ctx != nullptr && m != nullptr && desc != nullptr && out != nullptr, "null argument");
+static int validate_mesh(sb_ctx* ctx, const sb_mesh_soa* m, int64_t n_rows, sb_op** out) {
+  SB_REQUIRE(ctx != nullptr && m != nullptr && out != nullptr, "null argument");
   *out = nullptr;
   SB_REQUIRE(n_rows > 0 && n_rows <= m->n_cells, "row count out of range");
   SB_REQUIRE(m->n_cells > 0 && m->n_cells < (int64_t) INT32_MAX - kTile, "n_cells out of range (int32 indices)");
@@ -101,22 +154,20 @@ static int op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, 
   SB_REQUIRE(m->n_faces == 0 || (m->face_cell && m->face_area && m->face_dist), "null face arrays");
   SB_REQUIRE(m->n_bfaces == 0 || (m->bface_cell && m->bface_area && m->bface_dist), "null boundary-face arrays");
   SB_REQUIRE(m->cell_vol != nullptr, "null cell_vol");
-  SB_REQUIRE(desc->form == SB_FORM_FAITHFUL || desc->form == SB_FORM_COEF, "unknown operator form");
-  SB_REQUIRE(desc->prefill == 0 || desc->prefill == 1, "prefill must be 0 or 1");
-  // The dependency order of the ghost fold matters for bit-exactness in the coef form: the oracle
-  // subtracts interior coefficients and ghost terms in row order (interior first, then ghosts),
-  // which is exactly the order of the two loops in build_rows.
-  HostRows R;
-  SB_TRY(build_rows(m, desc, n_rows, R));
+  return SB_OK;
+}
+
+// Upload the host rows: blocked SELL-64 records for the coefficient form, plain ELL arrays otherwise.
+static int finish_op(sb_ctx* ctx, HostRows& R, int form, int prefill, double dt, int64_t n_rows, sb_op** out) {
   SB_REQUIRE(R.width <= 8, "cells with more than 8 faces are not supported yet");
   std::unique_ptr<sb_op> op(new sb_op());
-  op->d.n = n_rows, op->d.ld = R.ld, op->d.width = R.width, op->d.form = desc->form;
-  op->d.prefill = desc->prefill, op->d.dt = desc->dt;
+  op->d.n = n_rows, op->d.ld = R.ld, op->d.width = R.width, op->d.form = form;
+  op->d.prefill = prefill, op->d.dt = dt;
   op->n_entries = R.entries;
-  if (const char* dbg = std::getenv("SB_DEBUG")) op->d.debug = std::atoi(dbg);
+  if (const char* dbg = std::getenv("SB_DEBUG")) op->d.debug = std::atoi(dbg) & 1;
   SB_CUDA(cudaSetDevice(ctx->device));
   std::vector<unsigned char> blk;
-  if (desc->form == SB_FORM_COEF && !apply_v1_forced()) {
+  if (form == SB_FORM_COEF && !apply_v1_forced()) {
     // blocked layout: slice record = [col[W][64] | coef[W][64] | diag[64]]
     const int W = R.width;
     const int64_t slice_bytes = 768 * (int64_t) W + 512, n_slices = R.ld / 64;
@@ -153,24 +204,32 @@ static int op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, 
   return SB_OK;
 }
 
-int sb_op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, sb_op** out) {
-  SB_REQUIRE(m != nullptr, "null argument");
-  return op_create(ctx, m, desc, m->n_cells, out);
+static int op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, int64_t n_rows, sb_op** out) {
+  SB_REQUIRE(desc != nullptr, "null argument");
+  SB_TRY(validate_mesh(ctx, m, n_rows, out));
+  SB_REQUIRE(desc->form == SB_FORM_FAITHFUL || desc->form == SB_FORM_COEF, "unknown operator form");
+  SB_REQUIRE(desc->prefill == 0 || desc->prefill == 1, "prefill must be 0 or 1");
+  // The dependency order of the ghost fold matters for bit-exactness in the coef form: the oracle
+  // subtracts interior coefficients and ghost terms in row order (interior first, then ghosts),
+  // which is exactly the order of the two loops in build_rows.
+  HostRows R;
+  SB_TRY(build_rows(m, desc, n_rows, R));
+  return finish_op(ctx, R, desc->form, desc->prefill, desc->dt, n_rows, out);
 }
 
-int sb_dist_op_create(sb_ctx* ctx, const sb_local_mesh* loc, const sb_op_desc* desc, sb_op** out) {
-  SB_REQUIRE(ctx != nullptr && loc != nullptr && desc != nullptr && out != nullptr, "null argument");
-  *out = nullptr;
-  if (ctx->comm.mode < 0) {
-    set_error("sb_dist_op_create needs a communicator (sb_comm_prepare / sb_comm_connect)");
-    return SB_ERR_STATE;
-  }
-  SB_REQUIRE(loc->rank == ctx->comm.rank && loc->n_parts == ctx->comm.world, "local mesh belongs to another rank / world size");
-  SB_REQUIRE(loc->n_nbr >= 0 && loc->n_nbr < kMaxRanks, "too many neighbours");
-  SB_REQUIRE(loc->halo_base == pad_up(loc->n_owned) && loc->soa.n_cells == loc->halo_base + loc->n_halo, "local mesh layout");
-  SB_REQUIRE(loc->halo_base + loc->n_halo <= ctx->vec_capacity, "local vector does not fit the pool block (vec_capacity)");
-  sb_op* op = nullptr;
-  SB_TRY(op_create(ctx, &loc->soa, desc, loc->n_owned, &op));
+static int op_create_convdiff(sb_ctx* ctx, const sb_mesh_soa* m, const sb_convdiff_desc* desc, int64_t n_rows, sb_op** out) {
+  SB_REQUIRE(desc != nullptr, "null argument");
+  SB_TRY(validate_mesh(ctx, m, n_rows, out));
+  SB_REQUIRE(m->n_faces == 0 || desc->face_un != nullptr, "null face_un");
+  SB_REQUIRE(m->n_bfaces == 0 || desc->bface_un != nullptr, "null bface_un");
+  SB_REQUIRE(desc->nu >= 0.0, "nu must be >= 0");
+  HostRows R;
+  SB_TRY(build_rows_convdiff(m, desc, n_rows, R));
+  return finish_op(ctx, R, SB_FORM_COEF, 0, 0.0, n_rows, out);
+}
+
+// Halo plan of a distributed operator (shared by the diffusion and convection-diffusion forms).
+static int attach_halo(sb_ctx* ctx, const sb_local_mesh* loc, sb_op* op) {
   op->distributed = true;
   op->halo_base = loc->halo_base, op->n_halo = loc->n_halo;
   HaloDev& h = op->halo;
@@ -189,6 +248,57 @@ int sb_dist_op_create(sb_ctx* ctx, const sb_local_mesh* loc, const sb_op_desc* d
     SB_CUDA(cudaMemcpy(op->d_send_idx, loc->send_idx, sizeof(int32_t) * (size_t) total, cudaMemcpyHostToDevice));
   }
   h.send_idx = op->d_send_idx;
+  return SB_OK;
+}
+
+static int check_local(sb_ctx* ctx, const sb_local_mesh* loc) {
+  if (ctx->comm.mode < 0) {
+    set_error("a distributed operator needs a communicator (sb_comm_prepare / sb_comm_connect)");
+    return SB_ERR_STATE;
+  }
+  SB_REQUIRE(loc->rank == ctx->comm.rank && loc->n_parts == ctx->comm.world, "local mesh belongs to another rank / world size");
+  SB_REQUIRE(loc->n_nbr >= 0 && loc->n_nbr < kMaxRanks, "too many neighbours");
+  SB_REQUIRE(loc->halo_base == pad_up(loc->n_owned) && loc->soa.n_cells == loc->halo_base + loc->n_halo, "local mesh layout");
+  SB_REQUIRE(loc->halo_base + loc->n_halo <= ctx->vec_capacity, "local vector does not fit the pool block (vec_capacity)");
+  return SB_OK;
+}
+
+int sb_op_create(sb_ctx* ctx, const sb_mesh_soa* m, const sb_op_desc* desc, sb_op** out) {
+  SB_REQUIRE(m != nullptr, "null argument");
+  return op_create(ctx, m, desc, m->n_cells, out);
+}
+
+int sb_op_create_convdiff(sb_ctx* ctx, const sb_mesh_soa* m, const sb_convdiff_desc* desc, sb_op** out) {
+  SB_REQUIRE(m != nullptr, "null argument");
+  return op_create_convdiff(ctx, m, desc, m->n_cells, out);
+}
+
+int sb_dist_op_create(sb_ctx* ctx, const sb_local_mesh* loc, const sb_op_desc* desc, sb_op** out) {
+  SB_REQUIRE(ctx != nullptr && loc != nullptr && desc != nullptr && out != nullptr, "null argument");
+  *out = nullptr;
+  SB_TRY(check_local(ctx, loc));
+  sb_op* op = nullptr;
+  SB_TRY(op_create(ctx, &loc->soa, desc, loc->n_owned, &op));
+  const int rc = attach_halo(ctx, loc, op);
+  if (rc != SB_OK) {
+    sb_op_destroy(ctx, op);
+    return rc;
+  }
+  *out = op;
+  return SB_OK;
+}
+
+int sb_dist_op_create_convdiff(sb_ctx* ctx, const sb_local_mesh* loc, const sb_convdiff_desc* desc, sb_op** out) {
+  SB_REQUIRE(ctx != nullptr && loc != nullptr && desc != nullptr && out != nullptr, "null argument");
+  *out = nullptr;
+  SB_TRY(check_local(ctx, loc));
+  sb_op* op = nullptr;
+  SB_TRY(op_create_convdiff(ctx, &loc->soa, desc, loc->n_owned, &op));
+  const int rc = attach_halo(ctx, loc, op);
+  if (rc != SB_OK) {
+    sb_op_destroy(ctx, op);
+    return rc;
+  }
   *out = op;
   return SB_OK;
 }

@@ -58,7 +58,7 @@ struct Local {
   // local face list
   std::vector<int32_t> face_cell, bface_cell;
   std::vector<double> face_area, face_dist, cell_vol, bface_area, bface_dist;
-  std::vector<int64_t> face_global;
+  std::vector<int64_t> face_global, bface_global;
   // neighbours
   std::vector<int32_t> nbr_rank, send_idx;
   std::vector<int64_t> send_ptr, recv_ptr, send_dst;
@@ -189,10 +189,11 @@ void build_local(const sb_part& P, int rank, Local& L) {
   for (int64_t k = 0; k < L.n_owned; ++k) L.cell_vol[(size_t) k] = P.g.cell_vol[L.l2g[(size_t) k]];
   for (int64_t h = 0; h < L.n_halo; ++h)
     L.cell_vol[(size_t) (L.halo_base + h)] = P.g.cell_vol[L.l2g[(size_t) (L.n_owned + h)]];
-  L.bface_cell.clear(), L.bface_area.clear(), L.bface_dist.clear();
+  L.bface_cell.clear(), L.bface_area.clear(), L.bface_dist.clear(), L.bface_global.clear();
   for (int64_t b = 0; b < B; ++b) {
     const int32_t c = P.g.bface_cell[b];
     if (part[c] != rank) continue;
+    L.bface_global.push_back(b);
     L.bface_cell.push_back(g2l[(size_t) c]);
     L.bface_area.push_back(P.g.bface_area[b]), L.bface_dist.push_back(P.g.bface_dist[b]);
   }
@@ -293,6 +294,7 @@ int sb_part_local(sb_part* P, int rank, sb_local_mesh* out) {
   out->nbr_rank = L.nbr_rank.data();
   out->send_ptr = L.send_ptr.data(), out->send_idx = L.send_idx.data(), out->recv_ptr = L.recv_ptr.data();
   out->send_dst = L.send_dst.data();
+  out->bface_global = L.bface_global.data();
   return SB_OK;
 }
 

@@ -77,6 +77,18 @@ class Mesh:
         capi.check(self.lib.sb_mesh_cell_centers(self.handle, out.ctypes.data_as(capi.f64p)))
         return out
 
+    def face_normals(self):
+        """(interior [F,3] inner -> outer, boundary [B,3] outward) unit normals."""
+        fn, bn = np.empty((self.n_faces, 3)), np.empty((self.n_bfaces, 3))
+        capi.check(self.lib.sb_mesh_face_normals(self.handle, fn.ctypes.data_as(capi.f64p), bn.ctypes.data_as(capi.f64p)))
+        return fn, bn
+
+    def face_flux(self, beta):
+        """beta . n per interior / boundary face for a uniform velocity `beta` ((beta_x*n_x + beta_y*n_y) + beta_z*n_z)."""
+        fn, bn = self.face_normals()
+        bx, by, bz = (float(v) for v in beta)
+        return (bx * fn[:, 0] + by * fn[:, 1]) + bz * fn[:, 2], (bx * bn[:, 0] + by * bn[:, 1]) + bz * bn[:, 2]
+
     @property
     def bandwidth(self) -> int:
         return int(self.lib.sb_mesh_bandwidth(self.handle))
@@ -109,6 +121,7 @@ class LocalView:
         self.recv_ptr = arr(lm.recv_ptr, self.n_nbr + 1, np.int64)
         self.send_idx = arr(lm.send_idx, int(self.send_ptr[-1]) if self.n_nbr else 0, np.int32)
         self.send_dst = arr(lm.send_dst, self.n_nbr, np.int64)
+        self.bface_global = arr(lm.bface_global, self.n_bfaces, np.int64)
 
     @property
     def owned_global(self) -> np.ndarray:

@@ -68,8 +68,7 @@ def main():
             out[f"{s}_stats"] = np.array([r.converged, r.iterations, r.abs_err, r.rel_err, r.n_apply,
                                           len(r.trace)], dtype=np.float64)
             out[f"{s}_trace_head"] = r.trace[:TRACE_HEAD]
-            if s in ("cg", "bicgstab"):
-                out[f"{s}_x"] = r.x
+            out[f"{s}_x"] = r.x
         # ... and CG/BiCGStab on the Dirichlet Poisson operator (boundary ghost rows, configs 2/4)
         opd = orc.FaceOp(mesh, prefill=0, dt=-1.0, dirichlet=True)
         for s in ("cg", "bicgstab"):

@@ -1,0 +1,107 @@
+"""Convection-diffusion on the GPU (BASELINE.json configs[2]): the non-symmetric
+upwind operator in the face-loop pattern of UpwindConvectionScheme (Feathers/ConvectionScheme.hpp:83-106),
+stored as coefficient rows and applied by the same kernels; GMRES(m) / FGMRES / BiCGStab / IDR(s) are the
+reference's own templates on Storm::DeviceVector.
+
+Oracle: oracle/sb_oracle.c (orc_apply_convdiff_faces: the face loop; orc_rows_convdiff: the row form whose
+operation order is the layout contract). Rows and apply are bit-exact against the row oracle and within
+rounding of the face loop; the solvers are bit-exact against the same reference headers on a host vector
+with the reduction tree matched, and within the north_star bars of the reference's sequential sums.
+"""
+import numpy as np
+import pytest
+
+import stormruler_b200 as sb
+from oracle import orc
+from stormruler_b200 import dropin
+from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh
+
+pytestmark = pytest.mark.gpu
+
+NU, BETA = 0.02, (1.0, 0.5, 0.25)
+X_TOL = 1e-8
+
+
+def make_case(ctx, kind, dims):
+    mesh = Mesh.box(CELL_TET if kind == "tet" else CELL_HEX, *dims)
+    mesh.renumber_rcm()
+    fu, bu = mesh.face_flux(BETA)
+    fm = orc.FaceMesh(mesh.n_cells, mesh.face_cell, mesh.face_area, mesh.face_dist, mesh.cell_vol, mesh.bface_cell,
+                      mesh.bface_area, mesh.bface_dist)
+    cpu = orc.ConvDiffOp(fm, NU, fu, bu)
+    gpu = sb.ConvDiffOperator(ctx, mesh, NU, fu, bu)
+    return mesh, cpu, gpu
+
+
+@pytest.fixture(scope="module")
+def tet_case(ctx):
+    return make_case(ctx, "tet", (12, 10, 9))
+
+
+@pytest.mark.parametrize("kind,dims", [("tet", (7, 6, 5)), ("hex", (11, 9, 8))])
+def test_rows_and_apply_bit_exact(ctx, kind, dims):
+    mesh, cpu, gpu = make_case(ctx, kind, dims)
+    rows = cpu.rows_coef(ld=gpu.info.ld)
+    w, ld, ocol, oa, odiag = rows.rows
+    col, a, _, diag = gpu.rows()
+    assert gpu.info.width == w and gpu.info.form == sb.FORM_COEF
+    assert np.array_equal(col, ocol) and np.array_equal(a, oa) and np.array_equal(diag, odiag)
+    assert gpu.info.algorithmic_bytes_per_apply == 24 * cpu.n + 12 * 2 * mesh.n_faces
+    rng = np.random.default_rng(5)
+    y = ctx.zeros(cpu.n)
+    tight = cpu.rows_coef()
+    for x in (rng.standard_normal(cpu.n), np.ones(cpu.n), np.zeros(cpu.n)):
+        gpu.mul(y, ctx.vector(x))
+        got = y.numpy()
+        assert np.array_equal(got, tight.apply(x))
+        ref = cpu.apply(x)
+        assert np.abs(got - ref).max() <= 1e-13 * max(np.abs(ref).max(), 1e-300)
+
+
+def test_create_rejects_bad_input(ctx):
+    mesh = Mesh.box(CELL_TET, 2, 2, 2)
+    fu, bu = mesh.face_flux(BETA)
+    with pytest.raises(sb.StormB200Error):
+        sb.ConvDiffOperator(ctx, mesh, -1.0, fu, bu)          # negative diffusion coefficient
+    with pytest.raises(AssertionError):
+        sb.ConvDiffOperator(ctx, mesh, NU, fu[:-1], bu)       # wrong face count
+
+
+@pytest.mark.parametrize("solver,num_inner", [("gmres", 0), ("gmres", 30), ("fgmres", 0), ("bicgstab", 0), ("bicgstabl", 0),
+                                              ("idrs", 0), ("tfqmr", 0), ("cgs", 0)])
+def test_reference_templates_on_convdiff_bit_identical(ctx, tet_case, solver, num_inner):
+    """Same reference headers, host vector + row oracle vs device vector + CUDA rows, reduction tree matched."""
+    assert dropin.available() and orc.have_ref()
+    _, cpu, gpu = tet_case
+    rows = cpu.rows_coef()
+    b = np.sin(0.37 * np.arange(cpu.n))
+    want = orc.ref_solve(solver, rows, b, num_iterations=400, abs_tol=0.0, rel_tol=1e-10, num_inner=num_inner,
+                         mode=orc.RED_TREE)
+    x = ctx.zeros(cpu.n)
+    got = dropin.solve(solver, gpu, x, ctx.vector(b), num_iterations=400, abs_tol=0.0, rel_tol=1e-10, num_inner=num_inner)
+    assert (got.converged, got.iterations, got.n_apply) == (want.converged, want.iterations, want.n_apply)
+    assert np.array_equal(got.trace, want.trace) and np.array_equal(got.hist, want.hist)
+    assert np.array_equal(x.numpy(), want.x)
+    assert want.converged
+    # against the reference's own sequential sums on the FACE LOOP (row rounding + reduction order differ)
+    seq = orc.ref_solve(solver, cpu, b, num_iterations=400, abs_tol=0.0, rel_tol=1e-10, num_inner=num_inner)
+    assert seq.converged
+    assert np.linalg.norm(x.numpy() - seq.x) <= X_TOL * np.linalg.norm(seq.x)
+    k = min(10, len(seq.hist), len(got.hist))
+    assert (np.abs(got.hist[:k] - seq.hist[:k]) <= 1e-10 * seq.hist[:k]).all()
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_bicgstab_on_convdiff_bit_identical(ctx, tet_case, use_graph):
+    _, cpu, gpu = tet_case
+    rows = cpu.rows_coef()
+    b = np.sin(0.37 * np.arange(cpu.n))
+    want = orc.solve("bicgstab", rows, b, num_iterations=300, abs_tol=0.0, rel_tol=1e-10, mode=orc.RED_TREE)
+    s = sb.BiCgStabSolver(num_iterations=300, absolute_error_tolerance=0.0, relative_error_tolerance=1e-10,
+                          use_graph=use_graph)
+    x = ctx.zeros(cpu.n)
+    conv = s.solve(x, ctx.vector(b), gpu)
+    assert conv and conv == want.converged and s.iteration == want.iterations
+    assert np.array_equal(s.history, want.hist) and np.array_equal(x.numpy(), want.x)
+    res = np.linalg.norm(b - cpu.apply(x.numpy())) / np.linalg.norm(b)
+    assert res < 1e-9

@@ -44,6 +44,30 @@ def test_box_mesh_soa_bit_exact(kind, dims, shuffle):
     assert 2 * mesh.n_faces + mesh.n_bfaces == n_faces_expected
 
 
+@pytest.mark.parametrize("kind,dims", [("tet", (5, 4, 3)), ("hex", (6, 5, 4))])
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_face_normals_bit_exact_and_closed(kind, dims, shuffle):
+    """Unit normals (what FaceView::normal() feeds the reference's flux schemes): bit-exact against the numpy
+    restatement, unit length, oriented inner -> outer / outward; a tetrahedron's area vectors cancel."""
+    mesh = Mesh.box(KIND[kind], *dims, jitter=0.2, seed_jitter=42, shuffle=shuffle, seed_shuffle=43)
+    want = mo.face_list(*mo.box_cells(kind, *dims, jitter=0.2, seed_jitter=42, shuffle=shuffle, seed_shuffle=43))
+    fn, bn = mesh.face_normals()
+    assert np.array_equal(fn, want["face_normal"]) and np.array_equal(bn, want["bface_normal"])
+    assert np.abs(np.linalg.norm(fn, axis=1) - 1.0).max() < 4e-16
+    ctr = mesh.cell_centers()
+    assert (np.einsum("ij,ij->i", fn, ctr[mesh.face_cell[:, 1]] - ctr[mesh.face_cell[:, 0]]) > 0).all()
+    # boundary normals of the unit box are axis-aligned and point out of it
+    assert np.allclose(np.abs(bn).max(axis=1), 1.0, atol=1e-12)
+    if kind == "tet":
+        acc = np.zeros((mesh.n_cells, 3))
+        np.add.at(acc, mesh.face_cell[:, 0], mesh.face_area[:, None] * fn)
+        np.add.at(acc, mesh.face_cell[:, 1], -mesh.face_area[:, None] * fn)
+        np.add.at(acc, mesh.bface_cell, mesh.bface_area[:, None] * bn)
+        assert np.abs(acc).max() < 1e-15
+    fu, bu = mesh.face_flux((1.0, 0.5, 0.25))
+    assert np.array_equal(fu, (1.0 * fn[:, 0] + 0.5 * fn[:, 1]) + 0.25 * fn[:, 2]) and bu.shape == (mesh.n_bfaces,)
+
+
 @pytest.mark.parametrize("kind", ["tet", "hex"])
 def test_ingestion_from_cells_matches_generator(kind):
     xyz, cells = mo.box_cells(kind, 4, 3, 3)
@@ -84,7 +108,7 @@ def as_dict(mesh):
     return d
 
 
-LOCAL_KEYS = ("local_to_global", "nbr_rank", "send_ptr", "recv_ptr", "send_idx", "send_dst", "face_global",
+LOCAL_KEYS = ("local_to_global", "nbr_rank", "send_ptr", "recv_ptr", "send_idx", "send_dst", "face_global", "bface_global",
               "face_cell", "face_area", "face_dist", "cell_vol", "bface_cell", "bface_area", "bface_dist")
 
 
