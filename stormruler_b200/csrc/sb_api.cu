@@ -50,6 +50,7 @@ int sb_ctx_create(int device, sb_ctx** out) {
   sb_ctx* ctx = new sb_ctx();
   ctx->device = device;
   if (const char* dbg = std::getenv("SB_DEBUG")) ctx->debug = std::atoi(dbg);
+  if (const char* pdl = std::getenv("SB_PDL")) ctx->pdl = std::atoi(pdl) != 0;
   SB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   SB_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   SB_CUDA(cudaMalloc(&ctx->red.result, sizeof(double) * 64));
@@ -130,9 +131,9 @@ int launch_eval(sb_ctx* ctx, double* y, size_t n, const sb_expr* e, const Prog& 
   for (int k = 0; k < SB_EXPR_MAX_SCAL; ++k) body.sc[k] = e->scal[k];
   body.prog = prog;
   const unsigned grid = (unsigned) num_tiles((int64_t) n);
-  ew_kernel<0, EvalBody<NV, AOP, Prog>><<<grid, kThreads, 0, ctx->stream>>>((int64_t) n, body, RedPtrs{}, nullptr);
+  SB_CUDA(launch_kernel(ctx, ew_kernel<0, EvalBody<NV, AOP, Prog>>, grid, kThreads, 0, (int64_t) n, body, RedPtrs{},
+                        (const int*) nullptr));
   ctx->launches++;
-  SB_CUDA(cudaGetLastError());
   return SB_OK;
 }
 
@@ -244,10 +245,9 @@ int sb_fill(sb_ctx* ctx, double* y, size_t n, double value) {
   SB_REQUIRE(ctx != nullptr && y != nullptr, "null argument");
   if (n == 0) return SB_OK;
   FillBody body{y, value};
-  ew_kernel<0, FillBody><<<(unsigned) num_tiles((int64_t) n), kThreads, 0, ctx->stream>>>((int64_t) n, body, RedPtrs{},
-                                                                                     nullptr);
+  SB_CUDA(launch_kernel(ctx, ew_kernel<0, FillBody>, (unsigned) num_tiles((int64_t) n), kThreads, 0, (int64_t) n, body,
+                        RedPtrs{}, (const int*) nullptr));
   ctx->launches++;
-  SB_CUDA(cudaGetLastError());
   return SB_OK;
 }
 
@@ -267,10 +267,9 @@ int launch_dots(sb_ctx* ctx, const double* const* a, const double* const* b, siz
   DotBody<M> body;
   for (int k = 0; k < M; ++k) body.a[k] = a[k], body.b[k] = b[k];
   SB_TRY(ensure_red_scratch(ctx, (int64_t) n));
-  ew_kernel<M, DotBody<M>><<<(unsigned) num_tiles((int64_t) n), kThreads, 0, ctx->stream>>>((int64_t) n, body,
-                                                                                          red_ptrs(ctx), nullptr);
+  SB_CUDA(launch_kernel(ctx, ew_kernel<M, DotBody<M>>, (unsigned) num_tiles((int64_t) n), kThreads, 0, (int64_t) n, body,
+                        red_ptrs(ctx), (const int*) nullptr));
   ctx->launches++;
-  SB_CUDA(cudaGetLastError());
   return launch_final<M>(ctx, (int64_t) n, StoreFinal<M>{d_out}, nullptr);
 }
 } // namespace

@@ -99,7 +99,10 @@ int vec_alloc(sb_ctx* ctx, size_t n, double** out) {
   }
   double* d = ctx->pool_free.back();
   ctx->pool_free.pop_back();
-  SB_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * ctx->vec_capacity, ctx->stream));
+  // Zero the owned part only: the halo tail belongs to the neighbours, who may already be storing the
+  // values of their next apply into it (they can run ahead of this rank's host code); it is never read
+  // before an exchange has filled it.
+  SB_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * (size_t) pad_up((int64_t) n > 0 ? (int64_t) n : 1), ctx->stream));
   *out = d;
   return SB_OK;
 }
@@ -142,7 +145,7 @@ __global__ void init_ctrl_kernel(CommCtrl* c) {
 }
 
 // ---- halo exchange: called by launch_apply before the apply kernel of a distributed operator -----------
-int halo_exchange(sb_ctx* ctx, const sb_op* op, const double* x, const int* done) {
+int halo_exchange(sb_ctx* ctx, const sb_op* op, const double* x, const int* done, int64_t* x_off) {
   const HaloDev& h = op->halo;
   const int64_t total = h.send_ptr[h.n_nbr];
   const unsigned char* xb = reinterpret_cast<const unsigned char*>(x);
@@ -150,14 +153,8 @@ int halo_exchange(sb_ctx* ctx, const sb_op* op, const double* x, const int* done
     set_error("distributed apply: x is not a vector of this context (its halo tail must live in the shared slab)");
     return SB_ERR_INVALID;
   }
-  if (ctx->comm.mode == SB_COMM_P2P) {
-    const int64_t x_off = (int64_t) (xb - ctx->slab);
-    const unsigned grid = (unsigned) std::max<int64_t>(1, std::min<int64_t>(2 * ctx->sm_count, (total + 4 * kThreads - 1) / (4 * kThreads)));
-    halo_pack_p2p_kernel<<<grid, kThreads, 0, ctx->stream>>>(ctx->comm, h, x, x_off, done);
-    ctx->launches++;
-    SB_CUDA(cudaGetLastError());
-    return SB_OK;
-  }
+  *x_off = (int64_t) (xb - ctx->slab);
+  if (ctx->comm.mode == SB_COMM_P2P) return SB_OK; // the exchange is fused into the apply kernel (halo_pack_role)
   // NCCL: pack -> grouped send/recv straight into the halo tail of x
   NcclApi* api = nccl_api();
   if (total > ctx->sendbuf_cap) {
@@ -167,9 +164,8 @@ int halo_exchange(sb_ctx* ctx, const sb_op* op, const double* x, const int* done
     SB_CUDA(cudaMalloc(&ctx->d_sendbuf, sizeof(double) * ctx->sendbuf_cap));
   }
   const unsigned grid = (unsigned) std::max<int64_t>(1, std::min<int64_t>(2 * ctx->sm_count, (total + 4 * kThreads - 1) / (4 * kThreads)));
-  halo_pack_local_kernel<<<grid, kThreads, 0, ctx->stream>>>(h, x, ctx->d_sendbuf, done);
+  SB_CUDA(launch_kernel(ctx, halo_pack_local_kernel, grid, kThreads, 0, h, x, ctx->d_sendbuf, done));
   ctx->launches++;
-  SB_CUDA(cudaGetLastError());
   ncclComm_t comm = (ncclComm_t) ctx->nccl;
   double* tail = const_cast<double*>(x) + op->halo_base;
   SB_NCCL(api->GroupStart());

@@ -2,14 +2,17 @@
 // in-kernel all-reduce (DESIGN.md "Multi-GPU").
 //
 // P2P protocol (all state lives in each rank's CommCtrl, written by peers over NVLink):
-//   halo exchange, apply #s on every rank:
-//     pack kernel:   block 0 first tells each neighbour "I have finished reading the halos of apply
-//                    #s-1" (ack_flag, true by stream order); every CTA waits until each neighbour has
-//                    acked #s-1 (its halo tail may be overwritten), stores its share of boundary
-//                    values straight into the neighbours' halo tails, fences; the last CTA (ticket)
-//                    release-stores halo_flag[me] = s at every neighbour and bumps apply_seq.
-//     apply kernel:  CTAs of boundary tiles acquire halo_flag[q] >= apply_seq for every neighbour q
-//                    before their first gather; interior tiles (scheduled first) never wait.
+//   halo exchange, apply #s = apply_seq + 1 on every rank -- all inside the apply kernel:
+//     pack CTAs      (the first n_pack blocks of the grid, so they are scheduled first and overlap the
+//                    interior tiles): block 0 tells each neighbour "I have finished reading the halos of
+//                    apply #s-1" (ack_flag; true because griddepcontrol.wait has returned); every pack CTA
+//                    waits until each neighbour has acked #s-1 (its halo tail may be overwritten), stores
+//                    its share of boundary values straight into the neighbours' halo tails, fences; the
+//                    last one (ticket) release-stores halo_flag[me] = s at every neighbour.
+//     boundary tiles acquire halo_flag[q] >= s for every neighbour q before their first gather;
+//                    interior tiles never wait.
+//     apply_seq is bumped by the one-CTA kernel that follows the apply (final reduce, or seq_bump_kernel
+//                    for a plain sb_apply), so all CTAs of an apply kernel read the same value.
 //   all-reduce #a (inside the one-CTA final-reduce kernel): thread (r, d) stores local sum d into
 //     rank r's mailbox ar_slot[a&1][me][d]; then spins on its own mailbox [a&1][r][d] until the value
 //     differs from the NaN sentinel, resets it, and thread 0 adds the P values in rank order.
@@ -24,6 +27,19 @@
 namespace sb {
 
 constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+// Programmatic dependent launch: every kernel calls pdl_trigger() (dependents may be scheduled) and then
+// pdl_wait() (all prerequisite grids have completed and their writes are visible) before it touches
+// anything a previous kernel wrote. Both are no-ops for kernels launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// The solver's stop flag, read around L1.
+__device__ __forceinline__ bool is_done(const int* done) {
+  if (done == nullptr) return false;
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(done) : "memory");
+  return v != 0;
+}
 
 struct HaloDev {
   int32_t n_nbr = 0;               // 0: operator is not distributed
@@ -74,21 +90,22 @@ __device__ __forceinline__ void wait_flag_ge(const unsigned long long* flag, uns
 }
 
 // ---- halo pack, P2P: boundary values go straight into the neighbours' halo tails -------------------
-// x_off: byte offset of the vector inside the slab (identical on every rank).
-static __global__ void __launch_bounds__(kThreads) halo_pack_p2p_kernel(CommDev comm, HaloDev halo, const double* __restrict__ x,
-                                                                 int64_t x_off, const int* __restrict__ done) {
-  if (done != nullptr && *done != 0) return;
+// Run by the first `n_pack` CTAs of the apply kernel. x_off: byte offset of the vector inside the slab
+// (identical on every rank).
+__device__ __forceinline__ void halo_pack_role(const CommDev& comm, const HaloDev& halo, const double* __restrict__ x,
+                                               int64_t x_off, int n_pack) {
   CommCtrl* me = comm.ctrl(comm.rank);
-  const unsigned long long seq = me->apply_seq + 1; // this apply's number (bumped by the last CTA below)
+  const unsigned long long seq = ld_acquire_sys(&me->apply_seq) + 1; // this apply's number
   if (blockIdx.x == 0 && threadIdx.x < halo.n_nbr) {
-    // stream order: every earlier apply of this rank has completed -> its halos are free to overwrite
+    // every earlier kernel of this rank has completed (griddepcontrol.wait) -> the halos of apply
+    // #seq-1 are free to overwrite
     st_release_sys(&comm.ctrl(halo.nbr_rank[threadIdx.x])->ack_flag[comm.rank], seq - 1);
   }
   if (threadIdx.x < halo.n_nbr)
     wait_flag_ge(&me->ack_flag[halo.nbr_rank[threadIdx.x]], seq - 1, me, 0xA000 + threadIdx.x);
   __syncthreads();
   const int64_t total = halo.send_ptr[halo.n_nbr];
-  for (int64_t i = (int64_t) blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t) gridDim.x * kThreads) {
+  for (int64_t i = (int64_t) blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t) n_pack * kThreads) {
     int k = 0;
 #pragma unroll
     for (int q = 1; q < kMaxRanks; ++q) k += (q < halo.n_nbr && i >= halo.send_ptr[q]) ? 1 : 0;
@@ -99,31 +116,32 @@ static __global__ void __launch_bounds__(kThreads) halo_pack_p2p_kernel(CommDev 
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned long long ticket = atomicAdd(&me->pack_ticket, 1ull);
-    if (ticket == (unsigned long long) gridDim.x - 1) {
+    if (ticket == (unsigned long long) n_pack - 1) {
       me->pack_ticket = 0;
       __threadfence_system();
       for (int k = 0; k < halo.n_nbr; ++k) st_release_sys(&comm.ctrl(halo.nbr_rank[k])->halo_flag[comm.rank], seq);
-      me->apply_seq = seq;
     }
   }
+}
+
+// Plain sb_apply on a distributed operator has no final-reduce kernel behind it: this bumps apply_seq.
+static __global__ void seq_bump_kernel(CommCtrl* me, const int* __restrict__ done) {
+  pdl_trigger();
+  pdl_wait();
+  if (is_done(done)) return;
+  me->apply_seq = me->apply_seq + 1;
 }
 
 // NCCL mode: gather into a contiguous local send buffer.
 static __global__ void __launch_bounds__(kThreads) halo_pack_local_kernel(HaloDev halo, const double* __restrict__ x,
                                                                    double* __restrict__ sendbuf,
                                                                    const int* __restrict__ done) {
-  if (done != nullptr && *done != 0) return;
+  pdl_trigger();
+  pdl_wait();
+  if (is_done(done)) return;
   const int64_t total = halo.send_ptr[halo.n_nbr];
   for (int64_t i = (int64_t) blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t) gridDim.x * kThreads)
     sendbuf[i] = x[halo.send_idx[i]];
-}
-
-// Called by the CTAs of boundary tiles before their first gather (P2P mode).
-__device__ __forceinline__ void halo_wait(const CommDev& comm, const HaloDev& halo) {
-  CommCtrl* me = comm.ctrl(comm.rank);
-  if (threadIdx.x < halo.n_nbr)
-    wait_flag_ge(&me->halo_flag[halo.nbr_rank[threadIdx.x]], me->apply_seq, me, 0xB000 + threadIdx.x);
-  __syncthreads();
 }
 
 // ---- in-kernel all-reduce (P2P), called by all threads of the one-CTA final-reduce kernel ----------

@@ -67,7 +67,8 @@ constexpr unsigned long long kArSentinel = 0xFFF8DEADBEEF0001ull; // a NaN paylo
 struct CommCtrl {
   unsigned long long halo_flag[kMaxRanks]; // [src]: halo values of apply #seq from rank src have landed
   unsigned long long ack_flag[kMaxRanks];  // [src]: rank src has finished reading the halos of apply #seq
-  unsigned long long apply_seq;            // applies issued so far by this rank (device-side: graph replay safe)
+  unsigned long long apply_seq;            // distributed applies completed by this rank (bumped by the one-CTA kernel
+                                           // that follows each apply, so it is stable while an apply kernel runs)
   unsigned long long ar_seq;               // all-reduces completed so far by this rank
   unsigned long long pack_ticket;          // last-CTA detection of the pack kernel
   unsigned long long error;                // set before a spin loop gives up
@@ -124,9 +125,26 @@ struct sb_ctx {
   // experiments only (SB_DEBUG env): bit1 = skip the halo exchange, bit2 = skip the cross-rank all-reduce
   // (results are wrong on purpose; used to attribute multi-GPU time, never set in tests or bench lines)
   int debug = 0;
+  // programmatic dependent launch (SB_PDL=0 disables): every kernel of the library starts with
+  // griddepcontrol.wait, so launching it with the programmatic-serialization attribute lets its CTAs
+  // become resident (and prefetch operator slices) while the previous kernel drains its last wave.
+  int pdl = 1;
 };
 
 namespace sb {
+// Launch on the context's stream, with the PDL attribute when enabled.
+template<class... KArgs, class... Args>
+inline cudaError_t launch_kernel(sb_ctx* ctx, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = ctx->pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int ensure_red_scratch(sb_ctx* ctx, int64_t n);
 // vector storage: pool block in multi-GPU mode, cudaMalloc otherwise (zero-filled either way)
 int vec_alloc(sb_ctx* ctx, size_t n, double** out);

@@ -34,10 +34,11 @@ __device__ __forceinline__ double warp_butterfly(double v) {
   return v;
 }
 
-// First element handled by this lane in sub-iteration j of its CTA tile.
-__device__ __forceinline__ int64_t lane_elem(int j) {
+// First element handled by this lane in sub-iteration j of tile `tile` (= blockIdx.x, except in the
+// distributed apply kernel whose first CTAs are halo-pack CTAs).
+__device__ __forceinline__ int64_t lane_elem(int64_t tile, int j) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  return (int64_t) blockIdx.x * kTile + warp * (kTile / kWarps) + j * 64 + 2 * lane;
+  return tile * kTile + warp * (kTile / kWarps) + j * 64 + 2 * lane;
 }
 
 // CTA-level combine of SB_TREE v1: warp butterflies, then the 8 warp sums are added left to right and
@@ -47,7 +48,7 @@ __device__ __forceinline__ int64_t lane_elem(int j) {
 // must wait for the CTA's outstanding y stores, stretched every CTA's lifetime and cost ~25 us per
 // reducing kernel at 10 M cells, against ~2 us for the extra launch.)
 template<int ND>
-__device__ __forceinline__ void block_reduce_partials(double (&acc)[ND], const RedPtrs& red) {
+__device__ __forceinline__ void block_reduce_partials(double (&acc)[ND], const RedPtrs& red, int64_t tile) {
   __shared__ double s_w[ND][kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -61,7 +62,7 @@ __device__ __forceinline__ void block_reduce_partials(double (&acc)[ND], const R
     double s = s_w[d][0];
 #pragma unroll
     for (int w = 1; w < kWarps; ++w) s = __dadd_rn(s, s_w[d][w]);
-    red.partials[(int64_t) d * red.cap_tiles + blockIdx.x] = s;
+    red.partials[(int64_t) d * red.cap_tiles + tile] = s;
   }
 }
 
@@ -71,8 +72,10 @@ __device__ __forceinline__ void block_reduce_partials(double (&acc)[ND], const R
 // thread: that is where the solver scalars (alpha, beta, residual, stop flag) are updated.
 template<int ND, class Final>
 __global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles, RedPtrs red, Final fin, CommDev comm,
-                                                                const int* __restrict__ done) {
-  if (done != nullptr && *done != 0) return;
+                                                                CommCtrl* bump, const int* __restrict__ done) {
+  pdl_trigger();
+  pdl_wait();
+  if (is_done(done)) return;
   __shared__ double s_w[ND][kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kBatch = 8;
@@ -117,7 +120,10 @@ __global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles,
   }
   // multi-GPU, P2P mode: exchange the rank sums with every peer inside this kernel (rank-ordered total)
   if (comm.mode == SB_COMM_P2P && comm.world > 1) allreduce_p2p<ND>(comm, sums);
-  if (threadIdx.x == 0) fin(sums);
+  if (threadIdx.x == 0) {
+    fin(sums);
+    if (bump != nullptr) bump->apply_seq = bump->apply_seq + 1; // the distributed apply in front of me is complete
+  }
 }
 
 template<int M>
@@ -132,7 +138,9 @@ struct StoreFinal {
 // NCCL mode: the solver's scalar update runs after ncclAllReduce has combined the rank sums.
 template<int ND, class Final>
 __global__ void scalar_final_kernel(const double* __restrict__ sums, Final fin, const int* __restrict__ done) {
-  if (done != nullptr && *done != 0) return;
+  pdl_trigger();
+  pdl_wait();
+  if (is_done(done)) return;
   double s[ND];
 #pragma unroll
   for (int d = 0; d < ND; ++d) s[d] = sums[d];
@@ -143,27 +151,23 @@ int nccl_allreduce_sum(sb_ctx* ctx, double* d_buf, int count); // sb_comm.cu
 
 // Launch helper shared by all reducing kernels: the one-CTA final stage, right behind the producer.
 template<int ND, class Final>
-inline int launch_final(sb_ctx* ctx, int64_t n, const Final& fin, const int* done) {
+inline int launch_final(sb_ctx* ctx, int64_t n, const Final& fin, const int* done, CommCtrl* bump = nullptr) {
   const RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
   if (ctx->debug & 4) { // experiment: rank-local sums only
-    final_reduce_kernel<ND, Final><<<1, kThreads, 0, ctx->stream>>>(num_tiles(n), red, fin, CommDev{}, done);
+    SB_CUDA(launch_kernel(ctx, final_reduce_kernel<ND, Final>, 1, kThreads, 0, num_tiles(n), red, fin, CommDev{}, bump, done));
     ctx->launches++;
-    SB_CUDA(cudaGetLastError());
     return SB_OK;
   }
   if (ctx->comm.mode == SB_COMM_NCCL && ctx->comm.world > 1) {
-    final_reduce_kernel<ND, StoreFinal<ND>>
-        <<<1, kThreads, 0, ctx->stream>>>(num_tiles(n), red, StoreFinal<ND>{ctx->d_ar}, CommDev{}, done);
-    SB_CUDA(cudaGetLastError());
+    SB_CUDA(launch_kernel(ctx, final_reduce_kernel<ND, StoreFinal<ND>>, 1, kThreads, 0, num_tiles(n), red,
+                          StoreFinal<ND>{ctx->d_ar}, CommDev{}, (CommCtrl*) nullptr, done));
     SB_TRY(nccl_allreduce_sum(ctx, ctx->d_ar, ND));
-    scalar_final_kernel<ND, Final><<<1, 1, 0, ctx->stream>>>(ctx->d_ar, fin, done);
+    SB_CUDA(launch_kernel(ctx, scalar_final_kernel<ND, Final>, 1, 1, 0, (const double*) ctx->d_ar, fin, done));
     ctx->launches += 2;
-    SB_CUDA(cudaGetLastError());
     return SB_OK;
   }
-  final_reduce_kernel<ND, Final><<<1, kThreads, 0, ctx->stream>>>(num_tiles(n), red, fin, ctx->comm, done);
+  SB_CUDA(launch_kernel(ctx, final_reduce_kernel<ND, Final>, 1, kThreads, 0, num_tiles(n), red, fin, ctx->comm, bump, done));
   ctx->launches++;
-  SB_CUDA(cudaGetLastError());
   return SB_OK;
 }
 
@@ -178,16 +182,18 @@ struct NoFinal {
 template<int ND, class Body>
 __global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, Body body, RedPtrs red,
                                                       const int* __restrict__ done) {
-  if (done != nullptr && *done != 0) return;
+  pdl_trigger();
+  pdl_wait();
+  if (is_done(done)) return;
   typename Body::Regs r[kSub];
 #pragma unroll
-  for (int j = 0; j < kSub; ++j) body.load(lane_elem(j), r[j]);
+  for (int j = 0; j < kSub; ++j) body.load(lane_elem(blockIdx.x, j), r[j]);
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
   for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
 #pragma unroll
-  for (int j = 0; j < kSub; ++j) body.run(lane_elem(j), n, r[j], acc);
-  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red);
+  for (int j = 0; j < kSub; ++j) body.run(lane_elem(blockIdx.x, j), n, r[j], acc);
+  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, blockIdx.x);
 }
 
 // masked accumulation: out-of-range elements contribute +0.0 (SB_TREE v1)

@@ -37,19 +37,22 @@ struct OpDev {
   int32_t debug = 0; // experiments only (SB_DEBUG env): bit0 = skip the gathers
 };
 
-// Multi-GPU (P2P mode): what the apply kernel needs to wait for its halo. n_nbr == 0: no waiting.
+// Multi-GPU (P2P mode): what the apply kernel needs for the fused halo exchange. n_pack == 0: none.
 struct ApplyDist {
-  CommCtrl* ctrl = nullptr;        // this rank's control block
-  int32_t n_nbr = 0;
-  int32_t first_boundary_tile = 0; // row tiles >= this one contain boundary cells (they read the halo)
-  int32_t nbr_rank[kMaxRanks] = {};
-  int32_t coherent_gather = 0;     // 1: gather x with ld.global.ca instead of the read-only path
+  CommDev comm;
+  HaloDev halo;
+  int64_t x_off = 0;           // byte offset of x inside the slab (the same on every rank)
+  int32_t n_pack = 0;          // the first n_pack CTAs of the grid pack + push my boundary values
+  int32_t coherent_gather = 0; // 1: gather x with ld.global.ca instead of the read-only path
 };
 
-__device__ __forceinline__ void apply_halo_wait(const ApplyDist& ad) {
-  if (ad.n_nbr > 0 && (int) blockIdx.x >= ad.first_boundary_tile) {
-    if (threadIdx.x < ad.n_nbr)
-      wait_flag_ge(&ad.ctrl->halo_flag[ad.nbr_rank[threadIdx.x]], ad.ctrl->apply_seq, ad.ctrl, 0xB000 + threadIdx.x);
+// Boundary tiles (they read the halo tail) wait until every neighbour's values of THIS apply have landed.
+__device__ __forceinline__ void apply_halo_wait(const ApplyDist& ad, int64_t tile) {
+  if (ad.n_pack > 0 && tile >= ad.halo.first_boundary_tile) {
+    CommCtrl* me = ad.comm.ctrl(ad.comm.rank);
+    if (threadIdx.x < ad.halo.n_nbr)
+      wait_flag_ge(&me->halo_flag[ad.halo.nbr_rank[threadIdx.x]], ld_acquire_sys(&me->apply_seq) + 1, me,
+                   0xB000 + threadIdx.x);
     __syncthreads();
   }
 }
@@ -182,14 +185,21 @@ template<int FORM, int W, int ND, bool RESID, class Epi>
 __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double* __restrict__ x, double* __restrict__ y,
                                                          Epi epi, RedPtrs red, ApplyDist ad,
                                                          const int* __restrict__ done) {
-  if (done != nullptr && *done != 0) return;
-  apply_halo_wait(ad);
+  pdl_trigger();
+  pdl_wait();
+  if (is_done(done)) return;
+  if (ad.n_pack > 0 && (int) blockIdx.x < ad.n_pack) {
+    halo_pack_role(ad.comm, ad.halo, x, ad.x_off, ad.n_pack);
+    return;
+  }
+  const int64_t tile = (int64_t) blockIdx.x - ad.n_pack;
+  apply_halo_wait(ad, tile);
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
   for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
 #pragma unroll 1
   for (int j = 0; j < kSub; ++j) {
-    const int64_t e0 = lane_elem(j);
+    const int64_t e0 = lane_elem(tile, j);
     const double2 xo = ld2(x, e0);
     typename Epi::Regs er;
     epi.load(e0, er);
@@ -202,7 +212,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double*
     st2(y, e0, out);
     if constexpr (!RESID) epi.run(e0, op.n, xo, out, er, acc);
   }
-  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red);
+  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, tile);
 }
 
 
@@ -267,18 +277,31 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
   using L = StageLayout<W, Epi::kExtra>;
   extern __shared__ __align__(128) unsigned char sb_smem[];
   __shared__ __align__(8) uint64_t bars[kWarps][kStages];
-  if (done != nullptr && *done != 0) return;
+  pdl_trigger();
+  if (ad.n_pack > 0 && (int) blockIdx.x < ad.n_pack) { // halo-pack CTAs: scheduled first, overlap the interior tiles
+    pdl_wait();
+    if (!is_done(done)) halo_pack_role(ad.comm, ad.halo, x, ad.x_off, ad.n_pack);
+    return;
+  }
+  const int64_t tile = (int64_t) blockIdx.x - ad.n_pack;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* wbase = sb_smem + (size_t) warp * kStages * L::bytes;
-  const int64_t row0 = (int64_t) blockIdx.x * kTile + warp * (kTile / kWarps);
+  const int64_t row0 = tile * kTile + warp * (kTile / kWarps);
 
-  auto issue = [&](int j) { // elected lane: fetch stage j (64 rows) into ring slot j % kStages
+  // A stage = the operator's slice record (never written by a kernel: may be fetched BEFORE
+  // griddepcontrol.wait, i.e. while the previous kernel is still draining) + this warp's own run of x
+  // (+ the epilogue vector), which previous kernels produce (fetched after the wait).
+  auto issue_op = [&](int j) {
+    const int s = j % kStages;
+    uint64_t* bar = &bars[warp][s];
+    mbar_expect_tx(bar, (uint32_t) L::bytes);
+    bulk_g2s(wbase + s * L::bytes, op.blk + ((row0 + j * 64) >> 6) * (int64_t) L::slice, L::slice, bar);
+  };
+  auto issue_vec = [&](int j) {
     const int s = j % kStages;
     unsigned char* dst = wbase + s * L::bytes;
     uint64_t* bar = &bars[warp][s];
     const int64_t r = row0 + j * 64;
-    mbar_expect_tx(bar, (uint32_t) L::bytes);
-    bulk_g2s(dst, op.blk + (r >> 6) * (int64_t) L::slice, L::slice, bar);
     bulk_g2s(dst + L::xown, x + r, 512, bar);
     if constexpr (Epi::kExtra) bulk_g2s(dst + L::extra, epi.extra() + r, 512, bar);
   };
@@ -289,10 +312,20 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
-    for (int j = 0; j < kStages; ++j) issue(j);
+    for (int j = 0; j < kStages; ++j) issue_op(j);
+  }
+  pdl_wait();
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kStages; ++j) issue_vec(j);
   }
   __syncwarp();
-  apply_halo_wait(ad); // the streamed operands are already in flight while boundary tiles wait
+  if (is_done(done)) { // drain the copies in flight: a CTA must not exit with bulk copies landing in its smem
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_wait(&bars[warp][s], 0);
+    return;
+  }
+  apply_halo_wait(ad, tile); // the streamed operands are already in flight while boundary tiles wait
 
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
@@ -315,7 +348,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     typename Epi::Regs er;
     if constexpr (Epi::kExtra) epi.from_stage(er, reinterpret_cast<const double2*>(src + L::extra)[lane]);
     __syncwarp(); // every lane has copied its slice out of the ring slot
-    if (lane == 0 && j + kStages < kSub) issue(j + kStages);
+    if (lane == 0 && j + kStages < kSub) issue_op(j + kStages), issue_vec(j + kStages);
 
     double g0[W], g1[W];
     if (op.debug & 1) {
@@ -346,7 +379,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     st2(y, e0, out);
     if constexpr (!RESID) epi.run(e0, op.n, xo, out, er, acc);
   }
-  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red);
+  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, tile);
 }
 
 } // namespace sb
@@ -375,31 +408,35 @@ inline bool apply_v1_forced() {
   return forced;
 }
 
-int halo_exchange(sb_ctx* ctx, const sb_op* op, const double* x, const int* done); // sb_comm.cu
+int halo_exchange(sb_ctx* ctx, const sb_op* op, const double* x, const int* done, int64_t* x_off); // sb_comm.cu
 
 // Launch y <- A x (+ epilogue) on the context's stream, dispatching on form and ELL width.
 template<int ND, bool RESID, class Epi, class Final>
 int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const Epi& epi, const Final& fin,
                  const int* done) {
   const OpDev& d = op->d;
-  const unsigned grid = (unsigned) num_tiles(d.n);
   if constexpr (ND > 0) {
     SB_TRY(ensure_red_scratch(ctx, d.n));
   }
   const RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
   ApplyDist ad;
+  CommCtrl* bump = nullptr;
   if (op->distributed && ctx->comm.world > 1) {
     const bool exchange = op->halo.n_nbr > 0 && !(ctx->debug & 2);
-    if (exchange) SB_TRY(halo_exchange(ctx, op, x, done));
+    int64_t x_off = 0;
+    // NCCL: pack kernel + grouped send/recv in front of the apply. P2P: validated here, done inside the apply kernel.
+    if (exchange) SB_TRY(halo_exchange(ctx, op, x, done, &x_off));
     if (ctx->comm.mode == SB_COMM_P2P && exchange) {
-      ad.ctrl = ctx->comm.ctrl(ctx->comm.rank);
-      ad.n_nbr = op->halo.n_nbr, ad.first_boundary_tile = op->halo.first_boundary_tile;
-      for (int k = 0; k < op->halo.n_nbr; ++k) ad.nbr_rank[k] = op->halo.nbr_rank[k];
+      ad.comm = ctx->comm, ad.halo = op->halo, ad.x_off = x_off;
+      const int64_t total = op->halo.send_ptr[op->halo.n_nbr];
+      ad.n_pack = (int32_t) std::max<int64_t>(1, std::min<int64_t>(64, (total + 2 * kThreads - 1) / (2 * kThreads)));
       ad.coherent_gather = 1;
+      bump = ctx->comm.ctrl(ctx->comm.rank);
     }
   }
-#define SB_LAUNCH(FORM, W)                                                                       \
-  apply_kernel<FORM, W, ND, RESID, Epi><<<grid, kThreads, 0, ctx->stream>>>(d, x, y, epi, red, ad, done)
+  const unsigned grid = (unsigned) (num_tiles(d.n) + ad.n_pack);
+#define SB_LAUNCH(FORM, W) \
+  SB_CUDA(launch_kernel(ctx, apply_kernel<FORM, W, ND, RESID, Epi>, grid, kThreads, 0, d, x, y, epi, red, ad, done))
 #define SB_WIDTHS(FORM)                   \
   switch (d.width) {                      \
     case 0: case 1: SB_LAUNCH(FORM, 1); break; \
@@ -417,14 +454,14 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
   if (d.form == SB_FORM_COEF && d.blk != nullptr) {
 #define SB_LAUNCH_TMA(W)                                                                                        \
   {                                                                                                             \
-    auto kern = apply_kernel_tma<W, ND, RESID, Epi>;                                                     \
+    auto kern = apply_kernel_tma<W, ND, RESID, Epi>;                                                            \
     constexpr int smem = StageLayout<W, Epi::kExtra>::cta_bytes;                                                \
     static bool configured = false;                                                                             \
     if (!configured) {                                                                                          \
       SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
       configured = true;                                                                                        \
     }                                                                                                           \
-    kern<<<grid, kThreads, smem, ctx->stream>>>(d, x, y, epi, red, ad, done);                                  \
+    SB_CUDA(launch_kernel(ctx, kern, grid, kThreads, smem, d, x, y, epi, red, ad, done));                       \
   }
     switch (d.width) {
       case 0: case 1: SB_LAUNCH_TMA(1) break;
@@ -448,8 +485,11 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
 #undef SB_WIDTHS
 #undef SB_LAUNCH
   ctx->launches++;
-  SB_CUDA(cudaGetLastError());
-  if constexpr (ND > 0) return launch_final<ND>(ctx, d.n, fin, done);
+  if constexpr (ND > 0) return launch_final<ND>(ctx, d.n, fin, done, bump);
+  if (bump != nullptr) {
+    SB_CUDA(launch_kernel(ctx, seq_bump_kernel, 1, 1, 0, bump, done));
+    ctx->launches++;
+  }
   return SB_OK;
 }
 

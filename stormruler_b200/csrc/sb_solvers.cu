@@ -265,9 +265,8 @@ struct BiEndBody { // x = (x + alpha*p) + omega*r ; r -= omega*t ; acc0 += r.r ;
 template<int ND, class Body, class Final>
 int launch_ew(sb_ctx* ctx, int64_t n, const Body& body, const Final& fin, const int* done) {
   RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
-  ew_kernel<ND, Body><<<(unsigned) num_tiles(n), kThreads, 0, ctx->stream>>>(n, body, red, done);
+  SB_CUDA(launch_kernel(ctx, ew_kernel<ND, Body>, (unsigned) num_tiles(n), kThreads, 0, n, body, red, done));
   ctx->launches++;
-  SB_CUDA(cudaGetLastError());
   if constexpr (ND > 0) return launch_final<ND>(ctx, n, fin, done);
   return SB_OK;
 }
