@@ -125,10 +125,12 @@ struct sb_ctx {
   // experiments only (SB_DEBUG env): bit1 = skip the halo exchange, bit2 = skip the cross-rank all-reduce
   // (results are wrong on purpose; used to attribute multi-GPU time, never set in tests or bench lines)
   int debug = 0;
-  // programmatic dependent launch (SB_PDL=0 disables): every kernel of the library starts with
+  // programmatic dependent launch (SB_PDL=1 enables): every kernel of the library starts with
   // griddepcontrol.wait, so launching it with the programmatic-serialization attribute lets its CTAs
   // become resident (and prefetch operator slices) while the previous kernel drains its last wave.
-  int pdl = 1;
+  // Off by default: measured on B200 it gains 1-2 % with plain stream launches but LOSES 4-7 % inside a
+  // replayed CUDA graph (programmatic edges), and the graph is the faster of the two.
+  int pdl = 0;
 };
 
 namespace sb {

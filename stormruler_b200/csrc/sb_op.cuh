@@ -66,8 +66,6 @@ __device__ __forceinline__ double gather(const double* p, int coherent) {
 // Epilogues fuse dot products into the apply: they see the input pair x[e0..e0+1] and the freshly
 // computed output pair, so <x,Ax>-style reductions cost no extra vector pass.
 struct NoEpi {
-  static constexpr bool kExtra = false;
-  __device__ __forceinline__ const double* extra() const { return nullptr; }
   struct Regs {};
   __device__ __forceinline__ void load(int64_t, Regs&) const {}
   __device__ __forceinline__ void run(int64_t, int64_t, double2, double2, Regs&, double (&)[1]) const {}
@@ -75,8 +73,6 @@ struct NoEpi {
 
 // acc[0] += x.y
 struct EpiXY {
-  static constexpr bool kExtra = false;
-  __device__ __forceinline__ const double* extra() const { return nullptr; }
   struct Regs {};
   __device__ __forceinline__ void load(int64_t, Regs&) const {}
   __device__ __forceinline__ void run(int64_t e0, int64_t n, double2 x, double2 y, Regs&, double (&acc)[1]) const {
@@ -87,13 +83,10 @@ struct EpiXY {
 // acc[0] += u.y  (u: a third vector, e.g. r~ in BiCGStab)
 struct EpiUY {
   const double* u;
-  static constexpr bool kExtra = true;
-  __device__ __forceinline__ const double* extra() const { return u; }
   struct Regs {
     double2 u;
   };
   __device__ __forceinline__ void load(int64_t e0, Regs& r) const { r.u = ld2(u, e0); }
-  __device__ __forceinline__ void from_stage(Regs& r, double2 v) const { r.u = v; }
   __device__ __forceinline__ void run(int64_t e0, int64_t n, double2, double2 y, Regs& r, double (&acc)[1]) const {
     acc_pair(acc[0], e0, n, __dmul_rn(r.u.x, y.x), __dmul_rn(r.u.y, y.y));
   }
@@ -101,8 +94,6 @@ struct EpiUY {
 
 // acc[0] += y.y ; acc[1] += y.x   (BiCGStab: <t,t>, <t,r>)
 struct EpiYYandYX {
-  static constexpr bool kExtra = false;
-  __device__ __forceinline__ const double* extra() const { return nullptr; }
   struct Regs {};
   __device__ __forceinline__ void load(int64_t, Regs&) const {}
   __device__ __forceinline__ void run(int64_t e0, int64_t n, double2 x, double2 y, Regs&, double (&acc)[2]) const {
@@ -115,13 +106,10 @@ struct EpiYYandYX {
 // The kernel stores the value returned through `out`.
 struct EpiResidual {
   const double* b;
-  static constexpr bool kExtra = true;
-  __device__ __forceinline__ const double* extra() const { return b; }
   struct Regs {
     double2 b;
   };
   __device__ __forceinline__ void load(int64_t e0, Regs& r) const { r.b = ld2(b, e0); }
-  __device__ __forceinline__ void from_stage(Regs& r, double2 v) const { r.b = v; }
 };
 
 template<int FORM, int W>
@@ -230,15 +218,14 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double*
 // The row->lane mapping, operation order and reduction tree are identical to v1 (bit-identical output).
 constexpr int kStages = 2;
 
-template<int W, bool EXTRA>
+template<int W>
 struct StageLayout {
   static constexpr int col = 0;              // W slices of 64 int32   } one slice record of the
   static constexpr int coef = W * 256;       // W slices of 64 fp64    } blocked operator layout,
   static constexpr int diag = coef + W * 512; //                        } fetched by ONE bulk copy
   static constexpr int slice = diag + 512;
   static constexpr int xown = slice;
-  static constexpr int extra = xown + 512;
-  static constexpr int bytes = extra + (EXTRA ? 512 : 0);
+  static constexpr int bytes = xown + 512;
   static constexpr int cta_bytes = bytes * kStages * kWarps;
 };
 
@@ -274,7 +261,7 @@ template<int W, int ND, bool RESID, class Epi>
 __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const double* __restrict__ x,
                                                             double* __restrict__ y, Epi epi, RedPtrs red,
                                                             ApplyDist ad, const int* __restrict__ done) {
-  using L = StageLayout<W, Epi::kExtra>;
+  using L = StageLayout<W>;
   extern __shared__ __align__(128) unsigned char sb_smem[];
   __shared__ __align__(8) uint64_t bars[kWarps][kStages];
   pdl_trigger();
@@ -289,8 +276,8 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
   const int64_t row0 = tile * kTile + warp * (kTile / kWarps);
 
   // A stage = the operator's slice record (never written by a kernel: may be fetched BEFORE
-  // griddepcontrol.wait, i.e. while the previous kernel is still draining) + this warp's own run of x
-  // (+ the epilogue vector), which previous kernels produce (fetched after the wait).
+  // griddepcontrol.wait, i.e. while the previous kernel is still draining) + this warp's own run of x,
+  // which previous kernels produce (fetched after the wait).
   auto issue_op = [&](int j) {
     const int s = j % kStages;
     uint64_t* bar = &bars[warp][s];
@@ -303,7 +290,6 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     uint64_t* bar = &bars[warp][s];
     const int64_t r = row0 + j * 64;
     bulk_g2s(dst + L::xown, x + r, 512, bar);
-    if constexpr (Epi::kExtra) bulk_g2s(dst + L::extra, epi.extra() + r, 512, bar);
   };
 
   if (lane == 0) {
@@ -325,6 +311,13 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     for (int s = 0; s < kStages; ++s) mbar_wait(&bars[warp][s], 0);
     return;
   }
+  // The epilogue's third vector (r~ or b) is read with plain coalesced loads, all four sub-iterations up
+  // front so they are in flight under the pipeline. (It used to be a third bulk copy per stage; with it
+  // the <r~,v> reduction was not reproducible at >= 1 M cells -- about one 64-row run per launch held other
+  // data -- although SASS, barrier accounting and compute-sanitizer showed nothing; see DESIGN.md.)
+  typename Epi::Regs er[kSub];
+#pragma unroll
+  for (int j = 0; j < kSub; ++j) epi.load(row0 + j * 64 + 2 * lane, er[j]);
   apply_halo_wait(ad, tile); // the streamed operands are already in flight while boundary tiles wait
 
   double acc[ND > 0 ? ND : 1];
@@ -345,8 +338,6 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     }
     const double2 dg = reinterpret_cast<const double2*>(src + L::diag)[lane];
     const double2 xo = reinterpret_cast<const double2*>(src + L::xown)[lane];
-    typename Epi::Regs er;
-    if constexpr (Epi::kExtra) epi.from_stage(er, reinterpret_cast<const double2*>(src + L::extra)[lane]);
     __syncwarp(); // every lane has copied its slice out of the ring slot
     if (lane == 0 && j + kStages < kSub) issue_op(j + kStages), issue_vec(j + kStages);
 
@@ -372,12 +363,12 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     double2 out = make_double2(u0, u1);
     const int64_t e0 = row0 + j * 64 + 2 * lane;
     if constexpr (RESID) {
-      out.x = __dsub_rn(er.b.x, out.x);
-      out.y = __dsub_rn(er.b.y, out.y);
+      out.x = __dsub_rn(er[j].b.x, out.x);
+      out.y = __dsub_rn(er[j].b.y, out.y);
       acc_pair(acc[0], e0, op.n, __dmul_rn(out.x, out.x), __dmul_rn(out.y, out.y));
     }
     st2(y, e0, out);
-    if constexpr (!RESID) epi.run(e0, op.n, xo, out, er, acc);
+    if constexpr (!RESID) epi.run(e0, op.n, xo, out, er[j], acc);
   }
   if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, tile);
 }
@@ -455,7 +446,7 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
 #define SB_LAUNCH_TMA(W)                                                                                        \
   {                                                                                                             \
     auto kern = apply_kernel_tma<W, ND, RESID, Epi>;                                                            \
-    constexpr int smem = StageLayout<W, Epi::kExtra>::cta_bytes;                                                \
+    constexpr int smem = StageLayout<W>::cta_bytes;                                                \
     static bool configured = false;                                                                             \
     if (!configured) {                                                                                          \
       SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \

@@ -1,0 +1,89 @@
+"""Parity and determinism at sizes where the grid spans many waves of CTAs (the small reference meshes are 3
+tiles): 1.2 M tetrahedra against the oracle bit for bit, 6 M tetrahedra run-to-run. Guards the properties the
+small cases cannot see -- inter-CTA ordering, the final-reduce stage over thousands of partials, graph replay,
+programmatic dependent launch."""
+import os
+
+import numpy as np
+import pytest
+
+import stormruler_b200 as sb
+from oracle import orc
+from stormruler_b200.mesh import CELL_TET, Mesh
+
+pytestmark = pytest.mark.gpu
+
+
+def box(n):
+    mesh = Mesh.box(CELL_TET, n, jitter=0.2, seed_jitter=42, shuffle=True, seed_shuffle=43)
+    mesh.renumber_rcm()
+    fm = orc.FaceMesh(mesh.n_cells, mesh.face_cell, mesh.face_area, mesh.face_dist, mesh.cell_vol, mesh.bface_cell,
+                      mesh.bface_area, mesh.bface_dist)
+    return mesh, fm
+
+
+@pytest.fixture(scope="module")
+def mesh_1m():
+    return box(58)   # 1 170 672 cells = 572 tiles
+
+
+@pytest.fixture(scope="module", params=[0, 1], ids=["pdl_off", "pdl_on"])
+def any_ctx(request):
+    old = os.environ.get("SB_PDL")
+    os.environ["SB_PDL"] = str(request.param)
+    c = sb.Context(0)
+    if old is None:
+        os.environ.pop("SB_PDL", None)
+    else:
+        os.environ["SB_PDL"] = old
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("solver", ["cg", "bicgstab"])
+def test_million_cell_solvers_bit_identical_to_oracle(any_ctx, mesh_1m, solver):
+    ctx = any_ctx
+    mesh, fm = mesh_1m
+    n = mesh.n_cells
+    c = mesh.cell_centers()
+    x_star = np.sin(np.pi * c[:, 0]) * np.sin(np.pi * c[:, 1]) * np.sin(np.pi * c[:, 2])
+    cpu = orc.FaceOp(fm, prefill=0, dt=-1.0, dirichlet=True)
+    rows = cpu.rows_coef()
+    rows_op = orc.RowsOp(n, *rows)
+    Solver = sb.CgSolver if solver == "cg" else sb.BiCgStabSolver
+    iters = 40
+    for form, oracle_op in ((sb.FORM_COEF, rows_op), (sb.FORM_FAITHFUL, cpu)):
+        gpu = sb.FvmOperator(ctx, mesh, prefill=0, dt=-1.0, form=form, dirichlet=True)
+        b_dev, xs = ctx.zeros(n), ctx.vector(x_star)
+        gpu.mul(b_dev, xs)
+        b = b_dev.numpy()
+        assert np.array_equal(b, oracle_op.apply(x_star)), "apply differs from the oracle at 1.2 M cells"
+        want = orc.solve(solver, oracle_op, b, num_iterations=iters, abs_tol=0.0, rel_tol=0.0, mode=orc.RED_TREE)
+        for use_graph in (False, True, True):
+            s = Solver(num_iterations=iters, absolute_error_tolerance=0.0, relative_error_tolerance=0.0,
+                       use_graph=use_graph)
+            x = ctx.zeros(n)
+            s.solve(x, b_dev, gpu)
+            assert s.iteration == iters
+            assert np.array_equal(s.history, want.hist), f"{solver} form {form} graph={use_graph}: residual history differs"
+            assert np.array_equal(s.trace, want.trace[:len(s.trace)])
+            assert np.array_equal(x.numpy(), want.x), f"{solver} form {form} graph={use_graph}: solution differs"
+
+
+@pytest.mark.parametrize("solver", ["cg", "bicgstab"])
+def test_six_million_cells_run_to_run_deterministic(any_ctx, solver):
+    ctx = any_ctx
+    mesh, _ = box(100)   # 6 000 000 cells, 2930 tiles, ~6.6 waves of the apply kernel
+    n = mesh.n_cells
+    gpu = sb.FvmOperator(ctx, mesh, prefill=0, dt=-1.0, form=sb.FORM_COEF, dirichlet=True)
+    b = ctx.vector(np.sin(0.37 * np.arange(n)))
+    Solver = sb.CgSolver if solver == "cg" else sb.BiCgStabSolver
+    runs = []
+    for use_graph in (True, True, False, True):
+        s = Solver(num_iterations=50, absolute_error_tolerance=0.0, relative_error_tolerance=0.0, use_graph=use_graph)
+        x = ctx.zeros(n)
+        s.solve(x, b, gpu)
+        runs.append((s.history.copy(), x.numpy()))
+    for hist, x in runs[1:]:
+        assert np.array_equal(hist, runs[0][0]), "residual history is not run-to-run deterministic"
+        assert np.array_equal(x, runs[0][1]), "solution is not run-to-run deterministic"
