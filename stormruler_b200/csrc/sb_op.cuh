@@ -35,6 +35,8 @@ struct OpDev {
   const unsigned char* blk = nullptr;
   int32_t slice_bytes = 0;
   int32_t debug = 0; // experiments only (SB_DEBUG env): bit0 = skip the gathers
+  int32_t zero = 0;  // always 0, but only known at run time: lets the kernel tie an instruction to a value it
+                     // must wait for without changing the arithmetic (see apply_kernel_tma)
 };
 
 // Multi-GPU (P2P mode): what the apply kernel needs for the fused halo exchange. n_pack == 0: none.
@@ -278,18 +280,19 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
   // A stage = the operator's slice record (never written by a kernel: may be fetched BEFORE
   // griddepcontrol.wait, i.e. while the previous kernel is still draining) + this warp's own run of x,
   // which previous kernels produce (fetched after the wait).
-  auto issue_op = [&](int j) {
+  // `dep` (always 0 at run time) is added to the source addresses: see the hazard note in the main loop.
+  auto issue_op = [&](int j, uint32_t dep) {
     const int s = j % kStages;
     uint64_t* bar = &bars[warp][s];
     mbar_expect_tx(bar, (uint32_t) L::bytes);
-    bulk_g2s(wbase + s * L::bytes, op.blk + ((row0 + j * 64) >> 6) * (int64_t) L::slice, L::slice, bar);
+    bulk_g2s(wbase + s * L::bytes, op.blk + ((row0 + j * 64) >> 6) * (int64_t) L::slice + dep, L::slice, bar);
   };
-  auto issue_vec = [&](int j) {
+  auto issue_vec = [&](int j, uint32_t dep) {
     const int s = j % kStages;
     unsigned char* dst = wbase + s * L::bytes;
     uint64_t* bar = &bars[warp][s];
     const int64_t r = row0 + j * 64;
-    bulk_g2s(dst + L::xown, x + r, 512, bar);
+    bulk_g2s(dst + L::xown, reinterpret_cast<const unsigned char*>(x + r) + dep, 512, bar);
   };
 
   if (lane == 0) {
@@ -298,12 +301,12 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
-    for (int j = 0; j < kStages; ++j) issue_op(j);
+    for (int j = 0; j < kStages; ++j) issue_op(j, 0u);
   }
   pdl_wait();
   if (lane == 0) {
 #pragma unroll
-    for (int j = 0; j < kStages; ++j) issue_vec(j);
+    for (int j = 0; j < kStages; ++j) issue_vec(j, 0u);
   }
   __syncwarp();
   if (is_done(done)) { // drain the copies in flight: a CTA must not exit with bulk copies landing in its smem
@@ -312,9 +315,8 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     return;
   }
   // The epilogue's third vector (r~ or b) is read with plain coalesced loads, all four sub-iterations up
-  // front so they are in flight under the pipeline. (It used to be a third bulk copy per stage; with it
-  // the <r~,v> reduction was not reproducible at >= 1 M cells -- about one 64-row run per launch held other
-  // data -- although SASS, barrier accounting and compute-sanitizer showed nothing; see DESIGN.md.)
+  // front so they are in flight under the pipeline: measured 10 % faster than staging it as a third bulk
+  // copy per stage (apply + <r~,v> at 10.1 M cells: 138 us against 152 us), and 512 B less ring per stage.
   typename Epi::Regs er[kSub];
 #pragma unroll
   for (int j = 0; j < kSub; ++j) epi.load(row0 + j * 64 + 2 * lane, er[j]);
@@ -338,8 +340,29 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     }
     const double2 dg = reinterpret_cast<const double2*>(src + L::diag)[lane];
     const double2 xo = reinterpret_cast<const double2*>(src + L::xown)[lane];
+    // WAR hazard between the generic proxy and the async proxy: the ld.shared above have been ISSUED, but
+    // their data may not have left shared memory yet (under DRAM-bound gather traffic the load/store unit
+    // queues back up), and the bulk copy issued below overwrites this very slot. So every loaded register is
+    // folded into one word and the refill's source addresses are made to depend on it (`& op.zero`: always
+    // 0, but the compiler cannot know): the copy cannot issue before the fold, the fold cannot issue before
+    // every load of the warp has returned. (Without this ~3 of 90 000 stages per launch read the NEXT
+    // stage's bytes at 6 M cells -- none at 1 M, where everything sits in L2; tests/test_gpu_scale.py.)
+    uint32_t fold = 0;
+    {
+      auto mix = [&](double v) {
+        const long long b = __double_as_longlong(v);
+        fold ^= (uint32_t) b ^ (uint32_t) (b >> 32);
+      };
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        fold ^= (uint32_t) c[k].x ^ (uint32_t) c[k].y;
+        mix(a[k].x), mix(a[k].y);
+      }
+      mix(dg.x), mix(dg.y), mix(xo.x), mix(xo.y);
+    }
+    const uint32_t dep = fold & (uint32_t) op.zero;
     __syncwarp(); // every lane has copied its slice out of the ring slot
-    if (lane == 0 && j + kStages < kSub) issue_op(j + kStages), issue_vec(j + kStages);
+    if (lane == 0 && j + kStages < kSub) issue_op(j + kStages, dep), issue_vec(j + kStages, dep);
 
     double g0[W], g1[W];
     if (op.debug & 1) {

@@ -137,6 +137,23 @@ class DistOperator:
         capi.check(self.ctx.lib.sb_apply(self.ctx.handle, self.handle, x.ptr, y.ptr))
 
 
+class DistConvDiffOperator(DistOperator):
+    """This rank's rows of the convection-diffusion operator (sb_dist_op_create_convdiff). `face_un` / `bface_un`
+    are GLOBAL per-face arrays (Mesh.face_flux); the local ones are gathered through face_global / bface_global."""
+
+    def __init__(self, ctx: DistContext, local: LocalView, nu: float, face_un, bface_un):
+        self.ctx, self.local = ctx, local
+        fu = np.ascontiguousarray(np.asarray(face_un, np.float64)[local.face_global])
+        bu = np.ascontiguousarray(np.asarray(bface_un, np.float64)[local.bface_global])
+        desc = capi.ConvDiffDesc(float(nu), fu.ctypes.data_as(capi.f64p), bu.ctypes.data_as(capi.f64p))
+        h = C.c_void_p()
+        capi.check(ctx.lib.sb_dist_op_create_convdiff(ctx.handle, C.byref(local.struct), C.byref(desc), C.byref(h)))
+        self.handle = h
+        info = capi.OpInfo()
+        capi.check(ctx.lib.sb_op_get_info(h, C.byref(info)))
+        self.info, self.n = info, int(info.n_cells)
+
+
 def gather_global(local: LocalView, x_local: np.ndarray, n_global: int) -> np.ndarray:
     """All ranks' owned values -> the global vector (on every rank). Test / reporting helper."""
     import torch

@@ -73,10 +73,18 @@ def test_million_cell_solvers_bit_identical_to_oracle(any_ctx, mesh_1m, solver):
 @pytest.mark.parametrize("solver", ["cg", "bicgstab"])
 def test_six_million_cells_run_to_run_deterministic(any_ctx, solver):
     ctx = any_ctx
-    mesh, _ = box(100)   # 6 000 000 cells, 2930 tiles, ~6.6 waves of the apply kernel
+    mesh, fm = box(100)   # 6 000 000 cells, 2930 tiles, ~6.6 waves of the apply kernel: DRAM-bound, unlike 1 M cells
     n = mesh.n_cells
     gpu = sb.FvmOperator(ctx, mesh, prefill=0, dt=-1.0, form=sb.FORM_COEF, dirichlet=True)
-    b = ctx.vector(np.sin(0.37 * np.arange(n)))
+    bh = np.sin(0.37 * np.arange(n))
+    b = ctx.vector(bh)
+    # the apply itself, against the row oracle, several launches (a stage that reads the wrong bytes shows here)
+    cpu = orc.FaceOp(fm, prefill=0, dt=-1.0, dirichlet=True)
+    want = orc.RowsOp(n, *cpu.rows_coef()).apply(bh)
+    y = ctx.zeros(n)
+    for _ in range(8):
+        gpu.mul(y, b)
+        assert np.array_equal(y.numpy(), want), "apply differs from the row oracle at 6 M cells"
     Solver = sb.CgSolver if solver == "cg" else sb.BiCgStabSolver
     runs = []
     for use_graph in (True, True, False, True):
