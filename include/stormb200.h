@@ -137,6 +137,13 @@ SB_API int sb_op_download_rows(sb_ctx* ctx, const sb_op* op, int32_t* h_col, dou
 /* y <- A(x): Operator::mul (Operator.hpp:74). x and y must not alias. */
 SB_API int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y);
 
+/* Jacobi (point-diagonal) preconditioner apply: y_i = x_i / a_ii, a_ii the operator's own diagonal (coefficient
+ * form only; the faithful form keeps no diagonal). Fills the reference's preconditioner slot
+ * (Solvers/Preconditioner.hpp:66-82, `Preconditioner<Vector>::mul`), which every reference solver already
+ * branches on (e.g. SolverBiCgStab.hpp:135-137,156-158; SolverGmres.hpp:149-156). The reference ships the
+ * identity preconditioner only (README: all others "planned"): SURVEY.md 8f rank 2. x may alias y. */
+SB_API int sb_op_jacobi(sb_ctx* ctx, const sb_op* op, const double* x, double* y);
+
 /* ---- mesh ingestion (host side, no GPU needed): replaces what the playground gets from
  * read_mesh_from_tetgen + UnstructuredMesh (Mallard/IoTetgen.hpp:44-235, MeshUnstructured.hpp:350-425,
  * 464-500, 509-554) for the hot path, in 3-D (the reference mesh layer is 2-D only):

@@ -73,7 +73,8 @@ class SolverReport(C.Structure):
 class RefOpts(C.Structure):
     _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
                 ("num_inner_iterations", C.c_int64), ("reduction_mode", C.c_int32),
-                ("relaxation_factor", C.c_double)]
+                ("relaxation_factor", C.c_double), ("pre_fn", C.c_void_p), ("pre_user", C.c_void_p),
+                ("pre_side", C.c_int32)]
 
 
 class RefReport(C.Structure):
@@ -390,12 +391,27 @@ def solve(solver: str, op, b, x0=None, num_iterations=2000, abs_tol=1e-6, rel_to
 
 REF_SOLVERS = ("cg", "cgs", "bicgstab", "bicgstabl", "gmres", "fgmres", "tfqmr", "tfqmr1", "idrs",
                "richardson")
+REF_NONLINEAR = ("jfnk",)
+
+
+class JacobiOp:
+    """y = x / diag, the point-diagonal preconditioner (restates sb_op_jacobi): a CallbackOp for ref_solve(pre=...)."""
+
+    def __init__(self, diag):
+        d = _f64(diag).copy()
+        self.n = d.shape[0]
+        self._cb = CallbackOp(lambda x: x / d, self.n)
+
+    @property
+    def callback(self):
+        return self._cb.callback
 
 
 def ref_solve(solver: str, op, b, x0=None, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6,
               num_inner=0, mode=RED_SEQ, relaxation_factor=0.0, reset_rng=True,
-              trace_cap=None) -> SolveResult:
-    """The reference's own solver headers (oracle/_ref), on a host vector."""
+              trace_cap=None, pre=None, pre_side="right") -> SolveResult:
+    """The reference's own solver headers (oracle/_ref), on a host vector. `pre`: optional operator object
+    with a .callback (e.g. JacobiOp) placed in the reference's pre_op slot; pre_side: left | right | symmetric."""
     R = ref()
     if reset_rng:
         R.ref_reset_rng()
@@ -405,7 +421,9 @@ def ref_solve(solver: str, op, b, x0=None, num_iterations=2000, abs_tol=1e-6, re
     cap_h = num_iterations + 2
     cap_t = trace_cap or (64 * num_iterations + 256)
     hist, trace = np.zeros(cap_h), np.zeros(cap_t)
-    opts = RefOpts(num_iterations, abs_tol, rel_tol, num_inner, mode, relaxation_factor)
+    pf, pu = pre.callback if pre is not None else (None, None)
+    opts = RefOpts(num_iterations, abs_tol, rel_tol, num_inner, mode, relaxation_factor, pf, pu,
+                   {"left": 0, "right": 1, "symmetric": 2}[pre_side])
     rep = RefReport()
     f, u = op.callback
     rc = R.ref_solve(solver.encode(), n, f, u, _p(b, _f64p), _p(x, _f64p), C.byref(opts), C.byref(rep),

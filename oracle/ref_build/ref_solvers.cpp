@@ -31,6 +31,7 @@
 
 #include <array>
 #include <cstring>
+#include <memory>
 #include <random>
 #include <string>
 #include <tuple>
@@ -138,6 +139,10 @@ inline HostVec& fill_randomly(HostVec& out) {
 #include <Storm/Solvers/SolverIdrs.hpp>
 #include <Storm/Solvers/SolverRichardson.hpp>
 #include <Storm/Solvers/SolverTfqmr.hpp>
+// JFNK (SolverNewton.hpp:101-173) uses BiCgStabSolver and std::numeric_limits without including them
+// ("fix the missing include"): included after SolverBiCgStab.hpp here, untouched.
+#include <limits>
+#include <Storm/Solvers/SolverNewton.hpp>
 
 namespace {
 
@@ -150,6 +155,10 @@ struct ref_opts {
   int64_t num_inner_iterations; // <= 0: keep the solver's default
   int32_t reduction_mode;
   double relaxation_factor; // Richardson only; <= 0 keeps the default 1e-4
+  // optional preconditioner in the reference's pre_op slot (Solver.hpp:74-75): y = P x through a callback
+  void (*pre_fn)(void* user, double* y, const double* x, size_t n);
+  void* pre_user;
+  int32_t pre_side;         // 0: Left, 1: Right (reference default), 2: Symmetric
 };
 
 struct ref_report {
@@ -184,6 +193,13 @@ struct CallbackOperator final : Storm::Operator<HostVec> {
   }
 };
 
+struct CallbackPreconditioner final : Storm::Preconditioner<HostVec> {
+  ref_apply_fn fn;
+  void* user;
+  void mul(HostVec& y, const HostVec& x) const override { fn(user, y.d.data(), x.d.data(), x.d.size()); }
+  void conj_mul(HostVec& x, const HostVec& y) const override { fn(user, x.d.data(), y.d.data(), y.d.size()); }
+};
+
 template<class SolverT>
 int run(size_t n, ref_apply_fn fn, void* user, const double* b, double* x, const ref_opts* o,
         ref_report* rep, double* hist, int64_t hist_cap, double* trace, int64_t trace_cap) {
@@ -196,6 +212,13 @@ int run(size_t n, ref_apply_fn fn, void* user, const double* b, double* x, const
   }
   if constexpr (requires { solver.relaxation_factor; }) {
     if (o->relaxation_factor > 0.0) solver.relaxation_factor = o->relaxation_factor;
+  }
+  if (o->pre_fn != nullptr) {
+    auto pre = std::make_unique<CallbackPreconditioner>();
+    pre->fn = o->pre_fn, pre->user = o->pre_user;
+    solver.pre_op = std::move(pre);
+    solver.pre_side = o->pre_side == 0 ? Storm::PreconditionerSide::Left
+                                       : (o->pre_side == 2 ? Storm::PreconditionerSide::Symmetric : Storm::PreconditionerSide::Right);
   }
   HostVec xv, bv;
   xv.d.assign(x, x + n);
@@ -224,7 +247,7 @@ int run(size_t n, ref_apply_fn fn, void* user, const double* b, double* x, const
 
 extern "C" {
 
-// Solver names: cg cgs bicgstab bicgstabl gmres fgmres tfqmr tfqmr1 idrs richardson.
+// Solver names: cg cgs bicgstab bicgstabl gmres fgmres tfqmr tfqmr1 idrs richardson jfnk.
 int ref_solve(const char* name, size_t n, ref_apply_fn fn, void* user, const double* b, double* x,
               const ref_opts* o, ref_report* rep, double* hist, int64_t hist_cap, double* trace,
               int64_t trace_cap) {
@@ -241,6 +264,7 @@ int ref_solve(const char* name, size_t n, ref_apply_fn fn, void* user, const dou
   REF_CASE("tfqmr1", Tfqmr1Solver);
   REF_CASE("idrs", IdrsSolver);
   REF_CASE("richardson", RichardsonSolver);
+  REF_CASE("jfnk", JfnkSolver);
 #undef REF_CASE
   return -1;
 }

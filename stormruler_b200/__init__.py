@@ -238,6 +238,10 @@ class FvmOperator:
         """Operator::mul (Operator.hpp:74)."""
         capi.check(self.ctx.lib.sb_apply(self.ctx.handle, self.handle, x.ptr, y.ptr))
 
+    def jacobi(self, y: DeviceVector, x: DeviceVector):
+        """y = D^-1 x with D the operator's diagonal (sb_op_jacobi): the Jacobi preconditioner's mul."""
+        capi.check(self.ctx.lib.sb_op_jacobi(self.ctx.handle, self.handle, x.ptr, y.ptr))
+
     def rows(self):
         """Download the row layout (col, val0, val1|None, diag|None) for integer/bit checks."""
         w, ld = self.info.width, self.info.ld

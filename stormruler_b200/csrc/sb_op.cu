@@ -357,6 +357,16 @@ int sb_op_download_rows(sb_ctx* ctx, const sb_op* op, int32_t* h_col, double* h_
   return SB_OK;
 }
 
+int sb_op_jacobi(sb_ctx* ctx, const sb_op* op, const double* x, double* y) {
+  SB_REQUIRE(ctx != nullptr && op != nullptr && x != nullptr && y != nullptr, "null argument");
+  SB_REQUIRE(op->d.form == SB_FORM_COEF, "the Jacobi preconditioner needs the coefficient form (it stores the diagonal)");
+  JacobiBody body{op->d, x, y};
+  SB_CUDA(launch_kernel(ctx, ew_kernel<0, JacobiBody>, (unsigned) num_tiles(op->d.n), kThreads, 0, op->d.n, body, RedPtrs{},
+                        (const int*) nullptr));
+  ctx->launches++;
+  return SB_OK;
+}
+
 int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y) {
   SB_REQUIRE(ctx != nullptr && op != nullptr && x != nullptr && y != nullptr, "null argument");
   SB_REQUIRE(x != y, "sb_apply: x and y must not alias");

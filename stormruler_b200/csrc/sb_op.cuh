@@ -396,6 +396,32 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
   if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, tile);
 }
 
+// y = x / diag (Jacobi). The diagonal lives inside the blocked slice records (or in OpDev::diag for the v1 layout).
+struct JacobiBody {
+  OpDev op;
+  const double* x;
+  double* y;
+  struct Regs {
+    double2 x, d;
+  };
+  __device__ __forceinline__ void load(int64_t e0, Regs& r) const {
+    r.x = ld2(x, e0);
+    if (op.blk != nullptr) {
+      const unsigned char* rec = op.blk + (e0 >> 6) * (int64_t) op.slice_bytes + (int64_t) op.width * 768;
+      r.d = *reinterpret_cast<const double2*>(rec + (e0 & 63) * 8);
+    } else {
+      r.d = ld2(op.diag, e0);
+    }
+  }
+  __device__ __forceinline__ void run(int64_t e0, int64_t n, Regs& r, double (&)[1]) const {
+    // padding rows have a zero diagonal: keep them 0 instead of producing inf/NaN
+    double2 out;
+    out.x = (e0 < n) ? __ddiv_rn(r.x.x, r.d.x) : 0.0;
+    out.y = (e0 + 1 < n) ? __ddiv_rn(r.x.y, r.d.y) : 0.0;
+    st2(y, e0, out);
+  }
+};
+
 } // namespace sb
 
 struct sb_op {

@@ -16,13 +16,14 @@ LIB_PATH = os.path.join(HERE, "host", "libstorm_dropin.so")
 
 GENERIC_SOLVERS = ("cg", "cgs", "bicgstab", "bicgstabl", "gmres", "fgmres", "tfqmr", "tfqmr1", "idrs",
                    "richardson")
+NONLINEAR_SOLVERS = ("jfnk",)   # SolverNewton.hpp:101-173, inner solve = the reference's BiCgStabSolver
 FUSED_SOLVERS = ("fused_cg", "fused_bicgstab")
 
 
 class Opts(C.Structure):
     _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
                 ("num_inner_iterations", C.c_int64), ("relaxation_factor", C.c_double),
-                ("use_graph", C.c_int32)]
+                ("use_graph", C.c_int32), ("precond", C.c_int32), ("pre_side", C.c_int32)]
 
 
 class Report(C.Structure):
@@ -69,16 +70,22 @@ class Result:
     n_apply: int
 
 
+PRE_SIDES = {"left": 0, "right": 1, "symmetric": 2}
+
+
 def solve(name: str, op, x, b, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6, num_inner=0,
-          relaxation_factor=0.0, use_graph=True, reset_rng=True, trace_cap=None) -> Result:
-    """Run solver `name` on DeviceVectors x (in/out) and b through the C++ drop-in."""
+          relaxation_factor=0.0, use_graph=True, reset_rng=True, trace_cap=None, precond=None,
+          pre_side="right") -> Result:
+    """Run solver `name` on DeviceVectors x (in/out) and b through the C++ drop-in.
+    precond: None | "jacobi" (Storm::JacobiPreconditioner in the reference's pre_op slot)."""
     L = load()
     if reset_rng:
         L.dropin_reset_rng()
     cap_h = num_iterations + 2
     cap_t = trace_cap or (64 * num_iterations + 256)
     hist, trace = np.zeros(cap_h), np.zeros(cap_t)
-    opts = Opts(num_iterations, abs_tol, rel_tol, num_inner, relaxation_factor, int(use_graph))
+    opts = Opts(num_iterations, abs_tol, rel_tol, num_inner, relaxation_factor, int(use_graph),
+                {None: 0, "jacobi": 1}[precond], PRE_SIDES[pre_side])
     rep = Report()
     rc = L.dropin_solve(name.encode(), op.ctx.handle, op.handle, x.ptr, b.ptr, x.n, C.byref(opts),
                         C.byref(rep), hist.ctypes.data_as(capi.f64p), cap_h,

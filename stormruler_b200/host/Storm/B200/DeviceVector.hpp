@@ -390,3 +390,31 @@ private:
 };
 
 } // namespace Storm
+
+#include <Storm/Solvers/Preconditioner.hpp>
+
+namespace Storm {
+
+/// Jacobi (point-diagonal) preconditioner for the device path: fills the slot every reference solver
+/// already branches on (`IterativeSolver::pre_op` / `pre_side`, Solver.hpp:74-75). y = D^-1 x with D the
+/// diagonal of the coefficient-form FVM operator (sb_op_jacobi). The reference ships only
+/// IdentityPreconditioner (Preconditioner.hpp:84-97), so this is new functionality behind its interface:
+///     solver.pre_op = std::make_unique<Storm::JacobiPreconditioner>(fvm_op);
+class JacobiPreconditioner final : public Preconditioner<DeviceVector> {
+public:
+
+  explicit JacobiPreconditioner(const FvmOperator& op) : _ctx{op.context()}, _op{op.handle()} {}
+  JacobiPreconditioner(sb_ctx* ctx, const sb_op* op) : _ctx{ctx}, _op{op} {}
+
+  void mul(DeviceVector& y, const DeviceVector& x) const override {
+    B200::check(sb_op_jacobi(_ctx, _op, x.data(), y.data()), "sb_op_jacobi");
+  }
+  void conj_mul(DeviceVector& x, const DeviceVector& y) const override { mul(x, y); } // D is real
+
+private:
+
+  sb_ctx* _ctx = nullptr;
+  const sb_op* _op = nullptr;
+};
+
+} // namespace Storm

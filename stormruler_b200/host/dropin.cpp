@@ -5,6 +5,7 @@
 // copied) after Storm/B200/DeviceVector.hpp and instantiates every solver on the device vector:
 //   SolverCg.hpp, SolverCgs.hpp, SolverBiCgStab.hpp (BiCGStab, BiCGStab(l)), SolverGmres.hpp
 //   (GMRES, FGMRES), SolverTfqmr.hpp (TFQMR, TFQMR1), SolverIdrs.hpp, SolverRichardson.hpp,
+//   SolverNewton.hpp (JFNK: the nonlinear outer loop whose inner solve is BiCGStab),
 // all driven by IterativeSolver::solve (Solver.hpp:116-147), plus the two fused fast-path solvers
 // of Storm/B200/FusedSolvers.hpp. It is exported behind a small C entry point so the parity tests
 // (Python, ctypes) can run it on vectors they own; g++ -std=c++23 builds it, linking libstormb200.so.
@@ -18,6 +19,10 @@
 #include <Storm/Solvers/SolverIdrs.hpp>
 #include <Storm/Solvers/SolverRichardson.hpp>
 #include <Storm/Solvers/SolverTfqmr.hpp>
+// JFNK (SolverNewton.hpp:101-173). The header relies on BiCgStabSolver and
+// std::numeric_limits being visible already ("fix the missing include"): included after them, untouched.
+#include <limits>
+#include <Storm/Solvers/SolverNewton.hpp>
 
 #include <cstring>
 #include <string>
@@ -33,6 +38,8 @@ struct dropin_opts {
   int64_t num_inner_iterations; // <= 0: keep the solver's default (Solver.hpp:159)
   double relaxation_factor;     // Richardson only; <= 0 keeps the default
   int32_t use_graph;            // fused solvers only
+  int32_t precond;              // 0: none, 1: Storm::JacobiPreconditioner (generic solvers)
+  int32_t pre_side;             // 0: Left, 1: Right (the reference's default), 2: Symmetric
 };
 
 struct dropin_report {
@@ -86,6 +93,11 @@ int run_generic(sb_ctx* ctx, const sb_op* op, double* d_x, const double* d_b, si
   }
   if constexpr (requires { solver.relaxation_factor; }) {
     if (o->relaxation_factor > 0.0) solver.relaxation_factor = o->relaxation_factor;
+  }
+  if (o->precond == 1) {
+    solver.pre_op = std::make_unique<Storm::JacobiPreconditioner>(ctx, op);
+    solver.pre_side = o->pre_side == 0 ? Storm::PreconditionerSide::Left
+                                       : (o->pre_side == 2 ? Storm::PreconditionerSide::Symmetric : Storm::PreconditionerSide::Right);
   }
   DeviceVector x = DeviceVector::view(ctx, d_x, n);
   const DeviceVector b = DeviceVector::view(ctx, const_cast<double*>(d_b), n);
@@ -146,7 +158,7 @@ extern "C" {
 
 DROPIN_API const char* dropin_last_error(void) { return g_error.c_str(); }
 
-// Solver names: cg cgs bicgstab bicgstabl gmres fgmres tfqmr tfqmr1 idrs richardson (the reference
+// Solver names: cg cgs bicgstab bicgstabl gmres fgmres tfqmr tfqmr1 idrs richardson jfnk (the reference
 // templates on DeviceVector), fused_cg fused_bicgstab (Storm::B200 fast path).
 DROPIN_API int dropin_solve(const char* name, sb_ctx* ctx, const sb_op* op, double* d_x, const double* d_b,
                             size_t n, const dropin_opts* o, dropin_report* rep, double* hist, int64_t hist_cap,
@@ -166,6 +178,7 @@ DROPIN_API int dropin_solve(const char* name, sb_ctx* ctx, const sb_op* op, doub
     DROPIN_CASE("tfqmr1", Tfqmr1Solver);
     DROPIN_CASE("idrs", IdrsSolver);
     DROPIN_CASE("richardson", RichardsonSolver);
+    DROPIN_CASE("jfnk", JfnkSolver);
 #undef DROPIN_CASE
     if (s == "fused_cg")
       return run_fused<Storm::B200::CgSolver>(ctx, op, d_x, d_b, n, o, rep, hist, hist_cap, trace, trace_cap);

@@ -105,3 +105,43 @@ def test_fused_bicgstab_on_convdiff_bit_identical(ctx, tet_case, use_graph):
     assert np.array_equal(s.history, want.hist) and np.array_equal(x.numpy(), want.x)
     res = np.linalg.norm(b - cpu.apply(x.numpy())) / np.linalg.norm(b)
     assert res < 1e-9
+
+
+# ---- the preconditioner slot: Storm::JacobiPreconditioner in IterativeSolver::pre_op ----
+def test_jacobi_apply_bit_exact(ctx, tet_case):
+    _, cpu, gpu = tet_case
+    w, ld, col, a, diag = cpu.rows_coef().rows
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal(cpu.n)
+    xd, yd = ctx.vector(x), ctx.zeros(cpu.n)
+    gpu.jacobi(yd, xd)
+    assert np.array_equal(yd.numpy(), x / diag[:cpu.n])
+    gpu.jacobi(xd, xd)                                   # in place
+    assert np.array_equal(xd.numpy(), x / diag[:cpu.n])
+    lap = sb.FvmOperator(ctx, tet_case[0], prefill=0, dt=-1.0, form=sb.FORM_FAITHFUL, dirichlet=True)
+    with pytest.raises(sb.StormB200Error):
+        lap.jacobi(yd, xd)                               # the faithful form keeps no diagonal
+
+
+@pytest.mark.parametrize("solver", ["bicgstab", "gmres", "fgmres", "idrs", "tfqmr", "bicgstabl", "cgs"])
+@pytest.mark.parametrize("side", ["right", "left"])
+def test_reference_templates_with_jacobi_preconditioner_bit_identical(ctx, tet_case, solver, side):
+    """Left/right/flexible preconditioned branches of the reference solvers (e.g. SolverBiCgStab.hpp:135-137,
+    SolverGmres.hpp:149-156,233-248), device vs host, reduction tree matched: every reduction scalar, the
+    residual history and the solution agree bit for bit; Jacobi never needs more iterations than no preconditioner."""
+    _, cpu, gpu = tet_case
+    rows = cpu.rows_coef()
+    diag = rows.rows[4][:cpu.n]
+    b = np.sin(0.37 * np.arange(cpu.n))
+    want = orc.ref_solve(solver, rows, b, num_iterations=400, abs_tol=0.0, rel_tol=1e-10, mode=orc.RED_TREE,
+                         pre=orc.JacobiOp(diag), pre_side=side)
+    x = ctx.zeros(cpu.n)
+    got = dropin.solve(solver, gpu, x, ctx.vector(b), num_iterations=400, abs_tol=0.0, rel_tol=1e-10,
+                       precond="jacobi", pre_side=side)
+    assert want.converged
+    assert (got.converged, got.iterations, got.n_apply) == (want.converged, want.iterations, want.n_apply)
+    assert np.array_equal(got.trace, want.trace) and np.array_equal(got.hist, want.hist)
+    assert np.array_equal(x.numpy(), want.x)
+    plain = orc.ref_solve(solver, rows, b, num_iterations=400, abs_tol=0.0, rel_tol=1e-10, mode=orc.RED_TREE)
+    assert want.iterations <= plain.iterations
+    assert np.linalg.norm(b - cpu.apply(x.numpy())) <= 1e-8 * np.linalg.norm(b)

@@ -85,6 +85,20 @@ def test_against_reference_sequential_golden(ctx, ops, solver):
     assert np.linalg.norm(x.numpy() - ref_x) <= X_TOL * np.linalg.norm(ref_x)
 
 
+def test_jfnk_template_on_device_vector_bit_identical(ctx, ops):
+    """the reference's JfnkSolver (SolverNewton.hpp:101-173) instantiated on the device
+    vector -- Jacobian-free products x + delta*y, delta^-1 (z - w), norms, and the reference's own BiCgStabSolver
+    as the inner solve. The operator is linear here, so two Newton steps reach the tolerance; every reduction
+    scalar, the outer residual history and the solution match the same header on a host vector bit for bit."""
+    want, got, x = run_both(ctx, ops, "jfnk", iters=10, rel_tol=1e-9)
+    assert want.converged and want.iterations >= 2
+    assert (got.converged, got.iterations, got.n_apply) == (want.converged, want.iterations, want.n_apply)
+    assert len(got.trace) == len(want.trace) and np.array_equal(got.trace, want.trace)
+    assert np.array_equal(got.hist, want.hist) and np.array_equal(x, want.x)
+    cpu, _ = ops
+    assert np.linalg.norm(rhs(cpu.n) - cpu.apply(x)) <= 1e-8 * np.linalg.norm(rhs(cpu.n))
+
+
 @pytest.mark.parametrize("solver", ["fused_cg", "fused_bicgstab"])
 def test_fused_solvers_behind_the_reference_solver_interface(ctx, ops, solver):
     """Storm::B200::CgSolver / BiCgStabSolver called through Solver<DeviceVector>::solve give the
