@@ -170,6 +170,14 @@ SB_API int sb_mesh_generate_box(int cell_kind, int nx, int ny, int nz, double ji
 /* General ingestion: h_xyz [3*n_nodes], h_cell_nodes [n_cells * (4 | 8)]. */
 SB_API int sb_mesh_from_cells(int cell_kind, int64_t n_nodes, const double* h_xyz, int64_t n_cells,
                               const int32_t* h_cell_nodes, sb_mesh** out);
+/* TetGen ingestion in 3-D: reads `<prefix>.node` and `<prefix>.ele` with the file
+ * grammar of the reference's reader (Mallard/IoTetgen.hpp:44-235: '#' comments, node header
+ * `count dim n_attribs has_labels`, element header `count nodes_per_cell has_attribs`, one entity per line led
+ * by its index) and hands the tetrahedra to sb_mesh_from_cells. The reference reader is hard-wired to 2-D
+ * at this commit -- its 3-D branch reads `.face` files it cannot build a mesh from -- so the face
+ * list follows this library's own creation-order convention, like every other 3-D mesh here. Node indices
+ * may start at 0 or 1 (TetGen -z); attributes and labels are skipped. */
+SB_API int sb_mesh_read_tetgen(const char* path_prefix, sb_mesh** out);
 SB_API int sb_mesh_destroy(sb_mesh* mesh);
 /* Reverse Cuthill-McKee renumbering of the cells over the face adjacency graph; faces are rebuilt
  * for the new cell order. h_perm (may be NULL) receives perm[new] = old (Utils/Permutations.hpp:77-103). */

@@ -8,6 +8,7 @@
 // operation (compiled with -ffp-contract=off) so the independent C restatement in
 // oracle/sb_oracle_mesh.c reproduces the arrays bit for bit.
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
@@ -16,6 +17,7 @@
 #include <memory>
 #include <numeric>
 #include <random>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -504,6 +506,111 @@ int sb_mesh_generate_box(int cell_kind, int nx, int ny, int nz, double jitter, u
     }
   }
   return sb_mesh_from_cells(cell_kind, n_nodes, xyz.data(), n_cells, cells.data(), out);
+}
+
+namespace {
+// Token reader with '#' comments (to end of line), like the reference's FilteringStreambuf<char,'#','\n'>.
+struct TokenFile {
+  std::vector<char> buf;
+  size_t pos = 0;
+  bool open(const std::string& path) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (f == nullptr) return false;
+    std::fseek(f, 0, SEEK_END);
+    const long n = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    buf.resize((size_t) (n > 0 ? n : 0) + 1);
+    const size_t got = std::fread(buf.data(), 1, buf.size() - 1, f);
+    std::fclose(f);
+    buf[got] = 0, buf.resize(got + 1);
+    return true;
+  }
+  void skip() {
+    for (;;) {
+      while (pos + 1 < buf.size() && std::isspace((unsigned char) buf[pos])) ++pos;
+      if (pos + 1 < buf.size() && buf[pos] == '#') {
+        while (pos + 1 < buf.size() && buf[pos] != '\n') ++pos;
+      } else {
+        return;
+      }
+    }
+  }
+  bool next_double(double& v) {
+    skip();
+    if (pos + 1 >= buf.size()) return false;
+    char* end = nullptr;
+    v = std::strtod(buf.data() + pos, &end);
+    if (end == buf.data() + pos) return false;
+    pos = (size_t) (end - buf.data());
+    return true;
+  }
+  bool next_int(int64_t& v) {
+    skip();
+    if (pos + 1 >= buf.size()) return false;
+    char* end = nullptr;
+    v = std::strtoll(buf.data() + pos, &end, 10);
+    if (end == buf.data() + pos) return false;
+    pos = (size_t) (end - buf.data());
+    return true;
+  }
+};
+} // namespace
+
+int sb_mesh_read_tetgen(const char* path_prefix, sb_mesh** out) {
+  SBM_REQUIRE(path_prefix != nullptr && out != nullptr, "null argument");
+  *out = nullptr;
+  const std::string prefix{path_prefix};
+  TokenFile nf, ef;
+  if (!nf.open(prefix + ".node")) {
+    sb::set_error("cannot open the node file '%s.node'", path_prefix);
+    return SB_ERR_INVALID;
+  }
+  if (!ef.open(prefix + ".ele")) {
+    sb::set_error("cannot open the cell file '%s.ele'", path_prefix);
+    return SB_ERR_INVALID;
+  }
+  int64_t n_nodes = 0, dim = 0, n_attr = 0, has_labels = 0;
+  SBM_REQUIRE(nf.next_int(n_nodes) && nf.next_int(dim) && nf.next_int(n_attr) && nf.next_int(has_labels),
+              "cannot read the node file header");
+  SBM_REQUIRE(dim == 3, "unexpected number of dimensions in the node file header (expected 3)");
+  SBM_REQUIRE(n_nodes > 0 && n_nodes < (int64_t) INT32_MAX && n_attr >= 0, "bad node file header");
+  std::vector<double> xyz(3 * (size_t) n_nodes);
+  int64_t first_index = 0;
+  for (int64_t k = 0; k < n_nodes; ++k) {
+    int64_t idx = 0;
+    double skipped = 0.0;
+    bool ok = nf.next_int(idx) && nf.next_double(xyz[3 * (size_t) k]) && nf.next_double(xyz[3 * (size_t) k + 1]) &&
+              nf.next_double(xyz[3 * (size_t) k + 2]);
+    for (int64_t a = 0; ok && a < n_attr + (has_labels ? 1 : 0); ++a) ok = nf.next_double(skipped);
+    if (!ok) {
+      sb::set_error("cannot read node # %lld from '%s.node'", (long long) k, path_prefix);
+      return SB_ERR_INVALID;
+    }
+    if (k == 0) first_index = idx;
+    SBM_REQUIRE(idx == first_index + k, "node indices must be consecutive");
+  }
+  SBM_REQUIRE(first_index == 0 || first_index == 1, "node numbering must start at 0 or 1");
+  int64_t n_cells = 0, npc = 0, has_attr = 0;
+  SBM_REQUIRE(ef.next_int(n_cells) && ef.next_int(npc) && ef.next_int(has_attr), "cannot read the cell file header");
+  SBM_REQUIRE(npc == 4, "unexpected number of nodes per cell in the cell file header (expected 4)");
+  SBM_REQUIRE(n_cells > 0 && n_cells < (int64_t) 250'000'000, "bad cell count");
+  std::vector<int32_t> cells(4 * (size_t) n_cells);
+  for (int64_t c = 0; c < n_cells; ++c) {
+    int64_t idx = 0, nd[4] = {0, 0, 0, 0};
+    double skipped = 0.0;
+    bool ok = ef.next_int(idx) && ef.next_int(nd[0]) && ef.next_int(nd[1]) && ef.next_int(nd[2]) && ef.next_int(nd[3]);
+    for (int64_t a = 0; ok && a < has_attr; ++a) ok = ef.next_double(skipped);
+    if (!ok) {
+      sb::set_error("cannot read cell # %lld from '%s.ele'", (long long) c, path_prefix);
+      return SB_ERR_INVALID;
+    }
+    for (int q = 0; q < 4; ++q) {
+      const int64_t v = nd[q] - first_index;
+      SBM_REQUIRE(v >= 0 && v < n_nodes, "cell node index out of range");
+      cells[4 * (size_t) c + q] = (int32_t) v;
+    }
+  }
+  return sb_mesh_from_cells(SB_CELL_TET, n_nodes, xyz.data(), n_cells, cells.data(), out);
 }
 
 int sb_mesh_destroy(sb_mesh* mesh) {

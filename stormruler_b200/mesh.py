@@ -39,6 +39,14 @@ class Mesh:
                                           cells.ctypes.data_as(capi.i32p), C.byref(h)))
         return Mesh(h)
 
+    @staticmethod
+    def read_tetgen(path_prefix: str) -> "Mesh":
+        """3-D TetGen `<prefix>.node` + `<prefix>.ele` (file grammar of Mallard/IoTetgen.hpp:44-235)."""
+        lib = capi.load()
+        h = C.c_void_p()
+        capi.check(lib.sb_mesh_read_tetgen(str(path_prefix).encode(), C.byref(h)))
+        return Mesh(h)
+
     def __del__(self):
         try:
             if self.handle:

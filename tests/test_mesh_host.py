@@ -81,6 +81,32 @@ def test_ingestion_from_cells_matches_generator(kind):
         Mesh.from_cells(KIND[kind], xyz, bad)
 
 
+@pytest.mark.parametrize("first_index", [0, 1])
+def test_tetgen_reader_3d(tmp_path, first_index):
+    """`.node` / `.ele` in the grammar the reference's reader accepts (IoTetgen.hpp:44-235): comments, attributes,
+    labels, 0- or 1-based indices. The mesh read back is the mesh built from the same arrays."""
+    xyz, cells = mo.box_cells("tet", 4, 3, 2)
+    prefix = tmp_path / "box.1"
+    with open(str(prefix) + ".node", "w") as f:
+        f.write(f"# nodes\n{len(xyz)} 3 1 1\n")
+        for k, p in enumerate(xyz):
+            f.write(f"{k + first_index} {float(p[0])!r} {float(p[1])!r} {float(p[2])!r} 0.5 {k % 3}  # attribute, label\n")
+    with open(str(prefix) + ".ele", "w") as f:
+        f.write(f"{len(cells)} 4 1\n")
+        for k, c in enumerate(cells):
+            f.write(f"{k + first_index} " + " ".join(str(int(v) + first_index) for v in c) + " 7\n")
+    a, b = Mesh.read_tetgen(prefix), Mesh.from_cells(CELL_TET, xyz, cells)
+    assert a.n_cells == b.n_cells
+    for k in SOA_KEYS:
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    with pytest.raises(capi.StormB200Error):
+        Mesh.read_tetgen(tmp_path / "missing")
+    with open(str(prefix) + ".ele", "w") as f:
+        f.write("1 4 0\n0 0 1 2 99999\n")
+    with pytest.raises(capi.StormB200Error):
+        Mesh.read_tetgen(prefix)
+
+
 @pytest.mark.parametrize("kind,dims", [("tet", (6, 5, 4)), ("hex", (7, 6, 5))])
 def test_rcm_permutation_and_renumbered_mesh_bit_exact(kind, dims):
     mesh = Mesh.box(KIND[kind], *dims)
