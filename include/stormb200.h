@@ -348,6 +348,26 @@ SB_API int sb_cg_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b,
 SB_API int sb_bicgstab_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b,
                              const sb_solver_opts* opts, sb_solver_report* report, double* h_hist,
                              int64_t hist_cap, double* h_trace, int64_t trace_cap);
+/* Fused restarted GMRES(m): GmresSolver / FgmresSolver without a preconditioner (SolverGmres.hpp:42-310) driven
+ * as InnerOuterIterativeSolver (Solver.hpp:154-259) + IterativeSolver::solve. The Arnoldi process runs on the
+ * device without host round trips (each modified-Gram-Schmidt step is one kernel: subtract the previous
+ * projection and reduce the next one; coefficients are read from device memory), the Givens rotations, the
+ * residual estimate and the stopping rule are the reference's own scalar statements evaluated on the host a few
+ * steps behind, from asynchronously copied H columns. Bit-identical to the reference headers (oracle tree
+ * reductions): iteration count, every reduction scalar (h_trace), residual history, solution.
+ * One deliberate deviation: when the initial residual is already below abs_tol (or num_iterations == 0) the
+ * reference's finalize() divides by H(0,0) = 0 and turns x into NaN; here x is left untouched. */
+typedef struct sb_gmres_opts {
+  int64_t num_iterations;       /* Solver.hpp:67 (default 2000); one iteration = one inner Arnoldi step */
+  double abs_tol;               /* <= 0 disables */
+  double rel_tol;               /* <= 0 disables */
+  int32_t num_inner_iterations; /* restart length m, Solver.hpp:159; 0 = the reference's default 50; max 128 */
+  int32_t lookahead;            /* Arnoldi steps the device may run ahead of the host's stopping test (0 = 3) */
+} sb_gmres_opts;
+SB_API int sb_gmres_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b, const sb_gmres_opts* opts,
+                          sb_solver_report* report, double* h_hist, int64_t hist_cap, double* h_trace,
+                          int64_t trace_cap);
+
 /* Same, with HOST buffers for x (in: initial guess, out: solution) and b: the copies are part
  * of the call (bench.py's e2e figure). solver: "cg" | "bicgstab". */
 SB_API int sb_solve_host(sb_ctx* ctx, const sb_op* op, const char* solver, double* h_x,

@@ -19,7 +19,7 @@ from . import capi
 from .capi import (ADD_ASSIGN, ASSIGN, DIV_ASSIGN, FORM_COEF, FORM_FAITHFUL, MUL_ASSIGN, SUB_ASSIGN,
                    StormB200Error)
 
-__all__ = ["Context", "DeviceVector", "FvmOperator", "ConvDiffOperator", "CgSolver", "BiCgStabSolver", "StormB200Error",
+__all__ = ["Context", "DeviceVector", "FvmOperator", "ConvDiffOperator", "CgSolver", "BiCgStabSolver", "GmresSolver", "StormB200Error",
            "FORM_COEF", "FORM_FAITHFUL", "ASSIGN", "ADD_ASSIGN", "SUB_ASSIGN", "MUL_ASSIGN",
            "DIV_ASSIGN", "expr"]
 
@@ -338,6 +338,44 @@ class CgSolver(_FusedSolver):
 class BiCgStabSolver(_FusedSolver):
     _entry = "sb_bicgstab_solve"
     _trace_per_iter = 5
+
+
+@dataclass
+class GmresSolver:
+    """Fused restarted GMRES(m) (sb_gmres_solve): GmresSolver / FgmresSolver of SolverGmres.hpp without a
+    preconditioner, with the public knobs of InnerOuterIterativeSolver (Solver.hpp:158-159)."""
+    num_iterations: int = 2000
+    absolute_error_tolerance: float = 1.0e-6
+    relative_error_tolerance: float = 1.0e-6
+    num_inner_iterations: int = 50
+    lookahead: int = 0
+    iteration: int = 0
+    absolute_error: float = 0.0
+    relative_error: float = 0.0
+    record: bool = True
+    history: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    trace: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    solve_ms: float = 0.0
+    iter_ms: float = 0.0
+    launches: int = 0
+
+    def solve(self, x: DeviceVector, b: DeviceVector, op) -> bool:
+        lib = op.ctx.lib
+        opts = capi.GmresOpts(int(self.num_iterations), float(self.absolute_error_tolerance),
+                              float(self.relative_error_tolerance), int(self.num_inner_iterations), int(self.lookahead))
+        rep = capi.SolverReport()
+        m = self.num_inner_iterations or 50
+        cap_h = self.num_iterations + 2 if self.record else 0
+        cap_t = (m + 3) * (self.num_iterations + 2) + 8 if self.record else 0
+        hist, trace = np.zeros(max(cap_h, 1)), np.zeros(max(cap_t, 1))
+        capi.check(lib.sb_gmres_solve(op.ctx.handle, op.handle, x.ptr, b.ptr, C.byref(opts), C.byref(rep),
+                                      hist.ctypes.data_as(capi.f64p) if self.record else None, cap_h,
+                                      trace.ctypes.data_as(capi.f64p) if self.record else None, cap_t))
+        self.iteration = int(rep.iterations)
+        self.absolute_error, self.relative_error = rep.abs_err, rep.rel_err
+        self.history, self.trace = hist[:rep.n_hist].copy(), trace[:rep.n_trace].copy()
+        self.solve_ms, self.iter_ms, self.launches = rep.solve_ms, rep.iter_ms, int(rep.launches)
+        return bool(rep.converged)
 
 
 def solve_host(ctx: Context, op: FvmOperator, solver: str, x_host: np.ndarray, b_host: np.ndarray,

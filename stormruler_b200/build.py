@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libstormb200.so")
-SOURCES = ["sb_api.cu", "sb_op.cu", "sb_solvers.cu", "sb_comm.cu", "sb_mesh_host.cpp", "sb_part_host.cpp"]
+SOURCES = ["sb_api.cu", "sb_op.cu", "sb_solvers.cu", "sb_gmres.cu", "sb_comm.cu", "sb_mesh_host.cpp", "sb_part_host.cpp"]
 METIS = "/usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a"  # ships with the CUDA toolkit
 HEADERS = [os.path.join(CSRC, h) for h in ("sb_common.cuh", "sb_kernels.cuh", "sb_op.cuh", "sb_comm.cuh")] + \
     [os.path.join(HERE, "..", "include", "stormb200.h"), os.path.abspath(__file__)]

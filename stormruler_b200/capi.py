@@ -74,6 +74,11 @@ class SolverOpts(C.Structure):
                 ("check_every", C.c_int32), ("use_graph", C.c_int32), ("profile", C.c_int32)]
 
 
+class GmresOpts(C.Structure):
+    _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
+                ("num_inner_iterations", C.c_int32), ("lookahead", C.c_int32)]
+
+
 class SolverReport(C.Structure):
     _fields_ = [("converged", C.c_int32), ("iterations", C.c_int64), ("initial_err", C.c_double),
                 ("abs_err", C.c_double), ("rel_err", C.c_double), ("n_hist", C.c_int64),
@@ -134,6 +139,8 @@ SIGNATURES = {
                               C.POINTER(SolverReport), f64p, C.c_int64, f64p, C.c_int64]),
     "sb_bicgstab_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SolverOpts),
                                     C.POINTER(SolverReport), f64p, C.c_int64, f64p, C.c_int64]),
+    "sb_gmres_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GmresOpts),
+                                 C.POINTER(SolverReport), f64p, C.c_int64, f64p, C.c_int64]),
     "sb_solve_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, f64p, f64p, C.POINTER(SolverOpts),
                                 C.POINTER(SolverReport), f64p, C.c_int64]),
 }

@@ -70,6 +70,11 @@ int sb_ctx_destroy(sb_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (double* w : ctx->work) vec_free(ctx, w);
   ctx->work.clear();
+  for (double* w : ctx->basis) vec_free(ctx, w);
+  ctx->basis.clear();
+  cudaFree(ctx->d_gmres_scal);
+  cudaFree(ctx->d_gmres_ptrs);
+  cudaFreeHost(ctx->h_gmres);
   comm_teardown(ctx);
   cudaFree(ctx->d_state);
   cudaFree(ctx->d_hist);

@@ -267,6 +267,8 @@ int sb_comm_destroy(sb_ctx* ctx) {
   // solver workspaces live in the pool: give them back first
   for (double* w : ctx->work) vec_free(ctx, w);
   ctx->work.clear(), ctx->work_n = 0;
+  for (double* w : ctx->basis) vec_free(ctx, w);
+  ctx->basis.clear(), ctx->basis_n = 0;
   return comm_teardown(ctx);
 }
 

@@ -111,6 +111,13 @@ struct sb_ctx {
   double* d_trace = nullptr;
   int64_t trace_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // fused GMRES (sb_gmres.cu): cached Krylov basis, device scalars (H records, betas), pinned mirror
+  std::vector<double*> basis;
+  size_t basis_n = 0;
+  double* d_gmres_scal = nullptr;
+  size_t gmres_scal_cap = 0;
+  double** d_gmres_ptrs = nullptr;
+  double* h_gmres = nullptr;
   // multi-GPU (sb_comm.cu); comm.mode < 0: single GPU
   sb::CommDev comm;
   unsigned char* slab = nullptr;

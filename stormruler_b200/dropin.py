@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, "host", "libstorm_dropin.so")
 GENERIC_SOLVERS = ("cg", "cgs", "bicgstab", "bicgstabl", "gmres", "fgmres", "tfqmr", "tfqmr1", "idrs",
                    "richardson")
 NONLINEAR_SOLVERS = ("jfnk",)   # SolverNewton.hpp:101-173, inner solve = the reference's BiCgStabSolver
-FUSED_SOLVERS = ("fused_cg", "fused_bicgstab")
+FUSED_SOLVERS = ("fused_cg", "fused_bicgstab", "fused_gmres")
 
 
 class Opts(C.Structure):

@@ -99,4 +99,28 @@ class BiCgStabSolver final : public FusedSolver {
   int64_t trace_per_iteration() const override { return 5; }
 };
 
+/// Drop-in for GmresSolver<DeviceVector> / FgmresSolver<DeviceVector> without a preconditioner
+/// (SolverGmres.hpp:42-310): device-resident Arnoldi process, host-side Givens bookkeeping (sb_gmres_solve).
+/// `num_inner_iterations` is InnerOuterIterativeSolver's restart length (Solver.hpp:159).
+class GmresSolver final : public FusedSolver {
+public:
+
+  size_t inner_iteration{0};
+  size_t num_inner_iterations{50};
+  int lookahead{0};
+
+private:
+
+  int run(sb_ctx* c, const sb_op* o, double* x, const double* b, const sb_solver_opts* so, sb_solver_report* r,
+          double* h, int64_t hc, double* t, int64_t tc) override {
+    sb_gmres_opts go{};
+    go.num_iterations = so->num_iterations, go.abs_tol = so->abs_tol, go.rel_tol = so->rel_tol;
+    go.num_inner_iterations = (int32_t) num_inner_iterations, go.lookahead = lookahead;
+    const int rc = sb_gmres_solve(c, o, x, b, &go, r, h, hc, t, tc);
+    if (rc == 0 && r->iterations > 0) inner_iteration = (size_t) ((r->iterations - 1) % (int64_t) num_inner_iterations);
+    return rc;
+  }
+  int64_t trace_per_iteration() const override { return (int64_t) num_inner_iterations + 3; }
+};
+
 } // namespace Storm::B200

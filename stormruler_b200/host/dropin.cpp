@@ -132,6 +132,9 @@ int run_fused(sb_ctx* ctx, const sb_op* op, double* d_x, const double* d_b, size
   solver.relative_error_tolerance = o->rel_tol;
   solver.use_graph = o->use_graph != 0;
   solver.record_history = true;
+  if constexpr (requires { solver.num_inner_iterations; }) {
+    if (o->num_inner_iterations > 0) solver.num_inner_iterations = (size_t) o->num_inner_iterations;
+  }
   DeviceVector x = DeviceVector::view(ctx, d_x, n);
   const DeviceVector b = DeviceVector::view(ctx, const_cast<double*>(d_b), n);
   const Storm::FvmOperator fvm{ctx, op};
@@ -184,6 +187,8 @@ DROPIN_API int dropin_solve(const char* name, sb_ctx* ctx, const sb_op* op, doub
       return run_fused<Storm::B200::CgSolver>(ctx, op, d_x, d_b, n, o, rep, hist, hist_cap, trace, trace_cap);
     if (s == "fused_bicgstab")
       return run_fused<Storm::B200::BiCgStabSolver>(ctx, op, d_x, d_b, n, o, rep, hist, hist_cap, trace, trace_cap);
+    if (s == "fused_gmres")
+      return run_fused<Storm::B200::GmresSolver>(ctx, op, d_x, d_b, n, o, rep, hist, hist_cap, trace, trace_cap);
   } catch (const std::exception& e) {
     g_error = e.what();
     return -2;

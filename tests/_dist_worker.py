@@ -128,7 +128,7 @@ def run_gpu(dist, rank, world, mode_name):
         order, seg = concat_order(part, world)
         orc.set_segments(seg)
         pm = permuted_face_mesh(mesh, order)
-        ctx = mg.DistContext(local_rank, rank, world, part.info.vec_capacity, n_vectors=16, mode=mode)
+        ctx = mg.DistContext(local_rank, rank, world, part.info.vec_capacity, n_vectors=30, mode=mode)
         rng = np.random.default_rng(11)
         xg = rng.standard_normal(n)
         bg = np.sin(0.37 * np.arange(n))
@@ -168,6 +168,18 @@ def run_gpu(dist, rank, world, mode_name):
                     assert np.array_equal(mg.gather_global(loc, xs.numpy(), n)[order], w.x), f"{name}: solution differs"
                     del xs
             del op, x, y, x2
+        # non-symmetric rows + the fused GMRES over the distributed operator (config 3)
+        fu, bu = mesh.face_flux((1.0, 0.5, 0.25))
+        cop = mg.DistConvDiffOperator(ctx, loc, 0.02, fu, bu)
+        ccpu = orc.ConvDiffOp(pm, 0.02, fu, bu).rows_coef()
+        xs = ctx.zeros(loc.n_owned)
+        g = sb.GmresSolver(num_iterations=80, absolute_error_tolerance=0.0, relative_error_tolerance=1e-9, num_inner_iterations=11)
+        conv = g.solve(xs, ctx.vector(bg[loc.owned_global]), cop)
+        w = orc.ref_solve("gmres", ccpu, bg[order], num_iterations=80, abs_tol=0.0, rel_tol=1e-9, num_inner=11, mode=orc.RED_TREE_SEG)
+        assert (conv, g.iteration) == (w.converged, w.iterations), (conv, g.iteration, w.converged, w.iterations)
+        assert np.array_equal(g.trace, w.trace) and np.array_equal(g.history, w.hist), "distributed GMRES differs from the oracle"
+        assert np.array_equal(mg.gather_global(loc, xs.numpy(), n)[order], w.x)
+        del cop, xs
         assert ctx.status() == 0
         ctx.close()
     return 0

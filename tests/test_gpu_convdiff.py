@@ -145,3 +145,59 @@ def test_reference_templates_with_jacobi_preconditioner_bit_identical(ctx, tet_c
     plain = orc.ref_solve(solver, rows, b, num_iterations=400, abs_tol=0.0, rel_tol=1e-10, mode=orc.RED_TREE)
     assert want.iterations <= plain.iterations
     assert np.linalg.norm(b - cpu.apply(x.numpy())) <= 1e-8 * np.linalg.norm(b)
+
+
+# ---- fused GMRES(m): device-resident Arnoldi process, host-side Givens bookkeeping (sb_gmres_solve) ----
+@pytest.mark.parametrize("m,lookahead", [(50, 0), (7, 0), (7, 1), (13, 6), (1, 0)])
+def test_fused_gmres_bit_identical_to_reference_headers(ctx, tet_case, m, lookahead):
+    _, cpu, gpu = tet_case
+    rows = cpu.rows_coef()
+    b = np.sin(0.37 * np.arange(cpu.n))
+    iters = 400 if m > 1 else 60
+    want = orc.ref_solve("gmres", rows, b, num_iterations=iters, abs_tol=0.0, rel_tol=1e-10, num_inner=m, mode=orc.RED_TREE)
+    s = sb.GmresSolver(num_iterations=iters, absolute_error_tolerance=0.0, relative_error_tolerance=1e-10,
+                       num_inner_iterations=m, lookahead=lookahead)
+    x = ctx.zeros(cpu.n)
+    conv = s.solve(x, ctx.vector(b), gpu)
+    assert (conv, s.iteration) == (want.converged, want.iterations)
+    assert len(s.trace) == len(want.trace) and np.array_equal(s.trace, want.trace)
+    assert np.array_equal(s.history, want.hist)
+    assert s.absolute_error == want.abs_err and s.relative_error == want.rel_err
+    assert np.array_equal(x.numpy(), want.x)
+    if want.converged:
+        assert np.linalg.norm(b - cpu.apply(x.numpy())) <= 1e-8 * np.linalg.norm(b)
+    # FGMRES without a preconditioner is the same algorithm
+    f = orc.ref_solve("fgmres", rows, b, num_iterations=iters, abs_tol=0.0, rel_tol=1e-10, num_inner=m, mode=orc.RED_TREE)
+    assert np.array_equal(f.x, want.x)
+
+
+def test_fused_gmres_fixed_count_stops_mid_cycle_and_nonzero_guess(ctx, tet_case):
+    _, cpu, gpu = tet_case
+    rows = cpu.rows_coef()
+    b = np.sin(0.37 * np.arange(cpu.n))
+    x0 = np.cos(0.11 * np.arange(cpu.n))
+    want = orc.ref_solve("gmres", rows, b, x0=x0, num_iterations=61, abs_tol=0.0, rel_tol=0.0, num_inner=9, mode=orc.RED_TREE)
+    s = sb.GmresSolver(num_iterations=61, absolute_error_tolerance=0.0, relative_error_tolerance=0.0, num_inner_iterations=9)
+    x = ctx.vector(x0)
+    assert s.solve(x, ctx.vector(b), gpu) is False and s.iteration == 61
+    assert np.array_equal(s.trace, want.trace) and np.array_equal(s.history, want.hist) and np.array_equal(x.numpy(), want.x)
+    # through the reference's abstract Solver interface (Storm::B200::GmresSolver in the C++ drop-in)
+    x = ctx.vector(x0)
+    got = dropin.solve("fused_gmres", gpu, x, ctx.vector(b), num_iterations=61, abs_tol=0.0, rel_tol=0.0, num_inner=9)
+    assert got.iterations == 61 and np.array_equal(got.hist, want.hist) and np.array_equal(x.numpy(), want.x)
+
+
+def test_fused_gmres_early_exit_leaves_x_untouched(ctx, tet_case):
+    """Solver.hpp:124-128 + SolverGmres.hpp:207-212: the reference back-substitutes through an all-zero H here and
+    returns NaN -- shown on the host vector; the fused path keeps x (documented deviation)."""
+    _, cpu, gpu = tet_case
+    rows = cpu.rows_coef()
+    b = np.sin(0.37 * np.arange(cpu.n))
+    ref = orc.ref_solve("gmres", rows, b, num_iterations=10, abs_tol=1e30, rel_tol=0.0)
+    assert ref.converged and ref.iterations == 0 and not np.isfinite(ref.x).all()
+    s = sb.GmresSolver(num_iterations=10, absolute_error_tolerance=1e30, relative_error_tolerance=0.0)
+    x = ctx.zeros(cpu.n)
+    assert s.solve(x, ctx.vector(b), gpu) is True and s.iteration == 0
+    assert np.array_equal(x.numpy(), np.zeros(cpu.n))
+    with pytest.raises(sb.StormB200Error):
+        sb.GmresSolver(num_inner_iterations=500).solve(x, ctx.vector(b), gpu)   # restart length out of range
