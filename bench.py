@@ -304,7 +304,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--solver", default="bicgstab", choices=["cg", "bicgstab"])
-    ap.add_argument("--n", type=int, default=119, help="hexes per axis (119 -> 10.1 M tets)")
+    ap.add_argument("--axis", "--n", dest="n", type=int, default=119,
+                    help="hexes per axis (119 -> 10.1 M tets); spell it --axis under torchrun, whose parser finds --n ambiguous")
     ap.add_argument("--cell", default="tet", choices=["tet", "hex"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")

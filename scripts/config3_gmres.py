@@ -1,7 +1,7 @@
 """BASELINE.json configs[2] / SURVEY.md 8d config 3: restarted GMRES(m) / FGMRES on 3-D convection-diffusion
 (non-symmetric upwind rows), synthetic tetrahedral box mesh, 1 GPU or METIS-partitioned over N GPUs.
 
-    python scripts/config3_gmres.py [--n 119] [--solver gmres|fgmres|bicgstab|idrs|tfqmr] [--m 50] [--steps 100]
+    python scripts/config3_gmres.py [--axis 119] [--solver gmres|fgmres|bicgstab|idrs|tfqmr] [--m 50] [--steps 100]
     torchrun --nproc-per-node N scripts/config3_gmres.py ...
 
 The solver is StormRuler's own GmresSolver template instantiated on Storm::DeviceVector (the C++23 drop-in,
@@ -30,7 +30,7 @@ from stormruler_b200.mesh import CELL_TET, Mesh  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=119)
+    ap.add_argument("--axis", "--n", dest="n", type=int, default=119, help="hexes per axis (use --axis under torchrun: --n is ambiguous to its parser)")
     ap.add_argument("--solver", default="gmres")
     ap.add_argument("--m", type=int, default=50, help="restart length (Solver.hpp:159 default 50)")
     ap.add_argument("--steps", type=int, default=100)

@@ -45,7 +45,9 @@ struct ApplyDist {
   HaloDev halo;
   int64_t x_off = 0;           // byte offset of x inside the slab (the same on every rank)
   int32_t n_pack = 0;          // the first n_pack CTAs of the grid pack + push my boundary values
-  int32_t coherent_gather = 0; // 1: gather x with ld.global.ca instead of the read-only path
+  int32_t coherent_gather = 0; // 1: BOUNDARY tiles gather x with ld.global.ca instead of the read-only path
+                               // (their halo tail is written by peers while the kernel runs); interior tiles
+                               // never touch the halo and keep ld.global.nc
 };
 
 // Boundary tiles (they read the halo tail) wait until every neighbour's values of THIS apply have landed.
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double*
     return;
   }
   const int64_t tile = (int64_t) blockIdx.x - ad.n_pack;
+  const int coh = ad.coherent_gather && tile >= ad.halo.first_boundary_tile;
   apply_halo_wait(ad, tile);
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double*
     const double2 xo = ld2(x, e0);
     typename Epi::Regs er;
     epi.load(e0, er);
-    double2 out = apply_rows<FORM, W>(op, x, e0, xo, ad.coherent_gather);
+    double2 out = apply_rows<FORM, W>(op, x, e0, xo, coh);
     if constexpr (RESID) {
       out.x = __dsub_rn(er.b.x, out.x);
       out.y = __dsub_rn(er.b.y, out.y);
@@ -273,6 +276,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     return;
   }
   const int64_t tile = (int64_t) blockIdx.x - ad.n_pack;
+  const int coh = ad.coherent_gather && tile >= ad.halo.first_boundary_tile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* wbase = sb_smem + (size_t) warp * kStages * L::bytes;
   const int64_t row0 = tile * kTile + warp * (kTile / kWarps);
@@ -371,8 +375,8 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     } else {
 #pragma unroll
       for (int k = 0; k < W; ++k) {
-        g0[k] = (c[k].x >= 0) ? gather(x + c[k].x, ad.coherent_gather) : 0.0;
-        g1[k] = (c[k].y >= 0) ? gather(x + c[k].y, ad.coherent_gather) : 0.0;
+        g0[k] = (c[k].x >= 0) ? gather(x + c[k].x, coh) : 0.0;
+        g1[k] = (c[k].y >= 0) ? gather(x + c[k].y, coh) : 0.0;
       }
     }
     double u0 = __dmul_rn(dg.x, xo.x), u1 = __dmul_rn(dg.y, xo.y);
