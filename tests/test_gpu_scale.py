@@ -9,13 +9,13 @@ import pytest
 
 import stormruler_b200 as sb
 from oracle import orc
-from stormruler_b200.mesh import CELL_TET, Mesh
+from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh
 
 pytestmark = pytest.mark.gpu
 
 
-def box(n):
-    mesh = Mesh.box(CELL_TET, n, jitter=0.2, seed_jitter=42, shuffle=True, seed_shuffle=43)
+def box(n, kind=CELL_TET):
+    mesh = Mesh.box(kind, n, jitter=0.2, seed_jitter=42, shuffle=True, seed_shuffle=43)
     mesh.renumber_rcm()
     fm = orc.FaceMesh(mesh.n_cells, mesh.face_cell, mesh.face_area, mesh.face_dist, mesh.cell_vol, mesh.bface_cell,
                       mesh.bface_area, mesh.bface_dist)
@@ -95,3 +95,31 @@ def test_six_million_cells_run_to_run_deterministic(any_ctx, solver):
     for hist, x in runs[1:]:
         assert np.array_equal(hist, runs[0][0]), "residual history is not run-to-run deterministic"
         assert np.array_equal(x, runs[0][1]), "solution is not run-to-run deterministic"
+
+
+def test_hexahedra_width_six_rows_at_scale(ctx):
+    """The 6-wide instantiation of the TMA kernel (hexahedra; 5.6 KB stages, 2 CTAs/SM) on 3.4 M cells: apply against
+    the row oracle over repeated launches, BiCGStab and GMRES against the oracle / the reference headers."""
+    mesh, fm = box(150, CELL_HEX)
+    n = mesh.n_cells
+    gpu = sb.FvmOperator(ctx, mesh, prefill=0, dt=-1.0, form=sb.FORM_COEF, dirichlet=True)
+    assert gpu.info.width == 6
+    cpu = orc.FaceOp(fm, prefill=0, dt=-1.0, dirichlet=True)
+    rows_op = orc.RowsOp(n, *cpu.rows_coef())
+    bh = np.sin(0.37 * np.arange(n))
+    b, y = ctx.vector(bh), ctx.zeros(n)
+    want = rows_op.apply(bh)
+    for _ in range(6):
+        gpu.mul(y, b)
+        assert np.array_equal(y.numpy(), want)
+    w = orc.solve("bicgstab", rows_op, bh, num_iterations=25, abs_tol=0.0, rel_tol=0.0, mode=orc.RED_TREE)
+    for use_graph in (False, True):
+        s = sb.BiCgStabSolver(num_iterations=25, absolute_error_tolerance=0.0, relative_error_tolerance=0.0, use_graph=use_graph)
+        x = ctx.zeros(n)
+        s.solve(x, b, gpu)
+        assert np.array_equal(s.history, w.hist) and np.array_equal(x.numpy(), w.x)
+    g = sb.GmresSolver(num_iterations=24, absolute_error_tolerance=0.0, relative_error_tolerance=0.0, num_inner_iterations=10)
+    x = ctx.zeros(n)
+    g.solve(x, b, gpu)
+    wg = orc.ref_solve("gmres", rows_op, bh, num_iterations=24, abs_tol=0.0, rel_tol=0.0, num_inner=10, mode=orc.RED_TREE)
+    assert np.array_equal(g.trace, wg.trace) and np.array_equal(g.history, wg.hist) and np.array_equal(x.numpy(), wg.x)
