@@ -1,13 +1,14 @@
 """BASELINE.json configs[4] / SURVEY.md 8d config 5: operator-apply (SpMV) bandwidth sweep against the HBM roofline.
 
-    python scripts/apply_sweep.py [--cells tet,hex] [--sizes 1e5,3e5,1e6,3e6,1e7,3e7] [--out profiles/...json]
+    python scripts/apply_sweep.py [--cells tet,hex,poly] [--sizes 1e5,3e5,1e6,3e6,1e7,3e7] [--out profiles/...json]
     torchrun --nproc-per-node N scripts/apply_sweep.py ...      (N > 1: METIS-partitioned, halo exchange inside the apply)
 
 For every (cell kind, size): synthetic jittered box mesh of about that many cells, shuffled then RCM-renumbered,
 3-D Poisson with Dirichlet mirror ghosts, coefficient form. Timed: 40 chained applies y = A x, z = A y, ... (the
 input of every apply is freshly written, as inside a Krylov iteration) bracketed by stream synchronisation, after 8
 warm-up applies; GB/s = algorithmic bytes (24 N + 12 entries) / time. One JSON line per point and a
-summary object at the end. Polyhedral (14-face) cells are out of range of the <= 8 wide row layout and are skipped.
+summary object at the end. `poly` = truncated octahedra (the Voronoi cells of a body-centred cubic lattice: 14 faces
+per cell, F ~ 7 N, the 14-wide instantiation of the apply kernel; lattice order, single GPU only).
 """
 from __future__ import annotations
 
@@ -24,11 +25,11 @@ sys.path.insert(0, ROOT)
 
 import stormruler_b200 as sb  # noqa: E402
 from stormruler_b200 import capi  # noqa: E402
-from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh  # noqa: E402
+from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh, PolyMesh  # noqa: E402
 
 
 def axis_for(kind, cells):
-    per = 6 if kind == "tet" else 1
+    per = {"tet": 6, "hex": 1, "poly": 2}[kind]
     return max(2, round((cells / per) ** (1.0 / 3.0)))
 
 
@@ -55,9 +56,16 @@ def main():
         for size in (float(s) for s in args.sizes.split(",")):
             n_axis = axis_for(kind, size)
             t0 = time.time()
-            mesh = Mesh.box(CELL_TET if kind == "tet" else CELL_HEX, n_axis, jitter=0.2, seed_jitter=42, shuffle=True,
-                            seed_shuffle=43)
-            mesh.renumber_rcm()
+            if kind == "poly":
+                if world > 1:
+                    if rank == 0:
+                        print(json.dumps({"cell": kind, "skipped": "the partitioner takes node-based meshes only"}), flush=True)
+                    continue
+                mesh = PolyMesh.bcc(n_axis, stretch=(1.0, 1.3, 0.7))
+            else:
+                mesh = Mesh.box(CELL_TET if kind == "tet" else CELL_HEX, n_axis, jitter=0.2, seed_jitter=42, shuffle=True,
+                                seed_shuffle=43)
+                mesh.renumber_rcm()
             t_mesh = time.time() - t0
             if world > 1:
                 part = mg.partition_mesh(mesh, world, capi.PART_METIS)

@@ -21,6 +21,14 @@ struct HostRows {
   std::vector<double> v0, v1, diag;
 };
 
+// ELL width for a maximum row degree: exact up to 8 (tets 4, hexes 6); wider rows (polyhedral cells) are
+// padded to the next even width up to 16, the widths the apply kernels are instantiated for.
+constexpr int32_t kMaxWidth = 16;
+inline int32_t ell_width(int32_t max_deg) {
+  const int32_t w = std::max<int32_t>(1, max_deg);
+  return w <= 8 ? w : ((w + 1) & ~1);
+}
+
 // n_rows: rows are built for cells [0, n_rows) only (distributed operator: the owned cells; columns
 // may reference any cell < n_cells, i.e. the halo tail). n_rows == n_cells on a single GPU.
 int build_rows(const sb_mesh_soa* m, const sb_op_desc* desc, int64_t n_rows, HostRows& R) {
@@ -35,8 +43,10 @@ int build_rows(const sb_mesh_soa* m, const sb_op_desc* desc, int64_t n_rows, Hos
   for (int64_t f = 0; f < F; ++f) deg[m->face_cell[2 * f]]++, deg[m->face_cell[2 * f + 1]]++;
   if (!coef)
     for (int64_t b = 0; b < B; ++b) deg[m->bface_cell[b]]++;
-  int32_t width = 1;
-  for (int64_t i = 0; i < n_rows; ++i) width = std::max(width, deg[i]);
+  int32_t max_deg = 1;
+  for (int64_t i = 0; i < n_rows; ++i) max_deg = std::max(max_deg, deg[i]);
+  const int32_t width = ell_width(max_deg);
+  SB_REQUIRE(width <= kMaxWidth, "cells with more than 16 faces are not supported");
   const int64_t ld = pad_up(n_rows);
   R.width = width, R.ld = ld, R.entries = 0;
   R.col.assign((size_t) width * ld, kColPad);
@@ -89,8 +99,10 @@ int build_rows_convdiff(const sb_mesh_soa* m, const sb_convdiff_desc* desc, int6
     SB_REQUIRE(m->bface_cell[b] >= 0 && m->bface_cell[b] < n_rows, "bface_cell index out of range");
   std::vector<int32_t> deg((size_t) n + 1, 0);
   for (int64_t f = 0; f < F; ++f) deg[m->face_cell[2 * f]]++, deg[m->face_cell[2 * f + 1]]++;
-  int32_t width = 1;
-  for (int64_t i = 0; i < n_rows; ++i) width = std::max(width, deg[i]);
+  int32_t max_deg = 1;
+  for (int64_t i = 0; i < n_rows; ++i) max_deg = std::max(max_deg, deg[i]);
+  const int32_t width = ell_width(max_deg);
+  SB_REQUIRE(width <= kMaxWidth, "cells with more than 16 faces are not supported");
   const int64_t ld = pad_up(n_rows);
   R.width = width, R.ld = ld, R.entries = 0;
   R.col.assign((size_t) width * ld, kColPad);
@@ -159,7 +171,6 @@ static int validate_mesh(sb_ctx* ctx, const sb_mesh_soa* m, int64_t n_rows, sb_o
 
 // Upload the host rows: blocked SELL-64 records for the coefficient form, plain ELL arrays otherwise.
 static int finish_op(sb_ctx* ctx, HostRows& R, int form, int prefill, double dt, int64_t n_rows, sb_op** out) {
-  SB_REQUIRE(R.width <= 8, "cells with more than 8 faces are not supported yet");
   std::unique_ptr<sb_op> op(new sb_op());
   op->d.n = n_rows, op->d.ld = R.ld, op->d.width = R.width, op->d.form = form;
   op->d.prefill = prefill, op->d.dt = dt;

@@ -116,60 +116,73 @@ struct EpiResidual {
   __device__ __forceinline__ void load(int64_t e0, Regs& r) const { r.b = ld2(b, e0); }
 };
 
+// Rows wider than 8 entries (polyhedral cells) are processed in chunks of 8: the sum over a row is
+// sequential in k either way, so chunking changes the register footprint, not the result.
 template<int FORM, int W>
 __device__ __forceinline__ double2 apply_rows(const OpDev& op, const double* __restrict__ x, int64_t e0, double2 xo,
                                               int coh) {
+  constexpr int C = W <= 8 ? W : 8;
   const int64_t h = e0 >> 1, ldh = op.ld >> 1;
   const int2* __restrict__ col2 = reinterpret_cast<const int2*>(op.col);
   const double2* __restrict__ a2 = reinterpret_cast<const double2*>(op.v0);
-  int2 c[W];
-  double2 a[W];
-#pragma unroll
-  for (int k = 0; k < W; ++k) c[k] = col2[k * ldh + h], a[k] = a2[k * ldh + h];
-  double2 out;
+  double u0, u1;
   if constexpr (FORM == SB_FORM_COEF) {
     const double2 dg = ld2(op.diag, e0);
-    double g0[W], g1[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) {
-      g0[k] = (c[k].x >= 0) ? gather(x + c[k].x, coh) : 0.0;
-      g1[k] = (c[k].y >= 0) ? gather(x + c[k].y, coh) : 0.0;
-    }
-    double u0 = __dmul_rn(dg.x, xo.x), u1 = __dmul_rn(dg.y, xo.y);
-#pragma unroll
-    for (int k = 0; k < W; ++k) {
-      const double t0 = __dadd_rn(u0, __dmul_rn(a[k].x, g0[k]));
-      const double t1 = __dadd_rn(u1, __dmul_rn(a[k].y, g1[k]));
-      u0 = (c[k].x >= 0) ? t0 : u0;
-      u1 = (c[k].y >= 0) ? t1 : u1;
-    }
-    out = make_double2(u0, u1);
+    u0 = __dmul_rn(dg.x, xo.x), u1 = __dmul_rn(dg.y, xo.y);
   } else {
-    const double2* __restrict__ d2 = reinterpret_cast<const double2*>(op.v1);
-    double2 d[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) d[k] = d2[k * ldh + h];
-    double g0[W], g1[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) {
-      // ghost entry (col == ~i): mirror state -x[i]; padding: skipped below
-      g0[k] = (c[k].x >= 0) ? gather(x + c[k].x, coh) : -xo.x;
-      g1[k] = (c[k].y >= 0) ? gather(x + c[k].y, coh) : -xo.y;
-    }
-    double u0 = op.prefill ? xo.x : 0.0, u1 = op.prefill ? xo.y : 0.0;
-#pragma unroll
-    for (int k = 0; k < W; ++k) {
-      // flux = dt*(x_nbr - x_i)/dist ; u += (area/vol)*flux      (Playground.cpp:125-128)
-      const double f0 = __ddiv_rn(__dmul_rn(op.dt, __dsub_rn(g0[k], xo.x)), d[k].x);
-      const double f1 = __ddiv_rn(__dmul_rn(op.dt, __dsub_rn(g1[k], xo.y)), d[k].y);
-      const double t0 = __dadd_rn(u0, __dmul_rn(a[k].x, f0));
-      const double t1 = __dadd_rn(u1, __dmul_rn(a[k].y, f1));
-      u0 = (c[k].x != kColPad) ? t0 : u0;
-      u1 = (c[k].y != kColPad) ? t1 : u1;
-    }
-    out = make_double2(u0, u1);
+    u0 = op.prefill ? xo.x : 0.0, u1 = op.prefill ? xo.y : 0.0;
   }
-  return out;
+#pragma unroll
+  for (int k0 = 0; k0 < W; k0 += C) {
+    int2 c[C];
+    double2 a[C];
+#pragma unroll
+    for (int k = 0; k < C; ++k)
+      if (k0 + k < W) c[k] = col2[(k0 + k) * ldh + h], a[k] = a2[(k0 + k) * ldh + h];
+    if constexpr (FORM == SB_FORM_COEF) {
+      double g0[C], g1[C];
+#pragma unroll
+      for (int k = 0; k < C; ++k)
+        if (k0 + k < W) {
+          g0[k] = (c[k].x >= 0) ? gather(x + c[k].x, coh) : 0.0;
+          g1[k] = (c[k].y >= 0) ? gather(x + c[k].y, coh) : 0.0;
+        }
+#pragma unroll
+      for (int k = 0; k < C; ++k)
+        if (k0 + k < W) {
+          const double t0 = __dadd_rn(u0, __dmul_rn(a[k].x, g0[k]));
+          const double t1 = __dadd_rn(u1, __dmul_rn(a[k].y, g1[k]));
+          u0 = (c[k].x >= 0) ? t0 : u0;
+          u1 = (c[k].y >= 0) ? t1 : u1;
+        }
+    } else {
+      const double2* __restrict__ d2 = reinterpret_cast<const double2*>(op.v1);
+      double2 d[C];
+#pragma unroll
+      for (int k = 0; k < C; ++k)
+        if (k0 + k < W) d[k] = d2[(k0 + k) * ldh + h];
+      double g0[C], g1[C];
+#pragma unroll
+      for (int k = 0; k < C; ++k)
+        if (k0 + k < W) {
+          // ghost entry (col == ~i): mirror state -x[i]; padding: skipped below
+          g0[k] = (c[k].x >= 0) ? gather(x + c[k].x, coh) : -xo.x;
+          g1[k] = (c[k].y >= 0) ? gather(x + c[k].y, coh) : -xo.y;
+        }
+#pragma unroll
+      for (int k = 0; k < C; ++k)
+        if (k0 + k < W) {
+          // flux = dt*(x_nbr - x_i)/dist ; u += (area/vol)*flux      (Playground.cpp:125-128)
+          const double f0 = __ddiv_rn(__dmul_rn(op.dt, __dsub_rn(g0[k], xo.x)), d[k].x);
+          const double f1 = __ddiv_rn(__dmul_rn(op.dt, __dsub_rn(g1[k], xo.y)), d[k].y);
+          const double t0 = __dadd_rn(u0, __dmul_rn(a[k].x, f0));
+          const double t1 = __dadd_rn(u1, __dmul_rn(a[k].y, f1));
+          u0 = (c[k].x != kColPad) ? t0 : u0;
+          u1 = (c[k].y != kColPad) ? t1 : u1;
+        }
+    }
+  }
+  return make_double2(u0, u1);
 }
 
 // y <- A x with a fused reduction epilogue. RESID: store b - A x instead (and reduce <r,r>).
@@ -491,8 +504,12 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
     case 6: SB_LAUNCH(FORM, 6); break;    \
     case 7: SB_LAUNCH(FORM, 7); break;    \
     case 8: SB_LAUNCH(FORM, 8); break;    \
+    case 10: SB_LAUNCH(FORM, 10); break;  \
+    case 12: SB_LAUNCH(FORM, 12); break;  \
+    case 14: SB_LAUNCH(FORM, 14); break;  \
+    case 16: SB_LAUNCH(FORM, 16); break;  \
     default:                              \
-      set_error("operator width %d not supported (max 8)", d.width); \
+      set_error("operator width %d not supported (1..8, 10, 12, 14, 16)", d.width); \
       return SB_ERR_INVALID;              \
   }
   if (d.form == SB_FORM_COEF && d.blk != nullptr) {
@@ -516,8 +533,12 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
       case 6: SB_LAUNCH_TMA(6) break;
       case 7: SB_LAUNCH_TMA(7) break;
       case 8: SB_LAUNCH_TMA(8) break;
+      case 10: SB_LAUNCH_TMA(10) break;
+      case 12: SB_LAUNCH_TMA(12) break;
+      case 14: SB_LAUNCH_TMA(14) break;
+      case 16: SB_LAUNCH_TMA(16) break;
       default:
-        set_error("operator width %d not supported (max 8)", d.width);
+        set_error("operator width %d not supported (1..8, 10, 12, 14, 16)", d.width);
         return SB_ERR_INVALID;
     }
 #undef SB_LAUNCH_TMA

@@ -102,6 +102,88 @@ class Mesh:
         return int(self.lib.sb_mesh_bandwidth(self.handle))
 
 
+class PolyMesh:
+    """Synthetic polyhedral mesh for the dual-polyhedra leg of the apply sweep:
+    the Voronoi tessellation of a body-centred cubic lattice, i.e. truncated octahedra with 14 faces
+    (6 squares to the axis neighbours, 8 hexagons to the diagonal neighbours; F ~ 7 N), optionally
+    stretched per axis. N = 2 n^3 cells: corner sites (i, j, k) a and centre sites (i+1/2, j+1/2, k+1/2) a,
+    a = 1/n, interleaved so neighbours stay close in memory. Faces follow the reference's conventions:
+    created cell by cell in local-face order, the creating (lower) cell is the inner one
+    (MeshUnstructured.hpp:509-554); a face whose neighbour site lies outside the lattice is a boundary
+    face with the mirror-ghost distance. Duck-types the `mesh` argument of FvmOperator / oracle FaceMesh.
+    Host numpy only (a workload generator, not part of the hot path)."""
+
+    #: the 14 neighbour directions in half-lattice units (2 = one lattice step along an axis)
+    DIRS = np.array([(-2, 0, 0), (2, 0, 0), (0, -2, 0), (0, 2, 0), (0, 0, -2), (0, 0, 2)] +
+                    [(dx, dy, dz) for dz in (-1, 1) for dy in (-1, 1) for dx in (-1, 1)], np.int64)
+
+    def __init__(self, n: int, stretch=(1.0, 1.0, 1.0)):
+        n = int(n)
+        assert n >= 1 and 2 * n ** 3 < 2 ** 31 - 4096
+        self.n, self.stretch = n, tuple(float(v) for v in stretch)
+        sx, sy, sz = self.stretch
+        a = 1.0 / n
+        N = 2 * n ** 3
+        ids = np.arange(N, dtype=np.int64)
+        s, q = ids & 1, ids >> 1
+        i, j, k = q % n, (q // n) % n, q // (n * n)
+        # positions in half-lattice units: corner (2i, 2j, 2k), centre (2i+1, 2j+1, 2k+1)
+        hx, hy, hz = 2 * i + s, 2 * j + s, 2 * k + s
+        self._half = (hx, hy, hz)
+        det = sx * sy * sz
+        sq_area = (a * a / 8.0) * np.array([sy * sz, sx * sz, sx * sy])            # squares, normal x / y / z
+        hex_area = (3.0 * np.sqrt(3.0) * a * a / 16.0) / np.sqrt(3.0) * det * np.sqrt(sx ** -2 + sy ** -2 + sz ** -2)
+        nbr = np.empty((N, 14), np.int64)
+        area = np.empty(14)
+        dist = np.empty(14)
+        for d, (dx, dy, dz) in enumerate(self.DIRS):
+            px, py, pz = hx + dx, hy + dy, hz + dz
+            ps = px & 1                              # parity picks the sub-lattice (all three coordinates agree)
+            pi, pj, pk = (px - ps) >> 1, (py - ps) >> 1, (pz - ps) >> 1
+            ok = (pi >= 0) & (pi < n) & (pj >= 0) & (pj < n) & (pk >= 0) & (pk < n)
+            nbr[:, d] = np.where(ok, 2 * ((pk * n + pj) * n + pi) + ps, -1)
+            area[d] = sq_area[d // 2] if d < 6 else hex_area
+            dist[d] = 0.5 * a * np.sqrt((sx * dx) ** 2 + (sy * dy) ** 2 + (sz * dz) ** 2)
+        owner = np.broadcast_to(ids[:, None], nbr.shape)
+        dcol = np.broadcast_to(np.arange(14)[None, :], nbr.shape)
+        interior = nbr > owner                       # the lower cell creates the face and is its inner cell
+        boundary = nbr < 0
+        self.n_cells = N
+        self.face_cell = np.stack([owner[interior], nbr[interior]], axis=1).astype(np.int32)
+        self.face_dir = dcol[interior].astype(np.int8)
+        self.face_area, self.face_dist = area[self.face_dir], dist[self.face_dir]
+        self.bface_cell = owner[boundary].astype(np.int32)
+        self.bface_dir = dcol[boundary].astype(np.int8)
+        self.bface_area, self.bface_dist = area[self.bface_dir], dist[self.bface_dir]
+        self.n_faces, self.n_bfaces = int(self.face_cell.shape[0]), int(self.bface_cell.shape[0])
+        self.cell_vol = np.full(N, 0.5 * a ** 3 * det)
+
+    @staticmethod
+    def bcc(n: int, stretch=(1.0, 1.0, 1.0)) -> "PolyMesh":
+        return PolyMesh(n, stretch)
+
+    def cell_centers(self) -> np.ndarray:
+        hx, hy, hz = self._half
+        h = 0.5 / self.n
+        sx, sy, sz = self.stretch
+        return np.stack([sx * h * hx, sy * h * hy, sz * h * hz], axis=1).astype(np.float64)
+
+    def face_normals(self):
+        """Unit normals (interior inner -> outer, boundary outward): M^-T d normalised, M = diag(stretch)."""
+        nrm = self.DIRS / np.asarray(self.stretch)[None, :]
+        nrm = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+        return nrm[self.face_dir], nrm[self.bface_dir]
+
+    def face_flux(self, beta):
+        fn, bn = self.face_normals()
+        bx, by, bz = (float(v) for v in beta)
+        return (bx * fn[:, 0] + by * fn[:, 1]) + bz * fn[:, 2], (bx * bn[:, 0] + by * bn[:, 1]) + bz * bn[:, 2]
+
+    @property
+    def bandwidth(self) -> int:
+        return int(np.abs(self.face_cell[:, 1].astype(np.int64) - self.face_cell[:, 0]).max()) if self.n_faces else 0
+
+
 class LocalView:
     """One rank's local mesh (sb_local_mesh) as numpy views; duck-types the `mesh` argument of
     FvmOperator / oracle FaceMesh (n_cells, face_cell, ...)."""

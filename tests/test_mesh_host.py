@@ -7,7 +7,7 @@ import pytest
 from oracle import mesh_oracle as mo
 from oracle import orc
 from stormruler_b200 import capi
-from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh, Partition
+from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh, Partition, PolyMesh
 
 KIND = {"tet": CELL_TET, "hex": CELL_HEX}
 SOA_KEYS = ("face_cell", "face_area", "face_dist", "cell_vol", "bface_cell", "bface_area", "bface_dist")
@@ -208,3 +208,43 @@ def test_partition_rejects_bad_input():
         Partition(mesh, 2, part=np.zeros(mesh.n_cells, np.int32))        # part 1 owns nothing
     with pytest.raises(capi.StormB200Error):
         Partition(mesh, 10 ** 6)                                         # more parts than cells
+
+
+@pytest.mark.parametrize("n,stretch", [(1, (1.0, 1.0, 1.0)), (5, (1.0, 1.0, 1.0)), (6, (1.0, 1.3, 0.7))])
+def test_polyhedral_mesh_geometry_is_closed_and_consistent(n, stretch):
+    """Truncated-octahedra mesh (config 5's dual-polyhedra leg): 14 faces per cell, every cell's area vectors sum to
+    zero, the pyramid sum over the faces gives the cell volume, the cells tile the stretched box lattice, faces are
+    ordered by creating cell with inner < outer, and the oracle's row forms (14 wide) agree with its face loop."""
+    m = PolyMesh.bcc(n, stretch)
+    N = 2 * n ** 3
+    assert m.n_cells == N and m.face_cell.dtype == np.int32 and m.bface_cell.dtype == np.int32
+    assert 2 * m.n_faces + m.n_bfaces == 14 * N
+    assert (m.face_cell[:, 0] < m.face_cell[:, 1]).all() and (np.diff(m.face_cell[:, 0]) >= 0).all()
+    assert (np.diff(m.bface_cell) >= 0).all()
+    fn, bn = m.face_normals()
+    S, V = np.zeros((N, 3)), np.zeros(N)
+    np.add.at(S, m.face_cell[:, 0], m.face_area[:, None] * fn)
+    np.add.at(S, m.face_cell[:, 1], -m.face_area[:, None] * fn)
+    np.add.at(S, m.bface_cell, m.bface_area[:, None] * bn)
+    assert np.abs(S).max() < 1e-15
+    # pyramid heights: the face plane bisects the segment to the neighbour site, h = (M d / 2) . n
+    step = m.DIRS * np.asarray(stretch)[None, :] * (0.5 / n)
+    nrm = m.DIRS / np.asarray(stretch)[None, :]
+    nrm = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+    h = 0.5 * (step * nrm).sum(axis=1)
+    assert np.allclose(np.linalg.norm(step, axis=1)[m.face_dir], m.face_dist, rtol=1e-15)
+    for cells, area, d in ((m.face_cell[:, 0], m.face_area, m.face_dir), (m.face_cell[:, 1], m.face_area, m.face_dir),
+                           (m.bface_cell, m.bface_area, m.bface_dir)):
+        np.add.at(V, cells, area * h[d] / 3.0)
+    assert np.allclose(V, m.cell_vol, rtol=1e-13)
+    assert np.isclose(m.cell_vol.sum(), stretch[0] * stretch[1] * stretch[2], rtol=1e-13)
+    c = m.cell_centers()
+    d_centres = np.linalg.norm(c[m.face_cell[:, 1]] - c[m.face_cell[:, 0]], axis=1)
+    assert np.allclose(d_centres, m.face_dist, rtol=1e-13)
+    fm = orc.FaceMesh(N, m.face_cell, m.face_area, m.face_dist, m.cell_vol, m.bface_cell, m.bface_area, m.bface_dist)
+    cpu = orc.FaceOp(fm, prefill=1, dt=-0.05, dirichlet=True)
+    assert cpu.rows_faithful()[0] == 14
+    x = np.random.default_rng(3).standard_normal(N)
+    want = cpu.apply(x)
+    assert np.array_equal(cpu.apply_rows_faithful(x), want)
+    assert np.abs(cpu.apply_rows_coef(x) - want).max() <= 1e-13 * np.abs(want).max()
