@@ -160,6 +160,7 @@ SB_API int sb_op_jacobi(sb_ctx* ctx, const sb_op* op, const double* x, double* y
 typedef struct sb_mesh sb_mesh;
 #define SB_CELL_TET 0
 #define SB_CELL_HEX 1
+#define SB_CELL_FACELIST 2 /* any cell shape: the mesh is its face list (sb_mesh_from_faces) */
 
 /* Box [0,1]^3 of nx*ny*nz hexahedra, optionally split into 6 Kuhn tetrahedra each (SB_CELL_TET).
  * Interior nodes are displaced by U(-jitter*h, jitter*h) per coordinate (std::mt19937_64(seed_jitter),
@@ -170,6 +171,16 @@ SB_API int sb_mesh_generate_box(int cell_kind, int nx, int ny, int nz, double ji
 /* General ingestion: h_xyz [3*n_nodes], h_cell_nodes [n_cells * (4 | 8)]. */
 SB_API int sb_mesh_from_cells(int cell_kind, int64_t n_nodes, const double* h_xyz, int64_t n_cells,
                               const int32_t* h_cell_nodes, sb_mesh** out);
+/* Ingestion of a face list -- what the reference's own mesh classes export through interior_faces() /
+ * faces(label) (Mallard/Mesh.hpp:426-429,453-455), FaceView::inner_cell/outer_cell (:269-280) and the geometry
+ * getters area/volume/center (:254-261,304-311): any cell shape, up to 127 faces per cell (polyhedral meshes,
+ * the reference's 2-D meshes). The arrays are copied and kept verbatim (face order and inner/outer as given), so
+ * the handle can be renumbered (RCM, sb_mesh_permute_cells) and partitioned like a node-based mesh. A renumbering
+ * re-derives the face order by the creation rule above (creating cell = lower cell id, then the face's ordinal
+ * among that cell's faces in the given list). Optional: h_cell_ctr [3*n_cells]; unit normals h_face_normal
+ * [3*n_faces] (inner -> outer) and h_bface_normal [3*n_bfaces] (outward) -- both or neither. */
+SB_API int sb_mesh_from_faces(const sb_mesh_soa* h_soa, const double* h_cell_ctr, const double* h_face_normal,
+                              const double* h_bface_normal, sb_mesh** out);
 /* TetGen ingestion in 3-D: reads `<prefix>.node` and `<prefix>.ele` with the file
  * grammar of the reference's reader (Mallard/IoTetgen.hpp:44-235: '#' comments, node header
  * `count dim n_attribs has_labels`, element header `count nodes_per_cell has_attribs`, one entity per line led

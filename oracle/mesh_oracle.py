@@ -252,6 +252,49 @@ def permute(xyz, cells, perm):
     return xyz, cells[perm]
 
 
+def permute_face_list(mesh: dict, perm, face_normal=None, bface_normal=None, cell_ctr=None):
+    """Renumbering of a mesh that is given as its face list (include/stormb200.h: sb_mesh_from_faces).
+    The local face index of a face in a cell is its ordinal among that cell's faces in the ORIGINAL list
+    (interior faces first, then boundary faces); after the renumbering (cell `new` = old cell perm[new]) the
+    creating (inner) cell of an interior face is the lower new id, faces are ordered by (creating cell, its local
+    face index), interior faces first, and a normal flips when inner and outer swap."""
+    n = int(mesh["n_cells"])
+    perm = np.asarray(perm, np.int64)
+    iperm = np.empty(n, np.int64)
+    iperm[perm] = np.arange(n)
+    fc = np.asarray(mesh["face_cell"], np.int64).reshape(-1, 2)
+    bc = np.asarray(mesh["bface_cell"], np.int64)
+    F, B = fc.shape[0], bc.shape[0]
+    count = np.zeros(n, np.int64)
+    lf = np.zeros((F, 2), np.int64)
+    for f in range(F):
+        for side in (0, 1):
+            lf[f, side] = count[fc[f, side]]
+            count[fc[f, side]] += 1
+    blf = np.zeros(B, np.int64)
+    for q in range(B):
+        blf[q] = count[bc[q]]
+        count[bc[q]] += 1
+    a, b = iperm[fc[:, 0]], iperm[fc[:, 1]]
+    swap = b < a
+    inner, outer = np.where(swap, b, a), np.where(swap, a, b)
+    ilf = np.where(swap, lf[:, 1], lf[:, 0])
+    order = np.lexsort((ilf, inner))
+    border = np.lexsort((blf, iperm[bc]))
+    out = dict(n_cells=n, cell_vol=np.asarray(mesh["cell_vol"])[perm],
+               face_cell=np.stack([inner[order], outer[order]], 1).astype(np.int32),
+               face_area=np.asarray(mesh["face_area"])[order], face_dist=np.asarray(mesh["face_dist"])[order],
+               bface_cell=iperm[bc][border].astype(np.int32), bface_area=np.asarray(mesh["bface_area"])[border],
+               bface_dist=np.asarray(mesh["bface_dist"])[border])
+    if face_normal is not None:
+        sign = np.where(swap, -1.0, 1.0)[:, None]
+        out["face_normal"] = (sign * np.asarray(face_normal))[order]
+        out["bface_normal"] = np.asarray(bface_normal)[border]
+    if cell_ctr is not None:
+        out["cell_ctr"] = np.asarray(cell_ctr)[perm]
+    return out
+
+
 # ---- partitions ----------------------------------------------------------------------------------------
 def slab_partition(n, n_parts):
     part = np.zeros(n, np.int32)

@@ -8,7 +8,7 @@ For every (cell kind, size): synthetic jittered box mesh of about that many cell
 input of every apply is freshly written, as inside a Krylov iteration) bracketed by stream synchronisation, after 8
 warm-up applies; GB/s = algorithmic bytes (24 N + 12 entries) / time. One JSON line per point and a
 summary object at the end. `poly` = truncated octahedra (the Voronoi cells of a body-centred cubic lattice: 14 faces
-per cell, F ~ 7 N, the 14-wide instantiation of the apply kernel; lattice order, single GPU only).
+per cell, F ~ 7 N, the 14-wide instantiation of the apply kernel), ingested as a face list and RCM-renumbered.
 """
 from __future__ import annotations
 
@@ -57,11 +57,8 @@ def main():
             n_axis = axis_for(kind, size)
             t0 = time.time()
             if kind == "poly":
-                if world > 1:
-                    if rank == 0:
-                        print(json.dumps({"cell": kind, "skipped": "the partitioner takes node-based meshes only"}), flush=True)
-                    continue
-                mesh = PolyMesh.bcc(n_axis, stretch=(1.0, 1.3, 0.7))
+                mesh = PolyMesh.bcc(n_axis, stretch=(1.0, 1.3, 0.7)).to_mesh()   # face-list handle (sb_mesh_from_faces)
+                mesh.renumber_rcm()
             else:
                 mesh = Mesh.box(CELL_TET if kind == "tet" else CELL_HEX, n_axis, jitter=0.2, seed_jitter=42, shuffle=True,
                                 seed_shuffle=43)

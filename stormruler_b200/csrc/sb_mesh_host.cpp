@@ -123,6 +123,12 @@ struct sb_mesh {
   std::vector<int32_t> face_cell, bface_cell;
   std::vector<double> face_area, face_dist, bface_area, bface_dist;
 
+  // face-list meshes (SB_CELL_FACELIST, sb_mesh_from_faces): no nodes; the geometry is carried per face,
+  // indexed like `pairs`. pair_normal (optional, 3 per face) is oriented from pair_first to the other side.
+  std::vector<double> pair_area, pair_dist, pair_normal;
+  std::vector<int32_t> pair_first; // the cell the stored normal points away from, as an index into cell[] (0 | 1)
+  bool has_centers = false;
+
   V3 node(int32_t i) const { return {xyz[3 * (size_t) i], xyz[3 * (size_t) i + 1], xyz[3 * (size_t) i + 2]}; }
   const int* local_face(int lf) const { return kind == SB_CELL_TET ? kTetFaces[lf] : kHexFaces[lf]; }
 };
@@ -209,7 +215,45 @@ int match_faces(sb_mesh& m) {
 
 // Stage 2: order the faces by creation (first cell in cell order, then local face), interior first,
 // fix inner = creator, and evaluate the face geometry.
+// Face-list meshes: same ordering rule (creating cell = the lower cell id, then that cell's local face), the
+// geometry is the stored per-face payload instead of being evaluated from nodes.
+void order_faces_facelist(sb_mesh& m) {
+  const int64_t nf = (int64_t) m.pairs.size();
+  std::vector<uint64_t> key((size_t) nf);
+  int64_t n_int = 0;
+  for (int64_t f = 0; f < nf; ++f) {
+    FacePair& p = m.pairs[(size_t) f];
+    if (p.cell[1] >= 0 && p.cell[1] < p.cell[0]) {
+      std::swap(p.cell[0], p.cell[1]), std::swap(p.lf[0], p.lf[1]);
+      m.pair_first[(size_t) f] ^= 1;
+    }
+    n_int += p.cell[1] >= 0;
+    key[(size_t) f] = ((uint64_t) (p.cell[1] < 0) << 62) | ((uint64_t) p.cell[0] * 256u + (uint64_t) (uint8_t) p.lf[0]);
+  }
+  std::vector<int64_t> idx((size_t) nf);
+  std::iota(idx.begin(), idx.end(), 0);
+  parallel_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return key[(size_t) a] < key[(size_t) b]; });
+  const int64_t n_b = nf - n_int;
+  m.face_cell.assign(2 * (size_t) n_int, 0);
+  m.face_area.assign((size_t) n_int, 0.0), m.face_dist.assign((size_t) n_int, 0.0);
+  m.bface_cell.assign((size_t) n_b, 0);
+  m.bface_area.assign((size_t) n_b, 0.0), m.bface_dist.assign((size_t) n_b, 0.0);
+  for (int64_t q = 0; q < nf; ++q) {
+    const size_t f = (size_t) idx[(size_t) q];
+    const FacePair& p = m.pairs[f];
+    if (q < n_int) {
+      m.face_cell[2 * (size_t) q] = p.cell[0], m.face_cell[2 * (size_t) q + 1] = p.cell[1];
+      m.face_area[(size_t) q] = m.pair_area[f], m.face_dist[(size_t) q] = m.pair_dist[f];
+    } else {
+      const size_t b = (size_t) (q - n_int);
+      m.bface_cell[b] = p.cell[0], m.bface_area[b] = m.pair_area[f], m.bface_dist[b] = m.pair_dist[f];
+    }
+  }
+  m.face_order.swap(idx);
+}
+
 void order_faces(sb_mesh& m) {
+  if (m.kind == SB_CELL_FACELIST) return order_faces_facelist(m);
   const int64_t nf = (int64_t) m.pairs.size();
   std::vector<uint64_t> key((size_t) nf); // (creator cell * 8 + local face) << 1 ... sorted ascending
   int64_t n_int = 0;
@@ -273,6 +317,18 @@ void order_faces(sb_mesh& m) {
 // its length; flipped when it points against (x_outer - x_inner) / (face centre - x_inner).
 void face_normals(const sb_mesh& m, double* fn, double* bn) {
   const int64_t nf = (int64_t) m.face_order.size(), n_int = (int64_t) m.face_area.size();
+  if (m.kind == SB_CELL_FACELIST) {
+    // stored normals point away from pair_first; the inner cell is cell[0]
+    for (int64_t q = 0; q < nf; ++q) {
+      const size_t f = (size_t) m.face_order[(size_t) q];
+      const double sgn = m.pair_first[f] == 0 ? 1.0 : -1.0;
+      double* base = q < n_int ? fn : bn;
+      if (base == nullptr) continue;
+      double* out = base + 3 * (q < n_int ? q : q - n_int);
+      for (int c = 0; c < 3; ++c) out[c] = sgn * m.pair_normal[3 * f + (size_t) c];
+    }
+    return;
+  }
   parallel_for(nf, [&](int64_t lo, int64_t hi) {
     for (int64_t q = lo; q < hi; ++q) {
       const FacePair& p = m.pairs[(size_t) m.face_order[(size_t) q]];
@@ -335,12 +391,14 @@ int apply_permutation(sb_mesh& m, const int32_t* perm) {
   parallel_for(n, [&](int64_t lo, int64_t hi) {
     for (int64_t k = lo; k < hi; ++k) {
       const size_t o = (size_t) perm[k];
-      std::memcpy(&cells[(size_t) k * m.npc], &m.cells[o * m.npc], sizeof(int32_t) * m.npc);
+      if (m.npc > 0) std::memcpy(&cells[(size_t) k * m.npc], &m.cells[o * m.npc], sizeof(int32_t) * m.npc);
       vol[(size_t) k] = m.cell_vol[o];
-      ctr[3 * (size_t) k] = m.cell_ctr[3 * o], ctr[3 * (size_t) k + 1] = m.cell_ctr[3 * o + 1], ctr[3 * (size_t) k + 2] = m.cell_ctr[3 * o + 2];
+      if (!m.cell_ctr.empty())
+        ctr[3 * (size_t) k] = m.cell_ctr[3 * o], ctr[3 * (size_t) k + 1] = m.cell_ctr[3 * o + 1], ctr[3 * (size_t) k + 2] = m.cell_ctr[3 * o + 2];
     }
   });
-  m.cells.swap(cells), m.cell_vol.swap(vol), m.cell_ctr.swap(ctr);
+  m.cells.swap(cells), m.cell_vol.swap(vol);
+  if (!m.cell_ctr.empty()) m.cell_ctr.swap(ctr);
   for (FacePair& p : m.pairs) {
     p.cell[0] = iperm[(size_t) p.cell[0]];
     if (p.cell[1] >= 0) p.cell[1] = iperm[(size_t) p.cell[1]];
@@ -443,6 +501,62 @@ int sb_mesh_from_cells(int cell_kind, int64_t n_nodes, const double* h_xyz, int6
   if (rc != SB_OK) return rc;
   rc = derive(*m);
   if (rc != SB_OK) return rc;
+  *out = m.release();
+  return SB_OK;
+}
+
+int sb_mesh_from_faces(const sb_mesh_soa* h, const double* h_cell_ctr, const double* h_face_normal,
+                       const double* h_bface_normal, sb_mesh** out) {
+  SBM_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  SBM_REQUIRE(h != nullptr && h->n_cells > 0 && h->cell_vol != nullptr, "empty mesh");
+  SBM_REQUIRE(h->n_cells < (int64_t) 0x7FFFFFFF - 4096, "mesh too large for int32 indices");
+  SBM_REQUIRE(h->n_faces >= 0 && h->n_bfaces >= 0, "negative face count");
+  SBM_REQUIRE(h->n_faces == 0 || (h->face_cell && h->face_area && h->face_dist), "null face arrays");
+  SBM_REQUIRE(h->n_bfaces == 0 || (h->bface_cell && h->bface_area && h->bface_dist), "null boundary-face arrays");
+  const int64_t n = h->n_cells, F = h->n_faces, B = h->n_bfaces;
+  const bool normals = h_face_normal != nullptr || h_bface_normal != nullptr;
+  SBM_REQUIRE(!normals || ((F == 0 || h_face_normal != nullptr) && (B == 0 || h_bface_normal != nullptr)),
+              "give both normal arrays or neither");
+  std::unique_ptr<sb_mesh> m(new sb_mesh());
+  m->kind = SB_CELL_FACELIST, m->npc = 0, m->nfc = 0, m->n_nodes = 0, m->n_cells = n;
+  m->cell_vol.assign(h->cell_vol, h->cell_vol + n);
+  if (h_cell_ctr != nullptr) m->cell_ctr.assign(h_cell_ctr, h_cell_ctr + 3 * n), m->has_centers = true;
+  // local face index of a face in a cell = its ordinal among that cell's faces in the given order (interior faces
+  // first, then boundary faces): a property of the cell, independent of any later renumbering
+  std::vector<int32_t> count((size_t) n, 0);
+  m->pairs.resize((size_t) (F + B));
+  m->pair_area.resize((size_t) (F + B)), m->pair_dist.resize((size_t) (F + B));
+  m->pair_first.assign((size_t) (F + B), 0);
+  if (normals) m->pair_normal.resize(3 * (size_t) (F + B));
+  for (int64_t f = 0; f < F; ++f) {
+    const int32_t a = h->face_cell[2 * f], b = h->face_cell[2 * f + 1];
+    SBM_REQUIRE(a >= 0 && a < n && b >= 0 && b < n && a != b, "face_cell index out of range");
+    SBM_REQUIRE(count[(size_t) a] < 127 && count[(size_t) b] < 127, "more than 127 faces on a cell");
+    FacePair& p = m->pairs[(size_t) f];
+    p.cell[0] = a, p.cell[1] = b;
+    p.lf[0] = (int8_t) count[(size_t) a]++, p.lf[1] = (int8_t) count[(size_t) b]++;
+    m->pair_area[(size_t) f] = h->face_area[f], m->pair_dist[(size_t) f] = h->face_dist[f];
+    if (normals) std::memcpy(&m->pair_normal[3 * (size_t) f], h_face_normal + 3 * f, 3 * sizeof(double));
+  }
+  for (int64_t q = 0; q < B; ++q) {
+    const int32_t a = h->bface_cell[q];
+    SBM_REQUIRE(a >= 0 && a < n, "bface_cell index out of range");
+    SBM_REQUIRE(count[(size_t) a] < 127, "more than 127 faces on a cell");
+    FacePair& p = m->pairs[(size_t) (F + q)];
+    p.cell[0] = a, p.cell[1] = -1;
+    p.lf[0] = (int8_t) count[(size_t) a]++, p.lf[1] = -1;
+    m->pair_area[(size_t) (F + q)] = h->bface_area[q], m->pair_dist[(size_t) (F + q)] = h->bface_dist[q];
+    if (normals) std::memcpy(&m->pair_normal[3 * (size_t) (F + q)], h_bface_normal + 3 * q, 3 * sizeof(double));
+  }
+  // the face list is taken verbatim (order and inner/outer as given: "the reference's face order"); only a later
+  // renumbering re-derives the order by the creation rule
+  m->face_cell.assign(h->face_cell, h->face_cell + 2 * F);
+  m->face_area.assign(h->face_area, h->face_area + F), m->face_dist.assign(h->face_dist, h->face_dist + F);
+  m->bface_cell.assign(h->bface_cell, h->bface_cell + B);
+  m->bface_area.assign(h->bface_area, h->bface_area + B), m->bface_dist.assign(h->bface_dist, h->bface_dist + B);
+  m->face_order.resize((size_t) (F + B));
+  std::iota(m->face_order.begin(), m->face_order.end(), 0);
   *out = m.release();
   return SB_OK;
 }
@@ -644,12 +758,14 @@ int sb_mesh_get_soa(const sb_mesh* m, sb_mesh_soa* soa) {
 
 int sb_mesh_cell_centers(const sb_mesh* m, double* h_xyz) {
   SBM_REQUIRE(m != nullptr && h_xyz != nullptr, "null argument");
+  SBM_REQUIRE(!m->cell_ctr.empty(), "this face-list mesh was created without cell centres");
   std::memcpy(h_xyz, m->cell_ctr.data(), sizeof(double) * m->cell_ctr.size());
   return SB_OK;
 }
 
 int sb_mesh_face_normals(const sb_mesh* m, double* h_fn, double* h_bn) {
   SBM_REQUIRE(m != nullptr, "mesh is null");
+  SBM_REQUIRE(m->kind != SB_CELL_FACELIST || !m->pair_normal.empty(), "this face-list mesh was created without normals");
   face_normals(*m, h_fn, h_bn);
   return SB_OK;
 }

@@ -8,7 +8,7 @@ import numpy as np
 
 from . import capi
 
-CELL_TET, CELL_HEX = 0, 1
+CELL_TET, CELL_HEX, CELL_FACELIST = 0, 1, 2
 
 
 class Mesh:
@@ -37,6 +37,28 @@ class Mesh:
         h = C.c_void_p()
         capi.check(lib.sb_mesh_from_cells(kind, xyz.shape[0], xyz.ctypes.data_as(capi.f64p), cells.shape[0],
                                           cells.ctypes.data_as(capi.i32p), C.byref(h)))
+        return Mesh(h)
+
+    @staticmethod
+    def from_faces(mesh, centers=None, face_normals=None, bface_normals=None) -> "Mesh":
+        """sb_mesh_from_faces: a handle over a face list (`mesh` needs n_cells, face_cell [F,2], face_area,
+        face_dist, cell_vol, bface_cell, bface_area, bface_dist -- e.g. an export of the reference's own mesh
+        classes, or a PolyMesh), so it can be RCM-renumbered and partitioned like a node-based mesh."""
+        lib = capi.load()
+        f64 = lambda a: np.ascontiguousarray(a, np.float64)  # noqa: E731
+        fc = np.ascontiguousarray(mesh.face_cell, np.int32).reshape(-1)
+        fa, fd, cv = f64(mesh.face_area), f64(mesh.face_dist), f64(mesh.cell_vol)
+        bc = np.ascontiguousarray(mesh.bface_cell, np.int32)
+        ba, bd = f64(mesh.bface_area), f64(mesh.bface_dist)
+        soa = capi.MeshSoa(int(mesh.n_cells), int(fa.shape[0]), fc.ctypes.data_as(capi.i32p),
+                           fa.ctypes.data_as(capi.f64p), fd.ctypes.data_as(capi.f64p), cv.ctypes.data_as(capi.f64p),
+                           int(ba.shape[0]), bc.ctypes.data_as(capi.i32p), ba.ctypes.data_as(capi.f64p),
+                           bd.ctypes.data_as(capi.f64p))
+        opt = lambda a, cols: None if a is None else f64(a).reshape(-1, cols)  # noqa: E731
+        ctr, fn, bn = opt(centers, 3), opt(face_normals, 3), opt(bface_normals, 3)
+        ptr = lambda a: None if a is None else a.ctypes.data_as(capi.f64p)  # noqa: E731
+        h = C.c_void_p()
+        capi.check(lib.sb_mesh_from_faces(C.byref(soa), ptr(ctr), ptr(fn), ptr(bn), C.byref(h)))
         return Mesh(h)
 
     @staticmethod
@@ -182,6 +204,12 @@ class PolyMesh:
     @property
     def bandwidth(self) -> int:
         return int(np.abs(self.face_cell[:, 1].astype(np.int64) - self.face_cell[:, 0]).max()) if self.n_faces else 0
+
+    def to_mesh(self) -> Mesh:
+        """The same mesh as a library handle (sb_mesh_from_faces) with centres and normals attached: can be
+        renumbered (RCM) and partitioned for the multi-GPU path."""
+        fn, bn = self.face_normals()
+        return Mesh.from_faces(self, self.cell_centers(), fn, bn)
 
 
 class LocalView:

@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 from oracle import orc  # noqa: E402
 from stormruler_b200 import capi  # noqa: E402
 from stormruler_b200 import multigpu as mg  # noqa: E402
-from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh  # noqa: E402
+from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh, PolyMesh  # noqa: E402
 
 
 def face_mesh(m):
@@ -68,8 +68,12 @@ def host_halo_exchange(dist, loc, x_local):
 def run_cpu(dist, rank, world):
     import torch
     for kind, dims, method in ((CELL_TET, (6, 5, 4), capi.PART_METIS), (CELL_HEX, (7, 6, 5), capi.PART_SLAB),
-                               (CELL_TET, (9, 3, 3), capi.PART_SLAB)):
-        mesh = Mesh.box(kind, *dims, jitter=0.2, seed_jitter=42, shuffle=True, seed_shuffle=43)
+                               (CELL_TET, (9, 3, 3), capi.PART_SLAB), ("poly", (4,), capi.PART_METIS)):
+        if kind == "poly":   # 14-face cells, ingested as a face list (sb_mesh_from_faces)
+            mesh = PolyMesh.bcc(*dims, stretch=(1.0, 1.3, 0.7)).to_mesh()
+            mesh.permute_cells(np.random.default_rng(43).permutation(mesh.n_cells).astype(np.int32))
+        else:
+            mesh = Mesh.box(kind, *dims, jitter=0.2, seed_jitter=42, shuffle=True, seed_shuffle=43)
         mesh.renumber_rcm()
         part = mg.partition_mesh(mesh, world, method)
         loc = part.local(rank)

@@ -248,3 +248,88 @@ def test_polyhedral_mesh_geometry_is_closed_and_consistent(n, stretch):
     want = cpu.apply(x)
     assert np.array_equal(cpu.apply_rows_faithful(x), want)
     assert np.abs(cpu.apply_rows_coef(x) - want).max() <= 1e-13 * np.abs(want).max()
+
+
+def face_list_dict(m):
+    return dict(n_cells=m.n_cells, **{k: np.asarray(getattr(m, k)) for k in SOA_KEYS})
+
+
+@pytest.mark.parametrize("source", ["poly", "square_nb"])
+def test_face_list_mesh_handle_renumbering_and_partition_bit_exact(source):
+    """sb_mesh_from_faces: the mesh IS its face list (a polyhedral mesh; the reference mesh classes' own export of
+    tests/_data/mesh/square_nb.1). Verbatim on creation; permutations and RCM against the numpy restatement;
+    partition local meshes and halo maps against the same restatement as the node-based meshes."""
+    if source == "poly":
+        src = PolyMesh.bcc(5, (1.0, 1.3, 0.7))
+        ctr = src.cell_centers()
+        fn, bn = src.face_normals()
+    else:
+        from conftest import golden_mesh
+        src = golden_mesh("square_nb")
+        ctr = fn = bn = None
+    mesh = Mesh.from_faces(src, ctr, fn, bn)
+    before = face_list_dict(src)
+    assert_soa_equal(mesh, before)                                     # taken verbatim
+    if fn is not None:
+        got_fn, got_bn = mesh.face_normals()
+        assert np.array_equal(got_fn, fn) and np.array_equal(got_bn, bn)
+        assert np.array_equal(mesh.cell_centers(), ctr)
+    else:
+        with pytest.raises(capi.StormB200Error):
+            mesh.face_normals()
+        with pytest.raises(capi.StormB200Error):
+            mesh.cell_centers()
+    n = mesh.n_cells
+    shuffle = np.random.default_rng(7).permutation(n).astype(np.int32)
+    mesh.permute_cells(shuffle)
+    want = mo.permute_face_list(before, shuffle, fn, bn, ctr)
+    assert_soa_equal(mesh, want)
+    if fn is not None:
+        got_fn, got_bn = mesh.face_normals()
+        assert np.array_equal(got_fn, want["face_normal"]) and np.array_equal(got_bn, want["bface_normal"])
+        assert np.array_equal(mesh.cell_centers(), want["cell_ctr"])
+    assert (mesh.face_cell[:, 0] < mesh.face_cell[:, 1]).all()
+    bw_shuffled = mesh.bandwidth
+    perm = mesh.renumber_rcm()
+    assert np.array_equal(perm, mo.rcm(n, want["face_cell"])), "RCM permutation differs from the restatement"
+    total = shuffle[perm]                                              # old id of every new cell, both steps
+    assert_soa_equal(mesh, mo.permute_face_list(before, total, fn, bn, ctr))
+    assert mesh.bandwidth < bw_shuffled // 3
+    # the operator does not care how the cells are numbered: y_new[k] == y_old[total[k]] up to the sum order
+    x = np.cos(0.11 * np.arange(n)) + 0.3
+    y0 = orc.FaceOp(orc.FaceMesh(n, *[before[k] for k in SOA_KEYS]), prefill=1, dt=-0.05, dirichlet=True).apply(x)
+    fm = orc.FaceMesh(n, mesh.face_cell, mesh.face_area, mesh.face_dist, mesh.cell_vol, mesh.bface_cell,
+                      mesh.bface_area, mesh.bface_dist)
+    y1 = orc.FaceOp(fm, prefill=1, dt=-0.05, dirichlet=True).apply(x[total])
+    assert np.abs(y1 - y0[total]).max() <= 1e-13 * np.abs(y0).max()
+    # partitioning works on the handle like on a node-based mesh
+    gd = as_dict(mesh)
+    for method, n_parts in ((capi.PART_SLAB, 3), (capi.PART_METIS, 4)):
+        P = Partition(mesh, n_parts, method)
+        for r in range(n_parts):
+            L, wl = P.local(r), mo.local_maps(gd, P.part, r, n_parts)
+            for k in ("n_owned", "n_interior", "n_halo", "halo_base"):
+                assert getattr(L, k) == wl[k], (r, k)
+            for k in LOCAL_KEYS:
+                got = np.asarray(getattr(L, k))
+                assert got.shape == wl[k].shape and np.array_equal(got, wl[k]), (r, k)
+
+
+def test_face_list_mesh_rejects_bad_input():
+    src = PolyMesh.bcc(2)
+    bad = face_list_dict(src)
+
+    class M:
+        pass
+    m = M()
+    for k, v in bad.items():
+        setattr(m, k, v.copy() if isinstance(v, np.ndarray) else v)
+    m.face_cell[3, 1] = m.n_cells                                       # out of range
+    with pytest.raises(capi.StormB200Error):
+        Mesh.from_faces(m)
+    m.face_cell[3, 1] = m.face_cell[3, 0]                               # a face between a cell and itself
+    with pytest.raises(capi.StormB200Error):
+        Mesh.from_faces(m)
+    fn, bn = src.face_normals()
+    with pytest.raises(capi.StormB200Error):
+        Mesh.from_faces(src, None, fn, None)                            # one normal array without the other
