@@ -4,8 +4,11 @@
 
 One 3-D Poisson problem (BASELINE.json configs[1]: jittered Kuhn-tetrahedral box mesh, Dirichlet mirror ghosts,
 shuffled then RCM-renumbered, b = A x*), then for each solver: tolerances 0 so the iteration count is exact, one
-warm-up solve, then two timed solves of K and 3K iterations; iterations/s = 2K / (t_3K - t_K), which cancels the
-initialisation (initial residual, IDR(s)'s host-generated shadow vectors). Solvers:
+warm-up solve, then `--repeats` pairs of timed solves of K and 3K iterations; iterations/s = 2K / (min t_3K - min t_K),
+which cancels the initialisation (initial residual, allocations, IDR(s)'s host-generated shadow vectors: 0.3 s) and,
+through the minima, the hiccups of a shared host (a first version with single samples and K = 40 was off by up to 10x
+for individual solvers: 50 ms of signal against 0.4 s stalls). Wall clock around the C-ABI calls, stream drained
+on both sides: the generic path is host-driven, so this is what an application sees. Solvers:
 
   * generic drop-in: StormRuler's own solver templates instantiated on Storm::DeviceVector
     (cg cgs bicgstab bicgstabl gmres fgmres tfqmr tfqmr1 idrs richardson) -- one kernel per vector statement, one
@@ -54,7 +57,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--axis", type=int, default=119)
     ap.add_argument("--cell", default="tet", choices=["tet", "hex"])
-    ap.add_argument("--steps", type=int, default=40, help="K: the timed solves run K and 3K iterations")
+    ap.add_argument("--steps", type=int, default=100, help="K: the timed solves run K and 3K iterations")
+    ap.add_argument("--repeats", type=int, default=3)
     ap.add_argument("--m", type=int, default=50, help="GMRES restart length")
     ap.add_argument("--solvers", default=",".join(ALL))
     ap.add_argument("--out", default="")
@@ -105,8 +109,11 @@ def main():
     for solver in args.solvers.split(","):
         try:
             run(solver, min(K, 10))
-            t1, _ = run(solver, K)
-            t3, err = run(solver, 3 * K)
+            t1 = t3 = float("inf")
+            for _ in range(args.repeats):
+                t1 = min(t1, run(solver, K)[0])
+                t, err = run(solver, 3 * K)
+                t3 = min(t3, t)
         except Exception as e:  # keep the sweep going: one solver's failure is a data point, not the end
             pt = {"solver": solver, "error": str(e)[:300]}
             print(json.dumps(pt), flush=True)
@@ -124,7 +131,7 @@ def main():
         if args.out:  # rewritten after every solver: a cut-off run keeps what it measured
             with open(args.out, "w") as f:
                 json.dump({"what": "solver sweep (SURVEY.md 8d contract bytes)", "cell": args.cell, "cells": int(n),
-                           "K": K, "restart": args.m, "peak_gbs": peak, "points": points}, f, indent=1)
+                           "K": K, "repeats": args.repeats, "restart": args.m, "peak_gbs": peak, "points": points}, f, indent=1)
     ctx.close()
 
 
