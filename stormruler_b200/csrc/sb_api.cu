@@ -72,6 +72,7 @@ int sb_ctx_destroy(sb_ctx* ctx) {
   ctx->work.clear();
   for (double* w : ctx->basis) vec_free(ctx, w);
   ctx->basis.clear();
+  vec_cache_release(ctx);
   cudaFree(ctx->d_gmres_scal);
   cudaFree(ctx->d_gmres_ptrs);
   cudaFreeHost(ctx->h_gmres);

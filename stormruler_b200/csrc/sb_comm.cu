@@ -78,12 +78,52 @@ struct Blob { // SB_COMM_BLOB_BYTES
 static_assert(sizeof(Blob) == SB_COMM_BLOB_BYTES, "blob layout");
 
 // ---- vector storage ------------------------------------------------------------------------------------
+// Cache limit: SB_VEC_CACHE_MB (0 disables the cache), default a quarter of the device memory.
+static int64_t vec_cache_limit(sb_ctx* ctx) {
+  if (ctx->vec_cache_limit < 0) {
+    size_t free_b = 0, total_b = 0;
+    if (const char* e = std::getenv("SB_VEC_CACHE_MB")) {
+      ctx->vec_cache_limit = std::max<int64_t>(0, std::atoll(e)) << 20;
+    } else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      ctx->vec_cache_limit = (int64_t) (total_b / 4);
+    } else {
+      ctx->vec_cache_limit = 0;
+    }
+  }
+  return ctx->vec_cache_limit;
+}
+
+void vec_cache_release(sb_ctx* ctx) {
+  if (ctx->vec_cache.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->vec_cache) {
+    ctx->vec_cap.erase(kv.second);
+    cudaFree(kv.second);
+  }
+  ctx->vec_cache.clear();
+  ctx->vec_cache_bytes = 0;
+}
+
 int vec_alloc(sb_ctx* ctx, size_t n, double** out) {
   *out = nullptr;
   if (ctx->comm.mode < 0) {
     const int64_t cap = pad_up((int64_t) n > 0 ? (int64_t) n : 1);
     double* d = nullptr;
-    SB_CUDA(cudaMalloc(&d, sizeof(double) * cap));
+    auto hit = ctx->vec_cache.find(cap);
+    if (hit != ctx->vec_cache.end()) {
+      d = hit->second;
+      ctx->vec_cache.erase(hit);
+      ctx->vec_cache_bytes -= (int64_t) sizeof(double) * cap;
+    } else {
+      cudaError_t e = cudaMalloc(&d, sizeof(double) * cap);
+      if (e == cudaErrorMemoryAllocation && !ctx->vec_cache.empty()) {
+        (void) cudaGetLastError();
+        vec_cache_release(ctx); // give the cached blocks back and try once more
+        e = cudaMalloc(&d, sizeof(double) * cap);
+      }
+      SB_CUDA(e);
+      ctx->vec_cap[d] = cap;
+    }
     SB_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * cap, ctx->stream));
     *out = d;
     return SB_OK;
@@ -109,11 +149,29 @@ int vec_alloc(sb_ctx* ctx, size_t n, double** out) {
 
 int vec_free(sb_ctx* ctx, double* d) {
   if (d == nullptr) return SB_OK;
-  SB_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ctx->comm.mode < 0) {
+    auto it = ctx->vec_cap.find(d);
+    if (it == ctx->vec_cap.end()) {
+      set_error("sb_vec_free: pointer was not allocated by sb_vec_alloc on this context (or was freed twice)");
+      return SB_ERR_INVALID;
+    }
+    const int64_t bytes = (int64_t) sizeof(double) * it->second;
+    for (auto range = ctx->vec_cache.equal_range(it->second); range.first != range.second; ++range.first)
+      if (range.first->second == d) {
+        set_error("sb_vec_free: vector freed twice");
+        return SB_ERR_INVALID;
+      }
+    if (ctx->vec_cache_bytes + bytes <= vec_cache_limit(ctx)) {
+      ctx->vec_cache.emplace(it->second, d); // kept for the next sb_vec_alloc of this size (stream-ordered reuse)
+      ctx->vec_cache_bytes += bytes;
+      return SB_OK;
+    }
+    ctx->vec_cap.erase(it);
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
     SB_CUDA(cudaFree(d));
     return SB_OK;
   }
+  SB_CUDA(cudaStreamSynchronize(ctx->stream));
   const unsigned char* p = reinterpret_cast<unsigned char*>(d);
   if (p < ctx->slab + kCtrlBytes || p >= ctx->slab + ctx->slab_bytes) {
     set_error("sb_vec_free: pointer does not belong to this context's vector pool");
@@ -202,6 +260,7 @@ int sb_comm_prepare(sb_ctx* ctx, int rank, int world, int mode, int64_t vec_capa
   }
   SB_REQUIRE(ctx->work.empty(), "prepare the communicator before the first solve on this context");
   SB_CUDA(cudaSetDevice(ctx->device));
+  vec_cache_release(ctx); // from here on vectors come from the symmetric slab
   const int64_t cap = pad_up(vec_capacity);
   const size_t bytes = kCtrlBytes + sizeof(double) * (size_t) cap * (size_t) n_vectors;
   SB_CUDA(cudaMalloc(&ctx->slab, bytes));

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/stormb200.h"
@@ -118,6 +119,13 @@ struct sb_ctx {
   size_t gmres_scal_cap = 0;
   double** d_gmres_ptrs = nullptr;
   double* h_gmres = nullptr;
+  // single-GPU vector storage (sb_comm.cu: vec_alloc / vec_free): freed blocks are kept for reuse, because the
+  // reference's solvers allocate their workspaces inside every solve() (SolverCg.hpp:57-59, SolverGmres.hpp: m + 1
+  // basis vectors) and cudaMalloc + cudaFree of 4 GB costs ~0.4 s per solve at 10 M cells. Reuse is ordered by the
+  // context's stream (the zero-fill of the next owner is enqueued behind every kernel of the previous one).
+  std::unordered_map<double*, int64_t> vec_cap;            // live + cached blocks -> capacity in doubles
+  std::unordered_multimap<int64_t, double*> vec_cache;     // capacity -> cached block
+  int64_t vec_cache_bytes = 0, vec_cache_limit = -1;       // limit < 0: not initialised yet
   // multi-GPU (sb_comm.cu); comm.mode < 0: single GPU
   sb::CommDev comm;
   unsigned char* slab = nullptr;
@@ -158,5 +166,6 @@ int ensure_red_scratch(sb_ctx* ctx, int64_t n);
 // vector storage: pool block in multi-GPU mode, cudaMalloc otherwise (zero-filled either way)
 int vec_alloc(sb_ctx* ctx, size_t n, double** out);
 int vec_free(sb_ctx* ctx, double* d);
+void vec_cache_release(sb_ctx* ctx); // cudaFree every cached block (context teardown, out-of-memory retry)
 int comm_teardown(sb_ctx* ctx);
 } // namespace sb

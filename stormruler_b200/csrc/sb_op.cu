@@ -147,7 +147,13 @@ template<class T>
 int upload(sb_ctx* ctx, const std::vector<T>& h, void** d_out, int64_t& bytes) {
   *d_out = nullptr;
   if (h.empty()) return SB_OK;
-  SB_CUDA(cudaMalloc(d_out, sizeof(T) * h.size()));
+  cudaError_t e = cudaMalloc(d_out, sizeof(T) * h.size());
+  if (e == cudaErrorMemoryAllocation) {
+    (void) cudaGetLastError();
+    vec_cache_release(ctx); // cached vector blocks (sb_vec_free keeps them for reuse) give way to the operator
+    e = cudaMalloc(d_out, sizeof(T) * h.size());
+  }
+  SB_CUDA(e);
   SB_CUDA(cudaMemcpyAsync(*d_out, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
   bytes += (int64_t) (sizeof(T) * h.size());
   return SB_OK;

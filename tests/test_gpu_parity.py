@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import stormruler_b200 as sb
-from conftest import load_golden, rhs
+from conftest import golden_mesh, load_golden, rhs
 from oracle import orc
 
 pytestmark = pytest.mark.gpu
@@ -278,3 +278,40 @@ def test_solve_host_roundtrip(ctx, square_nb):
     # the solution actually solves the system: ||b - A x|| / ||b|| at the reference's tolerance
     r = b - cpu.apply(x)
     assert np.linalg.norm(r) / np.linalg.norm(b) < 10 * RTOL
+
+
+def test_vector_blocks_are_recycled_zero_filled(ctx):
+    """sb_vec_free keeps blocks for the next sb_vec_alloc of the same size (the reference's solvers allocate their
+    workspaces inside every solve()): a recycled block comes back zero-filled (Field::assign semantics,
+    Feathers/Field.hpp:82-84), reuse is ordered behind the kernels of its previous owner, a second free of the same
+    pointer is an error instead of a corrupted heap."""
+    import ctypes as C
+    n = 300_000
+    a = ctx.vector(np.full(n, 7.0))
+    b = ctx.zeros(n)
+    (sb.expr.v(a) + 1.0 * sb.expr.v(a)).assign_to(b)          # a kernel still reading `a` may be in flight ...
+    ptr_a = a.ptr.value
+    del a                                                       # ... when the block goes back to the cache
+    c = ctx.zeros(n)                                            # same size: the cached block, zero-filled on the stream
+    assert c.ptr.value == ptr_a
+    assert np.array_equal(c.numpy(), np.zeros(n)) and np.array_equal(b.numpy(), np.full(n, 14.0))
+    d = ctx.zeros(n + 5000)                                     # another capacity: a fresh block
+    assert d.ptr.value != ptr_a
+    p = C.c_void_p()
+    assert ctx.lib.sb_vec_alloc(ctx.handle, 1000, C.byref(p)) == 0
+    assert ctx.lib.sb_vec_free(ctx.handle, p) == 0
+    assert ctx.lib.sb_vec_free(ctx.handle, p) < 0               # double free
+    assert ctx.lib.sb_vec_free(ctx.handle, C.c_void_p(p.value + 8)) < 0   # not a vector of this context
+    # solver workspaces go through the same path: repeated generic solves stay bit-identical
+    from stormruler_b200 import dropin
+    if dropin.available():
+        mesh = golden_mesh("square_nb")
+        _, gpu = make_ops(ctx, mesh, "helmholtz", sb.FORM_FAITHFUL)
+        bh = rhs(mesh.n_cells)
+        runs = []
+        for _ in range(3):
+            x = ctx.zeros(mesh.n_cells)
+            r = dropin.solve("idrs", gpu, x, ctx.vector(bh), num_iterations=40, abs_tol=0.0, rel_tol=0.0)
+            runs.append((r.hist.copy(), x.numpy()))
+        for h, xx in runs[1:]:
+            assert np.array_equal(h, runs[0][0]) and np.array_equal(xx, runs[0][1])
