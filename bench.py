@@ -55,7 +55,9 @@ def build_problem(args):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms. Started before the operator upload (nvidia-smi needs
+    about a second before its first line) and stopped after the end-to-end leg, so the samples cover the timed
+    regions; `sm_mhz` is the median over the samples taken under load (clock above 30 % of max)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -66,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -97,7 +99,7 @@ class ClockSampler:
                 pass
         busy = [v for v in sm if sm_max and v > 0.3 * sm_max] or sm
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": sm_max,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(busy) if sm_max else 0}
 
 
 def peaks():
@@ -190,6 +192,7 @@ def run_own_arm(args):
         from stormruler_b200 import multigpu
         return multigpu.bench_main(args, build_problem, workload_config, peaks, ClockSampler)
     mesh, x_star = build_problem(args)
+    sampler = ClockSampler(local_rank).start()
     ctx = sb.Context(local_rank)
     t0 = time.time()
     op = sb.FvmOperator(ctx, mesh, prefill=0, dt=-1.0, form=sb.FORM_COEF, dirichlet=True)
@@ -210,7 +213,6 @@ def run_own_arm(args):
         assert s.iteration == iters, (s.iteration, iters)
         return s, x
 
-    sampler = ClockSampler(local_rank).start()
     solve(max(args.warmup, 3), use_graph=True)                       # warm-up (untimed)
     launches0 = ctx.launch_count
     s, x = solve(args.steps, use_graph=True)                         # timed: exactly K iterations
@@ -219,7 +221,6 @@ def run_own_arm(args):
     value = args.steps / (rep_ms * 1e-3)
     # per-kernel breakdown of the same K iterations (events around every launch, no graph)
     sp, _ = solve(args.steps, profile=True)
-    clocks = sampler.stop()
     kms = _kernel_ms(sp)
     err = np.linalg.norm(x.numpy() - x_star) / np.linalg.norm(x_star)
 
@@ -254,6 +255,7 @@ def run_own_arm(args):
     e2e_s = time.perf_counter() - t
     assert rep.iterations == args.steps
     e2e_value = args.steps / e2e_s
+    clocks = sampler.stop()
 
     # ---- CPU baseline beside it (bounded sample of the same workload) ----
     cpu = None

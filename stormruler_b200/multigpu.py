@@ -195,6 +195,7 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
     part = partition_mesh(mesh, world, method)
     loc = part.local(rank)
     pinfo = part.info
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None   # early: nvidia-smi needs ~1 s to its first line
     ctx = DistContext(local_rank, rank, world, pinfo.vec_capacity, n_vectors=12, mode=mode)
     op = DistOperator(ctx, loc, prefill=0, dt=-1.0, form=FORM_COEF, dirichlet=True)
     n = loc.n_owned
@@ -216,7 +217,6 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
         assert s.iteration == iters, (s.iteration, iters)
         return s, x
 
-    sampler = ClockSampler(local_rank).start() if rank == 0 else None
     solve(max(args.warmup, 3), use_graph=True)
     s, x = solve(args.steps, use_graph=True)
     iter_ms = max_over_ranks(s.iter_ms)
@@ -224,7 +224,6 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
     value = args.steps / (iter_ms * 1e-3)
     sp, _ = solve(args.steps, profile=True)
     kms = [max_over_ranks(v) for v in sp.kernel_ms]
-    clocks = sampler.stop() if sampler else None
     xg = gather_global(loc, x.numpy(), mesh.n_cells)
     err = float(np.linalg.norm(xg - x_star) / np.linalg.norm(x_star))
 
@@ -241,6 +240,7 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
     dist.barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t)
     assert rep.iterations == args.steps
+    clocks = sampler.stop() if sampler else None
 
     alg_apply = int(sum_over_ranks(op.info.algorithmic_bytes_per_apply))
     n_glob = mesh.n_cells
