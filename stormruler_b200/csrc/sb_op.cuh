@@ -17,6 +17,7 @@
 
 #include "sb_kernels.cuh"
 
+#include <atomic>
 #include <cstdlib>
 
 namespace sb {
@@ -517,10 +518,12 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
   {                                                                                                             \
     auto kern = apply_kernel_tma<W, ND, RESID, Epi>;                                                            \
     constexpr int smem = StageLayout<W>::cta_bytes;                                                \
-    static bool configured = false;                                                                             \
-    if (!configured) {                                                                                          \
+    /* the attribute is per device: a process may hold contexts on several GPUs (one host thread each) */         \
+    static std::atomic<uint64_t> configured{0};                                                                 \
+    const uint64_t bit = 1ull << (ctx->device & 63);                                                            \
+    if (!(configured.load(std::memory_order_acquire) & bit)) {                                                  \
       SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
-      configured = true;                                                                                        \
+      configured.fetch_or(bit, std::memory_order_release);                                                      \
     }                                                                                                           \
     SB_CUDA(launch_kernel(ctx, kern, grid, kThreads, smem, d, x, y, epi, red, ad, done));                       \
   }

@@ -315,3 +315,51 @@ def test_vector_blocks_are_recycled_zero_filled(ctx):
             runs.append((r.hist.copy(), x.numpy()))
         for h, xx in runs[1:]:
             assert np.array_equal(h, runs[0][0]) and np.array_equal(xx, runs[0][1])
+
+
+def _chain_mesh(n, seed, isolated=()):
+    """A 1-D chain of n cells (cell i -- i+1), optionally with isolated cells (no faces at all), random geometry."""
+    rng = np.random.default_rng(seed)
+    skip = set(isolated)
+    pairs = [(i, i + 1) for i in range(n - 1) if i not in skip and i + 1 not in skip]
+    fc = np.array(pairs, np.int32).reshape(-1, 2)
+    F = fc.shape[0]
+    bc = np.array([c for c in (0, n - 1) if c not in skip], np.int32)
+    return orc.FaceMesh(n, fc, rng.uniform(0.5, 1.5, F), rng.uniform(0.5, 1.5, F), rng.uniform(0.5, 1.5, n), bc,
+                        rng.uniform(0.5, 1.5, len(bc)), rng.uniform(0.5, 1.5, len(bc)))
+
+
+@pytest.mark.parametrize("n,isolated", [(1, (0,)), (2, ()), (3, (1,)), (63, ()), (2047, ()), (2048, (5, 2047)),
+                                         (2049, (2048,)), (4097, (0, 4096))])
+def test_degenerate_and_ragged_meshes_bit_exact(ctx, n, isolated):
+    """Edge cases of the row layout: a single cell without faces, isolated cells (empty rows), sizes around the
+    2048-row tile boundary (the padding rows must neither be read as neighbours nor leak into the reductions)."""
+    fm = _chain_mesh(n, seed=n, isolated=isolated)
+    cpu = orc.FaceOp(fm, prefill=1, dt=-0.05, dirichlet=True)
+    x = np.random.default_rng(n + 1).standard_normal(n)
+    y = ctx.zeros(n)
+    for form in (sb.FORM_FAITHFUL, sb.FORM_COEF):
+        gpu = sb.FvmOperator(ctx, fm, prefill=1, dt=-0.05, form=form, dirichlet=True)
+        gpu.mul(y, ctx.vector(x))
+        want = cpu.apply(x) if form == sb.FORM_FAITHFUL else cpu.apply_rows_coef(x)
+        assert np.array_equal(y.numpy(), want)
+    b = rhs(n)
+    for name, Solver in (("cg", sb.CgSolver), ("bicgstab", sb.BiCgStabSolver)):
+        gpu = sb.FvmOperator(ctx, fm, prefill=1, dt=-0.05, form=sb.FORM_FAITHFUL, dirichlet=True)
+        want = orc.solve(name, cpu, b, num_iterations=30, abs_tol=0.0, rel_tol=1e-12, mode=orc.RED_TREE)
+        for use_graph in (False, True):
+            s = Solver(num_iterations=30, absolute_error_tolerance=0.0, relative_error_tolerance=1e-12, use_graph=use_graph)
+            xs = ctx.zeros(n)
+            conv = s.solve(xs, ctx.vector(b), gpu)
+            assert (conv, s.iteration) == (want.converged, want.iterations)
+            assert np.array_equal(s.history, want.hist) and np.array_equal(xs.numpy(), want.x)
+
+
+def test_empty_vectors(ctx):
+    """Zero-length vectors are legal everywhere the reference allows them (an empty Field): no launch, zero sums."""
+    a, b = ctx.zeros(0), ctx.zeros(0)
+    assert ctx.dot(a, b) == 0.0 and ctx.norm2(a) == 0.0
+    (sb.expr.v(a) + 2.0 * sb.expr.v(b)).assign_to(a)
+    a.fill(3.0)
+    a.copy_from(b)
+    assert a.numpy().shape == (0,)
