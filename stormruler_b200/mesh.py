@@ -250,6 +250,53 @@ class LocalView:
         return self.local_to_global[self.n_owned:]
 
 
+LOCAL_ARRAYS = (("local_to_global", np.int32), ("face_cell", np.int32), ("face_area", np.float64),
+                ("face_dist", np.float64), ("cell_vol", np.float64), ("bface_cell", np.int32),
+                ("bface_area", np.float64), ("bface_dist", np.float64), ("face_global", np.int64),
+                ("nbr_rank", np.int32), ("send_ptr", np.int64), ("recv_ptr", np.int64), ("send_idx", np.int32),
+                ("send_dst", np.int64), ("bface_global", np.int64))
+LOCAL_SCALARS = ("rank", "n_parts", "n_owned", "n_interior", "n_halo", "halo_base", "n_cells", "n_faces", "n_bfaces",
+                 "n_nbr")
+
+
+class LocalArrays:
+    """A rank's local mesh rebuilt from plain arrays (what LocalView exposes), e.g. after it travelled from the rank
+    that partitioned the global mesh (multigpu.scatter_mesh). Same attributes as LocalView, and a `struct`
+    (sb_local_mesh) pointing into the arrays it keeps alive."""
+
+    def __init__(self, scalars: dict, arrays: dict):
+        for k in LOCAL_SCALARS:
+            setattr(self, k, int(scalars[k]))
+        self._keep = {}
+        for k, dt in LOCAL_ARRAYS:
+            a = np.ascontiguousarray(arrays[k], dt)
+            self._keep[k] = a
+            setattr(self, k, a.reshape(-1, 2) if k == "face_cell" else a)
+        K = self._keep
+        ip, lp, dp = capi.i32p, capi.i64p, capi.f64p
+        ptr = lambda k, t: K[k].ctypes.data_as(t)  # noqa: E731
+        soa = capi.MeshSoa(self.n_cells, self.n_faces, ptr("face_cell", ip), ptr("face_area", dp), ptr("face_dist", dp),
+                           ptr("cell_vol", dp), self.n_bfaces, ptr("bface_cell", ip), ptr("bface_area", dp),
+                           ptr("bface_dist", dp))
+        self.struct = capi.LocalMesh(self.rank, self.n_parts, self.n_owned, self.n_interior, self.n_halo, self.halo_base,
+                                     ptr("local_to_global", ip), soa, ptr("face_global", lp), self.n_nbr,
+                                     ptr("nbr_rank", ip), ptr("send_ptr", lp), ptr("send_idx", ip), ptr("recv_ptr", lp),
+                                     ptr("send_dst", lp), ptr("bface_global", lp))
+
+    @staticmethod
+    def from_view(v) -> "LocalArrays":
+        return LocalArrays({k: getattr(v, k) for k in LOCAL_SCALARS},
+                           {k: np.array(getattr(v, k), dt, copy=True).reshape(-1) for k, dt in LOCAL_ARRAYS})
+
+    @property
+    def owned_global(self) -> np.ndarray:
+        return self.local_to_global[:self.n_owned]
+
+    @property
+    def halo_global(self) -> np.ndarray:
+        return self.local_to_global[self.n_owned:]
+
+
 class Partition:
     """sb_part: a split of the mesh's cell graph into n_parts (METIS k-way or RCM slabs)."""
 

@@ -19,7 +19,7 @@ import numpy as np
 
 from . import Context, DeviceVector, BiCgStabSolver, CgSolver, FORM_COEF, solve_host
 from . import capi
-from .mesh import LocalView, Mesh, Partition
+from .mesh import LOCAL_ARRAYS, LOCAL_SCALARS, LocalArrays, LocalView, Mesh, Partition
 
 
 def log(*a):
@@ -68,6 +68,75 @@ def partition_mesh(mesh: Mesh, world: int, method: int = capi.PART_METIS) -> Par
         del p0
     part = broadcast_array(part, (mesh.n_cells,), np.int32)
     return Partition(mesh, world, part=part)
+
+
+def scatter_mesh(build_mesh, world: int, method: int = capi.PART_METIS, cell_fields=None):
+    """Rank 0 builds the global mesh (`build_mesh()` -> Mesh), partitions it and ships every rank its local mesh;
+    the other ranks never hold the global mesh (at 49.8 M hexahedra the global build peaks at 29 GB per process:
+    with partition_mesh() every rank pays that, here only rank 0 does). `cell_fields(mesh)` -> {name: per-cell array}
+    is evaluated on rank 0 and each rank receives the rows of its owned cells. Returns (local, info, fields) with
+    `local` a LocalArrays (same surface as LocalView), `info` the partition summary as a dict (n_cells, edge_cut,
+    min_owned, max_owned, max_halo, vec_capacity), `fields` this rank's slices; rank 0 additionally finds the global
+    mesh under info["mesh"] (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank()
+    info_keys = ("n_cells", "edge_cut", "min_owned", "max_owned", "max_halo", "vec_capacity")
+
+    def to_tensor(a):
+        return torch.from_numpy(np.ascontiguousarray(a))
+
+    if rank == 0:
+        t = time.time()
+        mesh = build_mesh()
+        part = Partition(mesh, world, method)
+        fields_g = cell_fields(mesh) if cell_fields is not None else {}
+        info = {k: int(getattr(part.info, k)) for k in info_keys}
+        log(f"[multigpu] rank 0 built and partitioned the global mesh ({mesh.n_cells} cells, {world} parts) in "
+            f"{time.time() - t:.1f}s, edge cut {info['edge_cut']}, owned {info['min_owned']}..{info['max_owned']}")
+        mine, my_fields = None, {}
+        for r in range(world):
+            L = LocalArrays.from_view(part.local(r))
+            fl = {k: np.ascontiguousarray(np.asarray(v)[L.owned_global]) for k, v in fields_g.items()}
+            if r == 0:
+                mine, my_fields = L, fl
+                continue
+            header = {"scalars": {k: getattr(L, k) for k in LOCAL_SCALARS},
+                      "lengths": {k: int(L._keep[k].size) for k, _ in LOCAL_ARRAYS},
+                      "fields": {k: (list(v.shape), str(v.dtype)) for k, v in fl.items()}, "info": info}
+            blob = np.frombuffer(json.dumps(header).encode(), np.uint8).copy()   # CPU tensors: travel over gloo
+            dist.send(torch.tensor([blob.size], dtype=torch.int64), dst=r)
+            dist.send(torch.from_numpy(blob), dst=r)
+            for k, _ in LOCAL_ARRAYS:
+                if L._keep[k].size:
+                    dist.send(to_tensor(L._keep[k]), dst=r)
+            for k, v in fl.items():
+                if v.size:
+                    dist.send(to_tensor(v), dst=r)
+            del L, fl
+        del part
+        info["mesh"] = mesh
+        return mine, info, my_fields
+    size = torch.zeros(1, dtype=torch.int64)
+    dist.recv(size, src=0)
+    blob = torch.empty(int(size[0]), dtype=torch.uint8)
+    dist.recv(blob, src=0)
+    header = json.loads(blob.numpy().tobytes().decode())
+    arrays = {}
+    for k, dt in LOCAL_ARRAYS:
+        a = np.empty(header["lengths"][k], dt)
+        if a.size:
+            dist.recv(torch.from_numpy(a), src=0)
+        arrays[k] = a
+    fields = {}
+    for k, (shape, dtype) in header["fields"].items():
+        a = np.empty(tuple(shape), np.dtype(dtype))
+        if a.size:
+            dist.recv(torch.from_numpy(a), src=0)
+        fields[k] = a
+    info = dict(header["info"])
+    info["mesh"] = None
+    return LocalArrays(header["scalars"], arrays), info, fields
 
 
 class DistContext(Context):
@@ -154,7 +223,7 @@ class DistConvDiffOperator(DistOperator):
         self.info, self.n = info, int(info.n_cells)
 
 
-def gather_global(local: LocalView, x_local: np.ndarray, n_global: int) -> np.ndarray:
+def gather_global(local, x_local: np.ndarray, n_global: int) -> np.ndarray:
     """All ranks' owned values -> the global vector (on every rank). Test / reporting helper."""
     import torch
     import torch.distributed as dist

@@ -115,6 +115,33 @@ def run_cpu(dist, rank, world):
             tot = tot + float(sums[r][0])
         assert tot == want, (tot, want)
         assert mg.max_over_ranks(float(rank)) == world - 1 and mg.sum_over_ranks(1.0) == world
+        if kind in (CELL_HEX, "poly"):
+            # scatter mode: only rank 0 holds the global mesh; what arrives must be what part.local(rank) builds
+            from stormruler_b200.mesh import LOCAL_ARRAYS, LOCAL_SCALARS
+            the_mesh, the_part = mesh, np.array(part.part, np.int32, copy=True)
+
+            class FixedPartition(mg.Partition):   # rank 0 reuses the partition every rank already agreed on
+                def __init__(self, m, n_parts, method_):
+                    super().__init__(m, n_parts, part=the_part)
+
+            saved = mg.Partition
+            mg.Partition = FixedPartition
+            try:
+                sl, info, fields = mg.scatter_mesh(lambda: the_mesh, world, method,
+                                                   cell_fields=lambda m: {"vol": np.asarray(m.cell_vol), "ctr": m.cell_centers()})
+            finally:
+                mg.Partition = saved
+            for k in LOCAL_SCALARS:
+                assert getattr(sl, k) == getattr(loc, k), k
+            for k, _ in LOCAL_ARRAYS:
+                assert np.array_equal(np.asarray(getattr(sl, k)), np.asarray(getattr(loc, k))), k
+            assert info["vec_capacity"] == part.info.vec_capacity and info["edge_cut"] == part.info.edge_cut
+            assert (info["mesh"] is not None) == (rank == 0)
+            assert np.array_equal(fields["vol"], np.asarray(mesh.cell_vol)[loc.owned_global])
+            assert np.array_equal(fields["ctr"], mesh.cell_centers()[loc.owned_global])
+            # the struct built from the received arrays feeds the oracle like the library's own
+            yl2 = orc.FaceOp(face_mesh(sl), prefill=1, dt=-0.05, dirichlet=True).apply(xl)
+            assert np.array_equal(yl2[:sl.n_owned], yg[sl.owned_global])
     return 0
 
 
@@ -122,9 +149,14 @@ def run_gpu(dist, rank, world, mode_name):
     import stormruler_b200 as sb
     mode = capi.COMM_NCCL if mode_name == "nccl" else capi.COMM_P2P
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cases = ((CELL_TET, (14, 12, 10), capi.PART_METIS), (CELL_HEX, (24, 20, 18), capi.PART_SLAB))
+    cases = ((CELL_TET, (14, 12, 10), capi.PART_METIS), (CELL_HEX, (24, 20, 18), capi.PART_SLAB),
+             ("poly", (16,), capi.PART_METIS))
     for kind, dims, method in cases:
-        mesh = Mesh.box(kind, *dims, jitter=0.2, seed_jitter=42, shuffle=True, seed_shuffle=43)
+        if kind == "poly":   # 14-wide rows: the wide instantiation of the apply kernel with the fused halo exchange
+            mesh = PolyMesh.bcc(*dims, stretch=(1.0, 1.3, 0.7)).to_mesh()
+            mesh.permute_cells(np.random.default_rng(43).permutation(mesh.n_cells).astype(np.int32))
+        else:
+            mesh = Mesh.box(kind, *dims, jitter=0.2, seed_jitter=42, shuffle=True, seed_shuffle=43)
         mesh.renumber_rcm()
         part = mg.partition_mesh(mesh, world, method)
         loc = part.local(rank)
