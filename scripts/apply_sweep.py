@@ -9,6 +9,8 @@ input of every apply is freshly written, as inside a Krylov iteration) bracketed
 warm-up applies; GB/s = algorithmic bytes (24 N + 12 entries) / time. One JSON line per point and a
 summary object at the end. `poly` = truncated octahedra (the Voronoi cells of a body-centred cubic lattice: 14 faces
 per cell, F ~ 7 N, the 14-wide instantiation of the apply kernel), ingested as a face list and RCM-renumbered.
+`hexlat` = uniform hexahedra in lattice order, face list generated directly (no node matching, no shuffle / RCM): the
+cheap way to the 1e8 and 2e8-cell points (about 15 s of host time per 1e8 cells).
 """
 from __future__ import annotations
 
@@ -25,11 +27,11 @@ sys.path.insert(0, ROOT)
 
 import stormruler_b200 as sb  # noqa: E402
 from stormruler_b200 import capi  # noqa: E402
-from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh, PolyMesh  # noqa: E402
+from stormruler_b200.mesh import CELL_HEX, CELL_TET, HexLattice, Mesh, PolyMesh  # noqa: E402
 
 
 def axis_for(kind, cells):
-    per = {"tet": 6, "hex": 1, "poly": 2}[kind]
+    per = {"tet": 6, "hex": 1, "poly": 2, "hexlat": 1}[kind]
     return max(2, round((cells / per) ** (1.0 / 3.0)))
 
 
@@ -59,6 +61,10 @@ def main():
             if kind == "poly":
                 mesh = PolyMesh.bcc(n_axis, stretch=(1.0, 1.3, 0.7)).to_mesh()   # face-list handle (sb_mesh_from_faces)
                 mesh.renumber_rcm()
+            elif kind == "hexlat":
+                mesh = HexLattice(n_axis)                  # lattice order (bandwidth n^2), generated directly
+                if world > 1:
+                    mesh = Mesh.from_faces(mesh)
             else:
                 mesh = Mesh.box(CELL_TET if kind == "tet" else CELL_HEX, n_axis, jitter=0.2, seed_jitter=42, shuffle=True,
                                 seed_shuffle=43)

@@ -124,6 +124,58 @@ class Mesh:
         return int(self.lib.sb_mesh_bandwidth(self.handle))
 
 
+class HexLattice:
+    """Uniform hexahedral box [0,1]^3 of nx*ny*nz cells as a face list, generated directly (vectorised numpy, no
+    node matching): the integer layout is that of `Mesh.box(CELL_HEX, ..., jitter=0, shuffle=False)` bit for bit
+    (lattice cell order; faces created cell by cell in the local-face order of Hexahedron::faces, Shape.hpp:833-837:
+    z-, y-, x+, y+, x-, z+; the creating cell is the inner one), the geometry is analytic (areas hy*hz etc., centre
+    distances hx etc., mirror-ghost distance = the same spacing). For the sweep points where the node-based
+    generator is too slow or too large (1e8 cells and beyond). Duck-types the `mesh` argument of FvmOperator."""
+
+    def __init__(self, nx: int, ny: int | None = None, nz: int | None = None):
+        ny, nz = ny or nx, nz or nx
+        n = nx * ny * nz
+        assert n < 2 ** 31 - 4096
+        self.dims = (nx, ny, nz)
+        hx, hy, hz = 1.0 / nx, 1.0 / ny, 1.0 / nz
+        ids = np.arange(n, dtype=np.int32)
+        i, j, k = ids % nx, (ids // nx) % ny, ids // (nx * ny)
+        self.n_cells = n
+        self.cell_vol = np.full(n, hx * hy * hz)
+        # interior faces: cell c creates its x+, y+, z+ faces (local faces 2, 3, 5), in that order
+        has = np.stack([i < nx - 1, j < ny - 1, k < nz - 1], axis=1)            # [n, 3]
+        step = np.array([1, nx, nx * ny], np.int32)
+        nbr = ids[:, None] + step[None, :]
+        owner = np.broadcast_to(ids[:, None], has.shape)
+        axis = np.broadcast_to(np.arange(3, dtype=np.int8)[None, :], has.shape)
+        self.face_cell = np.stack([owner[has], nbr[has]], axis=1)
+        self.face_axis = axis[has]
+        area = np.array([hy * hz, hx * hz, hx * hy])
+        dist = np.array([hx, hy, hz])
+        self.face_area, self.face_dist = area[self.face_axis], dist[self.face_axis]
+        del has, nbr, owner, axis
+        # boundary faces per cell in local-face order z-, y-, x+, y+, x-, z+
+        bnd = np.stack([k == 0, j == 0, i == nx - 1, j == ny - 1, i == 0, k == nz - 1], axis=1)   # [n, 6]
+        baxis = np.array([2, 1, 0, 1, 0, 2], np.int8)
+        bowner = np.broadcast_to(ids[:, None], bnd.shape)
+        blf = np.broadcast_to(np.arange(6, dtype=np.int8)[None, :], bnd.shape)
+        self.bface_cell = bowner[bnd]
+        self.bface_lf = blf[bnd]
+        self.bface_area, self.bface_dist = area[baxis[self.bface_lf]], dist[baxis[self.bface_lf]]
+        self.n_faces, self.n_bfaces = int(self.face_cell.shape[0]), int(self.bface_cell.shape[0])
+
+    def cell_centers(self) -> np.ndarray:
+        nx, ny, nz = self.dims
+        ids = np.arange(self.n_cells)
+        i, j, k = ids % nx, (ids // nx) % ny, ids // (nx * ny)
+        return np.stack([(i + 0.5) / nx, (j + 0.5) / ny, (k + 0.5) / nz], axis=1)
+
+    @property
+    def bandwidth(self) -> int:
+        nx, ny, nz = self.dims
+        return nx * ny if nz > 1 else (nx if ny > 1 else (1 if nx > 1 else 0))
+
+
 class PolyMesh:
     """Synthetic polyhedral mesh for the dual-polyhedra leg of the apply sweep:
     the Voronoi tessellation of a body-centred cubic lattice, i.e. truncated octahedra with 14 faces

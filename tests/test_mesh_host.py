@@ -7,7 +7,7 @@ import pytest
 from oracle import mesh_oracle as mo
 from oracle import orc
 from stormruler_b200 import capi
-from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh, Partition, PolyMesh
+from stormruler_b200.mesh import CELL_HEX, CELL_TET, HexLattice, Mesh, Partition, PolyMesh
 
 KIND = {"tet": CELL_TET, "hex": CELL_HEX}
 SOA_KEYS = ("face_cell", "face_area", "face_dist", "cell_vol", "bface_cell", "bface_area", "bface_dist")
@@ -333,3 +333,27 @@ def test_face_list_mesh_rejects_bad_input():
     fn, bn = src.face_normals()
     with pytest.raises(capi.StormB200Error):
         Mesh.from_faces(src, None, fn, None)                            # one normal array without the other
+
+
+@pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 1), (1, 3, 2), (5, 4, 3), (7, 7, 7)])
+def test_hex_lattice_face_list_matches_the_node_based_generator(dims):
+    """The direct (numpy) generator used for the largest sweep points: integer layout bit-identical to the node-based
+    generator without jitter and shuffle (face order, inner/outer, boundary-face order), geometry within rounding
+    (analytic h products against triangle cross products)."""
+    a, b = HexLattice(*dims), Mesh.box(CELL_HEX, *dims, jitter=0.0, shuffle=False)
+    assert (a.n_cells, a.n_faces, a.n_bfaces) == (b.n_cells, b.n_faces, b.n_bfaces)
+    assert a.face_cell.dtype == np.int32 and np.array_equal(a.face_cell, b.face_cell)
+    assert a.bface_cell.dtype == np.int32 and np.array_equal(a.bface_cell, b.bface_cell)
+    for k in ("face_area", "face_dist", "cell_vol", "bface_area", "bface_dist"):
+        assert np.allclose(getattr(a, k), getattr(b, k), rtol=1e-13, atol=0.0), k
+    assert np.allclose(a.cell_centers(), b.cell_centers(), rtol=1e-13, atol=1e-15)
+    assert a.bandwidth == b.bandwidth
+    # and it feeds the oracle / the face-list handle like any other mesh
+    fm = orc.FaceMesh(a.n_cells, a.face_cell, a.face_area, a.face_dist, a.cell_vol, a.bface_cell, a.bface_area, a.bface_dist)
+    gm = orc.FaceMesh(b.n_cells, b.face_cell, b.face_area, b.face_dist, b.cell_vol, b.bface_cell, b.bface_area, b.bface_dist)
+    x = np.cos(0.3 * np.arange(a.n_cells))
+    ya = orc.FaceOp(fm, prefill=0, dt=-1.0, dirichlet=True).apply(x)
+    yb = orc.FaceOp(gm, prefill=0, dt=-1.0, dirichlet=True).apply(x)
+    assert np.abs(ya - yb).max() <= 1e-12 * max(np.abs(yb).max(), 1.0)
+    h = Mesh.from_faces(a, a.cell_centers())
+    assert np.array_equal(h.face_cell, a.face_cell) and h.bandwidth == a.bandwidth
