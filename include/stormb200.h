@@ -246,6 +246,8 @@ typedef struct sb_local_mesh {
   const int64_t* bface_global;    /* h_ [soa.n_bfaces] global boundary-face index of each local one */
 } sb_local_mesh;
 
+/* SB_PART_METIS: METIS_PartGraphKway over the cell graph; if it leaves a part empty (tiny or edge-less graphs) the
+ * contiguous slabs of SB_PART_SLAB are used instead, so every rank always owns cells. */
 SB_API int sb_part_create(const sb_mesh* mesh, int n_parts, int method, sb_part** out);
 SB_API int sb_part_from_array(const sb_mesh* mesh, int n_parts, const int32_t* h_part, sb_part** out);
 SB_API int sb_part_destroy(sb_part* part);

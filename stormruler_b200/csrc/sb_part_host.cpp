@@ -259,6 +259,13 @@ int sb_part_create(const sb_mesh* mesh, int n_parts, int method, sb_part** out) 
       return SB_ERR_INVALID;
     }
     for (int64_t i = 0; i < n; ++i) part[(size_t) i] = (int32_t) p64[(size_t) i];
+    // METIS may leave a part empty on very small or edge-less graphs: every rank needs cells, so fall back to
+    // contiguous slabs there (deterministic as well)
+    std::vector<int64_t> count((size_t) n_parts, 0);
+    for (int64_t i = 0; i < n; ++i) count[(size_t) part[(size_t) i]]++;
+    if (*std::min_element(count.begin(), count.end()) == 0)
+      for (int p = 0; p < n_parts; ++p)
+        for (int64_t i = n * p / n_parts; i < n * (p + 1) / n_parts; ++i) part[(size_t) i] = p;
   }
   return sb_part_from_array(mesh, n_parts, part.data(), out);
 }

@@ -357,3 +357,48 @@ def test_hex_lattice_face_list_matches_the_node_based_generator(dims):
     assert np.abs(ya - yb).max() <= 1e-12 * max(np.abs(yb).max(), 1.0)
     h = Mesh.from_faces(a, a.cell_centers())
     assert np.array_equal(h.face_cell, a.face_cell) and h.bandwidth == a.bandwidth
+
+
+def _tiny_face_list(n, pairs, bcells, seed=0):
+    rng = np.random.default_rng(seed)
+
+    class M:
+        pass
+    m = M()
+    m.n_cells = n
+    m.face_cell = np.array(pairs, np.int32).reshape(-1, 2)
+    F, B = m.face_cell.shape[0], len(bcells)
+    m.face_area, m.face_dist, m.cell_vol = rng.uniform(.5, 1.5, F), rng.uniform(.5, 1.5, F), rng.uniform(.5, 1.5, n)
+    m.bface_cell = np.array(bcells, np.int32)
+    m.bface_area, m.bface_dist = rng.uniform(.5, 1.5, B), rng.uniform(.5, 1.5, B)
+    return m
+
+
+def test_degenerate_graphs_disconnected_isolated_duplicate_faces():
+    """Host integer work on graphs a real mesh reader can produce by accident: several components, isolated cells,
+    no faces at all, two faces between the same pair of cells, as many parts as cells."""
+    src = _tiny_face_list(10, [(0, 1), (1, 2), (5, 6), (8, 9)], [0, 3, 3, 9])
+    h = Mesh.from_faces(src)
+    perm = h.renumber_rcm()
+    assert np.array_equal(perm, mo.rcm(10, src.face_cell)) and sorted(perm.tolist()) == list(range(10))
+    gd = as_dict(h)
+    for method in (capi.PART_SLAB, capi.PART_METIS):
+        for k in (1, 2, 3):
+            P = Partition(h, k, method)
+            assert np.bincount(P.part, minlength=k).min() > 0
+            for r in range(k):
+                L, want = P.local(r), mo.local_maps(gd, P.part, r, k)
+                for key in LOCAL_KEYS:
+                    assert np.array_equal(np.asarray(getattr(L, key)), want[key]), (method, k, r, key)
+    empty = Mesh.from_faces(_tiny_face_list(4, [], [0, 1, 2, 3]))
+    assert sorted(empty.renumber_rcm().tolist()) == [0, 1, 2, 3] and empty.bandwidth == 0
+    for method in (capi.PART_SLAB, capi.PART_METIS):
+        P = Partition(empty, 2, method)
+        assert np.bincount(P.part, minlength=2).min() > 0 and P.info.edge_cut == 0 and P.local(1).n_halo == 0
+    dup = Mesh.from_faces(_tiny_face_list(3, [(0, 1), (0, 1), (1, 2)], []))
+    dup.renumber_rcm()
+    P = Partition(dup, 2, capi.PART_METIS)          # METIS leaves a part empty here: the slab fallback takes over
+    assert np.bincount(P.part, minlength=2).min() > 0
+    assert sum(P.local(r).n_owned for r in range(2)) == 3
+    P = Partition(Mesh.from_faces(_tiny_face_list(3, [(0, 1), (1, 2)], [])), 3, capi.PART_SLAB)
+    assert P.part.tolist() == [0, 1, 2]
