@@ -402,3 +402,34 @@ def test_degenerate_graphs_disconnected_isolated_duplicate_faces():
     assert sum(P.local(r).n_owned for r in range(2)) == 3
     P = Partition(Mesh.from_faces(_tiny_face_list(3, [(0, 1), (1, 2)], [])), 3, capi.PART_SLAB)
     assert P.part.tolist() == [0, 1, 2]
+
+
+@pytest.mark.parametrize("seed", range(0, 60, 3))
+def test_random_face_lists_renumbering_and_partition_against_the_restatement(seed):
+    """Random multigraphs (duplicate faces, isolated cells, several components, random boundary faces): ingestion,
+    an arbitrary permutation, RCM and both partitioners against the numpy restatement, every array bit for bit."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 60))
+    pairs = [(int(a), int(b)) for a, b in rng.integers(0, n, (int(rng.integers(0, 4 * n)), 2)) if a != b]
+    src = _tiny_face_list(n, pairs, np.sort(rng.integers(0, n, int(rng.integers(0, 2 * n)))).tolist(), seed)
+    before = face_list_dict(src)
+    h = Mesh.from_faces(src)
+    assert_soa_equal(h, before)
+    perm = rng.permutation(n).astype(np.int32)
+    h.permute_cells(perm)
+    want = mo.permute_face_list(before, perm)
+    assert_soa_equal(h, want)
+    p2 = h.renumber_rcm()
+    assert np.array_equal(p2, mo.rcm(n, want["face_cell"]))
+    assert_soa_equal(h, mo.permute_face_list(before, perm[p2]))
+    gd = as_dict(h)
+    for method in (capi.PART_SLAB, capi.PART_METIS):
+        k = int(rng.integers(1, min(5, n) + 1))
+        P = Partition(h, k, method)
+        for r in range(k):
+            L, wl = P.local(r), mo.local_maps(gd, P.part, r, k)
+            for key in ("n_owned", "n_interior", "n_halo", "halo_base"):
+                assert getattr(L, key) == wl[key], (method, k, r, key)
+            for key in LOCAL_KEYS:
+                got = np.asarray(getattr(L, key))
+                assert got.shape == wl[key].shape and np.array_equal(got, wl[key]), (method, k, r, key)
