@@ -204,6 +204,13 @@ SB_API int sb_mesh_cell_centers(const sb_mesh* mesh, double* h_xyz /* [3*n_cells
  * oriented out of the domain; either may be NULL. Triangle: cross(v2-v1, v3-v1); quadrangle: cross of
  * the diagonals; normalised, flipped if it points against (outer centre - inner centre). */
 SB_API int sb_mesh_face_normals(const sb_mesh* mesh, double* h_fn, double* h_bn);
+/* Legacy-VTK (ASCII, unstructured grid) dump of the mesh and of n_fields per-cell scalar fields in the CURRENT cell
+ * order, in the file grammar of the playground's save_vtk (source_apps/playground/Playground.cpp:65-109: header
+ * lines, 16 significant digits, POINTS / CELLS / CELL_TYPES / CELL_DATA with one SCALARS block per field); 3-D
+ * points, cell types VTK_TETRA (10) / VTK_HEXAHEDRON (12). Node-based meshes only. Host side, no GPU needed:
+ * download the device vectors first (sb_vec_download). */
+SB_API int sb_mesh_write_vtk(const sb_mesh* mesh, const char* path, int n_fields, const char* const* names,
+                             const double* const* h_fields /* n_fields arrays of [n_cells] */);
 /* Bandwidth of the cell graph, max |inner - outer| over interior faces (renumbering quality). */
 SB_API int64_t sb_mesh_bandwidth(const sb_mesh* mesh);
 

@@ -42,6 +42,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--rel-tol", type=float, default=1e-8)
     ap.add_argument("--max-iterations", type=int, default=20000)
+    ap.add_argument("--vtk", default="", help="prefix: write <prefix>-<step, 5 digits>.vtk (pressure and exact pressure) "
+                                              "after every step, outside the timed region (rank 0)")
     args = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -105,6 +107,8 @@ def main():
             ex_full = p_star(centers, t_k)
             d = (full - full.mean()) - (ex_full - ex_full.mean())
             err = float(np.linalg.norm(d) / np.linalg.norm(ex_full - ex_full.mean()))
+            if args.vtk:   # the playground's output step (Playground.cpp:205-208: save_vtk after the step)
+                mesh.write_vtk(f"{args.vtk}-{k:05d}.vtk", {"p": full, "p_exact": ex_full})
         records.append({"step": k, "iterations": int(s.iteration), "converged": bool(conv), "seconds": dt_,
                         "solve_ms_device": float(s.solve_ms), "rel_residual": float(s.relative_error),
                         "rel_error_vs_p_star": err, "rhs_shift": float(shift)})

@@ -118,6 +118,7 @@ SIGNATURES = {
     "sb_mesh_get_soa": (C.c_int, [C.c_void_p, C.POINTER(MeshSoa)]),
     "sb_mesh_cell_centers": (C.c_int, [C.c_void_p, f64p]),
     "sb_mesh_face_normals": (C.c_int, [C.c_void_p, f64p, f64p]),
+    "sb_mesh_write_vtk": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(f64p)]),
     "sb_mesh_bandwidth": (C.c_int64, [C.c_void_p]),
     "sb_part_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, vpp]),
     "sb_part_from_array": (C.c_int, [C.c_void_p, C.c_int, i32p, vpp]),

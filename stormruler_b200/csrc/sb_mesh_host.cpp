@@ -17,6 +17,9 @@
 #include <memory>
 #include <numeric>
 #include <random>
+#include <fstream>
+#include <iomanip>
+#include <limits>
 #include <string>
 #include <thread>
 #include <vector>
@@ -767,6 +770,57 @@ int sb_mesh_face_normals(const sb_mesh* m, double* h_fn, double* h_bn) {
   SBM_REQUIRE(m != nullptr, "mesh is null");
   SBM_REQUIRE(m->kind != SB_CELL_FACELIST || !m->pair_normal.empty(), "this face-list mesh was created without normals");
   face_normals(*m, h_fn, h_bn);
+  return SB_OK;
+}
+
+// Legacy-VTK dump in the file grammar of the playground's save_vtk (Playground.cpp:65-109): same header lines, 16
+// significant digits (digits10 + 1), "POINTS n double", count-prefixed node lists under CELLS, one type per cell under
+// CELL_TYPES, one "SCALARS <name> double 1 / LOOKUP_TABLE default" block per field under CELL_DATA. The reference
+// writes 2-D triangles (z = 0, type 5); here the points are 3-D and the types are VTK_TETRA (10) / VTK_HEXAHEDRON (12),
+// whose node orders are those of Shape.hpp:559-606 / 803-818.
+int sb_mesh_write_vtk(const sb_mesh* m, const char* path, int n_fields, const char* const* names,
+                      const double* const* h_fields) {
+  SBM_REQUIRE(m != nullptr && path != nullptr && n_fields >= 0, "null argument");
+  SBM_REQUIRE(m->kind == SB_CELL_TET || m->kind == SB_CELL_HEX, "a face-list mesh has no nodes to write");
+  SBM_REQUIRE(n_fields == 0 || (names != nullptr && h_fields != nullptr), "null field arrays");
+  for (int f = 0; f < n_fields; ++f) SBM_REQUIRE(names[f] != nullptr && h_fields[f] != nullptr, "null field");
+  std::ofstream file(path);
+  if (!file) {
+    sb::set_error("cannot open '%s' for writing", path);
+    return SB_ERR_INVALID;
+  }
+  file << std::setprecision(std::numeric_limits<double>::digits10 + 1);
+  file << "# vtk DataFile Version 2.0" << '\n';
+  file << "# Generated by Feathers/StormRuler/Mesh2VTK" << '\n';
+  file << "ASCII" << '\n';
+  file << "DATASET UNSTRUCTURED_GRID" << '\n';
+  file << "POINTS " << m->n_nodes << " double" << '\n';
+  for (int64_t i = 0; i < m->n_nodes; ++i)
+    file << m->xyz[3 * (size_t) i] << " " << m->xyz[3 * (size_t) i + 1] << " " << m->xyz[3 * (size_t) i + 2] << '\n';
+  file << '\n';
+  file << "CELLS " << m->n_cells << " " << m->n_cells * (m->npc + 1) << '\n';
+  for (int64_t c = 0; c < m->n_cells; ++c) {
+    file << m->npc << " ";
+    for (int k = 0; k < m->npc; ++k) file << m->cells[(size_t) c * m->npc + k] << " ";
+    file << '\n';
+  }
+  file << '\n';
+  file << "CELL_TYPES " << m->n_cells << '\n';
+  const char* type = m->kind == SB_CELL_TET ? "10" : "12";
+  for (int64_t c = 0; c < m->n_cells; ++c) file << type << '\n';
+  file << '\n';
+  file << "CELL_DATA " << m->n_cells << '\n';
+  for (int f = 0; f < n_fields; ++f) {
+    file << "SCALARS " << names[f] << " double 1" << '\n';
+    file << "LOOKUP_TABLE default" << '\n';
+    for (int64_t c = 0; c < m->n_cells; ++c) file << h_fields[f][c] << '\n';
+  }
+  file << '\n';
+  file.close();
+  if (!file) {
+    sb::set_error("write to '%s' failed", path);
+    return SB_ERR_INVALID;
+  }
   return SB_OK;
 }
 

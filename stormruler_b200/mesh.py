@@ -123,6 +123,17 @@ class Mesh:
     def bandwidth(self) -> int:
         return int(self.lib.sb_mesh_bandwidth(self.handle))
 
+    def write_vtk(self, path: str, fields: dict | None = None):
+        """Legacy-VTK dump of the mesh and per-cell scalar fields (host arrays, current cell order), in the file
+        grammar of the playground's save_vtk (Playground.cpp:65-109)."""
+        fields = fields or {}
+        arrs = [np.ascontiguousarray(v, np.float64) for v in fields.values()]
+        for a in arrs:
+            assert a.shape == (self.n_cells,), "one value per cell"
+        names = (C.c_char_p * max(len(arrs), 1))(*[k.encode() for k in fields])
+        ptrs = (capi.f64p * max(len(arrs), 1))(*[a.ctypes.data_as(capi.f64p) for a in arrs])
+        capi.check(self.lib.sb_mesh_write_vtk(self.handle, str(path).encode(), len(arrs), names, ptrs))
+
 
 class HexLattice:
     """Uniform hexahedral box [0,1]^3 of nx*ny*nz cells as a face list, generated directly (vectorised numpy, no

@@ -433,3 +433,51 @@ def test_random_face_lists_renumbering_and_partition_against_the_restatement(see
             for key in LOCAL_KEYS:
                 got = np.asarray(getattr(L, key))
                 assert got.shape == wl[key].shape and np.array_equal(got, wl[key]), (method, k, r, key)
+
+
+@pytest.mark.parametrize("kind", ["tet", "hex"])
+def test_vtk_dump_follows_the_playground_grammar(tmp_path, kind):
+    """sb_mesh_write_vtk against the file grammar of the reference's save_vtk (Playground.cpp:65-109): literal header
+    lines, POINTS / CELLS / CELL_TYPES / CELL_DATA blocks, 16 significant digits, fields in the current cell order
+    (after a renumbering too)."""
+    mesh = Mesh.box(KIND[kind], 3, 2, 2, jitter=0.2, seed_jitter=5, shuffle=True, seed_shuffle=6)
+    mesh.renumber_rcm()
+    n = mesh.n_cells
+    c = mesh.cell_centers()
+    fields = {"c": np.sin(c[:, 0]) + 0.1 * np.arange(n), "third": np.full(n, 1.0 / 3.0)}
+    path = tmp_path / "out-00001.vtk"
+    mesh.write_vtk(str(path), fields)
+    lines = path.read_text().split("\n")
+    assert lines[:4] == ["# vtk DataFile Version 2.0", "# Generated by Feathers/StormRuler/Mesh2VTK", "ASCII",
+                         "DATASET UNSTRUCTURED_GRID"]
+    xyz, cells = mo.box_cells(kind, 3, 2, 2, jitter=0.2, seed_jitter=5, shuffle=True, seed_shuffle=6)
+    n_nodes, npc = xyz.shape[0], cells.shape[1]
+    assert lines[4] == f"POINTS {n_nodes} double"
+    pts = np.array([[float(v) for v in ln.split()] for ln in lines[5:5 + n_nodes]])
+    assert np.allclose(pts, xyz, rtol=1e-15, atol=0.0)
+    k = 5 + n_nodes
+    assert lines[k] == "" and lines[k + 1] == f"CELLS {n} {n * (npc + 1)}"
+    rows = [ln.split() for ln in lines[k + 2:k + 2 + n]]
+    assert all(r[0] == str(npc) and len(r) == npc + 1 for r in rows)
+    got_cells = np.array([[int(v) for v in r[1:]] for r in rows])
+    # cell k of the dump is the k-th cell of the renumbered mesh: its centre is the mean of its nodes (tets) or close
+    ctr = xyz[got_cells].mean(axis=1)
+    assert np.abs(ctr - c).max() < (1e-12 if kind == "tet" else 0.05)
+    assert sorted(map(tuple, np.sort(got_cells, axis=1).tolist())) == sorted(map(tuple, np.sort(cells, axis=1).tolist()))
+    k += 2 + n
+    assert lines[k] == "" and lines[k + 1] == f"CELL_TYPES {n}"
+    assert set(lines[k + 2:k + 2 + n]) == {"10" if kind == "tet" else "12"}
+    k += 2 + n
+    assert lines[k] == "" and lines[k + 1] == f"CELL_DATA {n}"
+    k += 2
+    for name, values in fields.items():
+        assert lines[k] == f"SCALARS {name} double 1" and lines[k + 1] == "LOOKUP_TABLE default"
+        got = np.array([float(v) for v in lines[k + 2:k + 2 + n]])
+        assert np.allclose(got, values, rtol=1e-15, atol=0.0)
+        k += 2 + n
+    assert lines[k] == ""
+    assert "0.3333333333333333" in lines            # digits10 + 1 = 16 significant digits, like the reference
+    with pytest.raises(capi.StormB200Error):
+        Mesh.from_faces(PolyMesh.bcc(2)).write_vtk(str(tmp_path / "x.vtk"))     # no nodes
+    with pytest.raises(capi.StormB200Error):
+        mesh.write_vtk(str(tmp_path / "no_such_dir" / "x.vtk"))
