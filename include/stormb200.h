@@ -189,6 +189,18 @@ SB_API int sb_mesh_from_faces(const sb_mesh_soa* h_soa, const double* h_cell_ctr
  * list follows this library's own creation-order convention, like every other 3-D mesh here. Node indices
  * may start at 0 or 1 (TetGen -z); attributes and labels are skipped. */
 SB_API int sb_mesh_read_tetgen(const char* path_prefix, sb_mesh** out);
+/* 2-D ingestion of Triangle's `<prefix>.node`, `<prefix>.edge`, `<prefix>.ele` -- the reader the reference actually
+ * has (read_mesh_from_tetgen on UnstructuredMesh<2,2>, Mallard/IoTetgen.hpp:44-235; playground: Playground.cpp:248-255)
+ * and the files its own tests ship (tests/_data/mesh). Restates the reference's construction: faces numbered in
+ * .edge file order (unlisted edges appended with label 0), first inserted cell = inner cell
+ * (MeshUnstructured.hpp:350-425,509-554), faces stable-sorted by label with label 0 = interior first (:464-500),
+ * geometry operation by operation as Mallard/Shape.hpp computes it. The result is a face-list handle
+ * (SB_CELL_FACELIST, with cell centres and normals, z = 0) whose SoA is bit-identical to what the reference's mesh
+ * classes export; boundary faces are ordered by label. */
+SB_API int sb_mesh_read_tetgen_2d(const char* path_prefix, sb_mesh** out);
+/* Labels of the boundary faces in their current order (the reference's face labels, Mesh.hpp:426-429; 1 for every
+ * boundary face of a mesh that was not read from labelled files). h_labels [n_bfaces]. */
+SB_API int sb_mesh_bface_labels(const sb_mesh* mesh, int32_t* h_labels);
 SB_API int sb_mesh_destroy(sb_mesh* mesh);
 /* Reverse Cuthill-McKee renumbering of the cells over the face adjacency graph; faces are rebuilt
  * for the new cell order. h_perm (may be NULL) receives perm[new] = old (Utils/Permutations.hpp:77-103). */

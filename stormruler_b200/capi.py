@@ -112,6 +112,8 @@ SIGNATURES = {
     "sb_mesh_from_cells": (C.c_int, [C.c_int, C.c_int64, f64p, C.c_int64, i32p, vpp]),
     "sb_mesh_from_faces": (C.c_int, [C.POINTER(MeshSoa), f64p, f64p, f64p, vpp]),
     "sb_mesh_read_tetgen": (C.c_int, [C.c_char_p, vpp]),
+    "sb_mesh_read_tetgen_2d": (C.c_int, [C.c_char_p, vpp]),
+    "sb_mesh_bface_labels": (C.c_int, [C.c_void_p, i32p]),
     "sb_mesh_destroy": (C.c_int, [C.c_void_p]),
     "sb_mesh_renumber_rcm": (C.c_int, [C.c_void_p, i32p]),
     "sb_mesh_permute_cells": (C.c_int, [C.c_void_p, i32p]),

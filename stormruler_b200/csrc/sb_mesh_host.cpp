@@ -22,6 +22,7 @@
 #include <limits>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/stormb200.h"
@@ -130,6 +131,7 @@ struct sb_mesh {
   // indexed like `pairs`. pair_normal (optional, 3 per face) is oriented from pair_first to the other side.
   std::vector<double> pair_area, pair_dist, pair_normal;
   std::vector<int32_t> pair_first; // the cell the stored normal points away from, as an index into cell[] (0 | 1)
+  std::vector<int32_t> pair_label; // optional: the reference's face labels (0 = interior), sb_mesh_read_tetgen_2d
   bool has_centers = false;
 
   V3 node(int32_t i) const { return {xyz[3 * (size_t) i], xyz[3 * (size_t) i + 1], xyz[3 * (size_t) i + 2]}; }
@@ -728,6 +730,193 @@ int sb_mesh_read_tetgen(const char* path_prefix, sb_mesh** out) {
     }
   }
   return sb_mesh_from_cells(SB_CELL_TET, n_nodes, xyz.data(), n_cells, cells.data(), out);
+}
+
+// 2-D ingestion (Triangle's .node / .edge / .ele, the files the reference's own tests use): restates what
+// read_mesh_from_tetgen (Mallard/IoTetgen.hpp:44-235) + UnstructuredMesh::insert (MeshUnstructured.hpp:350-425) +
+// _update_face_orientation (:509-554) + assign_labels (:464-500) produce for a 2-D mesh:
+//   * faces (edges) are numbered in .edge file order; an edge of a cell that the file does not list is appended
+//     behind them with label 0 (find_or_insert);
+//   * the first cell inserted next to a face is its inner cell, the second one its outer cell;
+//   * assign_labels stable-sorts the faces by label: label 0 (interior) first in file order, then each boundary
+//     label in file order;
+//   * geometry, operation by operation (Shape.hpp:155-167,243-247,310-322; MatrixAlgorithms.hpp:262-270,303-305):
+//     edge length = sqrt((0 + dx*dx) + dy*dy), centres = node sums / node count, triangle area =
+//     0.5*|d0x*d1y - d0y*d1x|, centre distance as Playground.cpp:126, mirror-ghost distance 2*|x_f - x_i|.
+// The result is a face-list handle whose SoA is bit-identical to the reference mesh classes' export
+// (tests/golden/mesh_*.npz, made by oracle/_ref/ref_mesh_tool).
+int sb_mesh_read_tetgen_2d(const char* path_prefix, sb_mesh** out) {
+  SBM_REQUIRE(path_prefix != nullptr && out != nullptr, "null argument");
+  *out = nullptr;
+  const std::string prefix{path_prefix};
+  TokenFile nf, gf, ef;
+  if (!nf.open(prefix + ".node")) {
+    sb::set_error("cannot open the node file '%s.node'", path_prefix);
+    return SB_ERR_INVALID;
+  }
+  if (!gf.open(prefix + ".edge")) {
+    sb::set_error("cannot open the edge file '%s.edge'", path_prefix);
+    return SB_ERR_INVALID;
+  }
+  if (!ef.open(prefix + ".ele")) {
+    sb::set_error("cannot open the cell file '%s.ele'", path_prefix);
+    return SB_ERR_INVALID;
+  }
+  // nodes
+  int64_t n_nodes = 0, dim = 0, n_attr = 0, has_labels = 0;
+  SBM_REQUIRE(nf.next_int(n_nodes) && nf.next_int(dim) && nf.next_int(n_attr) && nf.next_int(has_labels),
+              "cannot read the node file header");
+  SBM_REQUIRE(dim == 2, "unexpected number of dimensions in the node file header (expected 2)");
+  SBM_REQUIRE(n_nodes > 0 && n_nodes < (int64_t) INT32_MAX && n_attr >= 0, "bad node file header");
+  std::vector<double> xy(2 * (size_t) n_nodes);
+  int64_t first_index = 0;
+  for (int64_t k = 0; k < n_nodes; ++k) {
+    int64_t idx = 0;
+    double skipped = 0.0;
+    bool ok = nf.next_int(idx) && nf.next_double(xy[2 * (size_t) k]) && nf.next_double(xy[2 * (size_t) k + 1]);
+    for (int64_t a = 0; ok && a < n_attr + (has_labels ? 1 : 0); ++a) ok = nf.next_double(skipped);
+    if (!ok) {
+      sb::set_error("cannot read node # %lld from '%s.node'", (long long) k, path_prefix);
+      return SB_ERR_INVALID;
+    }
+    if (k == 0) first_index = idx;
+    SBM_REQUIRE(idx == first_index + k, "node indices must be consecutive");
+  }
+  SBM_REQUIRE(first_index == 0 || first_index == 1, "node numbering must start at 0 or 1");
+  // edges (= faces), in file order, with labels
+  int64_t n_edges = 0, edges_have_labels = 0;
+  SBM_REQUIRE(gf.next_int(n_edges) && gf.next_int(edges_have_labels), "cannot read the edge file header");
+  SBM_REQUIRE(n_edges >= 0 && n_edges < (int64_t) INT32_MAX, "bad edge count");
+  struct Face {
+    int32_t n1, n2;      // node order as stored (reversed when the first cell sees the edge the other way round)
+    int32_t cell[2];
+    int32_t label;
+    int64_t file_pos;    // index before the label sort
+  };
+  std::vector<Face> faces;
+  faces.reserve((size_t) n_edges);
+  std::unordered_map<uint64_t, int32_t> by_nodes;
+  by_nodes.reserve((size_t) n_edges * 2);
+  auto key = [](int32_t a, int32_t b) {
+    const uint32_t lo = (uint32_t) std::min(a, b), hi = (uint32_t) std::max(a, b);
+    return ((uint64_t) hi << 32) | lo;
+  };
+  for (int64_t e = 0; e < n_edges; ++e) {
+    int64_t idx = 0, a = 0, b = 0, label = 0;
+    bool ok = gf.next_int(idx) && gf.next_int(a) && gf.next_int(b);
+    if (ok && edges_have_labels) ok = gf.next_int(label);
+    if (!ok) {
+      sb::set_error("cannot read edge # %lld from '%s.edge'", (long long) e, path_prefix);
+      return SB_ERR_INVALID;
+    }
+    a -= first_index, b -= first_index;
+    SBM_REQUIRE(a >= 0 && a < n_nodes && b >= 0 && b < n_nodes && a != b, "edge node index out of range");
+    SBM_REQUIRE(label >= 0 && label < (1 << 20), "edge label out of range");
+    const bool fresh = by_nodes.emplace(key((int32_t) a, (int32_t) b), (int32_t) faces.size()).second;
+    SBM_REQUIRE(fresh, "the edge file lists an edge twice");
+    faces.push_back(Face{(int32_t) a, (int32_t) b, {-1, -1}, (int32_t) label, e});
+  }
+  // cells, in file order: connect to the faces, fix inner / outer
+  int64_t n_cells = 0, npc = 0, has_attr = 0;
+  SBM_REQUIRE(ef.next_int(n_cells) && ef.next_int(npc) && ef.next_int(has_attr), "cannot read the cell file header");
+  SBM_REQUIRE(npc == 3, "unexpected number of nodes per cell in the cell file header (expected 3)");
+  SBM_REQUIRE(n_cells > 0 && n_cells < (int64_t) 250'000'000, "bad cell count");
+  std::vector<int32_t> tri(3 * (size_t) n_cells);
+  for (int64_t c = 0; c < n_cells; ++c) {
+    int64_t idx = 0, nd[3] = {0, 0, 0};
+    double skipped = 0.0;
+    bool ok = ef.next_int(idx) && ef.next_int(nd[0]) && ef.next_int(nd[1]) && ef.next_int(nd[2]);
+    for (int64_t a = 0; ok && a < has_attr; ++a) ok = ef.next_double(skipped);
+    if (!ok) {
+      sb::set_error("cannot read cell # %lld from '%s.ele'", (long long) c, path_prefix);
+      return SB_ERR_INVALID;
+    }
+    for (int q = 0; q < 3; ++q) {
+      const int64_t v = nd[q] - first_index;
+      SBM_REQUIRE(v >= 0 && v < n_nodes, "cell node index out of range");
+      tri[3 * (size_t) c + q] = (int32_t) v;
+    }
+    // Triangle::edges (Shape.hpp:303-305): (n1,n2), (n2,n3), (n3,n1)
+    for (int q = 0; q < 3; ++q) {
+      const int32_t a = tri[3 * (size_t) c + q], b = tri[3 * (size_t) c + (q + 1) % 3];
+      SBM_REQUIRE(a != b, "degenerate triangle");
+      auto it = by_nodes.find(key(a, b));
+      if (it == by_nodes.end()) { // find_or_insert: an edge the file does not list, label 0
+        it = by_nodes.emplace(key(a, b), (int32_t) faces.size()).first;
+        faces.push_back(Face{a, b, {-1, -1}, 0, (int64_t) faces.size()});
+      }
+      Face& f = faces[(size_t) it->second];
+      if (f.cell[0] < 0) {
+        f.cell[0] = (int32_t) c;
+        if (!(f.n1 == a && f.n2 == b)) std::swap(f.n1, f.n2); // the first cell becomes the inner one: flip the face
+      } else {
+        SBM_REQUIRE(f.cell[1] < 0, "an edge has more than two adjacent cells");
+        SBM_REQUIRE(f.n1 == b && f.n2 == a, "inconsistent cell orientation: the second cell of an edge cannot be the outer one");
+        f.cell[1] = (int32_t) c;
+      }
+    }
+  }
+  // assign_labels: stable sort by label
+  std::vector<int32_t> order(faces.size());
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return faces[(size_t) x].label < faces[(size_t) y].label; });
+  // geometry
+  auto px = [&](int32_t i) { return xy[2 * (size_t) i]; };
+  auto py = [&](int32_t i) { return xy[2 * (size_t) i + 1]; };
+  auto len2d = [](double dx, double dy) { return std::sqrt((0.0 + dx * dx) + dy * dy); };
+  std::vector<double> vol((size_t) n_cells), ctr(3 * (size_t) n_cells, 0.0);
+  for (int64_t c = 0; c < n_cells; ++c) {
+    const int32_t a = tri[3 * (size_t) c], b = tri[3 * (size_t) c + 1], d = tri[3 * (size_t) c + 2];
+    const double d0x = px(b) - px(a), d0y = py(b) - py(a), d1x = px(d) - px(a), d1y = py(d) - py(a);
+    vol[(size_t) c] = 0.5 * std::fabs(d0x * d1y - d0y * d1x);
+    ctr[3 * (size_t) c] = ((px(a) + px(b)) + px(d)) / 3.0;
+    ctr[3 * (size_t) c + 1] = ((py(a) + py(b)) + py(d)) / 3.0;
+  }
+  std::vector<int32_t> face_cell, bface_cell, labels;
+  std::vector<double> face_area, face_dist, bface_area, bface_dist, fnorm, bnorm;
+  for (const int32_t q : order) {
+    const Face& f = faces[(size_t) q];
+    SBM_REQUIRE(f.cell[0] >= 0, "an edge of the edge file belongs to no cell");
+    const double dx = px(f.n2) - px(f.n1), dy = py(f.n2) - py(f.n1);
+    const double area = len2d(dx, dy);
+    // Seg normal (Shape.hpp:250-257): -(-d.y, d.x) with d = (v2 - v1)/|v2 - v1|, for the stored (possibly flipped) node order
+    const double nx = dy / area, ny = -(dx / area);
+    const int32_t ci = f.cell[0];
+    if (f.label == 0) {
+      SBM_REQUIRE(f.cell[1] >= 0, "an edge with label 0 (interior) has a single adjacent cell");
+      const int32_t co = f.cell[1];
+      face_cell.push_back(ci), face_cell.push_back(co);
+      face_area.push_back(area);
+      face_dist.push_back(len2d(ctr[3 * (size_t) co] - ctr[3 * (size_t) ci], ctr[3 * (size_t) co + 1] - ctr[3 * (size_t) ci + 1]));
+      fnorm.push_back(nx), fnorm.push_back(ny), fnorm.push_back(0.0);
+    } else {
+      SBM_REQUIRE(f.cell[1] < 0, "an edge with a boundary label has two adjacent cells");
+      const double cx = (px(f.n1) + px(f.n2)) / 2.0, cy = (py(f.n1) + py(f.n2)) / 2.0;
+      bface_cell.push_back(ci);
+      bface_area.push_back(area);
+      bface_dist.push_back(2.0 * len2d(cx - ctr[3 * (size_t) ci], cy - ctr[3 * (size_t) ci + 1]));
+      bnorm.push_back(nx), bnorm.push_back(ny), bnorm.push_back(0.0);
+      labels.push_back(f.label);
+    }
+  }
+  sb_mesh_soa soa{};
+  soa.n_cells = n_cells, soa.n_faces = (int64_t) face_area.size(), soa.n_bfaces = (int64_t) bface_area.size();
+  soa.face_cell = face_cell.data(), soa.face_area = face_area.data(), soa.face_dist = face_dist.data();
+  soa.cell_vol = vol.data();
+  soa.bface_cell = bface_cell.data(), soa.bface_area = bface_area.data(), soa.bface_dist = bface_dist.data();
+  const int rc = sb_mesh_from_faces(&soa, ctr.data(), fnorm.data(), bnorm.data(), out);
+  if (rc != SB_OK) return rc;
+  (*out)->pair_label.assign((size_t) (soa.n_faces + soa.n_bfaces), 0);
+  std::copy(labels.begin(), labels.end(), (*out)->pair_label.begin() + soa.n_faces);
+  return SB_OK;
+}
+
+int sb_mesh_bface_labels(const sb_mesh* m, int32_t* h_labels) {
+  SBM_REQUIRE(m != nullptr && h_labels != nullptr, "null argument");
+  const int64_t n_int = (int64_t) m->face_area.size(), n_b = (int64_t) m->bface_area.size();
+  for (int64_t b = 0; b < n_b; ++b)
+    h_labels[b] = m->pair_label.empty() ? 1 : m->pair_label[(size_t) m->face_order[(size_t) (n_int + b)]];
+  return SB_OK;
 }
 
 int sb_mesh_destroy(sb_mesh* mesh) {

@@ -69,6 +69,20 @@ class Mesh:
         capi.check(lib.sb_mesh_read_tetgen(str(path_prefix).encode(), C.byref(h)))
         return Mesh(h)
 
+    @staticmethod
+    def read_tetgen_2d(path_prefix: str) -> "Mesh":
+        """2-D Triangle files `<prefix>.node/.edge/.ele`, as the reference's read_mesh_from_tetgen +
+        UnstructuredMesh<2,2> build them (face order, inner/outer, labels, geometry): sb_mesh_read_tetgen_2d."""
+        lib = capi.load()
+        h = C.c_void_p()
+        capi.check(lib.sb_mesh_read_tetgen_2d(str(path_prefix).encode(), C.byref(h)))
+        return Mesh(h)
+
+    def bface_labels(self) -> np.ndarray:
+        out = np.empty(self.n_bfaces, np.int32)
+        capi.check(self.lib.sb_mesh_bface_labels(self.handle, out.ctypes.data_as(capi.i32p)))
+        return out
+
     def __del__(self):
         try:
             if self.handle:

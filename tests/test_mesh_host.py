@@ -481,3 +481,91 @@ def test_vtk_dump_follows_the_playground_grammar(tmp_path, kind):
         Mesh.from_faces(PolyMesh.bcc(2)).write_vtk(str(tmp_path / "x.vtk"))     # no nodes
     with pytest.raises(capi.StormB200Error):
         mesh.write_vtk(str(tmp_path / "no_such_dir" / "x.vtk"))
+
+
+REF_MESH_DIR = "/root/reference/tests/_data/mesh"
+
+
+@pytest.mark.parametrize("name", ["square_nb", "rectangle", "step"])
+def test_tetgen_2d_reader_reproduces_the_reference_mesh_classes(tmp_path, name):
+    """sb_mesh_read_tetgen_2d on the reference's own test meshes against what the reference's reader +
+    UnstructuredMesh<2,2> + views export (golden npz made by oracle/_ref/ref_mesh_tool; `step` is exported live by
+    the tool): face order, inner/outer, geometry, boundary-face order -- every array bit for bit. Labels: the file's
+    labels, which the reference's label() reports shifted by one at the first face of every label range (lower_bound
+    instead of upper_bound, MeshUnstructured.hpp:185-192)."""
+    import os
+    import subprocess
+    prefix = os.path.join(REF_MESH_DIR, name + ".1")
+    if not os.path.exists(prefix + ".node"):
+        pytest.skip("the reference's test meshes are not mounted here")
+    mesh = Mesh.read_tetgen_2d(prefix)
+    golden = os.path.join(os.path.dirname(__file__), "golden", f"mesh_{name}.npz")
+    if os.path.exists(golden):
+        g = dict(np.load(golden))
+        centers = None
+    else:
+        tool = os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "_ref", "ref_mesh_tool")
+        if not os.path.exists(tool):
+            pytest.skip("oracle/_ref/ref_mesh_tool not built")
+        out = tmp_path / "export.bin"
+        # trailing dot: the reference swaps the path's extension (path.replace_extension, IoTetgen.hpp:54)
+        subprocess.run([tool, "export", prefix + ".", str(out)], check=True, capture_output=True)
+        fm, extra = orc.read_mesh_export(str(out))
+        g = dict(n_cells=fm.n_cells, face_cell=fm.face_cell, face_area=fm.face_area, face_dist=fm.face_dist,
+                 cell_vol=fm.cell_vol, bface_cell=fm.bface_cell, bface_area=fm.bface_area, bface_dist=fm.bface_dist,
+                 bface_label=extra["bface_label"])
+        centers = extra["cell_center"]
+    assert mesh.n_cells == int(g["n_cells"])
+    for k in SOA_KEYS:
+        got = np.asarray(getattr(mesh, k))
+        assert got.shape == g[k].shape and np.array_equal(got, g[k]), f"{k} differs from the reference's export"
+    if centers is not None:
+        assert np.array_equal(mesh.cell_centers()[:, :2], centers) and not mesh.cell_centers()[:, 2].any()
+    labels, ref_labels = mesh.bface_labels(), np.asarray(g["bface_label"])
+    assert (np.diff(labels) >= 0).all() and labels.min() >= 1
+    starts = np.r_[0, np.flatnonzero(np.diff(labels)) + 1]
+    rest = np.setdiff1d(np.arange(len(labels)), starts)
+    assert np.array_equal(labels[rest], ref_labels[rest]) and np.array_equal(ref_labels[starts], labels[starts] - 1)
+    # normals point from the inner to the outer cell / out of the domain, unit length
+    fn, bn = mesh.face_normals()
+    c = mesh.cell_centers()
+    assert (np.einsum("ij,ij->i", fn, c[mesh.face_cell[:, 1]] - c[mesh.face_cell[:, 0]]) > 0).all()
+    assert np.allclose(np.linalg.norm(fn, axis=1), 1.0, rtol=1e-14) and np.allclose(np.linalg.norm(bn, axis=1), 1.0, rtol=1e-14)
+    S = np.zeros((mesh.n_cells, 3))
+    np.add.at(S, mesh.face_cell[:, 0], mesh.face_area[:, None] * fn)
+    np.add.at(S, mesh.face_cell[:, 1], -mesh.face_area[:, None] * fn)
+    np.add.at(S, mesh.bface_cell, mesh.bface_area[:, None] * bn)
+    assert np.abs(S).max() < 1e-13           # every triangle's edge vectors close
+    # and the handle renumbers / partitions like any other (labels travel with the faces)
+    mesh.renumber_rcm()
+    assert sorted(mesh.bface_labels().tolist()) == sorted(labels.tolist())
+    assert Partition(mesh, 3, capi.PART_METIS).info.edge_cut > 0
+
+
+def test_tetgen_2d_reader_rejects_malformed_files(tmp_path):
+    def write(name, node, edge, ele):
+        for ext, text in ((".node", node), (".edge", edge), (".ele", ele)):
+            if text is not None:
+                (tmp_path / (name + ext)).write_text(text)
+        return str(tmp_path / name)
+    node = "4 2 0 0\n0 0 0\n1 1 0\n2 1 1\n3 0 1\n"
+    edge = "5 1\n0 0 1 1\n1 1 2 1\n2 2 3 2\n3 3 0 2\n4 0 2 0\n"
+    ele = "2 3 0\n0 0 1 2\n1 0 2 3\n"
+    ok = Mesh.read_tetgen_2d(write("ok", node, edge, ele))
+    assert (ok.n_cells, ok.n_faces, ok.n_bfaces) == (2, 1, 4) and ok.bface_labels().tolist() == [1, 1, 2, 2]
+    assert ok.face_cell.tolist() == [[0, 1]] and np.array_equal(ok.cell_vol, [0.5, 0.5])
+    # edges the file does not list are created by the cells (find_or_insert), with label 0
+    part = Mesh.read_tetgen_2d(write("partial", node, "4 1\n0 0 1 1\n1 1 2 1\n2 2 3 2\n3 3 0 2\n", ele))
+    assert (part.n_faces, part.n_bfaces) == (1, 4)
+    bad = {
+        "missing_edge_file": (node, None, ele),
+        "dim3": ("4 3 0 0\n0 0 0 0\n1 1 0 0\n2 1 1 0\n3 0 1 0\n", edge, ele),
+        "node_out_of_range": (node, edge, "2 3 0\n0 0 1 7\n1 0 2 3\n"),
+        "clockwise_second_cell": (node, edge, "2 3 0\n0 0 1 2\n1 0 3 2\n"),      # both cells see edge (0,2) the same way
+        "interior_label_on_boundary": (node, "5 1\n0 0 1 0\n1 1 2 1\n2 2 3 2\n3 3 0 2\n4 0 2 0\n", ele),
+        "duplicate_edge": (node, "6 1\n0 0 1 1\n1 1 2 1\n2 2 3 2\n3 3 0 2\n4 0 2 0\n5 2 0 0\n", ele),
+        "truncated": (node, edge, "2 3 0\n0 0 1\n"),
+    }
+    for name, (n_, e_, c_) in bad.items():
+        with pytest.raises(capi.StormB200Error):
+            Mesh.read_tetgen_2d(write(name, n_, e_, c_))
