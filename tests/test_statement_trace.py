@@ -1,0 +1,70 @@
+"""The statement stream of the reference's solvers (their own templates on Storm::DeviceVector, linked against a
+logging stand-in of the C ABI: oracle/statement_trace.py) pins the pass counts SURVEY.md 8a/8d quote and the
+measurement scripts divide by -- derived from what the solvers actually execute, not from reading their source."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def counts(tmp_path_factory):
+    sys.path.insert(0, ROOT)
+    from oracle import statement_trace as st
+    if not st.available():
+        pytest.skip("statement tracer not built (make -C oracle trace; needs the StormRuler sources)")
+    out = tmp_path_factory.mktemp("trace") / "counts.json"
+    # in a process of its own: the stand-in library exports the same symbols as libstormb200.so
+    subprocess.run([sys.executable, "-m", "oracle.statement_trace", "--json", str(out)], check=True, cwd=ROOT,
+                   capture_output=True)
+    return json.load(open(out))
+
+
+def test_as_written_pass_counts_match_the_survey(counts):
+    want = {            # solver: (applies, reductions, vector passes as written) per iteration, SURVEY.md 8a
+        "cg": (1, 2, 12), "bicgstab": (2, 5, 24), "cgs": (2, 3, 24), "tfqmr": (2, 4, 40),
+        "bicgstabl": (4 / 2, None, 63 / 2), "idrs": (5 / 4, None, 173 / 4), "richardson": (1, 1, 7),
+    }
+    for solver, (applies, reds, passes) in want.items():
+        c = counts[solver]
+        assert c["applies"] == applies and c["passes_written"] == passes, (solver, c)
+        if reds is not None:
+            assert c["reductions"] == reds, (solver, c)
+    assert counts["tfqmr1"]["passes_written"] <= 34 and counts["tfqmr1"]["applies"] == 2     # "<= 34V": x <- d is conditional
+    # GMRES(50): inner step k costs (5k + 8) V as written, 1 apply, k + 2 reductions; + restart and solution update
+    g = counts["gmres"]
+    ks = range(50)
+    assert abs(g["passes_written"] - (sum(5 * k + 8 for k in ks) + 50 * 1.0 + 7) / 50) < 2.0
+    assert abs(g["reductions"] - (sum(k + 2 for k in ks) + 1) / 50) < 0.1
+    assert counts["fgmres"] == g                                           # no preconditioner: the same stream
+
+
+def test_fused_schedules_written_down(counts):
+    """What a statement-fusing backend moves (element-wise statements + trailing reductions = one pass): equals the
+    hand-fused schedules where they exist (CG 9V; GMRES (4k+6)V on average) and is within 2V of the BiCGStab one
+    (15V: it also defers `x += alpha p` across an apply, which statement order alone does not allow)."""
+    assert counts["cg"]["passes_fused"] == 9
+    assert counts["bicgstab"]["passes_fused"] == 17
+    g = counts["gmres"]["passes_fused"]
+    assert abs(g - sum(4 * k + 6 for k in range(50)) / 50) < 2.0
+    for solver in ("cgs", "bicgstabl", "tfqmr", "tfqmr1", "idrs", "richardson"):
+        c = counts[solver]
+        assert c["passes_fused"] < c["passes_written"] and c["launches_fused"] < c["launches_written"]
+    # the numbers quoted in DESIGN.md
+    assert (counts["cgs"]["passes_fused"], counts["tfqmr"]["passes_fused"], counts["bicgstabl"]["passes_fused"],
+            counts["idrs"]["passes_fused"]) == (17, 35, 21.5, 29.25)
+
+
+def test_solver_sweep_contract_uses_the_traced_counts(counts):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("solver_sweep", os.path.join(ROOT, "scripts", "solver_sweep.py"))
+    sweep = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sweep)
+    B, V = 72.0, 8.0
+    for solver in ("cgs", "tfqmr", "bicgstabl", "idrs", "richardson"):
+        c = counts[solver]
+        assert sweep.contract_bytes(solver, B, V, 1, 50) == c["applies"] * B + c["passes_written"] * V, solver
