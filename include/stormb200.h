@@ -136,6 +136,13 @@ SB_API int sb_op_download_rows(sb_ctx* ctx, const sb_op* op, int32_t* h_col, dou
                                double* h_val1, double* h_diag);
 /* y <- A(x): Operator::mul (Operator.hpp:74). x and y must not alias. */
 SB_API int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y);
+/* y += dt * div grad x: `stormDivGrad(mesh, u, dt, c)` exactly as the playground calls it (Playground.cpp:115-131;
+ * call sites :159 `stormDivGrad(mesh, w_hat, -Gamma, c_in)` after `w_hat <<= f + sigma*(c_in - c)`, and :165
+ * `stormDivGrad(mesh, c_hat, -tau, w_hat)` after `c_hat <<= c_in`). Every row starts from the old y_i and adds its
+ * face terms in ascending face index, so the result is bit-identical to the face loop accumulating into a
+ * pre-filled field. `op` must be a faithful-form operator (SB_FORM_FAITHFUL; its own dt and prefill are not
+ * used); boundary faces of the mesh contribute their mirror-ghost term as in sb_apply. x and y must not alias. */
+SB_API int sb_apply_accumulate(sb_ctx* ctx, const sb_op* op, double dt, const double* x, double* y);
 
 /* Jacobi (point-diagonal) preconditioner apply: y_i = x_i / a_ii, a_ii the operator's own diagonal (coefficient
  * form only; the faithful form keeps no diagonal). Fills the reference's preconditioner slot
@@ -332,7 +339,7 @@ SB_API int sb_eval(sb_ctx* ctx, double* y, size_t n, int assign_op, const sb_exp
 SB_API int sb_fill(sb_ctx* ctx, double* y, size_t n, double value);
 SB_API int sb_copy(sb_ctx* ctx, double* y, const double* x, size_t n);
 
-/* dot_product (MatrixAlgorithms.hpp:310-317) and the square of norm_2 (:262-270) with the fixed
+/* dot_product (MatrixAlgorithms.hpp:310-317) and norm_2 (:262-270: sqrt of the sum of squares) with the fixed
  * reduction tree "SB_TREE v1" (DESIGN.md): run-to-run and grid-size independent. Results are
  * returned on the host (one stream synchronisation per call). sb_dot_batch evaluates m dot
  * products with one synchronisation. */

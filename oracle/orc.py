@@ -95,6 +95,8 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.orc_apply_faces.argtypes = [C.POINTER(FaceOpStruct), _f64p, _f64p]
         L.orc_apply_faces.restype = None
+        L.orc_divgrad_accumulate.argtypes = [C.POINTER(FaceOpStruct), C.c_double, _f64p, _f64p]
+        L.orc_divgrad_accumulate.restype = None
         L.orc_rows_width.argtypes = [C.POINTER(FaceOpStruct)]
         L.orc_rows_width.restype = C.c_int
         L.orc_build_rows.argtypes = [C.POINTER(FaceOpStruct), C.c_int, C.c_int64, _i32p, _i64p]
@@ -214,6 +216,13 @@ class FaceOp:
         y = np.empty(self.n)
         lib().orc_apply_faces(C.byref(self.struct), _p(x, _f64p), _p(y, _f64p))
         return y
+
+    def divgrad_accumulate(self, dt, c, u):
+        """u += dt * div grad c in place: stormDivGrad as the playground calls it (Playground.cpp:115-131)."""
+        c = _f64(c)
+        assert u.dtype == np.float64 and u.flags.c_contiguous
+        lib().orc_divgrad_accumulate(C.byref(self.struct), float(dt), _p(c, _f64p), _p(u, _f64p))
+        return u
 
     @property
     def callback(self):
@@ -434,6 +443,54 @@ def ref_solve(solver: str, op, b, x0=None, num_iterations=2000, abs_tol=1e-6, re
                        hist[:rep.n_hist].copy(), trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)
 
 
+# ---- the playground's Cahn-Hilliard time step (Playground.cpp:133-175) ------------------------------------------
+CH_TAU, CH_GAMMA, CH_SIGMA = 1.0e-3, 1.0e-4, 2.0   # Playground.cpp:113
+
+
+def ch_dF_dc(c):
+    """dF/dc of the double-well potential, in the reference's association order (Playground.cpp:142-144):
+    ((2.0 * c) * (c - 1.0)) * (2.0 * c - 1.0), every operation rounded separately."""
+    return ((2.0 * c) * (c - 1.0)) * (2.0 * c - 1.0)
+
+
+class CahnHilliardOp:
+    """The affine operator the playground hands to CG (Playground.cpp:153-167):
+        w_hat <<= f + sigma * (c_in - c);  stormDivGrad(mesh, w_hat, -Gamma, c_in);
+        c_hat <<= c_in;                    stormDivGrad(mesh, c_hat, -tau, w_hat)
+    over the interior faces of `mesh` (a FaceMesh). `w_hat` keeps the last evaluation, like the reference's."""
+
+    def __init__(self, mesh: FaceMesh, c, tau=CH_TAU, Gamma=CH_GAMMA, sigma=CH_SIGMA):
+        self.faces = FaceOp(mesh.without_boundary(), prefill=0, dt=0.0)
+        self.n = mesh.n_cells
+        self.c = _f64(c).copy()
+        self.f = ch_dF_dc(self.c)
+        self.tau, self.Gamma, self.sigma = float(tau), float(Gamma), float(sigma)
+        self.w_hat = np.zeros(self.n)
+        self._cb = CallbackOp(self.apply, self.n)
+
+    def apply(self, c_in):
+        c_in = _f64(c_in)
+        self.w_hat = self.f + self.sigma * (c_in - self.c)
+        self.faces.divgrad_accumulate(-self.Gamma, c_in, self.w_hat)
+        c_hat = c_in.copy()
+        self.faces.divgrad_accumulate(-self.tau, self.w_hat, c_hat)
+        return c_hat
+
+    @property
+    def callback(self):
+        return self._cb.callback
+
+
+def cahn_hilliard_step(mesh: FaceMesh, c, mode=RED_SEQ, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6,
+                       **constants) -> SolveResult:
+    """One time step: `c_hat <<= c; solve<CgSolver>(c_hat, c, op)` (Playground.cpp:148-167; the defaults are those
+    of IterativeSolver, Solver.hpp:61-63). Uses the reference's own CgSolver when oracle/_ref is built, the C
+    restatement otherwise (the two are pinned against each other in tests/test_oracle_golden.py)."""
+    op = CahnHilliardOp(mesh, c, **constants)
+    run = ref_solve if have_ref() else solve
+    return run("cg", op, op.c, x0=op.c, num_iterations=num_iterations, abs_tol=abs_tol, rel_tol=rel_tol, mode=mode)
+
+
 # ---- reading the binary dumps of oracle/_ref/ref_mesh_tool ------------------------------------
 class _Reader:
     def __init__(self, path):
@@ -479,3 +536,17 @@ def read_cg_dump(path):
     b, x, hist = r.arr(np.float64), r.arr(np.float64), r.arr(np.float64)
     return dict(n=n, converged=bool(conv), iterations=it, abs_err=abs_err, rel_err=rel_err, b=b, x=x,
                 hist=hist)
+
+
+def read_ch_dump(path):
+    """Output of `ref_mesh_tool ch`: initial c and, per time step, the new c with the CG solver's report."""
+    r = _Reader(path)
+    n, steps = r.i64(), r.i64()
+    out = dict(n=n, c0=r.arr(np.float64), steps=[])
+    for _ in range(steps):
+        conv, it = r.i64(), r.i64()
+        abs_err, rel_err = r.f64(), r.f64()
+        c, hist = r.arr(np.float64), r.arr(np.float64)
+        out["steps"].append(dict(converged=bool(conv), iterations=it, abs_err=abs_err, rel_err=rel_err, c=c,
+                                 hist=hist))
+    return out

@@ -19,6 +19,12 @@
 //       Runs the reference CgSolver on CellField with y = x - dt * div grad x written as the
 //       playground writes it, b[k] = sin(0.37 k), x0 = 0 (SURVEY.md 8d "Config 1");
 //       dumps b, x, the residual history and the solver's final public fields.
+//   ref_mesh_tool ch <prefix> <num_steps> <out.bin>
+//       The playground's own caller of the path, statement for statement (Playground.cpp:133-175 and the
+//       initial condition / swap of :176-210): c[cell] = rand()/RAND_MAX (glibc, default seed), then per
+//       time step  f <<= map(dF_dc, c);  c_hat <<= c;  solve<CgSolver>(c_hat, c, make_operator(lambda))
+//       with the two chained stormDivGrad calls of :153-167 and the constants of :113. Dumps the initial c
+//       and, per step, c_hat, the CG iteration count, final errors and the residual history.
 //
 // The only code here that is not the reference's is the restated face loop `div_grad` below
 // (the original is a file-local function of the playground app and cannot be included).
@@ -169,6 +175,69 @@ int cmd_cg(const std::string& prefix, double dt, size_t num_iterations, double r
   return 0;
 }
 
+// One Cahn-Hilliard time step, Playground.cpp:133-175 (the CgSolver is constructed here instead of inside
+// solve<CgSolver>, Solver.hpp:261-265, so that its public progress fields can be sampled; same defaults).
+constexpr double ch_tau = 1.0e-3, ch_Gamma = 1.0e-4, ch_sigma = 2.0; // Playground.cpp:113
+
+struct ChStepReport {
+  bool converged;
+  size_t iterations;
+  double abs_err, rel_err;
+  std::vector<double> hist;
+};
+
+ChStepReport cahn_hilliard_step(const RefMesh& mesh, const RefField& c, RefField& c_hat, RefField& w_hat) {
+  constexpr auto dF_dc = [](real_t c) noexcept { return 2.0 * c * (c - 1.0) * (2.0 * c - 1.0); };
+  RefField f{mesh};
+  f <<= map(dF_dc, c);
+  c_hat <<= c;
+  CgSolver<RefField> solver{};
+  ChStepReport rep{};
+  const auto op = make_operator<RefField>([&](RefField& c_out, const RefField& c_in) {
+    const size_t it = solver.iteration;
+    if (rep.hist.size() <= it) rep.hist.resize(it + 1);
+    rep.hist[it] = solver.absolute_error;
+    w_hat <<= f + ch_sigma * (c_in - c);
+    div_grad(mesh, w_hat, -ch_Gamma, c_in);
+    c_out <<= c_in;
+    div_grad(mesh, c_out, -ch_tau, w_hat);
+  });
+  rep.converged = solver.solve(c_hat, c, *op);
+  rep.iterations = solver.iteration;
+  rep.abs_err = solver.absolute_error, rep.rel_err = solver.relative_error;
+  if (rep.hist.size() <= solver.iteration) rep.hist.resize(solver.iteration + 1);
+  rep.hist[solver.iteration] = solver.absolute_error;
+  return rep;
+}
+
+int cmd_ch(const std::string& prefix, size_t num_steps, const char* out) {
+  const auto mesh = load(prefix);
+  const size_t n = mesh->num_cells();
+  RefField c{*mesh}, c_hat{*mesh}, w_hat{*mesh};
+  std::ranges::for_each(mesh->interior_cells(), [&](CellView<RefMesh> cell) {
+    c[cell] = (1.0 * rand()) / RAND_MAX; // Playground.cpp:183-185
+  });
+  Writer w{out};
+  w.i64((int64_t) n);
+  w.i64((int64_t) num_steps);
+  std::vector<double> v(n);
+  for (size_t k = 0; k < n; ++k) v[k] = c(k);
+  w.arr(v);
+  for (size_t step = 0; step < num_steps; ++step) {
+    const ChStepReport rep = cahn_hilliard_step(*mesh, c, c_hat, w_hat);
+    std::swap(c, c_hat); // Playground.cpp:204
+    for (size_t k = 0; k < n; ++k) v[k] = c(k);
+    w.i64(rep.converged ? 1 : 0);
+    w.i64((int64_t) rep.iterations);
+    w.f64(rep.abs_err);
+    w.f64(rep.rel_err);
+    w.arr(v), w.arr(rep.hist);
+    std::printf("ch: step=%zu converged=%d iterations=%zu abs=%.17g rel=%.17g\n", step, (int) rep.converged,
+                rep.iterations, rep.abs_err, rep.rel_err);
+  }
+  return 0;
+}
+
 } // namespace
 
 int main(int argc, char** argv) {
@@ -176,8 +245,11 @@ int main(int argc, char** argv) {
   if (argc >= 7 && std::strcmp(argv[1], "cg") == 0)
     return cmd_cg(argv[2], std::atof(argv[3]), (size_t) std::atoll(argv[4]), std::atof(argv[5]),
                   argv[6]);
+  if (argc >= 5 && std::strcmp(argv[1], "ch") == 0)
+    return cmd_ch(argv[2], (size_t) std::atoll(argv[3]), argv[4]);
   std::fprintf(stderr,
                "usage: ref_mesh_tool export <prefix> <out.bin>\n"
-               "       ref_mesh_tool cg <prefix> <dt> <num_iterations> <rel_tol> <out.bin>\n");
+               "       ref_mesh_tool cg <prefix> <dt> <num_iterations> <rel_tol> <out.bin>\n"
+               "       ref_mesh_tool ch <prefix> <num_steps> <out.bin>\n");
   return 1;
 }

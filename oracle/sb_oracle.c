@@ -39,6 +39,25 @@ void orc_apply_faces(const orc_face_op* op, const double* x, double* y) {
   }
 }
 
+/* stormDivGrad(mesh, u, dt, c) as the playground calls it (Playground.cpp:115-131): the face terms are ADDED
+ * to whatever the caller left in u (`w_hat <<= f + sigma*(c_in - c)` then stormDivGrad(mesh, w_hat, -Gamma, c_in),
+ * :157-159). op->prefill and op->dt are ignored. */
+void orc_divgrad_accumulate(const orc_face_op* op, double dt, const double* c, double* u) {
+  for (int64_t f = 0; f < op->n_faces; ++f) {
+    const int32_t ci = op->face_cell[2 * f + 0];
+    const int32_t co = op->face_cell[2 * f + 1];
+    const double flux = dt * (c[co] - c[ci]) / op->face_dist[f];
+    u[ci] += (op->face_area[f] / op->cell_vol[ci]) * flux;
+    u[co] -= (op->face_area[f] / op->cell_vol[co]) * flux;
+  }
+  for (int64_t b = 0; b < op->n_bfaces; ++b) {
+    const int32_t ci = op->bface_cell[b];
+    const double ghost = -c[ci];
+    const double flux = dt * (ghost - c[ci]) / op->bface_dist[b];
+    u[ci] += (op->bface_area[b] / op->cell_vol[ci]) * flux;
+  }
+}
+
 void orc_apply_faces_cb(void* user, double* y, const double* x, size_t n) {
   (void) n;
   orc_apply_faces((const orc_face_op*) user, x, y);
@@ -118,7 +137,7 @@ void orc_apply_rows_faithful(int64_t n, int width, int64_t ld, const int32_t* co
                              double* y) {
   for (int64_t i = 0; i < n; ++i) {
     const double xi = x[i];
-    double u = prefill ? xi : 0.0;
+    double u = prefill == 2 ? y[i] : (prefill ? xi : 0.0); /* 2: accumulate onto the old y (stormDivGrad as called) */
     for (int k = 0; k < width; ++k) {
       const int64_t e = (int64_t) k * ld + i;
       const int32_t c = col[e];

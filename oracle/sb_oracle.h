@@ -69,6 +69,10 @@ typedef struct {
 /* y <- A(x), face loop in ascending face index; boundary faces after all interior faces. */
 void orc_apply_faces(const orc_face_op* op, const double* x, double* y);
 
+/* u += dt * div grad c over the same faces: stormDivGrad exactly as the playground calls it (the caller pre-fills
+ * u; Playground.cpp:115-131, call sites :159,:165). Ignores op->prefill / op->dt. */
+void orc_divgrad_accumulate(const orc_face_op* op, double dt, const double* c, double* u);
+
 /* Same signature as the callback taken by oracle/_ref's ref_solve(): user = const orc_face_op*. */
 void orc_apply_faces_cb(void* user, double* y, const double* x, size_t n);
 
@@ -114,7 +118,7 @@ void orc_build_rows(const orc_face_op* op, int width, int64_t ld, int32_t* col, 
 /* "faithful" per-entry data: g = area/vol_i, d = dist, evaluated as in Playground.cpp:126-129. */
 void orc_rows_faithful(const orc_face_op* op, int width, int64_t ld, const int64_t* face, double* g,
                        double* d);
-/* y_i = prefill(x_i); for k: y_i += g_k * (dt * (xn_k - x_i) / d_k), xn_k = x[col] or -x[i] for a ghost.
+/* y_i = prefill(x_i) (prefill 2: the old y_i); for k: y_i += g_k * (dt * (xn_k - x_i) / d_k), xn_k = x[col] or -x[i] for a ghost.
  * Bit-identical to orc_apply_faces (u - g*F == u + g*(-F) exactly in IEEE-754). */
 void orc_apply_rows_faithful(int64_t n, int width, int64_t ld, const int32_t* col, const double* g,
                              const double* d, int32_t prefill, double dt, const double* x, double* y);

@@ -1,11 +1,11 @@
 /* TEST / ANALYSIS INFRASTRUCTURE -- not product code, computes nothing.
  *
- * A logging stand-in for the 15 C-ABI entry points that stormruler_b200/host/dropin.cpp imports (include/stormb200.h).
+ * A logging stand-in for the 16 C-ABI entry points that stormruler_b200/host/dropin.cpp imports (include/stormb200.h).
  * The drop-in TU -- the reference's unmodified solver templates on Storm::DeviceVector -- is linked against this
  * library instead of libstormb200.so (oracle/Makefile, target `trace`), so every vector statement, reduction and
  * operator apply the reference's solvers issue shows up as one line of a log, with vector identities instead of data:
  *     eval  y aop n_vec v0 v1 ...     y (op)= expr over these distinct vector operands
- *     fill  y | copy y x | dot a b | norm a | apply y x | jacobi y x | alloc v | free v | upload v
+ *     fill  y | copy y x | dot a b | norm a | apply y x | accum y x | jacobi y x | alloc v | free v | upload v
  * Vectors are numbered in order of first appearance. Reductions return 1.0 (solvers run with tolerances 0, so the
  * statement stream does not depend on values). oracle/statement_trace.py turns the log into vector-pass counts per
  * iteration: as written, and for the schedule a statement-fusing backend would execute. */
@@ -125,6 +125,13 @@ API int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y) {
   (void) ctx, (void) op;
   char line[64];
   snprintf(line, sizeof line, "apply %d %d\n", id_of(y), id_of(x));
+  put(line);
+  return SB_OK;
+}
+API int sb_apply_accumulate(sb_ctx* ctx, const sb_op* op, double dt, const double* x, double* y) {
+  (void) ctx, (void) op, (void) dt;
+  char line[64];
+  snprintf(line, sizeof line, "accum %d %d\n", id_of(y), id_of(x));
   put(line);
   return SB_OK;
 }

@@ -238,6 +238,11 @@ class FvmOperator:
         """Operator::mul (Operator.hpp:74)."""
         capi.check(self.ctx.lib.sb_apply(self.ctx.handle, self.handle, x.ptr, y.ptr))
 
+    def div_grad(self, u: DeviceVector, dt: float, c: DeviceVector):
+        """u += dt * div grad c: `stormDivGrad(mesh, u, dt, c)` as the playground calls it (Playground.cpp:115-131);
+        faithful-form operators only (sb_apply_accumulate)."""
+        capi.check(self.ctx.lib.sb_apply_accumulate(self.ctx.handle, self.handle, float(dt), c.ptr, u.ptr))
+
     def jacobi(self, y: DeviceVector, x: DeviceVector):
         """y = D^-1 x with D the operator's diagonal (sb_op_jacobi): the Jacobi preconditioner's mul."""
         capi.check(self.ctx.lib.sb_op_jacobi(self.ctx.handle, self.handle, x.ptr, y.ptr))

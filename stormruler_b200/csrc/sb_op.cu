@@ -390,4 +390,14 @@ int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y) {
   return launch_apply<0, false>(ctx, op, x, y, NoEpi{}, NoFinal{}, nullptr);
 }
 
+int sb_apply_accumulate(sb_ctx* ctx, const sb_op* op, double dt, const double* x, double* y) {
+  SB_REQUIRE(ctx != nullptr && op != nullptr && x != nullptr && y != nullptr, "null argument");
+  SB_REQUIRE(x != y, "sb_apply_accumulate: x and y must not alias");
+  SB_REQUIRE(op->d.form == SB_FORM_FAITHFUL,
+             "sb_apply_accumulate needs a faithful-form operator (the per-face terms, not dt-scaled coefficients)");
+  OpDev d = op->d;
+  d.dt = dt, d.prefill = 2;
+  return launch_apply<0, false>(ctx, op, x, y, NoEpi{}, NoFinal{}, nullptr, &d);
+}
+
 } // extern "C"

@@ -24,7 +24,7 @@ namespace sb {
 
 struct OpDev {
   int64_t n = 0, ld = 0;
-  int32_t width = 0, form = 0, prefill = 0;
+  int32_t width = 0, form = 0, prefill = 0; // prefill: 0 y = A x from 0, 1 from x, 2 (faithful form, per call) from the old y
   double dt = 0.0;
   const int32_t* col = nullptr;
   const double* v0 = nullptr;
@@ -121,7 +121,7 @@ struct EpiResidual {
 // sequential in k either way, so chunking changes the register footprint, not the result.
 template<int FORM, int W>
 __device__ __forceinline__ double2 apply_rows(const OpDev& op, const double* __restrict__ x, int64_t e0, double2 xo,
-                                              int coh) {
+                                              double2 yo, int coh) {
   constexpr int C = W <= 8 ? W : 8;
   const int64_t h = e0 >> 1, ldh = op.ld >> 1;
   const int2* __restrict__ col2 = reinterpret_cast<const int2*>(op.col);
@@ -131,7 +131,9 @@ __device__ __forceinline__ double2 apply_rows(const OpDev& op, const double* __r
     const double2 dg = ld2(op.diag, e0);
     u0 = __dmul_rn(dg.x, xo.x), u1 = __dmul_rn(dg.y, xo.y);
   } else {
-    u0 = op.prefill ? xo.x : 0.0, u1 = op.prefill ? xo.y : 0.0;
+    // prefill 2: the face terms are added to what the caller left in y (stormDivGrad as the playground calls it,
+    // Playground.cpp:157-165); the row sum then starts from the old y, like the face loop's `u[cell] +=`
+    u0 = op.prefill == 2 ? yo.x : (op.prefill ? xo.x : 0.0), u1 = op.prefill == 2 ? yo.y : (op.prefill ? xo.y : 0.0);
   }
 #pragma unroll
   for (int k0 = 0; k0 < W; k0 += C) {
@@ -210,7 +212,11 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double*
     const double2 xo = ld2(x, e0);
     typename Epi::Regs er;
     epi.load(e0, er);
-    double2 out = apply_rows<FORM, W>(op, x, e0, xo, coh);
+    double2 yo = make_double2(0.0, 0.0);
+    if constexpr (FORM == SB_FORM_FAITHFUL) {
+      if (op.prefill == 2) yo = ld2(y, e0); // read by the lane that overwrites it below
+    }
+    double2 out = apply_rows<FORM, W>(op, x, e0, xo, yo, coh);
     if constexpr (RESID) {
       out.x = __dsub_rn(er.b.x, out.x);
       out.y = __dsub_rn(er.b.y, out.y);
@@ -469,10 +475,11 @@ inline bool apply_v1_forced() {
 int halo_exchange(sb_ctx* ctx, const sb_op* op, const double* x, const int* done, int64_t* x_off); // sb_comm.cu
 
 // Launch y <- A x (+ epilogue) on the context's stream, dispatching on form and ELL width.
+// `per_call` (optional) replaces the operator's kernel arguments for this launch (sb_apply_accumulate: other dt/prefill).
 template<int ND, bool RESID, class Epi, class Final>
 int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const Epi& epi, const Final& fin,
-                 const int* done) {
-  const OpDev& d = op->d;
+                 const int* done, const OpDev* per_call = nullptr) {
+  const OpDev& d = per_call != nullptr ? *per_call : op->d;
   if constexpr (ND > 0) {
     SB_TRY(ensure_red_scratch(ctx, d.n));
   }

@@ -32,6 +32,11 @@ class Report(C.Structure):
                 ("n_apply", C.c_int64)]
 
 
+class ChParams(C.Structure):   # dropin_ch_params: Playground.cpp:113 constants + solver limits (<= 0 / < 0: defaults)
+    _fields_ = [("tau", C.c_double), ("Gamma", C.c_double), ("sigma", C.c_double),
+                ("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double)]
+
+
 _lib = None
 
 
@@ -51,6 +56,10 @@ def load():
                                    C.POINTER(Opts), C.POINTER(Report), capi.f64p, C.c_int64, capi.f64p,
                                    C.c_int64]
         L.dropin_solve.restype = C.c_int
+        L.dropin_cahn_hilliard_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_size_t, C.POINTER(ChParams), C.POINTER(Report), capi.f64p,
+                                                C.c_int64, capi.f64p, C.c_int64]
+        L.dropin_cahn_hilliard_step.restype = C.c_int
         L.dropin_last_error.restype = C.c_char_p
         L.dropin_reset_rng.restype = None
         L.dropin_selftest_errors.argtypes = [C.c_void_p]
@@ -92,5 +101,25 @@ def solve(name: str, op, x, b, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6, 
                         trace.ctypes.data_as(capi.f64p), cap_t)
     if rc != 0:
         raise capi.StormB200Error(f"dropin_solve({name}) failed ({rc}): {L.dropin_last_error().decode()}")
+    return Result(bool(rep.converged), rep.iterations, rep.abs_err, rep.rel_err,
+                  hist[:min(rep.n_hist, cap_h)].copy(), trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)
+
+
+def cahn_hilliard_step(faces, c, c_hat, w_hat, tau=1.0e-3, Gamma=1.0e-4, sigma=2.0, num_iterations=0,
+                       abs_tol=-1.0, rel_tol=-1.0) -> Result:
+    """One time step of the playground's Cahn-Hilliard solver (Playground.cpp:133-175) through the C++ drop-in:
+    `faces` a faithful-form FvmOperator over the mesh, c (in) / c_hat (out: the new c) / w_hat (workspace)
+    DeviceVectors. Defaults = the playground's constants (:113) and IterativeSolver's limits (2000, 1e-6, 1e-6)."""
+    L = load()
+    iters = num_iterations if num_iterations > 0 else 2000
+    cap_h, cap_t = iters + 2, 8 * iters + 64
+    hist, trace = np.zeros(cap_h), np.zeros(cap_t)
+    prm = ChParams(tau, Gamma, sigma, num_iterations, abs_tol, rel_tol)
+    rep = Report()
+    rc = L.dropin_cahn_hilliard_step(faces.ctx.handle, faces.handle, c.ptr, c_hat.ptr, w_hat.ptr, c.n,
+                                     C.byref(prm), C.byref(rep), hist.ctypes.data_as(capi.f64p), cap_h,
+                                     trace.ctypes.data_as(capi.f64p), cap_t)
+    if rc != 0:
+        raise capi.StormB200Error(f"dropin_cahn_hilliard_step failed ({rc}): {L.dropin_last_error().decode()}")
     return Result(bool(rep.converged), rep.iterations, rep.abs_err, rep.rel_err,
                   hist[:min(rep.n_hist, cap_h)].copy(), trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)

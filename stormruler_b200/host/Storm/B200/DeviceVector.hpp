@@ -33,6 +33,7 @@
 
 #include <array>
 #include <cmath>
+#include <concepts>
 #include <cstdint>
 #include <cstring>
 #include <random>
@@ -131,9 +132,15 @@ public:
       vmap[k] = slot;
     }
     for (int k = 0; k < rhs._n_scal; ++k) {
-      if (out._n_scal == SB_EXPR_MAX_SCAL) throw std::runtime_error("stormb200: expression uses more than 4 scalars");
-      smap[k] = out._n_scal;
-      out._e.scal[out._n_scal++] = rhs._e.scal[k];
+      int slot = -1; // a constant that occurs twice (the 2.0 and 1.0 of dF/dc, Playground.cpp:142-144) takes one slot
+      for (int q = 0; q < out._n_scal; ++q)
+        if (std::memcmp(&out._e.scal[q], &rhs._e.scal[k], sizeof(double)) == 0) slot = q;
+      if (slot < 0) {
+        if (out._n_scal == SB_EXPR_MAX_SCAL) throw std::runtime_error("stormb200: expression uses more than 4 scalars");
+        slot = out._n_scal++;
+        out._e.scal[slot] = rhs._e.scal[k];
+      }
+      smap[k] = slot;
     }
     for (int k = 0; k < rhs._e.n_ops; ++k) {
       const uint8_t o = rhs._e.ops[k];
@@ -304,6 +311,41 @@ inline DevExpr operator-(const DevExpr& a) { return a.negated(); }
 inline DevExpr operator-(DeviceVector& a) { return DevExpr{a}.negated(); }
 inline DevExpr operator-(const DeviceVector& a) { return DevExpr{a}.negated(); }
 
+// ---- map(func, vec) (MatrixMath.hpp:101-105) ------------------------------------------------------
+// The reference applies `func` to every element on the host. A C ABI cannot carry a C++ callable, so the
+// function is TRACED instead: it is called once with a symbolic element (B200::Sym), whose arithmetic
+// operators record the postfix program that sb_eval then runs per element on the device, in the association
+// order the function's body was written in. The callable must therefore be generic in its argument
+// (`[](auto c) { return 2.0 * c * (c - 1.0) * (2.0 * c - 1.0); }` -- the playground's dF_dc,
+// Playground.cpp:142-144, with `real_t c` spelled `auto c`) and use + - * / only.  `f <<= B200::map(dF_dc, c);`
+namespace B200 {
+struct Sym {
+  DevExpr e;
+};
+inline Sym operator+(const Sym& a, const Sym& b) { return {DevExpr::binary(a.e, b.e, SB_OP_ADD)}; }
+inline Sym operator-(const Sym& a, const Sym& b) { return {DevExpr::binary(a.e, b.e, SB_OP_SUB)}; }
+inline Sym operator*(const Sym& a, const Sym& b) { return {DevExpr::binary(a.e, b.e, SB_OP_MUL)}; }
+inline Sym operator/(const Sym& a, const Sym& b) { return {DevExpr::binary(a.e, b.e, SB_OP_DIV)}; }
+inline Sym operator+(const Sym& a, double s) { return {DevExpr::binary(a.e, DevExpr::scalar(s), SB_OP_ADD)}; }
+inline Sym operator-(const Sym& a, double s) { return {DevExpr::binary(a.e, DevExpr::scalar(s), SB_OP_SUB)}; }
+inline Sym operator*(const Sym& a, double s) { return {DevExpr::binary(a.e, DevExpr::scalar(s), SB_OP_MUL)}; }
+inline Sym operator/(const Sym& a, double s) { return {DevExpr::binary(a.e, DevExpr::scalar(s), SB_OP_DIV)}; }
+inline Sym operator+(double s, const Sym& a) { return {DevExpr::binary(DevExpr::scalar(s), a.e, SB_OP_ADD)}; }
+inline Sym operator-(double s, const Sym& a) { return {DevExpr::binary(DevExpr::scalar(s), a.e, SB_OP_SUB)}; }
+inline Sym operator*(double s, const Sym& a) { return {DevExpr::binary(DevExpr::scalar(s), a.e, SB_OP_MUL)}; }
+inline Sym operator/(double s, const Sym& a) { return {DevExpr::binary(DevExpr::scalar(s), a.e, SB_OP_DIV)}; }
+inline Sym operator-(const Sym& a) { return {a.e.negated()}; }
+inline Sym operator+(const Sym& a) { return a; }
+/// B200::map(func, vec): called QUALIFIED. An unqualified `map(...)` would also consider the reference's generic
+/// template (found by ADL), whose constraint instantiates `func` with the host element proxy -- a hard error inside a
+/// generic lambda's body, not a substitution failure.
+template<class Func>
+  requires requires(Func f, Sym s) { { f(s) } -> std::same_as<Sym>; }
+inline DevExpr map(Func func, const DeviceVector& v) {
+  return func(Sym{DevExpr{v}}).e;
+}
+} // namespace B200
+
 // ---- reductions (MatrixAlgorithms.hpp:262-270, 310-317): fixed tree SB_TREE v1, result on the host
 namespace B200 {
 inline double dot_impl(const DeviceVector& a, const DeviceVector& b) {
@@ -388,6 +430,18 @@ private:
   sb_op* _owned = nullptr;
   mutable size_t _num_applies = 0;
 };
+
+namespace B200 {
+/// `stormDivGrad(mesh, u, dt, c)` (Playground.cpp:115-131) on the device: u += dt * div grad c over the faces of the
+/// uploaded mesh, each cell adding its face terms to the value the caller left in u, in ascending face order
+/// (bit-identical to the face loop). `op` must hold a faithful-form operator (sb_op_desc::form = SB_FORM_FAITHFUL).
+inline void div_grad(const FvmOperator& op, DeviceVector& u, double dt, const DeviceVector& c) {
+  if (u.context() != c.context() || u.size() != c.size()) {
+    throw std::runtime_error("stormb200: div_grad on vectors of different size or context");
+  }
+  check(sb_apply_accumulate(op.context(), op.handle(), dt, c.data(), u.data()), "sb_apply_accumulate");
+}
+} // namespace B200
 
 } // namespace Storm
 

@@ -52,6 +52,14 @@ struct dropin_report {
   int64_t n_apply;
 };
 
+// Constants of the playground's Cahn-Hilliard step (Playground.cpp:113) and the solver limits; a negative tolerance or
+// num_iterations <= 0 keeps the IterativeSolver default (Solver.hpp:61-63), which is what solve<CgSolver> runs with.
+struct dropin_ch_params {
+  double tau, Gamma, sigma;
+  int64_t num_iterations;
+  double abs_tol, rel_tol;
+};
+
 thread_local std::string g_error;
 
 struct Trace {
@@ -195,6 +203,64 @@ DROPIN_API int dropin_solve(const char* name, sb_ctx* ctx, const sb_op* op, doub
   }
   g_error = "unknown solver name";
   return -1;
+}
+
+// One Cahn-Hilliard time step of the playground (Playground.cpp:133-175), the reference's own caller of the path,
+// after the switch to the device types: CellField -> DeviceVector, stormDivGrad(mesh, u, dt, c) ->
+// Storm::B200::div_grad(faces, u, dt, c), map -> Storm::B200::map and `real_t c` -> `auto c` in dF_dc (the function is
+// traced, not called per element). Everything else is the playground's statement sequence; the solver is the reference's CgSolver template.
+// `faces` is a faithful-form operator over the mesh (its own dt/prefill are not used). d_c: c (in), d_c_hat: the new
+// c (out), d_w_hat: workspace holding the chemical potential of the last operator evaluation (out).
+DROPIN_API int dropin_cahn_hilliard_step(sb_ctx* ctx, const sb_op* faces, const double* d_c, double* d_c_hat,
+                                         double* d_w_hat, size_t n, const dropin_ch_params* p, dropin_report* rep,
+                                         double* hist, int64_t hist_cap, double* trace, int64_t trace_cap) {
+  try {
+    const double tau = p->tau, Gamma = p->Gamma, sigma = p->sigma;
+    const DeviceVector c = DeviceVector::view(ctx, const_cast<double*>(d_c), n);
+    DeviceVector c_hat = DeviceVector::view(ctx, d_c_hat, n);
+    DeviceVector w_hat = DeviceVector::view(ctx, d_w_hat, n);
+    const Storm::FvmOperator mesh{ctx, faces};
+    Trace tr{trace, trace_cap, 0};
+    Storm::B200::g_observer = &Trace::push, Storm::B200::g_observer_user = &tr;
+
+    constexpr auto dF_dc = [](auto c) { return 2.0 * c * (c - 1.0) * (2.0 * c - 1.0); };
+    DeviceVector f{ctx, n};
+    f <<= Storm::B200::map(dF_dc, c);
+
+    c_hat <<= c;
+    Storm::CgSolver<DeviceVector> solver{}; // what solve<CgSolver>(...) constructs (Solver.hpp:261-265)
+    if (p->num_iterations > 0) solver.num_iterations = (size_t) p->num_iterations;
+    if (p->abs_tol >= 0.0) solver.absolute_error_tolerance = p->abs_tol;
+    if (p->rel_tol >= 0.0) solver.relative_error_tolerance = p->rel_tol;
+    int64_t n_apply = 0;
+    const auto op = Storm::make_operator<DeviceVector>([&](DeviceVector& c_out, const DeviceVector& c_in) {
+      const int64_t it = (int64_t) solver.iteration;
+      if (hist != nullptr && it < hist_cap) hist[it] = solver.absolute_error;
+      w_hat <<= f + sigma * (c_in - c);
+      Storm::B200::div_grad(mesh, w_hat, -Gamma, c_in);
+      c_out <<= c_in;
+      Storm::B200::div_grad(mesh, c_out, -tau, w_hat);
+      ++n_apply;
+    });
+    bool converged = false;
+    try {
+      converged = solver.solve(c_hat, c, *op);
+    } catch (...) {
+      Storm::B200::g_observer = nullptr;
+      throw;
+    }
+    Storm::B200::g_observer = nullptr;
+    const int64_t it = (int64_t) solver.iteration;
+    if (hist != nullptr && it < hist_cap) hist[it] = solver.absolute_error;
+    rep->converged = converged ? 1 : 0;
+    rep->iterations = it;
+    rep->abs_err = solver.absolute_error, rep->rel_err = solver.relative_error;
+    rep->n_hist = it + 1, rep->n_trace = tr.count, rep->n_apply = n_apply;
+    return 0;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -2;
+  }
 }
 
 // Reset the engine behind fill_randomly(DeviceVector&) to the reference's initial state.

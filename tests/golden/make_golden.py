@@ -13,6 +13,10 @@ Outputs (small, committed):
   tests/golden/cg_native_<name>.npz  CgSolver on the reference's own CellField: history, final x
   tests/golden/solvers_<name>.npz    all ten solvers through ref_solve: histories, final errors,
                                      iteration counts, reduction traces (head), x of cg/bicgstab
+  tests/golden/cahn_hilliard_square_nb.npz  the playground's Cahn-Hilliard time step (Playground.cpp:133-210)
+                                     run by the reference's own mesh / CellField / map / CgSolver on
+                                     square_nb.1: initial c (glibc rand()), c after each of 2 steps, CG reports
+                                     and residual histories (`--only ch` regenerates just this file)
   tests/golden/blas1_kat.npz         known answers of tests/unit/BitternReductions.cpp /
                                      BitternMath.cpp evaluated by the reference templates
 
@@ -36,10 +40,29 @@ DT, ITERS, RTOL = 0.05, 500, 1e-10
 TRACE_HEAD = 64
 
 
+CH_STEPS = 2
+
+
+def make_cahn_hilliard(tmp):
+    name = "square_nb"
+    ch_bin = f"{tmp}/{name}_ch.bin"
+    subprocess.run([orc.REF_MESH_TOOL, "ch", f"{REF_DATA}/{name}.1.", str(CH_STEPS), ch_bin], check=True)
+    ch = orc.read_ch_dump(ch_bin)
+    out = dict(c0=ch["c0"], tau=1.0e-3, Gamma=1.0e-4, sigma=2.0, num_steps=CH_STEPS)
+    for k, st in enumerate(ch["steps"]):
+        out[f"step{k}_c"] = st["c"]
+        out[f"step{k}_hist"] = st["hist"]
+        out[f"step{k}_stats"] = np.array([st["converged"], st["iterations"], st["abs_err"], st["rel_err"]])
+    np.savez_compressed(f"{OUT}/cahn_hilliard_{name}.npz", **out)
+
+
 def main():
     assert os.path.isdir(REF_DATA), "reference tree not mounted"
     orc.build()
     tmp = tempfile.mkdtemp()
+    make_cahn_hilliard(tmp)
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ch":
+        return
     for name in ("square_nb", "rectangle"):
         prefix = f"{REF_DATA}/{name}.1."
         mesh_bin, cg_bin = f"{tmp}/{name}.bin", f"{tmp}/{name}_cg.bin"

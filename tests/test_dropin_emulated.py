@@ -1,0 +1,105 @@
+"""CPU tests of the C++23 host layer (Storm::DeviceVector, DevExpr, traced B200::map, B200::div_grad, the drop-in TU):
+the product's drop-in translation unit, linked against a host-executing stand-in of the C ABI (oracle/emu), must issue
+exactly the reference's arithmetic. With sequential reductions its results equal the reference's own run bit for bit:
+
+  * all ten solver templates + JFNK on Storm::DeviceVector  ==  the same headers on a host vector (oracle/_ref);
+  * the playground's Cahn-Hilliard time step (Playground.cpp:133-175) on the device types  ==  the committed golden
+    fixture, produced by the reference's own mesh reader / CellField / map / CgSolver (tests/golden/make_golden.py).
+
+The GPU tests (tests/test_gpu_playground.py, test_gpu_dropin.py) show that libstormb200.so honours the same contract.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rhs
+from oracle import emu, orc
+
+pytestmark = pytest.mark.skipif(not (emu.available() and orc.have_ref()),
+                                reason="oracle/_ref (emulated drop-in + reference build) needs the StormRuler sources at build time")
+
+DT, ITERS, RTOL = 0.05, 300, 1e-10
+
+
+def same(a, b):
+    return (a.converged == b.converged and a.iterations == b.iterations and np.array_equal(a.x, b.x)
+            and np.array_equal(a.hist, b.hist) and np.array_equal(a.trace, b.trace) and a.n_apply == b.n_apply)
+
+
+@pytest.mark.parametrize("solver", orc.REF_SOLVERS + orc.REF_NONLINEAR)
+def test_reference_templates_on_device_vector_issue_the_reference_arithmetic(square_nb, solver):
+    op = orc.FaceOp(square_nb, prefill=1, dt=-DT)
+    b = rhs(square_nb.n_cells)
+    kw = dict(num_iterations=60 if solver == "richardson" else ITERS, abs_tol=0.0, rel_tol=RTOL)
+    want = orc.ref_solve(solver, op, b, **kw)
+    got = emu.solve(solver, emu.EmuOp(op), b, **kw)
+    assert got.iterations > 10 and same(got, want)
+
+
+@pytest.mark.parametrize("mode", [orc.RED_SEQ, orc.RED_TREE])
+def test_nonsymmetric_operator_and_both_reduction_modes(square_nb, mode):
+    rng = np.random.default_rng(5)
+    un, bun = rng.standard_normal(square_nb.n_faces), rng.standard_normal(square_nb.n_bfaces)
+    op = orc.ConvDiffOp(square_nb, 0.02, un, bun)
+    b = rhs(square_nb.n_cells)
+    for solver in ("bicgstab", "gmres", "idrs", "tfqmr"):
+        kw = dict(num_iterations=80, abs_tol=0.0, rel_tol=1e-12, mode=mode, num_inner=20 if solver == "gmres" else 0)
+        assert same(emu.solve(solver, emu.EmuOp(op), b, **kw), orc.ref_solve(solver, op, b, **kw)), solver
+
+
+@pytest.mark.parametrize("side", ["left", "right"])
+def test_preconditioner_slot(square_nb, side):
+    """Storm::JacobiPreconditioner in the reference's pre_op slot == the same headers with x / diag as a callback."""
+    op = orc.FaceOp(square_nb, prefill=0, dt=-1.0, dirichlet=True)
+    _, _, _, _, diag = op.rows_coef()
+    diag = diag[:square_nb.n_cells].copy()
+    b = rhs(square_nb.n_cells)
+    for solver in ("cg", "bicgstab", "fgmres"):
+        kw = dict(num_iterations=120, abs_tol=0.0, rel_tol=1e-10, pre_side=side)
+        want = orc.ref_solve(solver, op, b, pre=orc.JacobiOp(diag), **kw)
+        got = emu.solve(solver, emu.EmuOp(op, diag=diag), b, precond="jacobi", **kw)
+        assert same(got, want), solver
+        assert emu.counts()["jacobi"] > 0
+
+
+def test_host_layer_rejects_misuse():
+    assert emu.selftest_errors() == 3
+
+
+def test_playground_cahn_hilliard_step_equals_the_reference_run(square_nb):
+    """Two time steps of the playground's Cahn-Hilliard solver: 2 x 2000 CG iterations on the affine 4th-order
+    operator (the reference's CG does not converge on it within its 2000-iteration cap -- that IS the reference's
+    behaviour, and the iterate is reproduced bit for bit)."""
+    g = load_golden("cahn_hilliard_square_nb.npz")
+    faces = emu.EmuOp(orc.FaceOp(square_nb.without_boundary(), prefill=0, dt=0.0))
+    c = g["c0"]
+    for k in range(int(g["num_steps"])):
+        res, w_hat = emu.cahn_hilliard_step(faces, c)
+        conv, its, abs_err, rel_err = g[f"step{k}_stats"]
+        assert res.converged == bool(conv) and res.iterations == int(its) == 2000
+        assert res.abs_err == abs_err and res.rel_err == rel_err
+        assert np.array_equal(res.hist, g[f"step{k}_hist"])
+        assert np.array_equal(res.x, g[f"step{k}_c"])
+        # statement stream of one step: per operator evaluation 2 element-wise statements + 2 stormDivGrad; per CG
+        # iteration 3 updates + 2 dots; init: f, c_hat, residual, <r,r>, p
+        n_op = res.n_apply
+        assert n_op == its + 1
+        assert emu.counts() == dict(eval=2 * n_op + 3 * its + 4, fill=0, copy=0, dot=2 * its + 1, norm=0, apply=0,
+                                    accumulate=2 * n_op, jacobi=0)
+        c = res.x
+
+
+def test_oracle_restatement_of_the_cahn_hilliard_step_is_pinned(square_nb):
+    """oracle.orc.cahn_hilliard_step (numpy statements + the C face loop, the checker of the GPU test) against the
+    same golden fixture, and the traced dF/dc against its numpy restatement."""
+    g = load_golden("cahn_hilliard_square_nb.npz")
+    res = orc.cahn_hilliard_step(square_nb, g["c0"])
+    assert np.array_equal(res.x, g["step0_c"]) and np.array_equal(res.hist, g["step0_hist"])
+    op = orc.CahnHilliardOp(square_nb, g["c0"])
+    c_restated = orc.solve("cg", op, op.c, x0=op.c)   # plain-C CG restatement instead of the reference template
+    assert np.array_equal(c_restated.x, g["step0_c"])
+    # reduction order: the GPU tree changes the last bits of every dot; over 2000 non-converging CG iterations the
+    # iterate stays within 1e-11 of the sequential run, the residual history within 1e-10 for the first 80 iterations (1.3e-8 at worst over all 2000)
+    tree = orc.cahn_hilliard_step(square_nb, g["c0"], mode=orc.RED_TREE)
+    assert np.linalg.norm(tree.x - g["step0_c"]) <= 1e-10 * np.linalg.norm(g["step0_c"])
+    rel = np.abs(tree.hist - g["step0_hist"]) / g["step0_hist"]
+    assert rel[:80].max() < 1e-10 and rel.max() < 1e-7

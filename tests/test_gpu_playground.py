@@ -1,0 +1,110 @@
+"""GPU parity of the playground's own caller of the path: `stormDivGrad(mesh, u, dt, c)` as it
+is called there -- accumulating onto a pre-filled field (sb_apply_accumulate) -- the traced `map(dF_dc, c)`, and one
+whole Cahn-Hilliard time step (Playground.cpp:133-175) through the C++ drop-in on the device.
+
+Checker: the oracle restatement, pinned on the CPU against the reference's own run of the same step
+(tests/test_dropin_emulated.py, tests/golden/cahn_hilliard_square_nb.npz).
+"""
+import numpy as np
+import pytest
+
+import stormruler_b200 as sb
+from conftest import load_golden
+from oracle import orc
+from stormruler_b200 import dropin
+from stormruler_b200 import mesh as sbmesh
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_state(n, seed):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal(n), rng.standard_normal(n)
+
+
+@pytest.mark.parametrize("dirichlet", [False, True])
+@pytest.mark.parametrize("name", ["square_nb", "rectangle"])
+def test_div_grad_accumulates_like_the_face_loop(ctx, name, dirichlet, request):
+    m = request.getfixturevalue(name)
+    cpu = orc.FaceOp(m if dirichlet else m.without_boundary(), prefill=0, dt=0.0, dirichlet=dirichlet)
+    # the operator's own prefill / dt must not matter
+    gpu = sb.FvmOperator(ctx, m, prefill=1, dt=123.0, form=sb.FORM_FAITHFUL, dirichlet=dirichlet)
+    c, u0 = _random_state(m.n_cells, 3)
+    for dt in (-1.0e-4, -1.0e-3, 0.37):
+        want = cpu.divgrad_accumulate(dt, c, u0.copy())
+        u = ctx.vector(u0)
+        gpu.div_grad(u, dt, ctx.vector(c))
+        assert np.array_equal(u.numpy(), want), (name, dirichlet, dt)
+    # twice in a row accumulates twice (the second call starts from the first one's result)
+    u = ctx.vector(u0)
+    cv = ctx.vector(c)
+    gpu.div_grad(u, -0.5, cv)
+    gpu.div_grad(u, -0.5, cv)
+    want = cpu.divgrad_accumulate(-0.5, c, cpu.divgrad_accumulate(-0.5, c, u0.copy()))
+    assert np.array_equal(u.numpy(), want)
+
+
+def test_div_grad_on_a_3d_mesh_and_plain_apply_unchanged(ctx):
+    """Tetrahedra (rows up to 4 wide, Dirichlet ghosts), sizes off the 2048-row tile; sb_apply on the same operator
+    still starts from x (prefill 1) -- the per-call override must not leak into the stored operator."""
+    m = sbmesh.Mesh.box(sbmesh.CELL_TET, 9, 8, 7, jitter=0.2)   # 3024 Kuhn tetrahedra, shuffled
+    m.renumber_rcm()
+    cpu_acc = orc.FaceOp(m, prefill=0, dt=0.0, dirichlet=True)
+    cpu_mul = orc.FaceOp(m, prefill=1, dt=-0.05, dirichlet=True)
+    gpu = sb.FvmOperator(ctx, m, prefill=1, dt=-0.05, form=sb.FORM_FAITHFUL, dirichlet=True)
+    c, u0 = _random_state(m.n_cells, 4)
+    cv, u, y = ctx.vector(c), ctx.vector(u0), ctx.zeros(m.n_cells)
+    gpu.mul(y, cv)
+    assert np.array_equal(y.numpy(), cpu_mul.apply(c))
+    gpu.div_grad(u, -2.5e-3, cv)
+    assert np.array_equal(u.numpy(), cpu_acc.divgrad_accumulate(-2.5e-3, c, u0.copy()))
+    gpu.mul(y, cv)
+    assert np.array_equal(y.numpy(), cpu_mul.apply(c))
+
+
+def test_div_grad_needs_the_faithful_form_and_distinct_vectors(ctx, square_nb):
+    coef = sb.FvmOperator(ctx, square_nb, prefill=1, dt=-0.05, form=sb.FORM_COEF)
+    u, c = ctx.zeros(square_nb.n_cells), ctx.zeros(square_nb.n_cells)
+    with pytest.raises(sb.StormB200Error, match="faithful"):
+        coef.div_grad(u, -1.0, c)
+    faithful = sb.FvmOperator(ctx, square_nb, prefill=0, dt=0.0, form=sb.FORM_FAITHFUL)
+    with pytest.raises(sb.StormB200Error, match="alias"):
+        faithful.div_grad(u, -1.0, u)
+
+
+def test_traced_map_program_of_dF_dc(ctx):
+    """The postfix program B200::map records for the playground's dF_dc (2.0*c*(c-1.0)*(2.0*c-1.0), constants
+    deduplicated): S0 V0 MUL V0 S1 SUB MUL S0 V0 MUL S1 SUB MUL -- run through sb_eval's run-time interpreter."""
+    rng = np.random.default_rng(8)
+    c = rng.random(5000)
+    S0, S1, V0 = sb.capi.OP_SCAL0, sb.capi.OP_SCAL0 + 1, sb.capi.OP_VEC0
+    MUL, SUB = sb.capi.OP_MUL, sb.capi.OP_SUB
+    cv, f = ctx.vector(c), ctx.zeros(c.shape[0])
+    ctx.eval(f, sb.ASSIGN, [S0, V0, MUL, V0, S1, SUB, MUL, S0, V0, MUL, S1, SUB, MUL], [cv], [2.0, 1.0])
+    assert np.array_equal(f.numpy(), orc.ch_dF_dc(c))
+
+
+def test_playground_cahn_hilliard_step_on_the_device(ctx, square_nb):
+    """One whole time step (2000 CG iterations of the reference's CgSolver template on DeviceVector, each with two
+    element-wise statements and two accumulating stormDivGrad applies): bit-identical to the oracle with the GPU
+    reduction tree, and within the stated tolerances of the reference's own sequential run (golden fixture)."""
+    if not dropin.available():
+        pytest.fail("libstorm_dropin.so is missing on the GPU box (it is built where the reference tree is mounted)")
+    g = load_golden("cahn_hilliard_square_nb.npz")
+    n = square_nb.n_cells
+    faces = sb.FvmOperator(ctx, square_nb, prefill=0, dt=0.0, form=sb.FORM_FAITHFUL)
+    c, c_hat, w_hat = ctx.vector(g["c0"]), ctx.zeros(n), ctx.zeros(n)
+    got = dropin.cahn_hilliard_step(faces, c, c_hat, w_hat)
+    want = orc.cahn_hilliard_step(square_nb, g["c0"], mode=orc.RED_TREE)
+    assert got.iterations == want.iterations == 2000 and got.converged == want.converged
+    assert np.array_equal(got.trace, want.trace), "reduction trace differs from the oracle (GPU tree)"
+    assert np.array_equal(got.hist, want.hist)
+    assert np.array_equal(c_hat.numpy(), want.x)
+    assert got.n_apply == 2001
+    # against the reference's own run (sequential reductions): tolerances of the north star; the history of this
+    # non-converging 2000-iteration CG drifts apart slowly with the reduction order (1e-10 for the first 80 iterations, 1.3e-8 at worst)
+    gold_c, gold_h = g["step0_c"], g["step0_hist"]
+    assert np.linalg.norm(c_hat.numpy() - gold_c) <= 1e-8 * np.linalg.norm(gold_c)
+    rel = np.abs(got.hist - gold_h) / gold_h
+    assert rel[:80].max() < 1e-10 and rel.max() < 1e-7
+    assert np.isfinite(w_hat.numpy()).all()   # the chemical potential of the last operator evaluation
