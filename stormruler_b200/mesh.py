@@ -201,6 +201,176 @@ class HexLattice:
         return nx * ny if nz > 1 else (nx if ny > 1 else (1 if nx > 1 else 0))
 
 
+class HexLatticeSlab:
+    """One rank's local mesh of a HexLattice split into contiguous slabs of the lattice cell order (the split of
+    SB_PART_SLAB: rank r owns cells [n*r//P, n*(r+1)//P)), built DIRECTLY from the lattice arithmetic: no global mesh, no
+    partitioner, work and memory proportional to the slab. Every array is what
+    `Partition(Mesh.from_faces(HexLattice(...)), P, PART_SLAB).local(rank)` produces, bit for bit (local order
+    [interior owned | boundary owned | pad | halo by owner and id], faces in ascending global face index with their
+    global numbers, halo send / receive maps) -- tests/test_mesh_host.py compares them. For config 4 at full size
+    (49.8 M hexahedra on 8 GPUs: building and partitioning the global mesh costs minutes and 29 GB on rank 0).
+    `local` is a LocalArrays (the `local` argument of multigpu.DistOperator), `info` the partition summary."""
+
+    def __init__(self, nx: int, ny: int, nz: int, rank: int, n_parts: int):
+        n = nx * ny * nz
+        assert n < 2 ** 31 - 4096 and 0 <= rank < n_parts
+        self.dims, self.n_global, self.rank, self.n_parts = (nx, ny, nz), n, rank, n_parts
+        self.bounds = np.array([n * p // n_parts for p in range(n_parts + 1)], np.int64)
+        lo, hi = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.lo, self.hi = lo, hi
+        step = (1, nx, nx * ny)
+        sxy = nx * ny
+        hx, hy, hz = 1.0 / nx, 1.0 / ny, 1.0 / nz
+        area = np.array([hy * hz, hx * hz, hx * hy])
+        dist = np.array([hx, hy, hz])
+        vol = hx * hy * hz
+
+        # owned cells: interior first, then those with a face to another slab; both in ascending global id
+        own = np.arange(lo, hi, dtype=np.int64)
+        boundary = np.zeros(hi - lo, bool)
+        for a in range(3):
+            has_up, has_dn = self._has(own, a, +1), self._has(own, a, -1)
+            boundary |= (has_up & (own + step[a] >= hi)) | (has_dn & (own - step[a] < lo))
+        n_owned, n_interior = hi - lo, int((~boundary).sum())
+        owned = np.concatenate([own[~boundary], own[boundary]])
+        l_owned = np.empty(n_owned, np.int64)
+        l_owned[~boundary] = np.arange(n_interior)
+        l_owned[boundary] = n_interior + np.arange(n_owned - n_interior)
+        halo = self._halo_of(lo, hi)                      # ascending id == (owner rank, id) order for slabs
+        halo_base = _pad_tile(n_owned)
+
+        def g2l(g):
+            g = np.asarray(g, np.int64)
+            inside = (g >= lo) & (g < hi)
+            out = np.empty(g.shape, np.int64)
+            out[inside] = l_owned[g[inside] - lo]
+            out[~inside] = halo_base + np.searchsorted(halo, g[~inside])
+            return out
+
+        # faces with an owned end, in ascending global face index: created cell by cell (x+, y+, z+) by the lower cell
+        creators = np.arange(max(0, lo - sxy), hi, dtype=np.int64)
+        present = np.stack([self._has(creators, a, +1) for a in range(3)], axis=1)          # [m, 3]
+        nbr = creators[:, None] + np.array(step, np.int64)[None, :]
+        c_own = ((creators >= lo) & (creators < hi))[:, None]
+        keep = present & (c_own | ((nbr >= lo) & (nbr < hi)))
+        pos = np.cumsum(present, axis=1) - present                                           # index among the cell's faces
+        fglob = (self._faces_before(creators)[:, None] + pos)[keep]
+        owner_b = np.broadcast_to(creators[:, None], keep.shape)[keep]
+        nbr_k = nbr[keep]
+        axis = np.broadcast_to(np.arange(3)[None, :], keep.shape)[keep]
+        face_cell = np.stack([g2l(owner_b), g2l(nbr_k)], axis=1).astype(np.int32)
+
+        # halo exchange maps
+        part_of = lambda g: np.searchsorted(self.bounds, g, side="right") - 1  # noqa: E731
+        halo_part = part_of(halo)
+        nbr_rank = np.unique(halo_part)
+        recv_ptr = np.concatenate([[0], np.cumsum([(halo_part == q).sum() for q in nbr_rank])]).astype(np.int64)
+        o_in, n_in = (owner_b >= lo) & (owner_b < hi), (nbr_k >= lo) & (nbr_k < hi)
+        send, send_ptr, send_dst = [], [0], []
+        for q in nbr_rank:
+            qlo, qhi = int(self.bounds[q]), int(self.bounds[q + 1])
+            mine = np.concatenate([owner_b[o_in & (nbr_k >= qlo) & (nbr_k < qhi)],
+                                   nbr_k[n_in & (owner_b >= qlo) & (owner_b < qhi)]])
+            cells = np.unique(mine)
+            send.append(g2l(cells))
+            send_ptr.append(send_ptr[-1] + len(cells))
+            q_halo = self._halo_of(qlo, qhi)
+            send_dst.append(_pad_tile(qhi - qlo) + int((q_halo < lo).sum()))
+
+        # boundary faces of owned cells, per cell in local-face order z-, y-, x+, y+, x-, z+
+        i, j, k = own % nx, (own // nx) % ny, own // sxy
+        bnd = np.stack([k == 0, j == 0, i == nx - 1, j == ny - 1, i == 0, k == nz - 1], axis=1)
+        baxis = np.array([2, 1, 0, 1, 0, 2])
+        bpos = np.cumsum(bnd, axis=1) - bnd
+        bglob = (self._bfaces_before(own)[:, None] + bpos)[bnd]
+        bcell = np.broadcast_to(own[:, None], bnd.shape)[bnd]
+        blf = np.broadcast_to(np.arange(6)[None, :], bnd.shape)[bnd]
+
+        cell_vol = np.ones(halo_base + len(halo))
+        cell_vol[:n_owned] = vol
+        cell_vol[halo_base:] = vol
+        scalars = dict(rank=rank, n_parts=n_parts, n_owned=n_owned, n_interior=n_interior, n_halo=len(halo),
+                       halo_base=halo_base, n_cells=halo_base + len(halo), n_faces=len(fglob), n_bfaces=len(bglob),
+                       n_nbr=len(nbr_rank))
+        arrays = dict(local_to_global=np.concatenate([owned, halo]), face_cell=face_cell.reshape(-1),
+                      face_area=area[axis], face_dist=dist[axis], cell_vol=cell_vol, bface_cell=g2l(bcell),
+                      bface_area=area[baxis[blf]], bface_dist=dist[baxis[blf]], face_global=fglob, nbr_rank=nbr_rank,
+                      send_ptr=np.array(send_ptr), recv_ptr=recv_ptr,
+                      send_idx=np.concatenate(send) if send else np.zeros(0), send_dst=np.array(send_dst),
+                      bface_global=bglob)
+        self.local = LocalArrays(scalars, arrays)
+        self.cell_vol_value = vol
+
+    # -- lattice arithmetic --------------------------------------------------------------------------------------
+    def _has(self, g, axis: int, sign: int):
+        """Does cell g have a lattice neighbour along `axis` in direction `sign`?"""
+        nx, ny, nz = self.dims
+        c = (g % nx, (g // nx) % ny, g // (nx * ny))[axis]
+        return c < (nx, ny, nz)[axis] - 1 if sign > 0 else c > 0
+
+    def _halo_of(self, lo: int, hi: int) -> np.ndarray:
+        """Ascending global ids of the cells outside [lo, hi) that share a face with a cell inside."""
+        nx, ny, _ = self.dims
+        step, sxy = (1, nx, nx * ny), nx * ny
+        below = np.arange(max(0, lo - sxy), lo, dtype=np.int64)
+        above = np.arange(hi, min(self.n_global, hi + sxy), dtype=np.int64)
+        kb, ka = np.zeros(below.shape, bool), np.zeros(above.shape, bool)
+        for a in range(3):
+            t = below + step[a]
+            kb |= self._has(below, a, +1) & (t >= lo) & (t < hi)
+            t = above - step[a]
+            ka |= self._has(above, a, -1) & (t >= lo) & (t < hi)
+        return np.concatenate([below[kb], above[ka]])
+
+    def _faces_before(self, c):
+        """Number of interior faces created by the cells with id < c (each creates its x+, y+, z+ faces)."""
+        nx, ny, nz = self.dims
+        i, j, k = c % nx, (c // nx) % ny, c // (nx * ny)
+        fx = (c // nx) * (nx - 1) + i
+        fy = k * nx * (ny - 1) + j * nx + np.where(j < ny - 1, i, 0)
+        fz = np.minimum(c, (nz - 1) * nx * ny)
+        return fx + fy + fz
+
+    def _bfaces_before(self, c):
+        """Number of boundary faces of the cells with id < c."""
+        nx, ny, nz = self.dims
+        sxy = nx * ny
+        i, j, k = c % nx, (c // nx) % ny, c // sxy
+        return (np.minimum(c, sxy) + np.maximum(0, c - (nz - 1) * sxy)            # k == 0, k == nz-1
+                + k * nx + np.where(j > 0, nx, i)                                 # j == 0
+                + k * nx + np.where(j == ny - 1, i, 0)                            # j == ny-1
+                + c // nx + (i > 0)                                               # i == 0
+                + c // nx)                                                        # i == nx-1
+
+    # -- what the drivers need besides the local mesh ---------------------------------------------------------------
+    def owned_centers(self) -> np.ndarray:
+        nx, ny, nz = self.dims
+        g = self.local.owned_global.astype(np.int64)
+        return np.stack([(g % nx + 0.5) / nx, ((g // nx) % ny + 0.5) / ny, (g // (nx * ny) + 0.5) / nz], axis=1)
+
+    def info(self) -> dict:
+        """Partition summary (the keys of sb_part_info) without building any other rank's mesh."""
+        P, b = self.n_parts, self.bounds
+        owned = np.diff(b)
+        halos = np.array([len(self._halo_of(int(b[r]), int(b[r + 1]))) for r in range(P)])
+        cap = max(_pad_tile(int(owned[r])) + _pad_tile(max(int(halos[r]), 1)) for r in range(P))
+        nx, ny, _ = self.dims
+        sxy = nx * ny
+        cand = np.unique(np.concatenate([np.arange(max(0, int(B) - sxy), int(B), dtype=np.int64) for B in b[1:-1]]
+                                        + [np.zeros(0, np.int64)]))
+        part_of = lambda g: np.searchsorted(b, g, side="right") - 1  # noqa: E731
+        cut = 0
+        for a, st in enumerate((1, nx, sxy)):
+            ok = self._has(cand, a, +1)
+            cut += int((part_of(cand[ok]) != part_of(cand[ok] + st)).sum())
+        return dict(n_cells=self.n_global, edge_cut=cut, min_owned=int(owned.min()), max_owned=int(owned.max()),
+                    max_halo=int(halos.max()), vec_capacity=int(cap))
+
+
+def _pad_tile(n: int) -> int:
+    return -(-int(n) // 2048) * 2048   # the kernels' 2048-row CTA tile (include/stormb200.h: sb_local_mesh.halo_base)
+
+
 class PolyMesh:
     """Synthetic polyhedral mesh for the dual-polyhedra leg of the apply sweep:
     the Voronoi tessellation of a body-centred cubic lattice, i.e. truncated octahedra with 14 faces

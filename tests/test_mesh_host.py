@@ -7,7 +7,8 @@ import pytest
 from oracle import mesh_oracle as mo
 from oracle import orc
 from stormruler_b200 import capi
-from stormruler_b200.mesh import CELL_HEX, CELL_TET, HexLattice, Mesh, Partition, PolyMesh
+from stormruler_b200.mesh import (CELL_HEX, CELL_TET, LOCAL_ARRAYS, LOCAL_SCALARS, HexLattice, HexLatticeSlab, Mesh,
+                                  Partition, PolyMesh)
 
 KIND = {"tet": CELL_TET, "hex": CELL_HEX}
 SOA_KEYS = ("face_cell", "face_area", "face_dist", "cell_vol", "bface_cell", "bface_area", "bface_dist")
@@ -357,6 +358,30 @@ def test_hex_lattice_face_list_matches_the_node_based_generator(dims):
     assert np.abs(ya - yb).max() <= 1e-12 * max(np.abs(yb).max(), 1.0)
     h = Mesh.from_faces(a, a.cell_centers())
     assert np.array_equal(h.face_cell, a.face_cell) and h.bandwidth == a.bandwidth
+
+
+@pytest.mark.parametrize("dims,n_parts", [((7, 5, 6), 3), ((4, 4, 4), 2), ((9, 3, 2), 4), ((16, 16, 16), 8),
+                                          ((5, 1, 1), 2), ((30, 20, 10), 5), ((3, 3, 40), 8), ((13, 11, 3), 7),
+                                          ((6, 6, 6), 1)])
+def test_rank_local_lattice_slab_equals_partitioning_the_global_mesh(dims, n_parts):
+    """HexLatticeSlab builds one rank's local mesh from lattice arithmetic alone (config 4 at full size: no rank holds
+    the 49.8 M-cell mesh). Every scalar and every array -- local order, global face numbers, halo send/receive maps,
+    boundary faces -- must equal what the general path produces: the lattice as a face-list mesh handle, split by
+    SB_PART_SLAB, sb_part_local. Slabs thinner than one lattice plane (neighbours beyond the adjacent ranks), slab
+    boundaries inside a plane and inside a row, and a single part are all covered."""
+    lat = HexLattice(*dims)
+    part = Partition(Mesh.from_faces(lat, lat.cell_centers()), n_parts, capi.PART_SLAB)
+    for r in range(n_parts):
+        want, slab = part.local(r), HexLatticeSlab(*dims, r, n_parts)
+        for k in LOCAL_SCALARS:
+            assert int(getattr(slab.local, k)) == int(getattr(want, k)), (r, k)
+        for k, dt in LOCAL_ARRAYS:
+            got, ref = np.asarray(getattr(slab.local, k)).reshape(-1), np.asarray(getattr(want, k)).reshape(-1)
+            assert got.dtype == dt and got.shape == ref.shape and np.array_equal(got, ref), (r, k)
+        assert np.array_equal(slab.owned_centers(), lat.cell_centers()[want.owned_global])
+    info = slab.info()
+    for k, v in info.items():
+        assert int(getattr(part.info, k)) == v, k
 
 
 def _tiny_face_list(n, pairs, bcells, seed=0):
