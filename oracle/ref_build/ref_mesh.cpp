@@ -19,6 +19,9 @@
 //       Runs the reference CgSolver on CellField with y = x - dt * div grad x written as the
 //       playground writes it, b[k] = sin(0.37 k), x0 = 0 (SURVEY.md 8d "Config 1");
 //       dumps b, x, the residual history and the solver's final public fields.
+//   ref_mesh_tool vtk <prefix> <out.vtk>
+//       The playground's save_vtk (Playground.cpp:65-109) on the reference's mesh with one cell field
+//       c[k] = sin(0.37 k): the file a drop-in has to reproduce (node order, per-cell node lists, number format).
 //   ref_mesh_tool ch <prefix> <num_steps> <out.bin>
 //       The playground's own caller of the path, statement for statement (Playground.cpp:133-175 and the
 //       initial condition / swap of :176-210): c[cell] = rand()/RAND_MAX (glibc, default seed), then per
@@ -42,6 +45,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <limits>
 #include <memory>
 #include <string>
 #include <vector>
@@ -175,6 +181,44 @@ int cmd_cg(const std::string& prefix, double dt, size_t num_iterations, double r
   return 0;
 }
 
+// save_vtk, statement order of Playground.cpp:65-109 (a file-local template of the app, restated like div_grad).
+int cmd_vtk(const std::string& prefix, const char* out) {
+  const auto mesh_ptr = load(prefix);
+  const RefMesh& mesh = *mesh_ptr;
+  RefField c{mesh};
+  for (size_t k = 0; k < mesh.num_cells(); ++k) c(k) = std::sin(0.37 * (double) k);
+  std::ofstream file(out);
+  file << std::setprecision(std::numeric_limits<real_t>::digits10 + 1);
+  file << "# vtk DataFile Version 2.0" << std::endl;
+  file << "# Generated by Feathers/StormRuler/Mesh2VTK" << std::endl;
+  file << "ASCII" << std::endl;
+  file << "DATASET UNSTRUCTURED_GRID" << std::endl;
+  file << "POINTS " << mesh.num_nodes() << " double" << std::endl;
+  std::ranges::for_each(mesh.nodes(), [&](auto node) {
+    const auto& pos = node.position();
+    file << pos(0) << " " << pos(1) << " " << 0.0 << std::endl;
+  });
+  file << std::endl;
+  size_t sum = 0;
+  std::ranges::for_each(mesh.interior_cells(), [&](auto cell) { sum += cell.nodes().size() + 1; });
+  file << "CELLS " << mesh.num_cells({}) << " " << sum << std::endl;
+  std::ranges::for_each(mesh.interior_cells(), [&](auto cell) {
+    file << cell.nodes().size() << " ";
+    cell.for_each_node([&](NodeIndex node_index) { file << node_index << " "; });
+    file << std::endl;
+  });
+  file << std::endl;
+  file << "CELL_TYPES " << mesh.num_cells({}) << std::endl;
+  std::ranges::for_each(mesh.interior_cells(), [&](auto cell) { file << "5" << std::endl; });
+  file << std::endl;
+  file << "CELL_DATA " << mesh.num_cells({}) << std::endl;
+  file << "SCALARS c double 1" << std::endl;
+  file << "LOOKUP_TABLE default" << std::endl;
+  std::ranges::for_each(mesh.interior_cells(), [&](auto cell) { file << c[cell] << std::endl; });
+  file << std::endl;
+  return 0;
+}
+
 // One Cahn-Hilliard time step, Playground.cpp:133-175 (the CgSolver is constructed here instead of inside
 // solve<CgSolver>, Solver.hpp:261-265, so that its public progress fields can be sampled; same defaults).
 constexpr double ch_tau = 1.0e-3, ch_Gamma = 1.0e-4, ch_sigma = 2.0; // Playground.cpp:113
@@ -245,11 +289,13 @@ int main(int argc, char** argv) {
   if (argc >= 7 && std::strcmp(argv[1], "cg") == 0)
     return cmd_cg(argv[2], std::atof(argv[3]), (size_t) std::atoll(argv[4]), std::atof(argv[5]),
                   argv[6]);
+  if (argc >= 4 && std::strcmp(argv[1], "vtk") == 0) return cmd_vtk(argv[2], argv[3]);
   if (argc >= 5 && std::strcmp(argv[1], "ch") == 0)
     return cmd_ch(argv[2], (size_t) std::atoll(argv[3]), argv[4]);
   std::fprintf(stderr,
                "usage: ref_mesh_tool export <prefix> <out.bin>\n"
                "       ref_mesh_tool cg <prefix> <dt> <num_iterations> <rel_tol> <out.bin>\n"
+               "       ref_mesh_tool vtk <prefix> <out.vtk>\n"
                "       ref_mesh_tool ch <prefix> <num_steps> <out.bin>\n");
   return 1;
 }

@@ -908,6 +908,12 @@ int sb_mesh_read_tetgen_2d(const char* path_prefix, sb_mesh** out) {
   if (rc != SB_OK) return rc;
   (*out)->pair_label.assign((size_t) (soa.n_faces + soa.n_bfaces), 0);
   std::copy(labels.begin(), labels.end(), (*out)->pair_label.begin() + soa.n_faces);
+  // keep the nodes and the cells' node lists (file order: what mesh.nodes() / cell.for_each_node visit) for
+  // sb_mesh_write_vtk; cell renumbering permutes `cells` like the node lists of the 3-D meshes
+  (*out)->npc = 3, (*out)->n_nodes = n_nodes;
+  (*out)->xyz.assign(3 * (size_t) n_nodes, 0.0);
+  for (int64_t k = 0; k < n_nodes; ++k) (*out)->xyz[3 * (size_t) k] = xy[2 * (size_t) k], (*out)->xyz[3 * (size_t) k + 1] = xy[2 * (size_t) k + 1];
+  (*out)->cells = tri;
   return SB_OK;
 }
 
@@ -965,12 +971,14 @@ int sb_mesh_face_normals(const sb_mesh* m, double* h_fn, double* h_bn) {
 // Legacy-VTK dump in the file grammar of the playground's save_vtk (Playground.cpp:65-109): same header lines, 16
 // significant digits (digits10 + 1), "POINTS n double", count-prefixed node lists under CELLS, one type per cell under
 // CELL_TYPES, one "SCALARS <name> double 1 / LOOKUP_TABLE default" block per field under CELL_DATA. The reference
-// writes 2-D triangles (z = 0, type 5); here the points are 3-D and the types are VTK_TETRA (10) / VTK_HEXAHEDRON (12),
-// whose node orders are those of Shape.hpp:559-606 / 803-818.
+// writes 2-D triangles (z = 0, type 5): a mesh read by sb_mesh_read_tetgen_2d produces that file byte for byte
+// (tests/golden/vtk_square_nb_head.txt); for the 3-D meshes the types are VTK_TETRA (10) / VTK_HEXAHEDRON (12), whose
+// node orders are those of Shape.hpp:559-606 / 803-818.
 int sb_mesh_write_vtk(const sb_mesh* m, const char* path, int n_fields, const char* const* names,
                       const double* const* h_fields) {
   SBM_REQUIRE(m != nullptr && path != nullptr && n_fields >= 0, "null argument");
-  SBM_REQUIRE(m->kind == SB_CELL_TET || m->kind == SB_CELL_HEX, "a face-list mesh has no nodes to write");
+  SBM_REQUIRE(m->kind == SB_CELL_TET || m->kind == SB_CELL_HEX || (m->npc == 3 && !m->cells.empty()),
+              "a face-list mesh has no nodes to write");
   SBM_REQUIRE(n_fields == 0 || (names != nullptr && h_fields != nullptr), "null field arrays");
   for (int f = 0; f < n_fields; ++f) SBM_REQUIRE(names[f] != nullptr && h_fields[f] != nullptr, "null field");
   std::ofstream file(path);
@@ -995,7 +1003,8 @@ int sb_mesh_write_vtk(const sb_mesh* m, const char* path, int n_fields, const ch
   }
   file << '\n';
   file << "CELL_TYPES " << m->n_cells << '\n';
-  const char* type = m->kind == SB_CELL_TET ? "10" : "12";
+  // VTK_TRIANGLE for the 2-D meshes of sb_mesh_read_tetgen_2d: the playground's own output (Playground.cpp:97-99)
+  const char* type = m->kind == SB_CELL_TET ? "10" : (m->kind == SB_CELL_HEX ? "12" : "5");
   for (int64_t c = 0; c < m->n_cells; ++c) file << type << '\n';
   file << '\n';
   file << "CELL_DATA " << m->n_cells << '\n';

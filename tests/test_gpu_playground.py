@@ -108,3 +108,24 @@ def test_playground_cahn_hilliard_step_on_the_device(ctx, square_nb):
     rel = np.abs(got.hist - gold_h) / gold_h
     assert rel[:80].max() < 1e-10 and rel.max() < 1e-7
     assert np.isfinite(w_hat.numpy()).all()   # the chemical potential of the last operator evaluation
+
+
+def test_playground_driver_end_to_end(tmp_path):
+    """scripts/playground_cahn_hilliard.py: mesh files -> reader -> upload -> two time steps -> VTK output, as a
+    separate process (the application a reference user would run)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "playground_cahn_hilliard.py"), "--generate", "24", "16",
+                          "--steps", "2", "--max-iterations", "60", "--out", str(tmp_path)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["cells"] == 2 * 24 * 16 and [r["cg_iterations"] for r in line["per_step"]] == [60, 60]
+    assert 0.0 < line["c_min"] < line["c_mean"] < line["c_max"] < 1.0
+    assert out.stdout.count("time = ") == 3
+    for k in range(3):
+        text = (tmp_path / f"fields-{k:05d}.vtk").read_text()
+        assert text.startswith("# vtk DataFile Version 2.0\n") and "SCALARS c double 1" in text

@@ -567,6 +567,69 @@ def test_tetgen_2d_reader_reproduces_the_reference_mesh_classes(tmp_path, name):
     assert Partition(mesh, 3, capi.PART_METIS).info.edge_cut > 0
 
 
+@pytest.mark.parametrize("name", ["square_nb", "rectangle"])
+def test_vtk_of_a_2d_mesh_is_the_playground_file_byte_for_byte(tmp_path, name):
+    """The playground's output step (Playground.cpp:205-208 -> save_vtk :65-109) on its own input format: a mesh read by
+    sb_mesh_read_tetgen_2d, written by sb_mesh_write_vtk, against the file the reference's mesh classes produce through
+    the same statements (oracle/_ref/ref_mesh_tool vtk): node order, per-cell node lists, VTK_TRIANGLE, number format.
+    After a renumbering the cells (and their field values) move together."""
+    import os
+    import subprocess
+    prefix = os.path.join(REF_MESH_DIR, name + ".1")
+    tool = os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "_ref", "ref_mesh_tool")
+    if not os.path.exists(prefix + ".node") or not os.path.exists(tool):
+        pytest.skip("needs the reference's test meshes and oracle/_ref/ref_mesh_tool")
+    want = tmp_path / "ref.vtk"
+    subprocess.run([tool, "vtk", prefix + ".", str(want)], check=True, capture_output=True)
+    mesh = Mesh.read_tetgen_2d(prefix)
+    c = np.sin(0.37 * np.arange(mesh.n_cells))
+    got = tmp_path / "got.vtk"
+    mesh.write_vtk(str(got), {"c": c})
+    assert got.read_bytes() == want.read_bytes()
+    perm = mesh.renumber_rcm()
+    mesh.write_vtk(str(got), {"c": c[perm]})
+    ref_lines, new_lines = want.read_text().split("\n"), got.read_text().split("\n")
+    assert len(ref_lines) == len(new_lines)
+    cells0 = ref_lines.index(next(ln for ln in ref_lines if ln.startswith("CELLS "))) + 1
+    data0 = ref_lines.index("LOOKUP_TABLE default") + 1
+    assert new_lines[:cells0] == ref_lines[:cells0]                                     # header and points unchanged
+    for k in (0, 1, mesh.n_cells // 2, mesh.n_cells - 1):
+        assert new_lines[cells0 + k] == ref_lines[cells0 + int(perm[k])]
+        assert new_lines[data0 + k] == ref_lines[data0 + int(perm[k])]
+
+
+def test_playground_driver_host_side(tmp_path):
+    """scripts/playground_cahn_hilliard.py, the parts that run without a GPU: the Triangle files it can generate are read
+    alike by the library and by the reference's own reader + mesh classes (every SoA array, and the VTK file byte for
+    byte), and its initial condition is the playground's glibc rand() stream (Playground.cpp:183-185; the committed
+    Cahn-Hilliard fixture holds the reference's)."""
+    import importlib.util
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(__file__))
+    spec = importlib.util.spec_from_file_location("playground_driver", os.path.join(root, "scripts", "playground_cahn_hilliard.py"))
+    drv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(drv)
+    g = np.load(os.path.join(root, "tests", "golden", "cahn_hilliard_square_nb.npz"))
+    assert np.array_equal(drv.initial_condition(len(g["c0"])), g["c0"])
+    prefix = str(tmp_path / "gen.1")
+    drv.write_triangle_files(prefix, 7, 5)
+    mesh = Mesh.read_tetgen_2d(prefix)
+    assert (mesh.n_cells, mesh.n_faces, mesh.n_bfaces) == (70, 93, 24)
+    assert sorted(set(mesh.bface_labels().tolist())) == [1, 2, 3, 4]
+    assert np.isclose(np.asarray(mesh.cell_vol).sum(), 4.0, rtol=1e-14)
+    tool = os.path.join(root, "oracle", "_ref", "ref_mesh_tool")
+    if not os.path.exists(tool):
+        pytest.skip("oracle/_ref/ref_mesh_tool not built")
+    subprocess.run([tool, "export", prefix + ".", str(tmp_path / "exp.bin")], check=True, capture_output=True)
+    fm, _ = orc.read_mesh_export(str(tmp_path / "exp.bin"))
+    for k in SOA_KEYS:
+        assert np.array_equal(np.asarray(getattr(mesh, k)), getattr(fm, k)), k
+    subprocess.run([tool, "vtk", prefix + ".", str(tmp_path / "ref.vtk")], check=True, capture_output=True)
+    mesh.write_vtk(str(tmp_path / "got.vtk"), {"c": np.sin(0.37 * np.arange(mesh.n_cells))})
+    assert (tmp_path / "got.vtk").read_bytes() == (tmp_path / "ref.vtk").read_bytes()
+
+
 def test_tetgen_2d_reader_rejects_malformed_files(tmp_path):
     def write(name, node, edge, ele):
         for ext, text in ((".node", node), (".edge", edge), (".ele", ele)):
