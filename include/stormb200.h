@@ -339,6 +339,31 @@ SB_API int sb_eval(sb_ctx* ctx, double* y, size_t n, int assign_op, const sb_exp
 SB_API int sb_fill(sb_ctx* ctx, double* y, size_t n, double value);
 SB_API int sb_copy(sb_ctx* ctx, double* y, const double* x, size_t n);
 
+/* A GROUP of element-wise statements and the reductions behind them in ONE kernel launch (one pass over the union of
+ * the operands, one host synchronisation for all the reductions): what a solver's consecutive vector statements
+ * cost when they are issued together instead of one kernel each. Every statement is a linear-combination chain, the
+ * shape all of the reference solvers' updates have (e.g. SolverIdrs.hpp:166-176 `v <<= r - gamma_k*g_k; v -= gamma_i*g_i`,
+ * SolverBiCgStab.hpp:266-268 `u_i <<= r_i - beta*u_i`):
+ *     y = ((base (+|-) c0*x0) (+|-) c1*x1) ...      base == NULL: the chain starts from c0*x0 itself
+ * evaluated per element in exactly that order, every product and every sum rounded separately -- bit-identical to
+ * issuing `y <<= base - c0*x0; y -= c1*x1; ...` one statement at a time. Statements run in the order given; a later
+ * statement (and the dots) see what an earlier one stored; y may alias base or any x of its own chain. After the last
+ * statement the n_dots dot products <dot_a[d], dot_b[d]> are reduced with SB_TREE over the final values and
+ * returned on the host in order. n_stmt and n_dots may be 0 (not both). */
+#define SB_GROUP_MAX_STMT 8
+#define SB_GROUP_MAX_TERMS 8
+#define SB_GROUP_MAX_DOTS 8
+typedef struct sb_chain {
+  double* y;
+  const double* base;                   /* may be NULL */
+  int32_t n_terms;                      /* 1..SB_GROUP_MAX_TERMS (>= 1) */
+  const double* x[SB_GROUP_MAX_TERMS];
+  double c[SB_GROUP_MAX_TERMS];
+  uint8_t sub[SB_GROUP_MAX_TERMS];      /* 0: + c*x, 1: - c*x (with base == NULL, sub[0] must be 0) */
+} sb_chain;
+SB_API int sb_eval_group(sb_ctx* ctx, size_t n, int n_stmt, const sb_chain* h_stmts, int n_dots,
+                         const double* const* h_dot_a, const double* const* h_dot_b, double* h_out);
+
 /* dot_product (MatrixAlgorithms.hpp:310-317) and norm_2 (:262-270: sqrt of the sum of squares) with the fixed
  * reduction tree "SB_TREE v1" (DESIGN.md): run-to-run and grid-size independent. Results are
  * returned on the host (one stream synchronisation per call). sb_dot_batch evaluates m dot

@@ -102,6 +102,13 @@ def counts() -> dict:
     return dict(zip(COUNT_NAMES, list(out)))
 
 
+def group_count() -> int:
+    """Number of sb_eval_group launches since the last solve started."""
+    em = _load()[0]
+    em.emu_group_count.restype = C.c_int64
+    return int(em.emu_group_count())
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

@@ -36,6 +36,7 @@ struct sb_op {
 static char g_error[256] = "";
 static int g_mode = ORC_RED_SEQ;
 static int64_t g_calls[8]; /* eval, fill, copy, dot, norm, apply, accumulate, jacobi */
+static int64_t g_groups; /* sb_eval_group calls */
 static int g_dummy_ctx;
 
 static int fail(int code, const char* what) {
@@ -46,7 +47,8 @@ static int fail(int code, const char* what) {
 /* ---- emulator control (called by oracle/emu.py) ------------------------------------------------------------------ */
 API sb_ctx* emu_ctx(void) { return (sb_ctx*) &g_dummy_ctx; }
 API void emu_set_reduction_mode(int mode) { g_mode = mode; }
-API void emu_reset_counts(void) { memset(g_calls, 0, sizeof g_calls); }
+API void emu_reset_counts(void) { memset(g_calls, 0, sizeof g_calls), g_groups = 0; }
+API int64_t emu_group_count(void) { return g_groups; }
 API void emu_get_counts(int64_t out[8]) { memcpy(out, g_calls, sizeof g_calls); }
 API sb_op* emu_op_create(int64_t n, orc_apply_fn apply, void* apply_user, const orc_face_op* faces, const double* diag) {
   struct sb_op* op = (struct sb_op*) calloc(1, sizeof *op);
@@ -125,6 +127,41 @@ API int sb_eval(sb_ctx* ctx, double* y, size_t n, int assign_op, const sb_expr* 
       case SB_MUL_ASSIGN: y[i] = y[i] * v; break;
       default: y[i] = y[i] / v; break;
     }
+  }
+  return SB_OK;
+}
+
+/* statement group: statements in order (each over all elements: element-wise statements commute with the element loop),
+ * then the dots over the final values -- the contract of sb_eval_group in include/stormb200.h */
+API int sb_eval_group(sb_ctx* ctx, size_t n, int n_stmt, const sb_chain* st, int n_dots, const double* const* da,
+                      const double* const* db, double* h_out) {
+  if (ctx == NULL) return fail(SB_ERR_INVALID, "null argument");
+  if (n_stmt < 0 || n_stmt > SB_GROUP_MAX_STMT || n_dots < 0 || n_dots > SB_GROUP_MAX_DOTS || n_stmt + n_dots == 0)
+    return fail(SB_ERR_INVALID, "statement / dot count out of range");
+  for (int s = 0; s < n_stmt; ++s) {
+    if (st[s].y == NULL || st[s].n_terms < 1 || st[s].n_terms > SB_GROUP_MAX_TERMS) return fail(SB_ERR_INVALID, "bad chain");
+    if (st[s].base == NULL && st[s].sub[0] != 0) return fail(SB_ERR_INVALID, "a chain without a base cannot start with a subtraction");
+    for (int t = 0; t < st[s].n_terms; ++t)
+      if (st[s].x[t] == NULL) return fail(SB_ERR_INVALID, "null term vector");
+  }
+  g_calls[0] += n_stmt; /* counted as the statements they stand for */
+  g_groups++;
+  for (int s = 0; s < n_stmt; ++s) {
+    const sb_chain* ch = &st[s];
+    for (size_t i = 0; i < n; ++i) {
+      volatile double a = ch->base != NULL ? ch->base[i] : 0.0;
+      for (int t = 0; t < ch->n_terms; ++t) {
+        volatile double p = ch->c[t] * ch->x[t][i];
+        if (t == 0 && ch->base == NULL) a = p;
+        else if (ch->sub[t]) a = a - p;
+        else a = a + p;
+      }
+      ch->y[i] = a;
+    }
+  }
+  for (int d = 0; d < n_dots; ++d) {
+    g_calls[3]++;
+    h_out[d] = orc_dot((int64_t) n, da[d], db[d], g_mode);
   }
   return SB_OK;
 }

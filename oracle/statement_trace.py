@@ -33,7 +33,9 @@ TRACE = os.path.join(HERE, "_ref", "trace", "libstormb200_trace.so")
 
 # solver -> (iterations per cycle, default inner size argument)
 SOLVERS = {"cg": (1, 0), "cgs": (1, 0), "bicgstab": (1, 0), "bicgstabl": (2, 0), "tfqmr": (1, 0), "tfqmr1": (1, 0),
-           "idrs": (4, 0), "gmres": (50, 50), "fgmres": (50, 50), "richardson": (1, 0)}
+           "idrs": (4, 0), "gmres": (50, 50), "fgmres": (50, 50), "richardson": (1, 0),
+           # Storm/B200/GroupedSolvers.hpp: the same algorithms, statements issued as sb_eval_group launches
+           "grouped_idrs": (4, 0), "grouped_bicgstabl": (2, 0)}
 READS_TARGET = {1, 2, 3, 4}   # += -= *= /= read y as well
 
 
@@ -131,6 +133,18 @@ def count(stream):
     for st in stream:
         kind = st[0]
         if kind in ("alloc", "free", "mark", "upload"):
+            continue
+        if kind == "group":     # group n_reads r.. n_writes w.. n_stmt n_dots: one launch over the union of its operands
+            close()
+            nr = st[1]
+            nw = st[2 + nr]
+            n_dots = st[2 + nr + 1 + nw + 1]
+            reductions += n_dots
+            written += nr + nw
+            fused += nr + nw
+            launches_written += 1
+            launches_fused += 1
+            apply_ctx = None
             continue
         if kind in ("apply", "jacobi"):
             close()

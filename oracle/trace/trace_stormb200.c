@@ -1,6 +1,6 @@
 /* TEST / ANALYSIS INFRASTRUCTURE -- not product code, computes nothing.
  *
- * A logging stand-in for the 16 C-ABI entry points that stormruler_b200/host/dropin.cpp imports (include/stormb200.h).
+ * A logging stand-in for the 17 C-ABI entry points that stormruler_b200/host/dropin.cpp imports (include/stormb200.h).
  * The drop-in TU -- the reference's unmodified solver templates on Storm::DeviceVector -- is linked against this
  * library instead of libstormb200.so (oracle/Makefile, target `trace`), so every vector statement, reduction and
  * operator apply the reference's solvers issue shows up as one line of a log, with vector identities instead of data:
@@ -91,6 +91,37 @@ API int sb_eval(sb_ctx* ctx, double* y, size_t n, int assign_op, const sb_expr* 
   put(line);
   return SB_OK;
 }
+/* group n_reads r... n_writes w... n_dots : one launch; reads = distinct vectors read before the group wrote them
+ * (operands of the statements and of the dots), writes = distinct targets */
+API int sb_eval_group(sb_ctx* ctx, size_t n, int n_stmt, const sb_chain* st, int n_dots, const double* const* da,
+                      const double* const* db, double* h_out) {
+  (void) ctx, (void) n;
+  const void* rd[128];
+  const void* wr[16];
+  int nr = 0, nw = 0;
+#define SEEN(arr, cnt, p) ({ int f_ = 0; for (int q_ = 0; q_ < (cnt); ++q_) f_ |= (arr)[q_] == (const void*) (p); f_; })
+  for (int s = 0; s < n_stmt; ++s) {
+    if (st[s].base != NULL && !SEEN(wr, nw, st[s].base) && !SEEN(rd, nr, st[s].base)) rd[nr++] = st[s].base;
+    for (int t = 0; t < st[s].n_terms; ++t)
+      if (!SEEN(wr, nw, st[s].x[t]) && !SEEN(rd, nr, st[s].x[t])) rd[nr++] = st[s].x[t];
+    if (!SEEN(wr, nw, st[s].y)) wr[nw++] = st[s].y;
+  }
+  for (int d = 0; d < n_dots; ++d) {
+    if (!SEEN(wr, nw, da[d]) && !SEEN(rd, nr, da[d])) rd[nr++] = da[d];
+    if (!SEEN(wr, nw, db[d]) && !SEEN(rd, nr, db[d])) rd[nr++] = db[d];
+    h_out[d] = 1.0;
+  }
+#undef SEEN
+  char line[1024];
+  int off = snprintf(line, sizeof line, "group %d", nr);
+  for (int q = 0; q < nr; ++q) off += snprintf(line + off, sizeof line - (size_t) off, " %d", id_of(rd[q]));
+  off += snprintf(line + off, sizeof line - (size_t) off, " %d", nw);
+  for (int q = 0; q < nw; ++q) off += snprintf(line + off, sizeof line - (size_t) off, " %d", id_of(wr[q]));
+  snprintf(line + off, sizeof line - (size_t) off, " %d %d\n", n_stmt, n_dots);
+  put(line);
+  return SB_OK;
+}
+
 API int sb_fill(sb_ctx* ctx, double* y, size_t n, double value) {
   (void) ctx, (void) n, (void) value;
   char line[64];

@@ -13,7 +13,9 @@ on both sides: the generic path is host-driven, so this is what an application s
   * generic drop-in: StormRuler's own solver templates instantiated on Storm::DeviceVector
     (cg cgs bicgstab bicgstabl gmres fgmres tfqmr tfqmr1 idrs richardson) -- one kernel per vector statement, one
     fused reduction + host read-back per dot/norm, exactly the reference's statement sequence;
-  * fused: fused_cg fused_bicgstab fused_gmres (sb_cg_solve / sb_bicgstab_solve / sb_gmres_solve).
+  * fused: fused_cg fused_bicgstab fused_gmres (sb_cg_solve / sb_bicgstab_solve / sb_gmres_solve);
+  * grouped: grouped_idrs grouped_bicgstabl (Storm/B200/GroupedSolvers.hpp: the reference algorithms with their statements
+    issued as sb_eval_group launches; host scalars).
 
 Contract bytes per iteration (V = 8 N, B = algorithmic bytes of one apply): fused-minimum schedules
 for CG (B + 9V), BiCGStab (2B + 15V), GMRES inner step k (B + (4k+6)V); as-written pass counts for the rest
@@ -38,12 +40,14 @@ from stormruler_b200 import dropin  # noqa: E402
 from stormruler_b200.mesh import CELL_HEX, CELL_TET, Mesh  # noqa: E402
 
 ALL = ["fused_cg", "fused_bicgstab", "fused_gmres", "cg", "bicgstab", "cgs", "bicgstabl", "tfqmr", "tfqmr1", "idrs",
-       "gmres", "fgmres", "richardson"]
+       "gmres", "fgmres", "richardson", "grouped_idrs", "grouped_bicgstabl"]
 
 
 def contract_bytes(solver: str, B: float, V: float, steps: int, m: int) -> float:
     """Algorithmic bytes of `steps` iterations."""
-    base = solver.replace("fused_", "")
+    # grouped_*: quoted against the same as-written bytes as the reference template they replace, so the two rows
+    # compare as iterations/s; what the grouped solver itself moves (31 V / 25.5 V) is in DESIGN.md section 5
+    base = solver.replace("fused_", "").replace("grouped_", "")
     if base in ("gmres", "fgmres"):
         ks = np.arange(steps) % m
         return float(np.sum(B + (4 * ks + 6) * V))
@@ -125,7 +129,9 @@ def main():
               "ms_per_iteration": 1e3 * secs / (2 * K), "contract_bytes_per_iteration": alg / (2 * K),
               "contract_gbs": alg / secs / 1e9, "frac_of_measured_peak": alg / secs / 1e9 / peak,
               "frac_of_nominal_8TBs": alg / secs / 8e12, "residual_after_3K": err,
-              "path": "fused" if solver.startswith("fused_") else "reference template on Storm::DeviceVector"}
+              "path": "fused" if solver.startswith("fused_") else
+                      ("statement groups (Storm::B200 grouped solver)" if solver.startswith("grouped_") else
+                       "reference template on Storm::DeviceVector")}
         print(json.dumps(pt), flush=True)
         points.append(pt)
         if args.out:  # rewritten after every solver: a cut-off run keeps what it measured

@@ -83,6 +83,24 @@ class Context:
             e.scal[k] = float(s)
         capi.check(self.lib.sb_eval(self.handle, y.ptr, y.n, assign_op, C.byref(e)))
 
+    def eval_group(self, stmts=(), dots=()) -> np.ndarray:
+        """sb_eval_group: `stmts` = [(y, base | None, [(c, x, sub), ...]), ...] run in order in one launch, then the
+        dot products of `dots` = [(a, b), ...] over the final values; returns the dot values."""
+        S = (capi.Chain * max(len(stmts), 1))()
+        n = None
+        for k, (y, base, terms) in enumerate(stmts):
+            S[k].y, S[k].base, S[k].n_terms = y.ptr, (base.ptr if base is not None else None), len(terms)
+            for t, (c, x, sub) in enumerate(terms):
+                S[k].c[t], S[k].x[t], S[k].sub[t] = float(c), x.ptr, int(bool(sub))
+            n = y.n
+        m = len(dots)
+        A = (C.c_void_p * max(m, 1))(*[p[0].ptr for p in dots])
+        B = (C.c_void_p * max(m, 1))(*[p[1].ptr for p in dots])
+        n = n if n is not None else dots[0][0].n
+        out = np.zeros(max(m, 1))
+        capi.check(self.lib.sb_eval_group(self.handle, n, len(stmts), S, m, A, B, out.ctypes.data_as(capi.f64p)))
+        return out[:m]
+
     def dot(self, a: "DeviceVector", b: "DeviceVector") -> float:
         out = C.c_double()
         capi.check(self.lib.sb_dot(self.handle, a.ptr, b.ptr, a.n, C.byref(out)))

@@ -69,6 +69,15 @@ class Expr(C.Structure):
                 ("vec", C.c_void_p * EXPR_MAX_VEC), ("scal", C.c_double * EXPR_MAX_SCAL)]
 
 
+GROUP_MAX_STMT, GROUP_MAX_TERMS, GROUP_MAX_DOTS = 8, 8, 8
+
+
+class Chain(C.Structure):      # sb_chain: y = ((base +- c0*x0) +- c1*x1) ...
+    _fields_ = [("y", C.c_void_p), ("base", C.c_void_p), ("n_terms", C.c_int32),
+                ("x", C.c_void_p * GROUP_MAX_TERMS), ("c", C.c_double * GROUP_MAX_TERMS),
+                ("sub", C.c_uint8 * GROUP_MAX_TERMS)]
+
+
 class SolverOpts(C.Structure):
     _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
                 ("check_every", C.c_int32), ("use_graph", C.c_int32), ("profile", C.c_int32)]
@@ -135,6 +144,7 @@ SIGNATURES = {
     "sb_comm_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "sb_dist_op_create": (C.c_int, [C.c_void_p, C.POINTER(LocalMesh), C.POINTER(OpDesc), vpp]),
     "sb_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Expr)]),
+    "sb_eval_group": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Chain), C.c_int, vpp, vpp, f64p]),
     "sb_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double]),
     "sb_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "sb_dot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, f64p]),

@@ -312,6 +312,77 @@ int sb_dot_batch(sb_ctx* ctx, int m, const double* const* h_a, const double* con
   return SB_OK;
 }
 
+int sb_eval_group(sb_ctx* ctx, size_t n, int n_stmt, const sb_chain* h_stmts, int n_dots,
+                  const double* const* h_dot_a, const double* const* h_dot_b, double* h_out) {
+  SB_REQUIRE(ctx != nullptr, "null argument");
+  SB_REQUIRE(n_stmt >= 0 && n_stmt <= SB_GROUP_MAX_STMT, "statement count out of range (0..8)");
+  SB_REQUIRE(n_dots >= 0 && n_dots <= SB_GROUP_MAX_DOTS, "dot count out of range (0..8)");
+  SB_REQUIRE(n_stmt + n_dots > 0, "empty group");
+  SB_REQUIRE(n_stmt == 0 || h_stmts != nullptr, "null statement array");
+  SB_REQUIRE(n_dots == 0 || (h_dot_a != nullptr && h_dot_b != nullptr && h_out != nullptr), "null dot arrays");
+  GroupBody body{};
+  for (int s = 0; s < n_stmt; ++s) {
+    const sb_chain& ch = h_stmts[s];
+    SB_REQUIRE(ch.y != nullptr, "statement without a target");
+    SB_REQUIRE(ch.n_terms >= 1 && ch.n_terms <= SB_GROUP_MAX_TERMS, "term count out of range (1..8)");
+    for (int t = 0; t < ch.n_terms; ++t) SB_REQUIRE(ch.x[t] != nullptr, "null term vector");
+    SB_REQUIRE(ch.base != nullptr || ch.sub[0] == 0, "a chain without a base cannot start with a subtraction");
+    body.st[s] = ch;
+  }
+  for (int d = 0; d < n_dots; ++d) SB_REQUIRE(h_dot_a[d] != nullptr && h_dot_b[d] != nullptr, "null vector");
+  if (n == 0) {
+    for (int d = 0; d < n_dots; ++d) h_out[d] = 0.0;
+    return SB_OK;
+  }
+  // the first kMaxDots dots ride on the statement kernel; the rest (long batches) are stand-alone dot kernels
+  const int fused = n_stmt > 0 ? std::min(n_dots, kMaxDots) : 0;
+  body.n_stmt = n_stmt, body.n_dots = fused;
+  for (int d = 0; d < fused; ++d) body.da[d] = h_dot_a[d], body.db[d] = h_dot_b[d];
+  const unsigned grid = (unsigned) num_tiles((int64_t) n);
+  if (n_stmt > 0) {
+    if (fused > 0) SB_TRY(ensure_red_scratch(ctx, (int64_t) n));
+    const RedPtrs red = fused > 0 ? red_ptrs(ctx) : RedPtrs{};
+    switch (fused) {
+      case 0:
+        SB_CUDA(launch_kernel(ctx, ew_kernel<0, GroupBody>, grid, kThreads, 0, (int64_t) n, body, red, (const int*) nullptr));
+        break;
+      case 1:
+        SB_CUDA(launch_kernel(ctx, ew_kernel<1, GroupBody>, grid, kThreads, 0, (int64_t) n, body, red, (const int*) nullptr));
+        break;
+      case 2:
+        SB_CUDA(launch_kernel(ctx, ew_kernel<2, GroupBody>, grid, kThreads, 0, (int64_t) n, body, red, (const int*) nullptr));
+        break;
+      default:
+        SB_CUDA(launch_kernel(ctx, ew_kernel<3, GroupBody>, grid, kThreads, 0, (int64_t) n, body, red, (const int*) nullptr));
+        break;
+    }
+    ctx->launches++;
+    if (fused == 1) SB_TRY(launch_final<1>(ctx, (int64_t) n, StoreFinal<1>{ctx->red.result}, nullptr));
+    if (fused == 2) SB_TRY(launch_final<2>(ctx, (int64_t) n, StoreFinal<2>{ctx->red.result}, nullptr));
+    if (fused == 3) SB_TRY(launch_final<3>(ctx, (int64_t) n, StoreFinal<3>{ctx->red.result}, nullptr));
+  }
+  int k = fused;
+  while (k < n_dots) {
+    const int left = n_dots - k;
+    if (left >= 3) {
+      SB_TRY(launch_dots<3>(ctx, h_dot_a + k, h_dot_b + k, n, ctx->red.result + k));
+      k += 3;
+    } else if (left == 2) {
+      SB_TRY(launch_dots<2>(ctx, h_dot_a + k, h_dot_b + k, n, ctx->red.result + k));
+      k += 2;
+    } else {
+      SB_TRY(launch_dots<1>(ctx, h_dot_a + k, h_dot_b + k, n, ctx->red.result + k));
+      k += 1;
+    }
+  }
+  if (n_dots > 0) {
+    SB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->red.result, sizeof(double) * n_dots, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < n_dots; ++q) h_out[q] = ctx->h_pinned[q];
+  }
+  return SB_OK;
+}
+
 int sb_dot(sb_ctx* ctx, const double* a, const double* b, size_t n, double* h_out) {
   return sb_dot_batch(ctx, 1, &a, &b, n, h_out);
 }

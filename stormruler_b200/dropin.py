@@ -18,6 +18,8 @@ GENERIC_SOLVERS = ("cg", "cgs", "bicgstab", "bicgstabl", "gmres", "fgmres", "tfq
                    "richardson")
 NONLINEAR_SOLVERS = ("jfnk",)   # SolverNewton.hpp:101-173, inner solve = the reference's BiCgStabSolver
 FUSED_SOLVERS = ("fused_cg", "fused_bicgstab", "fused_gmres")
+# Storm/B200/GroupedSolvers.hpp: IDR(s) / BiCGStab(l) with their statements issued as sb_eval_group launches
+GROUPED_SOLVERS = {"grouped_idrs": "idrs", "grouped_bicgstabl": "bicgstabl"}
 
 
 class Opts(C.Structure):

@@ -11,6 +11,7 @@
 // (Python, ctypes) can run it on vectors they own; g++ -std=c++23 builds it, linking libstormb200.so.
 // The built libstorm_dropin.so travels to the GPU box (the reference tree does not exist there).
 #include <Storm/B200/FusedSolvers.hpp>
+#include <Storm/B200/GroupedSolvers.hpp>
 
 #include <Storm/Solvers/SolverBiCgStab.hpp>
 #include <Storm/Solvers/SolverCg.hpp>
@@ -170,7 +171,8 @@ extern "C" {
 DROPIN_API const char* dropin_last_error(void) { return g_error.c_str(); }
 
 // Solver names: cg cgs bicgstab bicgstabl gmres fgmres tfqmr tfqmr1 idrs richardson jfnk (the reference
-// templates on DeviceVector), fused_cg fused_bicgstab (Storm::B200 fast path).
+// templates on DeviceVector), grouped_idrs grouped_bicgstabl (same algorithms, statements in groups), fused_cg
+// fused_bicgstab fused_gmres (Storm::B200 fast path).
 DROPIN_API int dropin_solve(const char* name, sb_ctx* ctx, const sb_op* op, double* d_x, const double* d_b,
                             size_t n, const dropin_opts* o, dropin_report* rep, double* hist, int64_t hist_cap,
                             double* trace, int64_t trace_cap) {
@@ -191,6 +193,11 @@ DROPIN_API int dropin_solve(const char* name, sb_ctx* ctx, const sb_op* op, doub
     DROPIN_CASE("richardson", RichardsonSolver);
     DROPIN_CASE("jfnk", JfnkSolver);
 #undef DROPIN_CASE
+    // the same algorithms with their statements issued in groups (Storm/B200/GroupedSolvers.hpp)
+    if (s == "grouped_idrs")
+      return run_generic<Storm::B200::IdrsSolver>(ctx, op, d_x, d_b, n, o, rep, hist, hist_cap, trace, trace_cap);
+    if (s == "grouped_bicgstabl")
+      return run_generic<Storm::B200::BiCgStabLSolver>(ctx, op, d_x, d_b, n, o, rep, hist, hist_cap, trace, trace_cap);
     if (s == "fused_cg")
       return run_fused<Storm::B200::CgSolver>(ctx, op, d_x, d_b, n, o, rep, hist, hist_cap, trace, trace_cap);
     if (s == "fused_bicgstab")

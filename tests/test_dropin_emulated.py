@@ -61,6 +61,46 @@ def test_preconditioner_slot(square_nb, side):
         assert emu.counts()["jacobi"] > 0
 
 
+@pytest.mark.parametrize("name,ref,inner", [("grouped_idrs", "idrs", 0), ("grouped_idrs", "idrs", 1), ("grouped_idrs", "idrs", 6),
+                                            ("grouped_idrs", "idrs", 11), ("grouped_bicgstabl", "bicgstabl", 0),
+                                            ("grouped_bicgstabl", "bicgstabl", 1), ("grouped_bicgstabl", "bicgstabl", 4)])
+def test_grouped_solvers_issue_the_reference_arithmetic(square_nb, name, ref, inner):
+    """Storm::B200::IdrsSolver / BiCgStabLSolver (statements issued as sb_eval_group launches) against the reference
+    templates: iterate, residual history, the whole sequence of reduction values and the number of operator applies,
+    bit for bit; symmetric and non-symmetric operator, sequential and GPU-tree reductions; s = 1 / 4 (default) / 6 / 11
+    (11: chains longer than the ABI's 8 terms and batches of more than 8 dots are split), l = 1 / 2 (default) / 4; and
+    far fewer launches than statements."""
+    rng = np.random.default_rng(5)
+    b = rhs(square_nb.n_cells)
+    ops = (orc.FaceOp(square_nb, prefill=1, dt=-DT),
+           orc.ConvDiffOp(square_nb, 0.02, rng.standard_normal(square_nb.n_faces), rng.standard_normal(square_nb.n_bfaces)))
+    for op in ops:
+        for mode in (orc.RED_SEQ, orc.RED_TREE):
+            kw = dict(num_iterations=150, abs_tol=0.0, rel_tol=RTOL, num_inner=inner, mode=mode)
+            want = orc.ref_solve(ref, op, b, **kw)
+            got = emu.solve(name, emu.EmuOp(op), b, **kw)
+            assert got.iterations > 20 and same(got, want), (name, inner, mode)
+            groups = emu.group_count()
+            plain = emu.solve(ref, emu.EmuOp(op), b, **kw)
+            statements = emu.counts()["eval"] + emu.counts()["dot"] + emu.counts()["norm"]
+            assert same(plain, want) and 0 < groups < 0.62 * statements
+
+
+def test_grouped_solvers_stop_mid_cycle_and_reject_a_preconditioner(square_nb):
+    op = orc.FaceOp(square_nb, prefill=0, dt=-1.0, dirichlet=True)
+    b = rhs(square_nb.n_cells)
+    for name, ref in (("grouped_idrs", "idrs"), ("grouped_bicgstabl", "bicgstabl")):
+        for iters in (1, 2, 3, 5, 7):          # num_iterations cuts the inner cycle at every position
+            kw = dict(num_iterations=iters, abs_tol=0.0, rel_tol=0.0)
+            assert same(emu.solve(name, emu.EmuOp(op), b, **kw), orc.ref_solve(ref, op, b, **kw)), (name, iters)
+        kw = dict(num_iterations=400, abs_tol=1e-7, rel_tol=0.0)          # stop on the absolute tolerance
+        got, want = emu.solve(name, emu.EmuOp(op), b, **kw), orc.ref_solve(ref, op, b, **kw)
+        assert got.converged and same(got, want)
+        _, _, _, _, diag = op.rows_coef()
+        with pytest.raises(RuntimeError, match="preconditioner"):
+            emu.solve(name, emu.EmuOp(op, diag=diag[:square_nb.n_cells].copy()), b, precond="jacobi", num_iterations=5)
+
+
 def test_host_layer_rejects_misuse():
     assert emu.selftest_errors() == 3
 

@@ -129,3 +129,65 @@ def test_playground_driver_end_to_end(tmp_path):
     for k in range(3):
         text = (tmp_path / f"fields-{k:05d}.vtk").read_text()
         assert text.startswith("# vtk DataFile Version 2.0\n") and "SCALARS c double 1" in text
+
+
+# ---- statement groups (sb_eval_group) and the grouped IDR(s) / BiCGStab(l) ------------------------------------------------
+def _chain_host(vals, y, base, terms):
+    a = None if base is None else vals[base].copy()
+    for t, (c, x, sub) in enumerate(terms):
+        p = c * vals[x]
+        a = p if (a is None and t == 0) else (a - p if sub else a + p)
+    vals[y] = a
+
+
+@pytest.mark.parametrize("n", [1, 2047, 2048, 2049, 100_003])
+def test_statement_group_kernel_bit_exact(ctx, n):
+    """sb_eval_group against numpy, statement by statement (every product and sum rounded separately), with the
+    aliasing the solvers use: targets that are their own base or term, later statements reading earlier targets, and
+    up to 8 dots over the final values (3 ride on the statement kernel, the rest are stand-alone dot kernels)."""
+    rng = np.random.default_rng(n)
+    names = "abcdefgh"
+    host = {k: rng.standard_normal(n) for k in names}
+    dev = {k: ctx.vector(v) for k, v in host.items()}
+    stmts = [("a", "b", [(0.3, "c", 1), (-1.7, "d", 0), (2.5, "a", 1)]),            # a = ((b - .3c) + (-1.7)d) - 2.5a
+             ("e", None, [(1.25, "a", 0), (0.5, "e", 0), (3.0, "f", 0)]),           # e = (1.25a + .5e) + 3f   (reads new a)
+             ("g", "g", [(0.75, "e", 1)]),                                           # g -= .75e                (reads new e)
+             ("h", "a", [(c, x, s) for c, x, s in zip(rng.standard_normal(8), "bcdefgab", [0, 1] * 4)])]   # 8 terms
+    dots = [("a", "e"), ("g", "g"), ("h", "b"), ("a", "a"), ("c", "h"), ("e", "g"), ("b", "b"), ("h", "h")]
+    for y, base, terms in stmts:
+        _chain_host(host, y, base, terms)
+    got = ctx.eval_group([(dev[y], dev[b] if b else None, [(c, dev[x], s) for c, x, s in terms]) for y, b, terms in stmts],
+                         [(dev[p], dev[q]) for p, q in dots])
+    for k in names:
+        assert np.array_equal(dev[k].numpy(), host[k]), k
+    want = np.array([orc.dot(host[p], host[q], orc.RED_TREE) for p, q in dots])
+    assert np.array_equal(got, want)
+    # statements only / dots only
+    ctx.eval_group([(dev["c"], dev["c"], [(2.0, dev["d"], 0)])])
+    assert np.array_equal(dev["c"].numpy(), host["c"] + 2.0 * host["d"])
+    assert ctx.eval_group(dots=[(dev["d"], dev["d"])])[0] == orc.dot(host["d"], host["d"], orc.RED_TREE)
+    with pytest.raises(sb.StormB200Error):
+        ctx.eval_group()
+
+
+@pytest.mark.parametrize("name,inner", [("grouped_idrs", 0), ("grouped_idrs", 7), ("grouped_idrs", 11),
+                                        ("grouped_bicgstabl", 0), ("grouped_bicgstabl", 3)])
+def test_grouped_solvers_bit_identical_to_the_reference_templates(ctx, square_nb, name, inner):
+    """Storm::B200::IdrsSolver / BiCgStabLSolver on the device against the reference's own templates on a host vector
+    (GPU reduction tree): iteration count, every reduction value, residual history, solution."""
+    ref = dropin.GROUPED_SOLVERS[name]
+    from conftest import rhs
+    rng = np.random.default_rng(12)
+    un, bun = rng.standard_normal(square_nb.n_faces), rng.standard_normal(square_nb.n_bfaces)
+    # (oracle operator, device operator) pairs whose applies are bit-identical: face loop vs faithful rows
+    # (tests/test_gpu_dropin.py), coefficient rows of the convection-diffusion operator (tests/test_gpu_convdiff.py)
+    cases = ((orc.FaceOp(square_nb, prefill=1, dt=-0.05), sb.FvmOperator(ctx, square_nb, prefill=1, dt=-0.05, form=sb.FORM_FAITHFUL)),
+             (orc.ConvDiffOp(square_nb, 0.02, un, bun).rows_coef(), sb.ConvDiffOperator(ctx, square_nb, 0.02, un, bun)))
+    b = rhs(square_nb.n_cells)
+    for cpu_op, gpu in cases:
+        want = orc.ref_solve(ref, cpu_op, b, num_iterations=200, abs_tol=0.0, rel_tol=1e-10, num_inner=inner, mode=orc.RED_TREE)
+        x = ctx.zeros(cpu_op.n)
+        got = dropin.solve(name, gpu, x, ctx.vector(b), num_iterations=200, abs_tol=0.0, rel_tol=1e-10, num_inner=inner)
+        assert (got.converged, got.iterations, got.n_apply) == (want.converged, want.iterations, want.n_apply)
+        assert np.array_equal(got.trace, want.trace) and np.array_equal(got.hist, want.hist)
+        assert np.array_equal(x.numpy(), want.x)

@@ -59,6 +59,15 @@ def test_fused_schedules_written_down(counts):
             counts["idrs"]["passes_fused"]) == (17, 35, 21.5, 29.25)
 
 
+def test_grouped_solvers_move_fewer_bytes_in_fewer_launches(counts):
+    """Storm::B200::IdrsSolver / BiCgStabLSolver (statement groups, host scalars): the numbers quoted in DESIGN.md."""
+    gi, gb = counts["grouped_idrs"], counts["grouped_bicgstabl"]
+    assert (gi["applies"], gi["reductions"]) == (counts["idrs"]["applies"], counts["idrs"]["reductions"])
+    assert (gb["applies"], gb["reductions"]) == (counts["bicgstabl"]["applies"], counts["bicgstabl"]["reductions"])
+    assert (gi["passes_written"], gi["launches_written"]) == (31.0, 6.5)          # 43.25 V, 18.25 launches as written
+    assert (gb["passes_written"], gb["launches_written"]) == (25.5, 8.5)          # 31.5 V, 15 launches as written
+
+
 def test_solver_sweep_contract_uses_the_traced_counts(counts):
     import importlib.util
     spec = importlib.util.spec_from_file_location("solver_sweep", os.path.join(ROOT, "scripts", "solver_sweep.py"))
