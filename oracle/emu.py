@@ -102,6 +102,11 @@ def counts() -> dict:
     return dict(zip(COUNT_NAMES, list(out)))
 
 
+def set_statement_grouping(on: bool) -> None:
+    """Storm::B200::set_statement_grouping in the emulated drop-in (off by default)."""
+    _load()[1].dropin_set_statement_grouping(int(bool(on)))
+
+
 def group_count() -> int:
     """Number of sb_eval_group launches since the last solve started."""
     em = _load()[0]

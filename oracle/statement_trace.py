@@ -71,9 +71,12 @@ def _load():
     return _libs
 
 
-def statement_stream(solver: str, iterations: int, precond: int = 0, pre_side: int = 1):
-    """Run `solver` for exactly `iterations` iterations on the tracer; returns the log as a list of tuples."""
+def statement_stream(solver: str, iterations: int, precond: int = 0, pre_side: int = 1, grouping: bool = False):
+    """Run `solver` for exactly `iterations` iterations on the tracer; returns the log as a list of tuples.
+    grouping: Storm::B200::set_statement_grouping(true) -- the generic path queues chain-shaped statements and
+    launches them as sb_eval_group with the reduction behind them."""
     tr, dr = _load()
+    dr.dropin_set_statement_grouping(int(grouping))
     tr.sbtrace_reset()
     n = 1000
     fake_ctx, fake_op = C.c_void_p(0x1000), C.c_void_p(0x2000)
@@ -83,6 +86,7 @@ def statement_stream(solver: str, iterations: int, precond: int = 0, pre_side: i
     rep = Report()
     rc = dr.dropin_solve(solver.encode(), fake_ctx, fake_op, C.cast(x, C.c_void_p), C.cast(b, C.c_void_p),
                          C.c_size_t(n), C.byref(opts), C.byref(rep), None, C.c_int64(0), None, C.c_int64(0))
+    dr.dropin_set_statement_grouping(0)
     if rc != 0:
         raise RuntimeError(f"dropin_solve({solver}) on the tracer failed: {dr.dropin_last_error().decode()}")
     assert rep.iterations == iterations, (solver, rep.iterations, iterations)
@@ -177,11 +181,12 @@ def count(stream):
                 launches_written=launches_written, launches_fused=launches_fused)
 
 
-def per_iteration(solver: str, cycles: int = 4):
+def per_iteration(solver: str, cycles: int = 4, grouping: bool = False):
     """Steady-state counts per iteration: (2K iterations) - (K iterations), K a multiple of the solver's cycle."""
     cyc = SOLVERS[solver][0]
     K = cyc * cycles
-    a, b = count(statement_stream(solver, K)), count(statement_stream(solver, 2 * K))
+    a = count(statement_stream(solver, K, grouping=grouping))
+    b = count(statement_stream(solver, 2 * K, grouping=grouping))
     return {k: (b[k] - a[k]) / K for k in a}
 
 
@@ -189,13 +194,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--solvers", default=",".join(SOLVERS))
     ap.add_argument("--json", default="")
+    ap.add_argument("--grouping", action="store_true", help="with Storm::B200::set_statement_grouping(true)")
     args = ap.parse_args()
     if not available():
         sys.exit("tracer not built: make -C oracle trace (needs the StormRuler sources)")
     rows = {}
     print(f"{'solver':12s} {'applies':>8s} {'reductions':>11s} {'V written':>10s} {'V fused':>8s} {'launches':>9s} {'fused':>6s}")
     for s in args.solvers.split(","):
-        r = per_iteration(s)
+        r = per_iteration(s, grouping=args.grouping)
         rows[s] = r
         print(f"{s:12s} {r['applies']:8.2f} {r['reductions']:11.2f} {r['passes_written']:10.2f} {r['passes_fused']:8.2f} "
               f"{r['launches_written']:9.2f} {r['launches_fused']:6.2f}")

@@ -31,6 +31,7 @@
 
 #include <Storm/Bittern/Matrix.hpp>
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <concepts>
@@ -83,6 +84,148 @@ inline std::mt19937_64& random_engine() {
   static std::mt19937_64 engine{};
   return engine;
 }
+
+/// ---- statement grouping (opt-in) ------------------------------------------------------------------------------
+/// With `set_statement_grouping(true)` the element-wise statements the solver templates issue one by one are not
+/// launched one by one: every statement that is a linear-combination chain `y = ((base +- c0*x0) +- c1*x1) ...`
+/// (all vector updates of the reference solvers except the nested `r + beta*(p - omega*v)` forms) is queued, and
+/// the queue is handed to the device as ONE sb_eval_group launch when something needs its result: a reduction (which
+/// joins the group: statements + dot in one launch and one synchronisation), an operator apply, a statement of another
+/// shape, a host access, a vector going away. Element-wise statements are independent per element and the group
+/// runs them in order, so nothing changes bit-wise (tests/test_dropin_emulated.py runs every reference solver both
+/// ways). Code that hands `DeviceVector::data()` to the C ABI itself must call `B200::flush()` first.
+struct StatementQueue {
+  bool enabled = false;
+  sb_ctx* ctx = nullptr;
+  size_t n = 0;
+  std::vector<sb_chain> stmts;
+
+  void launch(size_t first, size_t count, const double* dot_a, const double* dot_b, double* out) {
+    check(sb_eval_group(ctx, n, (int) count, count > 0 ? stmts.data() + first : nullptr, dot_a != nullptr ? 1 : 0,
+                        dot_a != nullptr ? &dot_a : nullptr, dot_a != nullptr ? &dot_b : nullptr, out),
+          "sb_eval_group");
+  }
+  void flush() {
+    const size_t total = stmts.size(); // a failing launch must not leave the statements queued for a second attempt
+    for (size_t s0 = 0; s0 < total; s0 += SB_GROUP_MAX_STMT) {
+      const size_t ns = std::min<size_t>(total - s0, SB_GROUP_MAX_STMT);
+      try {
+        launch(s0, ns, nullptr, nullptr, nullptr);
+      } catch (...) {
+        stmts.clear();
+        throw;
+      }
+    }
+    stmts.clear();
+  }
+  /// <a, b> over the vectors as they are after the queued statements: the statements and the dot in one launch.
+  double reduce(sb_ctx* c, const double* a, const double* b, size_t len) {
+    double v = 0.0;
+    if (!enabled || stmts.empty() || c != ctx || len != n) {
+      flush();
+      check(sb_dot(c, a, b, len, &v), "sb_dot");
+      return v;
+    }
+    const size_t total = stmts.size();
+    const size_t tail = (total - 1) / SB_GROUP_MAX_STMT * SB_GROUP_MAX_STMT; // first statement of the last launch
+    try {
+      for (size_t s0 = 0; s0 < tail; s0 += SB_GROUP_MAX_STMT) launch(s0, SB_GROUP_MAX_STMT, nullptr, nullptr, nullptr);
+      launch(tail, total - tail, a, b, &v);
+    } catch (...) {
+      stmts.clear();
+      throw;
+    }
+    stmts.clear();
+    return v;
+  }
+  /// Queue `y (aop)= expr` if it is a chain; false: the caller flushes and launches it directly.
+  bool try_enqueue(sb_ctx* c, double* y, size_t len, int aop, const sb_expr& e) {
+    if (!enabled || len == 0) return false;
+    struct Node {
+      int kind; // 0 vector, 1 scalar, 2 product c*x, 3 chain
+      const double* v;
+      double s;
+      sb_chain ch;
+    };
+    Node st[SB_EXPR_MAX_OPS];
+    int sp = 0;
+    auto as_term = [](const Node& nd, const double*& x, double& coef) {
+      if (nd.kind == 0) return x = nd.v, coef = 1.0, true; // a +- x == a +- 1.0*x exactly
+      if (nd.kind == 2) return x = nd.v, coef = nd.s, true;
+      return false;
+    };
+    auto start_chain = [&](const Node& nd, sb_chain& ch) {
+      ch = sb_chain{};
+      if (nd.kind == 0) return ch.base = nd.v, true;
+      if (nd.kind == 2) return ch.x[0] = nd.v, ch.c[0] = nd.s, ch.sub[0] = 0, ch.n_terms = 1, true;
+      return false;
+    };
+    for (int k = 0; k < e.n_ops; ++k) {
+      const int op = e.ops[k];
+      if (op <= SB_OP_VEC3) {
+        st[sp++] = Node{0, e.vec[op], 0.0, {}};
+      } else if (op >= SB_OP_SCAL0 && op <= SB_OP_SCAL3) {
+        st[sp++] = Node{1, nullptr, e.scal[op - SB_OP_SCAL0], {}};
+      } else if (op == SB_OP_MUL) {
+        const Node r = st[--sp], l = st[--sp];
+        if (l.kind == 1 && r.kind == 0) st[sp++] = Node{2, r.v, l.s, {}};
+        else if (l.kind == 0 && r.kind == 1) st[sp++] = Node{2, l.v, r.s, {}}; // x*c == c*x
+        else return false;
+      } else if (op == SB_OP_ADD || op == SB_OP_SUB) {
+        const Node r = st[--sp];
+        Node l = st[--sp];
+        const double* x = nullptr;
+        double coef = 0.0;
+        if (!as_term(r, x, coef)) return false; // a +- (chain): another association
+        if (l.kind != 3) {
+          sb_chain ch;
+          if (!start_chain(l, ch)) return false;
+          l = Node{3, nullptr, 0.0, ch};
+        }
+        if (l.ch.n_terms == SB_GROUP_MAX_TERMS) return false;
+        l.ch.x[l.ch.n_terms] = x, l.ch.c[l.ch.n_terms] = coef, l.ch.sub[l.ch.n_terms] = op == SB_OP_SUB ? 1 : 0;
+        l.ch.n_terms++;
+        st[sp++] = l;
+      } else {
+        return false; // division, negation
+      }
+    }
+    if (sp != 1) return false;
+    sb_chain ch{};
+    const Node& top = st[0];
+    if (aop == SB_ASSIGN) {
+      if (top.kind == 3) ch = top.ch;
+      else if (top.kind == 0 || top.kind == 2) ch.x[0] = top.v, ch.c[0] = top.kind == 2 ? top.s : 1.0, ch.n_terms = 1;
+      else return false;
+    } else if (aop == SB_ADD_ASSIGN || aop == SB_SUB_ASSIGN) {
+      const double* x = nullptr;
+      double coef = 0.0;
+      if (!as_term(top, x, coef)) return false; // y +- (a + b) is not (y +- a) +- b
+      ch.base = y, ch.x[0] = x, ch.c[0] = coef, ch.sub[0] = aop == SB_SUB_ASSIGN ? 1 : 0, ch.n_terms = 1;
+    } else {
+      return false;
+    }
+    ch.y = y;
+    if (!stmts.empty() && (c != ctx || len != n)) flush();
+    ctx = c, n = len;
+    stmts.push_back(ch);
+    return true;
+  }
+};
+inline StatementQueue& statement_queue() {
+  static StatementQueue q;
+  return q;
+}
+/// Launch whatever is queued (no-op when nothing is, or when grouping is off).
+inline void flush() {
+  StatementQueue& q = statement_queue();
+  if (!q.stmts.empty()) q.flush();
+}
+inline void set_statement_grouping(bool on) {
+  flush();
+  statement_queue().enabled = on;
+}
+inline bool statement_grouping() { return statement_queue().enabled; }
 
 } // namespace B200
 
@@ -215,6 +358,7 @@ public:
   /// Debug accessor (one-element D2H copy). Exists so that Storm::matrix<DeviceVector> holds.
   DeviceElement operator()(size_t row, size_t = 0) const {
     double v = 0.0;
+    B200::flush();
     B200::check(sb_vec_download(_ctx, _d + row, &v, 1), "sb_vec_download");
     return DeviceElement{v};
   }
@@ -222,7 +366,10 @@ public:
     if (&other == this) return;
     release();
     allocate(other._ctx, other._n); // zero-filled
-    if (copy && _n > 0) B200::check(sb_copy(_ctx, _d, other._d, _n), "sb_copy");
+    if (copy && _n > 0) {
+      B200::flush();
+      B200::check(sb_copy(_ctx, _d, other._d, _n), "sb_copy");
+    }
   }
 
   // -- storage -----------------------------------------------------------------------------------
@@ -230,8 +377,14 @@ public:
   double* data() noexcept { return _d; }
   const double* data() const noexcept { return _d; }
   size_t size() const noexcept { return _n; }
-  void upload(const double* host) { B200::check(sb_vec_upload(_ctx, _d, host, _n), "sb_vec_upload"); }
-  void download(double* host) const { B200::check(sb_vec_download(_ctx, _d, host, _n), "sb_vec_download"); }
+  void upload(const double* host) {
+    B200::flush();
+    B200::check(sb_vec_upload(_ctx, _d, host, _n), "sb_vec_upload");
+  }
+  void download(double* host) const {
+    B200::flush();
+    B200::check(sb_vec_download(_ctx, _d, host, _n), "sb_vec_download");
+  }
   std::vector<double> to_host() const {
     std::vector<double> h(_n);
     if (_n > 0) download(h.data());
@@ -243,6 +396,8 @@ public:
     if (e.context() != nullptr && (e.context() != _ctx || e.size() != _n)) {
       throw std::runtime_error("stormb200: assignment between vectors of different size or context");
     }
+    if (B200::statement_queue().try_enqueue(_ctx, _d, _n, assign_op, e.program())) return *this;
+    B200::flush();
     B200::check(sb_eval(_ctx, _d, _n, assign_op, &e.program()), "sb_eval");
     return *this;
   }
@@ -259,6 +414,12 @@ private:
     B200::check(sb_vec_alloc(ctx, n, &_d), "sb_vec_alloc");
   }
   void release() noexcept {
+    if (_d != nullptr && !B200::statement_queue().stmts.empty()) {
+      try { // queued statements may read or write this storage
+        B200::flush();
+      } catch (...) { // release() runs in destructors
+      }
+    }
     if (_owned && _d != nullptr) sb_vec_free(_ctx, _d);
     _d = nullptr, _n = 0, _owned = false;
   }
@@ -352,14 +513,18 @@ inline double dot_impl(const DeviceVector& a, const DeviceVector& b) {
   if (a.context() != b.context() || a.size() != b.size()) {
     throw std::runtime_error("stormb200: dot_product of vectors of different size or context");
   }
-  double v = 0.0;
-  check(sb_dot(a.context(), a.data(), b.data(), a.size(), &v), "sb_dot");
+  const double v = statement_queue().reduce(a.context(), a.data(), b.data(), a.size());
   observe(v);
   return v;
 }
 inline double norm_impl(const DeviceVector& a) {
   double v = 0.0;
-  check(sb_norm2(a.context(), a.data(), a.size(), &v), "sb_norm2");
+  if (statement_queue().enabled && !statement_queue().stmts.empty()) {
+    // norm_2 = sqrt(sum |a_i|^2) (MatrixAlgorithms.hpp:262-270), the sum riding on the queued statements
+    v = std::sqrt(statement_queue().reduce(a.context(), a.data(), a.data(), a.size()));
+  } else {
+    check(sb_norm2(a.context(), a.data(), a.size(), &v), "sb_norm2");
+  }
   observe(v);
   return v;
 }
@@ -373,6 +538,7 @@ inline double norm_2(const DeviceVector& a) { return B200::norm_impl(a); }
 
 // ---- fills ---------------------------------------------------------------------------------------
 inline DeviceVector& fill_with(DeviceVector& y, double s) {
+  B200::flush();
   B200::check(sb_fill(y.context(), y.data(), y.size(), s), "sb_fill");
   return y;
 }
@@ -415,6 +581,7 @@ public:
   }
 
   void mul(DeviceVector& y, const DeviceVector& x) const override {
+    B200::flush();
     B200::check(sb_apply(_ctx, _op, x.data(), y.data()), "sb_apply");
     ++_num_applies;
   }
@@ -439,6 +606,7 @@ inline void div_grad(const FvmOperator& op, DeviceVector& u, double dt, const De
   if (u.context() != c.context() || u.size() != c.size()) {
     throw std::runtime_error("stormb200: div_grad on vectors of different size or context");
   }
+  flush();
   check(sb_apply_accumulate(op.context(), op.handle(), dt, c.data(), u.data()), "sb_apply_accumulate");
 }
 } // namespace B200
@@ -461,6 +629,7 @@ public:
   JacobiPreconditioner(sb_ctx* ctx, const sb_op* op) : _ctx{ctx}, _op{op} {}
 
   void mul(DeviceVector& y, const DeviceVector& x) const override {
+    B200::flush();
     B200::check(sb_op_jacobi(_ctx, _op, x.data(), y.data()), "sb_op_jacobi");
   }
   void conj_mul(DeviceVector& x, const DeviceVector& y) const override { mul(x, y); } // D is real

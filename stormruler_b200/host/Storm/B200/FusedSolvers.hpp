@@ -55,6 +55,7 @@ public:
       throw std::runtime_error("stormb200: fused solvers do not take a preconditioner; "
                                "use the generic solver templates");
     }
+    flush(); // queued statements (statement grouping) may produce x or b
     sb_solver_opts opts{};
     opts.num_iterations = (int64_t) num_iterations;
     opts.abs_tol = absolute_error_tolerance, opts.rel_tol = relative_error_tolerance;

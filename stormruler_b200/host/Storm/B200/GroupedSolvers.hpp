@@ -65,6 +65,7 @@ public:
     }
     std::vector<double> out(_da.size(), 0.0);
     if (_stmts.empty() && _da.empty()) return out;
+    flush(); // statements queued by the automatic grouping of DeviceVector come first
     size_t s0 = 0, d0 = 0;
     // statements in launches of at most SB_GROUP_MAX_STMT; reductions ride on the last statement launch, at most
     // SB_GROUP_MAX_DOTS per call

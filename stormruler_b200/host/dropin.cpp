@@ -270,6 +270,10 @@ DROPIN_API int dropin_cahn_hilliard_step(sb_ctx* ctx, const sb_op* faces, const 
   }
 }
 
+// Opt-in statement grouping of the generic path (Storm::B200::set_statement_grouping, DeviceVector.hpp): chain-shaped
+// statements are queued and launched as sb_eval_group together with the reduction that follows them.
+DROPIN_API void dropin_set_statement_grouping(int on) { Storm::B200::set_statement_grouping(on != 0); }
+
 // Reset the engine behind fill_randomly(DeviceVector&) to the reference's initial state.
 DROPIN_API void dropin_reset_rng(void) { Storm::B200::random_engine() = std::mt19937_64{}; }
 

@@ -101,6 +101,46 @@ def test_grouped_solvers_stop_mid_cycle_and_reject_a_preconditioner(square_nb):
             emu.solve(name, emu.EmuOp(op, diag=diag[:square_nb.n_cells].copy()), b, precond="jacobi", num_iterations=5)
 
 
+@pytest.fixture
+def grouping():
+    emu.set_statement_grouping(True)
+    yield
+    emu.set_statement_grouping(False)
+
+
+@pytest.mark.parametrize("solver", orc.REF_SOLVERS + orc.REF_NONLINEAR + ("grouped_idrs", "grouped_bicgstabl"))
+def test_automatic_statement_grouping_changes_no_bit(square_nb, grouping, solver):
+    """Storm::B200::set_statement_grouping(true): the reference templates' chain-shaped statements are queued and launched
+    as one sb_eval_group with the reduction that follows. Same iterate, history, reduction values and apply count as the
+    reference, in both reduction modes -- with fewer launches than statements."""
+    ref = {"grouped_idrs": "idrs", "grouped_bicgstabl": "bicgstabl"}.get(solver, solver)
+    op = orc.FaceOp(square_nb, prefill=1, dt=-DT)
+    b = rhs(square_nb.n_cells)
+    for mode in (orc.RED_SEQ, orc.RED_TREE):
+        kw = dict(num_iterations=50 if solver == "richardson" else 120, abs_tol=0.0, rel_tol=RTOL, mode=mode)
+        got = emu.solve(solver, emu.EmuOp(op), b, **kw)
+        c = emu.counts()
+        assert same(got, orc.ref_solve(ref, op, b, **kw)), (solver, mode)
+        assert 0 < emu.group_count() < c["eval"] + c["dot"] + c["norm"]
+
+
+def test_automatic_grouping_with_preconditioner_and_cahn_hilliard(square_nb, grouping):
+    op = orc.FaceOp(square_nb, prefill=0, dt=-1.0, dirichlet=True)
+    _, _, _, _, diag = op.rows_coef()
+    diag = diag[:square_nb.n_cells].copy()
+    b = rhs(square_nb.n_cells)
+    for solver in ("cg", "bicgstab", "tfqmr", "idrs"):
+        kw = dict(num_iterations=100, abs_tol=0.0, rel_tol=1e-10, pre_side="right")
+        want = orc.ref_solve(solver, op, b, pre=orc.JacobiOp(diag), **kw)
+        assert same(emu.solve(solver, emu.EmuOp(op, diag=diag), b, precond="jacobi", **kw), want), solver
+    g = load_golden("cahn_hilliard_square_nb.npz")
+    faces = emu.EmuOp(orc.FaceOp(square_nb.without_boundary(), prefill=0, dt=0.0))
+    res, _ = emu.cahn_hilliard_step(faces, g["c0"])
+    assert np.array_equal(res.x, g["step0_c"]) and np.array_equal(res.hist, g["step0_hist"])
+    assert emu.group_count() == 3 * 2000 + 3        # 10006 statements + 4001 dots in 6003 launches (+ 4002 applies)
+    assert emu.selftest_errors() == 3
+
+
 def test_host_layer_rejects_misuse():
     assert emu.selftest_errors() == 3
 

@@ -191,3 +191,28 @@ def test_grouped_solvers_bit_identical_to_the_reference_templates(ctx, square_nb
         assert (got.converged, got.iterations, got.n_apply) == (want.converged, want.iterations, want.n_apply)
         assert np.array_equal(got.trace, want.trace) and np.array_equal(got.hist, want.hist)
         assert np.array_equal(x.numpy(), want.x)
+
+
+@pytest.mark.parametrize("solver", ["cg", "bicgstab", "tfqmr", "idrs", "gmres"])
+def test_automatic_statement_grouping_on_the_device(ctx, square_nb, solver):
+    """Storm::B200::set_statement_grouping(true): the reference templates' statements queued and launched as
+    sb_eval_group -- same bits as without, i.e. as the reference on a host vector with the GPU reduction tree."""
+    from conftest import rhs
+    cpu = orc.FaceOp(square_nb, prefill=1, dt=-0.05)
+    gpu = sb.FvmOperator(ctx, square_nb, prefill=1, dt=-0.05, form=sb.FORM_FAITHFUL)
+    b = rhs(square_nb.n_cells)
+    want = orc.ref_solve(solver, cpu, b, num_iterations=150, abs_tol=0.0, rel_tol=1e-10, mode=orc.RED_TREE)
+    dropin.set_statement_grouping(True)
+    try:
+        launches0 = ctx.launch_count
+        x = ctx.zeros(cpu.n)
+        got = dropin.solve(solver, gpu, x, ctx.vector(b), num_iterations=150, abs_tol=0.0, rel_tol=1e-10)
+        grouped_launches = ctx.launch_count - launches0
+    finally:
+        dropin.set_statement_grouping(False)
+    assert (got.converged, got.iterations, got.n_apply) == (want.converged, want.iterations, want.n_apply)
+    assert np.array_equal(got.trace, want.trace) and np.array_equal(got.hist, want.hist)
+    assert np.array_equal(x.numpy(), want.x)
+    launches0 = ctx.launch_count
+    dropin.solve(solver, gpu, ctx.zeros(cpu.n), ctx.vector(b), num_iterations=150, abs_tol=0.0, rel_tol=1e-10)
+    assert grouped_launches < ctx.launch_count - launches0

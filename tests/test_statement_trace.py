@@ -68,6 +68,23 @@ def test_grouped_solvers_move_fewer_bytes_in_fewer_launches(counts):
     assert (gb["passes_written"], gb["launches_written"]) == (25.5, 8.5)          # 31.5 V, 15 launches as written
 
 
+def test_automatic_grouping_pass_and_launch_counts(tmp_path):
+    """What the generic path moves with Storm::B200::set_statement_grouping(true): the numbers quoted in DESIGN.md."""
+    sys.path.insert(0, ROOT)
+    from oracle import statement_trace as st
+    if not st.available():
+        pytest.skip("statement tracer not built (make -C oracle trace; needs the StormRuler sources)")
+    out = tmp_path / "grouped.json"
+    subprocess.run([sys.executable, "-m", "oracle.statement_trace", "--grouping", "--json", str(out)], check=True, cwd=ROOT,
+                   capture_output=True)
+    g = json.load(open(out))
+    want = {"cg": (11, 4), "cgs": (21, 8), "bicgstab": (22, 9), "bicgstabl": (26.5, 9.5), "tfqmr": (37, 12),
+            "tfqmr1": (27, 8), "idrs": (33.5, 9), "richardson": (6, 3)}
+    for solver, (passes, launches) in want.items():
+        assert (g[solver]["passes_written"], g[solver]["launches_written"]) == (passes, launches), (solver, g[solver])
+    assert abs(g["gmres"]["passes_written"] - 106.4) < 0.1 and abs(g["gmres"]["launches_written"] - 28.7) < 0.1
+
+
 def test_solver_sweep_contract_uses_the_traced_counts(counts):
     import importlib.util
     spec = importlib.util.spec_from_file_location("solver_sweep", os.path.join(ROOT, "scripts", "solver_sweep.py"))
