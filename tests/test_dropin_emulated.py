@@ -183,3 +183,51 @@ def test_oracle_restatement_of_the_cahn_hilliard_step_is_pinned(square_nb):
     assert np.linalg.norm(tree.x - g["step0_c"]) <= 1e-10 * np.linalg.norm(g["step0_c"])
     rel = np.abs(tree.hist - g["step0_hist"]) / g["step0_hist"]
     assert rel[:80].max() < 1e-10 and rel.max() < 1e-7
+
+
+@pytest.mark.parametrize("n", [1, 2047, 2048, 2049, 100_003, 1_200_000])
+def test_group_kernel_body_compiled_for_the_host(n):
+    """The product's own device code of sb_eval_group (csrc/sb_group_body.cuh, compiled for the host by
+    oracle/emu/group_body_host.cpp and driven thread by thread like ew_kernel + the reduction tree) against numpy,
+    statement by statement, and the oracle's restatement of the tree: chains with and without a base, + and - terms,
+    targets that are their own base or term, later statements reading earlier targets, 8-term chains, 3 fused dots.
+    Same statements as tests/test_gpu_playground.py::test_statement_group_kernel_bit_exact runs on the device."""
+    import ctypes as C
+    import os
+    from stormruler_b200 import capi
+    path = os.path.join(os.path.dirname(emu.EMU), "libgroup_body_host.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/emu/libgroup_body_host.so not built")
+    lib = C.CDLL(path)
+    rng = np.random.default_rng(n)
+    cap = -(-n // 2048) * 2048
+    names = "abcdefgh"
+    host = {k: rng.standard_normal(n) for k in names}
+    dev = {}
+    for k, v in host.items():
+        dev[k] = np.zeros(cap)
+        dev[k][:n] = v
+    ptr = lambda k: dev[k].ctypes.data_as(C.c_void_p)  # noqa: E731
+    stmts = [("a", "b", [(0.3, "c", 1), (-1.7, "d", 0), (2.5, "a", 1)]),
+             ("e", None, [(1.25, "a", 0), (0.5, "e", 0), (3.0, "f", 0)]),
+             ("g", "g", [(0.75, "e", 1)]),
+             ("h", "a", [(c, x, s) for c, x, s in zip(rng.standard_normal(8), "bcdefgab", [0, 1] * 4)])]
+    dots = [("a", "e"), ("g", "g"), ("h", "b")]
+    S = (capi.Chain * len(stmts))()
+    for k, (y, base, terms) in enumerate(stmts):
+        S[k].y, S[k].base, S[k].n_terms = ptr(y), (ptr(base) if base else None), len(terms)
+        for t, (c, x, sub) in enumerate(terms):
+            S[k].c[t], S[k].x[t], S[k].sub[t] = float(c), ptr(x), sub
+        a = None if base is None else host[base].copy()
+        for t, (c, x, sub) in enumerate(terms):
+            p = c * host[x]
+            a = p if (a is None and t == 0) else (a - p if sub else a + p)
+        host[y] = a
+    A = (C.c_void_p * 3)(*[ptr(p) for p, _ in dots])
+    B = (C.c_void_p * 3)(*[ptr(q) for _, q in dots])
+    out = np.zeros(3)
+    lib.group_body_host_run.argtypes = [C.c_size_t, C.c_int, C.POINTER(capi.Chain), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert lib.group_body_host_run(n, len(stmts), S, 3, A, B, out.ctypes.data_as(C.c_void_p)) == 0
+    for k in names:
+        assert np.array_equal(dev[k][:n], host[k]), k
+    assert np.array_equal(out, [orc.dot(host[p], host[q], orc.RED_TREE) for p, q in dots])
