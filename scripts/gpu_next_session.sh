@@ -1,0 +1,45 @@
+#!/bin/bash
+# First GPU commands of the next session (round 1 ended with no GPU minutes left while the code below was written and
+# pinned on the CPU only). Run through gpurun, one block per call; outputs go to gpurun_out/<tag>/.
+#
+#   gpurun --timeout 1500 -- 'bash scripts/gpu_next_session.sh tests'
+#   gpurun --timeout 1200 -- 'bash scripts/gpu_next_session.sh sweep'
+#   gpurun --gpus 8 --timeout 900 -- 'bash scripts/gpu_next_session.sh config4'
+#   gpurun --timeout 900 -- 'bash scripts/gpu_next_session.sh config5'
+set -u
+what=${1:-tests}
+out=gpurun_out/next_$what
+mkdir -p "$out"
+case "$what" in
+  tests)
+    # 1. everything already proven, then the tests written without a GPU (tests/conftest.py: RUN_LAST collects them last):
+    #    sb_apply_accumulate, the playground's Cahn-Hilliard step + application, sb_eval_group, grouped IDR(s)/BiCGStab(l),
+    #    automatic statement grouping. Once green: empty RUN_LAST.
+    timeout 1300 python -m pytest tests -m gpu -q 2>&1 | tail -40 > "$out/pytest_gpu.log"
+    cat "$out/pytest_gpu.log"
+    python -c "import __graft_entry__ as g; g.smoke()" > "$out/smoke.log" 2>&1; tail -5 "$out/smoke.log"
+    ;;
+  sweep)
+    # 2. what the statement groups buy at full size: reference templates as written / with automatic grouping / the
+    #    grouped classes (expected from the bytes: IDR(4) x1.29, BiCGStab(2) x1.14, GMRES(50) generic x1.25)
+    python scripts/solver_sweep.py --solvers idrs,bicgstabl,tfqmr,tfqmr1,cgs,gmres,grouped_idrs,grouped_bicgstabl \
+        --out "$out/solver_sweep_as_written.json" > "$out/as_written.log" 2>&1
+    python scripts/solver_sweep.py --grouping --solvers idrs,bicgstabl,tfqmr,tfqmr1,cgs,gmres,cg,bicgstab \
+        --out "$out/solver_sweep_grouping.json" > "$out/grouping.log" 2>&1
+    tail -3 "$out/as_written.log" "$out/grouping.log"
+    ncu --set full --clock-control none --import-source on -k regex:GroupBody -c 3 -o "$out/group_kernel" \
+        python scripts/solver_sweep.py --axis 119 --steps 4 --repeats 1 --solvers grouped_idrs > "$out/ncu.log" 2>&1
+    ;;
+  config4)
+    # 3. config 4 at full size: 49.8 M hexahedra on 8 GPUs, every rank builds its own slab (4.6 s)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 \
+        scripts/config4_projection.py --axis 368 --lattice --steps 5 > "$out/config4_368_n8_lattice.json" 2> "$out/config4.err"
+    tail -c 1500 "$out/config4_368_n8_lattice.json"
+    ;;
+  config5)
+    # 4. the 1e8 / 2e8-cell points of the apply sweep (direct lattice generator)
+    python scripts/apply_sweep.py --cells hexlat --sizes 1e8,2e8 --out "$out/apply_sweep_hexlat.json" \
+        > "$out/config5.log" 2>&1
+    tail -5 "$out/config5.log"
+    ;;
+esac
