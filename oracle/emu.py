@@ -167,6 +167,30 @@ def cahn_hilliard_step(faces: EmuOp, c, mode=orc.RED_SEQ, tau=orc.CH_TAU, Gamma=
     return res, w_hat
 
 
+def solve_non_uniform(name: str, op: EmuOp, b, shift, x0=None, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6,
+                      mode=orc.RED_SEQ) -> orc.SolveResult:
+    """dropin_solve_non_uniform on the emulator: the reference's solve_non_uniform template on Storm::DeviceVector."""
+    em, dr = _load()
+    em.emu_set_reduction_mode(mode)
+    em.emu_reset_counts()
+    dr.dropin_solve_non_uniform.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_size_t, C.POINTER(Opts), C.POINTER(Report), orc._f64p, C.c_int64]
+    dr.dropin_solve_non_uniform.restype = C.c_int
+    b, shift = np.ascontiguousarray(b, np.float64), np.ascontiguousarray(shift, np.float64)
+    n = b.shape[0]
+    x = np.zeros(n) if x0 is None else np.ascontiguousarray(x0, np.float64).copy()
+    cap_t = 64 * num_iterations + 256
+    trace = np.zeros(cap_t)
+    opts = Opts(num_iterations, abs_tol, rel_tol, 0, 0.0, 0, 0, 1)
+    rep = Report()
+    rc = dr.dropin_solve_non_uniform(name.encode(), em.emu_ctx(), op.handle, _p(x), _p(b), _p(shift), n, C.byref(opts),
+                                     C.byref(rep), trace.ctypes.data_as(orc._f64p), cap_t)
+    if rc != 0:
+        raise RuntimeError(f"dropin_solve_non_uniform({name}) failed ({rc}): {dr.dropin_last_error().decode()}")
+    return orc.SolveResult(x, bool(rep.converged), rep.iterations, rep.abs_err, rep.rel_err, np.zeros(0),
+                           trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)
+
+
 def selftest_errors() -> int:
     em, dr = _load()
     return dr.dropin_selftest_errors(em.emu_ctx())

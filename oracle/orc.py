@@ -443,6 +443,29 @@ def ref_solve(solver: str, op, b, x0=None, num_iterations=2000, abs_tol=1e-6, re
                        hist[:rep.n_hist].copy(), trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)
 
 
+def ref_solve_non_uniform(solver: str, op, b, shift, x0=None, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6,
+                          mode=RED_SEQ) -> SolveResult:
+    """The reference's solve_non_uniform (Solver.hpp:271-292) on a host vector for A(x) = op(x) + shift."""
+    R = ref()
+    R.ref_solve_non_uniform.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, _f64p, _f64p, _f64p,
+                                        C.POINTER(RefOpts), C.POINTER(RefReport), _f64p, C.c_int64]
+    R.ref_solve_non_uniform.restype = C.c_int
+    b, shift = _f64(b), _f64(shift)
+    n = b.shape[0]
+    x = np.zeros(n) if x0 is None else _f64(x0).copy()
+    cap_t = 64 * num_iterations + 256
+    trace = np.zeros(cap_t)
+    opts = RefOpts(num_iterations, abs_tol, rel_tol, 0, mode, 0.0, None, None, 1)
+    rep = RefReport()
+    f, u = op.callback
+    rc = R.ref_solve_non_uniform(solver.encode(), n, f, u, _p(b, _f64p), _p(shift, _f64p), _p(x, _f64p), C.byref(opts),
+                                 C.byref(rep), _p(trace, _f64p), cap_t)
+    if rc != 0:
+        raise ValueError(f"ref_solve_non_uniform: unknown solver {solver!r}")
+    return SolveResult(x, bool(rep.converged), rep.iterations, rep.abs_err, rep.rel_err, np.zeros(0),
+                       trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)
+
+
 # ---- the playground's Cahn-Hilliard time step (Playground.cpp:133-175) ------------------------------------------
 CH_TAU, CH_GAMMA, CH_SIGMA = 1.0e-3, 1.0e-4, 2.0   # Playground.cpp:113
 

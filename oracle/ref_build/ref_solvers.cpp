@@ -269,6 +269,40 @@ int ref_solve(const char* name, size_t n, ref_apply_fn fn, void* user, const dou
   return -1;
 }
 
+// solve_non_uniform (Solver.hpp:271-292), the reference's own function template on the host vector, for the affine
+// operator A(x) = L x + shift (L through the callback). Mirrors dropin_solve_non_uniform of the product's drop-in TU.
+int ref_solve_non_uniform(const char* name, size_t n, ref_apply_fn fn, void* user, const double* b, const double* shift,
+                          double* x, const ref_opts* o, ref_report* rep, double* trace, int64_t trace_cap) {
+  const std::string s{name};
+  HostVec xv, bv, sv;
+  xv.d.assign(x, x + n), bv.d.assign(b, b + n), sv.d.assign(shift, shift + n);
+  int64_t n_apply = 0;
+  const auto affine = Storm::make_operator<HostVec>([&](HostVec& y, const HostVec& in) {
+    fn(user, y.d.data(), in.d.data(), n);
+    y += sv;
+    ++n_apply;
+  });
+  Storm::g_trace = Storm::RefTrace{o->reduction_mode, trace, (size_t) trace_cap, 0};
+  auto run = [&](auto solver) {
+    solver.num_iterations = (size_t) o->num_iterations;
+    solver.absolute_error_tolerance = o->abs_tol, solver.relative_error_tolerance = o->rel_tol;
+    const bool converged = Storm::solve_non_uniform(solver, xv, bv, *affine);
+    std::memcpy(x, xv.d.data(), n * sizeof(double));
+    rep->converged = converged ? 1 : 0;
+    rep->iterations = (int64_t) solver.iteration;
+    rep->abs_err = solver.absolute_error, rep->rel_err = solver.relative_error;
+    rep->n_hist = 0, rep->n_trace = (int64_t) Storm::g_trace.count, rep->n_apply = n_apply;
+    Storm::g_trace = Storm::RefTrace{};
+    return 0;
+  };
+  if (s == "cg") return run(Storm::CgSolver<HostVec>{});
+  if (s == "bicgstab") return run(Storm::BiCgStabSolver<HostVec>{});
+  if (s == "gmres") return run(Storm::GmresSolver<HostVec>{});
+  if (s == "idrs") return run(Storm::IdrsSolver<HostVec>{});
+  Storm::g_trace = Storm::RefTrace{};
+  return -1;
+}
+
 // Reset the engine behind fill_randomly(HostVec&) to the reference's initial state
 // (default-seeded std::mt19937_64; the reference's own engine is a function-local static that
 // cannot be reset).

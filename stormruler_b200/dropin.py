@@ -62,6 +62,9 @@ def load():
                                                 C.c_size_t, C.POINTER(ChParams), C.POINTER(Report), capi.f64p,
                                                 C.c_int64, capi.f64p, C.c_int64]
         L.dropin_cahn_hilliard_step.restype = C.c_int
+        L.dropin_solve_non_uniform.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_size_t, C.POINTER(Opts), C.POINTER(Report), capi.f64p, C.c_int64]
+        L.dropin_solve_non_uniform.restype = C.c_int
         L.dropin_last_error.restype = C.c_char_p
         L.dropin_reset_rng.restype = None
         L.dropin_selftest_errors.argtypes = [C.c_void_p]
@@ -131,3 +134,20 @@ def cahn_hilliard_step(faces, c, c_hat, w_hat, tau=1.0e-3, Gamma=1.0e-4, sigma=2
         raise capi.StormB200Error(f"dropin_cahn_hilliard_step failed ({rc}): {L.dropin_last_error().decode()}")
     return Result(bool(rep.converged), rep.iterations, rep.abs_err, rep.rel_err,
                   hist[:min(rep.n_hist, cap_h)].copy(), trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)
+
+
+def solve_non_uniform(name: str, op, x, b, shift, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6) -> Result:
+    """The reference's solve_non_uniform (Solver.hpp:271-292) on DeviceVectors for the affine operator
+    A(x) = op(x) + shift; name: cg | bicgstab | gmres | idrs."""
+    L = load()
+    L.dropin_reset_rng()
+    cap_t = 64 * num_iterations + 256
+    trace = np.zeros(cap_t)
+    opts = Opts(num_iterations, abs_tol, rel_tol, 0, 0.0, 0, 0, 1)
+    rep = Report()
+    rc = L.dropin_solve_non_uniform(name.encode(), op.ctx.handle, op.handle, x.ptr, b.ptr, shift.ptr, x.n, C.byref(opts),
+                                    C.byref(rep), trace.ctypes.data_as(capi.f64p), cap_t)
+    if rc != 0:
+        raise capi.StormB200Error(f"dropin_solve_non_uniform({name}) failed ({rc}): {L.dropin_last_error().decode()}")
+    return Result(bool(rep.converged), rep.iterations, rep.abs_err, rep.rel_err, np.zeros(0),
+                  trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)

@@ -270,6 +270,55 @@ DROPIN_API int dropin_cahn_hilliard_step(sb_ctx* ctx, const sb_op* faces, const 
   }
 }
 
+// solve_non_uniform (Solver.hpp:271-292): an operator equation A(x) = b with an AFFINE operator, A(0) != 0 -- here
+// A(x) = L x + shift with L the uploaded FVM operator. The reference's function template, instantiated on the device
+// vector: z <- A(0), f <- b - z, then the solver runs on the "uniformed" operator y <- A(x) - z.
+DROPIN_API int dropin_solve_non_uniform(const char* name, sb_ctx* ctx, const sb_op* op, double* d_x, const double* d_b,
+                                        const double* d_shift, size_t n, const dropin_opts* o, dropin_report* rep,
+                                        double* trace, int64_t trace_cap) {
+  const std::string s{name};
+  try {
+    DeviceVector x = DeviceVector::view(ctx, d_x, n);
+    const DeviceVector b = DeviceVector::view(ctx, const_cast<double*>(d_b), n);
+    const DeviceVector shift = DeviceVector::view(ctx, const_cast<double*>(d_shift), n);
+    const Storm::FvmOperator fvm{ctx, op};
+    int64_t n_apply = 0;
+    const auto affine = Storm::make_operator<DeviceVector>([&](DeviceVector& y, const DeviceVector& in) {
+      fvm.mul(y, in);
+      y += shift;
+      ++n_apply;
+    });
+    Trace tr{trace, trace_cap, 0};
+    auto run = [&](auto solver) {
+      solver.num_iterations = (size_t) o->num_iterations;
+      solver.absolute_error_tolerance = o->abs_tol, solver.relative_error_tolerance = o->rel_tol;
+      Storm::B200::g_observer = &Trace::push, Storm::B200::g_observer_user = &tr;
+      bool converged = false;
+      try {
+        converged = Storm::solve_non_uniform(solver, x, b, *affine);
+      } catch (...) {
+        Storm::B200::g_observer = nullptr;
+        throw;
+      }
+      Storm::B200::g_observer = nullptr;
+      rep->converged = converged ? 1 : 0;
+      rep->iterations = (int64_t) solver.iteration;
+      rep->abs_err = solver.absolute_error, rep->rel_err = solver.relative_error;
+      rep->n_hist = 0, rep->n_trace = tr.count, rep->n_apply = n_apply;
+      return 0;
+    };
+    if (s == "cg") return run(Storm::CgSolver<DeviceVector>{});
+    if (s == "bicgstab") return run(Storm::BiCgStabSolver<DeviceVector>{});
+    if (s == "gmres") return run(Storm::GmresSolver<DeviceVector>{});
+    if (s == "idrs") return run(Storm::IdrsSolver<DeviceVector>{});
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -2;
+  }
+  g_error = "unknown solver name";
+  return -1;
+}
+
 // Opt-in statement grouping of the generic path (Storm::B200::set_statement_grouping, DeviceVector.hpp): chain-shaped
 // statements are queued and launched as sb_eval_group together with the reduction that follows them.
 DROPIN_API void dropin_set_statement_grouping(int on) { Storm::B200::set_statement_grouping(on != 0); }

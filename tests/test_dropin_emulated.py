@@ -141,6 +141,25 @@ def test_automatic_grouping_with_preconditioner_and_cahn_hilliard(square_nb, gro
     assert emu.selftest_errors() == 3
 
 
+@pytest.mark.parametrize("solver", ["cg", "bicgstab", "gmres", "idrs"])
+def test_solve_non_uniform_on_device_vector(square_nb, solver):
+    """solve_non_uniform (Solver.hpp:271-292: A(x) = b with A(0) != 0) instantiated on Storm::DeviceVector for the affine
+    operator A(x) = L x + shift against the same function template on a host vector -- and the solution really solves
+    the affine equation."""
+    op = orc.FaceOp(square_nb, prefill=1, dt=-DT)
+    b = rhs(square_nb.n_cells)
+    shift = np.cos(0.11 * np.arange(square_nb.n_cells))
+    for mode in (orc.RED_SEQ, orc.RED_TREE):
+        kw = dict(num_iterations=1500, abs_tol=0.0, rel_tol=1e-10, mode=mode)
+        orc.ref().ref_reset_rng()                 # IDR(s) draws its shadow vectors from fill_randomly
+        emu._load()[1].dropin_reset_rng()
+        want = orc.ref_solve_non_uniform(solver, op, b, shift, **kw)
+        got = emu.solve_non_uniform(solver, emu.EmuOp(op), b, shift, **kw)
+        assert (got.converged, got.iterations, got.n_apply) == (want.converged, want.iterations, want.n_apply)
+        assert got.converged and np.array_equal(got.trace, want.trace) and np.array_equal(got.x, want.x)
+        assert np.linalg.norm(op.apply(got.x) + shift - b) <= 1e-8 * np.linalg.norm(b - shift)
+
+
 def test_host_layer_rejects_misuse():
     assert emu.selftest_errors() == 3
 

@@ -216,3 +216,18 @@ def test_automatic_statement_grouping_on_the_device(ctx, square_nb, solver):
     launches0 = ctx.launch_count
     dropin.solve(solver, gpu, ctx.zeros(cpu.n), ctx.vector(b), num_iterations=150, abs_tol=0.0, rel_tol=1e-10)
     assert grouped_launches < ctx.launch_count - launches0
+
+
+@pytest.mark.parametrize("solver", ["cg", "idrs"])
+def test_solve_non_uniform_on_the_device(ctx, square_nb, solver):
+    """The reference's solve_non_uniform template (Solver.hpp:271-292) on DeviceVector, affine operator A(x) = L x + shift."""
+    from conftest import rhs
+    cpu = orc.FaceOp(square_nb, prefill=1, dt=-0.05)
+    gpu = sb.FvmOperator(ctx, square_nb, prefill=1, dt=-0.05, form=sb.FORM_FAITHFUL)
+    b, shift = rhs(cpu.n), np.cos(0.11 * np.arange(cpu.n))
+    orc.ref().ref_reset_rng()
+    want = orc.ref_solve_non_uniform(solver, cpu, b, shift, num_iterations=1500, abs_tol=0.0, rel_tol=1e-10, mode=orc.RED_TREE)
+    x = ctx.zeros(cpu.n)
+    got = dropin.solve_non_uniform(solver, gpu, x, ctx.vector(b), ctx.vector(shift), num_iterations=1500, abs_tol=0.0, rel_tol=1e-10)
+    assert got.converged and (got.iterations, got.n_apply) == (want.iterations, want.n_apply)
+    assert np.array_equal(got.trace, want.trace) and np.array_equal(x.numpy(), want.x)
