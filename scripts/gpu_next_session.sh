@@ -27,6 +27,10 @@ case "$what" in
     python scripts/solver_sweep.py --grouping --solvers idrs,bicgstabl,tfqmr,tfqmr1,cgs,gmres,cg,bicgstab \
         --out "$out/solver_sweep_grouping.json" > "$out/grouping.log" 2>&1
     tail -3 "$out/as_written.log" "$out/grouping.log"
+    # the playground's caller at full size, as written and with automatic grouping
+    python scripts/playground_cahn_hilliard.py --box 119 --steps 1 --max-iterations 100 --no-vtk --out "$out/ch" > "$out/ch_10M.log" 2>&1
+    python scripts/playground_cahn_hilliard.py --box 119 --steps 1 --max-iterations 100 --no-vtk --grouping --out "$out/ch" > "$out/ch_10M_grouping.log" 2>&1
+    tail -1 "$out/ch_10M.log" "$out/ch_10M_grouping.log"
     ncu --set full --clock-control none --import-source on -k regex:GroupBody -c 3 -o "$out/group_kernel" \
         python scripts/solver_sweep.py --axis 119 --steps 4 --repeats 1 --solvers grouped_idrs > "$out/ncu.log" 2>&1
     ;;

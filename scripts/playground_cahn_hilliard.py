@@ -12,6 +12,10 @@ changes of INTEGRATION.md section 8 and nothing else:
 
     python scripts/playground_cahn_hilliard.py --mesh /path/to/step.1 [--steps 3] [--out out]
     python scripts/playground_cahn_hilliard.py --generate 96 64 [--steps 3]      (writes its own Triangle files first)
+    python scripts/playground_cahn_hilliard.py --box 119 --steps 1 --max-iterations 100 --no-vtk [--grouping]
+        the same time step on a synthetic 3-D mesh (119^3 x 6 = 10.1 M jittered Kuhn tetrahedra, RCM-renumbered): what the
+        playground's caller costs at the size the Krylov benchmarks run at (per CG iteration: 2 face-ordered
+        accumulating applies, 2 + 3 element-wise statements, 2 dots)
 
 Without --renumber the cell and face order is the file's, and the iterates are those of the reference with the GPU
 reduction tree (bit-identical to the oracle, tests/test_gpu_playground.py); --renumber applies RCM first (better
@@ -85,6 +89,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mesh", default="", help="prefix of <prefix>.node/.edge/.ele (e.g. tests/_data/mesh/step.1)")
     ap.add_argument("--generate", type=int, nargs=2, metavar=("NX", "NY"), help="write a structured Triangle mesh first")
+    ap.add_argument("--box", type=int, default=0, help="synthetic 3-D tetrahedral box mesh with this many hexes per axis")
+    ap.add_argument("--grouping", action="store_true", help="Storm::B200::set_statement_grouping(true)")
     ap.add_argument("--steps", type=int, default=3, help="time steps after the initial output (the playground runs 200000)")
     ap.add_argument("--out", default="out")
     ap.add_argument("--renumber", action="store_true", help="RCM-renumber the cells before the upload")
@@ -96,15 +102,24 @@ def main():
     if args.generate:
         prefix = os.path.join(args.out, f"generated_{args.generate[0]}x{args.generate[1]}.1")
         write_triangle_files(prefix, *args.generate)
-    if not prefix:
-        ap.error("give --mesh PREFIX or --generate NX NY")
+    if not prefix and not args.box:
+        ap.error("give --mesh PREFIX, --generate NX NY or --box N")
     t0 = time.time()
-    mesh = Mesh.read_tetgen_2d(prefix[:-1] if prefix.endswith(".") else prefix)
-    n = mesh.n_cells
-    c_host = initial_condition(n)
-    if args.renumber:
-        perm = mesh.renumber_rcm()
-        c_host = c_host[perm]
+    if args.box:
+        from stormruler_b200.mesh import CELL_TET
+        mesh = Mesh.box(CELL_TET, args.box, jitter=0.2, seed_jitter=42, shuffle=True, seed_shuffle=43)
+        mesh.renumber_rcm()
+        n = mesh.n_cells
+        c_host = np.random.default_rng(1).random(n)
+    else:
+        mesh = Mesh.read_tetgen_2d(prefix[:-1] if prefix.endswith(".") else prefix)
+        n = mesh.n_cells
+        c_host = initial_condition(n)
+        if args.renumber:
+            perm = mesh.renumber_rcm()
+            c_host = c_host[perm]
+    if args.grouping:
+        dropin.set_statement_grouping(True)
     print(f"mesh has {mesh.n_faces + mesh.n_bfaces} faces\nmesh has {n} cells\nmesh loaded ({time.time() - t0:.2f} s)", flush=True)
 
     ctx = sb.Context(0)
@@ -125,8 +140,10 @@ def main():
         if not args.no_vtk:
             mesh.write_vtk(os.path.join(args.out, f"fields-{step:05d}.vtk"), {"c": c.numpy()})
     final = c.numpy()
+    cg_its = sum(r["cg_iterations"] for r in records)
     print(json.dumps({"app": "playground cahn_hilliard_solve on the device path", "cells": n, "steps": args.steps,
-                      "seconds": total_time, "c_min": float(final.min()), "c_max": float(final.max()),
+                      "statement_grouping": bool(args.grouping), "seconds": total_time,
+                      "cg_iterations_per_sec": cg_its / total_time if total_time > 0 else None, "c_min": float(final.min()), "c_max": float(final.max()),
                       "c_mean": float(final.mean()), "per_step": records}), flush=True)
     del faces, c, c_hat, w_hat
     ctx.close()
