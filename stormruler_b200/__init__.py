@@ -96,7 +96,8 @@ class Context:
         m = len(dots)
         A = (C.c_void_p * max(m, 1))(*[p[0].ptr for p in dots])
         B = (C.c_void_p * max(m, 1))(*[p[1].ptr for p in dots])
-        n = n if n is not None else dots[0][0].n
+        if n is None:
+            n = dots[0][0].n if m else 0     # an empty group is rejected by the library
         out = np.zeros(max(m, 1))
         capi.check(self.lib.sb_eval_group(self.handle, n, len(stmts), S, m, A, B, out.ctypes.data_as(capi.f64p)))
         return out[:m]
