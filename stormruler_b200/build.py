@@ -21,7 +21,7 @@ OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libstormb200.so")
 SOURCES = ["sb_api.cu", "sb_op.cu", "sb_solvers.cu", "sb_gmres.cu", "sb_comm.cu", "sb_mesh_host.cpp", "sb_part_host.cpp"]
 METIS = "/usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a"  # ships with the CUDA toolkit
-HEADERS = [os.path.join(CSRC, h) for h in ("sb_common.cuh", "sb_kernels.cuh", "sb_group_body.cuh", "sb_op.cuh", "sb_comm.cuh")] + \
+HEADERS = [os.path.join(CSRC, h) for h in ("sb_common.cuh", "sb_kernels.cuh", "sb_group_body.cuh", "sb_apply_rows.cuh", "sb_op.cuh", "sb_comm.cuh")] + \
     [os.path.join(HERE, "..", "include", "stormb200.h"), os.path.abspath(__file__)]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -250,3 +250,60 @@ def test_group_kernel_body_compiled_for_the_host(n):
     for k in names:
         assert np.array_equal(dev[k][:n], host[k]), k
     assert np.array_equal(out, [orc.dot(host[p], host[q], orc.RED_TREE) for p, q in dots])
+
+
+def _apply_rows_host():
+    import ctypes as C
+    import os
+    path = os.path.join(os.path.dirname(emu.EMU), "libapply_rows_host.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/emu/libapply_rows_host.so not built")
+    lib = C.CDLL(path)
+    lib.apply_rows_host.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+
+    def run(form, w, n, ld, col, v0, v1, diag, prefill, dt, x, y):
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        assert lib.apply_rows_host(form, w, n, ld, p(col), p(v0), p(v1), p(diag), prefill, dt, p(x), p(y)) == 0
+    return run
+
+
+@pytest.mark.parametrize("dirichlet", [False, True])
+@pytest.mark.parametrize("mesh_name", ["square_nb", "rectangle", "tets", "poly"])
+def test_apply_row_arithmetic_compiled_for_the_host(request, mesh_name, dirichlet):
+    """The product's own per-row device code (csrc/sb_apply_rows.cuh, compiled for the host) on the oracle's rows in the
+    product's layout contract: the faithful form must reproduce the reference's FACE LOOP bit for bit -- from 0, from x
+    (`c_hat <<= c_in` first) and from the old y (sb_apply_accumulate: stormDivGrad as the playground calls it) -- and
+    the coefficient form its row oracle; triangles, tetrahedra (Dirichlet ghosts) and 14-face polyhedra (rows chunked by 8)."""
+    from stormruler_b200.mesh import CELL_TET, Mesh, PolyMesh
+    run = _apply_rows_host()
+    if mesh_name == "tets":
+        m = Mesh.box(CELL_TET, 6, 5, 4, jitter=0.2)
+        m.renumber_rcm()
+    elif mesh_name == "poly":
+        m = PolyMesh.bcc(4, stretch=(1.0, 1.3, 0.7))
+    else:
+        m = request.getfixturevalue(mesh_name)
+    fm = orc.FaceMesh(m.n_cells, m.face_cell, m.face_area, m.face_dist, m.cell_vol, m.bface_cell, m.bface_area, m.bface_dist)
+    n = fm.n_cells
+    ld = -(-n // 2048) * 2048
+    rng = np.random.default_rng(3)
+    x, y0 = np.zeros(ld), np.zeros(ld)
+    x[:n], y0[:n] = rng.standard_normal(n), rng.standard_normal(n)
+    for prefill, dt in ((0, -1.0), (1, -0.05)):
+        op = orc.FaceOp(fm, prefill=prefill, dt=dt, dirichlet=dirichlet)
+        w, _, col, g, d = op.rows_faithful(ld)
+        if w not in (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16):
+            pytest.skip(f"row width {w} has no kernel instantiation")
+        y = np.full(ld, np.nan)
+        run(0, w, n, ld, col, g, d, None, prefill, dt, x, y)
+        assert np.array_equal(y[:n], op.apply(x[:n])), ("faithful", prefill)
+        # accumulate mode: the operator's own prefill / dt are overridden per call
+        for dt2 in (-1.0e-4, 0.37):
+            y = y0.copy()
+            run(0, w, n, ld, col, g, d, None, 2, dt2, x, y)
+            assert np.array_equal(y[:n], op.divgrad_accumulate(dt2, x[:n], y0[:n].copy())), ("accumulate", dt2)
+        wc, _, colc, a, diag = op.rows_coef(ld)
+        y = np.full(ld, np.nan)
+        run(1, max(wc, 1), n, ld, colc, a, None, diag, prefill, dt, x, y)
+        assert np.array_equal(y[:n], op.apply_rows_coef(x[:n], (wc, ld, colc, a, diag))), ("coef", prefill)
