@@ -136,6 +136,11 @@ SB_API int sb_op_download_rows(sb_ctx* ctx, const sb_op* op, int32_t* h_col, dou
                                double* h_val1, double* h_diag);
 /* y <- A(x): Operator::mul (Operator.hpp:74). x and y must not alias. */
 SB_API int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y);
+/* y <- A(x) and <u, y> in one kernel (the dot rides on the apply: its operands are in registers, so it costs no pass
+ * over y; SB_TREE, result on the host): what `lin_op.mul(z, p); dot_product(p, z)` (SolverCg.hpp:95-96) or
+ * `lin_op.mul(v, p); dot_product(r_tilde, v)` (SolverBiCgStab.hpp:137-139) cost when issued together. u == NULL or
+ * u == x: <x, y>. u must not alias y; x and y must not alias. Same kernels as the fused solvers' apply + dot. */
+SB_API int sb_apply_dot(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const double* u, double* h_out);
 /* y += dt * div grad x: `stormDivGrad(mesh, u, dt, c)` exactly as the playground calls it (Playground.cpp:115-131;
  * call sites :159 `stormDivGrad(mesh, w_hat, -Gamma, c_in)` after `w_hat <<= f + sigma*(c_in - c)`, and :165
  * `stormDivGrad(mesh, c_hat, -tau, w_hat)` after `c_hat <<= c_in`). Every row starts from the old y_i and adds its

@@ -114,6 +114,13 @@ def group_count() -> int:
     return int(em.emu_group_count())
 
 
+def apply_dot_count() -> int:
+    """Number of sb_apply_dot calls (an apply with the following dot riding on it) since the last solve started."""
+    em = _load()[0]
+    em.emu_apply_dot_count.restype = C.c_int64
+    return int(em.emu_apply_dot_count())
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

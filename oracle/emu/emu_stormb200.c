@@ -37,6 +37,7 @@ static char g_error[256] = "";
 static int g_mode = ORC_RED_SEQ;
 static int64_t g_calls[8]; /* eval, fill, copy, dot, norm, apply, accumulate, jacobi */
 static int64_t g_groups; /* sb_eval_group calls */
+static int64_t g_apply_dots; /* sb_apply_dot calls */
 static int g_dummy_ctx;
 
 static int fail(int code, const char* what) {
@@ -47,7 +48,8 @@ static int fail(int code, const char* what) {
 /* ---- emulator control (called by oracle/emu.py) ------------------------------------------------------------------ */
 API sb_ctx* emu_ctx(void) { return (sb_ctx*) &g_dummy_ctx; }
 API void emu_set_reduction_mode(int mode) { g_mode = mode; }
-API void emu_reset_counts(void) { memset(g_calls, 0, sizeof g_calls), g_groups = 0; }
+API void emu_reset_counts(void) { memset(g_calls, 0, sizeof g_calls), g_groups = 0, g_apply_dots = 0; }
+API int64_t emu_apply_dot_count(void) { return g_apply_dots; }
 API int64_t emu_group_count(void) { return g_groups; }
 API void emu_get_counts(int64_t out[8]) { memcpy(out, g_calls, sizeof g_calls); }
 API sb_op* emu_op_create(int64_t n, orc_apply_fn apply, void* apply_user, const orc_face_op* faces, const double* diag) {
@@ -195,6 +197,15 @@ API int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y) {
   if (x == y) return fail(SB_ERR_INVALID, "sb_apply: x and y must not alias");
   g_calls[5]++;
   op->apply(op->apply_user, y, x, (size_t) op->n);
+  return SB_OK;
+}
+API int sb_apply_dot(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const double* u, double* h_out) {
+  if (ctx == NULL || op == NULL || x == NULL || y == NULL || h_out == NULL) return fail(SB_ERR_INVALID, "null argument");
+  if (x == y || u == y) return fail(SB_ERR_INVALID, "sb_apply_dot: y must not alias x or u");
+  g_calls[5]++, g_calls[3]++;
+  g_apply_dots++;
+  op->apply(op->apply_user, y, x, (size_t) op->n);
+  *h_out = orc_dot(op->n, u != NULL ? u : x, y, g_mode);
   return SB_OK;
 }
 API int sb_apply_accumulate(sb_ctx* ctx, const sb_op* op, double dt, const double* x, double* y) {

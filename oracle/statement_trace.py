@@ -150,6 +150,17 @@ def count(stream):
             launches_fused += 1
             apply_ctx = None
             continue
+        if kind == "applydot":  # applydot y x u: the dot's operands are in the apply's registers, except u when u != x
+            close()
+            applies += 1
+            reductions += 1
+            extra = 0 if st[3] == st[2] else 1
+            written += extra
+            fused += extra
+            launches_written += 1
+            launches_fused += 1
+            apply_ctx = (st[2], st[1])
+            continue
         if kind in ("apply", "jacobi"):
             close()
             applies += kind == "apply"

@@ -1,6 +1,6 @@
 /* TEST / ANALYSIS INFRASTRUCTURE -- not product code, computes nothing.
  *
- * A logging stand-in for the 17 C-ABI entry points that stormruler_b200/host/dropin.cpp imports (include/stormb200.h).
+ * A logging stand-in for the 18 C-ABI entry points that stormruler_b200/host/dropin.cpp imports (include/stormb200.h).
  * The drop-in TU -- the reference's unmodified solver templates on Storm::DeviceVector -- is linked against this
  * library instead of libstormb200.so (oracle/Makefile, target `trace`), so every vector statement, reduction and
  * operator apply the reference's solvers issue shows up as one line of a log, with vector identities instead of data:
@@ -157,6 +157,15 @@ API int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y) {
   char line[64];
   snprintf(line, sizeof line, "apply %d %d\n", id_of(y), id_of(x));
   put(line);
+  return SB_OK;
+}
+/* applydot y x u: an apply with one dot riding on it (u: the dot's operand besides y; == x when it is the input) */
+API int sb_apply_dot(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const double* u, double* h_out) {
+  (void) ctx, (void) op;
+  char line[96];
+  snprintf(line, sizeof line, "applydot %d %d %d\n", id_of(y), id_of(x), id_of(u != NULL ? u : x));
+  put(line);
+  *h_out = 1.0;
   return SB_OK;
 }
 API int sb_apply_accumulate(sb_ctx* ctx, const sb_op* op, double dt, const double* x, double* y) {

@@ -257,6 +257,13 @@ class FvmOperator:
         """Operator::mul (Operator.hpp:74)."""
         capi.check(self.ctx.lib.sb_apply(self.ctx.handle, self.handle, x.ptr, y.ptr))
 
+    def mul_dot(self, y: DeviceVector, x: DeviceVector, u: DeviceVector | None = None) -> float:
+        """y <- A(x) and <u, y> (u None: <x, y>) in one kernel (sb_apply_dot)."""
+        out = C.c_double()
+        capi.check(self.ctx.lib.sb_apply_dot(self.ctx.handle, self.handle, x.ptr, y.ptr, u.ptr if u is not None else None,
+                                             C.byref(out)))
+        return out.value
+
     def div_grad(self, u: DeviceVector, dt: float, c: DeviceVector):
         """u += dt * div grad c: `stormDivGrad(mesh, u, dt, c)` as the playground calls it (Playground.cpp:115-131);
         faithful-form operators only (sb_apply_accumulate)."""

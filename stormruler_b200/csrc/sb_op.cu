@@ -390,6 +390,22 @@ int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y) {
   return launch_apply<0, false>(ctx, op, x, y, NoEpi{}, NoFinal{}, nullptr);
 }
 
+int sb_apply_dot(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const double* u, double* h_out) {
+  SB_REQUIRE(ctx != nullptr && op != nullptr && x != nullptr && y != nullptr && h_out != nullptr, "null argument");
+  SB_REQUIRE(x != y, "sb_apply_dot: x and y must not alias");
+  SB_REQUIRE(u != y, "sb_apply_dot: u and y must not alias (the dot reads u before y exists)");
+  const StoreFinal<1> fin{ctx->red.result};
+  if (u == nullptr || u == x) {
+    SB_TRY((launch_apply<1, false>(ctx, op, x, y, EpiXY{}, fin, nullptr)));
+  } else {
+    SB_TRY((launch_apply<1, false>(ctx, op, x, y, EpiUY{u}, fin, nullptr)));
+  }
+  SB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->red.result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *h_out = ctx->h_pinned[0];
+  return SB_OK;
+}
+
 int sb_apply_accumulate(sb_ctx* ctx, const sb_op* op, double dt, const double* x, double* y) {
   SB_REQUIRE(ctx != nullptr && op != nullptr && x != nullptr && y != nullptr, "null argument");
   SB_REQUIRE(x != y, "sb_apply_accumulate: x and y must not alias");

@@ -99,6 +99,28 @@ struct StatementQueue {
   sb_ctx* ctx = nullptr;
   size_t n = 0;
   std::vector<sb_chain> stmts;
+  /// An operator apply that has been asked for but not launched yet: if the next thing the solver does is a dot product
+  /// of its output with its input or with a third vector (`lin_op.mul(z, p); dot_product(p, z)`, SolverCg.hpp:95-96),
+  /// the two go to the device as one sb_apply_dot. Invariant: a deferred apply and queued statements never coexist
+  /// (the apply is deferred after the statements before it were launched; anything queued after it launches it first).
+  struct {
+    bool active = false;
+    sb_ctx* ctx = nullptr;
+    const sb_op* op = nullptr;
+    const double* x = nullptr;
+    double* y = nullptr;
+    size_t n = 0;
+  } apply;
+
+  void launch_apply() {
+    if (!apply.active) return;
+    apply.active = false;
+    check(sb_apply(apply.ctx, apply.op, apply.x, apply.y), "sb_apply");
+  }
+  void defer_apply(sb_ctx* c, const sb_op* op, const double* x, double* y, size_t len) {
+    flush();
+    apply.active = true, apply.ctx = c, apply.op = op, apply.x = x, apply.y = y, apply.n = len;
+  }
 
   void launch(size_t first, size_t count, const double* dot_a, const double* dot_b, double* out) {
     check(sb_eval_group(ctx, n, (int) count, count > 0 ? stmts.data() + first : nullptr, dot_a != nullptr ? 1 : 0,
@@ -106,6 +128,7 @@ struct StatementQueue {
           "sb_eval_group");
   }
   void flush() {
+    launch_apply();
     const size_t total = stmts.size(); // a failing launch must not leave the statements queued for a second attempt
     for (size_t s0 = 0; s0 < total; s0 += SB_GROUP_MAX_STMT) {
       const size_t ns = std::min<size_t>(total - s0, SB_GROUP_MAX_STMT);
@@ -121,6 +144,16 @@ struct StatementQueue {
   /// <a, b> over the vectors as they are after the queued statements: the statements and the dot in one launch.
   double reduce(sb_ctx* c, const double* a, const double* b, size_t len) {
     double v = 0.0;
+    if (apply.active) { // the dot rides on the deferred apply when exactly one of its operands is the apply's output
+      const bool ya = a == apply.y, yb = b == apply.y;
+      if (c == apply.ctx && len == apply.n && ya != yb) {
+        const double* u = ya ? b : a;
+        apply.active = false;
+        check(sb_apply_dot(apply.ctx, apply.op, apply.x, apply.y, u == apply.x ? nullptr : u, &v), "sb_apply_dot");
+        return v;
+      }
+      launch_apply();
+    }
     if (!enabled || stmts.empty() || c != ctx || len != n) {
       flush();
       check(sb_dot(c, a, b, len, &v), "sb_dot");
@@ -206,6 +239,7 @@ struct StatementQueue {
       return false;
     }
     ch.y = y;
+    launch_apply(); // the statement may read what a deferred apply writes
     if (!stmts.empty() && (c != ctx || len != n)) flush();
     ctx = c, n = len;
     stmts.push_back(ch);
@@ -219,7 +253,7 @@ inline StatementQueue& statement_queue() {
 /// Launch whatever is queued (no-op when nothing is, or when grouping is off).
 inline void flush() {
   StatementQueue& q = statement_queue();
-  if (!q.stmts.empty()) q.flush();
+  if (!q.stmts.empty() || q.apply.active) q.flush();
 }
 inline void set_statement_grouping(bool on) {
   flush();
@@ -414,7 +448,7 @@ private:
     B200::check(sb_vec_alloc(ctx, n, &_d), "sb_vec_alloc");
   }
   void release() noexcept {
-    if (_d != nullptr && !B200::statement_queue().stmts.empty()) {
+    if (_d != nullptr && (!B200::statement_queue().stmts.empty() || B200::statement_queue().apply.active)) {
       try { // queued statements may read or write this storage
         B200::flush();
       } catch (...) { // release() runs in destructors
@@ -519,7 +553,7 @@ inline double dot_impl(const DeviceVector& a, const DeviceVector& b) {
 }
 inline double norm_impl(const DeviceVector& a) {
   double v = 0.0;
-  if (statement_queue().enabled && !statement_queue().stmts.empty()) {
+  if (statement_queue().enabled && (!statement_queue().stmts.empty() || statement_queue().apply.active)) {
     // norm_2 = sqrt(sum |a_i|^2) (MatrixAlgorithms.hpp:262-270), the sum riding on the queued statements
     v = std::sqrt(statement_queue().reduce(a.context(), a.data(), a.data(), a.size()));
   } else {
@@ -581,8 +615,12 @@ public:
   }
 
   void mul(DeviceVector& y, const DeviceVector& x) const override {
-    B200::flush();
-    B200::check(sb_apply(_ctx, _op, x.data(), y.data()), "sb_apply");
+    if (B200::statement_queue().enabled) { // launched with the next statement, or together with the dot that follows
+      B200::statement_queue().defer_apply(_ctx, _op, x.data(), y.data(), x.size());
+    } else {
+      B200::flush();
+      B200::check(sb_apply(_ctx, _op, x.data(), y.data()), "sb_apply");
+    }
     ++_num_applies;
   }
 

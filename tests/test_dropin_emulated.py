@@ -122,6 +122,8 @@ def test_automatic_statement_grouping_changes_no_bit(square_nb, grouping, solver
         c = emu.counts()
         assert same(got, orc.ref_solve(ref, op, b, **kw)), (solver, mode)
         assert 0 < emu.group_count() < c["eval"] + c["dot"] + c["norm"]
+        if solver in ("cg", "bicgstab", "cgs", "idrs", "gmres"):     # `lin_op.mul(z, p); dot_product(p, z)`: one sb_apply_dot
+            assert emu.apply_dot_count() >= got.iterations - 1
 
 
 def test_automatic_grouping_with_preconditioner_and_cahn_hilliard(square_nb, grouping):

@@ -231,3 +231,22 @@ def test_solve_non_uniform_on_the_device(ctx, square_nb, solver):
     got = dropin.solve_non_uniform(solver, gpu, x, ctx.vector(b), ctx.vector(shift), num_iterations=1500, abs_tol=0.0, rel_tol=1e-10)
     assert got.converged and (got.iterations, got.n_apply) == (want.iterations, want.n_apply)
     assert np.array_equal(got.trace, want.trace) and np.array_equal(x.numpy(), want.x)
+
+
+def test_apply_with_a_riding_dot(ctx, square_nb):
+    """sb_apply_dot: y = A x and <x, y> / <u, y> from one kernel -- the same y as sb_apply, the same value as sb_dot."""
+    rng = np.random.default_rng(21)
+    n = square_nb.n_cells
+    xh, uh = rng.standard_normal(n), rng.standard_normal(n)
+    for form in (sb.FORM_COEF, sb.FORM_FAITHFUL):
+        op = sb.FvmOperator(ctx, square_nb, prefill=1, dt=-0.05, form=form)
+        x, u, y, y2 = ctx.vector(xh), ctx.vector(uh), ctx.zeros(n), ctx.zeros(n)
+        op.mul(y, x)
+        d_xy = op.mul_dot(y2, x)
+        assert np.array_equal(y2.numpy(), y.numpy()) and d_xy == ctx.dot(x, y)
+        y2.fill(0.0)
+        d_uy = op.mul_dot(y2, x, u)
+        assert np.array_equal(y2.numpy(), y.numpy()) and d_uy == ctx.dot(u, y)
+        assert d_xy == orc.dot(xh, y.numpy(), orc.RED_TREE)
+        with pytest.raises(sb.StormB200Error, match="alias"):
+            op.mul_dot(y2, x, y2)
