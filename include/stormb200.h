@@ -141,6 +141,10 @@ SB_API int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y);
  * `lin_op.mul(v, p); dot_product(r_tilde, v)` (SolverBiCgStab.hpp:137-139) cost when issued together. u == NULL or
  * u == x: <x, y>. u must not alias y; x and y must not alias. Same kernels as the fused solvers' apply + dot. */
 SB_API int sb_apply_dot(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const double* u, double* h_out);
+/* y <- A(x) with h_out[0] = <y, y> and h_out[1] = <y, x> from the same kernel: `lin_op.mul(t, r);
+ * omega = safe_divide(dot_product(t, r), dot_product(t, t))` (SolverBiCgStab.hpp:158-160; IDR(s)'s
+ * `<v,r>/<v,v>`, SolverIdrs.hpp:247-248). x and y must not alias. */
+SB_API int sb_apply_dot_yy_yx(sb_ctx* ctx, const sb_op* op, const double* x, double* y, double* h_out);
 /* y += dt * div grad x: `stormDivGrad(mesh, u, dt, c)` exactly as the playground calls it (Playground.cpp:115-131;
  * call sites :159 `stormDivGrad(mesh, w_hat, -Gamma, c_in)` after `w_hat <<= f + sigma*(c_in - c)`, and :165
  * `stormDivGrad(mesh, c_hat, -tau, w_hat)` after `c_hat <<= c_in`). Every row starts from the old y_i and adds its

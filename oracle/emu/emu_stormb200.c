@@ -208,6 +208,16 @@ API int sb_apply_dot(sb_ctx* ctx, const sb_op* op, const double* x, double* y, c
   *h_out = orc_dot(op->n, u != NULL ? u : x, y, g_mode);
   return SB_OK;
 }
+API int sb_apply_dot_yy_yx(sb_ctx* ctx, const sb_op* op, const double* x, double* y, double* h_out) {
+  if (ctx == NULL || op == NULL || x == NULL || y == NULL || h_out == NULL) return fail(SB_ERR_INVALID, "null argument");
+  if (x == y) return fail(SB_ERR_INVALID, "sb_apply_dot_yy_yx: x and y must not alias");
+  g_calls[5]++, g_calls[3] += 2;
+  g_apply_dots++;
+  op->apply(op->apply_user, y, x, (size_t) op->n);
+  h_out[0] = orc_dot(op->n, y, y, g_mode);
+  h_out[1] = orc_dot(op->n, y, x, g_mode);
+  return SB_OK;
+}
 API int sb_apply_accumulate(sb_ctx* ctx, const sb_op* op, double dt, const double* x, double* y) {
   if (ctx == NULL || op == NULL || x == NULL || y == NULL) return fail(SB_ERR_INVALID, "null argument");
   if (x == y) return fail(SB_ERR_INVALID, "sb_apply_accumulate: x and y must not alias");

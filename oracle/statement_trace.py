@@ -150,6 +150,14 @@ def count(stream):
             launches_fused += 1
             apply_ctx = None
             continue
+        if kind == "applydot2":  # apply with <y,y> and <y,x>: both dots' operands are in the apply's registers
+            close()
+            applies += 1
+            reductions += 2
+            launches_written += 1
+            launches_fused += 1
+            apply_ctx = (st[2], st[1])
+            continue
         if kind == "applydot":  # applydot y x u: the dot's operands are in the apply's registers, except u when u != x
             close()
             applies += 1

@@ -1,6 +1,6 @@
 /* TEST / ANALYSIS INFRASTRUCTURE -- not product code, computes nothing.
  *
- * A logging stand-in for the 18 C-ABI entry points that stormruler_b200/host/dropin.cpp imports (include/stormb200.h).
+ * A logging stand-in for the 19 C-ABI entry points that stormruler_b200/host/dropin.cpp imports (include/stormb200.h).
  * The drop-in TU -- the reference's unmodified solver templates on Storm::DeviceVector -- is linked against this
  * library instead of libstormb200.so (oracle/Makefile, target `trace`), so every vector statement, reduction and
  * operator apply the reference's solvers issue shows up as one line of a log, with vector identities instead of data:
@@ -166,6 +166,15 @@ API int sb_apply_dot(sb_ctx* ctx, const sb_op* op, const double* x, double* y, c
   snprintf(line, sizeof line, "applydot %d %d %d\n", id_of(y), id_of(x), id_of(u != NULL ? u : x));
   put(line);
   *h_out = 1.0;
+  return SB_OK;
+}
+/* applydot2 y x: an apply with <y,y> and <y,x> riding on it */
+API int sb_apply_dot_yy_yx(sb_ctx* ctx, const sb_op* op, const double* x, double* y, double* h_out) {
+  (void) ctx, (void) op;
+  char line[96];
+  snprintf(line, sizeof line, "applydot2 %d %d\n", id_of(y), id_of(x));
+  put(line);
+  h_out[0] = h_out[1] = 1.0;
   return SB_OK;
 }
 API int sb_apply_accumulate(sb_ctx* ctx, const sb_op* op, double dt, const double* x, double* y) {

@@ -264,6 +264,12 @@ class FvmOperator:
                                              C.byref(out)))
         return out.value
 
+    def mul_dot_yy_yx(self, y: DeviceVector, x: DeviceVector):
+        """y <- A(x); returns (<y, y>, <y, x>) from the same kernel (sb_apply_dot_yy_yx)."""
+        out = np.zeros(2)
+        capi.check(self.ctx.lib.sb_apply_dot_yy_yx(self.ctx.handle, self.handle, x.ptr, y.ptr, out.ctypes.data_as(capi.f64p)))
+        return float(out[0]), float(out[1])
+
     def div_grad(self, u: DeviceVector, dt: float, c: DeviceVector):
         """u += dt * div grad c: `stormDivGrad(mesh, u, dt, c)` as the playground calls it (Playground.cpp:115-131);
         faithful-form operators only (sb_apply_accumulate)."""

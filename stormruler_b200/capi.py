@@ -116,6 +116,7 @@ SIGNATURES = {
     "sb_op_download_rows": (C.c_int, [C.c_void_p, C.c_void_p, i32p, f64p, f64p, f64p]),
     "sb_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_apply_dot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, f64p]),
+    "sb_apply_dot_yy_yx": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, f64p]),
     "sb_apply_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "sb_op_jacobi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sb_mesh_generate_box": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_int,

@@ -406,6 +406,16 @@ int sb_apply_dot(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
   return SB_OK;
 }
 
+int sb_apply_dot_yy_yx(sb_ctx* ctx, const sb_op* op, const double* x, double* y, double* h_out) {
+  SB_REQUIRE(ctx != nullptr && op != nullptr && x != nullptr && y != nullptr && h_out != nullptr, "null argument");
+  SB_REQUIRE(x != y, "sb_apply_dot_yy_yx: x and y must not alias");
+  SB_TRY((launch_apply<2, false>(ctx, op, x, y, EpiYYandYX{}, StoreFinal<2>{ctx->red.result}, nullptr)));
+  SB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->red.result, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SB_CUDA(cudaStreamSynchronize(ctx->stream));
+  h_out[0] = ctx->h_pinned[0], h_out[1] = ctx->h_pinned[1];
+  return SB_OK;
+}
+
 int sb_apply_accumulate(sb_ctx* ctx, const sb_op* op, double dt, const double* x, double* y) {
   SB_REQUIRE(ctx != nullptr && op != nullptr && x != nullptr && y != nullptr, "null argument");
   SB_REQUIRE(x != y, "sb_apply_accumulate: x and y must not alias");

@@ -112,6 +112,17 @@ struct StatementQueue {
     size_t n = 0;
   } apply;
 
+  /// <y, x> computed by the same kernel as <y, y> (sb_apply_dot_yy_yx), kept for the dot product that follows in
+  /// `safe_divide(dot_product(t, r), dot_product(t, t))` (g++ evaluates the second argument first). Dropped by anything
+  /// that could change x or y: every such path goes through flush(), try_enqueue() or defer_apply().
+  struct {
+    bool valid = false;
+    const double* x = nullptr;
+    const double* y = nullptr;
+    size_t n = 0;
+    double yx = 0.0;
+  } spare;
+
   void launch_apply() {
     if (!apply.active) return;
     apply.active = false;
@@ -128,6 +139,7 @@ struct StatementQueue {
           "sb_eval_group");
   }
   void flush() {
+    spare.valid = false;
     launch_apply();
     const size_t total = stmts.size(); // a failing launch must not leave the statements queued for a second attempt
     for (size_t s0 = 0; s0 < total; s0 += SB_GROUP_MAX_STMT) {
@@ -144,8 +156,19 @@ struct StatementQueue {
   /// <a, b> over the vectors as they are after the queued statements: the statements and the dot in one launch.
   double reduce(sb_ctx* c, const double* a, const double* b, size_t len) {
     double v = 0.0;
+    if (spare.valid) {
+      spare.valid = false;
+      if (len == spare.n && ((a == spare.y && b == spare.x) || (a == spare.x && b == spare.y))) return spare.yx;
+    }
     if (apply.active) { // the dot rides on the deferred apply when exactly one of its operands is the apply's output
       const bool ya = a == apply.y, yb = b == apply.y;
+      if (c == apply.ctx && len == apply.n && ya && yb) { // <y, y>: take <y, x> along for the dot that usually follows
+        double both[2] = {0.0, 0.0};
+        apply.active = false;
+        check(sb_apply_dot_yy_yx(apply.ctx, apply.op, apply.x, apply.y, both), "sb_apply_dot_yy_yx");
+        spare.valid = true, spare.x = apply.x, spare.y = apply.y, spare.n = len, spare.yx = both[1];
+        return both[0];
+      }
       if (c == apply.ctx && len == apply.n && ya != yb) {
         const double* u = ya ? b : a;
         apply.active = false;
@@ -239,6 +262,7 @@ struct StatementQueue {
       return false;
     }
     ch.y = y;
+    spare.valid = false;
     launch_apply(); // the statement may read what a deferred apply writes
     if (!stmts.empty() && (c != ctx || len != n)) flush();
     ctx = c, n = len;
@@ -253,6 +277,7 @@ inline StatementQueue& statement_queue() {
 /// Launch whatever is queued (no-op when nothing is, or when grouping is off).
 inline void flush() {
   StatementQueue& q = statement_queue();
+  q.spare.valid = false;
   if (!q.stmts.empty() || q.apply.active) q.flush();
 }
 inline void set_statement_grouping(bool on) {

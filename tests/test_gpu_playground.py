@@ -250,3 +250,6 @@ def test_apply_with_a_riding_dot(ctx, square_nb):
         assert d_xy == orc.dot(xh, y.numpy(), orc.RED_TREE)
         with pytest.raises(sb.StormB200Error, match="alias"):
             op.mul_dot(y2, x, y2)
+        y2.fill(0.0)
+        yy, yx = op.mul_dot_yy_yx(y2, x)
+        assert np.array_equal(y2.numpy(), y.numpy()) and yy == ctx.dot(y, y) and yx == ctx.dot(y, x)
