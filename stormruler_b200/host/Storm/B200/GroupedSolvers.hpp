@@ -65,8 +65,20 @@ public:
     }
     std::vector<double> out(_da.size(), 0.0);
     if (_stmts.empty() && _da.empty()) return out;
-    flush(); // statements queued by the automatic grouping of DeviceVector come first
     size_t s0 = 0, d0 = 0;
+    // Under statement grouping an operator apply may still be pending (FvmOperator::mul defers it): a leading dot with
+    // its output rides on it (sb_apply_dot), and <y,x> right behind <y,y> comes from the same kernel.
+    StatementQueue& q = statement_queue();
+    if (q.enabled && q.apply.active && _stmts.empty()) {
+      out[0] = q.reduce(_ctx, _da[0], _db[0], _n);
+      d0 = 1;
+      if (_da.size() > 1 && q.spare.valid) out[1] = q.reduce(_ctx, _da[1], _db[1], _n), d0 = 2;
+    }
+    flush(); // statements queued by the automatic grouping of DeviceVector come first
+    if (d0 == _da.size() && _stmts.empty()) { // everything rode on the apply
+      finish(out);
+      return out;
+    }
     // statements in launches of at most SB_GROUP_MAX_STMT; reductions ride on the last statement launch, at most
     // SB_GROUP_MAX_DOTS per call
     do {
@@ -79,15 +91,19 @@ public:
             "sb_eval_group");
       s0 += ns, d0 += nd;
     } while (s0 < _stmts.size() || d0 < _da.size());
+    finish(out);
+    return out;
+  }
+
+private:
+
+  void finish(std::vector<double>& out) {
     for (size_t d = 0; d < out.size(); ++d) {
       if (_is_norm[d]) out[d] = std::sqrt(out[d]); // norm_2 = sqrt(sum |a_i|^2), MatrixAlgorithms.hpp:262-270
       observe(out[d]);
     }
     _stmts.clear(), _da.clear(), _db.clear(), _is_norm.clear();
-    return out;
   }
-
-private:
 
   const double* checked(const DeviceVector& v) const {
     if (v.context() != _ctx || v.size() != _n) {
