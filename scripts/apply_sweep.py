@@ -10,7 +10,9 @@ warm-up applies; GB/s = algorithmic bytes (24 N + 12 entries) / ti
 summary object at the end. `poly` = truncated octahedra (the Voronoi cells of a body-centred cubic lattice: 14 faces
 per cell, F ~ 7 N, the 14-wide instantiation of the apply kernel), ingested as a face list and RCM-renumbered.
 `hexlat` = uniform hexahedra in lattice order, face list generated directly (no node matching, no shuffle / RCM): the
-cheap way to the 1e8 and 2e8-cell points (about 15 s of host time per 1e8 cells).
+cheap way to the 1e8 and 2e8-cell points (about 15 s of host time per 1e8 cells). Under torchrun every rank builds only
+its own slab of the lattice (mesh.HexLatticeSlab: no global mesh, no partitioner), so 2e8 cells on 8 GPUs cost each rank
+what 2.5e7 cells cost one.
 """
 from __future__ import annotations
 
@@ -27,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 import stormruler_b200 as sb  # noqa: E402
 from stormruler_b200 import capi  # noqa: E402
-from stormruler_b200.mesh import CELL_HEX, CELL_TET, HexLattice, Mesh, PolyMesh  # noqa: E402
+from stormruler_b200.mesh import CELL_HEX, CELL_TET, HexLattice, HexLatticeSlab, Mesh, PolyMesh  # noqa: E402
 
 
 def axis_for(kind, cells):
@@ -61,25 +63,32 @@ def main():
             if kind == "poly":
                 mesh = PolyMesh.bcc(n_axis, stretch=(1.0, 1.3, 0.7)).to_mesh()   # face-list handle (sb_mesh_from_faces)
                 mesh.renumber_rcm()
+            elif kind == "hexlat" and world > 1:
+                mesh = None                                # rank-local: nobody holds the global mesh
+                slab = HexLatticeSlab(n_axis, n_axis, n_axis, rank, world)
             elif kind == "hexlat":
                 mesh = HexLattice(n_axis)                  # lattice order (bandwidth n^2), generated directly
-                if world > 1:
-                    mesh = Mesh.from_faces(mesh)
             else:
                 mesh = Mesh.box(CELL_TET if kind == "tet" else CELL_HEX, n_axis, jitter=0.2, seed_jitter=42, shuffle=True,
                                 seed_shuffle=43)
                 mesh.renumber_rcm()
             t_mesh = time.time() - t0
             if world > 1:
-                part = mg.partition_mesh(mesh, world, capi.PART_METIS)
-                loc = part.local(rank)
-                ctx = mg.DistContext(local_rank, rank, world, part.info.vec_capacity, n_vectors=6)
+                if mesh is None:
+                    loc, vec_capacity = slab.local, slab.info()["vec_capacity"]
+                    n_global, n_faces_global = n_axis ** 3, 3 * n_axis * n_axis * (n_axis - 1)
+                else:
+                    part = mg.partition_mesh(mesh, world, capi.PART_METIS)
+                    loc, vec_capacity = part.local(rank), part.info.vec_capacity
+                    n_global, n_faces_global = mesh.n_cells, mesh.n_faces
+                ctx = mg.DistContext(local_rank, rank, world, vec_capacity, n_vectors=6)
                 op = mg.DistOperator(ctx, loc, prefill=0, dt=-1.0, form=sb.FORM_COEF, dirichlet=True)
                 n_loc = loc.n_owned
             else:
                 ctx = sb.Context(local_rank)
                 op = sb.FvmOperator(ctx, mesh, prefill=0, dt=-1.0, form=sb.FORM_COEF, dirichlet=True)
-                n_loc = mesh.n_cells
+                n_loc = n_global = mesh.n_cells
+                n_faces_global = mesh.n_faces
             rng = np.random.default_rng(rank)
             x, y = ctx.vector(rng.standard_normal(n_loc) * 1e-3), ctx.zeros(n_loc)
 
@@ -101,8 +110,8 @@ def main():
             if dist:
                 dt_ = mg.max_over_ranks(dt_)
                 alg = mg.sum_over_ranks(alg)
-            pt = {"cell": kind, "cells": int(mesh.n_cells), "n_axis": int(n_axis), "n_gpus": world,
-                  "faces_per_cell": round(2.0 * mesh.n_faces / mesh.n_cells, 3), "width": int(op.info.width),
+            pt = {"cell": kind, "cells": int(n_global), "n_axis": int(n_axis), "n_gpus": world,
+                  "faces_per_cell": round(2.0 * n_faces_global / n_global, 3), "width": int(op.info.width),
                   "us_per_apply": dt_ * 1e6, "applies_per_sec": 1.0 / dt_, "algorithmic_bytes": alg,
                   "gbs": alg / dt_ / 1e9, "frac_of_measured_peak": alg / dt_ / 1e9 / (peak * world),
                   "frac_of_nominal_8TBs": alg / dt_ / (8e12 * world), "mesh_build_s": round(t_mesh, 1)}

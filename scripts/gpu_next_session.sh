@@ -45,5 +45,7 @@ case "$what" in
     python scripts/apply_sweep.py --cells hexlat --sizes 1e8,2e8 --out "$out/apply_sweep_hexlat.json" \
         > "$out/config5.log" 2>&1
     tail -5 "$out/config5.log"
+    # and, on an 8-GPU box: python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+    #   --master-port 29518 scripts/apply_sweep.py --cells hexlat --sizes 1e7,1e8,2e8 --out "$out/apply_sweep_hexlat_n8.json"
     ;;
 esac
