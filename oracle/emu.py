@@ -102,9 +102,9 @@ def counts() -> dict:
     return dict(zip(COUNT_NAMES, list(out)))
 
 
-def set_statement_grouping(on: bool) -> None:
+def set_statement_grouping(on) -> None:   # False / True / 2 (= on + dependency-aware scheduling)
     """Storm::B200::set_statement_grouping in the emulated drop-in (off by default)."""
-    _load()[1].dropin_set_statement_grouping(int(bool(on)))
+    _load()[1].dropin_set_statement_grouping(int(on))
 
 
 def group_count() -> int:

@@ -76,7 +76,7 @@ def statement_stream(solver: str, iterations: int, precond: int = 0, pre_side: i
     grouping: Storm::B200::set_statement_grouping(true) -- the generic path queues chain-shaped statements and
     launches them as sb_eval_group with the reduction behind them."""
     tr, dr = _load()
-    dr.dropin_set_statement_grouping(int(grouping))
+    dr.dropin_set_statement_grouping(int(grouping))  # 0 / 1 / 2
     tr.sbtrace_reset()
     n = 1000
     fake_ctx, fake_op = C.c_void_p(0x1000), C.c_void_p(0x2000)
@@ -213,7 +213,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--solvers", default=",".join(SOLVERS))
     ap.add_argument("--json", default="")
-    ap.add_argument("--grouping", action="store_true", help="with Storm::B200::set_statement_grouping(true)")
+    ap.add_argument("--grouping", nargs="?", const=1, default=0, type=int,
+                    help="with Storm::B200::set_statement_grouping(true); --grouping 2: + dependency-aware scheduling")
     args = ap.parse_args()
     if not available():
         sys.exit("tracer not built: make -C oracle trace (needs the StormRuler sources)")

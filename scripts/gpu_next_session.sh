@@ -26,7 +26,9 @@ case "$what" in
         --out "$out/solver_sweep_as_written.json" > "$out/as_written.log" 2>&1
     python scripts/solver_sweep.py --grouping --solvers idrs,bicgstabl,tfqmr,tfqmr1,cgs,gmres,cg,bicgstab \
         --out "$out/solver_sweep_grouping.json" > "$out/grouping.log" 2>&1
-    tail -3 "$out/as_written.log" "$out/grouping.log"
+    python scripts/solver_sweep.py --grouping 2 --solvers idrs,bicgstabl,tfqmr,tfqmr1,cgs,gmres,cg,bicgstab \
+        --out "$out/solver_sweep_scheduling.json" > "$out/scheduling.log" 2>&1
+    tail -3 "$out/as_written.log" "$out/grouping.log" "$out/scheduling.log"
     # the playground's caller at full size, as written and with automatic grouping
     python scripts/playground_cahn_hilliard.py --box 119 --steps 1 --max-iterations 100 --no-vtk --out "$out/ch" > "$out/ch_10M.log" 2>&1
     python scripts/playground_cahn_hilliard.py --box 119 --steps 1 --max-iterations 100 --no-vtk --grouping --out "$out/ch" > "$out/ch_10M_grouping.log" 2>&1

@@ -90,7 +90,8 @@ def main():
     ap.add_argument("--mesh", default="", help="prefix of <prefix>.node/.edge/.ele (e.g. tests/_data/mesh/step.1)")
     ap.add_argument("--generate", type=int, nargs=2, metavar=("NX", "NY"), help="write a structured Triangle mesh first")
     ap.add_argument("--box", type=int, default=0, help="synthetic 3-D tetrahedral box mesh with this many hexes per axis")
-    ap.add_argument("--grouping", action="store_true", help="Storm::B200::set_statement_grouping(true)")
+    ap.add_argument("--grouping", nargs="?", const=1, default=0, type=int,
+                    help="Storm::B200::set_statement_grouping(true); 2: + dependency-aware scheduling")
     ap.add_argument("--steps", type=int, default=3, help="time steps after the initial output (the playground runs 200000)")
     ap.add_argument("--out", default="out")
     ap.add_argument("--renumber", action="store_true", help="RCM-renumber the cells before the upload")
@@ -119,7 +120,7 @@ def main():
             perm = mesh.renumber_rcm()
             c_host = c_host[perm]
     if args.grouping:
-        dropin.set_statement_grouping(True)
+        dropin.set_statement_grouping(args.grouping)
     print(f"mesh has {mesh.n_faces + mesh.n_bfaces} faces\nmesh has {n} cells\nmesh loaded ({time.time() - t0:.2f} s)", flush=True)
 
     ctx = sb.Context(0)
@@ -142,7 +143,7 @@ def main():
     final = c.numpy()
     cg_its = sum(r["cg_iterations"] for r in records)
     print(json.dumps({"app": "playground cahn_hilliard_solve on the device path", "cells": n, "steps": args.steps,
-                      "statement_grouping": bool(args.grouping), "seconds": total_time,
+                      "statement_grouping": int(args.grouping), "seconds": total_time,
                       "cg_iterations_per_sec": cg_its / total_time if total_time > 0 else None, "c_min": float(final.min()), "c_max": float(final.max()),
                       "c_mean": float(final.mean()), "per_step": records}), flush=True)
     del faces, c, c_hat, w_hat

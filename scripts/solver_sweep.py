@@ -66,12 +66,13 @@ def main():
     ap.add_argument("--m", type=int, default=50, help="GMRES restart length")
     ap.add_argument("--solvers", default=",".join(ALL))
     ap.add_argument("--out", default="")
-    ap.add_argument("--grouping", action="store_true",
+    ap.add_argument("--grouping", nargs="?", const=1, default=0, type=int,
                     help="generic solvers with Storm::B200::set_statement_grouping(true): chain-shaped statements queued "
-                         "and launched as one sb_eval_group with the reduction behind them")
+                         "and launched as one sb_eval_group with the reduction behind them; --grouping 2: + dependency-"
+                         "aware scheduling (consumers launch only the statements they depend on)")
     args = ap.parse_args()
     if args.grouping:
-        dropin.set_statement_grouping(True)
+        dropin.set_statement_grouping(args.grouping)
     peak = 6550.0
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
@@ -141,7 +142,7 @@ def main():
         points.append(pt)
         if args.out:  # rewritten after every solver: a cut-off run keeps what it measured
             with open(args.out, "w") as f:
-                json.dump({"what": "solver sweep (SURVEY.md 8d contract bytes)", "statement_grouping": bool(args.grouping), "cell": args.cell, "cells": int(n),
+                json.dump({"what": "solver sweep (SURVEY.md 8d contract bytes)", "statement_grouping": int(args.grouping), "cell": args.cell, "cells": int(n),
                            "K": K, "repeats": args.repeats, "restart": args.m, "peak_gbs": peak, "points": points}, f, indent=1)
     ctx.close()
 

@@ -73,10 +73,10 @@ def load():
     return _lib
 
 
-def set_statement_grouping(on: bool) -> None:
+def set_statement_grouping(on) -> None:   # False / True / 2 (= on + dependency-aware scheduling)
     """Storm::B200::set_statement_grouping (DeviceVector.hpp): queue chain-shaped statements of the generic path and launch
     them as one sb_eval_group together with the reduction that follows. Off by default."""
-    load().dropin_set_statement_grouping(int(bool(on)))
+    load().dropin_set_statement_grouping(int(on))
 
 
 @dataclass

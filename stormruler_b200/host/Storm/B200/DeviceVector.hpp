@@ -37,6 +37,7 @@
 #include <concepts>
 #include <cstdint>
 #include <cstring>
+#include <initializer_list>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -96,6 +97,13 @@ inline std::mt19937_64& random_engine() {
 /// ways). Code that hands `DeviceVector::data()` to the C ABI itself must call `B200::flush()` first.
 struct StatementQueue {
   bool enabled = false;
+  /// Dependency-aware scheduling: a consumer (apply, reduction, other statement, host access) launches only the queued
+  /// statements it conflicts with -- and those they in turn depend on -- instead of everything; the rest stay queued
+  /// and join a later group (BiCGStab's `x += alpha*p` waits for `x += omega*r`, CG's for the direction update).
+  /// Statements are only ever moved past statements and launches they share no vector with in a conflicting role
+  /// (read-after-write, write-after-read, write-after-write), so every vector sees its operations in program order.
+  bool reorder = false;
+  static constexpr size_t kMaxQueued = 24;
   sb_ctx* ctx = nullptr;
   size_t n = 0;
   std::vector<sb_chain> stmts;
@@ -129,29 +137,81 @@ struct StatementQueue {
     check(sb_apply(apply.ctx, apply.op, apply.x, apply.y), "sb_apply");
   }
   void defer_apply(sb_ctx* c, const sb_op* op, const double* x, double* y, size_t len) {
-    flush();
+    const double* w = y;
+    flush_for(&x, 1, &w, 1);
+    launch_apply(); // an earlier apply that is still pending comes first
     apply.active = true, apply.ctx = c, apply.op = op, apply.x = x, apply.y = y, apply.n = len;
   }
 
-  void launch(size_t first, size_t count, const double* dot_a, const double* dot_b, double* out) {
-    check(sb_eval_group(ctx, n, (int) count, count > 0 ? stmts.data() + first : nullptr, dot_a != nullptr ? 1 : 0,
-                        dot_a != nullptr ? &dot_a : nullptr, dot_a != nullptr ? &dot_b : nullptr, out),
-          "sb_eval_group");
+  static bool reads(const sb_chain& s, const double* p) {
+    if (s.base == p) return true;
+    for (int t = 0; t < s.n_terms; ++t)
+      if (s.x[t] == p) return true;
+    return false;
   }
+  static bool depends(const sb_chain& a, const sb_chain& b) { return a.y == b.y || reads(a, b.y) || reads(b, a.y); }
+
+  /// Launch the queued statements that conflict with a consumer reading R and writing W (all of them unless `reorder`),
+  /// closed under dependencies on earlier statements, in program order, with an optional dot riding on the last
+  /// launch. Returns how many statements were launched; the others stay queued in order.
+  size_t launch_conflicting(const double* const* R, int nR, const double* const* W, int nW, const double* dot_a,
+                            const double* dot_b, double* dot_out) {
+    const size_t total = stmts.size();
+    std::vector<char> take(total, reorder ? 0 : 1);
+    if (reorder) {
+      for (size_t i = 0; i < total; ++i) {
+        const sb_chain& s = stmts[i];
+        for (int k = 0; k < nR && !take[i]; ++k) take[i] = s.y == R[k];                 // the consumer reads what s writes
+        for (int k = 0; k < nW && !take[i]; ++k) take[i] = s.y == W[k] || reads(s, W[k]); // ... or overwrites s's target / source
+      }
+      for (bool changed = true; changed;) {
+        changed = false;
+        for (size_t i = 0; i < total; ++i) {
+          if (!take[i]) continue;
+          for (size_t j = 0; j < i; ++j)
+            if (!take[j] && depends(stmts[j], stmts[i])) take[j] = 1, changed = true;
+        }
+      }
+    }
+    std::vector<sb_chain> sel, keep;
+    for (size_t i = 0; i < total; ++i) (take[i] ? sel : keep).push_back(stmts[i]);
+    stmts.swap(keep); // a failing launch must not leave the launched statements queued for a second attempt
+    const size_t ns = sel.size();
+    if (ns == 0) return 0;
+    const size_t tail = (ns - 1) / SB_GROUP_MAX_STMT * SB_GROUP_MAX_STMT; // first statement of the last launch
+    for (size_t s0 = 0; s0 < ns; s0 += SB_GROUP_MAX_STMT) {
+      const size_t cnt = std::min<size_t>(ns - s0, SB_GROUP_MAX_STMT);
+      const bool with_dot = dot_a != nullptr && s0 == tail;
+      check(sb_eval_group(ctx, n, (int) cnt, sel.data() + s0, with_dot ? 1 : 0, with_dot ? &dot_a : nullptr,
+                          with_dot ? &dot_b : nullptr, with_dot ? dot_out : nullptr),
+            "sb_eval_group");
+    }
+    return ns;
+  }
+  /// What must happen before a consumer that reads R and writes W runs.
+  void flush_for(const double* const* R, int nR, const double* const* W, int nW) {
+    spare.valid = false;
+    if (apply.active) {
+      bool conflict = !reorder;
+      for (int k = 0; k < nR; ++k) conflict |= R[k] == apply.y;
+      for (int k = 0; k < nW; ++k) conflict |= W[k] == apply.y || W[k] == apply.x;
+      if (conflict) launch_apply();
+    }
+    if (!stmts.empty()) launch_conflicting(R, nR, W, nW, nullptr, nullptr, nullptr);
+  }
+
   void flush() {
     spare.valid = false;
     launch_apply();
-    const size_t total = stmts.size(); // a failing launch must not leave the statements queued for a second attempt
-    for (size_t s0 = 0; s0 < total; s0 += SB_GROUP_MAX_STMT) {
-      const size_t ns = std::min<size_t>(total - s0, SB_GROUP_MAX_STMT);
-      try {
-        launch(s0, ns, nullptr, nullptr, nullptr);
-      } catch (...) {
-        stmts.clear();
-        throw;
-      }
+    const bool was = reorder;
+    reorder = false; // everything
+    try {
+      if (!stmts.empty()) launch_conflicting(nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr);
+    } catch (...) {
+      reorder = was;
+      throw;
     }
-    stmts.clear();
+    reorder = was;
   }
   /// <a, b> over the vectors as they are after the queued statements: the statements and the dot in one launch.
   double reduce(sb_ctx* c, const double* a, const double* b, size_t len) {
@@ -182,16 +242,8 @@ struct StatementQueue {
       check(sb_dot(c, a, b, len, &v), "sb_dot");
       return v;
     }
-    const size_t total = stmts.size();
-    const size_t tail = (total - 1) / SB_GROUP_MAX_STMT * SB_GROUP_MAX_STMT; // first statement of the last launch
-    try {
-      for (size_t s0 = 0; s0 < tail; s0 += SB_GROUP_MAX_STMT) launch(s0, SB_GROUP_MAX_STMT, nullptr, nullptr, nullptr);
-      launch(tail, total - tail, a, b, &v);
-    } catch (...) {
-      stmts.clear();
-      throw;
-    }
-    stmts.clear();
+    const double* R[2] = {a, b};
+    if (launch_conflicting(R, 2, nullptr, 0, a, b, &v) == 0) check(sb_dot(c, a, b, len, &v), "sb_dot");
     return v;
   }
   /// Queue `y (aop)= expr` if it is a chain; false: the caller flushes and launches it directly.
@@ -264,7 +316,7 @@ struct StatementQueue {
     ch.y = y;
     spare.valid = false;
     launch_apply(); // the statement may read what a deferred apply writes
-    if (!stmts.empty() && (c != ctx || len != n)) flush();
+    if (!stmts.empty() && (c != ctx || len != n || stmts.size() >= kMaxQueued)) flush();
     ctx = c, n = len;
     stmts.push_back(ch);
     return true;
@@ -280,9 +332,18 @@ inline void flush() {
   q.spare.valid = false;
   if (!q.stmts.empty() || q.apply.active) q.flush();
 }
-inline void set_statement_grouping(bool on) {
+/// Launch what a consumer reading `reads` and writing `writes` (device pointers) depends on; everything when the
+/// dependency-aware mode is off.
+inline void flush_for(std::initializer_list<const double*> reads, std::initializer_list<const double*> writes) {
+  StatementQueue& q = statement_queue();
+  q.spare.valid = false;
+  if (!q.stmts.empty() || q.apply.active) q.flush_for(reads.begin(), (int) reads.size(), writes.begin(), (int) writes.size());
+}
+/// on: queue chain-shaped statements; reorder: additionally let consumers launch only what they depend on.
+inline void set_statement_grouping(bool on, bool reorder = false) {
   flush();
   statement_queue().enabled = on;
+  statement_queue().reorder = on && reorder;
 }
 inline bool statement_grouping() { return statement_queue().enabled; }
 
@@ -417,7 +478,7 @@ public:
   /// Debug accessor (one-element D2H copy). Exists so that Storm::matrix<DeviceVector> holds.
   DeviceElement operator()(size_t row, size_t = 0) const {
     double v = 0.0;
-    B200::flush();
+    B200::flush_for({_d}, {});
     B200::check(sb_vec_download(_ctx, _d + row, &v, 1), "sb_vec_download");
     return DeviceElement{v};
   }
@@ -426,7 +487,7 @@ public:
     release();
     allocate(other._ctx, other._n); // zero-filled
     if (copy && _n > 0) {
-      B200::flush();
+      B200::flush_for({other._d}, {_d});
       B200::check(sb_copy(_ctx, _d, other._d, _n), "sb_copy");
     }
   }
@@ -437,11 +498,11 @@ public:
   const double* data() const noexcept { return _d; }
   size_t size() const noexcept { return _n; }
   void upload(const double* host) {
-    B200::flush();
+    B200::flush_for({}, {_d});
     B200::check(sb_vec_upload(_ctx, _d, host, _n), "sb_vec_upload");
   }
   void download(double* host) const {
-    B200::flush();
+    B200::flush_for({_d}, {});
     B200::check(sb_vec_download(_ctx, _d, host, _n), "sb_vec_download");
   }
   std::vector<double> to_host() const {
@@ -456,7 +517,16 @@ public:
       throw std::runtime_error("stormb200: assignment between vectors of different size or context");
     }
     if (B200::statement_queue().try_enqueue(_ctx, _d, _n, assign_op, e.program())) return *this;
-    B200::flush();
+    {
+      const sb_expr& pr = e.program(); // reads: the expression's operands (and y for += -= *= /=); writes: y
+      const double* rd[SB_EXPR_MAX_VEC + 1];
+      int nr = 0;
+      for (int k = 0; k < SB_EXPR_MAX_VEC; ++k)
+        if (pr.vec[k] != nullptr) rd[nr++] = pr.vec[k];
+      rd[nr++] = _d;
+      const double* wr = _d;
+      B200::statement_queue().flush_for(rd, nr, &wr, 1);
+    }
     B200::check(sb_eval(_ctx, _d, _n, assign_op, &e.program()), "sb_eval");
     return *this;
   }
@@ -475,7 +545,7 @@ private:
   void release() noexcept {
     if (_d != nullptr && (!B200::statement_queue().stmts.empty() || B200::statement_queue().apply.active)) {
       try { // queued statements may read or write this storage
-        B200::flush();
+        B200::flush_for({_d}, {_d});
       } catch (...) { // release() runs in destructors
       }
     }
@@ -597,7 +667,7 @@ inline double norm_2(const DeviceVector& a) { return B200::norm_impl(a); }
 
 // ---- fills ---------------------------------------------------------------------------------------
 inline DeviceVector& fill_with(DeviceVector& y, double s) {
-  B200::flush();
+  B200::flush_for({}, {y.data()});
   B200::check(sb_fill(y.context(), y.data(), y.size(), s), "sb_fill");
   return y;
 }
@@ -669,7 +739,7 @@ inline void div_grad(const FvmOperator& op, DeviceVector& u, double dt, const De
   if (u.context() != c.context() || u.size() != c.size()) {
     throw std::runtime_error("stormb200: div_grad on vectors of different size or context");
   }
-  flush();
+  flush_for({c.data(), u.data()}, {u.data()});
   check(sb_apply_accumulate(op.context(), op.handle(), dt, c.data(), u.data()), "sb_apply_accumulate");
 }
 } // namespace B200
@@ -692,7 +762,7 @@ public:
   JacobiPreconditioner(sb_ctx* ctx, const sb_op* op) : _ctx{ctx}, _op{op} {}
 
   void mul(DeviceVector& y, const DeviceVector& x) const override {
-    B200::flush();
+    B200::flush_for({x.data()}, {y.data()});
     B200::check(sb_op_jacobi(_ctx, _op, x.data(), y.data()), "sb_op_jacobi");
   }
   void conj_mul(DeviceVector& x, const DeviceVector& y) const override { mul(x, y); } // D is real

@@ -321,7 +321,8 @@ DROPIN_API int dropin_solve_non_uniform(const char* name, sb_ctx* ctx, const sb_
 
 // Opt-in statement grouping of the generic path (Storm::B200::set_statement_grouping, DeviceVector.hpp): chain-shaped
 // statements are queued and launched as sb_eval_group together with the reduction that follows them.
-DROPIN_API void dropin_set_statement_grouping(int on) { Storm::B200::set_statement_grouping(on != 0); }
+// 0: off (default), 1: on, 2: on + dependency-aware scheduling (consumers launch only the statements they depend on).
+DROPIN_API void dropin_set_statement_grouping(int on) { Storm::B200::set_statement_grouping(on != 0, on == 2); }
 
 // Reset the engine behind fill_randomly(DeviceVector&) to the reference's initial state.
 DROPIN_API void dropin_reset_rng(void) { Storm::B200::random_engine() = std::mt19937_64{}; }

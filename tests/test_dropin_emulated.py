@@ -101,10 +101,12 @@ def test_grouped_solvers_stop_mid_cycle_and_reject_a_preconditioner(square_nb):
             emu.solve(name, emu.EmuOp(op, diag=diag[:square_nb.n_cells].copy()), b, precond="jacobi", num_iterations=5)
 
 
-@pytest.fixture
-def grouping():
-    emu.set_statement_grouping(True)
-    yield
+@pytest.fixture(params=[1, 2], ids=["grouping", "grouping+scheduling"])
+def grouping(request):
+    """1: chain-shaped statements queued, everything launched at the next consumer; 2: consumers launch only what they
+    depend on (statements may wait across applies and reductions they share no vector with)."""
+    emu.set_statement_grouping(request.param)
+    yield request.param
     emu.set_statement_grouping(False)
 
 
@@ -139,8 +141,24 @@ def test_automatic_grouping_with_preconditioner_and_cahn_hilliard(square_nb, gro
     faces = emu.EmuOp(orc.FaceOp(square_nb.without_boundary(), prefill=0, dt=0.0))
     res, _ = emu.cahn_hilliard_step(faces, g["c0"])
     assert np.array_equal(res.x, g["step0_c"]) and np.array_equal(res.hist, g["step0_hist"])
-    assert emu.group_count() == 3 * 2000 + 3        # 10006 statements + 4001 dots in 6003 launches (+ 4002 applies)
+    assert emu.group_count() == 3 * 2000 + 3 + (grouping == 2)   # 10006 statements + 4001 dots (+ 4002 applies)
     assert emu.selftest_errors() == 3
+    # an affine operator through solve_non_uniform, a non-symmetric one, and stops at every position of an inner cycle
+    shift = np.cos(0.11 * np.arange(square_nb.n_cells))
+    hop = orc.FaceOp(square_nb, prefill=1, dt=-DT)
+    for solver in ("cg", "bicgstab", "idrs"):
+        orc.ref().ref_reset_rng()
+        emu._load()[1].dropin_reset_rng()
+        kw = dict(num_iterations=300, abs_tol=0.0, rel_tol=1e-10)
+        want, got = orc.ref_solve_non_uniform(solver, hop, b, shift, **kw), emu.solve_non_uniform(solver, emu.EmuOp(hop), b, shift, **kw)
+        assert (got.iterations, got.n_apply) == (want.iterations, want.n_apply) and np.array_equal(got.trace, want.trace)
+        assert np.array_equal(got.x, want.x)
+    rng = np.random.default_rng(5)
+    cd = orc.ConvDiffOp(square_nb, 0.02, rng.standard_normal(square_nb.n_faces), rng.standard_normal(square_nb.n_bfaces))
+    for solver in ("bicgstab", "bicgstabl", "tfqmr", "idrs", "gmres", "cgs"):
+        for iters in (1, 2, 3, 5, 60):
+            kw = dict(num_iterations=iters, abs_tol=0.0, rel_tol=0.0, num_inner=7 if solver == "gmres" else 0)
+            assert same(emu.solve(solver, emu.EmuOp(cd), b, **kw), orc.ref_solve(solver, cd, b, **kw)), (solver, iters)
 
 
 @pytest.mark.parametrize("solver", ["cg", "bicgstab", "gmres", "idrs"])

@@ -199,8 +199,9 @@ def test_grouped_solvers_bit_identical_to_the_reference_templates(ctx, square_nb
         assert np.array_equal(x.numpy(), want.x)
 
 
+@pytest.mark.parametrize("level", [1, 2], ids=["grouping", "grouping+scheduling"])
 @pytest.mark.parametrize("solver", ["cg", "bicgstab", "tfqmr", "idrs", "gmres"])
-def test_automatic_statement_grouping_on_the_device(ctx, square_nb, solver):
+def test_automatic_statement_grouping_on_the_device(ctx, square_nb, solver, level):
     """Storm::B200::set_statement_grouping(true): the reference templates' statements queued and launched as
     sb_eval_group -- same bits as without, i.e. as the reference on a host vector with the GPU reduction tree."""
     from conftest import rhs
@@ -208,7 +209,7 @@ def test_automatic_statement_grouping_on_the_device(ctx, square_nb, solver):
     gpu = sb.FvmOperator(ctx, square_nb, prefill=1, dt=-0.05, form=sb.FORM_FAITHFUL)
     b = rhs(square_nb.n_cells)
     want = orc.ref_solve(solver, cpu, b, num_iterations=150, abs_tol=0.0, rel_tol=1e-10, mode=orc.RED_TREE)
-    dropin.set_statement_grouping(True)
+    dropin.set_statement_grouping(level)
     try:
         launches0 = ctx.launch_count
         x = ctx.zeros(cpu.n)
