@@ -322,8 +322,9 @@ struct StatementQueue {
     return true;
   }
 };
+/// One queue per host thread (one context = one device = one host thread at a time).
 inline StatementQueue& statement_queue() {
-  static StatementQueue q;
+  static thread_local StatementQueue q;
   return q;
 }
 /// Launch whatever is queued (no-op when nothing is, or when grouping is off).
