@@ -198,6 +198,24 @@ def solve_non_uniform(name: str, op: EmuOp, b, shift, x0=None, num_iterations=20
                            trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)
 
 
+def random_program(op: EmuOp, init, seed: int, steps: int, mode=orc.RED_SEQ):
+    """dropin_random_program on the emulator under the current grouping mode: (final vectors [n_vecs, n], recorded values)."""
+    em, dr = _load()
+    em.emu_set_reduction_mode(mode)
+    em.emu_reset_counts()
+    init = np.ascontiguousarray(init, np.float64)
+    n_vecs, n = init.shape
+    final, rec, nrec = np.zeros_like(init), np.zeros(steps + 8), C.c_int64(0)
+    dr.dropin_random_program.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    dr.dropin_random_program.restype = C.c_int
+    rc = dr.dropin_random_program(em.emu_ctx(), op.handle, n, seed, steps, _p(init), n_vecs, _p(final), _p(rec), rec.shape[0],
+                                  C.byref(nrec))
+    if rc != 0:
+        raise RuntimeError(f"dropin_random_program failed ({rc}): {dr.dropin_last_error().decode()}")
+    return final, rec[:nrec.value].copy()
+
+
 def selftest_errors() -> int:
     em, dr = _load()
     return dr.dropin_selftest_errors(em.emu_ctx())

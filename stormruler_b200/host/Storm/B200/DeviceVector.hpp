@@ -231,6 +231,8 @@ struct StatementQueue {
       }
       if (c == apply.ctx && len == apply.n && ya != yb) {
         const double* u = ya ? b : a;
+        // statements still queued never touch the apply's x or y, but they may write u (dependency-aware mode)
+        if (!stmts.empty()) launch_conflicting(&u, 1, nullptr, 0, nullptr, nullptr, nullptr);
         apply.active = false;
         check(sb_apply_dot(apply.ctx, apply.op, apply.x, apply.y, u == apply.x ? nullptr : u, &v), "sb_apply_dot");
         return v;

@@ -25,8 +25,12 @@
 #include <limits>
 #include <Storm/Solvers/SolverNewton.hpp>
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <random>
 #include <string>
+#include <vector>
 
 namespace {
 
@@ -317,6 +321,76 @@ DROPIN_API int dropin_solve_non_uniform(const char* name, sb_ctx* ctx, const sb_
   }
   g_error = "unknown solver name";
   return -1;
+}
+
+// A random program over a pool of device vectors -- chain-shaped and other statements, reductions, operator applies,
+// fills, copies, pointer swaps, re-allocations, host reads -- run through the DeviceVector operators under whatever
+// statement-grouping mode is set. The tests run the same seed with grouping off, on, and on with dependency-aware
+// scheduling: every recorded value and every final vector must agree bit for bit (a scheduling mistake -- a statement
+// moved past a launch it shares a vector with -- shows up as a difference).
+DROPIN_API int dropin_random_program(sb_ctx* ctx, const sb_op* op, size_t n, uint64_t seed, int steps, const double* h_init,
+                                     int n_vecs, double* h_final, double* h_record, int64_t record_cap, int64_t* n_record) {
+  try {
+    std::mt19937_64 rng{seed};
+    auto pick = [&](int m) { return (int) (rng() % (uint64_t) m); };
+    auto coef = [&]() { return ((double) (rng() % 2001) - 1000.0) / 1250.0; }; // [-0.8, 0.8]
+    std::vector<DeviceVector> v((size_t) n_vecs);
+    for (int k = 0; k < n_vecs; ++k) {
+      v[(size_t) k] = DeviceVector{ctx, n};
+      v[(size_t) k].upload(h_init + (size_t) k * n);
+    }
+    const Storm::FvmOperator fvm{ctx, op};
+    int64_t nr = 0;
+    auto record = [&](double x) {
+      if (nr < record_cap) h_record[nr] = x;
+      ++nr;
+    };
+    for (int s = 0; s < steps; ++s) {
+      const int a = pick(n_vecs);
+      int b = pick(n_vecs), d = pick(n_vecs), e = pick(n_vecs);
+      const double c1 = coef(), c2 = coef();
+      const int kind = pick(16);
+      if (std::getenv("DROPIN_TRACE") != nullptr) std::fprintf(stderr, "step %d kind %d a %d b %d d %d e %d\n", s, kind, a, b, d, e);
+      switch (kind) {
+        case 0: v[a] <<= v[b] + c1 * v[d]; break;
+        case 1: v[a] += c1 * v[b]; break;
+        case 2: v[a] -= c1 * v[b]; break;
+        case 3: v[a] <<= c1 * v[b] + c2 * v[d]; break;
+        case 4:
+          v[a] <<= v[b] - c1 * v[d];
+          v[a] -= c2 * v[e];
+          break;
+        case 5: record(Storm::dot_product(v[a], v[b])); break;
+        case 6: record(Storm::norm_2(v[a])); break;
+        case 7:
+        case 8:
+          if (b == a) b = (a + 1) % n_vecs;
+          fvm.mul(v[a], v[b]);
+          break;
+        case 9: v[a] <<= v[b] + c1 * (v[d] - c2 * v[e]); break; // nested: not a chain
+        case 10: Storm::fill_with(v[a], c1); break;
+        case 11: v[a] /= (2.0 + c1); break;
+        case 12: std::swap(v[a], v[b]); break;
+        case 13:
+          if (b != a) v[a].assign(v[b], (rng() & 1) != 0);
+          break;
+        case 14: {
+          const std::vector<double> h = v[a].to_host();
+          double sum = 0.0;
+          for (double x : h) sum += x;
+          record(sum);
+          break;
+        }
+        default: v[a] <<= v[b]; break;
+      }
+    }
+    for (int k = 0; k < n_vecs; ++k) v[(size_t) k].download(h_final + (size_t) k * n);
+    *n_record = nr;
+    return 0;
+  } catch (const std::exception& ex) {
+    g_error = ex.what();
+    return -2;
+  }
 }
 
 // Opt-in statement grouping of the generic path (Storm::B200::set_statement_grouping, DeviceVector.hpp): chain-shaped
