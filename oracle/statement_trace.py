@@ -136,7 +136,7 @@ def count(stream):
 
     for st in stream:
         kind = st[0]
-        if kind in ("alloc", "free", "mark", "upload"):
+        if kind in ("alloc", "free", "mark", "upload", "download"):
             continue
         if kind == "group":     # group n_reads r.. n_writes w.. n_stmt n_dots: one launch over the union of its operands
             close()

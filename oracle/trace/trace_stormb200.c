@@ -1,6 +1,6 @@
 /* TEST / ANALYSIS INFRASTRUCTURE -- not product code, computes nothing.
  *
- * A logging stand-in for the 19 C-ABI entry points that stormruler_b200/host/dropin.cpp imports (include/stormb200.h).
+ * A logging stand-in for the 20 C-ABI entry points that stormruler_b200/host/dropin.cpp imports (include/stormb200.h).
  * The drop-in TU -- the reference's unmodified solver templates on Storm::DeviceVector -- is linked against this
  * library instead of libstormb200.so (oracle/Makefile, target `trace`), so every vector statement, reduction and
  * operator apply the reference's solvers issue shows up as one line of a log, with vector identities instead of data:
@@ -75,6 +75,14 @@ API int sb_vec_upload(sb_ctx* ctx, double* d, const double* h_src, size_t n) {
   char line[64];
   snprintf(line, sizeof line, "upload %d\n", id_of(d));
   put(line);
+  return SB_OK;
+}
+API int sb_vec_download(sb_ctx* ctx, const double* d, double* h_dst, size_t n) {
+  (void) ctx;
+  char line[64];
+  snprintf(line, sizeof line, "download %d\n", id_of(d));
+  put(line);
+  memset(h_dst, 0, n * sizeof(double));
   return SB_OK;
 }
 API int sb_eval(sb_ctx* ctx, double* y, size_t n, int assign_op, const sb_expr* e) {
