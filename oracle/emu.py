@@ -198,7 +198,7 @@ def solve_non_uniform(name: str, op: EmuOp, b, shift, x0=None, num_iterations=20
                            trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)
 
 
-def random_program(op: EmuOp, init, seed: int, steps: int, mode=orc.RED_SEQ):
+def random_program(op: EmuOp, init, seed: int, steps: int, mode=orc.RED_SEQ, with_accumulate=False, with_jacobi=False):
     """dropin_random_program on the emulator under the current grouping mode: (final vectors [n_vecs, n], recorded values)."""
     em, dr = _load()
     em.emu_set_reduction_mode(mode)
@@ -207,10 +207,11 @@ def random_program(op: EmuOp, init, seed: int, steps: int, mode=orc.RED_SEQ):
     n_vecs, n = init.shape
     final, rec, nrec = np.zeros_like(init), np.zeros(steps + 8), C.c_int64(0)
     dr.dropin_random_program.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_void_p, C.c_int,
-                                         C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+                                         C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int, C.c_int]
     dr.dropin_random_program.restype = C.c_int
+    final, rec = np.zeros_like(init), np.zeros(2 * steps + 8)
     rc = dr.dropin_random_program(em.emu_ctx(), op.handle, n, seed, steps, _p(init), n_vecs, _p(final), _p(rec), rec.shape[0],
-                                  C.byref(nrec))
+                                  C.byref(nrec), int(with_accumulate), int(with_jacobi))
     if rc != 0:
         raise RuntimeError(f"dropin_random_program failed ({rc}): {dr.dropin_last_error().decode()}")
     return final, rec[:nrec.value].copy()

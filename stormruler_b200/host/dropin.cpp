@@ -329,7 +329,8 @@ DROPIN_API int dropin_solve_non_uniform(const char* name, sb_ctx* ctx, const sb_
 // scheduling: every recorded value and every final vector must agree bit for bit (a scheduling mistake -- a statement
 // moved past a launch it shares a vector with -- shows up as a difference).
 DROPIN_API int dropin_random_program(sb_ctx* ctx, const sb_op* op, size_t n, uint64_t seed, int steps, const double* h_init,
-                                     int n_vecs, double* h_final, double* h_record, int64_t record_cap, int64_t* n_record) {
+                                     int n_vecs, double* h_final, double* h_record, int64_t record_cap, int64_t* n_record,
+                                     int with_accumulate, int with_jacobi) {
   try {
     std::mt19937_64 rng{seed};
     auto pick = [&](int m) { return (int) (rng() % (uint64_t) m); };
@@ -349,7 +350,7 @@ DROPIN_API int dropin_random_program(sb_ctx* ctx, const sb_op* op, size_t n, uin
       const int a = pick(n_vecs);
       int b = pick(n_vecs), d = pick(n_vecs), e = pick(n_vecs);
       const double c1 = coef(), c2 = coef();
-      const int kind = pick(16);
+      const int kind = pick(20);
       if (std::getenv("DROPIN_TRACE") != nullptr) std::fprintf(stderr, "step %d kind %d a %d b %d d %d e %d\n", s, kind, a, b, d, e);
       switch (kind) {
         case 0: v[a] <<= v[b] + c1 * v[d]; break;
@@ -381,7 +382,27 @@ DROPIN_API int dropin_random_program(sb_ctx* ctx, const sb_op* op, size_t n, uin
           record(sum);
           break;
         }
-        default: v[a] <<= v[b]; break;
+        case 15: v[a] <<= v[b]; break;
+        case 16: // stormDivGrad as the playground calls it (faithful-form operators only; skipped otherwise)
+          if (b == a) b = (a + 1) % n_vecs;
+          if (with_accumulate) Storm::B200::div_grad(fvm, v[a], 1.0e-4 * c1, v[b]); // scaled: the operator's norm is ~1e4
+          break;
+        case 17: // omega = <t,r>/<t,t> of BiCGStab: <y,y> rides on the apply and brings <y,x> along
+          if (b == a) b = (a + 1) % n_vecs;
+          fvm.mul(v[a], v[b]);
+          record(Storm::norm_2(v[a]));
+          record(Storm::dot_product(v[a], v[b]));
+          break;
+        case 18: // <r~, v> after v = A p, with an update of r~ possibly still queued
+          if (b == a) b = (a + 1) % n_vecs;
+          if (d == a) d = b;
+          v[d] += c2 * v[e == a ? b : e];
+          fvm.mul(v[a], v[b]);
+          record(Storm::dot_product(v[d], v[a]));
+          break;
+        default: // the preconditioner slot (coefficient-form operators with a diagonal only)
+          if (with_jacobi) Storm::JacobiPreconditioner{fvm}.mul(v[a], v[b]);
+          break;
       }
     }
     for (int k = 0; k < n_vecs; ++k) v[(size_t) k].download(h_final + (size_t) k * n);

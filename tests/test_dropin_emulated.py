@@ -337,7 +337,9 @@ def test_random_programs_agree_across_grouping_modes(square_nb, block):
     bit-identical whether statements are launched one by one, queued and grouped, or queued with dependency-aware
     scheduling. (This test found the one scheduling hazard the solver runs do not exercise: a dot riding on a deferred
     apply whose third operand still had a queued update.)"""
-    op = emu.EmuOp(orc.FaceOp(square_nb, prefill=1, dt=-DT))
+    face_op = orc.FaceOp(square_nb, prefill=1, dt=-1.0e-4, dirichlet=True)   # norm ~ 2: values stay finite over 300 steps
+    _, _, _, _, diag = face_op.rows_coef()
+    op = emu.EmuOp(face_op, diag=diag[:square_nb.n_cells].copy())      # accumulate + Jacobi available on the emulator
     n = square_nb.n_cells
     try:
         for seed in range(25 * block, 25 * (block + 1)):
@@ -345,9 +347,10 @@ def test_random_programs_agree_across_grouping_modes(square_nb, block):
             res = []
             for level in (0, 1, 2):
                 emu.set_statement_grouping(level)
-                final, rec = emu.random_program(op, init, seed, 300, mode=seed % 2)
+                final, rec = emu.random_program(op, init, seed, 300, mode=seed % 2, with_accumulate=True, with_jacobi=True)
                 res.append((final.view(np.uint64).copy(), rec.view(np.uint64).copy()))
             for level in (1, 2):
                 assert np.array_equal(res[0][0], res[level][0]) and np.array_equal(res[0][1], res[level][1]), (seed, level)
+            assert np.isfinite(res[0][0].view(np.float64)).all() and np.isfinite(res[0][1].view(np.float64)).all()
     finally:
         emu.set_statement_grouping(0)
