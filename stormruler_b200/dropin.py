@@ -151,3 +151,21 @@ def solve_non_uniform(name: str, op, x, b, shift, num_iterations=2000, abs_tol=1
         raise capi.StormB200Error(f"dropin_solve_non_uniform({name}) failed ({rc}): {L.dropin_last_error().decode()}")
     return Result(bool(rep.converged), rep.iterations, rep.abs_err, rep.rel_err, np.zeros(0),
                   trace[:min(rep.n_trace, cap_t)].copy(), rep.n_apply)
+
+
+def random_program(op, init, seed: int, steps: int, with_accumulate=False, with_jacobi=False):
+    """dropin_random_program (stormruler_b200/host/dropin.cpp): a seeded random program over a pool of DeviceVectors under
+    the current statement-grouping mode. init: [n_vecs, n] host array. Returns (final vectors, recorded values)."""
+    L = load()
+    init = np.ascontiguousarray(init, np.float64)
+    n_vecs, n = init.shape
+    final, rec, nrec = np.zeros_like(init), np.zeros(2 * steps + 8), C.c_int64(0)
+    L.dropin_random_program.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_int, C.c_int]
+    L.dropin_random_program.restype = C.c_int
+    rc = L.dropin_random_program(op.ctx.handle, op.handle, n, seed, steps, init.ctypes.data_as(C.c_void_p), n_vecs,
+                                 final.ctypes.data_as(C.c_void_p), rec.ctypes.data_as(C.c_void_p), rec.shape[0],
+                                 C.byref(nrec), int(with_accumulate), int(with_jacobi))
+    if rc != 0:
+        raise capi.StormB200Error(f"dropin_random_program failed ({rc}): {L.dropin_last_error().decode()}")
+    return final, rec[:nrec.value].copy()

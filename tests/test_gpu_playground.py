@@ -260,3 +260,28 @@ def test_apply_with_a_riding_dot(ctx, square_nb):
         y2.fill(0.0)
         yy, yx = op.mul_dot_yy_yx(y2, x)
         assert np.array_equal(y2.numpy(), y.numpy()) and yy == ctx.dot(y, y) and yx == ctx.dot(y, x)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_programs_on_the_device_agree_across_grouping_modes_and_with_the_emulator(ctx, square_nb, seed):
+    """The property test of tests/test_dropin_emulated.py on the device: a random program of statements, reductions,
+    applies (plain and accumulating), fills, swaps, re-allocations and host reads gives the same bits with grouping
+    off, on, and on with dependency-aware scheduling -- and the same bits as the host emulator of the C ABI with the
+    GPU reduction tree, i.e. every kernel involved honours the contract the emulator restates."""
+    from oracle import emu
+    face_cpu = orc.FaceOp(square_nb, prefill=1, dt=-1.0e-4, dirichlet=True)
+    gpu = sb.FvmOperator(ctx, square_nb, prefill=1, dt=-1.0e-4, form=sb.FORM_FAITHFUL, dirichlet=True)
+    init = np.random.default_rng(seed).standard_normal((3 + seed % 5, square_nb.n_cells))
+    res = []
+    try:
+        for level in (0, 1, 2):
+            dropin.set_statement_grouping(level)
+            final, rec = dropin.random_program(gpu, init, seed, 250, with_accumulate=True)
+            res.append((final.view(np.uint64).copy(), rec.view(np.uint64).copy()))
+    finally:
+        dropin.set_statement_grouping(0)
+    for level in (1, 2):
+        assert np.array_equal(res[0][0], res[level][0]) and np.array_equal(res[0][1], res[level][1]), level
+    if emu.available():
+        want_final, want_rec = emu.random_program(emu.EmuOp(face_cpu), init, seed, 250, mode=orc.RED_TREE, with_accumulate=True)
+        assert np.array_equal(res[0][1], want_rec.view(np.uint64)) and np.array_equal(res[0][0], want_final.view(np.uint64))
