@@ -6,6 +6,7 @@
 #   gpurun --timeout 1200 -- 'bash scripts/gpu_next_session.sh sweep'
 #   gpurun --gpus 8 --timeout 900 -- 'bash scripts/gpu_next_session.sh config4'
 #   gpurun --timeout 900 -- 'bash scripts/gpu_next_session.sh config5'
+#   gpurun --gpus 8 --timeout 900 -- 'bash scripts/gpu_next_session.sh scale8'
 set -u
 what=${1:-tests}
 out=gpurun_out/next_$what
@@ -41,6 +42,19 @@ case "$what" in
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 \
         scripts/config4_projection.py --axis 368 --lattice --steps 5 > "$out/config4_368_n8_lattice.json" 2> "$out/config4.err"
     tail -c 1500 "$out/config4_368_n8_lattice.json"
+    ;;
+  scale8)
+    # 5. the 8-GPU efficiency gap (51 % at 10.1 M cells): two cheap A/B runs before any kernel work -- programmatic
+    #    dependent launch was measured slower at 10 M cells per GPU, never at 1.26 M per rank where the 8 kernel
+    #    boundaries are 20 of 103 us; and the slab partition (2 neighbours per rank instead of up to 7)
+    for env in "SB_PDL=0" "SB_PDL=1"; do
+      env $env python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 \
+          bench.py --gpus 8 --steps 200 --warmup 20 > "$out/bench_n8_$env.json" 2> "$out/bench_n8_$env.err"
+      tail -c 600 "$out/bench_n8_$env.json"
+    done
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 \
+        bench.py --gpus 8 --steps 200 --warmup 20 --partition slab > "$out/bench_n8_slab.json" 2> "$out/bench_n8_slab.err"
+    tail -c 600 "$out/bench_n8_slab.json"
     ;;
   config5)
     # 4. the 1e8 / 2e8-cell points of the apply sweep (direct lattice generator)
