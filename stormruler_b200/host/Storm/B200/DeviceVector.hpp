@@ -320,6 +320,20 @@ struct StatementQueue {
     launch_apply(); // the statement may read what a deferred apply writes
     if (!stmts.empty() && (c != ctx || len != n || stmts.size() >= kMaxQueued)) flush();
     ctx = c, n = len;
+    // `y += a*p` right behind another update of the same y continues that chain ((y + ..) + a*p: the same roundings),
+    // so y is read and written once by the group instead of twice
+    if (!stmts.empty() && ch.base == y && stmts.back().y == y && stmts.back().n_terms + ch.n_terms <= SB_GROUP_MAX_TERMS) {
+      bool reads_y = false;
+      for (int t = 0; t < ch.n_terms; ++t) reads_y |= ch.x[t] == y;
+      if (!reads_y) {
+        sb_chain& last = stmts.back();
+        for (int t = 0; t < ch.n_terms; ++t) {
+          last.x[last.n_terms] = ch.x[t], last.c[last.n_terms] = ch.c[t], last.sub[last.n_terms] = ch.sub[t];
+          last.n_terms++;
+        }
+        return true;
+      }
+    }
     stmts.push_back(ch);
     return true;
   }

@@ -84,7 +84,7 @@ def test_automatic_grouping_pass_and_launch_counts(tmp_path):
             "grouped_idrs": (29.75, 5.5), "grouped_bicgstabl": (25.0, 8.0)}
     for solver, (passes, launches) in want.items():
         assert (g[solver]["passes_written"], g[solver]["launches_written"]) == (passes, launches), (solver, g[solver])
-    assert abs(g["gmres"]["passes_written"] - 105.4) < 0.1 and abs(g["gmres"]["launches_written"] - 27.7) < 0.1
+    assert abs(g["gmres"]["passes_written"] - 105.1) < 0.1 and abs(g["gmres"]["launches_written"] - 27.6) < 0.1
     # CG from the reference's unmodified template now runs the hand-fused schedule: B + 9V in 3 launches
     assert (g["cg"]["applies"], g["cg"]["reductions"]) == (1, 2)
 
@@ -92,7 +92,7 @@ def test_automatic_grouping_pass_and_launch_counts(tmp_path):
 def test_dependency_aware_scheduling_pass_counts(tmp_path):
     """set_statement_grouping(true, reorder = true): consumers launch only the queued statements they depend on. The
     reference's unmodified templates then move fewer bytes than the hand-written schedules in two cases (CG 8 V vs 9 V,
-    IDR(4) 27.25 V vs 29.75 V); the numbers quoted in DESIGN.md."""
+    IDR(4) 26 V vs 29.75 V); the numbers quoted in DESIGN.md."""
     sys.path.insert(0, ROOT)
     from oracle import statement_trace as st
     if not st.available():
@@ -102,7 +102,7 @@ def test_dependency_aware_scheduling_pass_counts(tmp_path):
                    cwd=ROOT, capture_output=True)
     g = json.load(open(out))
     want = {"cg": (8, 3), "cgs": (20, 8), "bicgstab": (16, 6), "bicgstabl": (23.5, 8.5), "tfqmr": (35, 12),
-            "tfqmr1": (25, 8), "idrs": (27.25, 7.75), "richardson": (6, 3)}
+            "tfqmr1": (25, 8), "idrs": (26.0, 7.5), "richardson": (6, 3)}
     for solver, (passes, launches) in want.items():
         assert (g[solver]["passes_written"], g[solver]["launches_written"]) == (passes, launches), (solver, g[solver])
 
