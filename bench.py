@@ -138,6 +138,47 @@ def cpu_reference_rate(mesh, x_star, solver, budget_s=20.0, max_iters=None):
     return rate, kind, iters, t_n
 
 
+def cpu_all_cores_rate(mesh, x_star, solver, budget_s=6.0):
+    """The same iteration on every host core: an OpenMP port on the operator's coefficient rows
+    (oracle/sb_oracle_omp.c; the reference itself has no threading). Measurement aid only: its 5-iteration residual is
+    checked against the single-threaded reference before the time is quoted. Returns a cpu_baseline-shaped dict."""
+    import ctypes as C
+    from oracle import orc
+    path = os.path.join(ROOT, "oracle", "liboracle_omp.so")
+    if not os.path.exists(path):
+        return {"unavailable": "oracle/liboracle_omp.so not built"}
+    L = C.CDLL(path)
+    L.orc_omp_solve.restype = C.c_double
+    L.orc_omp_threads.restype = C.c_int
+    fm = orc.FaceMesh(mesh.n_cells, mesh.face_cell, mesh.face_area, mesh.face_dist, mesh.cell_vol,
+                      mesh.bface_cell, mesh.bface_area, mesh.bface_dist)
+    op = orc.FaceOp(fm, prefill=0, dt=-1.0, dirichlet=True)
+    b = op.apply(x_star)
+    w, ld, col, a, diag = op.rows_coef()
+    n = mesh.n_cells
+    ptr = lambda arr: arr.ctypes.data_as(C.c_void_p)  # noqa: E731
+    kind = {"cg": 0, "bicgstab": 1}[solver]
+
+    def run(iters):
+        x = np.zeros(n)
+        secs = C.c_double()
+        err = L.orc_omp_solve(kind, C.c_int64(n), int(w), C.c_int64(ld), ptr(col), ptr(a), ptr(diag), ptr(b), ptr(x),
+                              C.c_int64(iters), C.byref(secs))
+        return err, secs.value
+
+    err5, t5 = run(5)
+    run_ref = orc.ref_solve if orc.have_ref() else orc.solve
+    want = run_ref(solver, op, b, num_iterations=5, abs_tol=0.0, rel_tol=0.0).abs_err
+    if not abs(err5 - want) <= 1e-9 * abs(want):
+        return {"unavailable": f"port disagrees with the reference after 5 iterations ({err5!r} vs {want!r})"}
+    iters = int(max(10, min(budget_s / max(t5 / 5.0, 1e-6), 5000)))
+    _, t = run(iters)
+    return {"value": iters / max(t, 1e-9), "unit": "it/s", "cores": int(L.orc_omp_threads()), "kind": "port",
+            "sample": f"{iters} {solver} iterations of the same {n}-cell problem ({t:.1f} s), OpenMP port of the reference's "
+                      f"statement sequence on the coefficient rows (oracle/sb_oracle_omp.c, gcc -O2 -fopenmp), all host "
+                      f"threads; residual after 5 iterations equal to the single-threaded reference's within 1e-9"}
+
+
 # ---------------------------------------------------------------------------------------------------
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -266,6 +307,13 @@ def run_own_arm(args):
                          f"solver headers + face-loop operator, g++ -O2 -ffp-contract=off, 1 thread "
                          f"(the reference is single-threaded by construction)"}
 
+    cpu_all = None
+    if not args.no_cpu_baseline:
+        try:   # an extra, never allowed to take the bench line down
+            cpu_all = cpu_all_cores_rate(mesh, x_star, args.solver)
+        except Exception as e:  # noqa: BLE001
+            cpu_all = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
     line = {
         "metric": "krylov_iterations_per_sec", "value": value, "unit": "it/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": rep_ms / args.steps,
@@ -282,6 +330,7 @@ def run_own_arm(args):
         "kernel_ms_per_iteration": {nm: kms[k] / args.steps for k, nm in enumerate(slots)},
         "applies_per_sec": applies_per_it * value,
         "cpu_baseline": cpu,
+        "cpu_baseline_all_cores": cpu_all,
         "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": 16 * n / args.steps,
                 "d2h_bytes_per_step": 8 * n / args.steps,
                 "note": f"one sb_solve_host call = H2D(x0,b) + init + {args.steps} iterations + D2H(x), pinned host buffers"},
