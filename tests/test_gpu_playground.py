@@ -17,9 +17,67 @@ from stormruler_b200 import mesh as sbmesh
 pytestmark = pytest.mark.gpu
 
 
+# Order: the tests that only involve kernels already proven on the device come first (pytest -x).
 def _random_state(n, seed):
     rng = np.random.default_rng(seed)
     return rng.standard_normal(n), rng.standard_normal(n)
+
+
+def _chain_host(vals, y, base, terms):
+    a = None if base is None else vals[base].copy()
+    for t, (c, x, sub) in enumerate(terms):
+        p = c * vals[x]
+        a = p if (a is None and t == 0) else (a - p if sub else a + p)
+    vals[y] = a
+
+
+def test_traced_map_program_of_dF_dc(ctx):
+    """The postfix program B200::map records for the playground's dF_dc (2.0*c*(c-1.0)*(2.0*c-1.0), constants
+    deduplicated): S0 V0 MUL V0 S1 SUB MUL S0 V0 MUL S1 SUB MUL -- run through sb_eval's run-time interpreter."""
+    rng = np.random.default_rng(8)
+    c = rng.random(5000)
+    S0, S1, V0 = sb.capi.OP_SCAL0, sb.capi.OP_SCAL0 + 1, sb.capi.OP_VEC0
+    MUL, SUB = sb.capi.OP_MUL, sb.capi.OP_SUB
+    cv, f = ctx.vector(c), ctx.zeros(c.shape[0])
+    ctx.eval(f, sb.ASSIGN, [S0, V0, MUL, V0, S1, SUB, MUL, S0, V0, MUL, S1, SUB, MUL], [cv], [2.0, 1.0])
+    assert np.array_equal(f.numpy(), orc.ch_dF_dc(c))
+
+
+@pytest.mark.parametrize("solver", ["cg", "idrs"])
+def test_solve_non_uniform_on_the_device(ctx, square_nb, solver):
+    """The reference's solve_non_uniform template (Solver.hpp:271-292) on DeviceVector, affine operator A(x) = L x + shift."""
+    from conftest import rhs
+    cpu = orc.FaceOp(square_nb, prefill=1, dt=-0.05)
+    gpu = sb.FvmOperator(ctx, square_nb, prefill=1, dt=-0.05, form=sb.FORM_FAITHFUL)
+    b, shift = rhs(cpu.n), np.cos(0.11 * np.arange(cpu.n))
+    orc.ref().ref_reset_rng()
+    want = orc.ref_solve_non_uniform(solver, cpu, b, shift, num_iterations=1500, abs_tol=0.0, rel_tol=1e-10, mode=orc.RED_TREE)
+    x = ctx.zeros(cpu.n)
+    got = dropin.solve_non_uniform(solver, gpu, x, ctx.vector(b), ctx.vector(shift), num_iterations=1500, abs_tol=0.0, rel_tol=1e-10)
+    assert got.converged and (got.iterations, got.n_apply) == (want.iterations, want.n_apply)
+    assert np.array_equal(got.trace, want.trace) and np.array_equal(x.numpy(), want.x)
+
+
+def test_apply_with_a_riding_dot(ctx, square_nb):
+    """sb_apply_dot: y = A x and <x, y> / <u, y> from one kernel -- the same y as sb_apply, the same value as sb_dot."""
+    rng = np.random.default_rng(21)
+    n = square_nb.n_cells
+    xh, uh = rng.standard_normal(n), rng.standard_normal(n)
+    for form in (sb.FORM_COEF, sb.FORM_FAITHFUL):
+        op = sb.FvmOperator(ctx, square_nb, prefill=1, dt=-0.05, form=form)
+        x, u, y, y2 = ctx.vector(xh), ctx.vector(uh), ctx.zeros(n), ctx.zeros(n)
+        op.mul(y, x)
+        d_xy = op.mul_dot(y2, x)
+        assert np.array_equal(y2.numpy(), y.numpy()) and d_xy == ctx.dot(x, y)
+        y2.fill(0.0)
+        d_uy = op.mul_dot(y2, x, u)
+        assert np.array_equal(y2.numpy(), y.numpy()) and d_uy == ctx.dot(u, y)
+        assert d_xy == orc.dot(xh, y.numpy(), orc.RED_TREE)
+        with pytest.raises(sb.StormB200Error, match="alias"):
+            op.mul_dot(y2, x, y2)
+        y2.fill(0.0)
+        yy, yx = op.mul_dot_yy_yx(y2, x)
+        assert np.array_equal(y2.numpy(), y.numpy()) and yy == ctx.dot(y, y) and yx == ctx.dot(y, x)
 
 
 @pytest.mark.parametrize("dirichlet", [False, True])
@@ -70,18 +128,6 @@ def test_div_grad_needs_the_faithful_form_and_distinct_vectors(ctx, square_nb):
     faithful = sb.FvmOperator(ctx, square_nb, prefill=0, dt=0.0, form=sb.FORM_FAITHFUL)
     with pytest.raises(sb.StormB200Error, match="alias"):
         faithful.div_grad(u, -1.0, u)
-
-
-def test_traced_map_program_of_dF_dc(ctx):
-    """The postfix program B200::map records for the playground's dF_dc (2.0*c*(c-1.0)*(2.0*c-1.0), constants
-    deduplicated): S0 V0 MUL V0 S1 SUB MUL S0 V0 MUL S1 SUB MUL -- run through sb_eval's run-time interpreter."""
-    rng = np.random.default_rng(8)
-    c = rng.random(5000)
-    S0, S1, V0 = sb.capi.OP_SCAL0, sb.capi.OP_SCAL0 + 1, sb.capi.OP_VEC0
-    MUL, SUB = sb.capi.OP_MUL, sb.capi.OP_SUB
-    cv, f = ctx.vector(c), ctx.zeros(c.shape[0])
-    ctx.eval(f, sb.ASSIGN, [S0, V0, MUL, V0, S1, SUB, MUL, S0, V0, MUL, S1, SUB, MUL], [cv], [2.0, 1.0])
-    assert np.array_equal(f.numpy(), orc.ch_dF_dc(c))
 
 
 def test_playground_cahn_hilliard_step_on_the_device(ctx, square_nb):
@@ -135,15 +181,6 @@ def test_playground_driver_end_to_end(tmp_path):
     for k in range(3):
         text = (tmp_path / f"fields-{k:05d}.vtk").read_text()
         assert text.startswith("# vtk DataFile Version 2.0\n") and "SCALARS c double 1" in text
-
-
-# ---- statement groups (sb_eval_group) and the grouped IDR(s) / BiCGStab(l) ------------------------------------------------
-def _chain_host(vals, y, base, terms):
-    a = None if base is None else vals[base].copy()
-    for t, (c, x, sub) in enumerate(terms):
-        p = c * vals[x]
-        a = p if (a is None and t == 0) else (a - p if sub else a + p)
-    vals[y] = a
 
 
 @pytest.mark.parametrize("n", [1, 2047, 2048, 2049, 100_003])
@@ -223,43 +260,6 @@ def test_automatic_statement_grouping_on_the_device(ctx, square_nb, solver, leve
     launches0 = ctx.launch_count
     dropin.solve(solver, gpu, ctx.zeros(cpu.n), ctx.vector(b), num_iterations=150, abs_tol=0.0, rel_tol=1e-10)
     assert grouped_launches < ctx.launch_count - launches0
-
-
-@pytest.mark.parametrize("solver", ["cg", "idrs"])
-def test_solve_non_uniform_on_the_device(ctx, square_nb, solver):
-    """The reference's solve_non_uniform template (Solver.hpp:271-292) on DeviceVector, affine operator A(x) = L x + shift."""
-    from conftest import rhs
-    cpu = orc.FaceOp(square_nb, prefill=1, dt=-0.05)
-    gpu = sb.FvmOperator(ctx, square_nb, prefill=1, dt=-0.05, form=sb.FORM_FAITHFUL)
-    b, shift = rhs(cpu.n), np.cos(0.11 * np.arange(cpu.n))
-    orc.ref().ref_reset_rng()
-    want = orc.ref_solve_non_uniform(solver, cpu, b, shift, num_iterations=1500, abs_tol=0.0, rel_tol=1e-10, mode=orc.RED_TREE)
-    x = ctx.zeros(cpu.n)
-    got = dropin.solve_non_uniform(solver, gpu, x, ctx.vector(b), ctx.vector(shift), num_iterations=1500, abs_tol=0.0, rel_tol=1e-10)
-    assert got.converged and (got.iterations, got.n_apply) == (want.iterations, want.n_apply)
-    assert np.array_equal(got.trace, want.trace) and np.array_equal(x.numpy(), want.x)
-
-
-def test_apply_with_a_riding_dot(ctx, square_nb):
-    """sb_apply_dot: y = A x and <x, y> / <u, y> from one kernel -- the same y as sb_apply, the same value as sb_dot."""
-    rng = np.random.default_rng(21)
-    n = square_nb.n_cells
-    xh, uh = rng.standard_normal(n), rng.standard_normal(n)
-    for form in (sb.FORM_COEF, sb.FORM_FAITHFUL):
-        op = sb.FvmOperator(ctx, square_nb, prefill=1, dt=-0.05, form=form)
-        x, u, y, y2 = ctx.vector(xh), ctx.vector(uh), ctx.zeros(n), ctx.zeros(n)
-        op.mul(y, x)
-        d_xy = op.mul_dot(y2, x)
-        assert np.array_equal(y2.numpy(), y.numpy()) and d_xy == ctx.dot(x, y)
-        y2.fill(0.0)
-        d_uy = op.mul_dot(y2, x, u)
-        assert np.array_equal(y2.numpy(), y.numpy()) and d_uy == ctx.dot(u, y)
-        assert d_xy == orc.dot(xh, y.numpy(), orc.RED_TREE)
-        with pytest.raises(sb.StormB200Error, match="alias"):
-            op.mul_dot(y2, x, y2)
-        y2.fill(0.0)
-        yy, yx = op.mul_dot_yy_yx(y2, x)
-        assert np.array_equal(y2.numpy(), y.numpy()) and yy == ctx.dot(y, y) and yx == ctx.dot(y, x)
 
 
 @pytest.mark.parametrize("seed", range(6))
