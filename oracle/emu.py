@@ -39,7 +39,7 @@ class Report(C.Structure):
 
 class ChParams(C.Structure):  # dropin_ch_params
     _fields_ = [("tau", C.c_double), ("Gamma", C.c_double), ("sigma", C.c_double),
-                ("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double)]
+                ("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double), ("uniformed", C.c_int32)]
 
 
 def available() -> bool:
@@ -151,7 +151,7 @@ def solve(name: str, op: EmuOp, b, x0=None, num_iterations=2000, abs_tol=1e-6, r
 
 
 def cahn_hilliard_step(faces: EmuOp, c, mode=orc.RED_SEQ, tau=orc.CH_TAU, Gamma=orc.CH_GAMMA, sigma=orc.CH_SIGMA,
-                       num_iterations=0, abs_tol=-1.0, rel_tol=-1.0):
+                       num_iterations=0, abs_tol=-1.0, rel_tol=-1.0, uniformed=False):
     """dropin_cahn_hilliard_step on the emulator. Returns (SolveResult with x = the new c, w_hat)."""
     em, dr = _load()
     em.emu_set_reduction_mode(mode)
@@ -162,7 +162,7 @@ def cahn_hilliard_step(faces: EmuOp, c, mode=orc.RED_SEQ, tau=orc.CH_TAU, Gamma=
     iters = num_iterations if num_iterations > 0 else 2000
     cap_h, cap_t = iters + 2, 8 * iters + 64
     hist, trace = np.zeros(cap_h), np.zeros(cap_t)
-    prm = ChParams(tau, Gamma, sigma, num_iterations, abs_tol, rel_tol)
+    prm = ChParams(tau, Gamma, sigma, num_iterations, abs_tol, rel_tol, int(uniformed))
     rep = Report()
     rc = dr.dropin_cahn_hilliard_step(em.emu_ctx(), faces.handle, _p(c), _p(c_hat), _p(w_hat), n, C.byref(prm),
                                       C.byref(rep), hist.ctypes.data_as(orc._f64p), cap_h,

@@ -450,7 +450,8 @@ def ref_solve_non_uniform(solver: str, op, b, shift, x0=None, num_iterations=200
     R.ref_solve_non_uniform.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, _f64p, _f64p, _f64p,
                                         C.POINTER(RefOpts), C.POINTER(RefReport), _f64p, C.c_int64]
     R.ref_solve_non_uniform.restype = C.c_int
-    b, shift = _f64(b), _f64(shift)
+    b = _f64(b)
+    shift = None if shift is None else _f64(shift)     # None: `op` is the affine operator itself
     n = b.shape[0]
     x = np.zeros(n) if x0 is None else _f64(x0).copy()
     cap_t = 64 * num_iterations + 256
@@ -458,7 +459,8 @@ def ref_solve_non_uniform(solver: str, op, b, shift, x0=None, num_iterations=200
     opts = RefOpts(num_iterations, abs_tol, rel_tol, 0, mode, 0.0, None, None, 1)
     rep = RefReport()
     f, u = op.callback
-    rc = R.ref_solve_non_uniform(solver.encode(), n, f, u, _p(b, _f64p), _p(shift, _f64p), _p(x, _f64p), C.byref(opts),
+    rc = R.ref_solve_non_uniform(solver.encode(), n, f, u, _p(b, _f64p), None if shift is None else _p(shift, _f64p),
+                                 _p(x, _f64p), C.byref(opts),
                                  C.byref(rep), _p(trace, _f64p), cap_t)
     if rc != 0:
         raise ValueError(f"ref_solve_non_uniform: unknown solver {solver!r}")
@@ -505,11 +507,14 @@ class CahnHilliardOp:
 
 
 def cahn_hilliard_step(mesh: FaceMesh, c, mode=RED_SEQ, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6,
-                       **constants) -> SolveResult:
+                       uniformed=False, **constants) -> SolveResult:
     """One time step: `c_hat <<= c; solve<CgSolver>(c_hat, c, op)` (Playground.cpp:148-167; the defaults are those
     of IterativeSolver, Solver.hpp:61-63). Uses the reference's own CgSolver when oracle/_ref is built, the C
     restatement otherwise (the two are pinned against each other in tests/test_oracle_golden.py)."""
     op = CahnHilliardOp(mesh, c, **constants)
+    if uniformed:   # the same step through the reference's solve_non_uniform (the operator is affine): CG converges
+        return ref_solve_non_uniform("cg", op, op.c, None, x0=op.c, num_iterations=num_iterations, abs_tol=abs_tol,
+                                     rel_tol=rel_tol, mode=mode)
     run = ref_solve if have_ref() else solve
     return run("cg", op, op.c, x0=op.c, num_iterations=num_iterations, abs_tol=abs_tol, rel_tol=rel_tol, mode=mode)
 

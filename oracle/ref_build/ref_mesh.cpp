@@ -22,7 +22,8 @@
 //   ref_mesh_tool vtk <prefix> <out.vtk>
 //       The playground's save_vtk (Playground.cpp:65-109) on the reference's mesh with one cell field
 //       c[k] = sin(0.37 k): the file a drop-in has to reproduce (node order, per-cell node lists, number format).
-//   ref_mesh_tool ch <prefix> <num_steps> <out.bin>
+//   ref_mesh_tool ch <prefix> <num_steps> <out.bin> [uniformed]
+//       (uniformed: the same step through the reference's solve_non_uniform instead of solve<CgSolver>)
 //       The playground's own caller of the path, statement for statement (Playground.cpp:133-175 and the
 //       initial condition / swap of :176-210): c[cell] = rand()/RAND_MAX (glibc, default seed), then per
 //       time step  f <<= map(dF_dc, c);  c_hat <<= c;  solve<CgSolver>(c_hat, c, make_operator(lambda))
@@ -31,6 +32,16 @@
 //
 // The only code here that is not the reference's is the restated face loop `div_grad` below
 // (the original is a file-local function of the playground app and cannot be included).
+
+#include <Storm/Bittern/Matrix.hpp>
+
+namespace Storm {
+// a name the legacy solver headers expect but the tree no longer defines (Solver.hpp:281)
+template<class M>
+constexpr auto& fill_with(M& m, double s) {
+  return fill(m, s);
+}
+} // namespace Storm
 
 #include <Storm/Solvers/Operator.hpp>
 #include <Storm/Solvers/SolverCg.hpp>
@@ -230,7 +241,8 @@ struct ChStepReport {
   std::vector<double> hist;
 };
 
-ChStepReport cahn_hilliard_step(const RefMesh& mesh, const RefField& c, RefField& c_hat, RefField& w_hat) {
+ChStepReport cahn_hilliard_step(const RefMesh& mesh, const RefField& c, RefField& c_hat, RefField& w_hat,
+                                bool uniformed = false) {
   constexpr auto dF_dc = [](real_t c) noexcept { return 2.0 * c * (c - 1.0) * (2.0 * c - 1.0); };
   RefField f{mesh};
   f <<= map(dF_dc, c);
@@ -246,7 +258,9 @@ ChStepReport cahn_hilliard_step(const RefMesh& mesh, const RefField& c, RefField
     c_out <<= c_in;
     div_grad(mesh, c_out, -ch_tau, w_hat);
   });
-  rep.converged = solver.solve(c_hat, c, *op);
+  // uniformed: the operator is affine (A(0) = -tau lap(f - sigma c) != 0), which is what the reference's own
+  // solve_non_uniform (Solver.hpp:271-292) exists for; the playground calls plain solve<CgSolver> (:149)
+  rep.converged = uniformed ? solve_non_uniform(solver, c_hat, c, *op) : solver.solve(c_hat, c, *op);
   rep.iterations = solver.iteration;
   rep.abs_err = solver.absolute_error, rep.rel_err = solver.relative_error;
   if (rep.hist.size() <= solver.iteration) rep.hist.resize(solver.iteration + 1);
@@ -254,7 +268,7 @@ ChStepReport cahn_hilliard_step(const RefMesh& mesh, const RefField& c, RefField
   return rep;
 }
 
-int cmd_ch(const std::string& prefix, size_t num_steps, const char* out) {
+int cmd_ch(const std::string& prefix, size_t num_steps, const char* out, bool uniformed) {
   const auto mesh = load(prefix);
   const size_t n = mesh->num_cells();
   RefField c{*mesh}, c_hat{*mesh}, w_hat{*mesh};
@@ -268,7 +282,7 @@ int cmd_ch(const std::string& prefix, size_t num_steps, const char* out) {
   for (size_t k = 0; k < n; ++k) v[k] = c(k);
   w.arr(v);
   for (size_t step = 0; step < num_steps; ++step) {
-    const ChStepReport rep = cahn_hilliard_step(*mesh, c, c_hat, w_hat);
+    const ChStepReport rep = cahn_hilliard_step(*mesh, c, c_hat, w_hat, uniformed);
     std::swap(c, c_hat); // Playground.cpp:204
     for (size_t k = 0; k < n; ++k) v[k] = c(k);
     w.i64(rep.converged ? 1 : 0);
@@ -291,11 +305,11 @@ int main(int argc, char** argv) {
                   argv[6]);
   if (argc >= 4 && std::strcmp(argv[1], "vtk") == 0) return cmd_vtk(argv[2], argv[3]);
   if (argc >= 5 && std::strcmp(argv[1], "ch") == 0)
-    return cmd_ch(argv[2], (size_t) std::atoll(argv[3]), argv[4]);
+    return cmd_ch(argv[2], (size_t) std::atoll(argv[3]), argv[4], argc >= 6 && std::strcmp(argv[5], "uniformed") == 0);
   std::fprintf(stderr,
                "usage: ref_mesh_tool export <prefix> <out.bin>\n"
                "       ref_mesh_tool cg <prefix> <dt> <num_iterations> <rel_tol> <out.bin>\n"
                "       ref_mesh_tool vtk <prefix> <out.vtk>\n"
-               "       ref_mesh_tool ch <prefix> <num_steps> <out.bin>\n");
+               "       ref_mesh_tool ch <prefix> <num_steps> <out.bin> [uniformed]\n");
   return 1;
 }

@@ -275,11 +275,12 @@ int ref_solve_non_uniform(const char* name, size_t n, ref_apply_fn fn, void* use
                           double* x, const ref_opts* o, ref_report* rep, double* trace, int64_t trace_cap) {
   const std::string s{name};
   HostVec xv, bv, sv;
-  xv.d.assign(x, x + n), bv.d.assign(b, b + n), sv.d.assign(shift, shift + n);
+  xv.d.assign(x, x + n), bv.d.assign(b, b + n);
+  if (shift != nullptr) sv.d.assign(shift, shift + n); // NULL: the callback is the affine operator itself
   int64_t n_apply = 0;
   const auto affine = Storm::make_operator<HostVec>([&](HostVec& y, const HostVec& in) {
     fn(user, y.d.data(), in.d.data(), n);
-    y += sv;
+    if (shift != nullptr) y += sv;
     ++n_apply;
   });
   Storm::g_trace = Storm::RefTrace{o->reduction_mode, trace, (size_t) trace_cap, 0};

@@ -33,7 +33,8 @@ case "$what" in
     # the playground's caller at full size, as written and with automatic grouping
     python scripts/playground_cahn_hilliard.py --box 119 --steps 1 --max-iterations 100 --no-vtk --out "$out/ch" > "$out/ch_10M.log" 2>&1
     python scripts/playground_cahn_hilliard.py --box 119 --steps 1 --max-iterations 100 --no-vtk --grouping --out "$out/ch" > "$out/ch_10M_grouping.log" 2>&1
-    tail -1 "$out/ch_10M.log" "$out/ch_10M_grouping.log"
+    python scripts/playground_cahn_hilliard.py --box 119 --steps 2 --uniformed --no-vtk --grouping 2 --out "$out/ch" > "$out/ch_10M_uniformed.log" 2>&1
+    tail -1 "$out/ch_10M.log" "$out/ch_10M_grouping.log" "$out/ch_10M_uniformed.log"
     ncu --set full --clock-control none --import-source on -k regex:GroupBody -c 3 -o "$out/group_kernel" \
         python scripts/solver_sweep.py --axis 119 --steps 4 --repeats 1 --solvers grouped_idrs > "$out/ncu.log" 2>&1
     ;;

@@ -36,7 +36,7 @@ class Report(C.Structure):
 
 class ChParams(C.Structure):   # dropin_ch_params: Playground.cpp:113 constants + solver limits (<= 0 / < 0: defaults)
     _fields_ = [("tau", C.c_double), ("Gamma", C.c_double), ("sigma", C.c_double),
-                ("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double)]
+                ("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double), ("uniformed", C.c_int32)]
 
 
 _lib = None
@@ -117,7 +117,7 @@ def solve(name: str, op, x, b, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6, 
 
 
 def cahn_hilliard_step(faces, c, c_hat, w_hat, tau=1.0e-3, Gamma=1.0e-4, sigma=2.0, num_iterations=0,
-                       abs_tol=-1.0, rel_tol=-1.0) -> Result:
+                       abs_tol=-1.0, rel_tol=-1.0, uniformed=False) -> Result:
     """One time step of the playground's Cahn-Hilliard solver (Playground.cpp:133-175) through the C++ drop-in:
     `faces` a faithful-form FvmOperator over the mesh, c (in) / c_hat (out: the new c) / w_hat (workspace)
     DeviceVectors. Defaults = the playground's constants (:113) and IterativeSolver's limits (2000, 1e-6, 1e-6)."""
@@ -125,7 +125,7 @@ def cahn_hilliard_step(faces, c, c_hat, w_hat, tau=1.0e-3, Gamma=1.0e-4, sigma=2
     iters = num_iterations if num_iterations > 0 else 2000
     cap_h, cap_t = iters + 2, 8 * iters + 64
     hist, trace = np.zeros(cap_h), np.zeros(cap_t)
-    prm = ChParams(tau, Gamma, sigma, num_iterations, abs_tol, rel_tol)
+    prm = ChParams(tau, Gamma, sigma, num_iterations, abs_tol, rel_tol, int(uniformed))
     rep = Report()
     rc = L.dropin_cahn_hilliard_step(faces.ctx.handle, faces.handle, c.ptr, c_hat.ptr, w_hat.ptr, c.n,
                                      C.byref(prm), C.byref(rep), hist.ctypes.data_as(capi.f64p), cap_h,

@@ -63,6 +63,8 @@ struct dropin_ch_params {
   double tau, Gamma, sigma;
   int64_t num_iterations;
   double abs_tol, rel_tol;
+  int32_t uniformed; // 0: solve<CgSolver> as the playground calls it (Playground.cpp:149); 1: through the reference's
+                     // solve_non_uniform (Solver.hpp:271-292) -- the operator is affine, and only then does CG converge
 };
 
 thread_local std::string g_error;
@@ -255,7 +257,7 @@ DROPIN_API int dropin_cahn_hilliard_step(sb_ctx* ctx, const sb_op* faces, const 
     });
     bool converged = false;
     try {
-      converged = solver.solve(c_hat, c, *op);
+      converged = p->uniformed != 0 ? Storm::solve_non_uniform(solver, c_hat, c, *op) : solver.solve(c_hat, c, *op);
     } catch (...) {
       Storm::B200::g_observer = nullptr;
       throw;

@@ -16,7 +16,9 @@ Outputs (small, committed):
   tests/golden/cahn_hilliard_square_nb.npz  the playground's Cahn-Hilliard time step (Playground.cpp:133-210)
                                      run by the reference's own mesh / CellField / map / CgSolver on
                                      square_nb.1: initial c (glibc rand()), c after each of 2 steps, CG reports
-                                     and residual histories (`--only ch` regenerates just this file)
+                                     and residual histories (`--only ch` regenerates just this file and
+                                     cahn_hilliard_uniformed_square_nb.npz: 3 steps through the reference's
+                                     solve_non_uniform, which is what makes its CG converge on this affine operator)
   tests/golden/blas1_kat.npz         known answers of tests/unit/BitternReductions.cpp /
                                      BitternMath.cpp evaluated by the reference templates
 
@@ -54,6 +56,14 @@ def make_cahn_hilliard(tmp):
         out[f"step{k}_hist"] = st["hist"]
         out[f"step{k}_stats"] = np.array([st["converged"], st["iterations"], st["abs_err"], st["rel_err"]])
     np.savez_compressed(f"{OUT}/cahn_hilliard_{name}.npz", **out)
+    # the same steps through the reference's solve_non_uniform (the operator is affine): CG converges in ~50 iterations
+    subprocess.run([orc.REF_MESH_TOOL, "ch", f"{REF_DATA}/{name}.1.", "3", ch_bin, "uniformed"], check=True)
+    ch = orc.read_ch_dump(ch_bin)
+    out = dict(c0=ch["c0"], num_steps=3)
+    for k, st in enumerate(ch["steps"]):
+        out[f"step{k}_c"] = st["c"]
+        out[f"step{k}_stats"] = np.array([st["converged"], st["iterations"], st["abs_err"], st["rel_err"]])
+    np.savez_compressed(f"{OUT}/cahn_hilliard_uniformed_{name}.npz", **out)
 
 
 def main():

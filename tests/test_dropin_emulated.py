@@ -207,6 +207,32 @@ def test_playground_cahn_hilliard_step_equals_the_reference_run(square_nb):
         c = res.x
 
 
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_cahn_hilliard_step_through_solve_non_uniform_equals_the_reference_run(square_nb, level):
+    """The playground hands an AFFINE operator to plain solve<CgSolver>, which is why its CG never converges; the
+    reference's own solve_non_uniform (Solver.hpp:271-292) is made for exactly that. The same step through it
+    (dropin_ch_params::uniformed), on the device types, against the reference's run of it (its mesh, CellField, map,
+    CgSolver, solve_non_uniform: golden fixture): three time steps of 49 / 53 / 54 CG iterations instead of 3 x 2000, bit
+    for bit, with statement grouping off, on, and on with scheduling."""
+    g = load_golden("cahn_hilliard_uniformed_square_nb.npz")
+    faces = emu.EmuOp(orc.FaceOp(square_nb.without_boundary(), prefill=0, dt=0.0))
+    emu.set_statement_grouping(level)
+    try:
+        c = g["c0"]
+        for k in range(int(g["num_steps"])):
+            res, _ = emu.cahn_hilliard_step(faces, c, uniformed=True)
+            conv, its, abs_err, rel_err = g[f"step{k}_stats"]
+            assert (res.converged, res.iterations) == (bool(conv), int(its)) and int(its) < 60
+            assert res.abs_err == abs_err and res.rel_err == rel_err
+            assert np.array_equal(res.x, g[f"step{k}_c"])
+            c = res.x
+    finally:
+        emu.set_statement_grouping(0)
+    # and the oracle restatement used by the GPU test
+    res = orc.cahn_hilliard_step(square_nb, g["c0"], uniformed=True)
+    assert res.iterations == 49 and np.array_equal(res.x, g["step0_c"])
+
+
 def test_oracle_restatement_of_the_cahn_hilliard_step_is_pinned(square_nb):
     """oracle.orc.cahn_hilliard_step (numpy statements + the C face loop, the checker of the GPU test) against the
     same golden fixture, and the traced dF/dc against its numpy restatement."""

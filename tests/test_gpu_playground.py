@@ -156,6 +156,21 @@ def test_playground_cahn_hilliard_step_on_the_device(ctx, square_nb):
     assert np.isfinite(w_hat.numpy()).all()   # the chemical potential of the last operator evaluation
 
 
+def test_cahn_hilliard_step_through_solve_non_uniform_on_the_device(ctx, square_nb):
+    """The same step through the reference's solve_non_uniform (the operator is affine): CG converges in 49 iterations;
+    bit-identical to the oracle with the GPU tree, within tolerance of the reference's own sequential run."""
+    g = load_golden("cahn_hilliard_uniformed_square_nb.npz")
+    n = square_nb.n_cells
+    faces = sb.FvmOperator(ctx, square_nb, prefill=0, dt=0.0, form=sb.FORM_FAITHFUL)
+    c, c_hat, w_hat = ctx.vector(g["c0"]), ctx.zeros(n), ctx.zeros(n)
+    got = dropin.cahn_hilliard_step(faces, c, c_hat, w_hat, uniformed=True)
+    want = orc.cahn_hilliard_step(square_nb, g["c0"], mode=orc.RED_TREE, uniformed=True)
+    assert got.converged and got.iterations == want.iterations
+    assert np.array_equal(got.trace, want.trace) and np.array_equal(c_hat.numpy(), want.x)
+    assert abs(got.iterations - int(g["step0_stats"][1])) <= 1
+    assert np.linalg.norm(c_hat.numpy() - g["step0_c"]) <= 1e-8 * np.linalg.norm(g["step0_c"])
+
+
 def test_playground_driver_end_to_end(tmp_path):
     """scripts/playground_cahn_hilliard.py: mesh files -> reader -> upload -> two time steps -> VTK output, as a
     separate process (the application a reference user would run)."""
