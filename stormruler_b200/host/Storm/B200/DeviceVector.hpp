@@ -109,8 +109,9 @@ struct StatementQueue {
   std::vector<sb_chain> stmts;
   /// An operator apply that has been asked for but not launched yet: if the next thing the solver does is a dot product
   /// of its output with its input or with a third vector (`lin_op.mul(z, p); dot_product(p, z)`, SolverCg.hpp:95-96),
-  /// the two go to the device as one sb_apply_dot. Invariant: a deferred apply and queued statements never coexist
-  /// (the apply is deferred after the statements before it were launched; anything queued after it launches it first).
+  /// the two go to the device as one sb_apply_dot. Invariant: no queued statement writes the deferred apply's input or
+  /// touches its output (such statements were launched when the apply was deferred; a statement queued after it
+  /// launches it first). Without `reorder` nothing at all is queued while an apply is deferred.
   struct {
     bool active = false;
     sb_ctx* ctx = nullptr;
