@@ -19,8 +19,8 @@ import numpy as np
 from . import orc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DROPIN = os.path.join(HERE, "_ref", "emu", "libstorm_dropin_emu.so")
-EMU = os.path.join(HERE, "_ref", "emu", "libstormb200_emu.so")
+DROPIN = os.path.join(HERE, "_ref", "emu", "liboracle_dropin_on_emulator.so")
+EMU = os.path.join(HERE, "_ref", "emu", "liboracle_cabi_emulator.so")
 
 COUNT_NAMES = ("eval", "fill", "copy", "dot", "norm", "apply", "accumulate", "jacobi")
 PRE_SIDES = {"left": 0, "right": 1, "symmetric": 2}
