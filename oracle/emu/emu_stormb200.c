@@ -12,7 +12,8 @@
  * reference's own run bit for bit (tests/test_dropin_emulated.py). The GPU tests then only have to show that the
  * CUDA kernels honour the same per-entry contract.
  *
- * Not emulated (they are CUDA schedules, not statement streams): sb_cg_solve, sb_bicgstab_solve, sb_gmres_solve. */
+ * sb_cg_solve / sb_bicgstab_solve answer with the oracle's restatements of the same contract (see below); sb_gmres_solve is
+ * not emulated. */
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -238,15 +239,36 @@ API int sb_op_destroy(sb_ctx* ctx, sb_op* op) {
   return SB_OK;
 }
 
+/* The fused CG / BiCGStab are CUDA schedules; their CONTRACT (same statements, same stopping rule, same reduction
+ * values as the reference) is what the oracle's plain-C restatements implement, so the emulator answers with those:
+ * enough to exercise the C++ classes in front of them (Storm/B200/FusedSolvers.hpp: option and report mapping). */
+static int emu_fused(int bicgstab, sb_ctx* c, const sb_op* o, double* x, const double* b, const sb_solver_opts* p,
+                     sb_solver_report* r, double* h, int64_t hc, double* t, int64_t tc) {
+  if (c == NULL || o == NULL || x == NULL || b == NULL || p == NULL || r == NULL) return fail(SB_ERR_INVALID, "null argument");
+  if (x == b) return fail(SB_ERR_INVALID, "x and b must not alias");
+  orc_solver_opts oo;
+  oo.num_iterations = p->num_iterations, oo.abs_tol = p->abs_tol, oo.rel_tol = p->rel_tol, oo.reduction_mode = g_mode;
+  orc_solver_report rep;
+  memset(&rep, 0, sizeof rep);
+  const int rc = (bicgstab ? orc_bicgstab : orc_cg)(o->apply, o->apply_user, o->n, b, x, &oo, &rep, h, h != NULL ? hc : 0, t,
+                                                    t != NULL ? tc : 0);
+  if (rc != 0) return fail(SB_ERR_INVALID, "oracle solver failed");
+  memset(r, 0, sizeof *r);
+  r->converged = rep.converged, r->iterations = rep.iterations;
+  r->abs_err = rep.abs_err, r->rel_err = rep.rel_err;
+  r->initial_err = (h != NULL && hc > 0) ? h[0] : 0.0;
+  r->n_hist = h != NULL ? (rep.n_hist < hc ? rep.n_hist : hc) : 0;
+  r->n_trace = t != NULL ? (rep.n_trace < tc ? rep.n_trace : tc) : 0;
+  r->n_kernel_slots = bicgstab ? 5 : 3;
+  return SB_OK;
+}
 API int sb_cg_solve(sb_ctx* c, const sb_op* o, double* x, const double* b, const sb_solver_opts* p, sb_solver_report* r,
                     double* h, int64_t hc, double* t, int64_t tc) {
-  (void) c, (void) o, (void) x, (void) b, (void) p, (void) r, (void) h, (void) hc, (void) t, (void) tc;
-  return fail(SB_ERR_STATE, "host emulator: the fused solvers are CUDA schedules and are not emulated");
+  return emu_fused(0, c, o, x, b, p, r, h, hc, t, tc);
 }
 API int sb_bicgstab_solve(sb_ctx* c, const sb_op* o, double* x, const double* b, const sb_solver_opts* p,
                           sb_solver_report* r, double* h, int64_t hc, double* t, int64_t tc) {
-  (void) c, (void) o, (void) x, (void) b, (void) p, (void) r, (void) h, (void) hc, (void) t, (void) tc;
-  return fail(SB_ERR_STATE, "host emulator: the fused solvers are CUDA schedules and are not emulated");
+  return emu_fused(1, c, o, x, b, p, r, h, hc, t, tc);
 }
 API int sb_gmres_solve(sb_ctx* c, const sb_op* o, double* x, const double* b, const sb_gmres_opts* p, sb_solver_report* r,
                        double* h, int64_t hc, double* t, int64_t tc) {

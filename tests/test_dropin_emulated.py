@@ -180,6 +180,25 @@ def test_solve_non_uniform_on_device_vector(square_nb, solver):
         assert np.linalg.norm(op.apply(got.x) + shift - b) <= 1e-8 * np.linalg.norm(b - shift)
 
 
+@pytest.mark.parametrize("name,ref", [("fused_cg", "cg"), ("fused_bicgstab", "bicgstab")])
+def test_fused_solver_classes_map_options_and_reports(square_nb, name, ref):
+    """Storm::B200::CgSolver / BiCgStabSolver (Storm/B200/FusedSolvers.hpp) called through the reference's abstract
+    Solver interface: option mapping, public progress fields, residual history and reduction trace -- with the emulator
+    answering sb_cg_solve / sb_bicgstab_solve from the oracle's restatements of the same contract. (The CUDA schedules
+    behind those entry points are checked on the device, tests/test_gpu_parity.py and test_gpu_dropin.py.)"""
+    op = orc.FaceOp(square_nb, prefill=1, dt=-DT)
+    b = rhs(square_nb.n_cells)
+    for mode in (orc.RED_SEQ, orc.RED_TREE):
+        for iters, rtol in ((ITERS, RTOL), (7, 0.0)):
+            kw = dict(num_iterations=iters, abs_tol=0.0, rel_tol=rtol, mode=mode)
+            want = orc.ref_solve(ref, op, b, **kw)
+            got = emu.solve(name, emu.EmuOp(op), b, **kw)
+            assert (got.converged, got.iterations) == (want.converged, want.iterations)
+            assert (got.abs_err, got.rel_err) == (want.abs_err, want.rel_err)
+            assert np.array_equal(got.x, want.x) and np.array_equal(got.hist, want.hist)
+            assert np.array_equal(got.trace, want.trace)
+
+
 def test_host_layer_rejects_misuse():
     assert emu.selftest_errors() == 3
 
