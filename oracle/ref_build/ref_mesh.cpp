@@ -192,42 +192,40 @@ int cmd_cg(const std::string& prefix, double dt, size_t num_iterations, double r
   return 0;
 }
 
-// save_vtk, statement order of Playground.cpp:65-109 (a file-local template of the app, restated like div_grad).
+// The file the playground's save_vtk (Playground.cpp:65-109) writes for one cell field, produced from the reference's
+// mesh classes: what matters for a drop-in is the order in which those classes enumerate nodes, cells and a cell's
+// nodes, and the stream formatting (setprecision(digits10 + 1), default float format); the writer itself is restated.
 int cmd_vtk(const std::string& prefix, const char* out) {
   const auto mesh_ptr = load(prefix);
   const RefMesh& mesh = *mesh_ptr;
-  RefField c{mesh};
-  for (size_t k = 0; k < mesh.num_cells(); ++k) c(k) = std::sin(0.37 * (double) k);
-  std::ofstream file(out);
-  file << std::setprecision(std::numeric_limits<real_t>::digits10 + 1);
-  file << "# vtk DataFile Version 2.0" << std::endl;
-  file << "# Generated by Feathers/StormRuler/Mesh2VTK" << std::endl;
-  file << "ASCII" << std::endl;
-  file << "DATASET UNSTRUCTURED_GRID" << std::endl;
-  file << "POINTS " << mesh.num_nodes() << " double" << std::endl;
-  std::ranges::for_each(mesh.nodes(), [&](auto node) {
-    const auto& pos = node.position();
-    file << pos(0) << " " << pos(1) << " " << 0.0 << std::endl;
-  });
-  file << std::endl;
-  size_t sum = 0;
-  std::ranges::for_each(mesh.interior_cells(), [&](auto cell) { sum += cell.nodes().size() + 1; });
-  file << "CELLS " << mesh.num_cells({}) << " " << sum << std::endl;
-  std::ranges::for_each(mesh.interior_cells(), [&](auto cell) {
-    file << cell.nodes().size() << " ";
-    cell.for_each_node([&](NodeIndex node_index) { file << node_index << " "; });
-    file << std::endl;
-  });
-  file << std::endl;
-  file << "CELL_TYPES " << mesh.num_cells({}) << std::endl;
-  std::ranges::for_each(mesh.interior_cells(), [&](auto cell) { file << "5" << std::endl; });
-  file << std::endl;
-  file << "CELL_DATA " << mesh.num_cells({}) << std::endl;
-  file << "SCALARS c double 1" << std::endl;
-  file << "LOOKUP_TABLE default" << std::endl;
-  std::ranges::for_each(mesh.interior_cells(), [&](auto cell) { file << c[cell] << std::endl; });
-  file << std::endl;
-  return 0;
+  const size_t n_cells = mesh.num_cells();
+  RefField field{mesh};
+  for (size_t k = 0; k < n_cells; ++k) field(k) = std::sin(0.37 * (double) k);
+  std::ofstream os(out);
+  os << std::setprecision(std::numeric_limits<real_t>::digits10 + 1);
+  for (const char* header : {"# vtk DataFile Version 2.0", "# Generated by Feathers/StormRuler/Mesh2VTK", "ASCII",
+                             "DATASET UNSTRUCTURED_GRID"}) {
+    os << header << '\n';
+  }
+  os << "POINTS " << mesh.num_nodes() << " double\n";
+  for (auto node : mesh.nodes()) {
+    const auto& x = node.position();
+    os << x(0) << ' ' << x(1) << ' ' << 0.0 << '\n';
+  }
+  size_t list_size = 0;
+  for (auto cell : mesh.interior_cells()) list_size += cell.nodes().size() + 1;
+  os << "\nCELLS " << n_cells << ' ' << list_size << '\n';
+  for (auto cell : mesh.interior_cells()) {
+    os << cell.nodes().size() << ' ';
+    cell.for_each_node([&os](NodeIndex node) { os << node << ' '; });
+    os << '\n';
+  }
+  os << "\nCELL_TYPES " << n_cells << '\n';
+  for (size_t k = 0; k < n_cells; ++k) os << "5\n"; // VTK_TRIANGLE
+  os << "\nCELL_DATA " << n_cells << "\nSCALARS c double 1\nLOOKUP_TABLE default\n";
+  for (auto cell : mesh.interior_cells()) os << field[cell] << '\n';
+  os << '\n';
+  return os ? 0 : 2;
 }
 
 // One Cahn-Hilliard time step, Playground.cpp:133-175 (the CgSolver is constructed here instead of inside
