@@ -137,13 +137,13 @@ SB_API int sb_op_download_rows(sb_ctx* ctx, const sb_op* op, int32_t* h_col, dou
 /* y <- A(x): Operator::mul (Operator.hpp:74). x and y must not alias. */
 SB_API int sb_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y);
 /* y <- A(x) and <u, y> in one kernel (the dot rides on the apply: its operands are in registers, so it costs no pass
- * over y; SB_TREE, result on the host): what `lin_op.mul(z, p); dot_product(p, z)` (SolverCg.hpp:95-96) or
+ * over y; SB_TREE, result on the host): what `lin_op.mul(z, p); dot_product(p, z)` (SolverCg.hpp:96-97) or
  * `lin_op.mul(v, p); dot_product(r_tilde, v)` (SolverBiCgStab.hpp:137-139) cost when issued together. u == NULL or
  * u == x: <x, y>. u must not alias y; x and y must not alias. Same kernels as the fused solvers' apply + dot. */
 SB_API int sb_apply_dot(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const double* u, double* h_out);
 /* y <- A(x) with h_out[0] = <y, y> and h_out[1] = <y, x> from the same kernel: `lin_op.mul(t, r);
  * omega = safe_divide(dot_product(t, r), dot_product(t, t))` (SolverBiCgStab.hpp:158-160; IDR(s)'s
- * `<v,r>/<v,v>`, SolverIdrs.hpp:247-248). x and y must not alias. */
+ * `<v,r>/<v,v>`, SolverIdrs.hpp:276-277). x and y must not alias. */
 SB_API int sb_apply_dot_yy_yx(sb_ctx* ctx, const sb_op* op, const double* x, double* y, double* h_out);
 /* y += dt * div grad x: `stormDivGrad(mesh, u, dt, c)` exactly as the playground calls it (Playground.cpp:115-131;
  * call sites :159 `stormDivGrad(mesh, w_hat, -Gamma, c_in)` after `w_hat <<= f + sigma*(c_in - c)`, and :165
@@ -351,8 +351,8 @@ SB_API int sb_copy(sb_ctx* ctx, double* y, const double* x, size_t n);
 /* A GROUP of element-wise statements and the reductions behind them in ONE kernel launch (one pass over the union of
  * the operands, one host synchronisation for all the reductions): what a solver's consecutive vector statements
  * cost when they are issued together instead of one kernel each. Every statement is a linear-combination chain, the
- * shape all of the reference solvers' updates have (e.g. SolverIdrs.hpp:166-176 `v <<= r - gamma_k*g_k; v -= gamma_i*g_i`,
- * SolverBiCgStab.hpp:266-268 `u_i <<= r_i - beta*u_i`):
+ * shape all of the reference solvers' updates have (e.g. SolverIdrs.hpp:195-198 `v <<= r - gamma_k*g_k; v -= gamma_i*g_i`,
+ * SolverBiCgStab.hpp:271-273 `u_i <<= r_i - beta*u_i`):
  *     y = ((base (+|-) c0*x0) (+|-) c1*x1) ...      base == NULL: the chain starts from c0*x0 itself
  * evaluated per element in exactly that order, every product and every sum rounded separately -- bit-identical to
  * issuing `y <<= base - c0*x0; y -= c1*x1; ...` one statement at a time. Statements run in the order given; a later

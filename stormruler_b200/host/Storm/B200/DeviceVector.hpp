@@ -108,7 +108,7 @@ struct StatementQueue {
   size_t n = 0;
   std::vector<sb_chain> stmts;
   /// An operator apply that has been asked for but not launched yet: if the next thing the solver does is a dot product
-  /// of its output with its input or with a third vector (`lin_op.mul(z, p); dot_product(p, z)`, SolverCg.hpp:95-96),
+  /// of its output with its input or with a third vector (`lin_op.mul(z, p); dot_product(p, z)`, SolverCg.hpp:96-97),
   /// the two go to the device as one sb_apply_dot. Invariant: no queued statement writes the deferred apply's input or
   /// touches its output (such statements were launched when the apply was deferred; a statement queued after it
   /// launches it first). Without `reorder` nothing at all is queued while an apply is deferred.

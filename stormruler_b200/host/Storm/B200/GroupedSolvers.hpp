@@ -1,6 +1,6 @@
 // Storm/B200/GroupedSolvers.hpp -- IDR(s) and BiCGStab(l) with their vector statements issued in groups.
 //
-// The reference's IdrsSolver (Solvers/SolverIdrs.hpp:42-300) and BiCgStabLSolver (SolverBiCgStab.hpp:183-385) spend
+// The reference's IdrsSolver (Solvers/SolverIdrs.hpp:42-292) and BiCgStabLSolver (SolverBiCgStab.hpp:185-383) spend
 // most of their vector passes in runs of consecutive linear-combination statements (`v <<= r - gamma_k*g_k;
 // v -= gamma_i*g_i; ...`, `u_i <<= r_i - beta*u_i` for every i, the 3(l-1)+3 updates that close a BiCGStab(l) cycle)
 // and in runs of dot products whose results are only needed together. On the generic drop-in path every one of them
@@ -144,7 +144,7 @@ inline void no_preconditioner(const void* pre_op) {
 }
 } // namespace detail
 
-/// IDR(s) (SolverIdrs.hpp:42-300), statements grouped. Same defaults (s = 4).
+/// IDR(s) (SolverIdrs.hpp:42-292), statements grouped. Same defaults (s = 4).
 class IdrsSolver final : public InnerOuterIterativeSolver<DeviceVector> {
 public:
 
@@ -169,7 +169,7 @@ private:
     for (DeviceVector& p_vec : _p_vecs) p_vec.assign(x_vec, false);
     for (DeviceVector& u_vec : _u_vecs) u_vec.assign(x_vec, false);
     for (DeviceVector& g_vec : _g_vecs) g_vec.assign(x_vec, false);
-    // r <- b - A x, phi_0 <- ||r||   (:96-101)
+    // r <- b - A x, phi_0 <- ||r||   (:94-99)
     lin_op.mul(_r_vec, x_vec);
     Group grp{x_vec.context(), x_vec.size()};
     grp.chain(_r_vec, &b_vec).minus(1.0, _r_vec).norm(_r_vec); // b - r: 1.0*r is exact
@@ -181,7 +181,7 @@ private:
                   const Preconditioner<DeviceVector>*) override {
     const size_t s = this->num_inner_iterations;
     if (this->iteration == 0) {
-      // the shadow space (:123-135): one-time set-up, the reference's statements as they are
+      // the shadow space (:131-141): one-time set-up, the reference's statements as they are
       _omega = mu(0, 0) = 1.0;
       _p_vecs[0] <<= _r_vec / _phi[0];
       for (size_t i = 1; i < s; ++i) {
@@ -194,7 +194,7 @@ private:
         _p_vecs[i] /= norm_2(_p_vecs[i]);
       }
     } else {
-      // phi_i <- <p_i, r> for every i (:137-139): one batch, one synchronisation
+      // phi_i <- <p_i, r> for every i (:143-145): one batch, one synchronisation
       Group grp{x_vec.context(), x_vec.size()};
       for (size_t i = 0; i < s; ++i) grp.dot(_p_vecs[i], _r_vec);
       const std::vector<double> d = grp.run();
@@ -208,23 +208,23 @@ private:
     const size_t k = this->inner_iteration;
     Group grp{x_vec.context(), x_vec.size()};
 
-    // gamma_{k:s-1} <- (mu_{k:s-1,k:s-1})^-1 phi_{k:s-1}   (:157-163), host scalars
+    // gamma_{k:s-1} <- (mu_{k:s-1,k:s-1})^-1 phi_{k:s-1}   (:184-190), host scalars
     for (size_t i = k; i < s; ++i) {
       _gamma[i] = _phi[i];
       for (size_t j = k; j < i; ++j) _gamma[i] -= mu(i, j) * _gamma[j];
       _gamma[i] /= mu(i, i);
     }
 
-    // v <- r - gamma_k g_k - sum_{i>k} gamma_i g_i ;  u_k <- omega v + gamma_k u_k + sum_{i>k} gamma_i u_i   (:166-176)
+    // v <- r - gamma_k g_k - sum_{i>k} gamma_i g_i ;  u_k <- omega v + gamma_k u_k + sum_{i>k} gamma_i u_i   (:195-206)
     grp.chain(_v_vec, &_r_vec);
     for (size_t i = k; i < s; ++i) grp.minus(_gamma[i], _g_vecs[i]);
     grp.chain(_u_vecs[k], nullptr).plus(_omega, _v_vec);
     for (size_t i = k; i < s; ++i) grp.plus(_gamma[i], _u_vecs[i]);
     grp.run();
-    lin_op.mul(_g_vecs[k], _u_vecs[k]); // (:180)
+    lin_op.mul(_g_vecs[k], _u_vecs[k]); // (:210)
 
-    // bi-orthogonalise g_k and u_k against p_0..p_{k-1} (:192-197): alpha_i needs g_k as updated by step i-1, so the
-    // dot for step i+1 rides on the update of step i; the new column of mu (:206-208) rides on the last update
+    // bi-orthogonalise g_k and u_k against p_0..p_{k-1} (:221-226): alpha_i needs g_k as updated by step i-1, so the
+    // dot for step i+1 rides on the update of step i; the new column of mu (:234-236) rides on the last update
     if (k > 0) {
       grp.dot(_p_vecs[0], _g_vecs[k]);
       double pg = grp.run()[0];
@@ -244,14 +244,14 @@ private:
       for (size_t i = k; i < s; ++i) mu(i, k) = d[i - k];
     }
 
-    // beta <- phi_k / mu_kk ; x += beta u_k ; r -= beta g_k ; phi_{k+1:} -= beta mu_{k+1:,k}   (:216-227)
+    // beta <- phi_k / mu_kk ; x += beta u_k ; r -= beta g_k ; phi_{k+1:} -= beta mu_{k+1:,k}   (:244-256)
     const real_t beta = safe_divide(_phi[k], mu(k, k));
     grp.chain(x_vec, &x_vec).plus(beta, _u_vecs[k]);
     grp.chain(_r_vec, &_r_vec).minus(beta, _g_vecs[k]);
     for (size_t i = k + 1; i < s; ++i) _phi[i] -= beta * mu(i, k);
 
     if (k == s - 1) {
-      // enter the next G subspace (:243-250): v <- A r ; omega <- <v,r>/<v,v> ; x += omega r ; r -= omega v
+      // enter the next G subspace (:272-279): v <- A r ; omega <- <v,r>/<v,v> ; x += omega r ; r -= omega v
       grp.run();
       lin_op.mul(_v_vec, _r_vec);
       grp.dot(_v_vec, _v_vec).dot(_v_vec, _r_vec); // g++ evaluates safe_divide's arguments right to left: <v,v> first
@@ -260,12 +260,12 @@ private:
       grp.chain(x_vec, &x_vec).plus(_omega, _r_vec);
       grp.chain(_r_vec, &_r_vec).minus(_omega, _v_vec);
     }
-    grp.norm(_r_vec); // (:253) rides on the last update
+    grp.norm(_r_vec); // (:282) rides on the last update
     return grp.run()[0];
   }
 };
 
-/// BiCGStab(l) (SolverBiCgStab.hpp:183-385), statements grouped. Same defaults (l = 2).
+/// BiCGStab(l) (SolverBiCgStab.hpp:185-383), statements grouped. Same defaults (l = 2).
 class BiCgStabLSolver final : public InnerOuterIterativeSolver<DeviceVector> {
 public:
 
@@ -290,7 +290,7 @@ private:
     _r_vecs.resize(l + 1), _u_vecs.resize(l + 1);
     for (DeviceVector& r_vec : _r_vecs) r_vec.assign(x_vec, false);
     for (DeviceVector& u_vec : _u_vecs) u_vec.assign(x_vec, false);
-    // u_0 <- 0 ; r_0 <- b - A x ; r~ <- r_0 ; rho <- <r~, r_0>   (:222-231)
+    // u_0 <- 0 ; r_0 <- b - A x ; r~ <- r_0 ; rho <- <r~, r_0>   (:224-231)
     fill_with(_u_vecs[0], 0.0);
     lin_op.Residual(_r_vecs[0], b_vec, x_vec);
     _r_tilde_vec <<= _r_vecs[0];
@@ -304,7 +304,7 @@ private:
     const size_t j = this->inner_iteration;
     Group grp{x_vec.context(), x_vec.size()};
 
-    // BiCG part (:262-280)
+    // BiCG part (:264-283)
     if (this->iteration == 0) {
       _u_vecs[0] <<= _r_vecs[0];
     } else {
@@ -318,13 +318,13 @@ private:
     grp.dot(_r_tilde_vec, _u_vecs[j + 1]);
     _alpha = safe_divide(_rho, grp.run()[0]);
     for (size_t i = 0; i <= j; ++i) grp.chain(_r_vecs[i], &_r_vecs[i]).minus(_alpha, _u_vecs[i + 1]);
-    // x += alpha u_0 ; r_{j+1} <- A r_j   (:291-296)
+    // x += alpha u_0 ; r_{j+1} <- A r_j   (:294-299)
     grp.chain(x_vec, &x_vec).plus(_alpha, _u_vecs[0]);
     grp.run();
     lin_op.mul(_r_vecs[j + 1], _r_vecs[j]);
 
     if (j == l - 1) {
-      // minimal-residual part (:311-320): modified Gram-Schmidt over r_1..r_l; tau_ij needs r_j as updated by the
+      // minimal-residual part (:312-323): modified Gram-Schmidt over r_1..r_l; tau_ij needs r_j as updated by the
       // previous i, so each dot rides on the update before it; sigma_j and <r_0, r_j> ride on the last update of r_j
       for (size_t jj = 1; jj <= l; ++jj) {
         if (jj > 1) {
