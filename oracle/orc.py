@@ -509,7 +509,7 @@ class CahnHilliardOp:
 def cahn_hilliard_step(mesh: FaceMesh, c, mode=RED_SEQ, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6,
                        uniformed=False, **constants) -> SolveResult:
     """One time step: `c_hat <<= c; solve<CgSolver>(c_hat, c, op)` (Playground.cpp:148-167; the defaults are those
-    of IterativeSolver, Solver.hpp:61-63). Uses the reference's own CgSolver when oracle/_ref is built, the C
+    of IterativeSolver, Solver.hpp:67-72). Uses the reference's own CgSolver when oracle/_ref is built, the C
     restatement otherwise (the two are pinned against each other in tests/test_oracle_golden.py)."""
     op = CahnHilliardOp(mesh, c, **constants)
     if uniformed:   # the same step through the reference's solve_non_uniform (the operator is affine): CG converges

@@ -271,7 +271,7 @@ int cmd_ch(const std::string& prefix, size_t num_steps, const char* out, bool un
   const size_t n = mesh->num_cells();
   RefField c{*mesh}, c_hat{*mesh}, w_hat{*mesh};
   std::ranges::for_each(mesh->interior_cells(), [&](CellView<RefMesh> cell) {
-    c[cell] = (1.0 * rand()) / RAND_MAX; // Playground.cpp:183-185
+    c[cell] = (1.0 * rand()) / RAND_MAX; // Playground.cpp:182-184
   });
   Writer w{out};
   w.i64((int64_t) n);
@@ -281,7 +281,7 @@ int cmd_ch(const std::string& prefix, size_t num_steps, const char* out, bool un
   w.arr(v);
   for (size_t step = 0; step < num_steps; ++step) {
     const ChStepReport rep = cahn_hilliard_step(*mesh, c, c_hat, w_hat, uniformed);
-    std::swap(c, c_hat); // Playground.cpp:204
+    std::swap(c, c_hat); // Playground.cpp:203
     for (size_t k = 0; k < n; ++k) v[k] = c(k);
     w.i64(rep.converged ? 1 : 0);
     w.i64((int64_t) rep.iterations);

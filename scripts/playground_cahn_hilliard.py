@@ -80,7 +80,7 @@ def write_triangle_files(prefix: str, nx: int, ny: int, lx: float = 2.0, ly: flo
 
 
 def initial_condition(n: int) -> np.ndarray:
-    """c[cell] = (1.0 * rand()) / RAND_MAX in cell order (Playground.cpp:183-185): glibc's rand() from its default state."""
+    """c[cell] = (1.0 * rand()) / RAND_MAX in cell order (Playground.cpp:182-184): glibc's rand() from its default state."""
     libc = ctypes.CDLL("libc.so.6")
     libc.srand(1)
     rand_max = 2147483647

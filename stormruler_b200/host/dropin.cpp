@@ -58,12 +58,12 @@ struct dropin_report {
 };
 
 // Constants of the playground's Cahn-Hilliard step (Playground.cpp:113) and the solver limits; a negative tolerance or
-// num_iterations <= 0 keeps the IterativeSolver default (Solver.hpp:61-63), which is what solve<CgSolver> runs with.
+// num_iterations <= 0 keeps the IterativeSolver default (Solver.hpp:67-72), which is what solve<CgSolver> runs with.
 struct dropin_ch_params {
   double tau, Gamma, sigma;
   int64_t num_iterations;
   double abs_tol, rel_tol;
-  int32_t uniformed; // 0: solve<CgSolver> as the playground calls it (Playground.cpp:149); 1: through the reference's
+  int32_t uniformed; // 0: solve<CgSolver> as the playground calls it (Playground.cpp:151); 1: through the reference's
                      // solve_non_uniform (Solver.hpp:271-292) -- the operator is affine, and only then does CG converge
 };
 

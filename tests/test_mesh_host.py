@@ -601,7 +601,7 @@ def test_vtk_of_a_2d_mesh_is_the_playground_file_byte_for_byte(tmp_path, name):
 def test_playground_driver_host_side(tmp_path):
     """scripts/playground_cahn_hilliard.py, the parts that run without a GPU: the Triangle files it can generate are read
     alike by the library and by the reference's own reader + mesh classes (every SoA array, and the VTK file byte for
-    byte), and its initial condition is the playground's glibc rand() stream (Playground.cpp:183-185; the committed
+    byte), and its initial condition is the playground's glibc rand() stream (Playground.cpp:182-184; the committed
     Cahn-Hilliard fixture holds the reference's)."""
     import importlib.util
     import os
