@@ -140,7 +140,7 @@ def solve(name: str, op: EmuOp, b, x0=None, num_iterations=2000, abs_tol=1e-6, r
     cap_h, cap_t = num_iterations + 2, trace_cap or (64 * num_iterations + 256)
     hist, trace = np.zeros(cap_h), np.zeros(cap_t)
     opts = Opts(num_iterations, abs_tol, rel_tol, num_inner, relaxation_factor, 0,
-                {None: 0, "jacobi": 1}[precond], PRE_SIDES[pre_side])
+                {None: 0, "jacobi": 1, "identity": 2}[precond], PRE_SIDES[pre_side])
     rep = Report()
     rc = dr.dropin_solve(name.encode(), em.emu_ctx(), op.handle, _p(x), _p(b), n, C.byref(opts), C.byref(rep),
                          hist.ctypes.data_as(orc._f64p), cap_h, trace.ctypes.data_as(orc._f64p), cap_t)

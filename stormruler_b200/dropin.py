@@ -105,7 +105,7 @@ def solve(name: str, op, x, b, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6, 
     cap_t = trace_cap or (64 * num_iterations + 256)
     hist, trace = np.zeros(cap_h), np.zeros(cap_t)
     opts = Opts(num_iterations, abs_tol, rel_tol, num_inner, relaxation_factor, int(use_graph),
-                {None: 0, "jacobi": 1}[precond], PRE_SIDES[pre_side])
+                {None: 0, "jacobi": 1, "identity": 2}[precond], PRE_SIDES[pre_side])
     rep = Report()
     rc = L.dropin_solve(name.encode(), op.ctx.handle, op.handle, x.ptr, b.ptr, x.n, C.byref(opts),
                         C.byref(rep), hist.ctypes.data_as(capi.f64p), cap_h,

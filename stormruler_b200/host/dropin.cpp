@@ -43,7 +43,7 @@ struct dropin_opts {
   int64_t num_inner_iterations; // <= 0: keep the solver's default (Solver.hpp:159)
   double relaxation_factor;     // Richardson only; <= 0 keeps the default
   int32_t use_graph;            // fused solvers only
-  int32_t precond;              // 0: none, 1: Storm::JacobiPreconditioner (generic solvers)
+  int32_t precond;              // 0: none, 1: Storm::JacobiPreconditioner, 2: the reference's IdentityPreconditioner (generic solvers)
   int32_t pre_side;             // 0: Left, 1: Right (the reference's default), 2: Symmetric
 };
 
@@ -108,6 +108,11 @@ int run_generic(sb_ctx* ctx, const sb_op* op, double* d_x, const double* d_b, si
   }
   if constexpr (requires { solver.relaxation_factor; }) {
     if (o->relaxation_factor > 0.0) solver.relaxation_factor = o->relaxation_factor;
+  }
+  if (o->precond == 2) { // the one preconditioner the reference ships (Preconditioner.hpp:84-97), on the device vector
+    solver.pre_op = std::make_unique<Storm::IdentityPreconditioner<DeviceVector>>();
+    solver.pre_side = o->pre_side == 0 ? Storm::PreconditionerSide::Left
+                                       : (o->pre_side == 2 ? Storm::PreconditionerSide::Symmetric : Storm::PreconditionerSide::Right);
   }
   if (o->precond == 1) {
     solver.pre_op = std::make_unique<Storm::JacobiPreconditioner>(ctx, op);

@@ -199,6 +199,21 @@ def test_fused_solver_classes_map_options_and_reports(square_nb, name, ref):
             assert np.array_equal(got.trace, want.trace)
 
 
+def test_reference_identity_preconditioner_on_device_vector(square_nb, capfd):
+    """IdentityPreconditioner<DeviceVector> (Preconditioner.hpp:84-97, the one preconditioner the reference ships) in the
+    pre_op slot, left and right: the same run as the same headers with y = x as a callback."""
+    op = orc.FaceOp(square_nb, prefill=1, dt=-DT)
+    b = rhs(square_nb.n_cells)
+    ident = orc.CallbackOp(lambda x: x.copy(), square_nb.n_cells)
+    for solver in ("cg", "bicgstab", "gmres", "tfqmr", "idrs", "cgs"):
+        for side in ("left", "right"):
+            kw = dict(num_iterations=40, abs_tol=0.0, rel_tol=1e-10, pre_side=side)
+            want = orc.ref_solve(solver, op, b, pre=ident, **kw)
+            got = emu.solve(solver, emu.EmuOp(op), b, precond="identity", **kw)
+            assert same(got, want), (solver, side)
+    capfd.readouterr()   # the reference's class logs every call to std::clog
+
+
 def test_host_layer_rejects_misuse():
     assert emu.selftest_errors() == 3
 
