@@ -1,0 +1,53 @@
+"""bench.py's contract, the parts that run without a GPU: the reference arm (`--impl reference`, the reference's own CPU
+solver on the same workload) prints ONE JSON line with the keys the driver reads, and the all-cores CPU port used for
+`cpu_baseline_all_cores` agrees with the single-threaded reference. (Small mesh: the arm's code path, not its speed.)"""
+import json
+import os
+import subprocess
+import sys
+import types
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.argv = argv
+    return mod
+
+
+@pytest.mark.parametrize("solver", ["bicgstab", "cg"])
+def test_reference_arm_prints_the_contract_line(solver):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n", "14", "--steps", "3",
+                          "--warmup", "2", "--solver", solver], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "krylov_iterations_per_sec" and line["unit"] == "it/s"
+    assert line["steps"] == 3 and line["warmup"] == 2 and line["n_gpus"] == 1 and line["higher_is_better"] is True
+    assert line["value"] > 0 and abs(line["ms_per_step"] * line["value"] - 1000.0) < 1e-6 * 1000.0
+    assert line["dtype"] == "f64" and line["data"] == "synthetic" and line["vs_baseline"] is None
+    assert line["config"]["solver"] == solver and line["config"]["cells"] == 6 * 14 ** 3
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"] == {"value": line["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.parametrize("solver", ["bicgstab", "cg"])
+def test_all_cores_port_agrees_with_the_reference(solver):
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle_omp.so")):
+        pytest.skip("oracle/liboracle_omp.so not built (no OpenMP-capable compiler)")
+    bench = _bench_module()
+    mesh, x_star = bench.build_problem(types.SimpleNamespace(cell="tet", n=16))
+    got = bench.cpu_all_cores_rate(mesh, x_star, solver, budget_s=0.2)
+    assert "unavailable" not in got, got
+    assert got["kind"] == "port" and got["cores"] >= 1 and got["value"] > 0 and np.isfinite(got["value"])
