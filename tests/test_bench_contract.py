@@ -51,3 +51,19 @@ def test_all_cores_port_agrees_with_the_reference(solver):
     got = bench.cpu_all_cores_rate(mesh, x_star, solver, budget_s=0.2)
     assert "unavailable" not in got, got
     assert got["kind"] == "port" and got["cores"] >= 1 and got["value"] > 0 and np.isfinite(got["value"])
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """N > 1: the driver launches the arm under torchrun like the product arm; rank 0 alone runs and prints, the other
+    ranks exit 0 without work."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--gpus", "2", "--n", "12", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2 and json.loads(lines[0])["impl"] == "reference"
