@@ -62,7 +62,7 @@ def test_reference_arm_under_torchrun_prints_once():
         port = s.getsockname()[1]
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference",
-                          "--gpus", "2", "--n", "12", "--steps", "2", "--warmup", "1"],
+                          "--gpus", "2", "--axis", "12", "--steps", "2", "--warmup", "1"],
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
