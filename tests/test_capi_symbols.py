@@ -29,6 +29,14 @@ def test_header_declares_the_expected_surface():
         assert must in syms
 
 
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/stormb200.h must compile as C99 (and as C++) on its own."""
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", HEADER],
+                ["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", HEADER]):
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+
+
 def test_library_exports_every_declared_symbol(lib):
     from stormruler_b200 import capi
     syms = declared_symbols()
