@@ -1,0 +1,33 @@
+#!/bin/bash
+# GPU sessions of round 2, one block per gpurun call; outputs go to gpurun_out/r02_<what>/ (summaries are copied to
+# profiles/ by hand afterwards).
+#
+#   gpurun --timeout 1500 -- 'bash scripts/gpu_session_r02.sh a'
+set -u
+what=${1:-a}
+out=gpurun_out/r02_$what
+mkdir -p "$out"
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+case "$what" in
+  a)
+    # 1. can two ranks share ONE GPU (time-sliced contexts, CUDA-IPC peer mapping of the same device)? If so the
+    #    world-size-2 bit-exactness tests run on the driver's 1-GPU test box.
+    ( time timeout 600 $TR --nproc-per-node 2 --master-port 29531 tests/_dist_worker.py p2p ) > "$out/two_ranks_one_gpu.log" 2>&1
+    echo "two ranks on one GPU: rc=$?"; tail -4 "$out/two_ranks_one_gpu.log"
+    # 2. statement grouping at full size (VERDICT task 3)
+    python scripts/solver_sweep.py --solvers cg,bicgstab,cgs,bicgstabl,tfqmr,tfqmr1,idrs,gmres,fgmres,richardson,grouped_idrs,grouped_bicgstabl \
+        --out "$out/solver_sweep_as_written.json" > "$out/as_written.log" 2>&1
+    python scripts/solver_sweep.py --grouping 1 --solvers cg,bicgstab,cgs,bicgstabl,tfqmr,tfqmr1,idrs,gmres,fgmres,richardson \
+        --out "$out/solver_sweep_grouping1.json" > "$out/grouping1.log" 2>&1
+    python scripts/solver_sweep.py --grouping 2 --solvers cg,bicgstab,cgs,bicgstabl,tfqmr,tfqmr1,idrs,gmres,fgmres,richardson \
+        --out "$out/solver_sweep_grouping2.json" > "$out/grouping2.log" 2>&1
+    tail -2 "$out/as_written.log" "$out/grouping1.log" "$out/grouping2.log"
+    # 3. what one rank of the 8-GPU run costs without any communication: 1.23 M tets on one GPU, per kernel slot
+    python bench.py --axis 59 --steps 200 --warmup 20 --no-cpu-baseline > "$out/bench_n1_axis59_bicgstab.json" 2> "$out/bench_axis59.err"
+    python bench.py --axis 59 --steps 200 --warmup 20 --no-cpu-baseline --solver cg > "$out/bench_n1_axis59_cg.json" 2>> "$out/bench_axis59.err"
+    tail -c 700 "$out/bench_n1_axis59_bicgstab.json"
+    # 4. config 5: the 1e8 / 2e8-cell points
+    python scripts/apply_sweep.py --cells hexlat --sizes 1e8,2e8 --out "$out/apply_sweep_hexlat.json" > "$out/config5.log" 2>&1
+    tail -3 "$out/config5.log"
+    ;;
+esac

@@ -27,6 +27,19 @@ def log(*a):
 
 
 # ---- torch.distributed plumbing ---------------------------------------------------------------------
+def local_device() -> int:
+    """CUDA device of this rank: LOCAL_RANK modulo the number of visible devices. With more ranks than devices the
+    ranks share GPUs (their kernels are time-sliced): slow, but the peer-memory protocol is exactly the one that
+    runs with a GPU per rank, so a 1-GPU box can run the world-size-2 bit-exactness tests."""
+    import torch
+    return int(os.environ.get("LOCAL_RANK", "0")) % max(1, torch.cuda.device_count())
+
+
+def oversubscribed() -> bool:
+    import torch
+    return int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))) > max(1, torch.cuda.device_count())
+
+
 def init_process_group(cuda: bool):
     """RANK / WORLD_SIZE / MASTER_* come from torchrun. CPU tensors travel over gloo (blobs, the
     partition array, timings); NCCL is initialised too on a GPU box so the launch contract's backend is
@@ -38,8 +51,10 @@ def init_process_group(cuda: bool):
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29511")
     if cuda:
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        dist.init_process_group(backend="cpu:gloo,cuda:nccl")
+        torch.cuda.set_device(local_device())
+        # several ranks on one device (protocol tests on a 1-GPU box): NCCL refuses duplicate devices, gloo carries
+        # the host-side plumbing alone (the data path never goes through torch.distributed anyway)
+        dist.init_process_group(backend="gloo" if oversubscribed() else "cpu:gloo,cuda:nccl")
     else:
         dist.init_process_group(backend="gloo")
     return dist
@@ -256,8 +271,8 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
     iter_ms), bracketed by barrier + synchronize; rank 0 reports K / max over ranks."""
     import torch
     world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = init_process_group(cuda=True)
+    local_rank = local_device()
     mode = capi.COMM_NCCL if args.comm == "nccl" else capi.COMM_P2P
     method = capi.PART_SLAB if args.partition == "slab" else capi.PART_METIS
     mesh, x_star = build_problem(args)

@@ -175,7 +175,7 @@ def run_cpu_lattice(dist, rank, world):
 def run_gpu(dist, rank, world, mode_name):
     import stormruler_b200 as sb
     mode = capi.COMM_NCCL if mode_name == "nccl" else capi.COMM_P2P
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_rank = mg.local_device()
     cases = ((CELL_TET, (14, 12, 10), capi.PART_METIS), (CELL_HEX, (24, 20, 18), capi.PART_SLAB),
              ("poly", (16,), capi.PART_METIS))
     for kind, dims, method in cases:
