@@ -126,16 +126,16 @@ def cpu_reference_rate(mesh, x_star, solver, budget_s=20.0, max_iters=None):
         else:
             r = orc.solve(solver, op, b, num_iterations=iters, abs_tol=0.0, rel_tol=0.0)
         assert r.iterations == iters
-        return time.perf_counter() - t
+        return time.perf_counter() - t, r
 
-    t1 = run(1)                       # init + 1 iteration: calibrates the budget
+    t1, _ = run(1)                    # init + 1 iteration: calibrates the budget
     per_it = max(t1 / 2.0, 1e-6)
     iters = int(max(2, min(budget_s / per_it, 2000)))
     if max_iters is not None:
         iters = max(2, min(iters, max_iters))
-    t_n = run(iters)
+    t_n, res = run(iters)
     rate = (iters - 1) / max(t_n - t1, 1e-9)   # subtract the initialisation (residual + first iteration)
-    return rate, kind, iters, t_n
+    return rate, kind, iters, t_n, res.hist
 
 
 def cpu_all_cores_rate(mesh, x_star, solver, budget_s=6.0):
@@ -223,11 +223,47 @@ def workload_config(args, mesh):
             "l2_policy": "inputs_larger_than_L2 (per-iteration working set >> 126 MB)"}
 
 
+def history_parity(gpu_hist, ref_hist):
+    """Residual history of the GPU path against the reference's own CPU run of the same problem: relative difference
+    per iteration (north_star bar 1e-10), its maximum, and the first iteration that exceeds the bar."""
+    k = min(len(gpu_hist), len(ref_hist))
+    rel = np.abs(np.asarray(gpu_hist[:k]) - np.asarray(ref_hist[:k])) / np.abs(np.asarray(ref_hist[:k]))
+    over = np.flatnonzero(rel > 1e-10)
+    return {"iterations_compared": int(k - 1), "max_rel_diff": float(rel.max()),
+            "first_iteration_over_1e-10": int(over[0]) if over.size else None,
+            "rel_diff_at": {str(i): float(rel[i]) for i in (1, 2, 5, 10, 20, 40) if i < k}}
+
+
+def phase_times(timeline, solver):
+    """Mean microseconds per step of an iteration from the persistent kernel's own timeline (globaltimer stamps of
+    CTA 0 behind every grid barrier), plus the waits it records."""
+    tl = np.asarray(timeline, dtype=np.int64)
+    names = {"bicgstab": ["direction", "apply+dot", "half_update", "apply+2dots", "final_update+2dots"],
+             "cg": ["apply+dot", "update+dot", "direction"]}[solver]
+    nb = len(names)
+    if tl.shape[0] < 2:
+        return None
+    tl = tl[1:]                                                  # the first iteration warms the caches
+    steps = np.diff(tl[:, :nb + 1], axis=1)
+    out = {"us_per_step": {nm: float(steps[:, k].mean()) * 1e-3 for k, nm in enumerate(names)},
+           "us_per_iteration": float((tl[:, nb] - tl[:, 0]).mean()) * 1e-3,
+           "us_barrier_wait_for_last_cta": {nm: float(tl[:, 6 + k].mean()) * 1e-3 for k, nm in enumerate(names)},
+           "us_allreduce_wait": {nm: float(tl[:, 11 + k].mean()) * 1e-3 for k, nm in enumerate(names) if "dot" in nm},
+           "us_halo_wait_max": [float(tl[:, 16 + k].mean()) * 1e-3 for k in range(2 if solver == "bicgstab" else 1)],
+           "iterations_sampled": int(tl.shape[0])}
+    return out
+
+
+SLOTS = {"bicgstab": ["direction", "apply+dot", "half_update", "apply+2dots", "final_update+2dots"],
+         "cg": ["apply+dot", "update+dot", "direction"]}
+KERNEL_NAME = {"bicgstab": "sb::krylov_persistent_kernel<BiCgStab, W> (the whole iteration loop, ONE cooperative launch)",
+               "cg": "sb::krylov_persistent_kernel<Cg, W> (the whole iteration loop, ONE cooperative launch)"}
+
+
 def run_own_arm(args):
     import stormruler_b200 as sb
     from stormruler_b200 import capi
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from stormruler_b200 import multigpu
@@ -243,42 +279,65 @@ def run_own_arm(args):
     xs = ctx.vector(x_star)
     b = ctx.zeros(n)
     op.mul(b, xs)                                   # b = A x*
-    Solver = sb.BiCgStabSolver if args.solver == "bicgstab" else sb.CgSolver
-    applies_per_it, passes_per_it = (2, 15) if args.solver == "bicgstab" else (1, 9)
-
-    def solve(iters, **kw):
-        s = Solver(num_iterations=iters, absolute_error_tolerance=0.0, relative_error_tolerance=0.0,
-                   record=False, **kw)
-        x = ctx.zeros(n)
-        s.solve(x, b, op)
-        assert s.iteration == iters, (s.iteration, iters)
-        return s, x
-
-    solve(max(args.warmup, 3), use_graph=True)                       # warm-up (untimed)
-    launches0 = ctx.launch_count
-    s, x = solve(args.steps, use_graph=True)                         # timed: exactly K iterations
-    gpu_launches = s.launches
-    rep_ms = _iter_ms(s)
-    value = args.steps / (rep_ms * 1e-3)
-    # per-kernel breakdown of the same K iterations (events around every launch, no graph)
-    sp, _ = solve(args.steps, profile=True)
-    kms = _kernel_ms(sp)
-    err = np.linalg.norm(x.numpy() - x_star) / np.linalg.norm(x_star)
-
-    # ---- roofline of the dominant kernel: the operator apply ----
+    schedule = {"auto": capi.SCHEDULE_AUTO, "stepwise": capi.SCHEDULE_STEPWISE, "persistent": capi.SCHEDULE_PERSISTENT}[args.schedule]
     peak, peak_src = peaks()
     alg_apply = op.info.algorithmic_bytes_per_apply
-    slots = {"bicgstab": ["direction", "apply+dot", "half_update", "apply+2dots", "final_update+2dots"],
-             "cg": ["apply+dot", "update+dot", "direction"]}[args.solver]
-    apply_slots = [k for k, nm in enumerate(slots) if nm.startswith("apply")]
-    apply_ms = sum(kms[k] for k in apply_slots) / (len(apply_slots) * args.steps)   # avg per launch
-    achieved = alg_apply / (apply_ms * 1e-3) / 1e9
-    alg_iter = applies_per_it * alg_apply + passes_per_it * 8 * n
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "apply_traffic.json")
+
+    def measure(solver):
+        """W untimed + exactly K timed iterations of `solver` (device time of the iteration loop, CUDA events on the
+        solver's stream), the in-kernel timeline of the same schedule, and the per-kernel times of the stepwise one."""
+        Solver = sb.BiCgStabSolver if solver == "bicgstab" else sb.CgSolver
+        applies_per_it, passes_per_it = (2, 15) if solver == "bicgstab" else (1, 9)
+
+        def solve(iters, **kw):
+            s = Solver(num_iterations=iters, absolute_error_tolerance=0.0, relative_error_tolerance=0.0,
+                       record=kw.pop("record", False), **kw)
+            x = ctx.zeros(n)
+            s.solve(x, b, op)
+            assert s.iteration == iters, (s.iteration, iters)
+            return s, x
+
+        solve(max(args.warmup, 3), use_graph=True, schedule=schedule)            # warm-up (untimed)
+        s, x = solve(args.steps, use_graph=True, schedule=schedule)              # timed: exactly K iterations
+        value = args.steps / (s.iter_ms * 1e-3)
+        alg_iter = applies_per_it * alg_apply + passes_per_it * 8 * n
+        out = {"solver": solver, "s": s, "x": x, "value": value, "ms_per_step": s.iter_ms / args.steps,
+               "alg_iter": alg_iter, "applies_per_it": applies_per_it,
+               "schedule": {capi.SCHEDULE_PERSISTENT: "persistent", capi.SCHEDULE_STEPWISE: "stepwise"}[s.schedule_used],
+               "iteration_roofline": {"algorithmic_bytes_per_iteration": int(alg_iter),
+                                      "achieved_gbs": alg_iter * value / 1e9,
+                                      "frac_of_measured_peak": alg_iter * value / 1e9 / peak,
+                                      "frac_of_nominal_8TBs": alg_iter * value / 8e12}}
+        if s.schedule_used == capi.SCHEDULE_PERSISTENT:
+            st, _ = solve(min(args.steps, 64), schedule=schedule, timeline_iters=min(args.steps, 64))
+            out["phases"] = phase_times(st.timeline, solver)
+        # per-kernel breakdown of the same K iterations in the stepwise schedule (events around every launch, no graph)
+        sp, _ = solve(args.steps, profile=True)
+        kms = list(sp.kernel_ms)
+        slots = SLOTS[solver]
+        apply_slots = [k for k, nm in enumerate(slots) if nm.startswith("apply")]
+        apply_ms = sum(kms[k] for k in apply_slots) / (len(apply_slots) * args.steps)   # avg per launch
+        out["stepwise"] = {"kernel_ms_per_iteration": {nm: kms[k] / args.steps for k, nm in enumerate(slots)},
+                           "apply_kernel": {"kernel": "sb::apply_kernel_tma + one-CTA final stage (stepwise schedule, profiled)",
+                                            "algorithmic_bytes_per_launch": int(alg_apply), "avg_launch_ms": apply_ms,
+                                            "achieved": alg_apply / (apply_ms * 1e-3) / 1e9,
+                                            "frac": alg_apply / (apply_ms * 1e-3) / 1e9 / peak,
+                                            "share_of_step": sum(kms[k] for k in apply_slots) / sum(kms[:len(slots)])}}
+        return out
+
+    main = measure(args.solver)
+    other = None
+    if not args.single_solver:
+        other = measure("cg" if args.solver == "bicgstab" else "bicgstab")   # the other target solver, same problem
+    s, x = main["s"], main["x"]
+    err = np.linalg.norm(x.numpy() - x_star) / np.linalg.norm(x_star)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "persistent_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            t = json.load(open(tpath))[args.solver]
+            # dram bytes per iteration of the same kernel from the committed ncu --set full capture, scaled to K
+            traffic, traffic_src = t["dram_bytes_per_iteration"] * args.steps, t["source"]
         except Exception:
             traffic = None
 
@@ -287,25 +346,37 @@ def run_own_arm(args):
     hx = torch.zeros(n, dtype=torch.float64).pin_memory()
     hb = torch.from_numpy(b.numpy()).pin_memory()
     hxn, hbn = hx.numpy(), hb.numpy()
-    sb.solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=3, abs_tol=0.0, rel_tol=0.0, use_graph=True)
+    sb.solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=3, abs_tol=0.0, rel_tol=0.0, use_graph=True, schedule=schedule)
     hxn[:] = 0.0
     ctx.sync()
     t = time.perf_counter()
     rep = sb.solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=args.steps, abs_tol=0.0, rel_tol=0.0,
-                        use_graph=True)
+                        use_graph=True, schedule=schedule)
     e2e_s = time.perf_counter() - t
     assert rep.iterations == args.steps
     e2e_value = args.steps / e2e_s
     clocks = sampler.stop()
 
-    # ---- CPU baseline beside it (bounded sample of the same workload) ----
-    cpu = None
+    # ---- CPU baseline beside it (bounded sample of the same workload) + parity of the residual histories ----
+    cpu = parity = None
     if not args.no_cpu_baseline:
-        rate, kind, iters, secs = cpu_reference_rate(mesh, x_star, args.solver, budget_s=args.cpu_budget)
+        rate, kind, iters, secs, ref_hist = cpu_reference_rate(mesh, x_star, args.solver, budget_s=args.cpu_budget)
         cpu = {"value": rate, "unit": "it/s", "cores": 1, "kind": kind,
                "sample": f"{iters} {args.solver} iterations of the same {n}-cell problem ({secs:.1f} s), reference "
                          f"solver headers + face-loop operator, g++ -O2 -ffp-contract=off, 1 thread "
                          f"(the reference is single-threaded by construction)"}
+        # the same iterations on the GPU, history recorded: the measured path (coefficient rows, tree reductions) and
+        # the faithful rows (the face loop's own arithmetic: only the reduction order differs from the reference)
+        Solver = sb.BiCgStabSolver if args.solver == "bicgstab" else sb.CgSolver
+        parity = {"against": f"{kind}: the reference's solver headers + face loop, sequential sums, first {iters} iterations "
+                             f"of the same {n}-cell problem", "bar": "1e-10 relative per iteration (north_star)"}
+        for label, form in (("measured_path_coef_rows", sb.FORM_COEF), ("faithful_rows", sb.FORM_FAITHFUL)):
+            o = op if form == sb.FORM_COEF else sb.FvmOperator(ctx, mesh, prefill=0, dt=-1.0, form=form, dirichlet=True)
+            sg = Solver(num_iterations=iters, absolute_error_tolerance=0.0, relative_error_tolerance=0.0, record=True)
+            xg = ctx.zeros(n)
+            sg.solve(xg, b, o)
+            parity[label] = history_parity(sg.history, ref_hist)
+            del o, xg
 
     cpu_all = None
     if not args.no_cpu_baseline:
@@ -314,38 +385,40 @@ def run_own_arm(args):
         except Exception as e:  # noqa: BLE001
             cpu_all = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
+    persistent = main["schedule"] == "persistent"
+    alg_launch = main["alg_iter"] * args.steps if persistent else alg_apply
+    launch_ms = s.iter_ms if persistent else main["stepwise"]["apply_kernel"]["avg_launch_ms"]
+    achieved = alg_launch / (launch_ms * 1e-3) / 1e9
     line = {
-        "metric": "krylov_iterations_per_sec", "value": value, "unit": "it/s", "n_gpus": 1,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": rep_ms / args.steps,
+        "metric": "krylov_iterations_per_sec", "value": main["value"], "unit": "it/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, mesh),
-        "roofline": {"bound": "hbm", "kernel": "operator apply + fused dot(s) (sb::apply_kernel)",
+        "config": dict(workload_config(args, mesh), schedule=main["schedule"]),
+        "roofline": {"bound": "hbm",
+                     "kernel": KERNEL_NAME[args.solver] if persistent else main["stepwise"]["apply_kernel"]["kernel"],
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": int(alg_apply), "avg_launch_ms": apply_ms,
-                     "share_of_step": sum(kms[k] for k in apply_slots) / sum(kms[:len(slots)])},
-        "iteration_roofline": {"algorithmic_bytes_per_iteration": int(alg_iter),
-                               "achieved_gbs": alg_iter * value / 1e9, "frac_of_measured_peak": alg_iter * value / 1e9 / peak,
-                               "frac_of_nominal_8TBs": alg_iter * value / 8e12},
-        "kernel_ms_per_iteration": {nm: kms[k] / args.steps for k, nm in enumerate(slots)},
-        "applies_per_sec": applies_per_it * value,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(alg_launch), "avg_launch_ms": launch_ms,
+                     "launches_timed": 1 if persistent else 2 * args.steps,
+                     "share_of_step": 1.0 if persistent else main["stepwise"]["apply_kernel"]["share_of_step"],
+                     "note": "persistent schedule: one launch = K iterations = K x (applies x (24 N + 12 entries) + passes x 8 N) "
+                             "algorithmic bytes, timed by CUDA events around the launch" if persistent else None},
+        "iteration_roofline": main["iteration_roofline"],
+        "phases": main.get("phases"),
+        "stepwise": main["stepwise"],
+        "applies_per_sec": main["applies_per_it"] * main["value"],
+        "other_solver": None if other is None else {k: other[k] for k in ("solver", "value", "ms_per_step", "schedule",
+                                                                        "iteration_roofline", "phases", "stepwise")},
         "cpu_baseline": cpu,
         "cpu_baseline_all_cores": cpu_all,
+        "parity": parity,
         "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": 16 * n / args.steps,
                 "d2h_bytes_per_step": 8 * n / args.steps,
                 "note": f"one sb_solve_host call = H2D(x0,b) + init + {args.steps} iterations + D2H(x), pinned host buffers"},
-        "gpu_launches": int(gpu_launches), "clocks": clocks,
+        "gpu_launches": int(s.launches), "clocks": clocks,
         "rel_error_vs_exact_after_steps": float(err), "residual_after_steps": float(s.absolute_error),
     }
     print(json.dumps(line), flush=True)
-
-
-def _iter_ms(s):
-    return float(s.iter_ms)
-
-
-def _kernel_ms(s):
-    return list(s.kernel_ms)
 
 
 def main():
@@ -363,6 +436,9 @@ def main():
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: halo exchange + reductions by in-kernel NVLink peer stores (p2p) or NCCL send/recv + allreduce")
     ap.add_argument("--partition", default="metis", choices=["metis", "slab"], help="N>1: METIS k-way or contiguous RCM slabs")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "stepwise", "persistent"],
+                    help="fused-solver schedule of the timed run (auto = persistent whole-solve kernel)")
+    ap.add_argument("--single-solver", action="store_true", help="skip the leg of the other target solver (cg <-> bicgstab)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -39,6 +39,8 @@ extern "C" {
 #define SB_ERR_NOMEM (-3)
 #define SB_ERR_NCCL (-4)
 #define SB_ERR_STATE (-5)   /* call not valid in this state (e.g. comm not initialised) */
+#define SB_ERR_COMM (-6)    /* a device-side wait for a peer (or for the grid) gave up after SB_SPIN_TIMEOUT_S
+                               seconds (default 120): results are meaningless, the context is unusable */
 
 typedef struct sb_ctx sb_ctx;
 typedef struct sb_op sb_op;
@@ -393,8 +395,30 @@ typedef struct sb_solver_opts {
   int32_t check_every;    /* host polls the device convergence flag every this many iterations (0 = 32) */
   int32_t use_graph;      /* 1: replay one captured CUDA graph per iteration */
   int32_t profile;        /* 1: bracket every kernel of the iteration with CUDA events (no graph) and
-                             report the accumulated time per kernel slot in sb_solver_report.kernel_ms */
+                             report the accumulated time per kernel slot in sb_solver_report.kernel_ms
+                             (implies the stepwise schedule) */
+  int32_t schedule;       /* SB_SCHEDULE_*; 0 = automatic: persistent wherever it is available */
+  int32_t timeline_iters; /* persistent schedule: record the in-kernel timeline of the first this-many
+                             iterations into h_timeline (0 = off) */
+  uint64_t* h_timeline;   /* [timeline_iters][SB_TIMELINE_WORDS], globaltimer nanoseconds, written by CTA 0:
+                             [0] iteration start; [1+b] time after grid barrier b of the iteration (BiCGStab:
+                             b = 0 direction, 1 apply+dot, 2 half update, 3 apply+2 dots, 4 final update;
+                             CG: 0 apply+dot, 1 update+dot, 2 direction); [6+b] ns CTA 0 waited at barrier b for
+                             the last CTA of its own GPU; [11+b] ns between posting this rank's sums and
+                             holding every rank's (reducing barriers only); [16+k] longest wait of any warp
+                             of this rank for a neighbour's halo values in apply k */
 } sb_solver_opts;
+
+/* Schedules of the fused CG / BiCGStab solvers (bit-identical results):
+ *   STEPWISE   one kernel per step of the iteration + a one-CTA kernel per reduction (optionally replayed as a
+ *              CUDA graph): 5 / 8 launches per CG / BiCGStab iteration;
+ *   PERSISTENT one cooperative kernel runs the whole iteration loop; steps are separated by grid-wide barriers
+ *              in global memory, the reductions and (multi-GPU) the all-reduce over NVLink peer memory happen
+ *              inside the barrier. Needs the coefficient form; multi-GPU needs SB_COMM_P2P. */
+#define SB_SCHEDULE_AUTO 0
+#define SB_SCHEDULE_STEPWISE 1
+#define SB_SCHEDULE_PERSISTENT 2
+#define SB_TIMELINE_WORDS 20
 
 #define SB_MAX_KERNEL_SLOTS 8
 
@@ -413,6 +437,7 @@ typedef struct sb_solver_report {
   double kernel_ms[SB_MAX_KERNEL_SLOTS]; /* profile=1: total device time per kernel slot, in launch order
                                             (CG: apply+dot, update+dot, direction; BiCGStab: direction,
                                             apply+dot, half update, apply+2 dots, final update+2 dots) */
+  int32_t schedule;    /* SB_SCHEDULE_STEPWISE or SB_SCHEDULE_PERSISTENT: the one that ran */
 } sb_solver_report;
 
 SB_API int sb_cg_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b,

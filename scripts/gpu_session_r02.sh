@@ -30,4 +30,26 @@ case "$what" in
     python scripts/apply_sweep.py --cells hexlat --sizes 1e8,2e8 --out "$out/apply_sweep_hexlat.json" > "$out/config5.log" 2>&1
     tail -3 "$out/config5.log"
     ;;
+  b)
+    # the persistent whole-solve kernel: parity first (bounded spins so that a protocol bug ends in an error, not a hang)
+    export SB_SPIN_TIMEOUT_S=20
+    timeout 900 python -m pytest tests/test_gpu_mega.py -x -q 2>&1 | tail -25 > "$out/pytest_mega.log"; cat "$out/pytest_mega.log"
+    timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -30 > "$out/pytest_gpu.log"; tail -12 "$out/pytest_gpu.log"
+    ( time timeout 600 $TR --nproc-per-node 2 --master-port 29531 tests/_dist_worker.py p2p ) > "$out/two_ranks_one_gpu.log" 2>&1
+    echo "two ranks on one GPU: rc=$?"; tail -6 "$out/two_ranks_one_gpu.log"
+    unset SB_SPIN_TIMEOUT_S
+    python bench.py --axis 59 --steps 200 --warmup 20 --no-cpu-baseline > "$out/bench_n1_axis59.json" 2> "$out/bench_axis59.err"
+    tail -c 1500 "$out/bench_n1_axis59.json"
+    python bench.py --steps 200 --warmup 20 > "$out/bench_n1.json" 2> "$out/bench_n1.err"
+    tail -c 2500 "$out/bench_n1.json"; tail -3 "$out/bench_n1.err"
+    python scripts/solver_sweep.py --solvers cg,bicgstab,cgs,bicgstabl,tfqmr,tfqmr1,idrs,gmres,fgmres,richardson,grouped_idrs,grouped_bicgstabl \
+        --out "$out/solver_sweep_as_written.json" > "$out/as_written.log" 2>&1
+    python scripts/solver_sweep.py --grouping 1 --solvers cg,bicgstab,cgs,bicgstabl,tfqmr,tfqmr1,idrs,gmres,fgmres,richardson \
+        --out "$out/solver_sweep_grouping1.json" > "$out/grouping1.log" 2>&1
+    python scripts/solver_sweep.py --grouping 2 --solvers cg,bicgstab,cgs,bicgstabl,tfqmr,tfqmr1,idrs,gmres,fgmres,richardson \
+        --out "$out/solver_sweep_grouping2.json" > "$out/grouping2.log" 2>&1
+    tail -2 "$out/as_written.log" "$out/grouping1.log" "$out/grouping2.log"
+    python scripts/apply_sweep.py --cells hexlat --sizes 1e8,2e8 --out "$out/apply_sweep_hexlat.json" > "$out/config5.log" 2>&1
+    tail -3 "$out/config5.log"
+    ;;
 esac

@@ -19,9 +19,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libstormb200.so")
-SOURCES = ["sb_api.cu", "sb_op.cu", "sb_solvers.cu", "sb_gmres.cu", "sb_comm.cu", "sb_mesh_host.cpp", "sb_part_host.cpp"]
+SOURCES = ["sb_api.cu", "sb_op.cu", "sb_solvers.cu", "sb_mega.cu", "sb_gmres.cu", "sb_comm.cu", "sb_mesh_host.cpp", "sb_part_host.cpp"]
 METIS = "/usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a"  # ships with the CUDA toolkit
-HEADERS = [os.path.join(CSRC, h) for h in ("sb_common.cuh", "sb_kernels.cuh", "sb_group_body.cuh", "sb_apply_rows.cuh", "sb_op.cuh", "sb_comm.cuh")] + \
+HEADERS = [os.path.join(CSRC, h) for h in ("sb_common.cuh", "sb_kernels.cuh", "sb_group_body.cuh", "sb_apply_rows.cuh", "sb_op.cuh", "sb_comm.cuh", "sb_solver_bodies.cuh", "sb_mega.cuh")] + \
     [os.path.join(HERE, "..", "include", "stormb200.h"), os.path.abspath(__file__)]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     todo = [s for s in SOURCES
             if force or _stale(os.path.join(OBJ, os.path.splitext(s)[0] + ".o"), [os.path.join(CSRC, s)] + HEADERS)]
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=8) as ex:
         list(ex.map(lambda s: _compile(s, verbose), todo))
     objs = [os.path.join(OBJ, os.path.splitext(s)[0] + ".o") for s in SOURCES]
     if todo or _stale(LIB, objs):

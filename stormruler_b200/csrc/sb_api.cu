@@ -51,6 +51,11 @@ int sb_ctx_create(int device, sb_ctx** out) {
   ctx->device = device;
   if (const char* dbg = std::getenv("SB_DEBUG")) ctx->debug = std::atoi(dbg);
   if (const char* pdl = std::getenv("SB_PDL")) ctx->pdl = std::atoi(pdl) != 0;
+  ctx->spin_timeout_ns = sb::kDefaultSpinTimeoutNs;
+  if (const char* t = std::getenv("SB_SPIN_TIMEOUT_S")) {
+    const double secs = std::atof(t);
+    if (secs > 0.0) ctx->spin_timeout_ns = (unsigned long long) (secs * 1e9);
+  }
   SB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   SB_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   SB_CUDA(cudaMalloc(&ctx->red.result, sizeof(double) * 64));
@@ -77,6 +82,8 @@ int sb_ctx_destroy(sb_ctx* ctx) {
   cudaFree(ctx->d_gmres_ptrs);
   cudaFreeHost(ctx->h_gmres);
   comm_teardown(ctx);
+  cudaFree(ctx->d_mega);
+  cudaFree(ctx->d_timeline);
   cudaFree(ctx->d_state);
   cudaFree(ctx->d_hist);
   cudaFree(ctx->d_trace);

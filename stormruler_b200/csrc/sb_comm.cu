@@ -275,6 +275,7 @@ int sb_comm_prepare(sb_ctx* ctx, int rank, int world, int mode, int64_t vec_capa
     ctx->pool_free.push_back(reinterpret_cast<double*>(ctx->slab + kCtrlBytes) + (size_t) k * (size_t) cap);
   ctx->comm = CommDev{};
   ctx->comm.rank = rank, ctx->comm.world = world, ctx->comm.mode = mode;
+  ctx->comm.timeout_ns = ctx->spin_timeout_ns;
   ctx->comm.base[rank] = ctx->slab;
   Blob b{};
   b.rank = rank, b.world = world, b.mode = mode, b.device = ctx->device;

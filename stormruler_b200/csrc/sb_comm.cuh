@@ -18,15 +18,18 @@
 //     differs from the NaN sentinel, resets it, and thread 0 adds the P values in rank order.
 //     Two parities suffice: a rank can start all-reduce #a+2 only after every peer contributed to
 //     #a+1, i.e. after every peer has read (and reset) its #a mailboxes.
-// Every spin loop is bounded (SB_SPIN_TIMEOUT_NS, default 20 s): on expiry the kernel records the
-// reason in CommCtrl::error and traps, so a lost peer fails loudly instead of hanging the GPU.
+// Every spin loop is bounded (CommDev::timeout_ns = sb_ctx::spin_timeout_ns: env SB_SPIN_TIMEOUT_S, default 120 s):
+// on expiry the kernel records the reason in CommCtrl::error and gives up WITHOUT trapping (a trap would destroy the
+// CUDA context of this rank and, one timeout later, of every peer); every later wait of this rank sees the error
+// word and returns at once, so whatever is queued drains in microseconds with meaningless values, and the host turns
+// the error word into SB_ERR_COMM at the end of the solve (sb_comm_status for the stand-alone entry points).
 #pragma once
 
 #include "sb_common.cuh"
 
 namespace sb {
 
-constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long kDefaultSpinTimeoutNs = 120ull * 1000ull * 1000ull * 1000ull;
 
 // Programmatic dependent launch: every kernel calls pdl_trigger() (dependents may be scheduled) and then
 // pdl_wait() (all prerequisite grids have completed and their writes are visible) before it touches
@@ -72,21 +75,32 @@ __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned l
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-static __device__ __noinline__ void comm_fail(CommCtrl* ctrl, unsigned long long code) {
-  ctrl->error = code;
-  __threadfence_system();
-  __trap();
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
-// Spin until *flag >= want (acquire).
-__device__ __forceinline__ void wait_flag_ge(const unsigned long long* flag, unsigned long long want, CommCtrl* ctrl,
-                                             unsigned long long code) {
-  if (ld_acquire_sys(flag) >= want) return;
+static __device__ __noinline__ void comm_fail(CommCtrl* ctrl, unsigned long long code) {
+  atomicCAS(&ctrl->error, 0ull, code); // the first failure is the one reported
+  __threadfence_system();
+}
+__device__ __forceinline__ bool comm_failed(const CommCtrl* ctrl) { return ld_relaxed_gpu(&ctrl->error) != 0; }
+
+// Spin until *flag >= want (acquire). False: gave up (timeout, or this rank has already failed).
+__device__ __forceinline__ bool wait_flag_ge(const unsigned long long* flag, unsigned long long want, CommCtrl* ctrl,
+                                             unsigned long long code, unsigned long long timeout_ns) {
+  if (ld_acquire_sys(flag) >= want) return true;
+  if (comm_failed(ctrl)) return false;
   const unsigned long long t0 = globaltimer_ns();
   while (ld_acquire_sys(flag) < want) {
     __nanosleep(64);
-    if (globaltimer_ns() - t0 > kSpinTimeoutNs) comm_fail(ctrl, code);
+    if (globaltimer_ns() - t0 > timeout_ns || comm_failed(ctrl)) {
+      comm_fail(ctrl, code);
+      return false;
+    }
   }
+  return true;
 }
 
 // ---- halo pack, P2P: boundary values go straight into the neighbours' halo tails -------------------
@@ -102,7 +116,7 @@ __device__ __forceinline__ void halo_pack_role(const CommDev& comm, const HaloDe
     st_release_sys(&comm.ctrl(halo.nbr_rank[threadIdx.x])->ack_flag[comm.rank], seq - 1);
   }
   if (threadIdx.x < halo.n_nbr)
-    wait_flag_ge(&me->ack_flag[halo.nbr_rank[threadIdx.x]], seq - 1, me, 0xA000 + threadIdx.x);
+    wait_flag_ge(&me->ack_flag[halo.nbr_rank[threadIdx.x]], seq - 1, me, 0xA000 + halo.nbr_rank[threadIdx.x], comm.timeout_ns);
   __syncthreads();
   const int64_t total = halo.send_ptr[halo.n_nbr];
   for (int64_t i = (int64_t) blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t) n_pack * kThreads) {
@@ -167,10 +181,14 @@ __device__ __forceinline__ void allreduce_p2p(const CommDev& comm, double (&sums
     st_relaxed_sys(&comm.ctrl(r)->ar_slot[par][comm.rank][d], (unsigned long long) __double_as_longlong(s_local[d]));
     unsigned long long* box = &me->ar_slot[par][r][d];
     unsigned long long v = ld_relaxed_sys(box);
-    if (v == kArSentinel) {
+    if (v == kArSentinel && !comm_failed(me)) {
       const unsigned long long t0 = globaltimer_ns();
+      unsigned spins = 0;
       while ((v = ld_relaxed_sys(box)) == kArSentinel) {
-        if (globaltimer_ns() - t0 > kSpinTimeoutNs) comm_fail(me, 0xC000 + r);
+        if ((++spins & 63u) == 0 && (globaltimer_ns() - t0 > comm.timeout_ns || comm_failed(me))) {
+          comm_fail(me, 0xC000 + r);
+          break;
+        }
       }
     }
     st_relaxed_sys(box, kArSentinel);

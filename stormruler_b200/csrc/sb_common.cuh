@@ -25,8 +25,8 @@ constexpr int kTile = kThreads * 2 * kSub; // 2048
 constexpr int kMaxDots = 3;
 constexpr int32_t kColPad = INT32_MIN;
 
-inline int64_t pad_up(int64_t n) { return ((n + kTile - 1) / kTile) * kTile; }
-inline int64_t num_tiles(int64_t n) { return (n + kTile - 1) / kTile; }
+__host__ __device__ inline int64_t pad_up(int64_t n) { return ((n + kTile - 1) / kTile) * kTile; }
+__host__ __device__ inline int64_t num_tiles(int64_t n) { return (n + kTile - 1) / kTile; }
 
 // ---- errors ----------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
@@ -72,7 +72,9 @@ struct CommCtrl {
                                            // that follows each apply, so it is stable while an apply kernel runs)
   unsigned long long ar_seq;               // all-reduces completed so far by this rank
   unsigned long long pack_ticket;          // last-CTA detection of the pack kernel
-  unsigned long long error;                // set before a spin loop gives up
+  unsigned long long error;                // set when a spin wait gave up (code | waited-for rank); once non-zero every
+                                           // later wait of this rank returns at once, so queued kernels drain, and the
+                                           // host reports SB_ERR_COMM (sb_comm_status, end of every fused solve)
   unsigned long long pad[4];
   unsigned long long ar_slot[2][kMaxRanks][4]; // all-reduce mailboxes (value is the flag), by seq parity
 };
@@ -82,11 +84,14 @@ static_assert(sizeof(CommCtrl) <= kCtrlBytes, "control block too large");
 struct CommDev {
   int32_t rank = 0, world = 1, mode = -1; // mode: -1 none, SB_COMM_NCCL, SB_COMM_P2P
   int32_t pad = 0;
+  unsigned long long timeout_ns = 0;      // bound of every peer spin wait (sb_ctx::spin_timeout_ns)
   unsigned char* base[kMaxRanks] = {};    // mapped slab of every rank (base[rank] = my own)
   __host__ __device__ CommCtrl* ctrl(int r) const { return reinterpret_cast<CommCtrl*>(base[r]); }
 };
 
 // Device-resident reduction scratch: per-tile partial sums and the output slots.
+struct MegaCtrl; // sb_mega.cuh
+
 struct RedScratch {
   double* partials = nullptr; // [kMaxDots][cap_tiles]
   int64_t cap_tiles = 0;
@@ -146,6 +151,11 @@ struct sb_ctx {
   // Off by default: measured on B200 it gains 1-2 % with plain stream launches but LOSES 4-7 % inside a
   // replayed CUDA graph (programmatic edges), and the graph is the faster of the two.
   int pdl = 0;
+  // persistent whole-solve kernel (sb_mega.cu): grid barrier / mailbox block, timeline scratch
+  struct sb::MegaCtrl* d_mega = nullptr;
+  unsigned long long* d_timeline = nullptr;
+  int64_t timeline_cap = 0;
+  unsigned long long spin_timeout_ns = 0; // bound of every device-side spin wait (SB_SPIN_TIMEOUT_S, default 120 s)
 };
 
 namespace sb {

@@ -66,17 +66,13 @@ __device__ __forceinline__ void block_reduce_partials(double (&acc)[ND], const R
   }
 }
 
-// Final stage of SB_TREE v1: one CTA of 256 threads. Thread t adds partial[t], partial[t+256], ...
+// Final stage of SB_TREE v1, run by one CTA of 256 threads. Thread t adds partial[t], partial[t+256], ...
 // in that order (loads of a batch are independent and issued together; only the additions are
-// sequential), butterfly per warp, the 8 warp sums added left to right. `fin(sums)` then runs on one
-// thread: that is where the solver scalars (alpha, beta, residual, stop flag) are updated.
-template<int ND, class Final>
-__global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles, RedPtrs red, Final fin, CommDev comm,
-                                                                CommCtrl* bump, const int* __restrict__ done) {
-  pdl_trigger();
-  pdl_wait();
-  if (is_done(done)) return;
-  __shared__ double s_w[ND][kWarps];
+// sequential), butterfly per warp, the 8 warp sums added left to right. The totals are valid in thread 0.
+// `s_w` is caller-provided shared scratch; the function ends behind a __syncthreads.
+template<int ND>
+__device__ __forceinline__ void final_stage(int64_t n_tiles, const RedPtrs& red, double (&s_w)[kMaxDots][kWarps],
+                                            double (&sums)[ND]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kBatch = 8;
   double s[ND];
@@ -108,7 +104,6 @@ __global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles,
     if (lane == 0) s_w[d][warp] = v;
   }
   __syncthreads();
-  double sums[ND];
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
@@ -118,6 +113,19 @@ __global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles,
       sums[d] = t;
     }
   }
+}
+
+// The one-CTA kernel behind every reducing kernel of the one-kernel-per-step schedule. `fin(sums)` runs on one
+// thread: that is where the solver scalars (alpha, beta, residual, stop flag) are updated.
+template<int ND, class Final>
+__global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles, RedPtrs red, Final fin, CommDev comm,
+                                                                CommCtrl* bump, const int* __restrict__ done) {
+  pdl_trigger();
+  pdl_wait();
+  if (is_done(done)) return;
+  __shared__ double s_w[kMaxDots][kWarps];
+  double sums[ND];
+  final_stage<ND>(n_tiles, red, s_w, sums);
   // multi-GPU, P2P mode: exchange the rank sums with every peer inside this kernel (rank-ordered total)
   if (comm.mode == SB_COMM_P2P && comm.world > 1) allreduce_p2p<ND>(comm, sums);
   if (threadIdx.x == 0) {

@@ -1,0 +1,501 @@
+// sb_mega.cuh -- the persistent whole-solve kernel of the fused CG / BiCGStab solvers.
+//
+// The one-kernel-per-step schedule (sb_solvers.cu) pays a kernel boundary per step: 8 launches per BiCGStab
+// iteration (5 steps + 3 one-CTA reduction stages), each ~2.6 us of drain + launch + ramp-up, plus a second wave of
+// CTAs per launch. At 10 M cells on one GPU that is 5 % of an iteration; at 1.26 M cells per rank (10 M cells on 8
+// GPUs) it is a third of it, and the cross-GPU all-reduce sits behind yet another launch. Here ONE cooperative
+// kernel runs the whole iteration loop: a grid of (SMs x resident CTAs) persistent CTAs, every CTA owns the row
+// tiles {blockIdx.x, blockIdx.x + grid, ...} in every step, and the steps are separated by grid-wide barriers in
+// global memory (~1 us) instead of kernel boundaries:
+//
+//   BiCGStab iteration (SolverBiCgStab.hpp:93-165)          CG iteration (SolverCg.hpp:86-126)
+//     p = r + beta (p - omega v)        | barrier             z = A p, <p,z>          | barrier + all-reduce
+//     v = A p, <r~,v>                   | barrier + all-reduce x += a p, r -= a z, <r,r> | barrier + all-reduce
+//     r -= alpha v                      | barrier             p = r + beta p          | barrier
+//     t = A r, <t,t>, <t,r>             | barrier + all-reduce
+//     x = (x + alpha p) + omega r, r -= omega t, <r,r>, <r~,r> | barrier + all-reduce
+//
+// Same element-wise bodies, same scalar updates, same reduction tree (SB_TREE v1) as the one-kernel-per-step
+// schedule, so the two are bit-identical to each other and to the oracle (tests/test_gpu_mega.py).
+//
+// Reducing barrier: every CTA stores its tile partials and arrives; CTA 0 sees the last arrival, runs the final stage
+// of SB_TREE over the partials and "sends" the rank sums into the all-reduce mailbox of every rank (its own included;
+// on one GPU the mailbox is local); EVERY CTA polls the mailbox, adds the rank sums in rank order and runs the
+// solver's scalar update on its own copy of the solver state in shared memory -- identical inputs, identical code,
+// identical bits, so all CTAs of all ranks take the same decisions (alpha, beta, omega, stop) without another
+// broadcast. Only CTA 0 records the residual history and writes the state back. The mailbox of all-reduce #a is
+// reset by CTA 0 while it handles #a+1 (every local CTA has read it by then), before it sends #a+1 -- a peer cannot
+// post #a+2 before it has seen my #a+1.
+//
+// Operator apply inside the loop: the TMA-staged tile pipeline of apply_kernel_tma, with the ring running across
+// the tiles of a CTA (no pipeline ramp per tile). Gathers use the coherent path (ld.global.ca): x is written by
+// this very kernel, and every grid barrier ends in a gpu-scope fence (which invalidates L1). Distributed operator:
+// the boundary values are packed and pushed to the neighbours' halo tails by the first CTAs at the start of the
+// apply step, boundary tiles (the last ones of every CTA) acquire the neighbours' flags. No ack round is needed:
+// between two applies that write the same halo tail there is always an all-reduce, and a rank contributes to it
+// only after all its CTAs have finished the earlier apply.
+#pragma once
+
+#include "sb_solver_bodies.cuh"
+
+namespace sb {
+
+// Per-context device block of the persistent kernel (grid barrier, single-GPU mailbox, abort flag).
+struct MegaCtrl {
+  unsigned long long arrive; // grid-barrier arrival counter (zeroed by the host before every launch)
+  unsigned long long pad0[15];
+  unsigned long long abort;  // a spin wait timed out: every CTA leaves (code of the first failure)
+  unsigned long long ar_seq; // single-GPU: all-reduces completed (mailbox parity); multi-GPU uses CommCtrl::ar_seq
+  unsigned long long pad1[14];
+  unsigned long long box[2][4]; // single-GPU all-reduce mailbox
+};
+
+constexpr int kMegaStamps = SB_TIMELINE_WORDS; // timeline record per iteration (include/stormb200.h: sb_solver_opts::h_timeline)
+
+struct MegaArgs {
+  OpDev op;
+  ApplyDist ad;                 // ad.n_pack > 0: distributed operator with neighbours (x_off unused here)
+  double *x, *r, *p, *v, *t, *rt; // CG: v = z; t, rt unused
+  int64_t off_p, off_r;         // byte offsets of p and r inside the slab (halo pushes)
+  SolverState* st;
+  double* hist;
+  double* trace;
+  RedPtrs red;
+  MegaCtrl* mc;
+  unsigned long long timeout_ns;
+  // optional timeline, CTA 0 only: per iteration kMegaStamps words:
+  //   [0] iteration start; [1+b] time after barrier b (b = 0..4); [6+b] ns CTA 0 waited for the last local arrival at
+  //   barrier b; [11+b] ns between CTA 0's mailbox send and the last peer's value (reducing barriers);
+  //   [16+k] longest halo-flag wait of any warp of this rank in apply k (k = 0, 1)
+  unsigned long long* timeline;
+  int32_t timeline_iters;
+};
+
+// ---- grid barrier ------------------------------------------------------------------------------------------
+struct MegaRun {
+  unsigned long long gen = 0;  // barriers passed in this launch
+  unsigned long long ar = 0;   // all-reduce sequence number of the next reducing barrier
+  unsigned long long seq = 0;  // distributed applies completed (CommCtrl::apply_seq)
+  uint32_t ringq = 0;          // stages that went through this warp's TMA ring
+  int32_t stamp_it = -1;       // timeline: iteration being stamped (-1: off)
+  int32_t stamp_b = 0;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Spin on `ready()`; gives up on timeout or when another CTA has given up. Returns false in that case.
+template<class Pred>
+__device__ __forceinline__ bool mega_spin(Pred ready, MegaCtrl* mc, unsigned long long timeout_ns, unsigned long long code) {
+  if (ready()) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  for (unsigned spins = 1;; ++spins) {
+    if (ready()) return true;
+    if ((spins & 127u) == 0) {
+      if (ld_relaxed_gpu(&mc->abort) != 0) return false;
+      if (globaltimer_ns() - t0 > timeout_ns) {
+        atomicCAS(&mc->abort, 0ull, code);
+        return false;
+      }
+    }
+  }
+}
+
+// Shared-memory scratch of a CTA.
+struct MegaShared {
+  SolverState st;                       // this CTA's copy of the solver state
+  double s_w[2][4][kMaxDots][kWarps];   // tile combine: warp sums of up to 4 tiles, double-buffered
+  double s_fin[kMaxDots][kWarps];       // final stage (CTA 0)
+  double s_all[kMaxRanks][4];           // mailbox values
+  double s_local[4];
+  int abort;
+};
+
+// All threads. Everything this CTA wrote is visible to every CTA that leaves the barrier.
+__device__ __forceinline__ void grid_arrive(const MegaArgs& a, MegaRun& run) {
+  fence_proxy_async_all(); // my generic-proxy stores vs. the bulk copies (async proxy) issued after the barrier
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&a.mc->arrive, 1ull);
+  }
+  run.gen++;
+}
+
+__device__ __forceinline__ void stamp(const MegaArgs& a, MegaRun& run, int slot, unsigned long long v) {
+  if (run.stamp_it >= 0) a.timeline[(int64_t) run.stamp_it * kMegaStamps + slot] = v;
+}
+
+// Plain grid barrier. Returns false when the kernel must be abandoned.
+__device__ __forceinline__ bool grid_barrier(const MegaArgs& a, MegaRun& run, MegaShared& sh) {
+  grid_arrive(a, run);
+  if (threadIdx.x == 0) {
+    const unsigned long long want = run.gen * gridDim.x, t0 = run.stamp_it >= 0 ? globaltimer_ns() : 0;
+    const unsigned long long* arrive = &a.mc->arrive;
+    if (!mega_spin([&] { return ld_acquire_gpu(arrive) >= want; }, a.mc, a.timeout_ns, 0xD000 + run.gen)) sh.abort = 1;
+    __threadfence(); // as cooperative_groups' grid sync: the fence (it invalidates this SM's L1) orders every thread
+                     // of the CTA, through the __syncthreads below, behind the arrivals just observed
+    if (run.stamp_it >= 0 && blockIdx.x == 0) {
+      const unsigned long long t1 = globaltimer_ns();
+      stamp(a, run, 6 + run.stamp_b, t1 - t0), stamp(a, run, 1 + run.stamp_b, t1);
+    }
+  }
+  run.stamp_b++;
+  __syncthreads();
+  fence_proxy_async_all();
+  return sh.abort == 0;
+}
+
+__device__ __forceinline__ unsigned long long* mega_box(const MegaArgs& a, int rank, unsigned long long par, int src, int d) {
+  if (a.ad.comm.world > 1) return &a.ad.comm.ctrl(rank)->ar_slot[par][src][d];
+  return &a.mc->box[par][d];
+}
+
+// Reducing barrier: grid barrier + final stage of SB_TREE + all-reduce over the ranks + the solver's scalar update
+// (`fin`) on this CTA's state copy. n_tiles: tiles whose partials the producers of this step have written.
+template<int ND, class Final>
+__device__ __forceinline__ bool reduce_barrier(const MegaArgs& a, MegaRun& run, MegaShared& sh, int64_t n_tiles, const Final& fin) {
+  const int world = a.ad.comm.world, me = a.ad.comm.rank;
+  const unsigned long long par = run.ar & 1ull;
+  grid_arrive(a, run);
+  if (blockIdx.x == 0) {
+    unsigned long long t0 = 0;
+    if (threadIdx.x == 0) {
+      const unsigned long long want = run.gen * gridDim.x;
+      const unsigned long long* arrive = &a.mc->arrive;
+      if (run.stamp_it >= 0) t0 = globaltimer_ns();
+      if (!mega_spin([&] { return ld_acquire_gpu(arrive) >= want; }, a.mc, a.timeout_ns, 0xD000 + run.gen)) sh.abort = 1;
+      if (run.stamp_it >= 0) stamp(a, run, 6 + run.stamp_b, globaltimer_ns() - t0);
+    }
+    __syncthreads();
+    // every local CTA has arrived, hence has read the mailbox of the previous all-reduce: make it empty again
+    // BEFORE my sums go out (a peer posts into it only after it has seen those)
+    if (threadIdx.x < world * 4) {
+      const int r = threadIdx.x >> 2, d = threadIdx.x & 3;
+      st_relaxed_sys(mega_box(a, me, par ^ 1ull, r, d), kArSentinel);
+    }
+    double sums[ND];
+    final_stage<ND>(n_tiles, a.red, sh.s_fin, sums);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int d = 0; d < ND; ++d) sh.s_local[d] = sums[d];
+      // release: the reset above (and everything the arrivals made visible) is performed before any rank / CTA can
+      // act on the values sent below
+      if (world > 1) __threadfence_system();
+      else __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x < world * ND) {
+      const int r = threadIdx.x / ND, d = threadIdx.x % ND;
+      st_relaxed_sys(mega_box(a, r, par, me, d), (unsigned long long) __double_as_longlong(sh.s_local[d]));
+    }
+  }
+  // every CTA: collect the rank sums
+  if (threadIdx.x < world * ND) {
+    const int r = threadIdx.x / ND, d = threadIdx.x % ND;
+    const unsigned long long* box = mega_box(a, me, par, r, d);
+    unsigned long long v = kArSentinel;
+    const unsigned long long t0 = (run.stamp_it >= 0 && blockIdx.x == 0) ? globaltimer_ns() : 0;
+    if (!mega_spin([&] { return (v = ld_relaxed_sys(box)) != kArSentinel; }, a.mc, a.timeout_ns, 0xC000 + r)) sh.abort = 1;
+    sh.s_all[r][d] = __longlong_as_double((long long) v);
+    if (run.stamp_it >= 0 && blockIdx.x == 0) atomicMax(&a.timeline[(int64_t) run.stamp_it * kMegaStamps + 11 + run.stamp_b], globaltimer_ns() - t0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && sh.abort == 0) {
+    double tot[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      double s = sh.s_all[0][d];
+      for (int r = 1; r < world; ++r) s = __dadd_rn(s, sh.s_all[r][d]);
+      tot[d] = s;
+    }
+    fin(tot);
+    if (run.stamp_it >= 0 && blockIdx.x == 0) stamp(a, run, 1 + run.stamp_b, globaltimer_ns());
+  }
+  run.ar++;
+  run.stamp_b++;
+  __threadfence(); // acquire side for the vector data of the other CTAs (and drops stale L1 lines)
+  __syncthreads();
+  fence_proxy_async_all();
+  return sh.abort == 0;
+}
+
+// ---- tile combine: SB_TREE's "8 warp sums left to right", one CTA barrier per 4 tiles -----------------------------
+template<int ND>
+struct TileCombine {
+  MegaShared& sh;
+  const RedPtrs& red;
+  int buf = 0, cnt = 0;
+  int64_t tile0 = 0;
+  __device__ __forceinline__ TileCombine(MegaShared& s, const RedPtrs& r) : sh(s), red(r) {}
+  __device__ __forceinline__ void flush() {
+    if (cnt == 0) return;
+    __syncthreads();
+    if (threadIdx.x < cnt * ND) {
+      const int c = threadIdx.x / ND, d = threadIdx.x % ND;
+      double s = sh.s_w[buf][c][d][0];
+#pragma unroll
+      for (int w = 1; w < kWarps; ++w) s = __dadd_rn(s, sh.s_w[buf][c][d][w]);
+      red.partials[(int64_t) d * red.cap_tiles + tile0 + (int64_t) c * gridDim.x] = s;
+    }
+    buf ^= 1, cnt = 0;
+  }
+  __device__ __forceinline__ void add(double (&acc)[ND], int64_t tile) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (cnt == 0) tile0 = tile;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const double v = warp_butterfly(acc[d]);
+      if (lane == 0) sh.s_w[buf][cnt][d][warp] = v;
+      acc[d] = 0.0;
+    }
+    if (++cnt == 4) flush();
+  }
+};
+
+// ---- element-wise step over this CTA's tiles -----------------------------------------------------------------------
+// Loads are issued two sub-iterations at a time (the persistent kernel keeps the register budget of three CTAs per SM).
+template<int ND, class Body>
+__device__ __forceinline__ void ew_phase(const Body& body, int64_t n, MegaShared& sh, const RedPtrs& red) {
+  const int64_t n_tiles = num_tiles(n);
+  TileCombine<(ND > 0 ? ND : 1)> tc(sh, red);
+  double acc[ND > 0 ? ND : 1];
+#pragma unroll
+  for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll
+    for (int h = 0; h < kSub; h += 2) {
+      typename Body::Regs r[2];
+      body.load(lane_elem(tile, h), r[0]);
+      body.load(lane_elem(tile, h + 1), r[1]);
+      body.run(lane_elem(tile, h), n, r[0], acc);
+      body.run(lane_elem(tile, h + 1), n, r[1], acc);
+    }
+    if constexpr (ND > 0) tc.add(acc, tile);
+  }
+  if constexpr (ND > 0) tc.flush();
+}
+
+// ---- operator-apply step -------------------------------------------------------------------------------------------
+// apply_kernel_tma's pipeline with the ring running across this CTA's tiles. `x_off`: byte offset of x in the slab.
+template<int W, int ND, bool RESID, class Epi>
+__device__ __forceinline__ void apply_phase(const MegaArgs& a, MegaRun& run, MegaShared& sh, const double* __restrict__ x,
+                                            double* __restrict__ y, int64_t x_off, const Epi& epi, unsigned char* smem,
+                                            uint64_t (*bars)[kStages], int apply_ordinal) {
+  using L = StageLayout<W>;
+  const OpDev& op = a.op;
+  const ApplyDist& ad = a.ad;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t G = gridDim.x, n_tiles = num_tiles(op.n);
+  const int64_t K = n_tiles > (int64_t) blockIdx.x ? (n_tiles - 1 - blockIdx.x) / G + 1 : 0; // my tiles
+  const int64_t Q = K * kSub;                                                                 // my warp's stages
+  unsigned char* wbase = smem + (size_t) warp * kStages * L::bytes;
+  const uint32_t q0 = run.ringq;
+  auto row_of = [&](int64_t q) { return ((int64_t) blockIdx.x + (q / kSub) * G) * kTile + warp * (kTile / kWarps) + (q % kSub) * 64; };
+  auto issue = [&](int64_t q, uint32_t dep) {
+    const int s = (int) ((q0 + q) % kStages);
+    uint64_t* bar = &bars[warp][s];
+    unsigned char* dst = wbase + s * L::bytes;
+    const int64_t r = row_of(q);
+    mbar_expect_tx(bar, (uint32_t) L::bytes);
+    bulk_g2s(dst, op.blk + (r >> 6) * (int64_t) L::slice + dep, L::slice, bar);
+    bulk_g2s(dst + L::xown, reinterpret_cast<const unsigned char*>(x + r) + dep, 512, bar);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kStages; ++j)
+      if (j < Q) issue(j, 0u);
+  }
+  const unsigned long long seq = run.seq + 1; // this apply's number (all CTAs of all ranks agree)
+  if (ad.n_pack > 0) {
+    // halo push: boundary values straight into the neighbours' halo tails over NVLink, one element per thread
+    CommCtrl* me = ad.comm.ctrl(ad.comm.rank);
+    const int64_t total = ad.halo.send_ptr[ad.halo.n_nbr];
+    const int64_t n_pack = (total + kThreads - 1) / kThreads < G ? (total + kThreads - 1) / kThreads : G;
+    if ((int64_t) blockIdx.x < n_pack) {
+      for (int64_t i = (int64_t) blockIdx.x * kThreads + threadIdx.x; i < total; i += n_pack * kThreads) {
+        int k = 0;
+#pragma unroll
+        for (int q = 1; q < kMaxRanks; ++q) k += (q < ad.halo.n_nbr && i >= ad.halo.send_ptr[q]) ? 1 : 0;
+        double* dst = reinterpret_cast<double*>(ad.comm.base[ad.halo.nbr_rank[k]] + x_off) + ad.halo.send_dst[k] + (i - ad.halo.send_ptr[k]);
+        *dst = __ldcg(x + ad.halo.send_idx[i]);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence_system(); // this CTA's peer stores are performed before the ticket is taken
+        const unsigned long long ticket = atomicAdd(&me->pack_ticket, 1ull);
+        if (ticket == (unsigned long long) n_pack - 1) {
+          me->pack_ticket = 0;
+          __threadfence_system();
+          for (int k = 0; k < ad.halo.n_nbr; ++k) st_relaxed_sys(&ad.comm.ctrl(ad.halo.nbr_rank[k])->halo_flag[ad.comm.rank], seq);
+        }
+      }
+    }
+  }
+  TileCombine<(ND > 0 ? ND : 1)> tc(sh, a.red);
+  double acc[ND > 0 ? ND : 1];
+#pragma unroll
+  for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+  bool halo_ready = ad.n_pack == 0;
+  for (int64_t k = 0; k < K; ++k) {
+    const int64_t tile = (int64_t) blockIdx.x + k * G;
+    const int64_t row0 = tile * kTile + warp * (kTile / kWarps);
+    typename Epi::Regs er[kSub];
+#pragma unroll
+    for (int j = 0; j < kSub; ++j) epi.load(row0 + j * 64 + 2 * lane, er[j]);
+    if (!halo_ready && tile >= ad.halo.first_boundary_tile) {
+      // boundary rows gather from the halo tail: wait until every neighbour's values of THIS apply have landed
+      CommCtrl* me = ad.comm.ctrl(ad.comm.rank);
+      if (lane < ad.halo.n_nbr) {
+        const unsigned long long* flag = &me->halo_flag[ad.halo.nbr_rank[lane]];
+        const unsigned long long t0 = run.stamp_it >= 0 ? globaltimer_ns() : 0;
+        if (!mega_spin([&] { return ld_acquire_sys(flag) >= seq; }, a.mc, a.timeout_ns, 0xB000 + ad.halo.nbr_rank[lane])) sh.abort = 1;
+        if (run.stamp_it >= 0) atomicMax(&a.timeline[(int64_t) run.stamp_it * kMegaStamps + 16 + apply_ordinal], globaltimer_ns() - t0);
+      }
+      __syncwarp();
+      halo_ready = true;
+    }
+#pragma unroll
+    for (int j = 0; j < kSub; ++j) {
+      const int64_t q = k * kSub + j;
+      const int s = (int) ((q0 + q) % kStages);
+      mbar_wait(&bars[warp][s], (uint32_t) (((q0 + q) / kStages) & 1));
+      const unsigned char* src = wbase + s * L::bytes;
+      int2 c[W];
+      double2 cf[W];
+#pragma unroll
+      for (int e = 0; e < W; ++e) {
+        c[e] = reinterpret_cast<const int2*>(src + L::col + e * 256)[lane];
+        cf[e] = reinterpret_cast<const double2*>(src + L::coef + e * 512)[lane];
+      }
+      const double2 dg = reinterpret_cast<const double2*>(src + L::diag)[lane];
+      const double2 xo = reinterpret_cast<const double2*>(src + L::xown)[lane];
+      // generic-proxy loads vs. the async-proxy refill of this slot: see apply_kernel_tma (sb_op.cuh)
+      uint32_t fold = 0;
+      {
+        auto mix = [&](double v) {
+          const long long b = __double_as_longlong(v);
+          fold ^= (uint32_t) b ^ (uint32_t) (b >> 32);
+        };
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+          fold ^= (uint32_t) c[e].x ^ (uint32_t) c[e].y;
+          mix(cf[e].x), mix(cf[e].y);
+        }
+        mix(dg.x), mix(dg.y), mix(xo.x), mix(xo.y);
+      }
+      const uint32_t dep = fold & (uint32_t) op.zero;
+      __syncwarp();
+      if (lane == 0 && q + kStages < Q) issue(q + kStages, dep);
+
+      double g0[W], g1[W];
+#pragma unroll
+      for (int e = 0; e < W; ++e) {
+        g0[e] = (c[e].x >= 0) ? __ldca(x + c[e].x) : 0.0;
+        g1[e] = (c[e].y >= 0) ? __ldca(x + c[e].y) : 0.0;
+      }
+      double u0 = __dmul_rn(dg.x, xo.x), u1 = __dmul_rn(dg.y, xo.y);
+#pragma unroll
+      for (int e = 0; e < W; ++e) {
+        const double t0 = __dadd_rn(u0, __dmul_rn(cf[e].x, g0[e]));
+        const double t1 = __dadd_rn(u1, __dmul_rn(cf[e].y, g1[e]));
+        u0 = (c[e].x >= 0) ? t0 : u0;
+        u1 = (c[e].y >= 0) ? t1 : u1;
+      }
+      double2 out = make_double2(u0, u1);
+      const int64_t e0 = row0 + j * 64 + 2 * lane;
+      if constexpr (RESID) {
+        out.x = __dsub_rn(er[j].b.x, out.x);
+        out.y = __dsub_rn(er[j].b.y, out.y);
+        acc_pair(acc[0], e0, op.n, __dmul_rn(out.x, out.x), __dmul_rn(out.y, out.y));
+      }
+      st2(y, e0, out);
+      if constexpr (!RESID) epi.run(e0, op.n, xo, out, er[j], acc);
+    }
+    if constexpr (ND > 0) tc.add(acc, tile);
+  }
+  if constexpr (ND > 0) tc.flush();
+  run.ringq = q0 + (uint32_t) Q;
+  run.seq = seq;
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------------
+// Resident CTAs per SM the kernel is compiled for: the TMA ring (16 stages of 768 W + 1024 bytes per CTA) allows
+// three CTAs per SM up to W = 4, two up to W = 7, one beyond; the register budget follows.
+constexpr int mega_ctas_per_sm(int W) { return W <= 4 ? 3 : (W <= 7 ? 2 : 1); }
+
+template<int KIND, int W>
+__global__ void __launch_bounds__(kThreads, mega_ctas_per_sm(W)) krylov_persistent_kernel(const __grid_constant__ MegaArgs a) {
+  extern __shared__ __align__(128) unsigned char sb_smem[];
+  __shared__ __align__(8) uint64_t bars[kWarps][kStages];
+  __shared__ MegaShared sh;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool dist = a.ad.comm.world > 1;
+  CommCtrl* ctl = dist ? a.ad.comm.ctrl(a.ad.comm.rank) : nullptr;
+  if (threadIdx.x == 0) {
+    sh.st = *a.st;
+    sh.abort = 0;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async_all();
+  }
+  MegaRun run;
+  run.ar = dist ? ctl->ar_seq : a.mc->ar_seq;
+  run.seq = dist ? ctl->apply_seq : 0;
+  __syncthreads();
+  SolverState* S = &sh.st;
+  const Recorder rec{S, blockIdx.x == 0 ? a.hist : nullptr, blockIdx.x == 0 ? a.trace : nullptr};
+  const int64_t n = a.op.n, n_tiles = num_tiles(n);
+  bool ok = true;
+  long long it = 0;
+  while (ok && !S->done) {
+    run.stamp_it = (a.timeline != nullptr && blockIdx.x == 0 && it < a.timeline_iters) ? (int32_t) it : -1;
+    if (a.timeline != nullptr && blockIdx.x != 0 && it < a.timeline_iters) run.stamp_it = (int32_t) it; // halo waits of all CTAs
+    run.stamp_b = 0;
+    if (threadIdx.x == 0 && blockIdx.x == 0) stamp(a, run, 0, globaltimer_ns());
+    if constexpr (KIND == (int) Kind::BiCgStab) {
+      ew_phase<0>(BiDirectionBody{S, a.p, a.r, a.v}, n, sh, a.red);
+      if (!(ok = grid_barrier(a, run, sh))) break;
+      apply_phase<W, 1, false>(a, run, sh, a.p, a.v, a.off_p, EpiUY{a.rt}, sb_smem, bars, 0);
+      if (!(ok = reduce_barrier<1>(a, run, sh, n_tiles, BiAlphaFinal{rec}))) break;
+      ew_phase<0>(BiHalfBody{S, a.r, a.v}, n, sh, a.red);
+      if (!(ok = grid_barrier(a, run, sh))) break;
+      apply_phase<W, 2, false>(a, run, sh, a.r, a.t, a.off_r, EpiYYandYX{}, sb_smem, bars, 1);
+      if (!(ok = reduce_barrier<2>(a, run, sh, n_tiles, BiOmegaFinal{rec}))) break;
+      ew_phase<2>(BiEndBody{S, a.x, a.r, a.p, a.t, a.rt}, n, sh, a.red);
+      if (!(ok = reduce_barrier<2>(a, run, sh, n_tiles, BiEndFinal{rec}))) break;
+    } else {
+      apply_phase<W, 1, false>(a, run, sh, a.p, a.v, a.off_p, EpiXY{}, sb_smem, bars, 0);
+      if (!(ok = reduce_barrier<1>(a, run, sh, n_tiles, CgAlphaFinal{rec}))) break;
+      ew_phase<1>(CgUpdateBody{S, a.x, a.r, a.p, a.v}, n, sh, a.red);
+      if (!(ok = reduce_barrier<1>(a, run, sh, n_tiles, CgBetaFinal{rec}))) break;
+      ew_phase<0>(CgDirectionBody{S, a.p, a.r}, n, sh, a.red);
+      if (!(ok = grid_barrier(a, run, sh))) break;
+    }
+    ++it;
+  }
+  // Every CTA has read the last mailbox before CTA 0 empties it (the next kernel expects empty mailboxes).
+  run.stamp_it = -1;
+  if (ok) ok = grid_barrier(a, run, sh);
+  if (blockIdx.x == 0 && ok) {
+    if (run.ar > 0 && threadIdx.x < a.ad.comm.world * 4) {
+      const int r = threadIdx.x >> 2, d = threadIdx.x & 3;
+      st_relaxed_sys(mega_box(a, a.ad.comm.rank, (run.ar - 1) & 1ull, r, d), kArSentinel);
+    }
+    if (threadIdx.x == 0) {
+      *a.st = *S;
+      if (dist) ctl->ar_seq = run.ar, ctl->apply_seq = run.seq;
+      else a.mc->ar_seq = run.ar;
+    }
+  }
+  if (!ok && blockIdx.x == 0 && threadIdx.x == 0 && dist) comm_fail(ctl, ld_relaxed_gpu(&a.mc->abort));
+}
+
+} // namespace sb

@@ -41,7 +41,7 @@ __device__ __forceinline__ void apply_halo_wait(const ApplyDist& ad, int64_t til
     CommCtrl* me = ad.comm.ctrl(ad.comm.rank);
     if (threadIdx.x < ad.halo.n_nbr)
       wait_flag_ge(&me->halo_flag[ad.halo.nbr_rank[threadIdx.x]], ld_acquire_sys(&me->apply_seq) + 1, me,
-                   0xB000 + threadIdx.x);
+                   0xB000 + ad.halo.nbr_rank[threadIdx.x], ad.comm.timeout_ns);
     __syncthreads();
   }
 }
@@ -403,8 +403,11 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
       const int64_t total = op->halo.send_ptr[op->halo.n_nbr];
       ad.n_pack = (int32_t) std::max<int64_t>(1, std::min<int64_t>(64, (total + 2 * kThreads - 1) / (2 * kThreads)));
       ad.coherent_gather = 1;
-      bump = ctx->comm.ctrl(ctx->comm.rank);
     }
+    // The apply sequence number counts EVERY apply of a distributed operator on every rank, whether this rank has
+    // neighbours in this operator or not: the flags of different operators (other partitions, a rank without
+    // neighbours) are compared against the same counter, which therefore has to advance in lockstep on all ranks.
+    if (ctx->comm.mode == SB_COMM_P2P && !(ctx->debug & 2)) bump = ctx->comm.ctrl(ctx->comm.rank);
   }
   const unsigned grid = (unsigned) (num_tiles(d.n) + ad.n_pack);
 #define SB_LAUNCH(FORM, W) \

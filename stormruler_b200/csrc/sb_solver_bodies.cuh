@@ -1,0 +1,267 @@
+// sb_solver_bodies.cuh -- the device-side pieces of the fused CG / BiCGStab solvers: the solver state, the scalar
+// updates that follow each reduction ("Final" functors) and the element-wise update bodies. Shared by the two
+// schedules that run them: one kernel per step (sb_solvers.cu) and the persistent whole-solve kernel (sb_mega.cuh).
+//
+// Reference: CgSolver (source/Storm/Solvers/SolverCg.hpp:54-126), BiCgStabSolver (SolverBiCgStab.hpp:59-165), driven
+// as IterativeSolver::solve (Solver.hpp:116-147), no preconditioner. Every statement keeps the reference's
+// per-element operation order.
+#pragma once
+
+#include "sb_op.cuh"
+
+struct SolverState {
+  double gamma, alpha, beta, rho, omega;
+  double initial_err, abs_err, rel_err;
+  double abs_tol, rel_tol;
+  long long iteration, max_iter;
+  long long n_hist, n_trace, hist_cap, trace_cap;
+  int done, converged;
+};
+
+namespace sb {
+
+__device__ __forceinline__ double safe_divide(double x, double y) {
+  // Crow/MathUtils.hpp:49-52
+  return (y == 0.0) ? 0.0 : __ddiv_rn(x, y);
+}
+
+struct Recorder {
+  SolverState* st;
+  double* hist;
+  double* trace;
+  __device__ void push_trace(double v) const {
+    if (trace != nullptr && st->n_trace < st->trace_cap) trace[st->n_trace] = v;
+    st->n_trace++;
+  }
+  __device__ void push_hist(double v) const {
+    if (hist != nullptr && st->n_hist < st->hist_cap) hist[st->n_hist] = v;
+    st->n_hist++;
+  }
+  // Solver.hpp:124-128: early exit when the initial residual is already below abs_tol.
+  __device__ void init_error(double err) const {
+    st->initial_err = err, st->abs_err = err, st->rel_err = 0.0;
+    st->iteration = 0;
+    push_hist(err);
+    if (st->abs_tol > 0.0 && err < st->abs_tol) st->converged = 1, st->done = 1;
+    if (st->max_iter <= 0) st->done = 1;
+  }
+  // Solver.hpp:132-140: one pass of the iteration loop after iterate() returned `err`.
+  __device__ void iteration_error(double err) const {
+    st->abs_err = err;
+    st->rel_err = __ddiv_rn(err, st->initial_err); // no zero guard
+    push_hist(err);
+    bool conv = (st->abs_tol > 0.0) && (err < st->abs_tol);
+    conv |= (st->rel_tol > 0.0) && (st->rel_err < st->rel_tol);
+    st->iteration++;
+    if (conv) st->converged = 1;
+    if (conv || st->iteration >= st->max_iter) st->done = 1;
+  }
+};
+
+// ---- CG -------------------------------------------------------------------------------------------
+struct CgInitFinal { // after r = b - A x fused with <r,r>   (SolverCg.hpp:73,80,83)
+  Recorder rec;
+  __device__ void operator()(const double* s) const {
+    rec.st->gamma = s[0];
+    rec.push_trace(s[0]);
+    rec.init_error(sqrt(s[0]));
+  }
+};
+struct CgAlphaFinal { // after z = A p fused with <p,z>       (:95-96)
+  Recorder rec;
+  __device__ void operator()(const double* s) const {
+    rec.push_trace(s[0]);
+    rec.st->alpha = safe_divide(rec.st->gamma, s[0]);
+  }
+};
+struct CgBetaFinal { // after the x/r update fused with <r,r>  (:109,114,121,124)
+  Recorder rec;
+  __device__ void operator()(const double* s) const {
+    const double gamma_bar = rec.st->gamma;
+    rec.st->gamma = s[0];
+    rec.push_trace(s[0]);
+    rec.st->beta = safe_divide(s[0], gamma_bar);
+    rec.iteration_error(sqrt(s[0]));
+  }
+};
+
+struct CopyBody { // p <- r
+  double* dst;
+  const double* src;
+  struct Regs {
+    double2 v;
+  };
+  __device__ __forceinline__ void load(int64_t e0, Regs& r) const { r.v = ld2(src, e0); }
+  __device__ __forceinline__ void run(int64_t e0, int64_t, Regs& r, double (&)[1]) const { st2(dst, e0, r.v); }
+};
+
+struct CgUpdateBody { // x += alpha*p ; r -= alpha*z ; acc += r.r     (:97-98,114)
+  const SolverState* st;
+  double *x, *r;
+  const double *p, *z;
+  struct Regs {
+    double2 x, r, p, z;
+  };
+  __device__ __forceinline__ void load(int64_t e0, Regs& g) const {
+    g.x = ld2(x, e0), g.p = ld2(p, e0), g.r = ld2(r, e0), g.z = ld2(z, e0);
+  }
+  __device__ __forceinline__ void run(int64_t e0, int64_t n, Regs& g, double (&acc)[1]) const {
+    const double alpha = st->alpha;
+    double2 xn, rn;
+    xn.x = __dadd_rn(g.x.x, __dmul_rn(alpha, g.p.x));
+    xn.y = __dadd_rn(g.x.y, __dmul_rn(alpha, g.p.y));
+    rn.x = __dsub_rn(g.r.x, __dmul_rn(alpha, g.z.x));
+    rn.y = __dsub_rn(g.r.y, __dmul_rn(alpha, g.z.y));
+    st2(x, e0, xn);
+    st2(r, e0, rn);
+    acc_pair(acc[0], e0, n, __dmul_rn(rn.x, rn.x), __dmul_rn(rn.y, rn.y));
+  }
+};
+
+struct CgDirectionBody { // p <- r + beta*p     (:122)
+  const SolverState* st;
+  double* p;
+  const double* r;
+  struct Regs {
+    double2 p, r;
+  };
+  __device__ __forceinline__ void load(int64_t e0, Regs& g) const { g.p = ld2(p, e0), g.r = ld2(r, e0); }
+  __device__ __forceinline__ void run(int64_t e0, int64_t, Regs& g, double (&)[1]) const {
+    const double beta = st->beta;
+    double2 pn;
+    pn.x = __dadd_rn(g.r.x, __dmul_rn(beta, g.p.x));
+    pn.y = __dadd_rn(g.r.y, __dmul_rn(beta, g.p.y));
+    st2(p, e0, pn);
+  }
+};
+
+// ---- BiCGStab -------------------------------------------------------------------------------------
+struct BiInitFinal { // r = b - A x, r~ = r, rho = <r~,r>      (SolverBiCgStab.hpp:83,88-91)
+  Recorder rec;
+  __device__ void operator()(const double* s) const {
+    rec.st->rho = s[0];
+    rec.push_trace(s[0]);
+    rec.init_error(sqrt(s[0]));
+  }
+};
+struct BiAlphaFinal { // after v = A p fused with <r~,v>        (:137,139)
+  Recorder rec;
+  __device__ void operator()(const double* s) const {
+    rec.push_trace(s[0]);
+    rec.st->alpha = safe_divide(rec.st->rho, s[0]);
+  }
+};
+struct BiOmegaFinal { // after t = A r fused with <t,t>, <t,r>  (:158-160)
+  Recorder rec;
+  __device__ void operator()(const double* s) const {
+    // g++ evaluates safe_divide's arguments right to left: <t,t> is traced before <t,r>.
+    rec.push_trace(s[0]);
+    rec.push_trace(s[1]);
+    rec.st->omega = safe_divide(s[1], s[0]);
+  }
+};
+struct BiEndFinal { // after the final update fused with <r,r> and <r~,r>   (:164 and next :115-117)
+  Recorder rec;
+  __device__ void operator()(const double* s) const {
+    const double nrm = sqrt(s[0]);
+    rec.push_trace(nrm);
+    rec.iteration_error(nrm);
+    if (!rec.st->done) {
+      // head of the next iteration: rho_bar <- rho, rho <- <r~,r>, beta <- (alpha*rho)/(omega*rho_bar)
+      const double rho_bar = rec.st->rho;
+      rec.st->rho = s[1];
+      rec.push_trace(s[1]);
+      rec.st->beta = safe_divide(__dmul_rn(rec.st->alpha, s[1]), __dmul_rn(rec.st->omega, rho_bar));
+    }
+  }
+};
+
+struct BiInitBody { // r~ <- r after the fused residual (r already stored by the apply kernel)
+  double* rt;
+  const double* r;
+  struct Regs {
+    double2 v;
+  };
+  __device__ __forceinline__ void load(int64_t e0, Regs& g) const { g.v = ld2(r, e0); }
+  __device__ __forceinline__ void run(int64_t e0, int64_t, Regs& g, double (&)[1]) const { st2(rt, e0, g.v); }
+};
+
+struct BiDirectionBody { // iteration 0: p <- r ; else p <- r + beta*(p - omega*v)   (:111-119)
+  const SolverState* st;
+  double* p;
+  const double *r, *v;
+  struct Regs {
+    double2 p, r, v;
+  };
+  __device__ __forceinline__ void load(int64_t e0, Regs& g) const {
+    g.r = ld2(r, e0);
+    if (st->iteration != 0) g.p = ld2(p, e0), g.v = ld2(v, e0);
+  }
+  __device__ __forceinline__ void run(int64_t e0, int64_t, Regs& g, double (&)[1]) const {
+    double2 pn = g.r;
+    if (st->iteration != 0) {
+      const double beta = st->beta, omega = st->omega;
+      pn.x = __dadd_rn(g.r.x, __dmul_rn(beta, __dsub_rn(g.p.x, __dmul_rn(omega, g.v.x))));
+      pn.y = __dadd_rn(g.r.y, __dmul_rn(beta, __dsub_rn(g.p.y, __dmul_rn(omega, g.v.y))));
+    }
+    st2(p, e0, pn);
+  }
+};
+
+struct BiHalfBody { // r -= alpha*v     (:141); x += alpha*p is deferred to BiEndBody
+  const SolverState* st;
+  double* r;
+  const double* v;
+  struct Regs {
+    double2 r, v;
+  };
+  __device__ __forceinline__ void load(int64_t e0, Regs& g) const { g.r = ld2(r, e0), g.v = ld2(v, e0); }
+  __device__ __forceinline__ void run(int64_t e0, int64_t, Regs& g, double (&)[1]) const {
+    const double alpha = st->alpha;
+    double2 rn;
+    rn.x = __dsub_rn(g.r.x, __dmul_rn(alpha, g.v.x));
+    rn.y = __dsub_rn(g.r.y, __dmul_rn(alpha, g.v.y));
+    st2(r, e0, rn);
+  }
+};
+
+struct BiEndBody { // x = (x + alpha*p) + omega*r ; r -= omega*t ; acc0 += r.r ; acc1 += r~.r   (:140,161-164)
+  const SolverState* st;
+  double *x, *r;
+  const double *p, *t, *rt;
+  struct Regs {
+    double2 x, r, p, t, rt;
+  };
+  __device__ __forceinline__ void load(int64_t e0, Regs& g) const {
+    g.x = ld2(x, e0), g.p = ld2(p, e0), g.r = ld2(r, e0), g.t = ld2(t, e0), g.rt = ld2(rt, e0);
+  }
+  __device__ __forceinline__ void run(int64_t e0, int64_t n, Regs& g, double (&acc)[2]) const {
+    const double alpha = st->alpha, omega = st->omega;
+    double2 xn, rn;
+    xn.x = __dadd_rn(__dadd_rn(g.x.x, __dmul_rn(alpha, g.p.x)), __dmul_rn(omega, g.r.x));
+    xn.y = __dadd_rn(__dadd_rn(g.x.y, __dmul_rn(alpha, g.p.y)), __dmul_rn(omega, g.r.y));
+    rn.x = __dsub_rn(g.r.x, __dmul_rn(omega, g.t.x));
+    rn.y = __dsub_rn(g.r.y, __dmul_rn(omega, g.t.y));
+    st2(x, e0, xn);
+    st2(r, e0, rn);
+    acc_pair(acc[0], e0, n, __dmul_rn(rn.x, rn.x), __dmul_rn(rn.y, rn.y));
+    acc_pair(acc[1], e0, n, __dmul_rn(g.rt.x, rn.x), __dmul_rn(g.rt.y, rn.y));
+  }
+};
+
+enum class Kind { Cg, BiCgStab };
+
+// The persistent whole-solve schedule (sb_mega.cu): the iteration loop of an initialised solve in ONE cooperative
+// launch. The vectors are the solver's workspaces, `st` the device solver state the initialisation kernels have filled.
+struct MegaLaunch {
+  Kind kind;
+  double *x, *r, *p, *v, *t, *rt; // CG: v = z; t, rt unused
+  SolverState* st;
+  double* hist;
+  double* trace;
+  int32_t timeline_iters; // > 0: record the in-kernel timeline of the first iterations into ctx->d_timeline
+};
+bool mega_supported(const sb_ctx* ctx, const sb_op* op);
+int launch_mega(sb_ctx* ctx, const sb_op* op, const MegaLaunch& L);
+
+} // namespace sb

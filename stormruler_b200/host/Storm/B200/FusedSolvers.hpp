@@ -38,7 +38,8 @@ public:
   std::string name;
 
   // additions
-  bool use_graph{true};             ///< replay one captured CUDA graph per iteration
+  int schedule{SB_SCHEDULE_AUTO};   ///< SB_SCHEDULE_*: persistent whole-solve kernel (default where available) or stepwise
+  bool use_graph{true};             ///< stepwise schedule: replay one captured CUDA graph per iteration
   int check_every{0};               ///< host polls the device stop flag every this many iterations (0 = 32)
   bool record_history{false};       ///< keep residual_history / reduction_trace
   std::vector<double> residual_history; ///< [0] initial, [k] after iteration k
@@ -55,8 +56,12 @@ public:
       throw std::runtime_error("stormb200: fused solvers do not take a preconditioner; "
                                "use the generic solver templates");
     }
+    if (x.size() != b.size()) { // the C ABI checks both against the operator's rows and their padded capacity
+      throw std::runtime_error("stormb200: fused solve: x and b must have the same number of rows");
+    }
     flush(); // queued statements (statement grouping) may produce x or b
     sb_solver_opts opts{};
+    opts.schedule = schedule;
     opts.num_iterations = (int64_t) num_iterations;
     opts.abs_tol = absolute_error_tolerance, opts.rel_tol = relative_error_tolerance;
     opts.check_every = check_every, opts.use_graph = use_graph ? 1 : 0, opts.profile = 0;

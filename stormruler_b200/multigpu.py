@@ -270,11 +270,13 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
     ranks. Every rank times exactly K iterations on its own stream with CUDA events (the fused solver's
     iter_ms), bracketed by barrier + synchronize; rank 0 reports K / max over ranks."""
     import torch
+    import bench as bench_mod   # phase_times, SLOTS, KERNEL_NAME (bench.py is the entry script: already imported)
     world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
     dist = init_process_group(cuda=True)
     local_rank = local_device()
     mode = capi.COMM_NCCL if args.comm == "nccl" else capi.COMM_P2P
     method = capi.PART_SLAB if args.partition == "slab" else capi.PART_METIS
+    schedule = {"auto": capi.SCHEDULE_AUTO, "stepwise": capi.SCHEDULE_STEPWISE, "persistent": capi.SCHEDULE_PERSISTENT}[args.schedule]
     mesh, x_star = build_problem(args)
     part = partition_mesh(mesh, world, method)
     loc = part.local(rank)
@@ -301,11 +303,22 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
         assert s.iteration == iters, (s.iteration, iters)
         return s, x
 
-    solve(max(args.warmup, 3), use_graph=True)
-    s, x = solve(args.steps, use_graph=True)
+    solve(max(args.warmup, 3), use_graph=True, schedule=schedule)
+    s, x = solve(args.steps, use_graph=True, schedule=schedule)
     iter_ms = max_over_ranks(s.iter_ms)
     launches = int(sum_over_ranks(s.launches))
     value = args.steps / (iter_ms * 1e-3)
+    persistent = s.schedule_used == capi.SCHEDULE_PERSISTENT
+    phases = None
+    if persistent:   # the kernel's own timeline, per rank (rank 0's is printed; the waits are maxima over the ranks)
+        k = min(args.steps, 64)
+        st, _ = solve(k, schedule=schedule, timeline_iters=k)
+        phases = bench_mod.phase_times(st.timeline, args.solver)
+        if phases is not None:
+            for key in ("us_barrier_wait_for_last_cta", "us_allreduce_wait"):
+                phases[key + "_max_over_ranks"] = {nm: max_over_ranks(v) for nm, v in phases[key].items()}
+            phases["us_halo_wait_max_over_ranks"] = [max_over_ranks(v) for v in phases["us_halo_wait_max"]]
+            phases["us_per_iteration_max_over_ranks"] = max_over_ranks(phases["us_per_iteration"])
     sp, _ = solve(args.steps, profile=True)
     kms = [max_over_ranks(v) for v in sp.kernel_ms]
     xg = gather_global(loc, x.numpy(), mesh.n_cells)
@@ -315,12 +328,13 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
     hx = torch.zeros(n, dtype=torch.float64).pin_memory()
     hb = torch.from_numpy(b.numpy()).pin_memory()
     hxn, hbn = hx.numpy(), hb.numpy()
-    solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=3, abs_tol=0.0, rel_tol=0.0, use_graph=True)
+    solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=3, abs_tol=0.0, rel_tol=0.0, use_graph=True, schedule=schedule)
     hxn[:] = 0.0
     ctx.sync()
     dist.barrier()
     t = time.perf_counter()
-    rep = solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=args.steps, abs_tol=0.0, rel_tol=0.0, use_graph=True)
+    rep = solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=args.steps, abs_tol=0.0, rel_tol=0.0, use_graph=True,
+                     schedule=schedule)
     dist.barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t)
     assert rep.iterations == args.steps
@@ -331,30 +345,37 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
     comm_err = ctx.status()
     if rank == 0:
         peak, peak_src = peaks()
-        slots = {"bicgstab": ["direction", "apply+dot", "half_update", "apply+2dots", "final_update+2dots"],
-                 "cg": ["apply+dot", "update+dot", "direction"]}[args.solver]
+        slots = bench_mod.SLOTS[args.solver]
         apply_slots = [k for k, nm in enumerate(slots) if nm.startswith("apply")]
         apply_ms = sum(kms[k] for k in apply_slots) / (len(apply_slots) * args.steps)
-        achieved = alg_apply / (apply_ms * 1e-3) / 1e9       # all ranks' bytes / slowest rank's launch time
         alg_iter = applies_per_it * alg_apply + passes_per_it * 8 * n_glob
+        alg_launch = alg_iter * args.steps if persistent else alg_apply
+        launch_ms = iter_ms if persistent else apply_ms
+        achieved = alg_launch / (launch_ms * 1e-3) / 1e9       # all ranks' bytes / slowest rank's launch time
         cfg = workload_config(args, mesh)
         cfg.update({"partition": args.partition, "comm": args.comm, "edge_cut": int(pinfo.edge_cut),
-                    "cells_per_rank": [int(pinfo.min_owned), int(pinfo.max_owned)], "max_halo": int(pinfo.max_halo)})
+                    "cells_per_rank": [int(pinfo.min_owned), int(pinfo.max_owned)], "max_halo": int(pinfo.max_halo),
+                    "schedule": "persistent" if persistent else "stepwise"})
         line = {
             "metric": "krylov_iterations_per_sec", "value": value, "unit": "it/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": iter_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": cfg,
-            "roofline": {"bound": "hbm", "kernel": "operator apply + fused dot(s) incl. halo pack/wait (all ranks)",
+            "roofline": {"bound": "hbm",
+                         "kernel": (bench_mod.KERNEL_NAME[args.solver] + ", halo push + all-reduce inside, all ranks") if persistent
+                         else "operator apply + fused dot(s) incl. halo pack/wait (all ranks)",
                          "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
-                         "algorithmic_bytes_per_launch": alg_apply, "avg_launch_ms": apply_ms,
-                         "share_of_step": sum(kms[k] for k in apply_slots) / max(sum(kms[:len(slots)]), 1e-12)},
+                         "algorithmic_bytes_per_launch": int(alg_launch), "avg_launch_ms": launch_ms,
+                         "share_of_step": 1.0 if persistent else
+                         sum(kms[k] for k in apply_slots) / max(sum(kms[:len(slots)]), 1e-12)},
             "iteration_roofline": {"algorithmic_bytes_per_iteration": int(alg_iter),
                                    "achieved_gbs": alg_iter * value / 1e9,
                                    "frac_of_measured_peak": alg_iter * value / 1e9 / (peak * world),
                                    "frac_of_nominal_8TBs": alg_iter * value / (8e12 * world)},
-            "kernel_ms_per_iteration": {nm: kms[k] / args.steps for k, nm in enumerate(slots)},
+            "phases": phases,
+            "stepwise": {"kernel_ms_per_iteration": {nm: kms[k] / args.steps for k, nm in enumerate(slots)},
+                         "apply_avg_launch_ms": apply_ms},
             "applies_per_sec": applies_per_it * value,
             "cpu_baseline": None,
             "e2e": {"value": args.steps / e2e_s, "unit": "it/s", "h2d_bytes_per_step": 16 * n_glob / args.steps,

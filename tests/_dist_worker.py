@@ -216,20 +216,35 @@ def run_gpu(dist, rank, world, mode_name):
             # distributed dot
             d = ctx.dot(x, y)
             assert d == orc.dot(xg[order], want, orc.RED_TREE_SEG), "rank-ordered dot differs"
-            if form != sb.FORM_FAITHFUL:
-                del op, x, y, x2
-                continue
+            # faithful form: the stepwise schedule (with and without graph replay); coefficient form: the stepwise one
+            # and the persistent whole-solve kernel (in-kernel halo push, grid barriers, mailbox all-reduce; P2P only),
+            # alternating on one context so that the sequence numbers of the two protocols have to stay in step
+            oracle_op = cpu if form == sb.FORM_FAITHFUL else orc.RowsOp(n, *cpu.rows_coef())
+            if form == sb.FORM_FAITHFUL:
+                variants = [(capi.SCHEDULE_AUTO, False), (capi.SCHEDULE_AUTO, True)]
+            elif mode == capi.COMM_P2P:
+                variants = [(capi.SCHEDULE_PERSISTENT, False), (capi.SCHEDULE_STEPWISE, True),
+                            (capi.SCHEDULE_PERSISTENT, False), (capi.SCHEDULE_AUTO, False)]
+            else:
+                variants = [(capi.SCHEDULE_STEPWISE, True)]
             for name, Solver in (("cg", sb.CgSolver), ("bicgstab", sb.BiCgStabSolver)):
-                for use_graph in (False, True):
+                w = orc.solve(name, oracle_op, bg[order], num_iterations=60, abs_tol=0.0, rel_tol=1e-9, mode=orc.RED_TREE_SEG)
+                for schedule, use_graph in variants:
                     s = Solver(num_iterations=60, absolute_error_tolerance=0.0, relative_error_tolerance=1e-9,
-                               use_graph=use_graph, check_every=7)
+                               use_graph=use_graph, check_every=7, schedule=schedule)
                     xs = ctx.zeros(loc.n_owned)
                     conv = s.solve(xs, ctx.vector(bg[loc.owned_global]), op)
-                    w = orc.solve(name, cpu, bg[order], num_iterations=60, abs_tol=0.0, rel_tol=1e-9, mode=orc.RED_TREE_SEG)
-                    assert conv == w.converged and s.iteration == w.iterations, (name, conv, s.iteration, w.iterations)
-                    assert np.array_equal(s.history, w.hist), f"{name}: residual history differs from the oracle"
-                    assert np.array_equal(mg.gather_global(loc, xs.numpy(), n)[order], w.x), f"{name}: solution differs"
+                    tag = f"{name} form {form} schedule {schedule}->{s.schedule_used}"
+                    if form == sb.FORM_COEF and mode == capi.COMM_P2P and schedule != capi.SCHEDULE_STEPWISE:
+                        assert s.schedule_used == capi.SCHEDULE_PERSISTENT, tag
+                    assert conv == w.converged and s.iteration == w.iterations, (tag, conv, s.iteration, w.iterations)
+                    assert np.array_equal(s.history, w.hist), f"{tag}: residual history differs from the oracle"
+                    assert np.array_equal(mg.gather_global(loc, xs.numpy(), n)[order], w.x), f"{tag}: solution differs"
                     del xs
+                # a plain apply between two solves: the ack / sequence protocol of the stepwise kernels picks up where
+                # the persistent kernel left the counters
+                op.mul(y, x)
+                assert np.array_equal(mg.gather_global(loc, y.numpy(), n)[order], want), "apply after the solves differs"
             del op, x, y, x2
         # non-symmetric rows + the fused GMRES over the distributed operator (config 3)
         fu, bu = mesh.face_flux((1.0, 0.5, 0.25))

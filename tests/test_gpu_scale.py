@@ -59,9 +59,10 @@ def test_million_cell_solvers_bit_identical_to_oracle(any_ctx, mesh_1m, solver):
         b = b_dev.numpy()
         assert np.array_equal(b, oracle_op.apply(x_star)), "apply differs from the oracle at 1.2 M cells"
         want = orc.solve(solver, oracle_op, b, num_iterations=iters, abs_tol=0.0, rel_tol=0.0, mode=orc.RED_TREE)
-        for use_graph in (False, True, True):
+        # stepwise without / with graph replay, then (coefficient form) the persistent whole-solve kernel, twice
+        for use_graph, schedule in ((False, 1), (True, 1), (True, 0), (False, 0)):
             s = Solver(num_iterations=iters, absolute_error_tolerance=0.0, relative_error_tolerance=0.0,
-                       use_graph=use_graph)
+                       use_graph=use_graph, schedule=schedule)
             x = ctx.zeros(n)
             s.solve(x, b_dev, gpu)
             assert s.iteration == iters
@@ -87,8 +88,9 @@ def test_six_million_cells_run_to_run_deterministic(any_ctx, solver):
         assert np.array_equal(y.numpy(), want), "apply differs from the row oracle at 6 M cells"
     Solver = sb.CgSolver if solver == "cg" else sb.BiCgStabSolver
     runs = []
-    for use_graph in (True, True, False, True):
-        s = Solver(num_iterations=50, absolute_error_tolerance=0.0, relative_error_tolerance=0.0, use_graph=use_graph)
+    for use_graph, schedule in ((True, 1), (True, 1), (False, 1), (True, 0), (True, 0)):   # 0: persistent kernel
+        s = Solver(num_iterations=50, absolute_error_tolerance=0.0, relative_error_tolerance=0.0, use_graph=use_graph,
+                   schedule=schedule)
         x = ctx.zeros(n)
         s.solve(x, b, gpu)
         runs.append((s.history.copy(), x.numpy()))
@@ -113,8 +115,9 @@ def test_hexahedra_width_six_rows_at_scale(ctx):
         gpu.mul(y, b)
         assert np.array_equal(y.numpy(), want)
     w = orc.solve("bicgstab", rows_op, bh, num_iterations=25, abs_tol=0.0, rel_tol=0.0, mode=orc.RED_TREE)
-    for use_graph in (False, True):
-        s = sb.BiCgStabSolver(num_iterations=25, absolute_error_tolerance=0.0, relative_error_tolerance=0.0, use_graph=use_graph)
+    for use_graph, schedule in ((False, 1), (True, 1), (False, 2)):   # 2: the persistent kernel, two CTAs per SM at this width
+        s = sb.BiCgStabSolver(num_iterations=25, absolute_error_tolerance=0.0, relative_error_tolerance=0.0, use_graph=use_graph,
+                              schedule=schedule)
         x = ctx.zeros(n)
         s.solve(x, b, gpu)
         assert np.array_equal(s.history, w.hist) and np.array_equal(x.numpy(), w.x)
