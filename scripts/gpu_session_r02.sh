@@ -52,4 +52,22 @@ case "$what" in
     python scripts/apply_sweep.py --cells hexlat --sizes 1e8,2e8 --out "$out/apply_sweep_hexlat.json" > "$out/config5.log" 2>&1
     tail -3 "$out/config5.log"
     ;;
+  c)
+    # persistent kernel v2 (dynamic tiles, bulk-copy staging of the element-wise steps): parity, then A/B against stepwise
+    export SB_SPIN_TIMEOUT_S=20
+    timeout 900 python -m pytest tests/test_gpu_mega.py tests/test_gpu_scale.py -x -q 2>&1 | tail -25 > "$out/pytest_mega.log"; tail -5 "$out/pytest_mega.log"
+    ( time timeout 600 $TR --nproc-per-node 2 --master-port 29531 tests/_dist_worker.py p2p ) > "$out/two_ranks_one_gpu.log" 2>&1
+    echo "two ranks on one GPU: rc=$?"; tail -4 "$out/two_ranks_one_gpu.log"
+    unset SB_SPIN_TIMEOUT_S
+    for ax in 59 119; do for sch in persistent stepwise; do
+      python bench.py --axis $ax --steps 200 --warmup 20 --no-cpu-baseline --schedule $sch > "$out/bench_n1_axis${ax}_$sch.json" 2>> "$out/bench.err"
+      python - "$out/bench_n1_axis${ax}_$sch.json" <<'PY'
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+o = d["other_solver"]
+print(sys.argv[1], "bicgstab", round(d["value"]), "it/s", round(1e3 * d["ms_per_step"], 1), "us;  cg", round(o["value"]), "it/s", round(1e3 * o["ms_per_step"], 1), "us")
+print("   phases", d["phases"] and {k: round(v, 1) for k, v in d["phases"]["us_per_step"].items()}, d["phases"] and {k: round(v, 1) for k, v in d["phases"]["us_barrier_wait_for_last_cta"].items()})
+PY
+    done; done
+    ;;
 esac

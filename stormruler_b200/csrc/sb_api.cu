@@ -50,7 +50,6 @@ int sb_ctx_create(int device, sb_ctx** out) {
   sb_ctx* ctx = new sb_ctx();
   ctx->device = device;
   if (const char* dbg = std::getenv("SB_DEBUG")) ctx->debug = std::atoi(dbg);
-  if (const char* pdl = std::getenv("SB_PDL")) ctx->pdl = std::atoi(pdl) != 0;
   ctx->spin_timeout_ns = sb::kDefaultSpinTimeoutNs;
   if (const char* t = std::getenv("SB_SPIN_TIMEOUT_S")) {
     const double secs = std::atof(t);

@@ -31,9 +31,11 @@ namespace sb {
 
 constexpr unsigned long long kDefaultSpinTimeoutNs = 120ull * 1000ull * 1000ull * 1000ull;
 
-// Programmatic dependent launch: every kernel calls pdl_trigger() (dependents may be scheduled) and then
-// pdl_wait() (all prerequisite grids have completed and their writes are visible) before it touches
-// anything a previous kernel wrote. Both are no-ops for kernels launched without the attribute.
+// Programmatic dependent launch hooks: every stepwise kernel calls pdl_trigger() (dependents may be scheduled) and
+// then pdl_wait() (all prerequisite grids have completed and their writes are visible) before it touches anything a
+// previous kernel wrote. The library launches without the programmatic-serialization attribute -- measured on the
+// B200 (round 1) it lost 4-7 % inside a replayed CUDA graph -- so both are no-ops; the persistent
+// kernel (sb_mega.cuh) removed the kernel boundaries they were meant to hide.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // The solver's stop flag, read around L1.

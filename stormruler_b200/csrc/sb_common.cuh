@@ -145,12 +145,6 @@ struct sb_ctx {
   // experiments only (SB_DEBUG env): bit1 = skip the halo exchange, bit2 = skip the cross-rank all-reduce
   // (results are wrong on purpose; used to attribute multi-GPU time, never set in tests or bench lines)
   int debug = 0;
-  // programmatic dependent launch (SB_PDL=1 enables): every kernel of the library starts with
-  // griddepcontrol.wait, so launching it with the programmatic-serialization attribute lets its CTAs
-  // become resident (and prefetch operator slices) while the previous kernel drains its last wave.
-  // Off by default: measured on B200 it gains 1-2 % with plain stream launches but LOSES 4-7 % inside a
-  // replayed CUDA graph (programmatic edges), and the graph is the faster of the two.
-  int pdl = 0;
   // persistent whole-solve kernel (sb_mega.cu): grid barrier / mailbox block, timeline scratch
   struct sb::MegaCtrl* d_mega = nullptr;
   unsigned long long* d_timeline = nullptr;
@@ -159,16 +153,12 @@ struct sb_ctx {
 };
 
 namespace sb {
-// Launch on the context's stream, with the PDL attribute when enabled.
+// Launch on the context's stream.
 template<class... KArgs, class... Args>
 inline cudaError_t launch_kernel(sb_ctx* ctx, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
                                  Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr, cfg.numAttrs = ctx->pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

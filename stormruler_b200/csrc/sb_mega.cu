@@ -34,7 +34,7 @@ bool mega_supported(const sb_ctx* ctx, const sb_op* op) {
 template<int KIND, int W>
 static int launch_one(sb_ctx* ctx, const MegaArgs& args) {
   auto kern = krylov_persistent_kernel<KIND, W>;
-  constexpr int smem = StageLayout<W>::cta_bytes;
+  constexpr int smem = MegaRing<W>::cta_bytes;
   static std::atomic<uint64_t> configured{0};
   static std::atomic<int> ctas_per_sm{0};
   const uint64_t bit = 1ull << (ctx->device & 63);
@@ -52,6 +52,7 @@ static int launch_one(sb_ctx* ctx, const MegaArgs& args) {
   const int64_t resident = (int64_t) ctas_per_sm.load(std::memory_order_acquire) * ctx->sm_count;
   const unsigned grid = (unsigned) std::max<int64_t>(1, std::min<int64_t>(resident, num_tiles(args.op.n)));
   SB_CUDA(cudaMemsetAsync(&ctx->d_mega->arrive, 0, sizeof(unsigned long long), ctx->stream));
+  SB_CUDA(cudaMemsetAsync(ctx->d_mega->dyn, 0, sizeof(ctx->d_mega->dyn), ctx->stream));
   void* kargs[] = {const_cast<MegaArgs*>(&args)};
   SB_CUDA(cudaLaunchCooperativeKernel((const void*) kern, dim3(grid), dim3(kThreads), kargs, (size_t) smem, ctx->stream));
   ctx->launches++;

@@ -27,6 +27,16 @@
 // reset by CTA 0 while it handles #a+1 (every local CTA has read it by then), before it sends #a+1 -- a peer cannot
 // post #a+2 before it has seen my #a+1.
 //
+// Tiles: every CTA owns the tiles {blockIdx.x + k grid} of the first three quarters of a step (no bookkeeping) and
+// draws the remaining ones from a counter in global memory, one at a time, two tiles ahead of where it works: the
+// CTAs that finish early take what is left (a static split leaves CTA 0 waiting 35 us of a 170 us apply step at
+// 10 M cells for the slowest CTA: profiles/r02_persistent_v1_*).
+//
+// Every streamed operand of every step arrives by bulk copy (cp.async.bulk) in a per-warp shared-memory ring:
+// the apply steps stage the operator's slice records and the warp's own run of x like apply_kernel_tma does, the
+// element-wise steps stage the 512-byte runs of their 2-5 input vectors, so the bytes in flight per SM (~190 KB)
+// do not depend on the register budget of three resident CTAs.
+//
 // Operator apply inside the loop: the TMA-staged tile pipeline of apply_kernel_tma, with the ring running across
 // the tiles of a CTA (no pipeline ramp per tile). Gathers use the coherent path (ld.global.ca): x is written by
 // this very kernel, and every grid barrier ends in a gpu-scope fence (which invalidates L1). Distributed operator:
@@ -48,7 +58,11 @@ struct MegaCtrl {
   unsigned long long ar_seq; // single-GPU: all-reduces completed (mailbox parity); multi-GPU uses CommCtrl::ar_seq
   unsigned long long pad1[14];
   unsigned long long box[2][4]; // single-GPU all-reduce mailbox
+  unsigned long long pad2[8];
+  unsigned long long dyn[16];   // dynamic-tile counters of three consecutive steps, 32 bytes apart (dyn_slot)
 };
+// The tile counter of step p is dyn_slot(p); CTA 0 zeroes the counter of step p+2 at the barrier that ends step p.
+__device__ __forceinline__ unsigned long long* dyn_slot(MegaCtrl* mc, unsigned long long step) { return &mc->dyn[(step % 3ull) * 4]; }
 
 constexpr int kMegaStamps = SB_TIMELINE_WORDS; // timeline record per iteration (include/stormb200.h: sb_solver_opts::h_timeline)
 
@@ -76,7 +90,7 @@ struct MegaRun {
   unsigned long long gen = 0;  // barriers passed in this launch
   unsigned long long ar = 0;   // all-reduce sequence number of the next reducing barrier
   unsigned long long seq = 0;  // distributed applies completed (CommCtrl::apply_seq)
-  uint32_t ringq = 0;          // stages that went through this warp's TMA ring
+  uint32_t par = 0;            // bit s: phase parity of the next wait on this warp's mbarrier s
   int32_t stamp_it = -1;       // timeline: iteration being stamped (-1: off)
   int32_t stamp_b = 0;
 };
@@ -108,7 +122,8 @@ __device__ __forceinline__ bool mega_spin(Pred ready, MegaCtrl* mc, unsigned lon
 // Shared-memory scratch of a CTA.
 struct MegaShared {
   SolverState st;                       // this CTA's copy of the solver state
-  double s_w[2][4][kMaxDots][kWarps];   // tile combine: warp sums of up to 4 tiles, double-buffered
+  double s_w[2][kMaxDots][kWarps];      // tile combine: the warp sums of a tile, double-buffered by tile parity
+  long long s_next[2];                  // tile scheduler: the tile after next, double-buffered by tile parity
   double s_fin[kMaxDots][kWarps];       // final stage (CTA 0)
   double s_all[kMaxRanks][4];           // mailbox values
   double s_local[4];
@@ -139,6 +154,7 @@ __device__ __forceinline__ bool grid_barrier(const MegaArgs& a, MegaRun& run, Me
     if (!mega_spin([&] { return ld_acquire_gpu(arrive) >= want; }, a.mc, a.timeout_ns, 0xD000 + run.gen)) sh.abort = 1;
     __threadfence(); // as cooperative_groups' grid sync: the fence (it invalidates this SM's L1) orders every thread
                      // of the CTA, through the __syncthreads below, behind the arrivals just observed
+    if (blockIdx.x == 0) *dyn_slot(a.mc, run.gen + 1) = 0; // tile counter of the step after next (nobody uses it now)
     if (run.stamp_it >= 0 && blockIdx.x == 0) {
       const unsigned long long t1 = globaltimer_ns();
       stamp(a, run, 6 + run.stamp_b, t1 - t0), stamp(a, run, 1 + run.stamp_b, t1);
@@ -170,6 +186,7 @@ __device__ __forceinline__ bool reduce_barrier(const MegaArgs& a, MegaRun& run, 
       if (run.stamp_it >= 0) t0 = globaltimer_ns();
       if (!mega_spin([&] { return ld_acquire_gpu(arrive) >= want; }, a.mc, a.timeout_ns, 0xD000 + run.gen)) sh.abort = 1;
       if (run.stamp_it >= 0) stamp(a, run, 6 + run.stamp_b, globaltimer_ns() - t0);
+      *dyn_slot(a.mc, run.gen + 1) = 0; // tile counter of the step after next (nobody uses it now)
     }
     __syncthreads();
     // every local CTA has arrived, hence has read the mailbox of the previous all-reduce: make it empty again
@@ -224,60 +241,137 @@ __device__ __forceinline__ bool reduce_barrier(const MegaArgs& a, MegaRun& run, 
   return sh.abort == 0;
 }
 
-// ---- tile combine: SB_TREE's "8 warp sums left to right", one CTA barrier per 4 tiles -----------------------------
+// ---- tile scheduler + tile combine ----------------------------------------------------------------------------------
+// The sequence of tiles a CTA works on in one step: blockIdx.x + k grid for k < Ks (static), then tickets of the
+// step's counter. `cur` and `nxt` are known to every thread; thread 0 determines the tile after `nxt` while the CTA
+// works on `cur` and publishes it through shared memory at the CTA barrier that ends every tile -- the same barrier
+// that completes SB_TREE's tile combine ("the 8 warp sums added left to right") in the reducing steps.
 template<int ND>
-struct TileCombine {
+struct TileSched {
   MegaShared& sh;
   const RedPtrs& red;
-  int buf = 0, cnt = 0;
-  int64_t tile0 = 0;
-  __device__ __forceinline__ TileCombine(MegaShared& s, const RedPtrs& r) : sh(s), red(r) {}
-  __device__ __forceinline__ void flush() {
-    if (cnt == 0) return;
-    __syncthreads();
-    if (threadIdx.x < cnt * ND) {
-      const int c = threadIdx.x / ND, d = threadIdx.x % ND;
-      double s = sh.s_w[buf][c][d][0];
-#pragma unroll
-      for (int w = 1; w < kWarps; ++w) s = __dadd_rn(s, sh.s_w[buf][c][d][w]);
-      red.partials[(int64_t) d * red.cap_tiles + tile0 + (int64_t) c * gridDim.x] = s;
-    }
-    buf ^= 1, cnt = 0;
+  unsigned long long* ctr;
+  long long n_tiles, G, Ks, base, i = 0, cur, nxt;
+  __device__ __forceinline__ long long after(long long k) const { // k-th tile of this CTA (k >= 2 only for thread 0)
+    return k < Ks ? (long long) blockIdx.x + k * G : base + (long long) atomicAdd(ctr, 1ull);
   }
-  __device__ __forceinline__ void add(double (&acc)[ND], int64_t tile) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (cnt == 0) tile0 = tile;
-#pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      const double v = warp_butterfly(acc[d]);
-      if (lane == 0) sh.s_w[buf][cnt][d][warp] = v;
-      acc[d] = 0.0;
+  __device__ __forceinline__ TileSched(MegaShared& s, const RedPtrs& r, const MegaArgs& a, const MegaRun& run, long long tiles)
+      : sh(s), red(r), ctr(dyn_slot(a.mc, run.gen)), n_tiles(tiles), G(gridDim.x) {
+    Ks = (n_tiles / G) * 3 / 4;
+    if (Ks < 1) Ks = 1;
+    base = Ks * G;
+    cur = blockIdx.x; // the grid never exceeds the number of tiles
+    if (Ks >= 2) {
+      nxt = cur + G;
+    } else {
+      if (threadIdx.x == 0) sh.s_next[1] = after(1);
+      __syncthreads();
+      nxt = sh.s_next[1];
+      __syncthreads(); // s_next[1] is written again during the second tile
     }
-    if (++cnt == 4) flush();
+  }
+  __device__ __forceinline__ bool more() const { return cur < n_tiles; }
+  // start of a tile: thread 0 looks two tiles ahead
+  __device__ __forceinline__ void begin() {
+    if (threadIdx.x == 0) sh.s_next[i & 1] = nxt < n_tiles ? after(i + 2) : n_tiles;
+  }
+  // end of a tile: combine the warp sums (reducing steps), advance
+  __device__ __forceinline__ void end(double (&acc)[ND > 0 ? ND : 1]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, buf = (int) (i & 1);
+    if constexpr (ND > 0) {
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        const double v = warp_butterfly(acc[d]);
+        if (lane == 0) sh.s_w[buf][d][warp] = v;
+        acc[d] = 0.0;
+      }
+    }
+    __syncthreads();
+    if constexpr (ND > 0) {
+      if (threadIdx.x < ND) {
+        const int d = threadIdx.x;
+        double t = sh.s_w[buf][d][0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) t = __dadd_rn(t, sh.s_w[buf][d][w]);
+        red.partials[(int64_t) d * red.cap_tiles + cur] = t;
+      }
+    }
+    const long long nxt2 = sh.s_next[i & 1];
+    cur = nxt, nxt = nxt2, ++i;
   }
 };
 
-// ---- element-wise step over this CTA's tiles -----------------------------------------------------------------------
-// Loads are issued two sub-iterations at a time (the persistent kernel keeps the register budget of three CTAs per SM).
-template<int ND, class Body>
-__device__ __forceinline__ void ew_phase(const Body& body, int64_t n, MegaShared& sh, const RedPtrs& red) {
-  const int64_t n_tiles = num_tiles(n);
-  TileCombine<(ND > 0 ? ND : 1)> tc(sh, red);
+// ---- per-warp staging ring ---------------------------------------------------------------------------------------
+constexpr int kMaxSlots = 4;
+template<int W>
+struct MegaRing {
+  static constexpr int apply_bytes = kStages * StageLayout<W>::bytes;
+  static constexpr int warp_bytes = apply_bytes > 8192 ? apply_bytes : 8192;
+  static constexpr int cta_bytes = warp_bytes * kWarps;
+};
+
+__device__ __forceinline__ void ring_wait(uint64_t* bars, MegaRun& run, int slot) {
+  mbar_wait(&bars[slot], (run.par >> slot) & 1u);
+  run.par ^= 1u << slot;
+}
+
+// ---- element-wise step --------------------------------------------------------------------------------------------
+// A stage = the 512-byte runs of the body's NV input vectors for one 64-element sub-iteration of the warp, one
+// mbarrier per ring slot; S = min(4, ring / stage) stages in flight per warp. Same element -> lane mapping, same
+// per-element arithmetic (Body::run) and same accumulation order as ew_kernel.
+template<int ND, int RING, class Body>
+__device__ __forceinline__ void ew_phase(const MegaArgs& a, MegaRun& run, MegaShared& sh, const Body& body, unsigned char* smem,
+                                         uint64_t (*bars_all)[kMaxSlots]) {
+  constexpr int NV = Body::NV, kStage = NV * 512;
+  constexpr int S = RING / kStage < kMaxSlots ? RING / kStage : kMaxSlots;
+  static_assert(S >= 1, "ring too small for this body");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = a.op.n;
+  unsigned char* wbase = smem + (size_t) warp * RING;
+  uint64_t* bars = bars_all[warp];
+  TileSched<ND> ts(sh, a.red, a, run, num_tiles(n));
+  auto issue = [&](long long tile, int j, int slot, uint32_t dep) {
+    const int64_t r0 = tile * kTile + warp * (kTile / kWarps) + j * 64;
+    mbar_expect_tx(&bars[slot], (uint32_t) kStage);
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      bulk_g2s(wbase + slot * kStage + k * 512, reinterpret_cast<const unsigned char*>(body.in(k) + r0) + dep, 512, &bars[slot]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < S; ++q) issue(ts.cur, q, q, 0u); // S <= kSub: all in the first tile
+  }
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
   for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  int slot = 0;
+  while (ts.more()) {
+    ts.begin();
 #pragma unroll
-    for (int h = 0; h < kSub; h += 2) {
-      typename Body::Regs r[2];
-      body.load(lane_elem(tile, h), r[0]);
-      body.load(lane_elem(tile, h + 1), r[1]);
-      body.run(lane_elem(tile, h), n, r[0], acc);
-      body.run(lane_elem(tile, h + 1), n, r[1], acc);
+    for (int j = 0; j < kSub; ++j) {
+      ring_wait(bars, run, slot);
+      double2 in[NV];
+      uint32_t fold = 0;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        in[k] = reinterpret_cast<const double2*>(wbase + slot * kStage + k * 512)[lane];
+        const long long b0 = __double_as_longlong(in[k].x), b1 = __double_as_longlong(in[k].y);
+        fold ^= (uint32_t) b0 ^ (uint32_t) (b0 >> 32) ^ (uint32_t) b1 ^ (uint32_t) (b1 >> 32);
+      }
+      // generic-proxy loads vs. the async-proxy refill of this slot: see apply_kernel_tma (sb_op.cuh)
+      const uint32_t dep = fold & (uint32_t) a.op.zero;
+      __syncwarp();
+      if (lane == 0) {
+        if (j + S < kSub) issue(ts.cur, j + S, slot, dep);
+        else if (ts.nxt < ts.n_tiles) issue(ts.nxt, j + S - kSub, slot, dep);
+      }
+      typename Body::Regs g;
+      body.fill(g, in);
+      body.run(lane_elem(ts.cur, j), n, g, acc);
+      slot = slot + 1 == S ? 0 : slot + 1;
     }
-    if constexpr (ND > 0) tc.add(acc, tile);
+    ts.end(acc);
   }
-  if constexpr (ND > 0) tc.flush();
 }
 
 // ---- operator-apply step -------------------------------------------------------------------------------------------
@@ -285,36 +379,29 @@ __device__ __forceinline__ void ew_phase(const Body& body, int64_t n, MegaShared
 template<int W, int ND, bool RESID, class Epi>
 __device__ __forceinline__ void apply_phase(const MegaArgs& a, MegaRun& run, MegaShared& sh, const double* __restrict__ x,
                                             double* __restrict__ y, int64_t x_off, const Epi& epi, unsigned char* smem,
-                                            uint64_t (*bars)[kStages], int apply_ordinal) {
+                                            uint64_t (*bars_all)[kMaxSlots], int apply_ordinal) {
   using L = StageLayout<W>;
   const OpDev& op = a.op;
   const ApplyDist& ad = a.ad;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t G = gridDim.x, n_tiles = num_tiles(op.n);
-  const int64_t K = n_tiles > (int64_t) blockIdx.x ? (n_tiles - 1 - blockIdx.x) / G + 1 : 0; // my tiles
-  const int64_t Q = K * kSub;                                                                 // my warp's stages
-  unsigned char* wbase = smem + (size_t) warp * kStages * L::bytes;
-  const uint32_t q0 = run.ringq;
-  auto row_of = [&](int64_t q) { return ((int64_t) blockIdx.x + (q / kSub) * G) * kTile + warp * (kTile / kWarps) + (q % kSub) * 64; };
-  auto issue = [&](int64_t q, uint32_t dep) {
-    const int s = (int) ((q0 + q) % kStages);
-    uint64_t* bar = &bars[warp][s];
+  unsigned char* wbase = smem + (size_t) warp * MegaRing<W>::warp_bytes;
+  uint64_t* bars = bars_all[warp];
+  TileSched<ND> ts(sh, a.red, a, run, num_tiles(op.n));
+  auto issue = [&](long long tile, int j, uint32_t dep) {
+    const int s = j & 1; // kStages == 2, four stages per tile: the slot is the parity of the sub-iteration
     unsigned char* dst = wbase + s * L::bytes;
-    const int64_t r = row_of(q);
-    mbar_expect_tx(bar, (uint32_t) L::bytes);
-    bulk_g2s(dst, op.blk + (r >> 6) * (int64_t) L::slice + dep, L::slice, bar);
-    bulk_g2s(dst + L::xown, reinterpret_cast<const unsigned char*>(x + r) + dep, 512, bar);
+    const int64_t r = tile * kTile + warp * (kTile / kWarps) + j * 64;
+    mbar_expect_tx(&bars[s], (uint32_t) L::bytes);
+    bulk_g2s(dst, op.blk + (r >> 6) * (int64_t) L::slice + dep, L::slice, &bars[s]);
+    bulk_g2s(dst + L::xown, reinterpret_cast<const unsigned char*>(x + r) + dep, 512, &bars[s]);
   };
-  if (lane == 0) {
-#pragma unroll
-    for (int j = 0; j < kStages; ++j)
-      if (j < Q) issue(j, 0u);
-  }
+  static_assert(kStages == 2 && kSub == 4, "slot arithmetic of the apply step");
+  if (lane == 0) issue(ts.cur, 0, 0u), issue(ts.cur, 1, 0u);
   const unsigned long long seq = run.seq + 1; // this apply's number (all CTAs of all ranks agree)
   if (ad.n_pack > 0) {
     // halo push: boundary values straight into the neighbours' halo tails over NVLink, one element per thread
     CommCtrl* me = ad.comm.ctrl(ad.comm.rank);
-    const int64_t total = ad.halo.send_ptr[ad.halo.n_nbr];
+    const int64_t G = gridDim.x, total = ad.halo.send_ptr[ad.halo.n_nbr];
     const int64_t n_pack = (total + kThreads - 1) / kThreads < G ? (total + kThreads - 1) / kThreads : G;
     if ((int64_t) blockIdx.x < n_pack) {
       for (int64_t i = (int64_t) blockIdx.x * kThreads + threadIdx.x; i < total; i += n_pack * kThreads) {
@@ -336,18 +423,17 @@ __device__ __forceinline__ void apply_phase(const MegaArgs& a, MegaRun& run, Meg
       }
     }
   }
-  TileCombine<(ND > 0 ? ND : 1)> tc(sh, a.red);
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
   for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
   bool halo_ready = ad.n_pack == 0;
-  for (int64_t k = 0; k < K; ++k) {
-    const int64_t tile = (int64_t) blockIdx.x + k * G;
-    const int64_t row0 = tile * kTile + warp * (kTile / kWarps);
+  while (ts.more()) {
+    ts.begin();
+    const int64_t row0 = ts.cur * kTile + warp * (kTile / kWarps);
     typename Epi::Regs er[kSub];
 #pragma unroll
     for (int j = 0; j < kSub; ++j) epi.load(row0 + j * 64 + 2 * lane, er[j]);
-    if (!halo_ready && tile >= ad.halo.first_boundary_tile) {
+    if (!halo_ready && ts.cur >= ad.halo.first_boundary_tile) {
       // boundary rows gather from the halo tail: wait until every neighbour's values of THIS apply have landed
       CommCtrl* me = ad.comm.ctrl(ad.comm.rank);
       if (lane < ad.halo.n_nbr) {
@@ -361,9 +447,8 @@ __device__ __forceinline__ void apply_phase(const MegaArgs& a, MegaRun& run, Meg
     }
 #pragma unroll
     for (int j = 0; j < kSub; ++j) {
-      const int64_t q = k * kSub + j;
-      const int s = (int) ((q0 + q) % kStages);
-      mbar_wait(&bars[warp][s], (uint32_t) (((q0 + q) / kStages) & 1));
+      const int s = j & 1;
+      ring_wait(bars, run, s);
       const unsigned char* src = wbase + s * L::bytes;
       int2 c[W];
       double2 cf[W];
@@ -390,8 +475,10 @@ __device__ __forceinline__ void apply_phase(const MegaArgs& a, MegaRun& run, Meg
       }
       const uint32_t dep = fold & (uint32_t) op.zero;
       __syncwarp();
-      if (lane == 0 && q + kStages < Q) issue(q + kStages, dep);
-
+      if (lane == 0) {
+        if (j + kStages < kSub) issue(ts.cur, j + kStages, dep);
+        else if (ts.nxt < ts.n_tiles) issue(ts.nxt, j + kStages - kSub, dep);
+      }
       double g0[W], g1[W];
 #pragma unroll
       for (int e = 0; e < W; ++e) {
@@ -416,10 +503,8 @@ __device__ __forceinline__ void apply_phase(const MegaArgs& a, MegaRun& run, Meg
       st2(y, e0, out);
       if constexpr (!RESID) epi.run(e0, op.n, xo, out, er[j], acc);
     }
-    if constexpr (ND > 0) tc.add(acc, tile);
+    ts.end(acc);
   }
-  if constexpr (ND > 0) tc.flush();
-  run.ringq = q0 + (uint32_t) Q;
   run.seq = seq;
 }
 
@@ -431,7 +516,7 @@ constexpr int mega_ctas_per_sm(int W) { return W <= 4 ? 3 : (W <= 7 ? 2 : 1); }
 template<int KIND, int W>
 __global__ void __launch_bounds__(kThreads, mega_ctas_per_sm(W)) krylov_persistent_kernel(const __grid_constant__ MegaArgs a) {
   extern __shared__ __align__(128) unsigned char sb_smem[];
-  __shared__ __align__(8) uint64_t bars[kWarps][kStages];
+  __shared__ __align__(8) uint64_t bars[kWarps][kMaxSlots];
   __shared__ MegaShared sh;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool dist = a.ad.comm.world > 1;
@@ -442,7 +527,7 @@ __global__ void __launch_bounds__(kThreads, mega_ctas_per_sm(W)) krylov_persiste
   }
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(&bars[warp][s], 1);
+    for (int s = 0; s < kMaxSlots; ++s) mbar_init(&bars[warp][s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async_all();
   }
@@ -452,7 +537,8 @@ __global__ void __launch_bounds__(kThreads, mega_ctas_per_sm(W)) krylov_persiste
   __syncthreads();
   SolverState* S = &sh.st;
   const Recorder rec{S, blockIdx.x == 0 ? a.hist : nullptr, blockIdx.x == 0 ? a.trace : nullptr};
-  const int64_t n = a.op.n, n_tiles = num_tiles(n);
+  const int64_t n_tiles = num_tiles(a.op.n);
+  constexpr int RING = MegaRing<W>::warp_bytes;
   bool ok = true;
   long long it = 0;
   while (ok && !S->done) {
@@ -461,22 +547,22 @@ __global__ void __launch_bounds__(kThreads, mega_ctas_per_sm(W)) krylov_persiste
     run.stamp_b = 0;
     if (threadIdx.x == 0 && blockIdx.x == 0) stamp(a, run, 0, globaltimer_ns());
     if constexpr (KIND == (int) Kind::BiCgStab) {
-      ew_phase<0>(BiDirectionBody{S, a.p, a.r, a.v}, n, sh, a.red);
+      ew_phase<0, RING>(a, run, sh, BiDirectionBody{S, a.p, a.r, a.v}, sb_smem, bars);
       if (!(ok = grid_barrier(a, run, sh))) break;
       apply_phase<W, 1, false>(a, run, sh, a.p, a.v, a.off_p, EpiUY{a.rt}, sb_smem, bars, 0);
       if (!(ok = reduce_barrier<1>(a, run, sh, n_tiles, BiAlphaFinal{rec}))) break;
-      ew_phase<0>(BiHalfBody{S, a.r, a.v}, n, sh, a.red);
+      ew_phase<0, RING>(a, run, sh, BiHalfBody{S, a.r, a.v}, sb_smem, bars);
       if (!(ok = grid_barrier(a, run, sh))) break;
       apply_phase<W, 2, false>(a, run, sh, a.r, a.t, a.off_r, EpiYYandYX{}, sb_smem, bars, 1);
       if (!(ok = reduce_barrier<2>(a, run, sh, n_tiles, BiOmegaFinal{rec}))) break;
-      ew_phase<2>(BiEndBody{S, a.x, a.r, a.p, a.t, a.rt}, n, sh, a.red);
+      ew_phase<2, RING>(a, run, sh, BiEndBody{S, a.x, a.r, a.p, a.t, a.rt}, sb_smem, bars);
       if (!(ok = reduce_barrier<2>(a, run, sh, n_tiles, BiEndFinal{rec}))) break;
     } else {
       apply_phase<W, 1, false>(a, run, sh, a.p, a.v, a.off_p, EpiXY{}, sb_smem, bars, 0);
       if (!(ok = reduce_barrier<1>(a, run, sh, n_tiles, CgAlphaFinal{rec}))) break;
-      ew_phase<1>(CgUpdateBody{S, a.x, a.r, a.p, a.v}, n, sh, a.red);
+      ew_phase<1, RING>(a, run, sh, CgUpdateBody{S, a.x, a.r, a.p, a.v}, sb_smem, bars);
       if (!(ok = reduce_barrier<1>(a, run, sh, n_tiles, CgBetaFinal{rec}))) break;
-      ew_phase<0>(CgDirectionBody{S, a.p, a.r}, n, sh, a.red);
+      ew_phase<0, RING>(a, run, sh, CgDirectionBody{S, a.p, a.r}, sb_smem, bars);
       if (!(ok = grid_barrier(a, run, sh))) break;
     }
     ++it;

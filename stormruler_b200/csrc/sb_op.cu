@@ -184,7 +184,7 @@ static int finish_op(sb_ctx* ctx, HostRows& R, int form, int prefill, double dt,
   if (const char* dbg = std::getenv("SB_DEBUG")) op->d.debug = std::atoi(dbg) & 1;
   SB_CUDA(cudaSetDevice(ctx->device));
   std::vector<unsigned char> blk;
-  if (form == SB_FORM_COEF && !apply_v1_forced()) {
+  if (form == SB_FORM_COEF) {
     // blocked layout: slice record = [col[W][64] | coef[W][64] | diag[64]]
     const int W = R.width;
     const int64_t slice_bytes = 768 * (int64_t) W + 512, n_slices = R.ld / 64;

@@ -370,15 +370,6 @@ struct sb_op {
 
 namespace sb {
 
-// SB_APPLY_V1=1 selects the register-staged kernel (v1) for A/B measurements.
-inline bool apply_v1_forced() {
-  static const bool forced = [] {
-    const char* e = std::getenv("SB_APPLY_V1");
-    return e != nullptr && e[0] == '1';
-  }();
-  return forced;
-}
-
 int halo_exchange(sb_ctx* ctx, const sb_op* op, const double* x, const int* done, int64_t* x_off); // sb_comm.cu
 
 // Launch y <- A x (+ epilogue) on the context's stream, dispatching on form and ELL width.

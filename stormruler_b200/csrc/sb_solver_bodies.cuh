@@ -105,6 +105,10 @@ struct CgUpdateBody { // x += alpha*p ; r -= alpha*z ; acc += r.r     (:97-98,11
   __device__ __forceinline__ void load(int64_t e0, Regs& g) const {
     g.x = ld2(x, e0), g.p = ld2(p, e0), g.r = ld2(r, e0), g.z = ld2(z, e0);
   }
+  // staged inputs (persistent kernel: the runs of the NV input vectors arrive by bulk copy)
+  static constexpr int NV = 4;
+  __device__ __forceinline__ const double* in(int k) const { return k == 0 ? x : (k == 1 ? p : (k == 2 ? r : z)); }
+  __device__ __forceinline__ void fill(Regs& g, const double2 (&v)[NV]) const { g.x = v[0], g.p = v[1], g.r = v[2], g.z = v[3]; }
   __device__ __forceinline__ void run(int64_t e0, int64_t n, Regs& g, double (&acc)[1]) const {
     const double alpha = st->alpha;
     double2 xn, rn;
@@ -126,6 +130,9 @@ struct CgDirectionBody { // p <- r + beta*p     (:122)
     double2 p, r;
   };
   __device__ __forceinline__ void load(int64_t e0, Regs& g) const { g.p = ld2(p, e0), g.r = ld2(r, e0); }
+  static constexpr int NV = 2;
+  __device__ __forceinline__ const double* in(int k) const { return k == 0 ? p : r; }
+  __device__ __forceinline__ void fill(Regs& g, const double2 (&v)[NV]) const { g.p = v[0], g.r = v[1]; }
   __device__ __forceinline__ void run(int64_t e0, int64_t, Regs& g, double (&)[1]) const {
     const double beta = st->beta;
     double2 pn;
@@ -197,6 +204,9 @@ struct BiDirectionBody { // iteration 0: p <- r ; else p <- r + beta*(p - omega*
     g.r = ld2(r, e0);
     if (st->iteration != 0) g.p = ld2(p, e0), g.v = ld2(v, e0);
   }
+  static constexpr int NV = 3; // the staged variant fetches p and v in iteration 0 too (unused there)
+  __device__ __forceinline__ const double* in(int k) const { return k == 0 ? r : (k == 1 ? p : v); }
+  __device__ __forceinline__ void fill(Regs& g, const double2 (&w)[NV]) const { g.r = w[0], g.p = w[1], g.v = w[2]; }
   __device__ __forceinline__ void run(int64_t e0, int64_t, Regs& g, double (&)[1]) const {
     double2 pn = g.r;
     if (st->iteration != 0) {
@@ -216,6 +226,9 @@ struct BiHalfBody { // r -= alpha*v     (:141); x += alpha*p is deferred to BiEn
     double2 r, v;
   };
   __device__ __forceinline__ void load(int64_t e0, Regs& g) const { g.r = ld2(r, e0), g.v = ld2(v, e0); }
+  static constexpr int NV = 2;
+  __device__ __forceinline__ const double* in(int k) const { return k == 0 ? r : v; }
+  __device__ __forceinline__ void fill(Regs& g, const double2 (&w)[NV]) const { g.r = w[0], g.v = w[1]; }
   __device__ __forceinline__ void run(int64_t e0, int64_t, Regs& g, double (&)[1]) const {
     const double alpha = st->alpha;
     double2 rn;
@@ -234,6 +247,11 @@ struct BiEndBody { // x = (x + alpha*p) + omega*r ; r -= omega*t ; acc0 += r.r ;
   };
   __device__ __forceinline__ void load(int64_t e0, Regs& g) const {
     g.x = ld2(x, e0), g.p = ld2(p, e0), g.r = ld2(r, e0), g.t = ld2(t, e0), g.rt = ld2(rt, e0);
+  }
+  static constexpr int NV = 5;
+  __device__ __forceinline__ const double* in(int k) const { return k == 0 ? x : (k == 1 ? p : (k == 2 ? r : (k == 3 ? t : rt))); }
+  __device__ __forceinline__ void fill(Regs& g, const double2 (&v)[NV]) const {
+    g.x = v[0], g.p = v[1], g.r = v[2], g.t = v[3], g.rt = v[4];
   }
   __device__ __forceinline__ void run(int64_t e0, int64_t n, Regs& g, double (&acc)[2]) const {
     const double alpha = st->alpha, omega = st->omega;

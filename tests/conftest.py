@@ -15,17 +15,6 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-# GPU tests written in a session that had no GPU time left to run them: collected LAST, so that `pytest -x` reaches
-# them only after every test already proven on the B200 has run (remove a file from this list once it has passed there)
-RUN_LAST = ("test_gpu_playground.py",)
-
-
-def pytest_collection_modifyitems(config, items):
-    late = [it for it in items if it.fspath.basename in RUN_LAST]
-    if late:
-        items[:] = [it for it in items if it.fspath.basename not in RUN_LAST] + late
-
-
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name))
 
@@ -46,6 +35,12 @@ def square_nb():
 @pytest.fixture(scope="session")
 def rectangle():
     return golden_mesh("rectangle")
+
+
+@pytest.fixture(scope="session")
+def step():
+    """tests/_data/mesh/step.1 of the reference: 79 672 triangles, the largest config-1 mesh."""
+    return golden_mesh("step")
 
 
 @pytest.fixture(scope="session")

@@ -19,6 +19,8 @@ Outputs (small, committed):
                                      and residual histories (`--only ch` regenerates just this file and
                                      cahn_hilliard_uniformed_square_nb.npz: 3 steps through the reference's
                                      solve_non_uniform, which is what makes its CG converge on this affine operator)
+  tests/golden/mesh_step.npz, cg_native_step.npz   the same two for the largest reference mesh, step.1
+                                     (`--only step`)
   tests/golden/blas1_kat.npz         known answers of tests/unit/BitternReductions.cpp /
                                      BitternMath.cpp evaluated by the reference templates
 
@@ -66,13 +68,39 @@ def make_cahn_hilliard(tmp):
     np.savez_compressed(f"{OUT}/cahn_hilliard_uniformed_{name}.npz", **out)
 
 
+def make_step(tmp):
+    """The third config-1 mesh, step.1 (79 672 triangles): the reference mesh classes' export and the reference's own
+    CgSolver on its own CellField (500 iterations, not converged: abs 0.23301109656816443). The solution is
+    kept at every 8th cell to keep the fixture small; the residual history is complete."""
+    name = "step"
+    prefix = f"{REF_DATA}/{name}.1."
+    mesh_bin, cg_bin = f"{tmp}/{name}.bin", f"{tmp}/{name}_cg.bin"
+    subprocess.run([orc.REF_MESH_TOOL, "export", prefix, mesh_bin], check=True)
+    subprocess.run([orc.REF_MESH_TOOL, "cg", prefix, str(DT), str(ITERS), str(RTOL), cg_bin], check=True)
+    mesh, extra = orc.read_mesh_export(mesh_bin)
+    np.savez_compressed(
+        f"{OUT}/mesh_{name}.npz", n_cells=mesh.n_cells, face_cell=mesh.face_cell,
+        face_area=mesh.face_area, face_dist=mesh.face_dist, cell_vol=mesh.cell_vol,
+        bface_cell=mesh.bface_cell, bface_area=mesh.bface_area, bface_dist=mesh.bface_dist,
+        bface_label=extra["bface_label"], n_nodes=extra["n_nodes"],
+        n_faces_total=extra["n_faces_total"], n_face_labels=extra["n_face_labels"])
+    cg = orc.read_cg_dump(cg_bin)
+    np.savez_compressed(f"{OUT}/cg_native_{name}.npz", converged=cg["converged"], iterations=cg["iterations"],
+                        abs_err=cg["abs_err"], rel_err=cg["rel_err"], hist=cg["hist"], x_every_8th=cg["x"][::8],
+                        x_norm=np.linalg.norm(cg["x"]), dt=DT, num_iterations=ITERS, rel_tol=RTOL)
+
+
 def main():
     assert os.path.isdir(REF_DATA), "reference tree not mounted"
     orc.build()
     tmp = tempfile.mkdtemp()
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "step":
+        make_step(tmp)
+        return
     make_cahn_hilliard(tmp)
     if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "ch":
         return
+    make_step(tmp)
     for name in ("square_nb", "rectangle"):
         prefix = f"{REF_DATA}/{name}.1."
         mesh_bin, cg_bin = f"{tmp}/{name}.bin", f"{tmp}/{name}_cg.bin"

@@ -1,7 +1,7 @@
 """Parity and determinism at sizes where the grid spans many waves of CTAs (the small reference meshes are 3
 tiles): 1.2 M tetrahedra against the oracle bit for bit, 6 M tetrahedra run-to-run. Guards the properties the
-small cases cannot see -- inter-CTA ordering, the final-reduce stage over thousands of partials, graph replay,
-programmatic dependent launch."""
+small cases cannot see -- inter-CTA ordering, the final-reduce stage over thousands of partials, graph replay, the
+persistent kernel's grid barriers with several tiles per CTA."""
 import os
 
 import numpy as np
@@ -27,15 +27,9 @@ def mesh_1m():
     return box(58)   # 1 170 672 cells = 572 tiles
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["pdl_off", "pdl_on"])
-def any_ctx(request):
-    old = os.environ.get("SB_PDL")
-    os.environ["SB_PDL"] = str(request.param)
+@pytest.fixture(scope="module")
+def any_ctx():
     c = sb.Context(0)
-    if old is None:
-        os.environ.pop("SB_PDL", None)
-    else:
-        os.environ["SB_PDL"] = old
     yield c
     c.close()
 
