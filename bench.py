@@ -247,8 +247,8 @@ def phase_times(timeline, solver):
     steps = np.diff(tl[:, :nb + 1], axis=1)
     out = {"us_per_step": {nm: float(steps[:, k].mean()) * 1e-3 for k, nm in enumerate(names)},
            "us_per_iteration": float((tl[:, nb] - tl[:, 0]).mean()) * 1e-3,
-           "us_barrier_wait_for_last_cta": {nm: float(tl[:, 6 + k].mean()) * 1e-3 for k, nm in enumerate(names)},
-           "us_allreduce_wait": {nm: float(tl[:, 11 + k].mean()) * 1e-3 for k, nm in enumerate(names) if "dot" in nm},
+           "us_in_barrier_cta0": {nm: float(tl[:, 6 + k].mean()) * 1e-3 for k, nm in enumerate(names)},
+           "us_wait_for_other_ranks": {nm: float(tl[:, 11 + k].mean()) * 1e-3 for k, nm in enumerate(names) if "dot" in nm},
            "us_halo_wait_max": [float(tl[:, 16 + k].mean()) * 1e-3 for k in range(2 if solver == "bicgstab" else 1)],
            "iterations_sampled": int(tl.shape[0])}
     return out
@@ -407,8 +407,8 @@ def run_own_arm(args):
         "phases": main.get("phases"),
         "stepwise": main["stepwise"],
         "applies_per_sec": main["applies_per_it"] * main["value"],
-        "other_solver": None if other is None else {k: other[k] for k in ("solver", "value", "ms_per_step", "schedule",
-                                                                        "iteration_roofline", "phases", "stepwise")},
+        "other_solver": None if other is None else {k: other.get(k) for k in ("solver", "value", "ms_per_step", "schedule",
+                                                                            "iteration_roofline", "phases", "stepwise")},
         "cpu_baseline": cpu,
         "cpu_baseline_all_cores": cpu_all,
         "parity": parity,

@@ -403,10 +403,11 @@ typedef struct sb_solver_opts {
   uint64_t* h_timeline;   /* [timeline_iters][SB_TIMELINE_WORDS], globaltimer nanoseconds, written by CTA 0:
                              [0] iteration start; [1+b] time after grid barrier b of the iteration (BiCGStab:
                              b = 0 direction, 1 apply+dot, 2 half update, 3 apply+2 dots, 4 final update;
-                             CG: 0 apply+dot, 1 update+dot, 2 direction); [6+b] ns CTA 0 waited at barrier b for
-                             the last CTA of its own GPU; [11+b] ns between posting this rank's sums and
-                             holding every rank's (reducing barriers only); [16+k] longest wait of any warp
-                             of this rank for a neighbour's halo values in apply k */
+                             CG: 0 apply+dot, 1 update+dot, 2 direction); [6+b] ns CTA 0 spent in barrier b, from
+                             its own arrival until it may go on (the wait for the slowest CTA, the reduction and
+                             the all-reduce included); [11+b] reducing barriers: ns the CTA that ran the reduction
+                             waited for the other ranks' sums after posting its own; [16+k] longest wait of any
+                             warp of this rank for a neighbour's halo values in apply k */
 } sb_solver_opts;
 
 /* Schedules of the fused CG / BiCGStab solvers (bit-identical results):

@@ -70,4 +70,25 @@ print("   phases", d["phases"] and {k: round(v, 1) for k, v in d["phases"]["us_p
 PY
     done; done
     ;;
+  d)
+    # persistent kernel v3 (balanced grid, last-arriver reduction, cross-barrier prefetch) + the CGS launch list
+    export SB_SPIN_TIMEOUT_S=20
+    timeout 900 python -m pytest tests/test_gpu_mega.py tests/test_gpu_scale.py -x -q 2>&1 | tail -25 > "$out/pytest_mega.log"; tail -5 "$out/pytest_mega.log"
+    ( time timeout 600 $TR --nproc-per-node 2 --master-port 29531 tests/_dist_worker.py p2p ) > "$out/two_ranks_one_gpu.log" 2>&1
+    echo "two ranks on one GPU: rc=$?"; tail -4 "$out/two_ranks_one_gpu.log"
+    unset SB_SPIN_TIMEOUT_S
+    for ax in 59 84 119; do for sch in persistent stepwise; do
+      python bench.py --axis $ax --steps 200 --warmup 20 --no-cpu-baseline --schedule $sch > "$out/bench_n1_axis${ax}_$sch.json" 2>> "$out/bench.err"
+      python - "$out/bench_n1_axis${ax}_$sch.json" <<'PY'
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+o = d["other_solver"]
+print(sys.argv[1], "bicgstab", round(d["value"]), "it/s", round(1e3 * d["ms_per_step"], 1), "us;  cg", round(o["value"]), "it/s", round(1e3 * o["ms_per_step"], 1), "us")
+print("   phases", d["phases"] and {k: round(v, 1) for k, v in d["phases"]["us_per_step"].items()}, d["phases"] and {k: round(v, 1) for k, v in d["phases"]["us_in_barrier_cta0"].items()})
+PY
+    done; done
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file "$out/launches_cgs_10M.csv" \
+        python scripts/solver_sweep.py --solvers cgs --steps 4 --repeats 1 > "$out/ncu_cgs.log" 2>&1
+    python scripts/summarize_ncu.py launches "$out/launches_cgs_10M.csv" "$out/launches_cgs_10M" "CGS, reference template on DeviceVector, 10.1 M tets" > /dev/null 2>&1; tail -15 "$out/launches_cgs_10M_summary.txt"
+    ;;
 esac

@@ -49,9 +49,14 @@ static int launch_one(sb_ctx* ctx, const MegaArgs& args) {
     ctas_per_sm.store(nb, std::memory_order_release);
     configured.fetch_or(bit, std::memory_order_release);
   }
+  // Grid: as many CTAs as fit the device at once (cooperative launch), shrunk so that the tiles divide evenly over
+  // them: R rounds of `grid` tiles, the last one short by less than R tiles.
   const int64_t resident = (int64_t) ctas_per_sm.load(std::memory_order_acquire) * ctx->sm_count;
-  const unsigned grid = (unsigned) std::max<int64_t>(1, std::min<int64_t>(resident, num_tiles(args.op.n)));
+  const int64_t tiles = std::max<int64_t>(1, num_tiles(args.op.n));
+  const int64_t rounds = (tiles + resident - 1) / resident;
+  const unsigned grid = (unsigned) ((tiles + rounds - 1) / rounds);
   SB_CUDA(cudaMemsetAsync(&ctx->d_mega->arrive, 0, sizeof(unsigned long long), ctx->stream));
+  SB_CUDA(cudaMemsetAsync(&ctx->d_mega->release, 0, sizeof(unsigned long long), ctx->stream));
   SB_CUDA(cudaMemsetAsync(ctx->d_mega->dyn, 0, sizeof(ctx->d_mega->dyn), ctx->stream));
   void* kargs[] = {const_cast<MegaArgs*>(&args)};
   SB_CUDA(cudaLaunchCooperativeKernel((const void*) kern, dim3(grid), dim3(kThreads), kargs, (size_t) smem, ctx->stream));

@@ -55,8 +55,9 @@ struct MegaCtrl {
   unsigned long long arrive; // grid-barrier arrival counter (zeroed by the host before every launch)
   unsigned long long pad0[15];
   unsigned long long abort;  // a spin wait timed out: every CTA leaves (code of the first failure)
+  unsigned long long release;// generation of the last completed plain grid barrier (written by its last arriver)
   unsigned long long ar_seq; // single-GPU: all-reduces completed (mailbox parity); multi-GPU uses CommCtrl::ar_seq
-  unsigned long long pad1[14];
+  unsigned long long pad1[13];
   unsigned long long box[2][4]; // single-GPU all-reduce mailbox
   unsigned long long pad2[8];
   unsigned long long dyn[16];   // dynamic-tile counters of three consecutive steps, 32 bytes apart (dyn_slot)
@@ -77,10 +78,7 @@ struct MegaArgs {
   RedPtrs red;
   MegaCtrl* mc;
   unsigned long long timeout_ns;
-  // optional timeline, CTA 0 only: per iteration kMegaStamps words:
-  //   [0] iteration start; [1+b] time after barrier b (b = 0..4); [6+b] ns CTA 0 waited for the last local arrival at
-  //   barrier b; [11+b] ns between CTA 0's mailbox send and the last peer's value (reducing barriers);
-  //   [16+k] longest halo-flag wait of any warp of this rank in apply k (k = 0, 1)
+  // optional timeline (include/stormb200.h: sb_solver_opts::h_timeline), kMegaStamps words per iteration
   unsigned long long* timeline;
   int32_t timeline_iters;
 };
@@ -91,6 +89,7 @@ struct MegaRun {
   unsigned long long ar = 0;   // all-reduce sequence number of the next reducing barrier
   unsigned long long seq = 0;  // distributed applies completed (CommCtrl::apply_seq)
   uint32_t par = 0;            // bit s: phase parity of the next wait on this warp's mbarrier s
+  int32_t pre = 0;             // stages of the NEXT step already in flight in ring slots 0..pre-1 (issued before the barrier)
   int32_t stamp_it = -1;       // timeline: iteration being stamped (-1: off)
   int32_t stamp_b = 0;
 };
@@ -122,40 +121,53 @@ __device__ __forceinline__ bool mega_spin(Pred ready, MegaCtrl* mc, unsigned lon
 // Shared-memory scratch of a CTA.
 struct MegaShared {
   SolverState st;                       // this CTA's copy of the solver state
-  double s_w[2][kMaxDots][kWarps];      // tile combine: the warp sums of a tile, double-buffered by tile parity
+  double s_w[2][4][kMaxDots][kWarps];   // tile combine: warp sums of up to 4 tiles, double-buffered
   long long s_next[2];                  // tile scheduler: the tile after next, double-buffered by tile parity
-  double s_fin[kMaxDots][kWarps];       // final stage (CTA 0)
+  double s_fin[kMaxDots][kWarps];       // final stage (the reducing CTA)
   double s_all[kMaxRanks][4];           // mailbox values
   double s_local[4];
   int abort;
+  int last;                             // this CTA was the last one to arrive at the current barrier
 };
 
-// All threads. Everything this CTA wrote is visible to every CTA that leaves the barrier.
-__device__ __forceinline__ void grid_arrive(const MegaArgs& a, MegaRun& run) {
-  fence_proxy_async_all(); // my generic-proxy stores vs. the bulk copies (async proxy) issued after the barrier
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(&a.mc->arrive, 1ull);
-  }
-  run.gen++;
+__device__ __forceinline__ void stamp(const MegaArgs& a, MegaRun& run, int slot, unsigned long long v) {
+  if (run.stamp_it >= 0 && blockIdx.x == 0) a.timeline[(int64_t) run.stamp_it * kMegaStamps + slot] = v;
 }
 
-__device__ __forceinline__ void stamp(const MegaArgs& a, MegaRun& run, int slot, unsigned long long v) {
-  if (run.stamp_it >= 0) a.timeline[(int64_t) run.stamp_it * kMegaStamps + slot] = v;
+// All threads. Everything this CTA wrote is visible to every CTA that leaves the barrier. The CTA whose arrival
+// completes the count learns it from its own atomic (sh.last): it releases the others (plain barrier) or runs the
+// reduction (reducing barrier) at once -- nobody polls the counter the arrivals are hammering.
+__device__ __forceinline__ void grid_arrive(const MegaArgs& a, MegaRun& run, MegaShared& sh) {
+  fence_proxy_async_all(); // my generic-proxy stores vs. the bulk copies (async proxy) issued after the barrier
+  __syncthreads();
+  run.gen++;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long old = atomicAdd(&a.mc->arrive, 1ull);
+    sh.last = (old + 1 == run.gen * gridDim.x) ? 1 : 0;
+    if (sh.last) {
+      __threadfence();                        // acquire: what the other CTAs wrote before they arrived
+      *dyn_slot(a.mc, run.gen + 1) = 0;       // tile counter of the step after next (nobody uses it now)
+    }
+  }
+  __syncthreads();
 }
 
 // Plain grid barrier. Returns false when the kernel must be abandoned.
 __device__ __forceinline__ bool grid_barrier(const MegaArgs& a, MegaRun& run, MegaShared& sh) {
-  grid_arrive(a, run);
+  const unsigned long long t0 = run.stamp_it >= 0 ? globaltimer_ns() : 0;
+  grid_arrive(a, run, sh);
   if (threadIdx.x == 0) {
-    const unsigned long long want = run.gen * gridDim.x, t0 = run.stamp_it >= 0 ? globaltimer_ns() : 0;
-    const unsigned long long* arrive = &a.mc->arrive;
-    if (!mega_spin([&] { return ld_acquire_gpu(arrive) >= want; }, a.mc, a.timeout_ns, 0xD000 + run.gen)) sh.abort = 1;
-    __threadfence(); // as cooperative_groups' grid sync: the fence (it invalidates this SM's L1) orders every thread
-                     // of the CTA, through the __syncthreads below, behind the arrivals just observed
-    if (blockIdx.x == 0) *dyn_slot(a.mc, run.gen + 1) = 0; // tile counter of the step after next (nobody uses it now)
-    if (run.stamp_it >= 0 && blockIdx.x == 0) {
+    if (sh.last) {
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&a.mc->release), "l"(run.gen) : "memory");
+    } else {
+      const unsigned long long want = run.gen;
+      const unsigned long long* rel = &a.mc->release;
+      if (!mega_spin([&] { return ld_acquire_gpu(rel) >= want; }, a.mc, a.timeout_ns, 0xD000 + run.gen)) sh.abort = 1;
+      __threadfence(); // as cooperative_groups' grid sync: the fence (it invalidates this SM's L1) orders every thread
+                       // of the CTA, through the __syncthreads below, behind the arrivals the release stands for
+    }
+    if (run.stamp_it >= 0) {
       const unsigned long long t1 = globaltimer_ns();
       stamp(a, run, 6 + run.stamp_b, t1 - t0), stamp(a, run, 1 + run.stamp_b, t1);
     }
@@ -177,18 +189,9 @@ template<int ND, class Final>
 __device__ __forceinline__ bool reduce_barrier(const MegaArgs& a, MegaRun& run, MegaShared& sh, int64_t n_tiles, const Final& fin) {
   const int world = a.ad.comm.world, me = a.ad.comm.rank;
   const unsigned long long par = run.ar & 1ull;
-  grid_arrive(a, run);
-  if (blockIdx.x == 0) {
-    unsigned long long t0 = 0;
-    if (threadIdx.x == 0) {
-      const unsigned long long want = run.gen * gridDim.x;
-      const unsigned long long* arrive = &a.mc->arrive;
-      if (run.stamp_it >= 0) t0 = globaltimer_ns();
-      if (!mega_spin([&] { return ld_acquire_gpu(arrive) >= want; }, a.mc, a.timeout_ns, 0xD000 + run.gen)) sh.abort = 1;
-      if (run.stamp_it >= 0) stamp(a, run, 6 + run.stamp_b, globaltimer_ns() - t0);
-      *dyn_slot(a.mc, run.gen + 1) = 0; // tile counter of the step after next (nobody uses it now)
-    }
-    __syncthreads();
+  const unsigned long long t0 = run.stamp_it >= 0 ? globaltimer_ns() : 0;
+  grid_arrive(a, run, sh);
+  if (sh.last) {
     // every local CTA has arrived, hence has read the mailbox of the previous all-reduce: make it empty again
     // BEFORE my sums go out (a peer posts into it only after it has seen those)
     if (threadIdx.x < world * 4) {
@@ -216,10 +219,11 @@ __device__ __forceinline__ bool reduce_barrier(const MegaArgs& a, MegaRun& run, 
     const int r = threadIdx.x / ND, d = threadIdx.x % ND;
     const unsigned long long* box = mega_box(a, me, par, r, d);
     unsigned long long v = kArSentinel;
-    const unsigned long long t0 = (run.stamp_it >= 0 && blockIdx.x == 0) ? globaltimer_ns() : 0;
+    const unsigned long long t1 = (run.stamp_it >= 0 && sh.last) ? globaltimer_ns() : 0;
     if (!mega_spin([&] { return (v = ld_relaxed_sys(box)) != kArSentinel; }, a.mc, a.timeout_ns, 0xC000 + r)) sh.abort = 1;
     sh.s_all[r][d] = __longlong_as_double((long long) v);
-    if (run.stamp_it >= 0 && blockIdx.x == 0) atomicMax(&a.timeline[(int64_t) run.stamp_it * kMegaStamps + 11 + run.stamp_b], globaltimer_ns() - t0);
+    // the reducing CTA: how long the other ranks' sums took to arrive after its own were posted
+    if (run.stamp_it >= 0 && sh.last) atomicMax(&a.timeline[(int64_t) run.stamp_it * kMegaStamps + 11 + run.stamp_b], globaltimer_ns() - t1);
   }
   __syncthreads();
   if (threadIdx.x == 0 && sh.abort == 0) {
@@ -231,7 +235,10 @@ __device__ __forceinline__ bool reduce_barrier(const MegaArgs& a, MegaRun& run, 
       tot[d] = s;
     }
     fin(tot);
-    if (run.stamp_it >= 0 && blockIdx.x == 0) stamp(a, run, 1 + run.stamp_b, globaltimer_ns());
+    if (run.stamp_it >= 0) {
+      const unsigned long long t2 = globaltimer_ns();
+      stamp(a, run, 6 + run.stamp_b, t2 - t0), stamp(a, run, 1 + run.stamp_b, t2);
+    }
   }
   run.ar++;
   run.stamp_b++;
@@ -242,61 +249,75 @@ __device__ __forceinline__ bool reduce_barrier(const MegaArgs& a, MegaRun& run, 
 }
 
 // ---- tile scheduler + tile combine ----------------------------------------------------------------------------------
-// The sequence of tiles a CTA works on in one step: blockIdx.x + k grid for k < Ks (static), then tickets of the
-// step's counter. `cur` and `nxt` are known to every thread; thread 0 determines the tile after `nxt` while the CTA
-// works on `cur` and publishes it through shared memory at the CTA barrier that ends every tile -- the same barrier
-// that completes SB_TREE's tile combine ("the 8 warp sums added left to right") in the reducing steps.
+// The sequence of tiles a CTA works on in one step. The host sizes the grid so that the tiles divide evenly:
+// R = ceil(tiles / resident CTAs) rounds, grid = ceil(tiles / R) CTAs (601 tiles on 444 resident CTAs: 301 CTAs with
+// two tiles each instead of 157 CTAs with two and 287 with one). Tiles blockIdx.x + k grid, k < Ks, are the CTA's
+// own (no bookkeeping, one CTA barrier per four tiles for SB_TREE's tile combine, "the 8 warp sums added left to
+// right"); with six rounds or more the last two rounds are handed out by a counter in global memory instead, one tile
+// at a time, to whichever CTA gets there first (SMs do not run at exactly the same speed, and at twelve rounds the
+// static split left a tail of 6-35 us per apply step). `cur` and `nxt` are known to every thread; from two tiles
+// before the dynamic part thread 0 draws the tile after `nxt` while the CTA works on `cur` (the ticket is consumed
+// only at the CTA barrier that ends the tile, which also publishes it).
 template<int ND>
 struct TileSched {
+  static constexpr int NA = ND > 0 ? ND : 1;
   MegaShared& sh;
   const RedPtrs& red;
   unsigned long long* ctr;
   long long n_tiles, G, Ks, base, i = 0, cur, nxt;
-  __device__ __forceinline__ long long after(long long k) const { // k-th tile of this CTA (k >= 2 only for thread 0)
-    return k < Ks ? (long long) blockIdx.x + k * G : base + (long long) atomicAdd(ctr, 1ull);
-  }
+  long long ticket = 0;      // thread 0: the tile drawn in begin()
+  long long chunk_tile0 = 0; // first tile of the pending combine chunk
+  int cnt = 0, buf = 0;      // pending tiles in the combine chunk, its buffer
   __device__ __forceinline__ TileSched(MegaShared& s, const RedPtrs& r, const MegaArgs& a, const MegaRun& run, long long tiles)
       : sh(s), red(r), ctr(dyn_slot(a.mc, run.gen)), n_tiles(tiles), G(gridDim.x) {
-    Ks = (n_tiles / G) * 3 / 4;
-    if (Ks < 1) Ks = 1;
+    const long long R = (n_tiles + G - 1) / G;
+    Ks = R >= 6 ? R - 2 : R;
     base = Ks * G;
     cur = blockIdx.x; // the grid never exceeds the number of tiles
-    if (Ks >= 2) {
-      nxt = cur + G;
-    } else {
-      if (threadIdx.x == 0) sh.s_next[1] = after(1);
-      __syncthreads();
-      nxt = sh.s_next[1];
-      __syncthreads(); // s_next[1] is written again during the second tile
-    }
+    nxt = cur + G;    // the second tile is always static (Ks >= 2 whenever there is one)
   }
   __device__ __forceinline__ bool more() const { return cur < n_tiles; }
-  // start of a tile: thread 0 looks two tiles ahead
+  __device__ __forceinline__ bool dynamic_from_here() const { return i + 2 >= Ks && Ks * G < n_tiles; }
+  // start of a tile: thread 0 looks two tiles ahead (only where the dynamic part begins)
   __device__ __forceinline__ void begin() {
-    if (threadIdx.x == 0) sh.s_next[i & 1] = nxt < n_tiles ? after(i + 2) : n_tiles;
+    if (threadIdx.x == 0 && dynamic_from_here()) ticket = nxt < n_tiles ? base + (long long) atomicAdd(ctr, 1ull) : n_tiles;
   }
-  // end of a tile: combine the warp sums (reducing steps), advance
-  __device__ __forceinline__ void end(double (&acc)[ND > 0 ? ND : 1]) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, buf = (int) (i & 1);
+  __device__ __forceinline__ void flush() {
     if constexpr (ND > 0) {
+      if (threadIdx.x < cnt * ND) {
+        const int c = threadIdx.x / ND, d = threadIdx.x % ND;
+        double t = sh.s_w[buf][c][d][0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) t = __dadd_rn(t, sh.s_w[buf][c][d][w]);
+        red.partials[(int64_t) d * red.cap_tiles + chunk_tile0 + (long long) c * G] = t;
+      }
+      buf ^= 1, cnt = 0;
+    }
+  }
+  // end of a tile: park the warp sums (reducing steps), advance; CTA barrier where something has to be published
+  __device__ __forceinline__ void end(double (&acc)[NA]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if constexpr (ND > 0) {
+      if (cnt == 0) chunk_tile0 = cur;
 #pragma unroll
       for (int d = 0; d < ND; ++d) {
         const double v = warp_butterfly(acc[d]);
-        if (lane == 0) sh.s_w[buf][d][warp] = v;
+        if (lane == 0) sh.s_w[buf][cnt][d][warp] = v;
         acc[d] = 0.0;
       }
+      ++cnt;
     }
-    __syncthreads();
-    if constexpr (ND > 0) {
-      if (threadIdx.x < ND) {
-        const int d = threadIdx.x;
-        double t = sh.s_w[buf][d][0];
-#pragma unroll
-        for (int w = 1; w < kWarps; ++w) t = __dadd_rn(t, sh.s_w[buf][d][w]);
-        red.partials[(int64_t) d * red.cap_tiles + cur] = t;
-      }
+    const bool dyn = dynamic_from_here();
+    long long nxt2 = nxt + G; // static successor of nxt
+    if (dyn) {
+      if (threadIdx.x == 0) sh.s_next[i & 1] = ticket;
+      __syncthreads();
+      nxt2 = sh.s_next[i & 1];
+      flush(); // dynamic tiles are not strided: one tile per chunk from here on
+    } else if (ND > 0 && (cnt == 4 || nxt >= n_tiles)) {
+      __syncthreads();
+      flush();
     }
-    const long long nxt2 = sh.s_next[i & 1];
     cur = nxt, nxt = nxt2, ++i;
   }
 };
@@ -337,10 +358,11 @@ __device__ __forceinline__ void ew_phase(const MegaArgs& a, MegaRun& run, MegaSh
     for (int k = 0; k < NV; ++k)
       bulk_g2s(wbase + slot * kStage + k * 512, reinterpret_cast<const unsigned char*>(body.in(k) + r0) + dep, 512, &bars[slot]);
   };
-  if (lane == 0) {
+  if (lane == 0 && run.pre == 0) {
 #pragma unroll
     for (int q = 0; q < S; ++q) issue(ts.cur, q, q, 0u); // S <= kSub: all in the first tile
   }
+  run.pre = 0;
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
   for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
@@ -374,6 +396,52 @@ __device__ __forceinline__ void ew_phase(const MegaArgs& a, MegaRun& run, MegaSh
   }
 }
 
+// Issue the first stages of the NEXT step before the barrier that precedes it, so that their latency overlaps the
+// barrier. Legal because a step's first tile is always the CTA's own tile blockIdx.x, whose elements are read and
+// written by the same warp (same lanes) in every step: what the copies read is final, and this warp's own stores are
+// ordered before them by the proxy fence + __syncwarp. If the step never runs (the solver stopped), the kernel drains
+// the copies before it exits.
+template<int RING, class Body>
+__device__ __forceinline__ void ew_prefetch(MegaRun& run, const Body& body, unsigned char* smem, uint64_t (*bars_all)[kMaxSlots]) {
+  constexpr int NV = Body::NV, kStage = NV * 512;
+  constexpr int S = RING / kStage < kMaxSlots ? RING / kStage : kMaxSlots;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  fence_proxy_async_all();
+  __syncwarp();
+  if (lane == 0) {
+    unsigned char* wbase = smem + (size_t) warp * RING;
+#pragma unroll
+    for (int q = 0; q < S; ++q) {
+      const int64_t r0 = (int64_t) blockIdx.x * kTile + warp * (kTile / kWarps) + q * 64;
+      mbar_expect_tx(&bars_all[warp][q], (uint32_t) kStage);
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        bulk_g2s(wbase + q * kStage + k * 512, reinterpret_cast<const unsigned char*>(body.in(k) + r0), 512, &bars_all[warp][q]);
+    }
+  }
+  run.pre = S;
+}
+
+template<int W>
+__device__ __forceinline__ void apply_prefetch(const MegaArgs& a, MegaRun& run, const double* x, unsigned char* smem,
+                                               uint64_t (*bars_all)[kMaxSlots]) {
+  using L = StageLayout<W>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  fence_proxy_async_all();
+  __syncwarp();
+  if (lane == 0) {
+    unsigned char* wbase = smem + (size_t) warp * MegaRing<W>::warp_bytes;
+#pragma unroll
+    for (int j = 0; j < kStages; ++j) {
+      const int64_t r = (int64_t) blockIdx.x * kTile + warp * (kTile / kWarps) + j * 64;
+      mbar_expect_tx(&bars_all[warp][j], (uint32_t) L::bytes);
+      bulk_g2s(wbase + j * L::bytes, a.op.blk + (r >> 6) * (int64_t) L::slice, L::slice, &bars_all[warp][j]);
+      bulk_g2s(wbase + j * L::bytes + L::xown, reinterpret_cast<const unsigned char*>(x + r), 512, &bars_all[warp][j]);
+    }
+  }
+  run.pre = kStages;
+}
+
 // ---- operator-apply step -------------------------------------------------------------------------------------------
 // apply_kernel_tma's pipeline with the ring running across this CTA's tiles. `x_off`: byte offset of x in the slab.
 template<int W, int ND, bool RESID, class Epi>
@@ -396,7 +464,8 @@ __device__ __forceinline__ void apply_phase(const MegaArgs& a, MegaRun& run, Meg
     bulk_g2s(dst + L::xown, reinterpret_cast<const unsigned char*>(x + r) + dep, 512, &bars[s]);
   };
   static_assert(kStages == 2 && kSub == 4, "slot arithmetic of the apply step");
-  if (lane == 0) issue(ts.cur, 0, 0u), issue(ts.cur, 1, 0u);
+  if (lane == 0 && run.pre == 0) issue(ts.cur, 0, 0u), issue(ts.cur, 1, 0u);
+  run.pre = 0;
   const unsigned long long seq = run.seq + 1; // this apply's number (all CTAs of all ranks agree)
   if (ad.n_pack > 0) {
     // halo push: boundary values straight into the neighbours' halo tails over NVLink, one element per thread
@@ -547,26 +616,41 @@ __global__ void __launch_bounds__(kThreads, mega_ctas_per_sm(W)) krylov_persiste
     run.stamp_b = 0;
     if (threadIdx.x == 0 && blockIdx.x == 0) stamp(a, run, 0, globaltimer_ns());
     if constexpr (KIND == (int) Kind::BiCgStab) {
-      ew_phase<0, RING>(a, run, sh, BiDirectionBody{S, a.p, a.r, a.v}, sb_smem, bars);
+      const BiDirectionBody dir{S, a.p, a.r, a.v};
+      const BiHalfBody half{S, a.r, a.v};
+      const BiEndBody fin{S, a.x, a.r, a.p, a.t, a.rt};
+      ew_phase<0, RING>(a, run, sh, dir, sb_smem, bars);
+      apply_prefetch<W>(a, run, a.p, sb_smem, bars);
       if (!(ok = grid_barrier(a, run, sh))) break;
       apply_phase<W, 1, false>(a, run, sh, a.p, a.v, a.off_p, EpiUY{a.rt}, sb_smem, bars, 0);
+      ew_prefetch<RING>(run, half, sb_smem, bars);
       if (!(ok = reduce_barrier<1>(a, run, sh, n_tiles, BiAlphaFinal{rec}))) break;
-      ew_phase<0, RING>(a, run, sh, BiHalfBody{S, a.r, a.v}, sb_smem, bars);
+      ew_phase<0, RING>(a, run, sh, half, sb_smem, bars);
+      apply_prefetch<W>(a, run, a.r, sb_smem, bars);
       if (!(ok = grid_barrier(a, run, sh))) break;
       apply_phase<W, 2, false>(a, run, sh, a.r, a.t, a.off_r, EpiYYandYX{}, sb_smem, bars, 1);
+      ew_prefetch<RING>(run, fin, sb_smem, bars);
       if (!(ok = reduce_barrier<2>(a, run, sh, n_tiles, BiOmegaFinal{rec}))) break;
-      ew_phase<2, RING>(a, run, sh, BiEndBody{S, a.x, a.r, a.p, a.t, a.rt}, sb_smem, bars);
+      ew_phase<2, RING>(a, run, sh, fin, sb_smem, bars);
+      ew_prefetch<RING>(run, dir, sb_smem, bars);
       if (!(ok = reduce_barrier<2>(a, run, sh, n_tiles, BiEndFinal{rec}))) break;
     } else {
+      const CgUpdateBody upd{S, a.x, a.r, a.p, a.v};
+      const CgDirectionBody dir{S, a.p, a.r};
       apply_phase<W, 1, false>(a, run, sh, a.p, a.v, a.off_p, EpiXY{}, sb_smem, bars, 0);
+      ew_prefetch<RING>(run, upd, sb_smem, bars);
       if (!(ok = reduce_barrier<1>(a, run, sh, n_tiles, CgAlphaFinal{rec}))) break;
-      ew_phase<1, RING>(a, run, sh, CgUpdateBody{S, a.x, a.r, a.p, a.v}, sb_smem, bars);
+      ew_phase<1, RING>(a, run, sh, upd, sb_smem, bars);
+      ew_prefetch<RING>(run, dir, sb_smem, bars);
       if (!(ok = reduce_barrier<1>(a, run, sh, n_tiles, CgBetaFinal{rec}))) break;
-      ew_phase<0, RING>(a, run, sh, CgDirectionBody{S, a.p, a.r}, sb_smem, bars);
+      ew_phase<0, RING>(a, run, sh, dir, sb_smem, bars);
+      apply_prefetch<W>(a, run, a.p, sb_smem, bars);
       if (!(ok = grid_barrier(a, run, sh))) break;
     }
     ++it;
   }
+  // copies issued for a step that did not run any more: a CTA must not exit with bulk copies landing in its smem
+  for (int q = 0; q < run.pre; ++q) ring_wait(bars[warp], run, q);
   // Every CTA has read the last mailbox before CTA 0 empties it (the next kernel expects empty mailboxes).
   run.stamp_it = -1;
   if (ok) ok = grid_barrier(a, run, sh);

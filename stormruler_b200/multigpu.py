@@ -315,7 +315,7 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
         st, _ = solve(k, schedule=schedule, timeline_iters=k)
         phases = bench_mod.phase_times(st.timeline, args.solver)
         if phases is not None:
-            for key in ("us_barrier_wait_for_last_cta", "us_allreduce_wait"):
+            for key in ("us_in_barrier_cta0", "us_wait_for_other_ranks"):
                 phases[key + "_max_over_ranks"] = {nm: max_over_ranks(v) for nm, v in phases[key].items()}
             phases["us_halo_wait_max_over_ranks"] = [max_over_ranks(v) for v in phases["us_halo_wait_max"]]
             phases["us_per_iteration_max_over_ranks"] = max_over_ranks(phases["us_per_iteration"])
