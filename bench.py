@@ -318,6 +318,7 @@ def run_own_arm(args):
         apply_slots = [k for k, nm in enumerate(slots) if nm.startswith("apply")]
         apply_ms = sum(kms[k] for k in apply_slots) / (len(apply_slots) * args.steps)   # avg per launch
         out["stepwise"] = {"kernel_ms_per_iteration": {nm: kms[k] / args.steps for k, nm in enumerate(slots)},
+                           "in_kernel_wait_ms_per_iteration": {nm: sp.wait_ms[k] / args.steps for k, nm in enumerate(slots)},
                            "apply_kernel": {"kernel": "sb::apply_kernel_tma + one-CTA final stage (stepwise schedule, profiled)",
                                             "algorithmic_bytes_per_launch": int(alg_apply), "avg_launch_ms": apply_ms,
                                             "achieved": alg_apply / (apply_ms * 1e-3) / 1e9,
@@ -437,7 +438,8 @@ def main():
                     help="N>1: halo exchange + reductions by in-kernel NVLink peer stores (p2p) or NCCL send/recv + allreduce")
     ap.add_argument("--partition", default="metis", choices=["metis", "slab"], help="N>1: METIS k-way or contiguous RCM slabs")
     ap.add_argument("--schedule", default="auto", choices=["auto", "stepwise", "persistent"],
-                    help="fused-solver schedule of the timed run (auto = persistent whole-solve kernel)")
+                    help="fused-solver schedule of the timed run (auto = stepwise: one kernel per step, reductions folded "
+                         "into their consumers, graph replay)")
     ap.add_argument("--single-solver", action="store_true", help="skip the leg of the other target solver (cg <-> bicgstab)")
     args = ap.parse_args()
     if args.impl == "reference":

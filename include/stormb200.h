@@ -397,7 +397,7 @@ typedef struct sb_solver_opts {
   int32_t profile;        /* 1: bracket every kernel of the iteration with CUDA events (no graph) and
                              report the accumulated time per kernel slot in sb_solver_report.kernel_ms
                              (implies the stepwise schedule) */
-  int32_t schedule;       /* SB_SCHEDULE_*; 0 = automatic: persistent wherever it is available */
+  int32_t schedule;       /* SB_SCHEDULE_*; 0 = automatic: the stepwise schedule (the faster one) */
   int32_t timeline_iters; /* persistent schedule: record the in-kernel timeline of the first this-many
                              iterations into h_timeline (0 = off) */
   uint64_t* h_timeline;   /* [timeline_iters][SB_TIMELINE_WORDS], globaltimer nanoseconds, written by CTA 0:
@@ -411,11 +411,14 @@ typedef struct sb_solver_opts {
 } sb_solver_opts;
 
 /* Schedules of the fused CG / BiCGStab solvers (bit-identical results):
- *   STEPWISE   one kernel per step of the iteration + a one-CTA kernel per reduction (optionally replayed as a
- *              CUDA graph): 5 / 8 launches per CG / BiCGStab iteration;
+ *   STEPWISE   one kernel per step of the iteration, replayed as a CUDA graph: 3 / 5 launches per CG / BiCGStab
+ *              iteration. The last stage of every reduction (final sum over the tile partials, all-reduce over the
+ *              ranks through NVLink peer memory, scalar update) is folded into the kernel that consumes the result;
+ *              NCCL mode keeps a one-CTA kernel + ncclAllReduce per reduction instead (5 / 8 launches);
  *   PERSISTENT one cooperative kernel runs the whole iteration loop; steps are separated by grid-wide barriers
- *              in global memory, the reductions and (multi-GPU) the all-reduce over NVLink peer memory happen
- *              inside the barrier. Needs the coefficient form; multi-GPU needs SB_COMM_P2P. */
+ *              in global memory, the reductions and the all-reduce happen inside the barrier. Needs the coefficient
+ *              form; multi-GPU needs SB_COMM_P2P. Measured slower than STEPWISE for BiCGStab (the barrier costs more
+ *              than a graph kernel boundary), on par for CG; kept for its in-kernel timeline. */
 #define SB_SCHEDULE_AUTO 0
 #define SB_SCHEDULE_STEPWISE 1
 #define SB_SCHEDULE_PERSISTENT 2
@@ -439,6 +442,10 @@ typedef struct sb_solver_report {
                                             (CG: apply+dot, update+dot, direction; BiCGStab: direction,
                                             apply+dot, half update, apply+2 dots, final update+2 dots) */
   int32_t schedule;    /* SB_SCHEDULE_STEPWISE or SB_SCHEDULE_PERSISTENT: the one that ran */
+  double wait_ms[SB_MAX_KERNEL_SLOTS];   /* profile=1: per kernel slot, the longest in-kernel wait of each launch summed
+                                            over the iterations -- apply slots: a boundary CTA waiting for a neighbour's
+                                            halo values; the other slots: CTA 0 waiting for the other ranks' partial sums
+                                            of the reduction it folds (0 on one GPU) */
 } sb_solver_report;
 
 SB_API int sb_cg_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b,

@@ -91,4 +91,21 @@ PY
         python scripts/solver_sweep.py --solvers cgs --steps 4 --repeats 1 > "$out/ncu_cgs.log" 2>&1
     python scripts/summarize_ncu.py launches "$out/launches_cgs_10M.csv" "$out/launches_cgs_10M" "CGS, reference template on DeviceVector, 10.1 M tets" > /dev/null 2>&1; tail -15 "$out/launches_cgs_10M_summary.txt"
     ;;
+  e)
+    # stepwise schedule with folded reductions (the default now): the whole GPU suite, then A/B against the persistent kernel
+    export SB_SPIN_TIMEOUT_S=30
+    timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 > "$out/pytest_gpu.log"; tail -8 "$out/pytest_gpu.log"
+    unset SB_SPIN_TIMEOUT_S
+    python -c "import __graft_entry__ as g; g.smoke()" > "$out/smoke.log" 2>&1; tail -4 "$out/smoke.log"
+    for ax in 59 84 119; do for sch in auto persistent; do
+      python bench.py --axis $ax --steps 200 --warmup 20 --no-cpu-baseline --schedule $sch > "$out/bench_n1_axis${ax}_$sch.json" 2>> "$out/bench.err"
+      python - "$out/bench_n1_axis${ax}_$sch.json" <<'PY'
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+o = d["other_solver"]
+print(sys.argv[1], "bicgstab", round(d["value"]), "it/s", round(1e3 * d["ms_per_step"], 1), "us;  cg", round(o["value"]), "it/s", round(1e3 * o["ms_per_step"], 1), "us; launches", d["gpu_launches"])
+print("   stepwise slots us", {k: round(1e3 * v, 1) for k, v in d["stepwise"]["kernel_ms_per_iteration"].items()})
+PY
+    done; done
+    ;;
 esac

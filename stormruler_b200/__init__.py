@@ -343,6 +343,7 @@ class _FusedSolver:
     solve_ms: float = 0.0
     iter_ms: float = 0.0
     kernel_ms: tuple = ()
+    wait_ms: tuple = ()
     launches: int = 0
     schedule_used: int = 0
     _entry = ""
@@ -368,6 +369,7 @@ class _FusedSolver:
         self.history, self.trace = hist[:rep.n_hist].copy(), trace[:rep.n_trace].copy()
         self.solve_ms, self.iter_ms, self.launches = rep.solve_ms, rep.iter_ms, int(rep.launches)
         self.kernel_ms = tuple(rep.kernel_ms[k] for k in range(rep.n_kernel_slots))
+        self.wait_ms = tuple(rep.wait_ms[k] for k in range(rep.n_kernel_slots))
         self.schedule_used = int(rep.schedule)
         self.timeline = tl[:min(int(self.timeline_iters), self.iteration)] if rep.schedule == capi.SCHEDULE_PERSISTENT else tl[:0]
         return bool(rep.converged)

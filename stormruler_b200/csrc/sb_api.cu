@@ -24,7 +24,7 @@ int ensure_red_scratch(sb_ctx* ctx, int64_t n) {
     ctx->red.partials = nullptr;
   }
   const int64_t cap = tiles + tiles / 4 + 64;
-  SB_CUDA(cudaMalloc(&ctx->red.partials, sizeof(double) * kMaxDots * cap));
+  SB_CUDA(cudaMalloc(&ctx->red.partials, sizeof(double) * 2 * kMaxDots * cap));
   ctx->red.cap_tiles = cap;
   return SB_OK;
 }
@@ -83,7 +83,7 @@ int sb_ctx_destroy(sb_ctx* ctx) {
   comm_teardown(ctx);
   cudaFree(ctx->d_mega);
   cudaFree(ctx->d_timeline);
-  cudaFree(ctx->d_state);
+  cudaFree(ctx->d_solve);
   cudaFree(ctx->d_hist);
   cudaFree(ctx->d_trace);
   cudaFree(ctx->red.partials);
@@ -186,6 +186,8 @@ bool prog_is(const sb_expr* e) {
   X(2, V0, S0, V1, MUL, SUB)                        \
   X(3, V0, S0, V1, S1, V2, MUL, SUB, MUL, ADD)      \
   X(3, V0, S0, V1, S1, V2, MUL, ADD, MUL, ADD)      \
+  X(3, V0, S0, V1, S0, V2, MUL, ADD, MUL, ADD)      \
+  X(3, V0, S0, V1, S0, V2, MUL, SUB, MUL, ADD)      \
   X(2, S0, V0, MUL, S1, V1, MUL, ADD)               \
   X(1, V0, S0, DIV)                                 \
   X(2, V0, V1, ADD)                                 \

@@ -109,17 +109,19 @@ __device__ __forceinline__ bool wait_flag_ge(const unsigned long long* flag, uns
 // Run by the first `n_pack` CTAs of the apply kernel. x_off: byte offset of the vector inside the slab
 // (identical on every rank).
 __device__ __forceinline__ void halo_pack_role(const CommDev& comm, const HaloDev& halo, const double* __restrict__ x,
-                                               int64_t x_off, int n_pack) {
+                                               int64_t x_off, int n_pack, bool no_ack) {
   CommCtrl* me = comm.ctrl(comm.rank);
   const unsigned long long seq = ld_acquire_sys(&me->apply_seq) + 1; // this apply's number
-  if (blockIdx.x == 0 && threadIdx.x < halo.n_nbr) {
-    // every earlier kernel of this rank has completed (griddepcontrol.wait) -> the halos of apply
-    // #seq-1 are free to overwrite
-    st_release_sys(&comm.ctrl(halo.nbr_rank[threadIdx.x])->ack_flag[comm.rank], seq - 1);
+  if (!no_ack) {
+    if (blockIdx.x == 0 && threadIdx.x < halo.n_nbr) {
+      // every earlier kernel of this rank has completed (griddepcontrol.wait) -> the halos of apply
+      // #seq-1 are free to overwrite
+      st_release_sys(&comm.ctrl(halo.nbr_rank[threadIdx.x])->ack_flag[comm.rank], seq - 1);
+    }
+    if (threadIdx.x < halo.n_nbr)
+      wait_flag_ge(&me->ack_flag[halo.nbr_rank[threadIdx.x]], seq - 1, me, 0xA000 + halo.nbr_rank[threadIdx.x], comm.timeout_ns);
+    __syncthreads();
   }
-  if (threadIdx.x < halo.n_nbr)
-    wait_flag_ge(&me->ack_flag[halo.nbr_rank[threadIdx.x]], seq - 1, me, 0xA000 + halo.nbr_rank[threadIdx.x], comm.timeout_ns);
-  __syncthreads();
   const int64_t total = halo.send_ptr[halo.n_nbr];
   for (int64_t i = (int64_t) blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t) n_pack * kThreads) {
     int k = 0;

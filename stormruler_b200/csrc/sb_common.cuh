@@ -100,6 +100,28 @@ struct RedScratch {
 
 } // namespace sb
 
+// State of a fused CG / BiCGStab solve (sb_solver_bodies.cuh: the functors that update it).
+struct SolverState {
+  double gamma, alpha, beta, rho, omega;
+  double initial_err, abs_err, rel_err;
+  double abs_tol, rel_tol;
+  long long iteration, max_iter;
+  long long n_hist, n_trace, hist_cap, trace_cap;
+  long long folds; // reductions of this solve consumed by a folding kernel so far (all-reduce mailbox parity)
+  int done, converged;
+};
+
+// Device block of a fused solve. The stepwise schedule keeps TWO versions of the state: a kernel that consumes a
+// reduction ("folds" it, sb_kernels.cuh: fold_prologue) reads version v in all its CTAs and CTA 0 writes version v^1,
+// so no CTA ever reads a field another CTA of the same kernel is writing; which one is current is a kernel argument.
+// `final_` is the state at the moment the stopping rule fired (what the host reads back), `done` the sticky stop flag
+// every later kernel checks first.
+struct SolveBlock {
+  SolverState ver[2];
+  SolverState final_;
+  int done;
+};
+
 struct sb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -111,7 +133,7 @@ struct sb_ctx {
   // solver workspaces, grown on demand and reused across solves
   std::vector<double*> work;
   size_t work_n = 0;
-  struct SolverState* d_state = nullptr; // device
+  struct SolveBlock* d_solve = nullptr;  // device: state versions of the fused CG / BiCGStab solve, stop flag
   double* d_hist = nullptr;
   int64_t hist_cap = 0;
   double* d_trace = nullptr;

@@ -183,6 +183,114 @@ struct NoFinal {
   __device__ void operator()(const double*) const {}
 };
 
+// ---- folding a reduction into the kernel that consumes it ----------------------------------------------------------
+// The one-CTA final stage costs a launch per reduction (~2.7 us of boundary + ~3 us of kernel inside a replayed graph:
+// a third of a BiCGStab iteration at 1.26 M cells per rank, profiles/r02_stepwise_unfolded_1M.json). A kernel that
+// needs the reduced scalars can finish the reduction itself instead: CTA 0 runs SB_TREE's final stage over the
+// producer's tile partials and posts the sums into the all-reduce mailbox of every rank (its own included; the single
+// mailbox of a one-GPU context is local); EVERY CTA polls its rank's mailbox, adds the rank sums in rank order and
+// runs the solver's scalar update on a copy of the solver state in shared memory -- identical inputs, identical code,
+// identical bits in all CTAs of all ranks. The copy comes from state version `in`; CTA 0 writes the updated state to
+// version `out` (never the version the other CTAs are reading), publishes the stop (`final_`, `done`) and bumps the
+// apply sequence number when the producer was a distributed apply. The mailbox of fold #a is emptied by CTA 0 of the
+// kernel that handles fold #a+1 (every CTA of the earlier kernel has finished by then), before it posts #a+1.
+struct FoldShared {
+  SolverState st;
+  double s_fin[kMaxDots][kWarps];
+  double s_all[kMaxRanks][4];
+  double s_local[4];
+};
+
+template<int ND, class Final>
+struct Fold {
+  int64_t n_tiles = -1;             // tiles of the producer; < 0: nothing to fold (the kernel reads version `in` as it is)
+  RedPtrs red{};
+  Final fin{};                      // fin.rec: history / trace buffers (CTA 0 records)
+  SolveBlock* blk = nullptr;
+  int32_t in = 0;                   // state version to start from; the result goes to in ^ 1
+  CommDev comm{};                   // world <= 1: one GPU
+  unsigned long long* box = nullptr;             // one GPU: mailbox [2][4]
+  const unsigned long long* ar_base = nullptr;   // all-reduces completed before this solve's folds (mailbox parity)
+  CommCtrl* bump = nullptr;         // the producer was a distributed apply: count it
+  unsigned long long* wait_ns = nullptr; // optional: longest wait of CTA 0 for the other ranks' sums (atomicMax)
+};
+
+__device__ __forceinline__ unsigned long long* fold_box(const CommDev& comm, unsigned long long* box, int rank, unsigned long long par,
+                                                        int src, int d) {
+  if (comm.world > 1) return &comm.ctrl(rank)->ar_slot[par][src][d];
+  return box + par * 4 + d;
+}
+
+// All threads of a folding kernel. On return sh.st is the updated state (valid for every thread).
+template<int ND, class Final>
+__device__ __forceinline__ void fold_prologue(const Fold<ND, Final>& f, FoldShared& sh) {
+  const int world = f.comm.world > 1 ? f.comm.world : 1, me = f.comm.world > 1 ? f.comm.rank : 0;
+  const SolverState* in = &f.blk->ver[f.in];
+  const unsigned long long par = (*f.ar_base + (unsigned long long) in->folds) & 1ull;
+  if (threadIdx.x == 0) sh.st = *in;
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < world * 4) { // empty the mailbox of the previous fold BEFORE my sums go out
+      const int r = threadIdx.x >> 2, d = threadIdx.x & 3;
+      st_relaxed_sys(fold_box(f.comm, f.box, me, par ^ 1ull, r, d), kArSentinel);
+    }
+    double sums[ND];
+    final_stage<ND>(f.n_tiles, f.red, sh.s_fin, sums);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int d = 0; d < ND; ++d) sh.s_local[d] = sums[d];
+      if (world > 1) __threadfence_system(); // the reset above is performed before any peer can answer what goes out below
+      else __threadfence();
+      if (f.bump != nullptr) f.bump->apply_seq = f.bump->apply_seq + 1; // the distributed apply in front of me is complete
+    }
+    __syncthreads();
+    if (threadIdx.x < world * ND) {
+      const int r = threadIdx.x / ND, d = threadIdx.x % ND;
+      st_relaxed_sys(fold_box(f.comm, f.box, r, par, me, d), (unsigned long long) __double_as_longlong(sh.s_local[d]));
+    }
+  }
+  if (threadIdx.x < world * ND) {
+    const int r = threadIdx.x / ND, d = threadIdx.x % ND;
+    const unsigned long long* box = fold_box(f.comm, f.box, me, par, r, d);
+    unsigned long long v = ld_relaxed_sys(box);
+    if (v == kArSentinel) {
+      CommCtrl* ctl = f.comm.world > 1 ? f.comm.ctrl(me) : nullptr;
+      const unsigned long long t0 = globaltimer_ns(), limit = f.comm.world > 1 ? f.comm.timeout_ns : kDefaultSpinTimeoutNs;
+      unsigned spins = 0;
+      while ((v = ld_relaxed_sys(box)) == kArSentinel) {
+        if ((++spins & 63u) == 0 && (globaltimer_ns() - t0 > limit || (ctl != nullptr && comm_failed(ctl)))) {
+          if (ctl != nullptr) comm_fail(ctl, 0xC000 + r);
+          break;
+        }
+      }
+      if (f.wait_ns != nullptr && blockIdx.x == 0) atomicMax(f.wait_ns, globaltimer_ns() - t0);
+    }
+    sh.s_all[r][d] = __longlong_as_double((long long) v);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      double t = sh.s_all[0][d];
+      for (int r = 1; r < world; ++r) t = __dadd_rn(t, sh.s_all[r][d]);
+      tot[d] = t;
+    }
+    Final fin = f.fin;
+    fin.rec.st = &sh.st;
+    if (blockIdx.x != 0) fin.rec.hist = nullptr, fin.rec.trace = nullptr;
+    fin(tot);
+    sh.st.folds++;
+    if (blockIdx.x == 0) {
+      f.blk->ver[f.in ^ 1] = sh.st;
+      if (sh.st.done) {
+        f.blk->final_ = sh.st;
+        f.blk->done = 1;
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // Generic tiled element-wise kernel. Body provides
 //   struct Regs; void load(int64_t e0, Regs&) const; void run(int64_t e0, int64_t n, Regs&, double (&acc)[max(ND,1)]) const;
 // `done` (may be null) is the solver's device-side stop flag: once set, later launches are no-ops, so
@@ -196,6 +304,37 @@ __global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, Body body, RedP
   typename Body::Regs r[kSub];
 #pragma unroll
   for (int j = 0; j < kSub; ++j) body.load(lane_elem(blockIdx.x, j), r[j]);
+  double acc[ND > 0 ? ND : 1];
+#pragma unroll
+  for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+#pragma unroll
+  for (int j = 0; j < kSub; ++j) body.run(lane_elem(blockIdx.x, j), n, r[j], acc);
+  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, blockIdx.x);
+}
+
+// The same kernel in front of which a reduction is folded (fold_prologue): the tile's loads are issued first, so the
+// final stage, the mailbox round trip and the scalar update run under their latency; the body then reads the solver
+// scalars from the CTA's own copy of the state (Body::st is redirected to it). One extra CTA beyond the tiles is never
+// needed: a fold without tiles (the flush at the end of a solve) is launched with n = 0 and one CTA.
+template<int ND, class Body, int FND, class Final>
+__global__ void __launch_bounds__(kThreads) ew_fold_kernel(int64_t n, Body body, RedPtrs red, const int* __restrict__ done,
+                                                           Fold<FND, Final> fold) {
+  __shared__ FoldShared sh;
+  if (is_done(done)) return;
+  const bool tile = (int64_t) blockIdx.x * kTile < n;
+  typename Body::Regs r[kSub];
+  if (tile) {
+#pragma unroll
+    for (int j = 0; j < kSub; ++j) body.load(lane_elem(blockIdx.x, j), r[j]);
+  }
+  if (fold.n_tiles >= 0) {
+    fold_prologue(fold, sh);
+  } else {
+    if (threadIdx.x == 0) sh.st = fold.blk->ver[fold.in];
+    __syncthreads();
+  }
+  if (sh.st.done || !tile) return; // the stopping rule has just fired: the iterate stays what it is
+  body.st = &sh.st;
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
   for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;

@@ -11,7 +11,10 @@ static __global__ void mega_ctrl_init_kernel(MegaCtrl* mc) {
   if (threadIdx.x < 8) (&mc->box[0][0])[threadIdx.x] = kArSentinel;
 }
 
-static int ensure_mega_ctrl(sb_ctx* ctx) {
+unsigned long long* single_gpu_box(sb_ctx* ctx) { return &ctx->d_mega->box[0][0]; }
+unsigned long long* single_gpu_ar_seq(sb_ctx* ctx) { return &ctx->d_mega->ar_seq; }
+
+int ensure_mega_ctrl(sb_ctx* ctx) {
   if (ctx->d_mega != nullptr) return SB_OK;
   SB_CUDA(cudaMalloc(&ctx->d_mega, sizeof(MegaCtrl)));
   SB_CUDA(cudaMemsetAsync(ctx->d_mega, 0, sizeof(MegaCtrl), ctx->stream));
@@ -70,7 +73,7 @@ int launch_mega(sb_ctx* ctx, const sb_op* op, const MegaLaunch& L) {
   MegaArgs a{};
   a.op = op->d;
   a.x = L.x, a.r = L.r, a.p = L.p, a.v = L.v, a.t = L.t, a.rt = L.rt;
-  a.st = L.st, a.hist = L.hist, a.trace = L.trace;
+  a.blk = L.blk, a.hist = L.hist, a.trace = L.trace;
   a.red = RedPtrs{ctx->red.partials, ctx->red.cap_tiles};
   a.mc = ctx->d_mega;
   a.timeout_ns = ctx->spin_timeout_ns;

@@ -72,7 +72,7 @@ struct MegaArgs {
   ApplyDist ad;                 // ad.n_pack > 0: distributed operator with neighbours (x_off unused here)
   double *x, *r, *p, *v, *t, *rt; // CG: v = z; t, rt unused
   int64_t off_p, off_r;         // byte offsets of p and r inside the slab (halo pushes)
-  SolverState* st;
+  SolveBlock* blk;
   double* hist;
   double* trace;
   RedPtrs red;
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, mega_ctas_per_sm(W)) krylov_persiste
   const bool dist = a.ad.comm.world > 1;
   CommCtrl* ctl = dist ? a.ad.comm.ctrl(a.ad.comm.rank) : nullptr;
   if (threadIdx.x == 0) {
-    sh.st = *a.st;
+    sh.st = a.blk->ver[0];
     sh.abort = 0;
   }
   if (lane == 0) {
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(kThreads, mega_ctas_per_sm(W)) krylov_persiste
       st_relaxed_sys(mega_box(a, a.ad.comm.rank, (run.ar - 1) & 1ull, r, d), kArSentinel);
     }
     if (threadIdx.x == 0) {
-      *a.st = *S;
+      a.blk->ver[0] = *S, a.blk->final_ = *S, a.blk->done = S->done;
       if (dist) ctl->ar_seq = run.ar, ctl->apply_seq = run.seq;
       else a.mc->ar_seq = run.ar;
     }

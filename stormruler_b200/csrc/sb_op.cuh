@@ -33,15 +33,22 @@ struct ApplyDist {
   int32_t coherent_gather = 0; // 1: BOUNDARY tiles gather x with ld.global.ca instead of the read-only path
                                // (their halo tail is written by peers while the kernel runs); interior tiles
                                // never touch the halo and keep ld.global.nc
+  int32_t no_ack = 0;          // 1: skip the ack round before the halo push. Valid inside the fused solvers: between two
+                               // applies that write the same halo tail there is always an all-reduce, and a rank
+                               // contributes to it only after its earlier apply has completed
+  unsigned long long* wait_ns = nullptr; // optional: longest halo-flag wait of any boundary CTA (atomicMax)
 };
 
 // Boundary tiles (they read the halo tail) wait until every neighbour's values of THIS apply have landed.
 __device__ __forceinline__ void apply_halo_wait(const ApplyDist& ad, int64_t tile) {
   if (ad.n_pack > 0 && tile >= ad.halo.first_boundary_tile) {
     CommCtrl* me = ad.comm.ctrl(ad.comm.rank);
-    if (threadIdx.x < ad.halo.n_nbr)
+    if (threadIdx.x < ad.halo.n_nbr) {
+      const unsigned long long t0 = ad.wait_ns != nullptr ? globaltimer_ns() : 0;
       wait_flag_ge(&me->halo_flag[ad.halo.nbr_rank[threadIdx.x]], ld_acquire_sys(&me->apply_seq) + 1, me,
                    0xB000 + ad.halo.nbr_rank[threadIdx.x], ad.comm.timeout_ns);
+      if (ad.wait_ns != nullptr) atomicMax(ad.wait_ns, globaltimer_ns() - t0);
+    }
     __syncthreads();
   }
 }
@@ -104,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double*
   pdl_wait();
   if (is_done(done)) return;
   if (ad.n_pack > 0 && (int) blockIdx.x < ad.n_pack) {
-    halo_pack_role(ad.comm, ad.halo, x, ad.x_off, ad.n_pack);
+    halo_pack_role(ad.comm, ad.halo, x, ad.x_off, ad.n_pack, ad.no_ack != 0);
     return;
   }
   const int64_t tile = (int64_t) blockIdx.x - ad.n_pack;
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
   pdl_trigger();
   if (ad.n_pack > 0 && (int) blockIdx.x < ad.n_pack) { // halo-pack CTAs: scheduled first, overlap the interior tiles
     pdl_wait();
-    if (!is_done(done)) halo_pack_role(ad.comm, ad.halo, x, ad.x_off, ad.n_pack);
+    if (!is_done(done)) halo_pack_role(ad.comm, ad.halo, x, ad.x_off, ad.n_pack, ad.no_ack != 0);
     return;
   }
   const int64_t tile = (int64_t) blockIdx.x - ad.n_pack;
@@ -374,9 +381,13 @@ int halo_exchange(sb_ctx* ctx, const sb_op* op, const double* x, const int* done
 
 // Launch y <- A x (+ epilogue) on the context's stream, dispatching on form and ELL width.
 // `per_call` (optional) replaces the operator's kernel arguments for this launch (sb_apply_accumulate: other dt/prefill).
+// `fold_later`: the reduction (and the count of this apply) is folded into the kernel that consumes it
+// (sb_kernels.cuh: fold_prologue) instead of a one-CTA final stage behind this launch; valid inside the fused solvers,
+// where the ack round of the halo exchange is not needed either (ApplyDist::no_ack). `halo_wait_ns`: optional timeline.
 template<int ND, bool RESID, class Epi, class Final>
 int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const Epi& epi, const Final& fin,
-                 const int* done, const OpDev* per_call = nullptr) {
+                 const int* done, const OpDev* per_call = nullptr, bool fold_later = false,
+                 unsigned long long* halo_wait_ns = nullptr) {
   const OpDev& d = per_call != nullptr ? *per_call : op->d;
   if constexpr (ND > 0) {
     SB_TRY(ensure_red_scratch(ctx, d.n));
@@ -394,6 +405,8 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
       const int64_t total = op->halo.send_ptr[op->halo.n_nbr];
       ad.n_pack = (int32_t) std::max<int64_t>(1, std::min<int64_t>(64, (total + 2 * kThreads - 1) / (2 * kThreads)));
       ad.coherent_gather = 1;
+      ad.no_ack = fold_later ? 1 : 0;
+      ad.wait_ns = halo_wait_ns;
     }
     // The apply sequence number counts EVERY apply of a distributed operator on every rank, whether this rank has
     // neighbours in this operator or not: the flags of different operators (other partitions, a rank without
@@ -461,6 +474,7 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
 #undef SB_WIDTHS
 #undef SB_LAUNCH
   ctx->launches++;
+  if (fold_later) return SB_OK;
   if constexpr (ND > 0) return launch_final<ND>(ctx, d.n, fin, done, bump);
   if (bump != nullptr) {
     SB_CUDA(launch_kernel(ctx, seq_bump_kernel, 1, 1, 0, bump, done));

@@ -9,15 +9,6 @@
 
 #include "sb_op.cuh"
 
-struct SolverState {
-  double gamma, alpha, beta, rho, omega;
-  double initial_err, abs_err, rel_err;
-  double abs_tol, rel_tol;
-  long long iteration, max_iter;
-  long long n_hist, n_trace, hist_cap, trace_cap;
-  int done, converged;
-};
-
 namespace sb {
 
 __device__ __forceinline__ double safe_divide(double x, double y) {
@@ -55,6 +46,17 @@ struct Recorder {
     st->iteration++;
     if (conv) st->converged = 1;
     if (conv || st->iteration >= st->max_iter) st->done = 1;
+  }
+};
+
+// One-CTA final stage (no folding: initialisation, NCCL mode): run the scalar update in place, then publish the stop.
+template<class Inner>
+struct PublishFinal {
+  Inner inner;
+  SolveBlock* blk;
+  __device__ void operator()(const double* s) const {
+    inner(s);
+    if (inner.rec.st->done) blk->final_ = *inner.rec.st, blk->done = 1;
   }
 };
 
@@ -201,8 +203,9 @@ struct BiDirectionBody { // iteration 0: p <- r ; else p <- r + beta*(p - omega*
     double2 p, r, v;
   };
   __device__ __forceinline__ void load(int64_t e0, Regs& g) const {
-    g.r = ld2(r, e0);
-    if (st->iteration != 0) g.p = ld2(p, e0), g.v = ld2(v, e0);
+    // p and v are fetched in iteration 0 as well (unused there): the loads are issued before the reduction in front
+    // of this kernel has been folded, i.e. before the iteration number is known
+    g.r = ld2(r, e0), g.p = ld2(p, e0), g.v = ld2(v, e0);
   }
   static constexpr int NV = 3; // the staged variant fetches p and v in iteration 0 too (unused there)
   __device__ __forceinline__ const double* in(int k) const { return k == 0 ? r : (k == 1 ? p : v); }
@@ -274,7 +277,7 @@ enum class Kind { Cg, BiCgStab };
 struct MegaLaunch {
   Kind kind;
   double *x, *r, *p, *v, *t, *rt; // CG: v = z; t, rt unused
-  SolverState* st;
+  SolveBlock* blk;        // version 0 holds the initialised state; the kernel publishes final_ / done
   double* hist;
   double* trace;
   int32_t timeline_iters; // > 0: record the in-kernel timeline of the first iterations into ctx->d_timeline

@@ -7,13 +7,16 @@
 //
 // What is different is the schedule (SURVEY.md a13/a14 "fused minimum"):
 //   * scalars (alpha, beta, rho, omega, gamma, residual, iteration, stop flag) live in a device
-//     struct; the last CTA of each reducing kernel updates them, so an iteration needs no host sync;
-//   * every dot/norm is fused into the kernel that produces its operand (apply or update);
+//     struct, so an iteration needs no host sync;
+//   * every dot/norm is fused into the kernel that produces its operand (apply or update), and its last stage
+//     -- SB_TREE's final sum over the tile partials, the all-reduce over the ranks, the scalar update -- is
+//     folded into the kernel that consumes the result (sb_kernels.cuh: fold_prologue): no one-CTA kernels
+//     between the steps (they remain for the initialisation and for NCCL mode);
 //   * BiCGStab's `x += alpha*p` is deferred into the final update kernel, which evaluates
 //     x = (x + alpha*p) + omega*r with the same two roundings per term as the reference;
 //   * once the device-side stop flag is set, the remaining queued kernels return immediately, so the
 //     solution is exactly the reference's iterate at the stopping iteration.
-// CG: 3 kernels / iteration, 9 vector passes + 1 apply. BiCGStab: 5 kernels, 15 passes + 2 applies.
+// CG: 3 launches / iteration, 9 vector passes + 1 apply. BiCGStab: 5 launches, 15 passes + 2 applies.
 #include "sb_solver_bodies.cuh"
 
 #include <cmath>
@@ -47,7 +50,7 @@ static int ensure_work(sb_ctx* ctx, size_t n, size_t count) {
 }
 
 static int ensure_records(sb_ctx* ctx, int64_t hist_cap, int64_t trace_cap) {
-  if (ctx->d_state == nullptr) SB_CUDA(cudaMalloc(&ctx->d_state, sizeof(SolverState)));
+  if (ctx->d_solve == nullptr) SB_CUDA(cudaMalloc(&ctx->d_solve, sizeof(SolveBlock)));
   if (hist_cap > ctx->hist_cap) {
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->d_hist);
@@ -86,16 +89,40 @@ static int check_vector(sb_ctx* ctx, const double* v, int64_t n, const char* wha
   return SB_ERR_INVALID;
 }
 
+int ensure_mega_ctrl(sb_ctx* ctx);                          // sb_mega.cu: also holds the one-GPU mailbox of the folds
+unsigned long long* single_gpu_box(sb_ctx* ctx);            // sb_mega.cu
+unsigned long long* single_gpu_ar_seq(sb_ctx* ctx);         // sb_mega.cu
+
+// End of a folded solve: the mailbox the last fold used is emptied (the one-CTA kernels of the other paths expect
+// empty mailboxes) and the all-reduce sequence number takes the folds of this solve in.
+static __global__ void fold_finish_kernel(SolveBlock* blk, unsigned long long* ar_seq, CommDev comm, unsigned long long* box) {
+  const unsigned long long folds = (unsigned long long) blk->final_.folds;
+  const int world = comm.world > 1 ? comm.world : 1, me = comm.world > 1 ? comm.rank : 0;
+  if (folds > 0 && (int) threadIdx.x < world * 4) {
+    const unsigned long long par = (*ar_seq + folds - 1) & 1ull;
+    st_relaxed_sys(fold_box(comm, box, me, par, threadIdx.x >> 2, threadIdx.x & 3), kArSentinel);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *ar_seq = *ar_seq + folds;
+}
+
 struct Solve {
   sb_ctx* ctx;
   const sb_op* op;
   double* x;
   const double* b;
   int64_t n;
-  Recorder rec;
+  Recorder rec;      // rec.st = version 0 of the state (the one-CTA final stages update it in place)
+  SolveBlock* blk;
   const int* done;
   double *p, *r, *z, *rt, *t, *v;
   std::vector<cudaEvent_t>* prof = nullptr; // profile=1: one event before every kernel + one per iteration end
+  // folded schedule
+  bool folded = false;
+  int ver = 0;              // current version of the state
+  bool pending_end = false; // BiCGStab: the reduction of the last final update has not been consumed yet
+  unsigned long long* tl = nullptr; // optional timeline: [launch ordinal] longest wait (halo flag / other ranks' sums)
+  int64_t tl_cap = 0, tl_pos = 0;
 
   int mark() {
     if (prof != nullptr) {
@@ -106,40 +133,110 @@ struct Solve {
     }
     return SB_OK;
   }
+  unsigned long long* wait_slot() { return (tl != nullptr && tl_pos < tl_cap) ? tl + tl_pos++ : nullptr; }
+  RedPtrs red_set(int k) const {
+    return RedPtrs{ctx->red.partials + (int64_t) k * kMaxDots * ctx->red.cap_tiles, ctx->red.cap_tiles};
+  }
+  bool dist() const { return op->distributed && ctx->comm.world > 1 && ctx->comm.mode == SB_COMM_P2P; }
 
   int init(Kind kind) {
     // r <- b - A x fused with <r,r>  (Operator::Residual, Operator.hpp:95-99)
     EpiResidual epi{b};
     if (kind == Kind::Cg) {
-      SB_TRY((launch_apply<1, true>(ctx, op, x, r, epi, CgInitFinal{rec}, nullptr)));
+      SB_TRY((launch_apply<1, true>(ctx, op, x, r, epi, PublishFinal<CgInitFinal>{CgInitFinal{rec}, blk}, nullptr)));
       SB_TRY((launch_ew<0>(ctx, n, CopyBody{p, r}, NoFinal{}, nullptr))); // p <- r
     } else {
-      SB_TRY((launch_apply<1, true>(ctx, op, x, r, epi, BiInitFinal{rec}, nullptr)));
+      SB_TRY((launch_apply<1, true>(ctx, op, x, r, epi, PublishFinal<BiInitFinal>{BiInitFinal{rec}, blk}, nullptr)));
       SB_TRY((launch_ew<0>(ctx, n, BiInitBody{rt, r}, NoFinal{}, nullptr))); // r~ <- r
     }
     return SB_OK;
   }
 
+  // One kernel of the folded schedule: the element-wise step `body` (ND reductions of its own, into partial set 1)
+  // behind the fold of the reduction in front of it (FND sums from partial set `from_set`; `active` false: none).
+  template<int ND, int FND, class Body, class Final>
+  int launch_fold(const Body& body, const Final& fin, bool active, int from_set, bool after_apply, int64_t rows) {
+    Fold<FND, Final> f;
+    f.n_tiles = active ? num_tiles(n) : -1;
+    f.red = red_set(from_set);
+    f.fin = fin;
+    f.blk = blk, f.in = ver;
+    if (dist()) {
+      f.comm = ctx->comm;
+      f.ar_base = &ctx->comm.ctrl(ctx->comm.rank)->ar_seq;
+      if (after_apply && !(ctx->debug & 2)) f.bump = ctx->comm.ctrl(ctx->comm.rank);
+    } else {
+      f.comm.world = 1;
+      f.box = single_gpu_box(ctx), f.ar_base = single_gpu_ar_seq(ctx);
+    }
+    f.wait_ns = wait_slot(); // one word per kernel slot, folding or not: the timeline stays aligned with the slots
+    const unsigned grid = (unsigned) std::max<int64_t>(1, num_tiles(rows));
+    SB_CUDA(launch_kernel(ctx, ew_fold_kernel<ND, Body, FND, Final>, grid, kThreads, 0, rows, body, red_set(1), done, f));
+    ctx->launches++;
+    if (active) ver ^= 1;
+    return SB_OK;
+  }
+
+  int iterate_folded(Kind kind) {
+    if (kind == Kind::Cg) {
+      SB_TRY(mark());
+      SB_TRY((launch_apply<1, false>(ctx, op, p, z, EpiXY{}, NoFinal{}, done, nullptr, true, wait_slot())));
+      SB_TRY(mark());
+      SB_TRY((launch_fold<1, 1>(CgUpdateBody{nullptr, x, r, p, z}, CgAlphaFinal{rec}, true, 0, true, n)));
+      SB_TRY(mark());
+      SB_TRY((launch_fold<0, 1>(CgDirectionBody{nullptr, p, r}, CgBetaFinal{rec}, true, 1, false, n)));
+    } else {
+      SB_TRY(mark());
+      SB_TRY((launch_fold<0, 2>(BiDirectionBody{nullptr, p, r, v}, BiEndFinal{rec}, pending_end, 1, false, n)));
+      SB_TRY(mark());
+      SB_TRY((launch_apply<1, false>(ctx, op, p, v, EpiUY{rt}, NoFinal{}, done, nullptr, true, wait_slot())));
+      SB_TRY(mark());
+      SB_TRY((launch_fold<0, 1>(BiHalfBody{nullptr, r, v}, BiAlphaFinal{rec}, true, 0, true, n)));
+      SB_TRY(mark());
+      SB_TRY((launch_apply<2, false>(ctx, op, r, t, EpiYYandYX{}, NoFinal{}, done, nullptr, true, wait_slot())));
+      SB_TRY(mark());
+      SB_TRY((launch_fold<2, 2>(BiEndBody{nullptr, x, r, p, t, rt}, BiOmegaFinal{rec}, true, 0, true, n)));
+      pending_end = true;
+    }
+    SB_TRY(mark());
+    return SB_OK;
+  }
+
+  // After the last iteration: consume what is still pending (BiCGStab's last <r,r>, <r~,r>), then close the fold
+  // sequence of this solve.
+  int finish_folded(Kind kind) {
+    if (kind == Kind::BiCgStab && pending_end)
+      SB_TRY((launch_fold<0, 2>(BiDirectionBody{nullptr, p, r, v}, BiEndFinal{rec}, true, 1, false, 0)));
+    CommDev comm{};
+    comm.world = 1;
+    unsigned long long* ar = single_gpu_ar_seq(ctx);
+    if (dist()) comm = ctx->comm, ar = &ctx->comm.ctrl(ctx->comm.rank)->ar_seq;
+    SB_CUDA(launch_kernel(ctx, fold_finish_kernel, 1, 64, 0, blk, ar, comm, single_gpu_box(ctx)));
+    ctx->launches++;
+    return SB_OK;
+  }
+
   int iterate(Kind kind) {
+    if (folded) return iterate_folded(kind);
     const SolverState* st = rec.st;
     if (kind == Kind::Cg) {
       SB_TRY(mark());
-      SB_TRY((launch_apply<1, false>(ctx, op, p, z, EpiXY{}, CgAlphaFinal{rec}, done)));
+      SB_TRY((launch_apply<1, false>(ctx, op, p, z, EpiXY{}, PublishFinal<CgAlphaFinal>{CgAlphaFinal{rec}, blk}, done)));
       SB_TRY(mark());
-      SB_TRY((launch_ew<1>(ctx, n, CgUpdateBody{st, x, r, p, z}, CgBetaFinal{rec}, done)));
+      SB_TRY((launch_ew<1>(ctx, n, CgUpdateBody{st, x, r, p, z}, PublishFinal<CgBetaFinal>{CgBetaFinal{rec}, blk}, done)));
       SB_TRY(mark());
       SB_TRY((launch_ew<0>(ctx, n, CgDirectionBody{st, p, r}, NoFinal{}, done)));
     } else {
       SB_TRY(mark());
       SB_TRY((launch_ew<0>(ctx, n, BiDirectionBody{st, p, r, v}, NoFinal{}, done)));
       SB_TRY(mark());
-      SB_TRY((launch_apply<1, false>(ctx, op, p, v, EpiUY{rt}, BiAlphaFinal{rec}, done)));
+      SB_TRY((launch_apply<1, false>(ctx, op, p, v, EpiUY{rt}, PublishFinal<BiAlphaFinal>{BiAlphaFinal{rec}, blk}, done)));
       SB_TRY(mark());
       SB_TRY((launch_ew<0>(ctx, n, BiHalfBody{st, r, v}, NoFinal{}, done)));
       SB_TRY(mark());
-      SB_TRY((launch_apply<2, false>(ctx, op, r, t, EpiYYandYX{}, BiOmegaFinal{rec}, done)));
+      SB_TRY((launch_apply<2, false>(ctx, op, r, t, EpiYYandYX{}, PublishFinal<BiOmegaFinal>{BiOmegaFinal{rec}, blk}, done)));
       SB_TRY(mark());
-      SB_TRY((launch_ew<2>(ctx, n, BiEndBody{st, x, r, p, t, rt}, BiEndFinal{rec}, done)));
+      SB_TRY((launch_ew<2>(ctx, n, BiEndBody{st, x, r, p, t, rt}, PublishFinal<BiEndFinal>{BiEndFinal{rec}, blk}, done)));
     }
     SB_TRY(mark());
     return SB_OK;
@@ -181,26 +278,30 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   SB_TRY(ensure_records(ctx, h_hist ? hist_cap : 0, h_trace ? trace_cap : 0));
   SB_TRY(ensure_red_scratch(ctx, n));
   const bool profile = opts->profile != 0 && !opts->use_graph;
-  // Schedule: the persistent whole-solve kernel unless the caller asks for per-kernel timing or for the stepwise one.
-  bool persistent = opts->schedule != SB_SCHEDULE_STEPWISE && !profile && mega_supported(ctx, op);
+  // Schedule: stepwise (one kernel per step, reductions folded into their consumers, graph replay) unless the caller
+  // asks for the persistent whole-solve kernel. Measured on the B200 (profiles/r02_persistent_*.json):
+  // a grid-wide barrier in global memory costs 5-7 us (the arriving CTA must first drain its stores), a kernel
+  // boundary inside a replayed graph 2.7 us, so five launches per BiCGStab iteration beat five barriers at every size.
+  bool persistent = opts->schedule == SB_SCHEDULE_PERSISTENT && !profile && mega_supported(ctx, op);
   if (opts->schedule == SB_SCHEDULE_PERSISTENT && !persistent) {
     set_error("the persistent schedule needs a coefficient-form operator (blocked layout), no per-kernel profile, and "
               "in-kernel (P2P) collectives");
     return SB_ERR_INVALID;
   }
 
-  SolverState h{};
+  SolveBlock* pinned_blk = reinterpret_cast<SolveBlock*>(ctx->h_pinned);
+  *pinned_blk = SolveBlock{};
+  SolverState& h = pinned_blk->ver[0];
   h.abs_tol = opts->abs_tol, h.rel_tol = opts->rel_tol;
   h.max_iter = opts->num_iterations;
   h.hist_cap = h_hist ? hist_cap : 0, h.trace_cap = h_trace ? trace_cap : 0;
-  SolverState* pinned_state = reinterpret_cast<SolverState*>(ctx->h_pinned);
-  *pinned_state = h;
-  SB_CUDA(cudaMemcpyAsync(ctx->d_state, pinned_state, sizeof(SolverState), cudaMemcpyHostToDevice, ctx->stream));
+  SB_CUDA(cudaMemcpyAsync(ctx->d_solve, pinned_blk, sizeof(SolveBlock), cudaMemcpyHostToDevice, ctx->stream));
 
   Solve S;
   S.ctx = ctx, S.op = op, S.x = x, S.b = b, S.n = n;
-  S.rec = Recorder{ctx->d_state, h_hist ? ctx->d_hist : nullptr, h_trace ? ctx->d_trace : nullptr};
-  S.done = &ctx->d_state->done;
+  S.blk = ctx->d_solve;
+  S.rec = Recorder{&ctx->d_solve->ver[0], h_hist ? ctx->d_hist : nullptr, h_trace ? ctx->d_trace : nullptr};
+  S.done = &ctx->d_solve->done;
   S.p = ctx->work[0], S.r = ctx->work[1];
   S.z = S.rt = S.t = S.v = nullptr;
   if (kind == Kind::Cg) {
@@ -208,6 +309,11 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   } else {
     S.rt = ctx->work[2], S.t = ctx->work[3], S.v = ctx->work[4];
   }
+  // The reductions are folded into their consumers wherever the all-reduce can run inside a kernel (one GPU, or
+  // peer-memory collectives over a distributed operator); NCCL mode keeps the one-CTA final stages.
+  S.folded = !persistent && !(ctx->debug & 4) &&
+             (ctx->comm.world <= 1 || (ctx->comm.mode == SB_COMM_P2P && op->distributed));
+  if (S.folded) SB_TRY(ensure_mega_ctrl(ctx));
   SolveGuard guard;
   const int64_t launches0 = ctx->launches;
   SB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -216,8 +322,20 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   SB_TRY(guard.make(&ev_mid));
   SB_CUDA(cudaEventRecord(ev_mid, ctx->stream));
   std::vector<cudaEvent_t>& prof_events = guard.events; // profile events are appended behind ev_mid / evs
-  const int per_iter = (kind == Kind::Cg) ? 3 : 5;       // profiled kernel slots (each includes its final stage)
+  const int per_iter = (kind == Kind::Cg) ? 3 : 5;       // profiled kernel slots
   size_t prof_first = 0;
+  const int64_t tl_words = (profile && S.folded) ? (int64_t) per_iter * opts->num_iterations : 0;
+  if (tl_words > 0) { // in-kernel waits of the profiled run: one word per kernel slot and iteration
+    if (tl_words > ctx->timeline_cap) {
+      SB_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_timeline);
+      ctx->d_timeline = nullptr, ctx->timeline_cap = 0;
+      SB_CUDA(cudaMalloc(&ctx->d_timeline, sizeof(unsigned long long) * tl_words));
+      ctx->timeline_cap = tl_words;
+    }
+    SB_CUDA(cudaMemsetAsync(ctx->d_timeline, 0, sizeof(unsigned long long) * tl_words, ctx->stream));
+    S.tl = ctx->d_timeline, S.tl_cap = tl_words;
+  }
 
   if (persistent) {
     // ONE cooperative launch runs the whole iteration loop (sb_mega.cuh); the stop rule is evaluated on the device
@@ -225,25 +343,36 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
       MegaLaunch L{};
       L.kind = kind, L.x = x, L.r = S.r, L.p = S.p;
       L.v = kind == Kind::Cg ? S.z : S.v, L.t = S.t, L.rt = S.rt;
-      L.st = ctx->d_state, L.hist = S.rec.hist, L.trace = S.rec.trace;
+      L.blk = ctx->d_solve, L.hist = S.rec.hist, L.trace = S.rec.trace;
       L.timeline_iters = opts->timeline_iters;
       SB_TRY(launch_mega(ctx, op, L));
     }
   } else {
-    // One captured graph per iteration: the kernel arguments never change (scalars are read from the
-    // device state), so the same graph is replayed; this removes the per-kernel launch cost that
-    // matters once a rank holds ~1 M cells.
+    // Graph replay: the kernel arguments never change (scalars are read from the device state), so one captured
+    // graph is replayed; this removes the per-kernel launch cost that matters once a rank holds ~1 M cells. The
+    // folded schedule bakes the state version into the arguments: the graph spans an even number of folds -- two
+    // BiCGStab iterations (3 folds each; the first iteration, which has no reduction in front of it, runs outside
+    // the graph) or one CG iteration (2 folds). Iterations queued beyond the stopping one are no-ops.
+    const int its_per_graph = (S.folded && kind == Kind::BiCgStab) ? 2 : 1;
+    int64_t it = 0;
     if (opts->use_graph && opts->num_iterations > 0) {
-      SB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-      const int64_t before = ctx->launches;
-      const int rc = S.iterate(kind);
-      cudaError_t ce = cudaStreamEndCapture(ctx->stream, &guard.graph);
-      ctx->launches = before;
-      if (rc != SB_OK) return rc;
-      SB_CUDA(ce);
-      SB_CUDA(cudaGraphInstantiate(&guard.graph_exec, guard.graph, 0));
+      if (its_per_graph == 2) {
+        SB_TRY(S.iterate(kind));
+        it = 1;
+      }
+      if (it < opts->num_iterations) {
+        SB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        const int64_t before = ctx->launches;
+        int rc = SB_OK;
+        for (int k = 0; k < its_per_graph && rc == SB_OK; ++k) rc = S.iterate(kind);
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &guard.graph);
+        ctx->launches = before;
+        if (rc != SB_OK) return rc;
+        SB_CUDA(ce);
+        SB_CUDA(cudaGraphInstantiate(&guard.graph_exec, guard.graph, 0));
+      }
     }
-    const int launches_per_iter = (kind == Kind::Cg) ? 5 : 8; // + one-CTA final-reduce launches
+    const int launches_per_iter = S.folded ? per_iter : ((kind == Kind::Cg) ? 5 : 8); // unfolded: + one-CTA final stages
 
     // Convergence polling: a flag copy is queued every `check` iterations and examined one batch later,
     // so the host never drains the stream while it still has work to enqueue.
@@ -254,22 +383,23 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
     SB_TRY(guard.make(&evs[0], cudaEventDisableTiming));
     SB_TRY(guard.make(&evs[1], cudaEventDisableTiming));
     prof_first = guard.events.size();
-    int64_t it = 0;
     int slot = 0;
     bool pending[2] = {false, false};
     bool stop = false;
     while (it < opts->num_iterations && !stop) {
       const int64_t batch_end = std::min<int64_t>(it + check, opts->num_iterations);
-      for (; it < batch_end; ++it) {
+      while (it < batch_end) {
         if (guard.graph_exec != nullptr) {
           SB_CUDA(cudaGraphLaunch(guard.graph_exec, ctx->stream));
-          ctx->launches += launches_per_iter;
+          ctx->launches += launches_per_iter * its_per_graph;
+          it += its_per_graph;
         } else {
           if (profile) S.prof = &prof_events;
           SB_TRY(S.iterate(kind));
+          ++it;
         }
       }
-      SB_CUDA(cudaMemcpyAsync(&h_flags[slot], &ctx->d_state->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      SB_CUDA(cudaMemcpyAsync(&h_flags[slot], &ctx->d_solve->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
       SB_CUDA(cudaEventRecord(evs[slot], ctx->stream));
       pending[slot] = true;
       const int prev = slot ^ 1;
@@ -280,11 +410,15 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
       }
       slot ^= 1;
     }
+    S.prof = nullptr;
+    if (S.folded) SB_TRY(S.finish_folded(kind));
   }
   SB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-  SB_CUDA(cudaMemcpyAsync(pinned_state, ctx->d_state, sizeof(SolverState), cudaMemcpyDeviceToHost, ctx->stream));
+  SB_CUDA(cudaMemcpyAsync(pinned_blk, ctx->d_solve, sizeof(SolveBlock), cudaMemcpyDeviceToHost, ctx->stream));
   SB_CUDA(cudaStreamSynchronize(ctx->stream));
-  const SolverState out = *pinned_state;
+  // the state at the moment the stopping rule fired; a solve always ends with the flag set (tolerance met, or the
+  // iteration count reached num_iterations)
+  const SolverState out = pinned_blk->done ? pinned_blk->final_ : pinned_blk->ver[S.ver];
   float ms = 0.f, ms_iter = 0.f;
   SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   SB_CUDA(cudaEventElapsedTime(&ms_iter, ev_mid, ctx->ev1));
@@ -292,6 +426,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   report->n_kernel_slots = persistent ? 0 : per_iter;
   report->schedule = persistent ? SB_SCHEDULE_PERSISTENT : SB_SCHEDULE_STEPWISE;
   for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->kernel_ms[k] = 0.0;
+  for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->wait_ms[k] = 0.0;
   if (profile && !persistent) {
     // events come in groups of per_iter + 1 per iteration
     const size_t group = (size_t) per_iter + 1;
@@ -301,6 +436,11 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
         cudaEventElapsedTime(&dt, prof_events[g + k], prof_events[g + k + 1]);
         report->kernel_ms[k] += dt;
       }
+    if (tl_words > 0) { // longest in-kernel wait per launch, summed per slot
+      std::vector<unsigned long long> tl((size_t) tl_words);
+      SB_CUDA(cudaMemcpy(tl.data(), ctx->d_timeline, sizeof(unsigned long long) * tl_words, cudaMemcpyDeviceToHost));
+      for (int64_t q = 0; q < S.tl_pos && q < tl_words; ++q) report->wait_ms[q % per_iter] += 1e-6 * (double) tl[(size_t) q];
+    }
   }
   // a device-side spin wait that gave up (lost peer, rank skew beyond SB_SPIN_TIMEOUT_S): values are meaningless
   unsigned long long fail = 0;

@@ -321,6 +321,7 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
             phases["us_per_iteration_max_over_ranks"] = max_over_ranks(phases["us_per_iteration"])
     sp, _ = solve(args.steps, profile=True)
     kms = [max_over_ranks(v) for v in sp.kernel_ms]
+    wms = [max_over_ranks(v) for v in sp.wait_ms]
     xg = gather_global(loc, x.numpy(), mesh.n_cells)
     err = float(np.linalg.norm(xg - x_star) / np.linalg.norm(x_star))
 
@@ -375,7 +376,11 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
                                    "frac_of_nominal_8TBs": alg_iter * value / (8e12 * world)},
             "phases": phases,
             "stepwise": {"kernel_ms_per_iteration": {nm: kms[k] / args.steps for k, nm in enumerate(slots)},
-                         "apply_avg_launch_ms": apply_ms},
+                         "in_kernel_wait_ms_per_iteration": {nm: wms[k] / args.steps for k, nm in enumerate(slots)},
+                         "apply_avg_launch_ms": apply_ms,
+                         "note": "profiled run (events around every launch, no graph), maxima over the ranks; waits: apply "
+                                 "slots = a boundary CTA waiting for a neighbour's halo values, other slots = CTA 0 "
+                                 "waiting for the other ranks' partial sums of the reduction it folds"},
             "applies_per_sec": applies_per_it * value,
             "cpu_baseline": None,
             "e2e": {"value": args.steps / e2e_s, "unit": "it/s", "h2d_bytes_per_step": 16 * n_glob / args.steps,

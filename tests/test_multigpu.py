@@ -40,6 +40,23 @@ def _gpu_count():
 
 
 @pytest.mark.gpu
+def test_distributed_solvers_bit_exact_two_ranks_sharing_one_gpu():
+    """World size 2 on whatever is there -- on a one-GPU box both ranks map to device 0 (multigpu.local_device): their
+    kernels are time-sliced, every peer wait costs a time slice instead of an NVLink round trip, but the protocol
+    (CUDA-IPC peer mapping, halo pushes, sequence flags, mailbox all-reduce, folded reductions, the persistent kernel's
+    grid barriers) is exactly the one that runs with a GPU per rank, and the results are bit-exact against the oracle."""
+    env_backup = os.environ.get("SB_SPIN_TIMEOUT_S")
+    os.environ["SB_SPIN_TIMEOUT_S"] = "60"
+    try:
+        launch(2, "p2p", timeout=900)
+    finally:
+        if env_backup is None:
+            os.environ.pop("SB_SPIN_TIMEOUT_S", None)
+        else:
+            os.environ["SB_SPIN_TIMEOUT_S"] = env_backup
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["p2p", "nccl"])
 def test_distributed_solvers_bit_exact_two_gpus(mode):
     if _gpu_count() < 2:
