@@ -29,7 +29,8 @@ PRE_SIDES = {"left": 0, "right": 1, "symmetric": 2}
 class Opts(C.Structure):      # dropin_opts of stormruler_b200/host/dropin.cpp
     _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
                 ("num_inner_iterations", C.c_int64), ("relaxation_factor", C.c_double),
-                ("use_graph", C.c_int32), ("precond", C.c_int32), ("pre_side", C.c_int32)]
+                ("use_graph", C.c_int32), ("precond", C.c_int32), ("pre_side", C.c_int32),
+                ("cheb_degree", C.c_int32), ("cheb_power_iterations", C.c_int32), ("cheb_eig_ratio", C.c_double)]
 
 
 class Report(C.Structure):
@@ -127,7 +128,7 @@ def _p(a):
 
 def solve(name: str, op: EmuOp, b, x0=None, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6, num_inner=0,
           relaxation_factor=0.0, mode=orc.RED_SEQ, precond=None, pre_side="right", reset_rng=True,
-          trace_cap=None) -> orc.SolveResult:
+          trace_cap=None, cheb_degree=0, cheb_power_iterations=0, cheb_eig_ratio=0.0) -> orc.SolveResult:
     """dropin_solve on the emulator: the reference template `name` on Storm::DeviceVector, host-executed."""
     em, dr = _load()
     em.emu_set_reduction_mode(mode)
@@ -140,7 +141,8 @@ def solve(name: str, op: EmuOp, b, x0=None, num_iterations=2000, abs_tol=1e-6, r
     cap_h, cap_t = num_iterations + 2, trace_cap or (64 * num_iterations + 256)
     hist, trace = np.zeros(cap_h), np.zeros(cap_t)
     opts = Opts(num_iterations, abs_tol, rel_tol, num_inner, relaxation_factor, 0,
-                {None: 0, "jacobi": 1, "identity": 2}[precond], PRE_SIDES[pre_side])
+                {None: 0, "jacobi": 1, "identity": 2, "chebyshev": 3}[precond], PRE_SIDES[pre_side], int(cheb_degree),
+                int(cheb_power_iterations), float(cheb_eig_ratio))
     rep = Report()
     rc = dr.dropin_solve(name.encode(), em.emu_ctx(), op.handle, _p(x), _p(b), n, C.byref(opts), C.byref(rep),
                          hist.ctypes.data_as(orc._f64p), cap_h, trace.ctypes.data_as(orc._f64p), cap_t)
@@ -188,7 +190,7 @@ def solve_non_uniform(name: str, op: EmuOp, b, shift, x0=None, num_iterations=20
     x = np.zeros(n) if x0 is None else np.ascontiguousarray(x0, np.float64).copy()
     cap_t = 64 * num_iterations + 256
     trace = np.zeros(cap_t)
-    opts = Opts(num_iterations, abs_tol, rel_tol, 0, 0.0, 0, 0, 1)
+    opts = Opts(num_iterations, abs_tol, rel_tol, 0, 0.0, 0, 0, 1, 0, 0, 0.0)
     rep = Report()
     rc = dr.dropin_solve_non_uniform(name.encode(), em.emu_ctx(), op.handle, _p(x), _p(b), _p(shift), n, C.byref(opts),
                                      C.byref(rep), trace.ctypes.data_as(orc._f64p), cap_t)

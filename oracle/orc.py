@@ -74,7 +74,8 @@ class RefOpts(C.Structure):
     _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
                 ("num_inner_iterations", C.c_int64), ("reduction_mode", C.c_int32),
                 ("relaxation_factor", C.c_double), ("pre_fn", C.c_void_p), ("pre_user", C.c_void_p),
-                ("pre_side", C.c_int32)]
+                ("pre_side", C.c_int32), ("pre_kind", C.c_int32), ("cheb_degree", C.c_int32),
+                ("cheb_power_iterations", C.c_int32), ("cheb_eig_ratio", C.c_double)]
 
 
 class RefReport(C.Structure):
@@ -418,9 +419,12 @@ class JacobiOp:
 
 def ref_solve(solver: str, op, b, x0=None, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6,
               num_inner=0, mode=RED_SEQ, relaxation_factor=0.0, reset_rng=True,
-              trace_cap=None, pre=None, pre_side="right") -> SolveResult:
+              trace_cap=None, pre=None, pre_side="right", cheb_degree=0, cheb_power_iterations=0,
+              cheb_eig_ratio=0.0) -> SolveResult:
     """The reference's own solver headers (oracle/_ref), on a host vector. `pre`: optional operator object
-    with a .callback (e.g. JacobiOp) placed in the reference's pre_op slot; pre_side: left | right | symmetric."""
+    with a .callback (e.g. JacobiOp) placed in the reference's pre_op slot, or the string "chebyshev": the product's
+    Storm::ChebyshevPreconditioner template compiled on the host vector (parameters 0 = class defaults);
+    pre_side: left | right | symmetric."""
     R = ref()
     if reset_rng:
         R.ref_reset_rng()
@@ -430,9 +434,11 @@ def ref_solve(solver: str, op, b, x0=None, num_iterations=2000, abs_tol=1e-6, re
     cap_h = num_iterations + 2
     cap_t = trace_cap or (64 * num_iterations + 256)
     hist, trace = np.zeros(cap_h), np.zeros(cap_t)
-    pf, pu = pre.callback if pre is not None else (None, None)
+    cheb = isinstance(pre, str) and pre == "chebyshev"
+    pf, pu = pre.callback if (pre is not None and not cheb) else (None, None)
     opts = RefOpts(num_iterations, abs_tol, rel_tol, num_inner, mode, relaxation_factor, pf, pu,
-                   {"left": 0, "right": 1, "symmetric": 2}[pre_side])
+                   {"left": 0, "right": 1, "symmetric": 2}[pre_side], 3 if cheb else 0, int(cheb_degree),
+                   int(cheb_power_iterations), float(cheb_eig_ratio))
     rep = RefReport()
     f, u = op.callback
     rc = R.ref_solve(solver.encode(), n, f, u, _p(b, _f64p), _p(x, _f64p), C.byref(opts), C.byref(rep),
@@ -456,7 +462,7 @@ def ref_solve_non_uniform(solver: str, op, b, shift, x0=None, num_iterations=200
     x = np.zeros(n) if x0 is None else _f64(x0).copy()
     cap_t = 64 * num_iterations + 256
     trace = np.zeros(cap_t)
-    opts = RefOpts(num_iterations, abs_tol, rel_tol, 0, mode, 0.0, None, None, 1)
+    opts = RefOpts(num_iterations, abs_tol, rel_tol, 0, mode, 0.0, None, None, 1, 0, 0, 0, 0.0)
     rep = RefReport()
     f, u = op.callback
     rc = R.ref_solve_non_uniform(solver.encode(), n, f, u, _p(b, _f64p), None if shift is None else _p(shift, _f64p),

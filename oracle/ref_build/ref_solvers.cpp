@@ -144,6 +144,10 @@ inline HostVec& fill_randomly(HostVec& out) {
 #include <limits>
 #include <Storm/Solvers/SolverNewton.hpp>
 
+// The product's polynomial preconditioner is a template in the reference's own vector vocabulary: compiled here on the
+// host vector, it is the checker of the very same template on the device vector (bit for bit, same reduction tree).
+#include <Storm/B200/ChebyshevPreconditioner.hpp>
+
 namespace {
 
 using Storm::HostVec;
@@ -159,6 +163,12 @@ struct ref_opts {
   void (*pre_fn)(void* user, double* y, const double* x, size_t n);
   void* pre_user;
   int32_t pre_side;         // 0: Left, 1: Right (reference default), 2: Symmetric
+  // pre_kind 3: Storm::ChebyshevPreconditioner<HostVec> (stormruler_b200/host/Storm/B200/ChebyshevPreconditioner.hpp) in
+  // the pre_op slot instead of the callback; the parameters as in dropin_opts (<= 0: class defaults)
+  int32_t pre_kind;
+  int32_t cheb_degree;
+  int32_t cheb_power_iterations;
+  double cheb_eig_ratio;
 };
 
 struct ref_report {
@@ -213,7 +223,15 @@ int run(size_t n, ref_apply_fn fn, void* user, const double* b, double* x, const
   if constexpr (requires { solver.relaxation_factor; }) {
     if (o->relaxation_factor > 0.0) solver.relaxation_factor = o->relaxation_factor;
   }
-  if (o->pre_fn != nullptr) {
+  if (o->pre_kind == 3) {
+    auto cheb = std::make_unique<Storm::ChebyshevPreconditioner<HostVec>>();
+    if (o->cheb_degree > 0) cheb->degree = (size_t) o->cheb_degree;
+    if (o->cheb_power_iterations > 0) cheb->num_power_iterations = (size_t) o->cheb_power_iterations;
+    if (o->cheb_eig_ratio > 0.0) cheb->eig_ratio = o->cheb_eig_ratio;
+    solver.pre_op = std::move(cheb);
+    solver.pre_side = o->pre_side == 0 ? Storm::PreconditionerSide::Left
+                                       : (o->pre_side == 2 ? Storm::PreconditionerSide::Symmetric : Storm::PreconditionerSide::Right);
+  } else if (o->pre_fn != nullptr) {
     auto pre = std::make_unique<CallbackPreconditioner>();
     pre->fn = o->pre_fn, pre->user = o->pre_user;
     solver.pre_op = std::move(pre);

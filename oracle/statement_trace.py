@@ -42,7 +42,8 @@ READS_TARGET = {1, 2, 3, 4}   # += -= *= /= read y as well
 class Opts(C.Structure):      # dropin_opts of stormruler_b200/host/dropin.cpp
     _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
                 ("num_inner_iterations", C.c_int64), ("relaxation_factor", C.c_double),
-                ("use_graph", C.c_int32), ("precond", C.c_int32), ("pre_side", C.c_int32)]
+                ("use_graph", C.c_int32), ("precond", C.c_int32), ("pre_side", C.c_int32),
+                ("cheb_degree", C.c_int32), ("cheb_power_iterations", C.c_int32), ("cheb_eig_ratio", C.c_double)]
 
 
 class Report(C.Structure):
@@ -82,7 +83,7 @@ def statement_stream(solver: str, iterations: int, precond: int = 0, pre_side: i
     fake_ctx, fake_op = C.c_void_p(0x1000), C.c_void_p(0x2000)
     x = (C.c_double * 2)()      # two distinct addresses for x and b; never dereferenced by the tracer
     b = (C.c_double * 2)()
-    opts = Opts(iterations, 0.0, 0.0, SOLVERS[solver][1], 0.0, 0, precond, pre_side)
+    opts = Opts(iterations, 0.0, 0.0, SOLVERS[solver][1], 0.0, 0, precond, pre_side, 0, 0, 0.0)
     rep = Report()
     rc = dr.dropin_solve(solver.encode(), fake_ctx, fake_op, C.cast(x, C.c_void_p), C.cast(b, C.c_void_p),
                          C.c_size_t(n), C.byref(opts), C.byref(rep), None, C.c_int64(0), None, C.c_int64(0))

@@ -108,4 +108,20 @@ print("   stepwise slots us", {k: round(1e3 * v, 1) for k, v in d["stepwise"]["k
 PY
     done; done
     ;;
+  f)
+    # folded reductions v2 (CTA 0 reduces and raises a flag; the other CTAs only acquire it)
+    export SB_SPIN_TIMEOUT_S=30
+    timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 > "$out/pytest_gpu.log"; tail -8 "$out/pytest_gpu.log"
+    unset SB_SPIN_TIMEOUT_S
+    for ax in 59 84 119; do
+      python bench.py --axis $ax --steps 200 --warmup 20 --no-cpu-baseline > "$out/bench_n1_axis${ax}_auto.json" 2>> "$out/bench.err"
+      python - "$out/bench_n1_axis${ax}_auto.json" <<'PY'
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+o = d["other_solver"]
+print(sys.argv[1], "bicgstab", round(d["value"]), "it/s", round(1e3 * d["ms_per_step"], 1), "us;  cg", round(o["value"]), "it/s", round(1e3 * o["ms_per_step"], 1), "us; launches", d["gpu_launches"])
+print("   stepwise slots us", {k: round(1e3 * v, 1) for k, v in d["stepwise"]["kernel_ms_per_iteration"].items()})
+PY
+    done
+    ;;
 esac

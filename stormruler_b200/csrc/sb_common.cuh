@@ -107,7 +107,6 @@ struct SolverState {
   double abs_tol, rel_tol;
   long long iteration, max_iter;
   long long n_hist, n_trace, hist_cap, trace_cap;
-  long long folds; // reductions of this solve consumed by a folding kernel so far (all-reduce mailbox parity)
   int done, converged;
 };
 
@@ -120,6 +119,8 @@ struct SolveBlock {
   SolverState ver[2];
   SolverState final_;
   int done;
+  int pad[31];
+  int ready[2]; // ready[v] != 0: version v is complete (raised by CTA 0 of the folding kernel that wrote it); a line of its own
 };
 
 struct sb_ctx {

@@ -186,109 +186,63 @@ struct NoFinal {
 // ---- folding a reduction into the kernel that consumes it ----------------------------------------------------------
 // The one-CTA final stage costs a launch per reduction (~2.7 us of boundary + ~3 us of kernel inside a replayed graph:
 // a third of a BiCGStab iteration at 1.26 M cells per rank, profiles/r02_stepwise_unfolded_1M.json). A kernel that
-// needs the reduced scalars can finish the reduction itself instead: CTA 0 runs SB_TREE's final stage over the
-// producer's tile partials and posts the sums into the all-reduce mailbox of every rank (its own included; the single
-// mailbox of a one-GPU context is local); EVERY CTA polls its rank's mailbox, adds the rank sums in rank order and
-// runs the solver's scalar update on a copy of the solver state in shared memory -- identical inputs, identical code,
-// identical bits in all CTAs of all ranks. The copy comes from state version `in`; CTA 0 writes the updated state to
-// version `out` (never the version the other CTAs are reading), publishes the stop (`final_`, `done`) and bumps the
-// apply sequence number when the producer was a distributed apply. The mailbox of fold #a is emptied by CTA 0 of the
-// kernel that handles fold #a+1 (every CTA of the earlier kernel has finished by then), before it posts #a+1.
-struct FoldShared {
-  SolverState st;
-  double s_fin[kMaxDots][kWarps];
-  double s_all[kMaxRanks][4];
-  double s_local[4];
-};
-
+// needs the reduced scalars can finish the reduction itself instead: its CTA 0 does what the one-CTA kernel did --
+// SB_TREE's final stage over the producer's tile partials, the rank-ordered all-reduce over NVLink peer memory, the
+// solver's scalar update -- on a private copy of state version `in`, stores the result as version `in ^ 1` and raises
+// that version's ready flag; every other CTA has its tile's loads in flight by then, acquires the flag (one L2 round
+// trip once it is up) and reads the scalars from the new version. Nobody ever reads a field that is being written:
+// the version a kernel's CTAs read is complete before the flag goes up. CTA 0 also lowers the flag of version `in`
+// (nobody waits for it in this kernel; the next folding kernel will raise it again), publishes the stop (`final_`,
+// `done`) and counts the producer when it was a distributed apply.
+// (A first version let EVERY CTA run the scalar update on a copy in shared memory behind a mailbox: two CTA barriers
+// and three dependent memory round trips per CTA stretched every CTA's lifetime, and the element-wise kernels lost
+// 15-25 % of their bandwidth -- profiles/r02_stepwise_folded_v1_every_cta_waits_*.json.)
 template<int ND, class Final>
 struct Fold {
   int64_t n_tiles = -1;             // tiles of the producer; < 0: nothing to fold (the kernel reads version `in` as it is)
   RedPtrs red{};
-  Final fin{};                      // fin.rec: history / trace buffers (CTA 0 records)
+  Final fin{};                      // fin.rec: history / trace buffers
   SolveBlock* blk = nullptr;
   int32_t in = 0;                   // state version to start from; the result goes to in ^ 1
-  CommDev comm{};                   // world <= 1: one GPU
-  unsigned long long* box = nullptr;             // one GPU: mailbox [2][4]
-  const unsigned long long* ar_base = nullptr;   // all-reduces completed before this solve's folds (mailbox parity)
+  CommDev comm{};                   // mode SB_COMM_P2P and world > 1: all-reduce over the ranks
   CommCtrl* bump = nullptr;         // the producer was a distributed apply: count it
-  unsigned long long* wait_ns = nullptr; // optional: longest wait of CTA 0 for the other ranks' sums (atomicMax)
+  unsigned long long* wait_ns = nullptr; // optional: how long CTA 0 waited for the other ranks' sums
 };
 
-__device__ __forceinline__ unsigned long long* fold_box(const CommDev& comm, unsigned long long* box, int rank, unsigned long long par,
-                                                        int src, int d) {
-  if (comm.world > 1) return &comm.ctrl(rank)->ar_slot[par][src][d];
-  return box + par * 4 + d;
+// CTA 0 of a folding kernel, all threads.
+template<int ND, class Final>
+__device__ __forceinline__ void fold_reduce(const Fold<ND, Final>& f) {
+  __shared__ double s_fin[kMaxDots][kWarps];
+  if (threadIdx.x == 0) f.blk->ready[f.in] = 0; // nobody waits for it during this kernel
+  double sums[ND];
+  final_stage<ND>(f.n_tiles, f.red, s_fin, sums);
+  if (f.comm.mode == SB_COMM_P2P && f.comm.world > 1) {
+    const unsigned long long t0 = (f.wait_ns != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0;
+    allreduce_p2p<ND>(f.comm, sums);
+    if (f.wait_ns != nullptr && threadIdx.x == 0) *f.wait_ns = globaltimer_ns() - t0;
+  }
+  if (threadIdx.x == 0) {
+    SolverState st = f.blk->ver[f.in];
+    Final fin = f.fin;
+    fin.rec.st = &st;
+    fin(sums);
+    f.blk->ver[f.in ^ 1] = st;
+    if (st.done) f.blk->final_ = st, f.blk->done = 1;
+    if (f.bump != nullptr) f.bump->apply_seq = f.bump->apply_seq + 1; // the distributed apply in front of me is complete
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&f.blk->ready[f.in ^ 1]), "r"(1) : "memory");
+  }
 }
 
-// All threads of a folding kernel. On return sh.st is the updated state (valid for every thread).
-template<int ND, class Final>
-__device__ __forceinline__ void fold_prologue(const Fold<ND, Final>& f, FoldShared& sh) {
-  const int world = f.comm.world > 1 ? f.comm.world : 1, me = f.comm.world > 1 ? f.comm.rank : 0;
-  const SolverState* in = &f.blk->ver[f.in];
-  const unsigned long long par = (*f.ar_base + (unsigned long long) in->folds) & 1ull;
-  if (threadIdx.x == 0) sh.st = *in;
-  if (blockIdx.x == 0) {
-    if (threadIdx.x < world * 4) { // empty the mailbox of the previous fold BEFORE my sums go out
-      const int r = threadIdx.x >> 2, d = threadIdx.x & 3;
-      st_relaxed_sys(fold_box(f.comm, f.box, me, par ^ 1ull, r, d), kArSentinel);
-    }
-    double sums[ND];
-    final_stage<ND>(f.n_tiles, f.red, sh.s_fin, sums);
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int d = 0; d < ND; ++d) sh.s_local[d] = sums[d];
-      if (world > 1) __threadfence_system(); // the reset above is performed before any peer can answer what goes out below
-      else __threadfence();
-      if (f.bump != nullptr) f.bump->apply_seq = f.bump->apply_seq + 1; // the distributed apply in front of me is complete
-    }
-    __syncthreads();
-    if (threadIdx.x < world * ND) {
-      const int r = threadIdx.x / ND, d = threadIdx.x % ND;
-      st_relaxed_sys(fold_box(f.comm, f.box, r, par, me, d), (unsigned long long) __double_as_longlong(sh.s_local[d]));
-    }
+// Every other CTA: wait until the new version is complete (lane 0 of each warp acquires, the warp follows).
+__device__ __forceinline__ void fold_wait(const int* ready) {
+  if ((threadIdx.x & 31) == 0) {
+    int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
+    } while (v == 0);
   }
-  if (threadIdx.x < world * ND) {
-    const int r = threadIdx.x / ND, d = threadIdx.x % ND;
-    const unsigned long long* box = fold_box(f.comm, f.box, me, par, r, d);
-    unsigned long long v = ld_relaxed_sys(box);
-    if (v == kArSentinel) {
-      CommCtrl* ctl = f.comm.world > 1 ? f.comm.ctrl(me) : nullptr;
-      const unsigned long long t0 = globaltimer_ns(), limit = f.comm.world > 1 ? f.comm.timeout_ns : kDefaultSpinTimeoutNs;
-      unsigned spins = 0;
-      while ((v = ld_relaxed_sys(box)) == kArSentinel) {
-        if ((++spins & 63u) == 0 && (globaltimer_ns() - t0 > limit || (ctl != nullptr && comm_failed(ctl)))) {
-          if (ctl != nullptr) comm_fail(ctl, 0xC000 + r);
-          break;
-        }
-      }
-      if (f.wait_ns != nullptr && blockIdx.x == 0) atomicMax(f.wait_ns, globaltimer_ns() - t0);
-    }
-    sh.s_all[r][d] = __longlong_as_double((long long) v);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double tot[ND];
-#pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      double t = sh.s_all[0][d];
-      for (int r = 1; r < world; ++r) t = __dadd_rn(t, sh.s_all[r][d]);
-      tot[d] = t;
-    }
-    Final fin = f.fin;
-    fin.rec.st = &sh.st;
-    if (blockIdx.x != 0) fin.rec.hist = nullptr, fin.rec.trace = nullptr;
-    fin(tot);
-    sh.st.folds++;
-    if (blockIdx.x == 0) {
-      f.blk->ver[f.in ^ 1] = sh.st;
-      if (sh.st.done) {
-        f.blk->final_ = sh.st;
-        f.blk->done = 1;
-      }
-    }
-  }
-  __syncthreads();
+  __syncwarp();
 }
 
 // Generic tiled element-wise kernel. Body provides
@@ -312,14 +266,13 @@ __global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, Body body, RedP
   if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, blockIdx.x);
 }
 
-// The same kernel in front of which a reduction is folded (fold_prologue): the tile's loads are issued first, so the
-// final stage, the mailbox round trip and the scalar update run under their latency; the body then reads the solver
-// scalars from the CTA's own copy of the state (Body::st is redirected to it). One extra CTA beyond the tiles is never
-// needed: a fold without tiles (the flush at the end of a solve) is launched with n = 0 and one CTA.
+// The same kernel in front of which a reduction is folded (fold_reduce / fold_wait): the tile's loads are issued
+// first, so the fold runs under their latency; the body then reads the solver scalars from the new state version
+// (Body::st is redirected to it). A fold without tiles (the flush at the end of a BiCGStab solve) is launched with
+// n = 0 and one CTA.
 template<int ND, class Body, int FND, class Final>
 __global__ void __launch_bounds__(kThreads) ew_fold_kernel(int64_t n, Body body, RedPtrs red, const int* __restrict__ done,
                                                            Fold<FND, Final> fold) {
-  __shared__ FoldShared sh;
   if (is_done(done)) return;
   const bool tile = (int64_t) blockIdx.x * kTile < n;
   typename Body::Regs r[kSub];
@@ -327,14 +280,18 @@ __global__ void __launch_bounds__(kThreads) ew_fold_kernel(int64_t n, Body body,
 #pragma unroll
     for (int j = 0; j < kSub; ++j) body.load(lane_elem(blockIdx.x, j), r[j]);
   }
+  const SolverState* st = &fold.blk->ver[fold.in];
   if (fold.n_tiles >= 0) {
-    fold_prologue(fold, sh);
-  } else {
-    if (threadIdx.x == 0) sh.st = fold.blk->ver[fold.in];
-    __syncthreads();
+    st = &fold.blk->ver[fold.in ^ 1];
+    if (blockIdx.x == 0) {
+      fold_reduce(fold);
+      __syncthreads();
+    } else {
+      fold_wait(&fold.blk->ready[fold.in ^ 1]);
+    }
   }
-  if (sh.st.done || !tile) return; // the stopping rule has just fired: the iterate stays what it is
-  body.st = &sh.st;
+  if (!tile || __ldcg(&st->done) != 0) return; // the stopping rule has just fired: the iterate stays what it is
+  body.st = st;
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
   for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;

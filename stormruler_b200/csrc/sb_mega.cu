@@ -11,10 +11,7 @@ static __global__ void mega_ctrl_init_kernel(MegaCtrl* mc) {
   if (threadIdx.x < 8) (&mc->box[0][0])[threadIdx.x] = kArSentinel;
 }
 
-unsigned long long* single_gpu_box(sb_ctx* ctx) { return &ctx->d_mega->box[0][0]; }
-unsigned long long* single_gpu_ar_seq(sb_ctx* ctx) { return &ctx->d_mega->ar_seq; }
-
-int ensure_mega_ctrl(sb_ctx* ctx) {
+static int ensure_mega_ctrl(sb_ctx* ctx) {
   if (ctx->d_mega != nullptr) return SB_OK;
   SB_CUDA(cudaMalloc(&ctx->d_mega, sizeof(MegaCtrl)));
   SB_CUDA(cudaMemsetAsync(ctx->d_mega, 0, sizeof(MegaCtrl), ctx->stream));

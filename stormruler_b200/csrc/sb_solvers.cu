@@ -89,23 +89,6 @@ static int check_vector(sb_ctx* ctx, const double* v, int64_t n, const char* wha
   return SB_ERR_INVALID;
 }
 
-int ensure_mega_ctrl(sb_ctx* ctx);                          // sb_mega.cu: also holds the one-GPU mailbox of the folds
-unsigned long long* single_gpu_box(sb_ctx* ctx);            // sb_mega.cu
-unsigned long long* single_gpu_ar_seq(sb_ctx* ctx);         // sb_mega.cu
-
-// End of a folded solve: the mailbox the last fold used is emptied (the one-CTA kernels of the other paths expect
-// empty mailboxes) and the all-reduce sequence number takes the folds of this solve in.
-static __global__ void fold_finish_kernel(SolveBlock* blk, unsigned long long* ar_seq, CommDev comm, unsigned long long* box) {
-  const unsigned long long folds = (unsigned long long) blk->final_.folds;
-  const int world = comm.world > 1 ? comm.world : 1, me = comm.world > 1 ? comm.rank : 0;
-  if (folds > 0 && (int) threadIdx.x < world * 4) {
-    const unsigned long long par = (*ar_seq + folds - 1) & 1ull;
-    st_relaxed_sys(fold_box(comm, box, me, par, threadIdx.x >> 2, threadIdx.x & 3), kArSentinel);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) *ar_seq = *ar_seq + folds;
-}
-
 struct Solve {
   sb_ctx* ctx;
   const sb_op* op;
@@ -163,11 +146,7 @@ struct Solve {
     f.blk = blk, f.in = ver;
     if (dist()) {
       f.comm = ctx->comm;
-      f.ar_base = &ctx->comm.ctrl(ctx->comm.rank)->ar_seq;
       if (after_apply && !(ctx->debug & 2)) f.bump = ctx->comm.ctrl(ctx->comm.rank);
-    } else {
-      f.comm.world = 1;
-      f.box = single_gpu_box(ctx), f.ar_base = single_gpu_ar_seq(ctx);
     }
     f.wait_ns = wait_slot(); // one word per kernel slot, folding or not: the timeline stays aligned with the slots
     const unsigned grid = (unsigned) std::max<int64_t>(1, num_tiles(rows));
@@ -202,17 +181,10 @@ struct Solve {
     return SB_OK;
   }
 
-  // After the last iteration: consume what is still pending (BiCGStab's last <r,r>, <r~,r>), then close the fold
-  // sequence of this solve.
+  // After the last iteration: consume what is still pending (BiCGStab's last <r,r>, <r~,r>).
   int finish_folded(Kind kind) {
     if (kind == Kind::BiCgStab && pending_end)
       SB_TRY((launch_fold<0, 2>(BiDirectionBody{nullptr, p, r, v}, BiEndFinal{rec}, true, 1, false, 0)));
-    CommDev comm{};
-    comm.world = 1;
-    unsigned long long* ar = single_gpu_ar_seq(ctx);
-    if (dist()) comm = ctx->comm, ar = &ctx->comm.ctrl(ctx->comm.rank)->ar_seq;
-    SB_CUDA(launch_kernel(ctx, fold_finish_kernel, 1, 64, 0, blk, ar, comm, single_gpu_box(ctx)));
-    ctx->launches++;
     return SB_OK;
   }
 
@@ -313,7 +285,6 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   // peer-memory collectives over a distributed operator); NCCL mode keeps the one-CTA final stages.
   S.folded = !persistent && !(ctx->debug & 4) &&
              (ctx->comm.world <= 1 || (ctx->comm.mode == SB_COMM_P2P && op->distributed));
-  if (S.folded) SB_TRY(ensure_mega_ctrl(ctx));
   SolveGuard guard;
   const int64_t launches0 = ctx->launches;
   SB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));

@@ -25,7 +25,8 @@ GROUPED_SOLVERS = {"grouped_idrs": "idrs", "grouped_bicgstabl": "bicgstabl"}
 class Opts(C.Structure):
     _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
                 ("num_inner_iterations", C.c_int64), ("relaxation_factor", C.c_double),
-                ("use_graph", C.c_int32), ("precond", C.c_int32), ("pre_side", C.c_int32)]
+                ("use_graph", C.c_int32), ("precond", C.c_int32), ("pre_side", C.c_int32),
+                ("cheb_degree", C.c_int32), ("cheb_power_iterations", C.c_int32), ("cheb_eig_ratio", C.c_double)]
 
 
 class Report(C.Structure):
@@ -95,9 +96,11 @@ PRE_SIDES = {"left": 0, "right": 1, "symmetric": 2}
 
 def solve(name: str, op, x, b, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6, num_inner=0,
           relaxation_factor=0.0, use_graph=True, reset_rng=True, trace_cap=None, precond=None,
-          pre_side="right") -> Result:
+          pre_side="right", cheb_degree=0, cheb_power_iterations=0, cheb_eig_ratio=0.0) -> Result:
     """Run solver `name` on DeviceVectors x (in/out) and b through the C++ drop-in.
-    precond: None | "jacobi" (Storm::JacobiPreconditioner in the reference's pre_op slot)."""
+    precond: None | "jacobi" (Storm::JacobiPreconditioner) | "identity" (the reference's own) | "chebyshev"
+    (Storm::ChebyshevPreconditioner: degree / power iterations / eigenvalue ratio, 0 = class defaults) in the
+    reference's pre_op slot."""
     L = load()
     if reset_rng:
         L.dropin_reset_rng()
@@ -105,7 +108,8 @@ def solve(name: str, op, x, b, num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6, 
     cap_t = trace_cap or (64 * num_iterations + 256)
     hist, trace = np.zeros(cap_h), np.zeros(cap_t)
     opts = Opts(num_iterations, abs_tol, rel_tol, num_inner, relaxation_factor, int(use_graph),
-                {None: 0, "jacobi": 1, "identity": 2}[precond], PRE_SIDES[pre_side])
+                {None: 0, "jacobi": 1, "identity": 2, "chebyshev": 3}[precond], PRE_SIDES[pre_side], int(cheb_degree), int(cheb_power_iterations),
+                float(cheb_eig_ratio))
     rep = Report()
     rc = L.dropin_solve(name.encode(), op.ctx.handle, op.handle, x.ptr, b.ptr, x.n, C.byref(opts),
                         C.byref(rep), hist.ctypes.data_as(capi.f64p), cap_h,

@@ -12,6 +12,7 @@
 // The built libstorm_dropin.so travels to the GPU box (the reference tree does not exist there).
 #include <Storm/B200/FusedSolvers.hpp>
 #include <Storm/B200/GroupedSolvers.hpp>
+#include <Storm/B200/ChebyshevPreconditioner.hpp>
 
 #include <Storm/Solvers/SolverBiCgStab.hpp>
 #include <Storm/Solvers/SolverCg.hpp>
@@ -43,8 +44,12 @@ struct dropin_opts {
   int64_t num_inner_iterations; // <= 0: keep the solver's default (Solver.hpp:159)
   double relaxation_factor;     // Richardson only; <= 0 keeps the default
   int32_t use_graph;            // fused solvers only
-  int32_t precond;              // 0: none, 1: Storm::JacobiPreconditioner, 2: the reference's IdentityPreconditioner (generic solvers)
+  int32_t precond;              // 0: none, 1: Storm::JacobiPreconditioner, 2: the reference's IdentityPreconditioner,
+                                // 3: Storm::ChebyshevPreconditioner (generic solvers)
   int32_t pre_side;             // 0: Left, 1: Right (the reference's default), 2: Symmetric
+  int32_t cheb_degree;          // precond 3: terms of the polynomial (<= 0: the class default, 4)
+  int32_t cheb_power_iterations; // precond 3: power iterations of build() (<= 0: default 10)
+  double cheb_eig_ratio;        // precond 3: lambda_max / lambda_min (<= 0: default 30)
 };
 
 struct dropin_report {
@@ -111,6 +116,15 @@ int run_generic(sb_ctx* ctx, const sb_op* op, double* d_x, const double* d_b, si
   }
   if (o->precond == 2) { // the one preconditioner the reference ships (Preconditioner.hpp:84-97), on the device vector
     solver.pre_op = std::make_unique<Storm::IdentityPreconditioner<DeviceVector>>();
+    solver.pre_side = o->pre_side == 0 ? Storm::PreconditionerSide::Left
+                                       : (o->pre_side == 2 ? Storm::PreconditionerSide::Symmetric : Storm::PreconditionerSide::Right);
+  }
+  if (o->precond == 3) {
+    auto cheb = std::make_unique<Storm::ChebyshevPreconditioner<DeviceVector>>();
+    if (o->cheb_degree > 0) cheb->degree = (size_t) o->cheb_degree;
+    if (o->cheb_power_iterations > 0) cheb->num_power_iterations = (size_t) o->cheb_power_iterations;
+    if (o->cheb_eig_ratio > 0.0) cheb->eig_ratio = o->cheb_eig_ratio;
+    solver.pre_op = std::move(cheb);
     solver.pre_side = o->pre_side == 0 ? Storm::PreconditionerSide::Left
                                        : (o->pre_side == 2 ? Storm::PreconditionerSide::Symmetric : Storm::PreconditionerSide::Right);
   }

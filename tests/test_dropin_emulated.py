@@ -414,3 +414,34 @@ def test_random_programs_agree_across_grouping_modes(square_nb, block):
             assert np.isfinite(res[0][0].view(np.float64)).all() and np.isfinite(res[0][1].view(np.float64)).all()
     finally:
         emu.set_statement_grouping(0)
+
+
+@pytest.mark.parametrize("grouping_mode", [0, 1, 2])
+@pytest.mark.parametrize("side", ["left", "right"])
+def test_chebyshev_preconditioner_same_template_on_host_and_device_vector(square_nb, side, grouping_mode):
+    """Storm::ChebyshevPreconditioner (host/Storm/B200/ChebyshevPreconditioner.hpp) is one template in the reference's
+    vector vocabulary: compiled on the reference's host vector inside oracle/_ref (with the reference's own solver
+    headers around it) it is the checker of itself on Storm::DeviceVector. Iterate, residual history, every reduction
+    value (the power iterations of build() included) and the number of operator applies, bit for bit -- for the
+    preconditioned branches of CG, BiCGStab, FGMRES and IDR(s), left and right, sequential and tree reductions, with
+    and without statement grouping; and the preconditioner does what it is for: far fewer iterations."""
+    emu.set_statement_grouping(grouping_mode)
+    try:
+        op = orc.FaceOp(square_nb, prefill=0, dt=-1.0, dirichlet=True)   # the Poisson operator of configs 2 / 4
+        b = rhs(square_nb.n_cells)
+        for solver in ("cg", "bicgstab", "fgmres", "idrs"):
+            for mode in (orc.RED_SEQ, orc.RED_TREE):
+                kw = dict(num_iterations=400, abs_tol=0.0, rel_tol=1e-9, pre_side=side, mode=mode, cheb_degree=5,
+                          cheb_eig_ratio=20.0, cheb_power_iterations=8)
+                want = orc.ref_solve(solver, op, b, pre="chebyshev", **kw)
+                got = emu.solve(solver, emu.EmuOp(op), b, precond="chebyshev", **kw)
+                assert want.converged and same(got, want), (solver, mode)
+                assert got.n_apply == want.n_apply and got.n_apply > 4 * got.iterations
+        plain = orc.ref_solve("cg", op, b, num_iterations=2000, abs_tol=0.0, rel_tol=1e-9)
+        pre = orc.ref_solve("cg", op, b, num_iterations=2000, abs_tol=0.0, rel_tol=1e-9, pre="chebyshev", cheb_degree=5,
+                            cheb_eig_ratio=20.0)
+        # 526 iterations without, 127 with (a similar number of operator applies, a quarter of the reductions); same solution
+        assert plain.converged and pre.converged and pre.iterations * 3 < plain.iterations
+        assert np.linalg.norm(pre.x - plain.x) <= 1e-7 * np.linalg.norm(plain.x)
+    finally:
+        emu.set_statement_grouping(False)

@@ -136,3 +136,30 @@ def test_early_exit_and_misuse(ctx, ops):
     assert dropin.load().dropin_selftest_errors(ctx.handle) == 3
     with pytest.raises(sb.StormB200Error):
         dropin.solve("no_such_solver", gpu, ctx.zeros(cpu.n), ctx.vector(b))
+
+
+@pytest.mark.parametrize("grouping", [0, 2])
+@pytest.mark.parametrize("side", ["left", "right"])
+def test_chebyshev_preconditioner_on_the_device_bit_identical(ctx, square_nb, side, grouping):
+    """Storm::ChebyshevPreconditioner in the reference's pre_op slot (Preconditioner.hpp:63-77), on the device vector,
+    against THE SAME template compiled on the reference's host vector inside oracle/_ref with the reference's solver
+    headers around it: iteration count, every reduction value (build()'s power iterations included), residual history,
+    number of operator applies and the solution, bit for bit -- as written and with statement grouping (the default)."""
+    cpu = orc.FaceOp(square_nb, prefill=0, dt=-1.0, dirichlet=True)
+    b = rhs(cpu.n)
+    dropin.set_statement_grouping(grouping)
+    try:
+        for form in (sb.FORM_FAITHFUL, sb.FORM_COEF):
+            gpu = sb.FvmOperator(ctx, square_nb, prefill=0, dt=-1.0, form=form, dirichlet=True)
+            oracle_op = cpu if form == sb.FORM_FAITHFUL else orc.RowsOp(cpu.n, *cpu.rows_coef())
+            for solver in ("cg", "bicgstab", "fgmres"):
+                kw = dict(num_iterations=400, abs_tol=0.0, rel_tol=1e-9, pre_side=side, cheb_degree=5, cheb_eig_ratio=20.0,
+                          cheb_power_iterations=8)
+                want = orc.ref_solve(solver, oracle_op, b, pre="chebyshev", mode=orc.RED_TREE, **kw)
+                x = ctx.zeros(cpu.n)
+                got = dropin.solve(solver, gpu, x, ctx.vector(b), precond="chebyshev", **kw)
+                assert want.converged and (got.converged, got.iterations, got.n_apply) == (True, want.iterations, want.n_apply)
+                assert np.array_equal(got.trace, want.trace) and np.array_equal(got.hist, want.hist)
+                assert np.array_equal(x.numpy(), want.x), (solver, form)
+    finally:
+        dropin.set_statement_grouping(2)   # the default
