@@ -296,6 +296,12 @@ int sb_dot_batch(sb_ctx* ctx, int m, const double* const* h_a, const double* con
   SB_REQUIRE(m >= 1 && m <= 60, "batch size out of range (1..60)");
   for (int k = 0; k < m; ++k) SB_REQUIRE(h_a[k] != nullptr && h_b[k] != nullptr, "null vector");
   if (n == 0) {
+    // multi-GPU: every reduction is a collective (in-kernel all-reduce / ncclAllReduce); a rank that skipped it would
+    // leave its peers waiting, so empty ranks are refused here and in sb_dist_op_create
+    if (ctx->comm.world > 1) {
+      set_error("sb_dot_batch: n = 0 on a multi-GPU context (reductions are collective: every rank must own rows)");
+      return SB_ERR_INVALID;
+    }
     for (int k = 0; k < m; ++k) h_out[k] = 0.0;
     return SB_OK;
   }
@@ -339,6 +345,10 @@ int sb_eval_group(sb_ctx* ctx, size_t n, int n_stmt, const sb_chain* h_stmts, in
   }
   for (int d = 0; d < n_dots; ++d) SB_REQUIRE(h_dot_a[d] != nullptr && h_dot_b[d] != nullptr, "null vector");
   if (n == 0) {
+    if (ctx->comm.world > 1 && n_dots > 0) {
+      set_error("sb_eval_group: n = 0 on a multi-GPU context (reductions are collective: every rank must own rows)");
+      return SB_ERR_INVALID;
+    }
     for (int d = 0; d < n_dots; ++d) h_out[d] = 0.0;
     return SB_OK;
   }

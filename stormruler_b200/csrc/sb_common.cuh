@@ -111,16 +111,22 @@ struct SolverState {
 };
 
 // Device block of a fused solve. The stepwise schedule keeps TWO versions of the state: a kernel that consumes a
-// reduction ("folds" it, sb_kernels.cuh: fold_prologue) reads version v in all its CTAs and CTA 0 writes version v^1,
-// so no CTA ever reads a field another CTA of the same kernel is writing; which one is current is a kernel argument.
-// `final_` is the state at the moment the stopping rule fired (what the host reads back), `done` the sticky stop flag
-// every later kernel checks first.
+// reduction ("folds" it, sb_kernels.cuh: fold_reduce / fold_wait) reads version v, its CTA 0 writes version v^1 and
+// raises ready[v^1]; the other CTAs read version v^1 once the flag is up, so nobody ever reads a field that is being
+// written; which version is current is a kernel argument. Every version has cache lines of its own (an SM that has
+// pulled in a line of version v must not have pulled in a stale piece of version v^1 with it). `final_` is the state at
+// the moment the stopping rule fired (what the host reads back), `done` the sticky stop flag every later kernel checks
+// first.
+struct alignas(256) StateSlot {
+  SolverState s;
+};
 struct SolveBlock {
-  SolverState ver[2];
-  SolverState final_;
-  int done;
-  int pad[31];
-  int ready[2]; // ready[v] != 0: version v is complete (raised by CTA 0 of the folding kernel that wrote it); a line of its own
+  StateSlot slot[2];
+  StateSlot final_slot;
+  alignas(128) int done;
+  alignas(128) int ready[2]; // ready[v] != 0: version v is complete
+  __host__ __device__ SolverState& ver(int v) { return slot[v].s; }
+  __host__ __device__ SolverState& final_() { return final_slot.s; }
 };
 
 struct sb_ctx {

@@ -248,11 +248,20 @@ int sb_gmres_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b, con
     return SB_OK;
   };
 
+  // events of this solve, destroyed on every return path
+  struct Events {
+    std::vector<cudaEvent_t> all;
+    ~Events() {
+      for (cudaEvent_t e : all) cudaEventDestroy(e);
+    }
+    int make(cudaEvent_t* e, unsigned flags) {
+      SB_CUDA(cudaEventCreateWithFlags(e, flags));
+      all.push_back(*e);
+      return SB_OK;
+    }
+  } events;
   std::vector<cudaEvent_t> ev((size_t) look + 1);
-  for (auto& e : ev) SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  auto cleanup = [&]() {
-    for (auto& e : ev) cudaEventDestroy(e);
-  };
+  for (auto& e : ev) SB_TRY(events.make(&e, cudaEventDisableTiming));
 
   // ---- IterativeSolver::solve, Solver.hpp:116-147
   SB_TRY(queue_restart());
@@ -264,7 +273,7 @@ int sb_gmres_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b, con
   bool converged = false;
   int64_t iteration = 0;
   cudaEvent_t ev_mid;
-  SB_CUDA(cudaEventCreate(&ev_mid));
+  SB_TRY(events.make(&ev_mid, cudaEventDefault));
   SB_CUDA(cudaEventRecord(ev_mid, ctx->stream));
   if (opts->abs_tol > 0.0 && initial < opts->abs_tol) {
     // Solver.hpp:124-128 calls finalize() here, which back-substitutes through an all-zero H and turns x into
@@ -318,8 +327,6 @@ int sb_gmres_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b, con
   float ms = 0.f, ms_iter = 0.f;
   SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   SB_CUDA(cudaEventElapsedTime(&ms_iter, ev_mid, ctx->ev1));
-  cudaEventDestroy(ev_mid);
-  cleanup();
   report->converged = converged ? 1 : 0;
   report->iterations = iteration;
   report->initial_err = initial, report->abs_err = abs_err, report->rel_err = rel_err;
@@ -328,7 +335,8 @@ int sb_gmres_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b, con
   report->solve_ms = ms, report->iter_ms = ms_iter;
   report->launches = ctx->launches - launches0;
   report->n_kernel_slots = 0;
-  for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->kernel_ms[k] = 0.0;
+  report->schedule = SB_SCHEDULE_STEPWISE;
+  for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->kernel_ms[k] = 0.0, report->wait_ms[k] = 0.0;
   if (h_hist) std::memcpy(h_hist, hist.data(), sizeof(double) * (size_t) report->n_hist);
   if (h_trace) std::memcpy(h_trace, trace.data(), sizeof(double) * (size_t) report->n_trace);
   return SB_OK;

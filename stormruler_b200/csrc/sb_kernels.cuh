@@ -222,24 +222,35 @@ __device__ __forceinline__ void fold_reduce(const Fold<ND, Final>& f) {
     if (f.wait_ns != nullptr && threadIdx.x == 0) *f.wait_ns = globaltimer_ns() - t0;
   }
   if (threadIdx.x == 0) {
-    SolverState st = f.blk->ver[f.in];
+    SolverState st; // version `in`, fetched around L1 (its lines must not linger in this SM's L1)
+    {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&f.blk->ver(f.in));
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&st);
+#pragma unroll
+      for (int k = 0; k < (int) (sizeof(SolverState) / 8); ++k) dst[k] = __ldcg(src + k);
+    }
     Final fin = f.fin;
     fin.rec.st = &st;
     fin(sums);
-    f.blk->ver[f.in ^ 1] = st;
-    if (st.done) f.blk->final_ = st, f.blk->done = 1;
+    f.blk->ver(f.in ^ 1) = st;
+    if (st.done) f.blk->final_() = st, f.blk->done = 1;
     if (f.bump != nullptr) f.bump->apply_seq = f.bump->apply_seq + 1; // the distributed apply in front of me is complete
     __threadfence();
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&f.blk->ready[f.in ^ 1]), "r"(1) : "memory");
   }
 }
 
-// Every other CTA: wait until the new version is complete (lane 0 of each warp acquires, the warp follows).
+// Every other CTA: wait until the new version is complete. Lane 0 of each warp polls around L1 with a plain volatile
+// load, the warp follows; the scalars are then read by ordinary loads that miss L1 (nothing of this version's lines
+// can be there: nobody reads them before the flag) and find in L2 what CTA 0 wrote before its fence. An acquire load
+// would be the textbook form, but it drags a fence behind it that waits for the tile loads this thread has in flight
+// -- exactly the latency the fold is supposed to hide (profiles/r02_stepwise_folded_v2_acquire_poll_10M.json: the
+// element-wise kernels lost 15-40 % of their bandwidth to it).
 __device__ __forceinline__ void fold_wait(const int* ready) {
   if ((threadIdx.x & 31) == 0) {
     int v;
     do {
-      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
+      asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
     } while (v == 0);
   }
   __syncwarp();
@@ -280,9 +291,9 @@ __global__ void __launch_bounds__(kThreads) ew_fold_kernel(int64_t n, Body body,
 #pragma unroll
     for (int j = 0; j < kSub; ++j) body.load(lane_elem(blockIdx.x, j), r[j]);
   }
-  const SolverState* st = &fold.blk->ver[fold.in];
+  const SolverState* st = &fold.blk->ver(fold.in);
   if (fold.n_tiles >= 0) {
-    st = &fold.blk->ver[fold.in ^ 1];
+    st = &fold.blk->ver(fold.in ^ 1);
     if (blockIdx.x == 0) {
       fold_reduce(fold);
       __syncthreads();

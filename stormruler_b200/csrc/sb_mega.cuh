@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, mega_ctas_per_sm(W)) krylov_persiste
   const bool dist = a.ad.comm.world > 1;
   CommCtrl* ctl = dist ? a.ad.comm.ctrl(a.ad.comm.rank) : nullptr;
   if (threadIdx.x == 0) {
-    sh.st = a.blk->ver[0];
+    sh.st = a.blk->ver(0);
     sh.abort = 0;
   }
   if (lane == 0) {
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(kThreads, mega_ctas_per_sm(W)) krylov_persiste
       st_relaxed_sys(mega_box(a, a.ad.comm.rank, (run.ar - 1) & 1ull, r, d), kArSentinel);
     }
     if (threadIdx.x == 0) {
-      a.blk->ver[0] = *S, a.blk->final_ = *S, a.blk->done = S->done;
+      a.blk->ver(0) = *S, a.blk->final_() = *S, a.blk->done = S->done;
       if (dist) ctl->ar_seq = run.ar, ctl->apply_seq = run.seq;
       else a.mc->ar_seq = run.ar;
     }

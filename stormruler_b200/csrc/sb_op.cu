@@ -275,6 +275,7 @@ static int check_local(sb_ctx* ctx, const sb_local_mesh* loc) {
   }
   SB_REQUIRE(loc->rank == ctx->comm.rank && loc->n_parts == ctx->comm.world, "local mesh belongs to another rank / world size");
   SB_REQUIRE(loc->n_nbr >= 0 && loc->n_nbr < kMaxRanks, "too many neighbours");
+  SB_REQUIRE(loc->n_owned > 0, "a rank without cells cannot take part (reductions and the apply sequence are collective)");
   SB_REQUIRE(loc->halo_base == pad_up(loc->n_owned) && loc->soa.n_cells == loc->halo_base + loc->n_halo, "local mesh layout");
   SB_REQUIRE(loc->halo_base + loc->n_halo <= ctx->vec_capacity, "local vector does not fit the pool block (vec_capacity)");
   return SB_OK;

@@ -56,7 +56,7 @@ struct PublishFinal {
   SolveBlock* blk;
   __device__ void operator()(const double* s) const {
     inner(s);
-    if (inner.rec.st->done) blk->final_ = *inner.rec.st, blk->done = 1;
+    if (inner.rec.st->done) blk->final_() = *inner.rec.st, blk->done = 1;
   }
 };
 

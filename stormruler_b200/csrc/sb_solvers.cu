@@ -263,7 +263,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
 
   SolveBlock* pinned_blk = reinterpret_cast<SolveBlock*>(ctx->h_pinned);
   *pinned_blk = SolveBlock{};
-  SolverState& h = pinned_blk->ver[0];
+  SolverState& h = pinned_blk->ver(0);
   h.abs_tol = opts->abs_tol, h.rel_tol = opts->rel_tol;
   h.max_iter = opts->num_iterations;
   h.hist_cap = h_hist ? hist_cap : 0, h.trace_cap = h_trace ? trace_cap : 0;
@@ -272,7 +272,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   Solve S;
   S.ctx = ctx, S.op = op, S.x = x, S.b = b, S.n = n;
   S.blk = ctx->d_solve;
-  S.rec = Recorder{&ctx->d_solve->ver[0], h_hist ? ctx->d_hist : nullptr, h_trace ? ctx->d_trace : nullptr};
+  S.rec = Recorder{&ctx->d_solve->ver(0), h_hist ? ctx->d_hist : nullptr, h_trace ? ctx->d_trace : nullptr};
   S.done = &ctx->d_solve->done;
   S.p = ctx->work[0], S.r = ctx->work[1];
   S.z = S.rt = S.t = S.v = nullptr;
@@ -389,7 +389,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   SB_CUDA(cudaStreamSynchronize(ctx->stream));
   // the state at the moment the stopping rule fired; a solve always ends with the flag set (tolerance met, or the
   // iteration count reached num_iterations)
-  const SolverState out = pinned_blk->done ? pinned_blk->final_ : pinned_blk->ver[S.ver];
+  const SolverState out = pinned_blk->done ? pinned_blk->final_() : pinned_blk->ver(S.ver);
   float ms = 0.f, ms_iter = 0.f;
   SB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
   SB_CUDA(cudaEventElapsedTime(&ms_iter, ev_mid, ctx->ev1));
