@@ -209,9 +209,13 @@ struct Fold {
   unsigned long long* wait_ns = nullptr; // optional: how long CTA 0 waited for the other ranks' sums
 };
 
-// CTA 0 of a folding kernel, all threads.
+// CTA 0 of a folding kernel, all threads. Deliberately NOT inlined: inlined, its register needs (the final stage keeps
+// 8 x ND partials in flight per thread, the all-reduce its mailbox addresses) became those of the whole kernel -- the
+// half update went from 32 to 85 registers, i.e. from eight resident CTAs per SM to two, and lost a quarter of its
+// bandwidth (profiles/r02_stepwise_folded_v2_acquire_poll_10M.json). As a call it lives within the register budget
+// the kernel's __launch_bounds__ gives the element-wise body; only CTA 0 ever pays for what it spills.
 template<int ND, class Final>
-__device__ __forceinline__ void fold_reduce(const Fold<ND, Final>& f) {
+__device__ __noinline__ void fold_reduce(const Fold<ND, Final>& f) {
   __shared__ double s_fin[kMaxDots][kWarps];
   if (threadIdx.x == 0) f.blk->ready[f.in] = 0; // nobody waits for it during this kernel
   double sums[ND];
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, Body body, RedP
 // (Body::st is redirected to it). A fold without tiles (the flush at the end of a BiCGStab solve) is launched with
 // n = 0 and one CTA.
 template<int ND, class Body, int FND, class Final>
-__global__ void __launch_bounds__(kThreads) ew_fold_kernel(int64_t n, Body body, RedPtrs red, const int* __restrict__ done,
+__global__ void __launch_bounds__(kThreads, Body::kMinCtas) ew_fold_kernel(int64_t n, Body body, RedPtrs red, const int* __restrict__ done,
                                                            Fold<FND, Final> fold) {
   if (is_done(done)) return;
   const bool tile = (int64_t) blockIdx.x * kTile < n;

@@ -98,6 +98,8 @@ struct CopyBody { // p <- r
 };
 
 struct CgUpdateBody { // x += alpha*p ; r -= alpha*z ; acc += r.r     (:97-98,114)
+  static constexpr int kMinCtas = 3; // resident CTAs per SM the folding kernel is compiled for: the tile's loads
+                                     // (4 vectors x 4 sub-iterations x 4 registers) stay live across the fold
   const SolverState* st;
   double *x, *r;
   const double *p, *z;
@@ -125,6 +127,7 @@ struct CgUpdateBody { // x += alpha*p ; r -= alpha*z ; acc += r.r     (:97-98,11
 };
 
 struct CgDirectionBody { // p <- r + beta*p     (:122)
+  static constexpr int kMinCtas = 6;
   const SolverState* st;
   double* p;
   const double* r;
@@ -196,6 +199,7 @@ struct BiInitBody { // r~ <- r after the fused residual (r already stored by the
 };
 
 struct BiDirectionBody { // iteration 0: p <- r ; else p <- r + beta*(p - omega*v)   (:111-119)
+  static constexpr int kMinCtas = 4;
   const SolverState* st;
   double* p;
   const double *r, *v;
@@ -222,6 +226,7 @@ struct BiDirectionBody { // iteration 0: p <- r ; else p <- r + beta*(p - omega*
 };
 
 struct BiHalfBody { // r -= alpha*v     (:141); x += alpha*p is deferred to BiEndBody
+  static constexpr int kMinCtas = 6;
   const SolverState* st;
   double* r;
   const double* v;
@@ -242,6 +247,7 @@ struct BiHalfBody { // r -= alpha*v     (:141); x += alpha*p is deferred to BiEn
 };
 
 struct BiEndBody { // x = (x + alpha*p) + omega*r ; r -= omega*t ; acc0 += r.r ; acc1 += r~.r   (:140,161-164)
+  static constexpr int kMinCtas = 2;
   const SolverState* st;
   double *x, *r;
   const double *p, *t, *rt;
