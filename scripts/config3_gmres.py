@@ -41,6 +41,11 @@ def main():
     ap.add_argument("--path", default="fused", choices=["fused", "generic"],
                     help="fused: sb_gmres_solve (device-resident Arnoldi); generic: the reference template on DeviceVector")
     ap.add_argument("--converge", action="store_true", help="also solve to rel 1e-8 and report iterations + true residual")
+    ap.add_argument("--precond", default="none", choices=["none", "jacobi", "chebyshev"],
+                    help="generic path: preconditioner in the reference's pre_op slot (FGMRES differs from GMRES only with one: "
+                         "SolverGmres.hpp:149-156,233-248)")
+    ap.add_argument("--pre-side", default="right", choices=["left", "right"])
+    ap.add_argument("--cheb-degree", type=int, default=4)
     args = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -58,7 +63,7 @@ def main():
         dist = mg.init_process_group(cuda=True)
         part = mg.partition_mesh(mesh, world, capi.PART_METIS)
         loc = part.local(rank)
-        ctx = mg.DistContext(local_rank, rank, world, part.info.vec_capacity, n_vectors=args.m + 12)
+        ctx = mg.DistContext(local_rank, rank, world, part.info.vec_capacity, n_vectors=2 * args.m + 16)
         op = mg.DistConvDiffOperator(ctx, loc, nu, fu, bu)
         n_loc, owned = loc.n_owned, loc.owned_global
     else:
@@ -75,13 +80,15 @@ def main():
         if dist:
             dist.barrier()
         t = time.perf_counter()
-        if args.path == "fused" and args.solver in ("gmres", "fgmres"):
+        if args.path == "fused" and args.solver in ("gmres", "fgmres") and args.precond == "none":
             g = sb.GmresSolver(num_iterations=iters, absolute_error_tolerance=0.0, relative_error_tolerance=rel_tol,
                                num_inner_iterations=args.m, record=False)
             conv = g.solve(x, b, op)
             r = dropin.Result(conv, g.iteration, g.absolute_error, g.relative_error, g.history, g.trace, -1)
         else:
-            r = dropin.solve(args.solver, op, x, b, num_iterations=iters, abs_tol=0.0, rel_tol=rel_tol, num_inner=args.m)
+            r = dropin.solve(args.solver, op, x, b, num_iterations=iters, abs_tol=0.0, rel_tol=rel_tol, num_inner=args.m,
+                             precond=None if args.precond == "none" else args.precond, pre_side=args.pre_side,
+                             cheb_degree=args.cheb_degree, trace_cap=64)
         ctx.sync()
         dt_ = time.perf_counter() - t
         if dist:
@@ -112,8 +119,8 @@ def main():
             "applies": int(r.n_apply),
             "algorithmic_gbs": (alg / secs / 1e9) if alg else None,
             "frac_of_nominal_8TBs": (alg / secs / (8e12 * world)) if alg else None,
-            "residual_after_steps": r.abs_err,
-            "path": "sb_gmres_solve (fused: device-resident Arnoldi, host Givens)" if (args.path == "fused" and args.solver in ("gmres", "fgmres"))
+            "residual_after_steps": r.abs_err, "preconditioner": args.precond, "pre_side": args.pre_side,
+            "path": "sb_gmres_solve (fused: device-resident Arnoldi, host Givens)" if (args.path == "fused" and args.solver in ("gmres", "fgmres") and args.precond == "none")
             else "reference solver template on Storm::DeviceVector (generic drop-in)"}
     if args.converge:
         rc, xc, sc = run(5000, 1e-8)

@@ -212,8 +212,9 @@ struct Fold {
 // CTA 0 of a folding kernel, all threads. Deliberately NOT inlined: inlined, its register needs (the final stage keeps
 // 8 x ND partials in flight per thread, the all-reduce its mailbox addresses) became those of the whole kernel -- the
 // half update went from 32 to 85 registers, i.e. from eight resident CTAs per SM to two, and lost a quarter of its
-// bandwidth (profiles/r02_stepwise_folded_v2_acquire_poll_10M.json). As a call it lives within the register budget
-// the kernel's __launch_bounds__ gives the element-wise body; only CTA 0 ever pays for what it spills.
+// bandwidth (profiles/r02_stepwise_folded_v2_acquire_poll_10M.json). As a call made before anything of the tile is
+// loaded it lives within the register budget the kernel's __launch_bounds__ gives the element-wise body, nothing is
+// live across it, and only CTA 0 ever pays for what it spills.
 template<int ND, class Final>
 __device__ __noinline__ void fold_reduce(const Fold<ND, Final>& f) {
   __shared__ double s_fin[kMaxDots][kWarps];
@@ -281,20 +282,20 @@ __global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, Body body, RedP
   if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, blockIdx.x);
 }
 
-// The same kernel in front of which a reduction is folded (fold_reduce / fold_wait): the tile's loads are issued
-// first, so the fold runs under their latency; the body then reads the solver scalars from the new state version
-// (Body::st is redirected to it). A fold without tiles (the flush at the end of a BiCGStab solve) is launched with
-// n = 0 and one CTA.
+// The same kernel in front of which a reduction is folded (fold_reduce / fold_wait), then the element-wise body exactly
+// as in ew_kernel, reading the solver scalars from the new state version (Body::st is redirected to it). The fold comes
+// FIRST, before the tile's loads are issued: keeping a tile's loads in flight across it was tried and lost more than it
+// hid -- the loaded registers stay live across CTA 0's call, so either the kernel's register count (and with it the
+// resident CTAs per SM) follows CTA 0's needs, or every CTA spills its tile to local memory
+// (profiles/r02_stepwise_folded_v{2,4}_*.json: the half update at 10 M cells went from 37 us to 50 us and 104 us). With
+// the fold first, a CTA that finds the flag up pays one L2 round trip before its first load, which eight resident
+// CTAs per SM absorb. A fold without tiles (the flush at the end of a BiCGStab solve) is launched with n = 0 and one CTA.
 template<int ND, class Body, int FND, class Final>
 __global__ void __launch_bounds__(kThreads, Body::kMinCtas) ew_fold_kernel(int64_t n, Body body, RedPtrs red, const int* __restrict__ done,
-                                                           Fold<FND, Final> fold) {
+                                                                          const __grid_constant__ Fold<FND, Final> fold) {
+  // (__grid_constant__: CTA 0 passes `fold` to fold_reduce by reference; without it EVERY thread of every CTA copied
+  // the 200-byte parameter to its local stack on entry -- as much store traffic as the half update itself produces)
   if (is_done(done)) return;
-  const bool tile = (int64_t) blockIdx.x * kTile < n;
-  typename Body::Regs r[kSub];
-  if (tile) {
-#pragma unroll
-    for (int j = 0; j < kSub; ++j) body.load(lane_elem(blockIdx.x, j), r[j]);
-  }
   const SolverState* st = &fold.blk->ver(fold.in);
   if (fold.n_tiles >= 0) {
     st = &fold.blk->ver(fold.in ^ 1);
@@ -305,8 +306,11 @@ __global__ void __launch_bounds__(kThreads, Body::kMinCtas) ew_fold_kernel(int64
       fold_wait(&fold.blk->ready[fold.in ^ 1]);
     }
   }
-  if (!tile || __ldcg(&st->done) != 0) return; // the stopping rule has just fired: the iterate stays what it is
+  if ((int64_t) blockIdx.x * kTile >= n || __ldcg(&st->done) != 0) return; // stopped just now: the iterate stays what it is
   body.st = st;
+  typename Body::Regs r[kSub];
+#pragma unroll
+  for (int j = 0; j < kSub; ++j) body.load(lane_elem(blockIdx.x, j), r[j]);
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
   for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
