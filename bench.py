@@ -184,6 +184,11 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # inputs through the host-only build of the mesh sources: this process never maps the CUDA library
+    prep = os.path.join(ROOT, "oracle", "libsb_meshprep.so")
+    if os.path.exists(prep):
+        from stormruler_b200 import capi
+        capi.use_host_library(prep)
     mesh, x_star = build_problem(args)
     t0 = time.perf_counter()
     from oracle import orc

@@ -185,6 +185,23 @@ def load():
     return _lib
 
 
+def use_host_library(path: str):
+    """Bind the HOST-ONLY entry points (sb_mesh_*, sb_part_*, sb_last_error) to another shared library that exports
+    them -- oracle/libsb_meshprep.so, the product's mesh sources built without any device code. bench.py's reference
+    arm prepares its inputs this way, so that the process timing the reference's CPU solver never maps the CUDA
+    library. Must be called before anything else has loaded the library; the device entry points are then absent."""
+    global _lib
+    if _lib is not None:
+        raise RuntimeError("use_host_library: a library is already loaded")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        if name.startswith(("sb_mesh_", "sb_part_")) or name == "sb_last_error":
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
 class StormB200Error(RuntimeError):
     pass
 

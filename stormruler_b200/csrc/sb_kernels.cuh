@@ -212,9 +212,9 @@ struct Fold {
 // CTA 0 of a folding kernel, all threads. Deliberately NOT inlined: inlined, its register needs (the final stage keeps
 // 8 x ND partials in flight per thread, the all-reduce its mailbox addresses) became those of the whole kernel -- the
 // half update went from 32 to 85 registers, i.e. from eight resident CTAs per SM to two, and lost a quarter of its
-// bandwidth (profiles/r02_stepwise_folded_v2_acquire_poll_10M.json). As a call made before anything of the tile is
-// loaded it lives within the register budget the kernel's __launch_bounds__ gives the element-wise body, nothing is
-// live across it, and only CTA 0 ever pays for what it spills.
+// bandwidth (profiles/r02_stepwise_folded_v2_acquire_poll_10M.json). As a call made by a CTA that owns no tile it lives
+// within the register budget the kernel's __launch_bounds__ gives the element-wise body, nothing is live across it,
+// and only that one CTA ever pays for what it spills.
 template<int ND, class Final>
 __device__ __noinline__ void fold_reduce(const Fold<ND, Final>& f) {
   __shared__ double s_fin[kMaxDots][kWarps];
@@ -282,41 +282,40 @@ __global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, Body body, RedP
   if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, blockIdx.x);
 }
 
-// The same kernel in front of which a reduction is folded (fold_reduce / fold_wait), then the element-wise body exactly
-// as in ew_kernel, reading the solver scalars from the new state version (Body::st is redirected to it). The fold comes
-// FIRST, before the tile's loads are issued: keeping a tile's loads in flight across it was tried and lost more than it
-// hid -- the loaded registers stay live across CTA 0's call, so either the kernel's register count (and with it the
-// resident CTAs per SM) follows CTA 0's needs, or every CTA spills its tile to local memory
-// (profiles/r02_stepwise_folded_v{2,4}_*.json: the half update at 10 M cells went from 37 us to 50 us and 104 us). With
-// the fold first, a CTA that finds the flag up pays one L2 round trip before its first load, which eight resident
-// CTAs per SM absorb. A fold without tiles (the flush at the end of a BiCGStab solve) is launched with n = 0 and one CTA.
+// The same kernel in front of which a reduction is folded. CTA 0 is a dedicated reducer (fold_reduce) and owns no tile;
+// CTA k > 0 owns tile k - 1: it issues the tile's loads, THEN waits for the ready flag (fold_wait: one volatile poll per
+// warp, no fence, no call), reads the solver scalars from the new state version (Body::st is redirected to it) and runs
+// the body exactly as ew_kernel does -- the flag's round trip and the scalar loads run under the latency of the tile's
+// loads. What was tried before (profiles/r02_stepwise_folded_v{1,2,4,5}_*.json, half update at 10 M cells, 37 us
+// unfolded): every CTA running the scalar update behind a mailbox (50 us); CTA 0 = reducer AND tile owner, inlined (its
+// registers became everybody's: 85 instead of 32, 50 us) or as a call (the tile's registers spill around it: 104 us);
+// the fold in front of the loads (two dependent L2 round trips per CTA before its first load: 63 us).
+// A fold without tiles (the flush at the end of a BiCGStab solve) is launched with n = 0: CTA 0 alone.
 template<int ND, class Body, int FND, class Final>
 __global__ void __launch_bounds__(kThreads, Body::kMinCtas) ew_fold_kernel(int64_t n, Body body, RedPtrs red, const int* __restrict__ done,
                                                                           const __grid_constant__ Fold<FND, Final> fold) {
   // (__grid_constant__: CTA 0 passes `fold` to fold_reduce by reference; without it EVERY thread of every CTA copied
   // the 200-byte parameter to its local stack on entry -- as much store traffic as the half update itself produces)
   if (is_done(done)) return;
-  const SolverState* st = &fold.blk->ver(fold.in);
-  if (fold.n_tiles >= 0) {
-    st = &fold.blk->ver(fold.in ^ 1);
-    if (blockIdx.x == 0) {
-      fold_reduce(fold);
-      __syncthreads();
-    } else {
-      fold_wait(&fold.blk->ready[fold.in ^ 1]);
-    }
+  const bool active = fold.n_tiles >= 0;
+  if (blockIdx.x == 0) {
+    if (active) fold_reduce(fold);
+    return;
   }
-  if ((int64_t) blockIdx.x * kTile >= n || __ldcg(&st->done) != 0) return; // stopped just now: the iterate stays what it is
-  body.st = st;
+  const int64_t tile = (int64_t) blockIdx.x - 1;
   typename Body::Regs r[kSub];
 #pragma unroll
-  for (int j = 0; j < kSub; ++j) body.load(lane_elem(blockIdx.x, j), r[j]);
+  for (int j = 0; j < kSub; ++j) body.load(lane_elem(tile, j), r[j]);
+  const SolverState* st = &fold.blk->ver(active ? (fold.in ^ 1) : fold.in);
+  if (active) fold_wait(&fold.blk->ready[fold.in ^ 1]);
+  if (__ldcg(&st->done) != 0) return; // the stopping rule has just fired: the iterate stays what it is
+  body.st = st;
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
   for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
 #pragma unroll
-  for (int j = 0; j < kSub; ++j) body.run(lane_elem(blockIdx.x, j), n, r[j], acc);
-  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, blockIdx.x);
+  for (int j = 0; j < kSub; ++j) body.run(lane_elem(tile, j), n, r[j], acc);
+  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, tile);
 }
 
 // masked accumulation: out-of-range elements contribute +0.0 (SB_TREE v1)

@@ -98,7 +98,8 @@ struct CopyBody { // p <- r
 };
 
 struct CgUpdateBody { // x += alpha*p ; r -= alpha*z ; acc += r.r     (:97-98,114)
-  static constexpr int kMinCtas = 4; // resident CTAs per SM the folding kernel is compiled for (= what ew_kernel gets)
+  static constexpr int kMinCtas = 3; // resident CTAs per SM the folding kernel is compiled for: the tile's loads
+                                     // (4 vectors x 4 sub-iterations x 4 registers) stay live across the flag wait
   const SolverState* st;
   double *x, *r;
   const double *p, *z;
@@ -126,7 +127,7 @@ struct CgUpdateBody { // x += alpha*p ; r -= alpha*z ; acc += r.r     (:97-98,11
 };
 
 struct CgDirectionBody { // p <- r + beta*p     (:122)
-  static constexpr int kMinCtas = 8;
+  static constexpr int kMinCtas = 5;
   const SolverState* st;
   double* p;
   const double* r;
@@ -198,7 +199,7 @@ struct BiInitBody { // r~ <- r after the fused residual (r already stored by the
 };
 
 struct BiDirectionBody { // iteration 0: p <- r ; else p <- r + beta*(p - omega*v)   (:111-119)
-  static constexpr int kMinCtas = 5;
+  static constexpr int kMinCtas = 4;
   const SolverState* st;
   double* p;
   const double *r, *v;
@@ -206,8 +207,9 @@ struct BiDirectionBody { // iteration 0: p <- r ; else p <- r + beta*(p - omega*
     double2 p, r, v;
   };
   __device__ __forceinline__ void load(int64_t e0, Regs& g) const {
-    g.r = ld2(r, e0);
-    if (st->iteration != 0) g.p = ld2(p, e0), g.v = ld2(v, e0);
+    // p and v are fetched in iteration 0 as well (unused there): in the folding kernel the loads are issued before the
+    // reduction in front of it has been folded, i.e. before the iteration number is known
+    g.r = ld2(r, e0), g.p = ld2(p, e0), g.v = ld2(v, e0);
   }
   static constexpr int NV = 3; // the staged variant fetches p and v in iteration 0 too (unused there)
   __device__ __forceinline__ const double* in(int k) const { return k == 0 ? r : (k == 1 ? p : v); }
@@ -224,7 +226,7 @@ struct BiDirectionBody { // iteration 0: p <- r ; else p <- r + beta*(p - omega*
 };
 
 struct BiHalfBody { // r -= alpha*v     (:141); x += alpha*p is deferred to BiEndBody
-  static constexpr int kMinCtas = 8;
+  static constexpr int kMinCtas = 5;
   const SolverState* st;
   double* r;
   const double* v;

@@ -149,7 +149,7 @@ struct Solve {
       if (after_apply && !(ctx->debug & 2)) f.bump = ctx->comm.ctrl(ctx->comm.rank);
     }
     f.wait_ns = wait_slot(); // one word per kernel slot, folding or not: the timeline stays aligned with the slots
-    const unsigned grid = (unsigned) std::max<int64_t>(1, num_tiles(rows));
+    const unsigned grid = (unsigned) (num_tiles(rows) + 1); // CTA 0 reduces, CTA k > 0 owns tile k - 1
     SB_CUDA(launch_kernel(ctx, ew_fold_kernel<ND, Body, FND, Final>, grid, kThreads, 0, rows, body, red_set(1), done, f));
     ctx->launches++;
     if (active) ver ^= 1;

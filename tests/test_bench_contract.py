@@ -67,3 +67,17 @@ def test_reference_arm_under_torchrun_prints_once():
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2 and json.loads(lines[0])["impl"] == "reference"
+
+
+def test_reference_arm_never_maps_the_cuda_library():
+    """The process that times the reference's CPU solver prepares its inputs through oracle/libsb_meshprep.so (the
+    product's host-only mesh sources, no device code) and maps nothing of the product's CUDA library."""
+    code = (
+        "import runpy, sys\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--axis', '12', '--steps', '2', '--warmup', '1']\n"
+        "runpy.run_path('bench.py', run_name='__main__')\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "print('MAPS', 'libstormb200.so' in maps, 'libsb_meshprep.so' in maps, 'libref_solvers.so' in maps or 'liboracle.so' in maps)\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "MAPS False True True" in out.stdout, out.stdout[-500:]
