@@ -282,42 +282,6 @@ __global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, Body body, RedP
   if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, blockIdx.x);
 }
 
-// The same kernel in front of which a reduction is folded. CTA 0 is a dedicated reducer (fold_reduce) and owns no tile;
-// CTA k > 0 owns tile k - 1: it issues the tile's loads, THEN waits for the ready flag (fold_wait: one volatile poll per
-// warp, no fence, no call), reads the solver scalars from the new state version (Body::st is redirected to it) and runs
-// the body exactly as ew_kernel does -- the flag's round trip and the scalar loads run under the latency of the tile's
-// loads. What was tried before (profiles/r02_stepwise_folded_v{1,2,4,5}_*.json, half update at 10 M cells, 37 us
-// unfolded): every CTA running the scalar update behind a mailbox (50 us); CTA 0 = reducer AND tile owner, inlined (its
-// registers became everybody's: 85 instead of 32, 50 us) or as a call (the tile's registers spill around it: 104 us);
-// the fold in front of the loads (two dependent L2 round trips per CTA before its first load: 63 us).
-// A fold without tiles (the flush at the end of a BiCGStab solve) is launched with n = 0: CTA 0 alone.
-template<int ND, class Body, int FND, class Final>
-__global__ void __launch_bounds__(kThreads, Body::kMinCtas) ew_fold_kernel(int64_t n, Body body, RedPtrs red, const int* __restrict__ done,
-                                                                          const __grid_constant__ Fold<FND, Final> fold) {
-  // (__grid_constant__: CTA 0 passes `fold` to fold_reduce by reference; without it EVERY thread of every CTA copied
-  // the 200-byte parameter to its local stack on entry -- as much store traffic as the half update itself produces)
-  if (is_done(done)) return;
-  const bool active = fold.n_tiles >= 0;
-  if (blockIdx.x == 0) {
-    if (active) fold_reduce(fold);
-    return;
-  }
-  const int64_t tile = (int64_t) blockIdx.x - 1;
-  typename Body::Regs r[kSub];
-#pragma unroll
-  for (int j = 0; j < kSub; ++j) body.load(lane_elem(tile, j), r[j]);
-  const SolverState* st = &fold.blk->ver(active ? (fold.in ^ 1) : fold.in);
-  if (active) fold_wait(&fold.blk->ready[fold.in ^ 1]);
-  if (__ldcg(&st->done) != 0) return; // the stopping rule has just fired: the iterate stays what it is
-  body.st = st;
-  double acc[ND > 0 ? ND : 1];
-#pragma unroll
-  for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
-#pragma unroll
-  for (int j = 0; j < kSub; ++j) body.run(lane_elem(tile, j), n, r[j], acc);
-  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, tile);
-}
-
 // masked accumulation: out-of-range elements contribute +0.0 (SB_TREE v1)
 __device__ __forceinline__ void acc_pair(double& acc, int64_t e0, int64_t n, double p0, double p1) {
   acc = __dadd_rn(acc, (e0 < n) ? p0 : 0.0);

@@ -334,6 +334,83 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
   if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, tile);
 }
 
+// ---- element-wise kernel with a folded reduction in front, bulk-copy staged ---------------------------------------------
+// (sb_kernels.cuh: Fold, fold_reduce, fold_wait.) CTA 0 is a dedicated reducer and owns no tile; CTA k > 0 owns tile k - 1.
+// A tile's inputs -- the 512-byte runs of the body's NV input vectors for the four sub-iterations of each warp -- are
+// fetched by bulk copies (cp.async.bulk) into shared memory, all sixteen NV per warp issued by one lane before
+// anything else; THEN the CTA waits for the ready flag (one volatile poll per warp: no fence, no call), reads the solver
+// scalars from the new state version (Body::st is redirected to it) and consumes the stages. Nothing is held in
+// registers across the wait, the flag's round trip and the scalar loads run under the latency of the copies, and the
+// bytes in flight per SM are set by shared memory (NV x 16 KB per CTA: 7 / 4 / 3 / 2 resident CTAs for 2 / 3 / 4 / 5
+// inputs = 160-224 KB per SM), not by the register file. What was tried before
+// (profiles/r02_stepwise_folded_v{1,2,4,5,6}_*.json; half update at 10 M cells, 37 us with the one-CTA final stage in
+// front): every CTA running the scalar update behind a mailbox (50 us); CTA 0 = reducer AND tile owner, inlined (its
+// registers became everybody's: 85 instead of 32, 50 us) or as a call (the tile's registers spill around it: 104 us);
+// the fold in front of the loads (two dependent L2 round trips per CTA before its first load: 63 us); register-staged
+// loads in front of the wait (32 data registers live across it: five resident CTAs instead of eight, 50 us).
+// A fold without tiles (the flush at the end of a BiCGStab solve) is launched with n = 0: CTA 0 alone.
+template<class Body>
+struct EwStage {
+  static constexpr int stage = Body::NV * 512;     // one sub-iteration of one warp
+  static constexpr int warp = stage * kSub;
+  static constexpr int cta = warp * kWarps;        // = NV x 16 KB
+  static constexpr int min_ctas = Body::NV <= 2 ? 7 : (Body::NV == 3 ? 4 : (Body::NV == 4 ? 3 : 2));
+};
+
+template<int ND, class Body, int FND, class Final>
+__global__ void __launch_bounds__(kThreads, EwStage<Body>::min_ctas) ew_fold_kernel(int64_t n, Body body, RedPtrs red, const int* __restrict__ done,
+                                                                                   const __grid_constant__ Fold<FND, Final> fold) {
+  // (__grid_constant__: CTA 0 passes `fold` to fold_reduce by reference; without it EVERY thread of every CTA copied
+  // the 200-byte parameter to its local stack on entry -- as much store traffic as the half update itself produces)
+  using E = EwStage<Body>;
+  constexpr int NV = Body::NV;
+  extern __shared__ __align__(128) unsigned char sb_smem[];
+  __shared__ __align__(8) uint64_t bars[kWarps][kSub];
+  if (is_done(done)) return;
+  const bool active = fold.n_tiles >= 0;
+  if (blockIdx.x == 0) {
+    if (active) fold_reduce(fold);
+    return;
+  }
+  const int64_t tile = (int64_t) blockIdx.x - 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* wbase = sb_smem + (size_t) warp * E::warp;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kSub; ++j) mbar_init(&bars[warp][j], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < kSub; ++j) {
+      const int64_t r0 = tile * kTile + warp * (kTile / kWarps) + j * 64;
+      mbar_expect_tx(&bars[warp][j], (uint32_t) E::stage);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) bulk_g2s(wbase + j * E::stage + k * 512, body.in(k) + r0, 512, &bars[warp][j]);
+    }
+  }
+  __syncwarp();
+  const SolverState* st = &fold.blk->ver(active ? (fold.in ^ 1) : fold.in);
+  if (active) fold_wait(&fold.blk->ready[fold.in ^ 1]);
+  const bool stopped = __ldcg(&st->done) != 0; // the stopping rule has just fired: the iterate stays what it is
+  body.st = st;
+  double acc[ND > 0 ? ND : 1];
+#pragma unroll
+  for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+#pragma unroll
+  for (int j = 0; j < kSub; ++j) {
+    mbar_wait(&bars[warp][j], 0); // also when stopped: a CTA must not exit with bulk copies landing in its smem
+    if (stopped) continue;
+    double2 in[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) in[k] = reinterpret_cast<const double2*>(wbase + j * E::stage + k * 512)[lane];
+    typename Body::Regs g;
+    body.fill(g, in);
+    body.run(lane_elem(tile, j), n, g, acc);
+  }
+  if (stopped) return;
+  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, tile);
+}
+
 // y = x / diag (Jacobi). The diagonal lives inside the blocked slice records (or in OpDev::diag for the v1 layout).
 struct JacobiBody {
   OpDev op;

@@ -98,8 +98,6 @@ struct CopyBody { // p <- r
 };
 
 struct CgUpdateBody { // x += alpha*p ; r -= alpha*z ; acc += r.r     (:97-98,114)
-  static constexpr int kMinCtas = 3; // resident CTAs per SM the folding kernel is compiled for: the tile's loads
-                                     // (4 vectors x 4 sub-iterations x 4 registers) stay live across the flag wait
   const SolverState* st;
   double *x, *r;
   const double *p, *z;
@@ -127,7 +125,6 @@ struct CgUpdateBody { // x += alpha*p ; r -= alpha*z ; acc += r.r     (:97-98,11
 };
 
 struct CgDirectionBody { // p <- r + beta*p     (:122)
-  static constexpr int kMinCtas = 5;
   const SolverState* st;
   double* p;
   const double* r;
@@ -199,7 +196,6 @@ struct BiInitBody { // r~ <- r after the fused residual (r already stored by the
 };
 
 struct BiDirectionBody { // iteration 0: p <- r ; else p <- r + beta*(p - omega*v)   (:111-119)
-  static constexpr int kMinCtas = 4;
   const SolverState* st;
   double* p;
   const double *r, *v;
@@ -207,9 +203,8 @@ struct BiDirectionBody { // iteration 0: p <- r ; else p <- r + beta*(p - omega*
     double2 p, r, v;
   };
   __device__ __forceinline__ void load(int64_t e0, Regs& g) const {
-    // p and v are fetched in iteration 0 as well (unused there): in the folding kernel the loads are issued before the
-    // reduction in front of it has been folded, i.e. before the iteration number is known
-    g.r = ld2(r, e0), g.p = ld2(p, e0), g.v = ld2(v, e0);
+    g.r = ld2(r, e0);
+    if (st->iteration != 0) g.p = ld2(p, e0), g.v = ld2(v, e0);
   }
   static constexpr int NV = 3; // the staged variant fetches p and v in iteration 0 too (unused there)
   __device__ __forceinline__ const double* in(int k) const { return k == 0 ? r : (k == 1 ? p : v); }
@@ -226,7 +221,6 @@ struct BiDirectionBody { // iteration 0: p <- r ; else p <- r + beta*(p - omega*
 };
 
 struct BiHalfBody { // r -= alpha*v     (:141); x += alpha*p is deferred to BiEndBody
-  static constexpr int kMinCtas = 5;
   const SolverState* st;
   double* r;
   const double* v;
@@ -247,7 +241,6 @@ struct BiHalfBody { // r -= alpha*v     (:141); x += alpha*p is deferred to BiEn
 };
 
 struct BiEndBody { // x = (x + alpha*p) + omega*r ; r -= omega*t ; acc0 += r.r ; acc1 += r~.r   (:140,161-164)
-  static constexpr int kMinCtas = 2;
   const SolverState* st;
   double *x, *r;
   const double *p, *t, *rt;

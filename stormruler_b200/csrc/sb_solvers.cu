@@ -150,7 +150,15 @@ struct Solve {
     }
     f.wait_ns = wait_slot(); // one word per kernel slot, folding or not: the timeline stays aligned with the slots
     const unsigned grid = (unsigned) (num_tiles(rows) + 1); // CTA 0 reduces, CTA k > 0 owns tile k - 1
-    SB_CUDA(launch_kernel(ctx, ew_fold_kernel<ND, Body, FND, Final>, grid, kThreads, 0, rows, body, red_set(1), done, f));
+    auto kern = ew_fold_kernel<ND, Body, FND, Final>;
+    constexpr int smem = EwStage<Body>::cta;
+    static std::atomic<uint64_t> configured{0}; // the attribute is per device
+    const uint64_t bit = 1ull << (ctx->device & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+      SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured.fetch_or(bit, std::memory_order_release);
+    }
+    SB_CUDA(launch_kernel(ctx, kern, grid, kThreads, smem, rows, body, red_set(1), done, f));
     ctx->launches++;
     if (active) ver ^= 1;
     return SB_OK;
