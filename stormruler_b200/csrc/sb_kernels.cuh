@@ -245,20 +245,25 @@ __device__ __noinline__ void fold_reduce(const Fold<ND, Final>& f) {
   }
 }
 
-// Every other CTA: wait until the new version is complete. Lane 0 of each warp polls around L1 with a plain volatile
-// load, the warp follows; the scalars are then read by ordinary loads that miss L1 (nothing of this version's lines
-// can be there: nobody reads them before the flag) and find in L2 what CTA 0 wrote before its fence. An acquire load
-// would be the textbook form, but it drags a fence behind it that waits for the tile loads this thread has in flight
-// -- exactly the latency the fold is supposed to hide (profiles/r02_stepwise_folded_v2_acquire_poll_10M.json: the
-// element-wise kernels lost 15-40 % of their bandwidth to it).
+// Every other CTA: wait until the new version is complete. ONE thread per CTA polls, around L1 with a plain volatile
+// load and a short sleep between polls; the CTA follows through a barrier. The scalars are then read by ordinary loads
+// that miss L1 (nothing of this version's lines can be there: nobody reads them before the flag) and find in L2 what
+// CTA 0 wrote before its fence.
+//  * An acquire load would be the textbook form, but it drags a fence behind it that waits for whatever the thread has
+//    in flight (profiles/r02_stepwise_folded_v2_acquire_poll_10M.json).
+//  * One poller per warp without a pause turned the first wave of CTAs into 8 000 threads hammering one L2 line: the
+//    reducer's own loads and its flag store queued behind them, and every folding kernel at 10 M cells took 15-20 us
+//    longer than with the one-CTA final stage in front (profiles/r02_stepwise_folded_v7_tma_staged_poll_storm_10M.json).
 __device__ __forceinline__ void fold_wait(const int* ready) {
-  if ((threadIdx.x & 31) == 0) {
+  if (threadIdx.x == 0) {
     int v;
-    do {
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
+    while (v == 0) {
+      __nanosleep(100);
       asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(ready) : "memory");
-    } while (v == 0);
+    }
   }
-  __syncwarp();
+  __syncthreads();
 }
 
 // Generic tiled element-wise kernel. Body provides

@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
 // (sb_kernels.cuh: Fold, fold_reduce, fold_wait.) CTA 0 is a dedicated reducer and owns no tile; CTA k > 0 owns tile k - 1.
 // A tile's inputs -- the 512-byte runs of the body's NV input vectors for the four sub-iterations of each warp -- are
 // fetched by bulk copies (cp.async.bulk) into shared memory, all sixteen NV per warp issued by one lane before
-// anything else; THEN the CTA waits for the ready flag (one volatile poll per warp: no fence, no call), reads the solver
+// anything else; THEN the CTA waits for the ready flag (one thread polls, the CTA follows: no fence, no call), reads the solver
 // scalars from the new state version (Body::st is redirected to it) and consumes the stages. Nothing is held in
 // registers across the wait, the flag's round trip and the scalar loads run under the latency of the copies, and the
 // bytes in flight per SM are set by shared memory (NV x 16 KB per CTA: 7 / 4 / 3 / 2 resident CTAs for 2 / 3 / 4 / 5
@@ -388,7 +388,6 @@ __global__ void __launch_bounds__(kThreads, EwStage<Body>::min_ctas) ew_fold_ker
       for (int k = 0; k < NV; ++k) bulk_g2s(wbase + j * E::stage + k * 512, body.in(k) + r0, 512, &bars[warp][j]);
     }
   }
-  __syncwarp();
   const SolverState* st = &fold.blk->ver(active ? (fold.in ^ 1) : fold.in);
   if (active) fold_wait(&fold.blk->ready[fold.in ^ 1]);
   const bool stopped = __ldcg(&st->done) != 0; // the stopping rule has just fired: the iterate stays what it is
