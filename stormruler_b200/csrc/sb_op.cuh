@@ -388,6 +388,7 @@ __global__ void __launch_bounds__(kThreads, EwStage<Body>::min_ctas) ew_fold_ker
       for (int k = 0; k < NV; ++k) bulk_g2s(wbase + j * E::stage + k * 512, body.in(k) + r0, 512, &bars[warp][j]);
     }
   }
+  __syncwarp(); // the mbarriers lane 0 initialised are waited on by the whole warp
   const SolverState* st = &fold.blk->ver(active ? (fold.in ^ 1) : fold.in);
   if (active) fold_wait(&fold.blk->ready[fold.in ^ 1]);
   const bool stopped = __ldcg(&st->done) != 0; // the stopping rule has just fired: the iterate stays what it is
