@@ -23,7 +23,7 @@ int ensure_red_scratch(sb_ctx* ctx, int64_t n) {
     SB_CUDA(cudaFree(ctx->red.partials));
     ctx->red.partials = nullptr;
   }
-  const int64_t cap = tiles + tiles / 4 + 64;
+  const int64_t cap = (tiles + tiles / 4 + 64 + 1) & ~(int64_t) 1; // even: every partial set starts 16-byte aligned (bulk copies)
   SB_CUDA(cudaMalloc(&ctx->red.partials, sizeof(double) * 2 * kMaxDots * cap));
   ctx->red.cap_tiles = cap;
   return SB_OK;

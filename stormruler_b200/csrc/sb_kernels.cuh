@@ -209,31 +209,90 @@ struct Fold {
   unsigned long long* wait_ns = nullptr; // optional: how long CTA 0 waited for the other ranks' sums
 };
 
-// CTA 0 of a folding kernel, all threads. Deliberately NOT inlined: inlined, its register needs (the final stage keeps
-// 8 x ND partials in flight per thread, the all-reduce its mailbox addresses) became those of the whole kernel -- the
-// half update went from 32 to 85 registers, i.e. from eight resident CTAs per SM to two, and lost a quarter of its
-// bandwidth (profiles/r02_stepwise_folded_v2_acquire_poll_10M.json). As a call made by a CTA that owns no tile it lives
-// within the register budget the kernel's __launch_bounds__ gives the element-wise body, nothing is live across it,
-// and only that one CTA ever pays for what it spills.
+// CTA 0 of a folding kernel, all threads. Deliberately NOT inlined: inlined, its register needs became those of the
+// whole kernel -- the half update went from 32 to 85 registers, i.e. from eight resident CTAs per SM to two
+// (profiles/r02_stepwise_folded_v2_acquire_poll_10M.json). As a call made by a CTA that owns no tile it lives within
+// the register budget the kernel's __launch_bounds__ gives the element-wise body, nothing is live across it.
+// Every resident CTA of the kernel waits for this chain, so it is kept to one memory round trip per stage: the tile
+// partials arrive by bulk copy in the CTA's (otherwise unused) dynamic shared memory -- in one piece up to
+// `smem_bytes / (8 ND)` tiles, in pieces of a multiple of 256 tiles beyond, so that thread t still adds
+// partial[t], partial[t + 256], ... in that order -- while thread 0 already has the old state version in flight; one
+// fence, one flag store. (With the register-staged final stage of the one-CTA kernel, compiled under the 32-register
+// budget of the half update, the chain took 4 us at 617 tiles and 10 us at 4 937: profiles/r02_fold_reducer_chain.txt.)
 template<int ND, class Final>
-__device__ __noinline__ void fold_reduce(const Fold<ND, Final>& f) {
+__device__ __noinline__ void fold_reduce(const Fold<ND, Final>& f, unsigned char* smem, int smem_bytes) {
   __shared__ double s_fin[kMaxDots][kWarps];
-  if (threadIdx.x == 0) f.blk->ready[f.in] = 0; // nobody waits for it during this kernel
+  __shared__ __align__(8) uint64_t bar;
+  const unsigned long long t_start = (f.wait_ns != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  SolverState st; // thread 0: version `in`, fetched around L1 (its lines must not linger in this SM's L1)
+  if (threadIdx.x == 0) {
+    f.blk->ready[f.in] = 0; // nobody waits for it during this kernel
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&f.blk->ver(f.in));
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&st);
+#pragma unroll
+    for (int k = 0; k < (int) (sizeof(SolverState) / 8); ++k) dst[k] = __ldcg(src + k);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t) __cvta_generic_to_shared(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  double* buf = reinterpret_cast<double*>(smem);
+  const int64_t per_piece = ((int64_t) (smem_bytes / 8) / ND) & ~(int64_t) 255; // tiles per piece, a multiple of 256
+  double s[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) s[d] = 0.0;
+  uint32_t phase = 0;
+  for (int64_t base = 0; base < f.n_tiles; base += per_piece) {
+    const int64_t cnt = f.n_tiles - base < per_piece ? f.n_tiles - base : per_piece;
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t) (((cnt * 8) + 15) & ~(int64_t) 15); // partial sets are 16-byte aligned and padded
+      const uint32_t bar_s = (uint32_t) __cvta_generic_to_shared(&bar);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes * ND) : "memory");
+#pragma unroll
+      for (int d = 0; d < ND; ++d)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t) __cvta_generic_to_shared(buf + d * per_piece)),
+                     "l"(f.red.partials + (int64_t) d * f.red.cap_tiles + base), "r"(bytes), "r"(bar_s)
+                     : "memory");
+    }
+    {
+      uint32_t ok = 0;
+      const uint32_t bar_s = (uint32_t) __cvta_generic_to_shared(&bar);
+      while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar_s), "r"(phase)
+                     : "memory");
+      phase ^= 1u;
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+      for (int64_t q = threadIdx.x; q < cnt; q += kThreads) s[d] = __dadd_rn(s[d], buf[d * per_piece + q]);
+    __syncthreads(); // the next piece overwrites the buffer
+  }
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const double v = warp_butterfly(s[d]);
+    if (lane == 0) s_fin[d][warp] = v;
+  }
+  __syncthreads();
   double sums[ND];
-  final_stage<ND>(f.n_tiles, f.red, s_fin, sums);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      double t = s_fin[d][0];
+#pragma unroll
+      for (int w = 1; w < kWarps; ++w) t = __dadd_rn(t, s_fin[d][w]);
+      sums[d] = t;
+    }
+  }
   if (f.comm.mode == SB_COMM_P2P && f.comm.world > 1) {
     const unsigned long long t0 = (f.wait_ns != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0;
     allreduce_p2p<ND>(f.comm, sums);
     if (f.wait_ns != nullptr && threadIdx.x == 0) *f.wait_ns = globaltimer_ns() - t0;
   }
   if (threadIdx.x == 0) {
-    SolverState st; // version `in`, fetched around L1 (its lines must not linger in this SM's L1)
-    {
-      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&f.blk->ver(f.in));
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&st);
-#pragma unroll
-      for (int k = 0; k < (int) (sizeof(SolverState) / 8); ++k) dst[k] = __ldcg(src + k);
-    }
     Final fin = f.fin;
     fin.rec.st = &st;
     fin(sums);
@@ -241,7 +300,9 @@ __device__ __noinline__ void fold_reduce(const Fold<ND, Final>& f) {
     if (st.done) f.blk->final_() = st, f.blk->done = 1;
     if (f.bump != nullptr) f.bump->apply_seq = f.bump->apply_seq + 1; // the distributed apply in front of me is complete
     __threadfence();
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&f.blk->ready[f.in ^ 1]), "r"(1) : "memory");
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(&f.blk->ready[f.in ^ 1]), "r"(1) : "memory");
+    // one GPU, profiled run: the timeline word holds how long this chain took, first instruction to flag
+    if (f.wait_ns != nullptr && !(f.comm.mode == SB_COMM_P2P && f.comm.world > 1)) *f.wait_ns = globaltimer_ns() - t_start;
   }
 }
 

@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, EwStage<Body>::min_ctas) ew_fold_ker
   if (is_done(done)) return;
   const bool active = fold.n_tiles >= 0;
   if (blockIdx.x == 0) {
-    if (active) fold_reduce(fold);
+    if (active) fold_reduce(fold, sb_smem, E::cta);
     return;
   }
   const int64_t tile = (int64_t) blockIdx.x - 1;
