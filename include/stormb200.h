@@ -397,7 +397,7 @@ typedef struct sb_solver_opts {
   int32_t profile;        /* 1: bracket every kernel of the iteration with CUDA events (no graph) and
                              report the accumulated time per kernel slot in sb_solver_report.kernel_ms
                              (implies the stepwise schedule) */
-  int32_t schedule;       /* SB_SCHEDULE_*; 0 = automatic: the stepwise schedule (the faster one) */
+  int32_t schedule;       /* SB_SCHEDULE_*; 0 = automatic: the stepwise schedule (the fastest one) */
   int32_t timeline_iters; /* persistent schedule: record the in-kernel timeline of the first this-many
                              iterations into h_timeline (0 = off) */
   uint64_t* h_timeline;   /* [timeline_iters][SB_TIMELINE_WORDS], globaltimer nanoseconds, written by CTA 0:
@@ -410,18 +410,25 @@ typedef struct sb_solver_opts {
                              warp of this rank for a neighbour's halo values in apply k */
 } sb_solver_opts;
 
-/* Schedules of the fused CG / BiCGStab solvers (bit-identical results):
- *   STEPWISE   one kernel per step of the iteration, replayed as a CUDA graph: 3 / 5 launches per CG / BiCGStab
- *              iteration. The last stage of every reduction (final sum over the tile partials, all-reduce over the
- *              ranks through NVLink peer memory, scalar update) is folded into the kernel that consumes the result;
- *              NCCL mode keeps a one-CTA kernel + ncclAllReduce per reduction instead (5 / 8 launches);
+/* Schedules of the fused CG / BiCGStab solvers (bit-identical results; measurements: DESIGN.md 5d):
+ *   STEPWISE   one kernel per step of the iteration + a one-CTA kernel per reduction (final sum over the tile
+ *              partials, all-reduce over the ranks through NVLink peer memory or NCCL, scalar update), replayed
+ *              as a CUDA graph: 5 / 8 launches per CG / BiCGStab iteration. The fastest of the three on the B200
+ *              at every size measured, hence the automatic choice;
+ *   FOLDED     the same steps, but the last stage of every reduction is folded into the kernel that consumes the
+ *              result (its CTA 0 reduces and raises a flag, the other CTAs have their loads in flight and wait
+ *              for it): 3 / 5 launches per iteration. One GPU or SB_COMM_P2P. Saves the kernel boundaries but
+ *              makes the whole first wave of the consumer wait for a reducer that now runs on a loaded machine:
+ *              1-4 % slower than STEPWISE;
  *   PERSISTENT one cooperative kernel runs the whole iteration loop; steps are separated by grid-wide barriers
  *              in global memory, the reductions and the all-reduce happen inside the barrier. Needs the coefficient
- *              form; multi-GPU needs SB_COMM_P2P. Measured slower than STEPWISE for BiCGStab (the barrier costs more
- *              than a graph kernel boundary), on par for CG; kept for its in-kernel timeline. */
+ *              form; multi-GPU needs SB_COMM_P2P. A grid barrier (5-7 us: the arriving CTA first drains its stores)
+ *              costs more than a kernel boundary inside a replayed graph (2.7 us): 5 % slower than STEPWISE for
+ *              BiCGStab, on par for CG; kept for its in-kernel timeline (sb_solver_opts::h_timeline). */
 #define SB_SCHEDULE_AUTO 0
 #define SB_SCHEDULE_STEPWISE 1
 #define SB_SCHEDULE_PERSISTENT 2
+#define SB_SCHEDULE_FOLDED 3
 #define SB_TIMELINE_WORDS 20
 
 #define SB_MAX_KERNEL_SLOTS 8
@@ -441,11 +448,13 @@ typedef struct sb_solver_report {
   double kernel_ms[SB_MAX_KERNEL_SLOTS]; /* profile=1: total device time per kernel slot, in launch order
                                             (CG: apply+dot, update+dot, direction; BiCGStab: direction,
                                             apply+dot, half update, apply+2 dots, final update+2 dots) */
-  int32_t schedule;    /* SB_SCHEDULE_STEPWISE or SB_SCHEDULE_PERSISTENT: the one that ran */
-  double wait_ms[SB_MAX_KERNEL_SLOTS];   /* profile=1: per kernel slot, the longest in-kernel wait of each launch summed
-                                            over the iterations -- apply slots: a boundary CTA waiting for a neighbour's
-                                            halo values; the other slots: CTA 0 waiting for the other ranks' partial sums
-                                            of the reduction it folds (0 on one GPU) */
+  int32_t schedule;    /* SB_SCHEDULE_STEPWISE, _FOLDED or _PERSISTENT: the one that ran */
+  double wait_ms[SB_MAX_KERNEL_SLOTS];   /* profile=1: per kernel slot, in-kernel waits summed over the iterations.
+                                            Apply slots: the longest wait of a boundary CTA for a neighbour's halo
+                                            values + (STEPWISE) the wait of the one-CTA stage behind the apply for
+                                            the other ranks' partial sums. Other slots: the wait for the other
+                                            ranks' sums of the reduction behind / (FOLDED) in front of the step;
+                                            FOLDED on one GPU: the duration of the reducer's chain instead */
 } sb_solver_report;
 
 SB_API int sb_cg_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b,

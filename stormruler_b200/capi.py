@@ -15,7 +15,7 @@ SB_OK = 0
 FORM_FAITHFUL, FORM_COEF = 0, 1
 PART_METIS, PART_SLAB = 0, 1
 COMM_NCCL, COMM_P2P = 0, 1
-SCHEDULE_AUTO, SCHEDULE_STEPWISE, SCHEDULE_PERSISTENT = 0, 1, 2
+SCHEDULE_AUTO, SCHEDULE_STEPWISE, SCHEDULE_PERSISTENT, SCHEDULE_FOLDED = 0, 1, 2, 3
 TIMELINE_WORDS = 20
 COMM_BLOB_BYTES = 256
 ASSIGN, ADD_ASSIGN, SUB_ASSIGN, MUL_ASSIGN, DIV_ASSIGN = range(5)

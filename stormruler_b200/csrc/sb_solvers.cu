@@ -248,7 +248,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   SB_REQUIRE(x != b, "x and b must not alias");
   SB_REQUIRE(opts->num_iterations >= 0, "num_iterations must be >= 0");
   SB_REQUIRE(hist_cap >= 0 && trace_cap >= 0, "negative capacity");
-  SB_REQUIRE(opts->schedule >= SB_SCHEDULE_AUTO && opts->schedule <= SB_SCHEDULE_PERSISTENT, "unknown schedule");
+  SB_REQUIRE(opts->schedule >= SB_SCHEDULE_AUTO && opts->schedule <= SB_SCHEDULE_FOLDED, "unknown schedule");
   SB_REQUIRE(opts->timeline_iters >= 0 && (opts->timeline_iters == 0 || opts->h_timeline != nullptr), "timeline buffer");
   const int64_t n = op->d.n;
   SB_CUDA(cudaSetDevice(ctx->device));
@@ -258,14 +258,20 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   SB_TRY(ensure_records(ctx, h_hist ? hist_cap : 0, h_trace ? trace_cap : 0));
   SB_TRY(ensure_red_scratch(ctx, n));
   const bool profile = opts->profile != 0 && !opts->use_graph;
-  // Schedule: stepwise (one kernel per step, reductions folded into their consumers, graph replay) unless the caller
-  // asks for the persistent whole-solve kernel. Measured on the B200 (profiles/r02_persistent_*.json):
-  // a grid-wide barrier in global memory costs 5-7 us (the arriving CTA must first drain its stores), a kernel
-  // boundary inside a replayed graph 2.7 us, so five launches per BiCGStab iteration beat five barriers at every size.
+  // Schedule: stepwise (one kernel per step + a one-CTA stage per reduction, graph replay) unless the caller asks for
+  // one of the other two. Measured on the B200 (profiles/r02_*): a grid-wide barrier in global memory
+  // costs 5-7 us (the arriving CTA must first drain its stores) against 2.7 us for a kernel boundary inside a replayed
+  // graph, and a folded reduction makes every resident CTA of the consumer wait for a reducer that runs on a loaded
+  // machine (4-9 us) instead of on an idle one (3 us + one boundary).
   bool persistent = opts->schedule == SB_SCHEDULE_PERSISTENT && !profile && mega_supported(ctx, op);
   if (opts->schedule == SB_SCHEDULE_PERSISTENT && !persistent) {
     set_error("the persistent schedule needs a coefficient-form operator (blocked layout), no per-kernel profile, and "
               "in-kernel (P2P) collectives");
+    return SB_ERR_INVALID;
+  }
+  const bool can_fold = !(ctx->debug & 4) && (ctx->comm.world <= 1 || (ctx->comm.mode == SB_COMM_P2P && op->distributed));
+  if (opts->schedule == SB_SCHEDULE_FOLDED && !can_fold) {
+    set_error("the folded schedule needs in-kernel (P2P) collectives over a distributed operator, or one GPU");
     return SB_ERR_INVALID;
   }
 
@@ -289,10 +295,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   } else {
     S.rt = ctx->work[2], S.t = ctx->work[3], S.v = ctx->work[4];
   }
-  // The reductions are folded into their consumers wherever the all-reduce can run inside a kernel (one GPU, or
-  // peer-memory collectives over a distributed operator); NCCL mode keeps the one-CTA final stages.
-  S.folded = !persistent && !(ctx->debug & 4) &&
-             (ctx->comm.world <= 1 || (ctx->comm.mode == SB_COMM_P2P && op->distributed));
+  S.folded = opts->schedule == SB_SCHEDULE_FOLDED;
   SolveGuard guard;
   const int64_t launches0 = ctx->launches;
   SB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -303,7 +306,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   std::vector<cudaEvent_t>& prof_events = guard.events; // profile events are appended behind ev_mid / evs
   const int per_iter = (kind == Kind::Cg) ? 3 : 5;       // profiled kernel slots
   size_t prof_first = 0;
-  const int64_t tl_words = (profile && S.folded) ? (int64_t) per_iter * opts->num_iterations : 0;
+  const int64_t tl_words = profile ? (int64_t) per_iter * opts->num_iterations : 0;
   if (tl_words > 0) { // in-kernel waits of the profiled run: one word per kernel slot and iteration
     if (tl_words > ctx->timeline_cap) {
       SB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -403,7 +406,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   SB_CUDA(cudaEventElapsedTime(&ms_iter, ev_mid, ctx->ev1));
   report->iter_ms = ms_iter;
   report->n_kernel_slots = persistent ? 0 : per_iter;
-  report->schedule = persistent ? SB_SCHEDULE_PERSISTENT : SB_SCHEDULE_STEPWISE;
+  report->schedule = persistent ? SB_SCHEDULE_PERSISTENT : (S.folded ? SB_SCHEDULE_FOLDED : SB_SCHEDULE_STEPWISE);
   for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->kernel_ms[k] = 0.0;
   for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->wait_ms[k] = 0.0;
   if (profile && !persistent) {
