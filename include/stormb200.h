@@ -408,7 +408,34 @@ typedef struct sb_solver_opts {
                              the all-reduce included); [11+b] reducing barriers: ns the CTA that ran the reduction
                              waited for the other ranks' sums after posting its own; [16+k] longest wait of any
                              warp of this rank for a neighbour's halo values in apply k */
+  uint32_t tuning;        /* stepwise schedule: SB_TUNE_* bits, 0 = the defaults (what SB_TUNE_DEFAULT names). Results
+                             are bit-identical whatever the bits; they exist so that one process can A/B them */
 } sb_solver_opts;
+
+/* Tuning bits of the stepwise schedule (sb_solver_opts::tuning; measurements: DESIGN.md 6):
+ *   PUSH_ON_PRODUCE  multi-GPU, SB_COMM_P2P: the kernel that PRODUCES an apply's input vector (CG: the direction update;
+ *                    BiCGStab: the direction and the half update) stores its boundary values straight into the
+ *                    neighbours' halo tails as soon as a boundary tile is computed (boundary tiles are scheduled
+ *                    first); the apply kernel has no pack CTAs and normally finds the halo flags already raised;
+ *   NO_ACK           multi-GPU: the in-apply halo push skips the ack round (valid inside the fused solvers: between two
+ *                    applies that write the same halo tail there is always an all-reduce);
+ *   STREAM_OPERATOR  the apply kernel's bulk copies of the operator slices carry an L2 evict-first policy, so that a
+ *                    rank whose vectors fit the 126 MB L2 (<= ~1.3 M cells) keeps them there between the kernels;
+ *   PDL_FINAL        the one-CTA final stages are launched with programmatic stream serialization (resident while
+ *                    the producer drains); PDL_AFTER_FINAL: so are the kernels that follow a final stage (resident,
+ *                    operator slices prefetched, while the one-CTA stage runs on an otherwise idle machine);
+ *   OFF              (with no other bit) switch every optional mechanism off: the round-1 behaviour. */
+#define SB_TUNE_PUSH_ON_PRODUCE 1u
+#define SB_TUNE_NO_ACK 2u
+#define SB_TUNE_STREAM_OPERATOR 4u
+#define SB_TUNE_PDL_FINAL 8u
+#define SB_TUNE_PDL_AFTER_FINAL 16u
+#define SB_TUNE_IN_KERNEL_REDUCER 64u /* every reduction is finished by the LAST CTA of the kernel that produces it: it
+                                         takes the tile partials as they appear (the value is the flag), runs the
+                                         all-reduce over the ranks and the scalar update; no one-CTA kernels between
+                                         the steps (3 / 5 launches per CG / BiCGStab iteration), nobody waits in-kernel */
+#define SB_TUNE_PDL_APPLY 32u /* the apply kernels too (they follow an element-wise kernel; slice prefetch under its tail) */
+#define SB_TUNE_OFF 0x80000000u
 
 /* Schedules of the fused CG / BiCGStab solvers (bit-identical results; measurements: DESIGN.md 5d):
  *   STEPWISE   one kernel per step of the iteration + a one-CTA kernel per reduction (final sum over the tile
@@ -455,6 +482,9 @@ typedef struct sb_solver_report {
                                             the other ranks' partial sums. Other slots: the wait for the other
                                             ranks' sums of the reduction behind / (FOLDED) in front of the step;
                                             FOLDED on one GPU: the duration of the reducer's chain instead */
+  double ar_wait_ms[SB_MAX_KERNEL_SLOTS]; /* profile=1, STEPWISE on several GPUs: per kernel slot, how long the one-CTA
+                                            final stage behind the slot waited for the other ranks' sums after posting
+                                            its own (rank skew + one NVLink crossing), summed over the iterations */
 } sb_solver_report;
 
 SB_API int sb_cg_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b,

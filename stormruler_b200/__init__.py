@@ -337,6 +337,7 @@ class _FusedSolver:
     record: bool = True
     schedule: int = 0          # SCHEDULE_AUTO / SCHEDULE_STEPWISE / SCHEDULE_PERSISTENT (include/stormb200.h)
     timeline_iters: int = 0    # persistent schedule: in-kernel timeline of the first iterations -> self.timeline
+    tuning: int = 0            # capi.TUNE_* bits of the stepwise schedule (0 = the library's defaults)
     history: np.ndarray = field(default_factory=lambda: np.zeros(0))
     trace: np.ndarray = field(default_factory=lambda: np.zeros(0))
     timeline: np.ndarray = field(default_factory=lambda: np.zeros((0, 20), np.uint64))
@@ -344,6 +345,7 @@ class _FusedSolver:
     iter_ms: float = 0.0
     kernel_ms: tuple = ()
     wait_ms: tuple = ()
+    ar_wait_ms: tuple = ()
     launches: int = 0
     schedule_used: int = 0
     _entry = ""
@@ -355,7 +357,7 @@ class _FusedSolver:
         opts = capi.SolverOpts(int(self.num_iterations), float(self.absolute_error_tolerance),
                                float(self.relative_error_tolerance), int(self.check_every),
                                int(bool(self.use_graph)), int(bool(self.profile)), int(self.schedule),
-                               int(self.timeline_iters), tl.ctypes.data_as(C.POINTER(C.c_uint64)))
+                               int(self.timeline_iters), tl.ctypes.data_as(C.POINTER(C.c_uint64)), int(self.tuning))
         rep = capi.SolverReport()
         cap_h = self.num_iterations + 2 if self.record else 0
         cap_t = self._trace_per_iter * self.num_iterations + 8 if self.record else 0
@@ -370,6 +372,7 @@ class _FusedSolver:
         self.solve_ms, self.iter_ms, self.launches = rep.solve_ms, rep.iter_ms, int(rep.launches)
         self.kernel_ms = tuple(rep.kernel_ms[k] for k in range(rep.n_kernel_slots))
         self.wait_ms = tuple(rep.wait_ms[k] for k in range(rep.n_kernel_slots))
+        self.ar_wait_ms = tuple(rep.ar_wait_ms[k] for k in range(rep.n_kernel_slots))
         self.schedule_used = int(rep.schedule)
         self.timeline = tl[:min(int(self.timeline_iters), self.iteration)] if rep.schedule == capi.SCHEDULE_PERSISTENT else tl[:0]
         return bool(rep.converged)
@@ -426,12 +429,12 @@ class GmresSolver:
 
 
 def solve_host(ctx: Context, op: FvmOperator, solver: str, x_host: np.ndarray, b_host: np.ndarray,
-               num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6, use_graph=False, check_every=0, schedule=0):
+               num_iterations=2000, abs_tol=1e-6, rel_tol=1e-6, use_graph=False, check_every=0, schedule=0, tuning=0):
     """sb_solve_host: host buffers in/out, copies inside the call. x_host is updated in place."""
     assert x_host.dtype == np.float64 and x_host.flags.c_contiguous
     b_host = _f64(b_host)
     opts = capi.SolverOpts(int(num_iterations), float(abs_tol), float(rel_tol), int(check_every), int(use_graph), 0,
-                           int(schedule), 0, None)
+                           int(schedule), 0, None, int(tuning))
     rep = capi.SolverReport()
     capi.check(ctx.lib.sb_solve_host(ctx.handle, op.handle, solver.encode(), x_host.ctypes.data_as(capi.f64p),
                                      b_host.ctypes.data_as(capi.f64p), C.byref(opts), C.byref(rep), None, 0))

@@ -17,6 +17,7 @@ PART_METIS, PART_SLAB = 0, 1
 COMM_NCCL, COMM_P2P = 0, 1
 SCHEDULE_AUTO, SCHEDULE_STEPWISE, SCHEDULE_PERSISTENT, SCHEDULE_FOLDED = 0, 1, 2, 3
 TIMELINE_WORDS = 20
+TUNE_PUSH_ON_PRODUCE, TUNE_NO_ACK, TUNE_STREAM_OPERATOR, TUNE_PDL_FINAL, TUNE_PDL_AFTER_FINAL, TUNE_PDL_APPLY, TUNE_IN_KERNEL_REDUCER, TUNE_OFF = 1, 2, 4, 8, 16, 32, 64, 0x80000000
 COMM_BLOB_BYTES = 256
 ASSIGN, ADD_ASSIGN, SUB_ASSIGN, MUL_ASSIGN, DIV_ASSIGN = range(5)
 OP_VEC0, OP_SCAL0 = 0, 8
@@ -83,7 +84,8 @@ class Chain(C.Structure):      # sb_chain: y = ((base +- c0*x0) +- c1*x1) ...
 class SolverOpts(C.Structure):
     _fields_ = [("num_iterations", C.c_int64), ("abs_tol", C.c_double), ("rel_tol", C.c_double),
                 ("check_every", C.c_int32), ("use_graph", C.c_int32), ("profile", C.c_int32),
-                ("schedule", C.c_int32), ("timeline_iters", C.c_int32), ("h_timeline", C.POINTER(C.c_uint64))]
+                ("schedule", C.c_int32), ("timeline_iters", C.c_int32), ("h_timeline", C.POINTER(C.c_uint64)),
+                ("tuning", C.c_uint32)]
 
 
 class GmresOpts(C.Structure):
@@ -96,7 +98,7 @@ class SolverReport(C.Structure):
                 ("abs_err", C.c_double), ("rel_err", C.c_double), ("n_hist", C.c_int64),
                 ("n_trace", C.c_int64), ("solve_ms", C.c_double), ("iter_ms", C.c_double),
                 ("launches", C.c_int64), ("n_kernel_slots", C.c_int32), ("kernel_ms", C.c_double * 8),
-                ("schedule", C.c_int32), ("wait_ms", C.c_double * 8)]
+                ("schedule", C.c_int32), ("wait_ms", C.c_double * 8), ("ar_wait_ms", C.c_double * 8)]
 
 
 # name -> (restype, argtypes); the keys are exactly the SB_API symbols of include/stormb200.h

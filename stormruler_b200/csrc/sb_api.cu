@@ -15,6 +15,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static __global__ void fill_sentinel_kernel(unsigned long long* p, int64_t n) {
+  const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = kArSentinel;
+}
+
 int ensure_red_scratch(sb_ctx* ctx, int64_t n) {
   const int64_t tiles = num_tiles(n) > 0 ? num_tiles(n) : 1;
   if (tiles <= ctx->red.cap_tiles) return SB_OK;
@@ -24,8 +29,13 @@ int ensure_red_scratch(sb_ctx* ctx, int64_t n) {
     ctx->red.partials = nullptr;
   }
   const int64_t cap = (tiles + tiles / 4 + 64 + 1) & ~(int64_t) 1; // even: every partial set starts 16-byte aligned (bulk copies)
-  SB_CUDA(cudaMalloc(&ctx->red.partials, sizeof(double) * 2 * kMaxDots * cap));
+  // two ordinary sets + the sentinel-managed set of the in-kernel reducer
+  SB_CUDA(cudaMalloc(&ctx->red.partials, sizeof(double) * 3 * kMaxDots * cap));
   ctx->red.cap_tiles = cap;
+  ctx->red.slots = ctx->red.partials + 2 * kMaxDots * cap;
+  const int64_t words = kMaxDots * cap;
+  fill_sentinel_kernel<<<(unsigned) ((words + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<unsigned long long*>(ctx->red.slots), words);
+  SB_CUDA(cudaGetLastError());
   return SB_OK;
 }
 

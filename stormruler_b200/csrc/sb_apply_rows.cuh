@@ -19,6 +19,7 @@ struct OpDev {
   const unsigned char* blk = nullptr;
   int32_t slice_bytes = 0;
   int32_t debug = 0; // experiments only (SB_DEBUG env): bit0 = skip the gathers
+  int32_t stream_hint = 0; // per call: the bulk copies of the slice records carry an L2 evict-first policy (SB_TUNE_STREAM_OPERATOR)
   int32_t zero = 0;  // always 0, but only known at run time: lets the kernel tie an instruction to a value it
                      // must wait for without changing the arithmetic (see apply_kernel_tma)
 };

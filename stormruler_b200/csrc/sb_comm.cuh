@@ -53,6 +53,12 @@ struct HaloDev {
   int64_t send_ptr[kMaxRanks + 1] = {};
   int64_t send_dst[kMaxRanks] = {}; // element offset inside neighbour k's vector
   const int32_t* send_idx = nullptr; // device
+  // push-on-produce plan (sb_op.cu: attach_halo): the send list once more, sorted by the 2048-row tile of its source
+  // cell. push_ptr[q] .. push_ptr[q + 1]: the entries of boundary tile first_boundary_tile + q; an entry is
+  // {source cell (local index) | neighbour slot << 28, element offset inside that neighbour's vector}.
+  const int32_t* push_ptr = nullptr;
+  const int2* push_entry = nullptr;
+  int32_t n_push_tiles = 0;          // tiles first_boundary_tile .. last owned tile
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -139,6 +145,41 @@ __device__ __forceinline__ void halo_pack_role(const CommDev& comm, const HaloDe
       // ONE system fence, then posted (relaxed) flag stores: fence + relaxed store is a release, and the
       // stores to the neighbours do not wait for each other. (A st.release.sys per neighbour serialises a
       // full fence round trip per flag: measured ~25 us per apply with 4-7 neighbours at 8 GPUs.)
+      __threadfence_system();
+      for (int k = 0; k < halo.n_nbr; ++k)
+        st_relaxed_sys(&comm.ctrl(halo.nbr_rank[k])->halo_flag[comm.rank], seq);
+    }
+  }
+}
+
+// ---- halo push by the PRODUCER of an apply's input (SB_TUNE_PUSH_ON_PRODUCE) ----------------------------------------
+// Called by every CTA of a pushing element-wise kernel that owns a boundary tile, right after the tile's values have
+// been stored to y: the CTA forwards the values its neighbours need (this tile's share of the send list) into their
+// halo tails, fences, takes a ticket; the CTA that takes the last ticket raises halo_flag[me] = #(next apply) at every
+// neighbour. Boundary tiles are the first CTAs of the producer's grid, so the values travel while the rest of the
+// kernel, the kernel boundary and the apply's interior tiles run; the apply itself has no pack CTAs and its boundary
+// tiles normally find the flags up. No ack round: a producer runs behind an all-reduce to which every neighbour
+// contributed only after its previous apply of this vector had completed (sb_op.cuh: ApplyDist::no_ack).
+__device__ __forceinline__ void halo_push_tile(const CommDev& comm, const HaloDev& halo, const double* y, int64_t y_off,
+                                               int64_t tile) {
+  __syncthreads(); // the tile's stores to y are visible to the whole CTA
+  CommCtrl* me = comm.ctrl(comm.rank);
+  const int q = (int) (tile - halo.first_boundary_tile);
+  const int32_t beg = halo.push_ptr[q], end = halo.push_ptr[q + 1];
+  for (int32_t i = beg + (int32_t) threadIdx.x; i < end; i += kThreads) {
+    const int2 en = halo.push_entry[i];
+    const int k = (int) ((uint32_t) en.x >> 28);
+    const double v = __ldcg(y + (en.x & 0x0fffffff));
+    double* dst = reinterpret_cast<double*>(comm.base[halo.nbr_rank[k]] + y_off) + en.y;
+    *dst = v;
+  }
+  __threadfence_system(); // my peer stores are performed before the ticket below is taken
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long ticket = atomicAdd(&me->push_ticket, 1ull);
+    if (ticket == (unsigned long long) halo.n_push_tiles - 1) {
+      me->push_ticket = 0;
+      const unsigned long long seq = ld_acquire_sys(&me->apply_seq) + 1; // the apply that will consume these values
       __threadfence_system();
       for (int k = 0; k < halo.n_nbr; ++k)
         st_relaxed_sys(&comm.ctrl(halo.nbr_rank[k])->halo_flag[comm.rank], seq);

@@ -75,7 +75,8 @@ struct CommCtrl {
   unsigned long long error;                // set when a spin wait gave up (code | waited-for rank); once non-zero every
                                            // later wait of this rank returns at once, so queued kernels drain, and the
                                            // host reports SB_ERR_COMM (sb_comm_status, end of every fused solve)
-  unsigned long long pad[4];
+  unsigned long long push_ticket;          // last-tile detection of a pushing producer kernel (halo_push_tile)
+  unsigned long long pad[3];
   unsigned long long ar_slot[2][kMaxRanks][4]; // all-reduce mailboxes (value is the flag), by seq parity
 };
 static_assert(sizeof(CommCtrl) <= kCtrlBytes, "control block too large");
@@ -96,6 +97,8 @@ struct RedScratch {
   double* partials = nullptr; // [kMaxDots][cap_tiles]
   int64_t cap_tiles = 0;
   double* result = nullptr;   // [64] result slots of the stand-alone dots
+  double* slots = nullptr;    // [kMaxDots][cap_tiles] partial sums of launches with an in-kernel reducer (sb_finals.cuh):
+                              // a NaN sentinel everywhere between kernels, the value is the flag
 };
 
 } // namespace sb
@@ -179,6 +182,10 @@ struct sb_ctx {
   unsigned long long* d_timeline = nullptr;
   int64_t timeline_cap = 0;
   unsigned long long spin_timeout_ns = 0; // bound of every device-side spin wait (SB_SPIN_TIMEOUT_S, default 120 s)
+  bool pdl_launch = false; // the next launch_kernel carries the programmatic-serialization attribute (fused solvers:
+                           // sb_solver_opts::tuning, SB_TUNE_PDL_*); every kernel of the library starts with
+                           // griddepcontrol.launch_dependents + griddepcontrol.wait, so any launch may carry it
+  uint32_t tuning = 0;     // SB_TUNE_* bits of the solve in progress (read by the launch helpers)
 };
 
 namespace sb {
@@ -188,8 +195,23 @@ inline cudaError_t launch_kernel(sb_ctx* ctx, void (*kernel)(KArgs...), unsigned
                                  Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr{};
+  if (ctx->pdl_launch) { // programmatic dependent launch: resident early, blocks in griddepcontrol.wait (sb_comm.cuh)
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+  }
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// Launches made while one of these is alive carry the programmatic-serialization attribute (if `on`).
+struct PdlScope {
+  sb_ctx* ctx;
+  PdlScope(sb_ctx* c, bool on) : ctx(c) { ctx->pdl_launch = on; }
+  ~PdlScope() { ctx->pdl_launch = false; }
+  PdlScope(const PdlScope&) = delete;
+  PdlScope& operator=(const PdlScope&) = delete;
+};
 
 int ensure_red_scratch(sb_ctx* ctx, int64_t n);
 // vector storage: pool block in multi-GPU mode, cudaMalloc otherwise (zero-filled either way)

@@ -34,6 +34,10 @@ __device__ __forceinline__ double warp_butterfly(double v) {
   return v;
 }
 
+} // namespace sb
+#include "sb_finals.cuh" // Recorder, the solvers' scalar updates, the in-kernel reducer (needs warp_butterfly)
+namespace sb {
+
 // First element handled by this lane in sub-iteration j of tile `tile` (= blockIdx.x, except in the
 // distributed apply kernel whose first CTAs are halo-pack CTAs).
 __device__ __forceinline__ int64_t lane_elem(int64_t tile, int j) {
@@ -62,7 +66,8 @@ __device__ __forceinline__ void block_reduce_partials(double (&acc)[ND], const R
     double s = s_w[d][0];
 #pragma unroll
     for (int w = 1; w < kWarps; ++w) s = __dadd_rn(s, s_w[d][w]);
-    red.partials[(int64_t) d * red.cap_tiles + tile] = s;
+    // one relaxed store: when the launch has an in-kernel reducer (sb_finals.cuh) the slot is being polled
+    deposit_partial(red.partials + (int64_t) d * red.cap_tiles + tile, s);
   }
 }
 
@@ -119,7 +124,8 @@ __device__ __forceinline__ void final_stage(int64_t n_tiles, const RedPtrs& red,
 // thread: that is where the solver scalars (alpha, beta, residual, stop flag) are updated.
 template<int ND, class Final>
 __global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles, RedPtrs red, Final fin, CommDev comm,
-                                                                CommCtrl* bump, const int* __restrict__ done) {
+                                                                CommCtrl* bump, const int* __restrict__ done,
+                                                                unsigned long long* wait_ns) {
   pdl_trigger();
   pdl_wait();
   if (is_done(done)) return;
@@ -127,7 +133,11 @@ __global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles,
   double sums[ND];
   final_stage<ND>(n_tiles, red, s_w, sums);
   // multi-GPU, P2P mode: exchange the rank sums with every peer inside this kernel (rank-ordered total)
-  if (comm.mode == SB_COMM_P2P && comm.world > 1) allreduce_p2p<ND>(comm, sums);
+  if (comm.mode == SB_COMM_P2P && comm.world > 1) {
+    const unsigned long long t0 = (wait_ns != nullptr && threadIdx.x == 0) ? globaltimer_ns() : 0;
+    allreduce_p2p<ND>(comm, sums);
+    if (wait_ns != nullptr && threadIdx.x == 0) *wait_ns = globaltimer_ns() - t0;
+  }
   if (threadIdx.x == 0) {
     fin(sums);
     if (bump != nullptr) bump->apply_seq = bump->apply_seq + 1; // the distributed apply in front of me is complete
@@ -159,22 +169,25 @@ int nccl_allreduce_sum(sb_ctx* ctx, double* d_buf, int count); // sb_comm.cu
 
 // Launch helper shared by all reducing kernels: the one-CTA final stage, right behind the producer.
 template<int ND, class Final>
-inline int launch_final(sb_ctx* ctx, int64_t n, const Final& fin, const int* done, CommCtrl* bump = nullptr) {
+inline int launch_final(sb_ctx* ctx, int64_t n, const Final& fin, const int* done, CommCtrl* bump = nullptr,
+                        unsigned long long* ar_wait_ns = nullptr, bool pdl = false) {
   const RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
+  unsigned long long* const no_wait = nullptr;
   if (ctx->debug & 4) { // experiment: rank-local sums only
-    SB_CUDA(launch_kernel(ctx, final_reduce_kernel<ND, Final>, 1, kThreads, 0, num_tiles(n), red, fin, CommDev{}, bump, done));
+    SB_CUDA(launch_kernel(ctx, final_reduce_kernel<ND, Final>, 1, kThreads, 0, num_tiles(n), red, fin, CommDev{}, bump, done, no_wait));
     ctx->launches++;
     return SB_OK;
   }
   if (ctx->comm.mode == SB_COMM_NCCL && ctx->comm.world > 1) {
     SB_CUDA(launch_kernel(ctx, final_reduce_kernel<ND, StoreFinal<ND>>, 1, kThreads, 0, num_tiles(n), red,
-                          StoreFinal<ND>{ctx->d_ar}, CommDev{}, (CommCtrl*) nullptr, done));
+                          StoreFinal<ND>{ctx->d_ar}, CommDev{}, (CommCtrl*) nullptr, done, no_wait));
     SB_TRY(nccl_allreduce_sum(ctx, ctx->d_ar, ND));
     SB_CUDA(launch_kernel(ctx, scalar_final_kernel<ND, Final>, 1, 1, 0, (const double*) ctx->d_ar, fin, done));
     ctx->launches += 2;
     return SB_OK;
   }
-  SB_CUDA(launch_kernel(ctx, final_reduce_kernel<ND, Final>, 1, kThreads, 0, num_tiles(n), red, fin, ctx->comm, bump, done));
+  PdlScope pdl_scope(ctx, pdl);
+  SB_CUDA(launch_kernel(ctx, final_reduce_kernel<ND, Final>, 1, kThreads, 0, num_tiles(n), red, fin, ctx->comm, bump, done, ar_wait_ns));
   ctx->launches++;
   return SB_OK;
 }

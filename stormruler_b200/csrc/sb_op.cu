@@ -265,6 +265,33 @@ static int attach_halo(sb_ctx* ctx, const sb_local_mesh* loc, sb_op* op) {
     SB_CUDA(cudaMemcpy(op->d_send_idx, loc->send_idx, sizeof(int32_t) * (size_t) total, cudaMemcpyHostToDevice));
   }
   h.send_idx = op->d_send_idx;
+  // push-on-produce plan: the same entries sorted by the tile of their source cell (stable: within a tile they keep the
+  // neighbour-major order of the send list), so that the CTA that produces a boundary tile can forward its share
+  const int64_t owned_tiles = num_tiles(loc->n_owned);
+  h.n_push_tiles = (int32_t) (owned_tiles - h.first_boundary_tile);
+  if (total > 0 && h.n_push_tiles > 0 && loc->n_owned < (1 << 28) && total < INT32_MAX) {
+    std::vector<int32_t> ptr((size_t) h.n_push_tiles + 1, 0);
+    for (int64_t i = 0; i < total; ++i) {
+      const int64_t q = loc->send_idx[i] / kTile - h.first_boundary_tile;
+      SB_REQUIRE(q >= 0 && q < h.n_push_tiles, "send_idx names a cell in front of the boundary block of the local order");
+      ptr[(size_t) q + 1]++;
+    }
+    for (int32_t q = 0; q < h.n_push_tiles; ++q) ptr[(size_t) q + 1] += ptr[(size_t) q];
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+    std::vector<int2> entry((size_t) total);
+    for (int k = 0; k < loc->n_nbr; ++k)
+      for (int64_t i = loc->send_ptr[k]; i < loc->send_ptr[k + 1]; ++i) {
+        const int64_t q = loc->send_idx[i] / kTile - h.first_boundary_tile;
+        const int64_t dst = loc->send_dst[k] + (i - loc->send_ptr[k]);
+        SB_REQUIRE(dst >= 0 && dst < INT32_MAX, "halo offset does not fit 31 bits");
+        entry[(size_t) fill[(size_t) q]++] = make_int2((int32_t) ((uint32_t) loc->send_idx[i] | ((uint32_t) k << 28)), (int32_t) dst);
+      }
+    SB_CUDA(cudaMalloc(&op->d_push_ptr, sizeof(int32_t) * ptr.size()));
+    SB_CUDA(cudaMemcpy(op->d_push_ptr, ptr.data(), sizeof(int32_t) * ptr.size(), cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMalloc(&op->d_push_entry, sizeof(int2) * entry.size()));
+    SB_CUDA(cudaMemcpy(op->d_push_entry, entry.data(), sizeof(int2) * entry.size(), cudaMemcpyHostToDevice));
+    h.push_ptr = op->d_push_ptr, h.push_entry = op->d_push_entry;
+  }
   return SB_OK;
 }
 
@@ -327,6 +354,8 @@ int sb_op_destroy(sb_ctx* ctx, sb_op* op) {
   SB_CUDA(cudaStreamSynchronize(ctx->stream));
   for (void* b : op->buffers) cudaFree(b);
   cudaFree(op->d_send_idx);
+  cudaFree(op->d_push_ptr);
+  cudaFree(op->d_push_entry);
   delete op;
   return SB_OK;
 }
@@ -424,7 +453,9 @@ int sb_apply_accumulate(sb_ctx* ctx, const sb_op* op, double dt, const double* x
              "sb_apply_accumulate needs a faithful-form operator (the per-face terms, not dt-scaled coefficients)");
   OpDev d = op->d;
   d.dt = dt, d.prefill = 2;
-  return launch_apply<0, false>(ctx, op, x, y, NoEpi{}, NoFinal{}, nullptr, &d);
+  ApplyOpts ao;
+  ao.per_call = &d;
+  return launch_apply<0, false>(ctx, op, x, y, NoEpi{}, NoFinal{}, nullptr, ao);
 }
 
 } // extern "C"

@@ -36,12 +36,14 @@ struct ApplyDist {
   int32_t no_ack = 0;          // 1: skip the ack round before the halo push. Valid inside the fused solvers: between two
                                // applies that write the same halo tail there is always an all-reduce, and a rank
                                // contributes to it only after its earlier apply has completed
+  int32_t pre_pushed = 0;      // 1: the kernel that produced x has already pushed the boundary values (halo_push_tile):
+                               // no pack CTAs (n_pack == 0), the boundary tiles only acquire the flags
   unsigned long long* wait_ns = nullptr; // optional: longest halo-flag wait of any boundary CTA (atomicMax)
 };
 
 // Boundary tiles (they read the halo tail) wait until every neighbour's values of THIS apply have landed.
 __device__ __forceinline__ void apply_halo_wait(const ApplyDist& ad, int64_t tile) {
-  if (ad.n_pack > 0 && tile >= ad.halo.first_boundary_tile) {
+  if ((ad.n_pack > 0 || ad.pre_pushed) && tile >= ad.halo.first_boundary_tile) {
     CommCtrl* me = ad.comm.ctrl(ad.comm.rank);
     if (threadIdx.x < ad.halo.n_nbr) {
       const unsigned long long t0 = ad.wait_ns != nullptr ? globaltimer_ns() : 0;
@@ -106,10 +108,15 @@ struct EpiResidual {
 template<int FORM, int W, int ND, bool RESID, class Epi>
 __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double* __restrict__ x, double* __restrict__ y,
                                                          Epi epi, RedPtrs red, ApplyDist ad,
-                                                         const int* __restrict__ done) {
+                                                         const int* __restrict__ done,
+                                                         const __grid_constant__ ReducerArgs ra) {
   pdl_trigger();
   pdl_wait();
   if (is_done(done)) return;
+  if (ra.kind != kFinalNone && blockIdx.x == gridDim.x - 1) { // the in-kernel reducer (sb_finals.cuh) owns no tile
+    reducer_role(ra);
+    return;
+  }
   if (ad.n_pack > 0 && (int) blockIdx.x < ad.n_pack) {
     halo_pack_role(ad.comm, ad.halo, x, ad.x_off, ad.n_pack, ad.no_ack != 0);
     return;
@@ -166,6 +173,11 @@ struct StageLayout {
   static constexpr int xown = slice;
   static constexpr int bytes = xown + 512;
   static constexpr int cta_bytes = bytes * kStages * kWarps;
+  // resident CTAs per SM as the ring allows (227 KB per SM, ~1 KB static + 1 KB reserved per CTA), at most 3: told to
+  // ptxas through __launch_bounds__ so that it uses the registers that occupancy leaves free anyway (85 at three CTAs)
+  // instead of spilling down to 64
+  static constexpr int fit = (227 * 1024) / (cta_bytes + 2048);
+  static constexpr int min_ctas = fit >= 3 ? 3 : (fit >= 1 ? fit : 1);
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -179,6 +191,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// The same with an L2 evict-first policy: data that is read once per kernel (the operator's slice records) should not
+// push the vectors out of L2 when a rank is small enough for them to live there.
+__device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -197,13 +219,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 template<int W, int ND, bool RESID, class Epi>
-__global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const double* __restrict__ x,
+__global__ void __launch_bounds__(kThreads, StageLayout<W>::min_ctas) apply_kernel_tma(OpDev op, const double* __restrict__ x,
                                                             double* __restrict__ y, Epi epi, RedPtrs red,
-                                                            ApplyDist ad, const int* __restrict__ done) {
+                                                            ApplyDist ad, const int* __restrict__ done,
+                                                            const __grid_constant__ ReducerArgs ra) {
   using L = StageLayout<W>;
   extern __shared__ __align__(128) unsigned char sb_smem[];
   __shared__ __align__(8) uint64_t bars[kWarps][kStages];
   pdl_trigger();
+  if (ra.kind != kFinalNone && blockIdx.x == gridDim.x - 1) { // the in-kernel reducer (sb_finals.cuh) owns no tile
+    pdl_wait();
+    if (!is_done(done)) reducer_role(ra);
+    return;
+  }
   if (ad.n_pack > 0 && (int) blockIdx.x < ad.n_pack) { // halo-pack CTAs: scheduled first, overlap the interior tiles
     pdl_wait();
     if (!is_done(done)) halo_pack_role(ad.comm, ad.halo, x, ad.x_off, ad.n_pack, ad.no_ack != 0);
@@ -223,7 +251,9 @@ __global__ void __launch_bounds__(kThreads) apply_kernel_tma(OpDev op, const dou
     const int s = j % kStages;
     uint64_t* bar = &bars[warp][s];
     mbar_expect_tx(bar, (uint32_t) L::bytes);
-    bulk_g2s(wbase + s * L::bytes, op.blk + ((row0 + j * 64) >> 6) * (int64_t) L::slice + dep, L::slice, bar);
+    const unsigned char* src = op.blk + ((row0 + j * 64) >> 6) * (int64_t) L::slice + dep;
+    if (op.stream_hint) bulk_g2s_stream(wbase + s * L::bytes, src, L::slice, bar);
+    else bulk_g2s(wbase + s * L::bytes, src, L::slice, bar);
   };
   auto issue_vec = [&](int j, uint32_t dep) {
     const int s = j % kStages;
@@ -411,6 +441,46 @@ __global__ void __launch_bounds__(kThreads, EwStage<Body>::min_ctas) ew_fold_ker
   if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, tile);
 }
 
+// ---- element-wise kernel of the fused solvers' stepwise schedule -------------------------------------------------------
+// ew_kernel with two optional roles:
+//  * push (SB_TUNE_PUSH_ON_PRODUCE, pa.push != 0): the tiles are taken in REVERSE order (the boundary block is the tail
+//    of the local order, so its tiles become the first CTAs of the grid), and a CTA that owns a boundary tile ends with
+//    halo_push_tile (sb_comm.cuh): the part of `y` -- the vector the body writes, the input of the next apply -- that
+//    the neighbours need is on its way over NVLink before the interior tiles of this kernel have even started;
+//  * in-kernel reducer (ra.kind != kFinalNone): the last CTA of the grid finishes the kernel's reductions (sb_finals.cuh).
+struct PushArgs {
+  CommDev comm;
+  HaloDev halo;
+  const double* y = nullptr; // the produced vector
+  int64_t y_off = 0;         // its byte offset inside the slab (the same on every rank)
+  int64_t n_tiles = 0;
+  int32_t push = 0;
+};
+
+template<int ND, class Body>
+__global__ void __launch_bounds__(kThreads) ew_solver_kernel(int64_t n, Body body, RedPtrs red, const int* __restrict__ done,
+                                                             const __grid_constant__ PushArgs pa,
+                                                             const __grid_constant__ ReducerArgs ra) {
+  pdl_trigger();
+  pdl_wait();
+  if (is_done(done)) return;
+  if (ra.kind != kFinalNone && blockIdx.x == gridDim.x - 1) {
+    reducer_role(ra);
+    return;
+  }
+  const int64_t tile = pa.push ? pa.n_tiles - 1 - (int64_t) blockIdx.x : (int64_t) blockIdx.x;
+  typename Body::Regs r[kSub];
+#pragma unroll
+  for (int j = 0; j < kSub; ++j) body.load(lane_elem(tile, j), r[j]);
+  double acc[ND > 0 ? ND : 1];
+#pragma unroll
+  for (int d = 0; d < (ND > 0 ? ND : 1); ++d) acc[d] = 0.0;
+#pragma unroll
+  for (int j = 0; j < kSub; ++j) body.run(lane_elem(tile, j), n, r[j], acc);
+  if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, tile);
+  if (pa.push && tile >= pa.halo.first_boundary_tile) halo_push_tile(pa.comm, pa.halo, pa.y, pa.y_off, tile);
+}
+
 // y = x / diag (Jacobi). The diagonal lives inside the blocked slice records (or in OpDev::diag for the v1 layout).
 struct JacobiBody {
   OpDev op;
@@ -449,6 +519,8 @@ struct sb_op {
   int64_t halo_base = 0, n_halo = 0;
   int64_t recv_ptr[sb::kMaxRanks + 1] = {};
   int32_t* d_send_idx = nullptr;
+  int32_t* d_push_ptr = nullptr; // push-on-produce plan (HaloDev::push_ptr / push_entry); null: not available
+  int2* d_push_entry = nullptr;
   bool distributed = false;
 };
 
@@ -457,19 +529,31 @@ namespace sb {
 int halo_exchange(sb_ctx* ctx, const sb_op* op, const double* x, const int* done, int64_t* x_off); // sb_comm.cu
 
 // Launch y <- A x (+ epilogue) on the context's stream, dispatching on form and ELL width.
-// `per_call` (optional) replaces the operator's kernel arguments for this launch (sb_apply_accumulate: other dt/prefill).
-// `fold_later`: the reduction (and the count of this apply) is folded into the kernel that consumes it
-// (sb_kernels.cuh: fold_prologue) instead of a one-CTA final stage behind this launch; valid inside the fused solvers,
-// where the ack round of the halo exchange is not needed either (ApplyDist::no_ack). `halo_wait_ns`: optional timeline.
+struct ApplyOpts {
+  const OpDev* per_call = nullptr; // replaces the operator's kernel arguments for this launch (sb_apply_accumulate: other dt/prefill)
+  bool fold_later = false;         // the reduction (and the count of this apply) is folded into the kernel that consumes
+                                   // it (sb_kernels.cuh: Fold) instead of a one-CTA final stage behind this launch
+  int halo_mode = 0;               // distributed operator, P2P: 0 = pack CTAs inside the apply + ack round (any caller);
+                                   // 1 = pack CTAs, no ack round (fused solvers: ApplyDist::no_ack); 2 = the producer of
+                                   // x has pushed the boundary values already (halo_push_tile), no pack CTAs
+  unsigned long long* halo_wait_ns = nullptr; // optional timeline: longest halo-flag wait of a boundary CTA
+  unsigned long long* ar_wait_ns = nullptr;   // optional timeline: the final stage's wait for the other ranks' sums
+  bool pdl = false, pdl_final = false;        // programmatic-serialization attribute on the apply / on its final stage
+  const ReducerArgs* reducer = nullptr;       // the reduction is finished by the last CTA of the apply kernel itself
+                                              // (sb_finals.cuh) instead of a one-CTA final stage behind this launch
+};
+
 template<int ND, bool RESID, class Epi, class Final>
 int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const Epi& epi, const Final& fin,
-                 const int* done, const OpDev* per_call = nullptr, bool fold_later = false,
-                 unsigned long long* halo_wait_ns = nullptr) {
-  const OpDev& d = per_call != nullptr ? *per_call : op->d;
+                 const int* done, const ApplyOpts& ao = ApplyOpts{}) {
+  OpDev d = ao.per_call != nullptr ? *ao.per_call : op->d;
+  d.stream_hint = (ctx->tuning & SB_TUNE_STREAM_OPERATOR) ? 1 : 0;
   if constexpr (ND > 0) {
     SB_TRY(ensure_red_scratch(ctx, d.n));
   }
-  const RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
+  ReducerArgs ra;
+  if (ao.reducer != nullptr) ra = *ao.reducer;
+  const RedPtrs red = ra.kind != kFinalNone ? RedPtrs{ra.slots, ra.cap_tiles} : RedPtrs{ctx->red.partials, ctx->red.cap_tiles};
   ApplyDist ad;
   CommCtrl* bump = nullptr;
   if (op->distributed && ctx->comm.world > 1) {
@@ -480,19 +564,26 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
     if (ctx->comm.mode == SB_COMM_P2P && exchange) {
       ad.comm = ctx->comm, ad.halo = op->halo, ad.x_off = x_off;
       const int64_t total = op->halo.send_ptr[op->halo.n_nbr];
-      ad.n_pack = (int32_t) std::max<int64_t>(1, std::min<int64_t>(64, (total + 2 * kThreads - 1) / (2 * kThreads)));
+      if (ao.halo_mode == 2) {
+        ad.n_pack = 0, ad.pre_pushed = 1;
+      } else {
+        ad.n_pack = (int32_t) std::max<int64_t>(1, std::min<int64_t>(64, (total + 2 * kThreads - 1) / (2 * kThreads)));
+        ad.no_ack = (ao.fold_later || ao.halo_mode == 1) ? 1 : 0;
+      }
       ad.coherent_gather = 1;
-      ad.no_ack = fold_later ? 1 : 0;
-      ad.wait_ns = halo_wait_ns;
+      ad.wait_ns = ao.halo_wait_ns;
     }
     // The apply sequence number counts EVERY apply of a distributed operator on every rank, whether this rank has
     // neighbours in this operator or not: the flags of different operators (other partitions, a rank without
     // neighbours) are compared against the same counter, which therefore has to advance in lockstep on all ranks.
     if (ctx->comm.mode == SB_COMM_P2P && !(ctx->debug & 2)) bump = ctx->comm.ctrl(ctx->comm.rank);
   }
-  const unsigned grid = (unsigned) (num_tiles(d.n) + ad.n_pack);
+  if (ra.kind != kFinalNone) ra.bump = bump, ra.n_tiles = num_tiles(d.n);
+  const unsigned grid = (unsigned) (num_tiles(d.n) + ad.n_pack + (ra.kind != kFinalNone ? 1 : 0));
+  {
+  PdlScope pdl_scope(ctx, ao.pdl);
 #define SB_LAUNCH(FORM, W) \
-  SB_CUDA(launch_kernel(ctx, apply_kernel<FORM, W, ND, RESID, Epi>, grid, kThreads, 0, d, x, y, epi, red, ad, done))
+  SB_CUDA(launch_kernel(ctx, apply_kernel<FORM, W, ND, RESID, Epi>, grid, kThreads, 0, d, x, y, epi, red, ad, done, ra))
 #define SB_WIDTHS(FORM)                   \
   switch (d.width) {                      \
     case 0: case 1: SB_LAUNCH(FORM, 1); break; \
@@ -523,7 +614,7 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
       SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
       configured.fetch_or(bit, std::memory_order_release);                                                      \
     }                                                                                                           \
-    SB_CUDA(launch_kernel(ctx, kern, grid, kThreads, smem, d, x, y, epi, red, ad, done));                       \
+    SB_CUDA(launch_kernel(ctx, kern, grid, kThreads, smem, d, x, y, epi, red, ad, done, ra));                   \
   }
     switch (d.width) {
       case 0: case 1: SB_LAUNCH_TMA(1) break;
@@ -550,9 +641,10 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
   }
 #undef SB_WIDTHS
 #undef SB_LAUNCH
+  }
   ctx->launches++;
-  if (fold_later) return SB_OK;
-  if constexpr (ND > 0) return launch_final<ND>(ctx, d.n, fin, done, bump);
+  if (ao.fold_later || ra.kind != kFinalNone) return SB_OK;
+  if constexpr (ND > 0) return launch_final<ND>(ctx, d.n, fin, done, bump, ao.ar_wait_ns, ao.pdl_final);
   if (bump != nullptr) {
     SB_CUDA(launch_kernel(ctx, seq_bump_kernel, 1, 1, 0, bump, done));
     ctx->launches++;

@@ -11,82 +11,9 @@
 
 namespace sb {
 
-__device__ __forceinline__ double safe_divide(double x, double y) {
-  // Crow/MathUtils.hpp:49-52
-  return (y == 0.0) ? 0.0 : __ddiv_rn(x, y);
-}
-
-struct Recorder {
-  SolverState* st;
-  double* hist;
-  double* trace;
-  __device__ void push_trace(double v) const {
-    if (trace != nullptr && st->n_trace < st->trace_cap) trace[st->n_trace] = v;
-    st->n_trace++;
-  }
-  __device__ void push_hist(double v) const {
-    if (hist != nullptr && st->n_hist < st->hist_cap) hist[st->n_hist] = v;
-    st->n_hist++;
-  }
-  // Solver.hpp:124-128: early exit when the initial residual is already below abs_tol.
-  __device__ void init_error(double err) const {
-    st->initial_err = err, st->abs_err = err, st->rel_err = 0.0;
-    st->iteration = 0;
-    push_hist(err);
-    if (st->abs_tol > 0.0 && err < st->abs_tol) st->converged = 1, st->done = 1;
-    if (st->max_iter <= 0) st->done = 1;
-  }
-  // Solver.hpp:132-140: one pass of the iteration loop after iterate() returned `err`.
-  __device__ void iteration_error(double err) const {
-    st->abs_err = err;
-    st->rel_err = __ddiv_rn(err, st->initial_err); // no zero guard
-    push_hist(err);
-    bool conv = (st->abs_tol > 0.0) && (err < st->abs_tol);
-    conv |= (st->rel_tol > 0.0) && (st->rel_err < st->rel_tol);
-    st->iteration++;
-    if (conv) st->converged = 1;
-    if (conv || st->iteration >= st->max_iter) st->done = 1;
-  }
-};
-
-// One-CTA final stage (no folding: initialisation, NCCL mode): run the scalar update in place, then publish the stop.
-template<class Inner>
-struct PublishFinal {
-  Inner inner;
-  SolveBlock* blk;
-  __device__ void operator()(const double* s) const {
-    inner(s);
-    if (inner.rec.st->done) blk->final_() = *inner.rec.st, blk->done = 1;
-  }
-};
+// (Recorder and the scalar updates behind the reductions live in sb_finals.cuh, where the in-kernel reducer needs them.)
 
 // ---- CG -------------------------------------------------------------------------------------------
-struct CgInitFinal { // after r = b - A x fused with <r,r>   (SolverCg.hpp:73,80,83)
-  Recorder rec;
-  __device__ void operator()(const double* s) const {
-    rec.st->gamma = s[0];
-    rec.push_trace(s[0]);
-    rec.init_error(sqrt(s[0]));
-  }
-};
-struct CgAlphaFinal { // after z = A p fused with <p,z>       (:95-96)
-  Recorder rec;
-  __device__ void operator()(const double* s) const {
-    rec.push_trace(s[0]);
-    rec.st->alpha = safe_divide(rec.st->gamma, s[0]);
-  }
-};
-struct CgBetaFinal { // after the x/r update fused with <r,r>  (:109,114,121,124)
-  Recorder rec;
-  __device__ void operator()(const double* s) const {
-    const double gamma_bar = rec.st->gamma;
-    rec.st->gamma = s[0];
-    rec.push_trace(s[0]);
-    rec.st->beta = safe_divide(s[0], gamma_bar);
-    rec.iteration_error(sqrt(s[0]));
-  }
-};
-
 struct CopyBody { // p <- r
   double* dst;
   const double* src;
@@ -145,46 +72,6 @@ struct CgDirectionBody { // p <- r + beta*p     (:122)
 };
 
 // ---- BiCGStab -------------------------------------------------------------------------------------
-struct BiInitFinal { // r = b - A x, r~ = r, rho = <r~,r>      (SolverBiCgStab.hpp:83,88-91)
-  Recorder rec;
-  __device__ void operator()(const double* s) const {
-    rec.st->rho = s[0];
-    rec.push_trace(s[0]);
-    rec.init_error(sqrt(s[0]));
-  }
-};
-struct BiAlphaFinal { // after v = A p fused with <r~,v>        (:137,139)
-  Recorder rec;
-  __device__ void operator()(const double* s) const {
-    rec.push_trace(s[0]);
-    rec.st->alpha = safe_divide(rec.st->rho, s[0]);
-  }
-};
-struct BiOmegaFinal { // after t = A r fused with <t,t>, <t,r>  (:158-160)
-  Recorder rec;
-  __device__ void operator()(const double* s) const {
-    // g++ evaluates safe_divide's arguments right to left: <t,t> is traced before <t,r>.
-    rec.push_trace(s[0]);
-    rec.push_trace(s[1]);
-    rec.st->omega = safe_divide(s[1], s[0]);
-  }
-};
-struct BiEndFinal { // after the final update fused with <r,r> and <r~,r>   (:164 and next :115-117)
-  Recorder rec;
-  __device__ void operator()(const double* s) const {
-    const double nrm = sqrt(s[0]);
-    rec.push_trace(nrm);
-    rec.iteration_error(nrm);
-    if (!rec.st->done) {
-      // head of the next iteration: rho_bar <- rho, rho <- <r~,r>, beta <- (alpha*rho)/(omega*rho_bar)
-      const double rho_bar = rec.st->rho;
-      rec.st->rho = s[1];
-      rec.push_trace(s[1]);
-      rec.st->beta = safe_divide(__dmul_rn(rec.st->alpha, s[1]), __dmul_rn(rec.st->omega, rho_bar));
-    }
-  }
-};
-
 struct BiInitBody { // r~ <- r after the fused residual (r already stored by the apply kernel)
   double* rt;
   const double* r;

@@ -26,11 +26,45 @@ namespace sb {
 
 // ---- host side ------------------------------------------------------------------------------------
 template<int ND, class Body, class Final>
-int launch_ew(sb_ctx* ctx, int64_t n, const Body& body, const Final& fin, const int* done) {
+int launch_ew(sb_ctx* ctx, int64_t n, const Body& body, const Final& fin, const int* done, bool pdl = false,
+              bool pdl_final = false, unsigned long long* ar_wait_ns = nullptr) {
   RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
-  SB_CUDA(launch_kernel(ctx, ew_kernel<ND, Body>, (unsigned) num_tiles(n), kThreads, 0, n, body, red, done));
+  {
+    PdlScope pdl_scope(ctx, pdl);
+    SB_CUDA(launch_kernel(ctx, ew_kernel<ND, Body>, (unsigned) num_tiles(n), kThreads, 0, n, body, red, done));
+  }
   ctx->launches++;
-  if constexpr (ND > 0) return launch_final<ND>(ctx, n, fin, done);
+  if constexpr (ND > 0) return launch_final<ND>(ctx, n, fin, done, nullptr, ar_wait_ns, pdl_final);
+  return SB_OK;
+}
+
+// An element-wise step of the stepwise schedule (ew_solver_kernel). `push_y` != null: the step's output is the input of
+// the next apply and the kernel forwards its boundary values to the neighbours itself (multi-GPU, in-kernel
+// collectives). `ra` (ND > 0): the reductions are finished by the kernel's last CTA; without it a one-CTA final stage
+// follows.
+template<int ND, class Body, class Final>
+int launch_ew_solver(sb_ctx* ctx, const sb_op* op, int64_t n, const Body& body, const double* push_y, const Final& fin,
+                     const int* done, bool pdl, bool pdl_final, const ReducerArgs* reducer, unsigned long long* ar_wait_ns) {
+  ReducerArgs ra;
+  if (reducer != nullptr) ra = *reducer, ra.n_tiles = num_tiles(n);
+  const bool in_kernel = ND > 0 && ra.kind != kFinalNone;
+  if (!in_kernel) ra = ReducerArgs{};
+  const RedPtrs red = in_kernel ? RedPtrs{ra.slots, ra.cap_tiles} : RedPtrs{ctx->red.partials, ctx->red.cap_tiles};
+  PushArgs pa;
+  pa.n_tiles = num_tiles(n);
+  if (push_y != nullptr) {
+    pa.comm = ctx->comm, pa.halo = op->halo, pa.y = push_y, pa.push = 1;
+    pa.y_off = (int64_t) (reinterpret_cast<const unsigned char*>(push_y) - ctx->slab);
+  }
+  {
+    PdlScope pdl_scope(ctx, pdl);
+    SB_CUDA(launch_kernel(ctx, ew_solver_kernel<ND, Body>, (unsigned) (num_tiles(n) + (in_kernel ? 1 : 0)), kThreads, 0, n, body,
+                          red, done, pa, ra));
+  }
+  ctx->launches++;
+  if constexpr (ND > 0) {
+    if (!in_kernel) return launch_final<ND>(ctx, n, fin, done, nullptr, ar_wait_ns, pdl_final);
+  }
   return SB_OK;
 }
 
@@ -89,6 +123,9 @@ static int check_vector(sb_ctx* ctx, const double* v, int64_t n, const char* wha
   return SB_ERR_INVALID;
 }
 
+// What sb_solver_opts::tuning == 0 selects (measured on 1, 2 and 8 GPUs).
+constexpr uint32_t kDefaultTuning = 0;
+
 struct Solve {
   sb_ctx* ctx;
   const sb_op* op;
@@ -116,7 +153,18 @@ struct Solve {
     }
     return SB_OK;
   }
-  unsigned long long* wait_slot() { return (tl != nullptr && tl_pos < tl_cap) ? tl + tl_pos++ : nullptr; }
+  // two timeline words per kernel slot and iteration: [0] the slot's own in-kernel wait (apply: longest halo-flag wait
+  // of a boundary CTA; folding kernel: the reducer's wait), [1] the wait of the one-CTA final stage behind the slot for
+  // the other ranks' sums. Every slot takes its pair, used or not, so the words stay aligned with the slots.
+  struct WaitPair {
+    unsigned long long *own = nullptr, *ar = nullptr;
+  };
+  WaitPair wait_slot() {
+    WaitPair w;
+    if (tl != nullptr && tl_pos + 2 <= tl_cap) w.own = tl + tl_pos, w.ar = tl + tl_pos + 1;
+    tl_pos += 2;
+    return w;
+  }
   RedPtrs red_set(int k) const {
     return RedPtrs{ctx->red.partials + (int64_t) k * kMaxDots * ctx->red.cap_tiles, ctx->red.cap_tiles};
   }
@@ -127,7 +175,10 @@ struct Solve {
     EpiResidual epi{b};
     if (kind == Kind::Cg) {
       SB_TRY((launch_apply<1, true>(ctx, op, x, r, epi, PublishFinal<CgInitFinal>{CgInitFinal{rec}, blk}, nullptr)));
-      SB_TRY((launch_ew<0>(ctx, n, CopyBody{p, r}, NoFinal{}, nullptr))); // p <- r
+      // p <- r; with push-on-produce this is the producer of the first apply's input (skipped, like that apply, when the
+      // initial residual already met the tolerance: a push that no apply consumes would leave a stale halo flag behind)
+      if (push) SB_TRY((launch_ew_solver<0>(ctx, op, n, CopyBody{p, r}, p, NoFinal{}, done, false, false, nullptr, nullptr)));
+      else SB_TRY((launch_ew<0>(ctx, n, CopyBody{p, r}, NoFinal{}, nullptr)));
     } else {
       SB_TRY((launch_apply<1, true>(ctx, op, x, r, epi, PublishFinal<BiInitFinal>{BiInitFinal{rec}, blk}, nullptr)));
       SB_TRY((launch_ew<0>(ctx, n, BiInitBody{rt, r}, NoFinal{}, nullptr))); // r~ <- r
@@ -148,7 +199,7 @@ struct Solve {
       f.comm = ctx->comm;
       if (after_apply && !(ctx->debug & 2)) f.bump = ctx->comm.ctrl(ctx->comm.rank);
     }
-    f.wait_ns = wait_slot(); // one word per kernel slot, folding or not: the timeline stays aligned with the slots
+    f.wait_ns = wait_slot().own; // one pair per kernel slot, folding or not: the timeline stays aligned with the slots
     const unsigned grid = (unsigned) (num_tiles(rows) + 1); // CTA 0 reduces, CTA k > 0 owns tile k - 1
     auto kern = ew_fold_kernel<ND, Body, FND, Final>;
     constexpr int smem = EwStage<Body>::cta;
@@ -164,10 +215,16 @@ struct Solve {
     return SB_OK;
   }
 
+  ApplyOpts folded_apply() {
+    ApplyOpts ao;
+    ao.fold_later = true, ao.halo_wait_ns = wait_slot().own;
+    return ao;
+  }
+
   int iterate_folded(Kind kind) {
     if (kind == Kind::Cg) {
       SB_TRY(mark());
-      SB_TRY((launch_apply<1, false>(ctx, op, p, z, EpiXY{}, NoFinal{}, done, nullptr, true, wait_slot())));
+      SB_TRY((launch_apply<1, false>(ctx, op, p, z, EpiXY{}, NoFinal{}, done, folded_apply())));
       SB_TRY(mark());
       SB_TRY((launch_fold<1, 1>(CgUpdateBody{nullptr, x, r, p, z}, CgAlphaFinal{rec}, true, 0, true, n)));
       SB_TRY(mark());
@@ -176,11 +233,11 @@ struct Solve {
       SB_TRY(mark());
       SB_TRY((launch_fold<0, 2>(BiDirectionBody{nullptr, p, r, v}, BiEndFinal{rec}, pending_end, 1, false, n)));
       SB_TRY(mark());
-      SB_TRY((launch_apply<1, false>(ctx, op, p, v, EpiUY{rt}, NoFinal{}, done, nullptr, true, wait_slot())));
+      SB_TRY((launch_apply<1, false>(ctx, op, p, v, EpiUY{rt}, NoFinal{}, done, folded_apply())));
       SB_TRY(mark());
       SB_TRY((launch_fold<0, 1>(BiHalfBody{nullptr, r, v}, BiAlphaFinal{rec}, true, 0, true, n)));
       SB_TRY(mark());
-      SB_TRY((launch_apply<2, false>(ctx, op, r, t, EpiYYandYX{}, NoFinal{}, done, nullptr, true, wait_slot())));
+      SB_TRY((launch_apply<2, false>(ctx, op, r, t, EpiYYandYX{}, NoFinal{}, done, folded_apply())));
       SB_TRY(mark());
       SB_TRY((launch_fold<2, 2>(BiEndBody{nullptr, x, r, p, t, rt}, BiOmegaFinal{rec}, true, 0, true, n)));
       pending_end = true;
@@ -196,27 +253,67 @@ struct Solve {
     return SB_OK;
   }
 
+  // Stepwise schedule: one kernel per step. Tuning (SB_TUNE_*):
+  // `in_kernel`: every reduction is finished by the last CTA of the kernel that produces it (sb_finals.cuh); without
+  //   it a one-CTA final stage follows every reducing kernel;
+  // `push`: the producers of the apply inputs (p; BiCGStab also r) forward the boundary values themselves;
+  // `pdl_final` / `pdl_after` / `pdl_apply`: programmatic-serialization attribute on the final stages / on the kernels
+  //   behind a reduction / on the applies.
+  bool push = false, no_ack = false, pdl_final = false, pdl_after = false, pdl_apply = false, in_kernel = false;
+
+  ReducerArgs reducer(FinalKind kind, int nd, unsigned long long* wait_ns) const {
+    ReducerArgs ra;
+    if (!in_kernel) return ra;
+    ra.kind = kind, ra.nd = nd;
+    ra.slots = ctx->red.slots, ra.cap_tiles = ctx->red.cap_tiles;
+    ra.rec = rec, ra.blk = blk;
+    if (dist() && !(ctx->debug & 4)) ra.comm = ctx->comm;
+    ra.comm.timeout_ns = ctx->spin_timeout_ns;
+    ra.wait_ns = wait_ns;
+    return ra;
+  }
+
+  template<int ND, bool RESID, class Epi, class Final>
+  int stepwise_apply(const double* in, double* out, const Epi& epi, const Final& fin, FinalKind kind) {
+    ApplyOpts ao;
+    ao.halo_mode = push ? 2 : (no_ack ? 1 : 0);
+    ao.pdl = pdl_apply, ao.pdl_final = pdl_final;
+    const WaitPair w = wait_slot();
+    ao.halo_wait_ns = w.own, ao.ar_wait_ns = w.ar;
+    const ReducerArgs ra = reducer(kind, ND, w.ar);
+    if (in_kernel) ao.reducer = &ra;
+    return launch_apply<ND, RESID>(ctx, op, in, out, epi, fin, done, ao);
+  }
+
+  template<int ND, class Body, class Final>
+  int stepwise_ew(const Body& body, const double* push_y, const Final& fin, FinalKind kind) {
+    const WaitPair w = wait_slot();
+    const ReducerArgs ra = reducer(kind, ND, w.ar);
+    return launch_ew_solver<ND>(ctx, op, n, body, push ? push_y : nullptr, fin, done, pdl_after, pdl_final,
+                                (ND > 0 && in_kernel) ? &ra : nullptr, w.ar);
+  }
+
   int iterate(Kind kind) {
     if (folded) return iterate_folded(kind);
     const SolverState* st = rec.st;
     if (kind == Kind::Cg) {
       SB_TRY(mark());
-      SB_TRY((launch_apply<1, false>(ctx, op, p, z, EpiXY{}, PublishFinal<CgAlphaFinal>{CgAlphaFinal{rec}, blk}, done)));
+      SB_TRY((stepwise_apply<1, false>(p, z, EpiXY{}, PublishFinal<CgAlphaFinal>{CgAlphaFinal{rec}, blk}, kFinalCgAlpha)));
       SB_TRY(mark());
-      SB_TRY((launch_ew<1>(ctx, n, CgUpdateBody{st, x, r, p, z}, PublishFinal<CgBetaFinal>{CgBetaFinal{rec}, blk}, done)));
+      SB_TRY((stepwise_ew<1>(CgUpdateBody{st, x, r, p, z}, nullptr, PublishFinal<CgBetaFinal>{CgBetaFinal{rec}, blk}, kFinalCgBeta)));
       SB_TRY(mark());
-      SB_TRY((launch_ew<0>(ctx, n, CgDirectionBody{st, p, r}, NoFinal{}, done)));
+      SB_TRY((stepwise_ew<0>(CgDirectionBody{st, p, r}, p, NoFinal{}, kFinalNone)));
     } else {
       SB_TRY(mark());
-      SB_TRY((launch_ew<0>(ctx, n, BiDirectionBody{st, p, r, v}, NoFinal{}, done)));
+      SB_TRY((stepwise_ew<0>(BiDirectionBody{st, p, r, v}, p, NoFinal{}, kFinalNone)));
       SB_TRY(mark());
-      SB_TRY((launch_apply<1, false>(ctx, op, p, v, EpiUY{rt}, PublishFinal<BiAlphaFinal>{BiAlphaFinal{rec}, blk}, done)));
+      SB_TRY((stepwise_apply<1, false>(p, v, EpiUY{rt}, PublishFinal<BiAlphaFinal>{BiAlphaFinal{rec}, blk}, kFinalBiAlpha)));
       SB_TRY(mark());
-      SB_TRY((launch_ew<0>(ctx, n, BiHalfBody{st, r, v}, NoFinal{}, done)));
+      SB_TRY((stepwise_ew<0>(BiHalfBody{st, r, v}, r, NoFinal{}, kFinalNone)));
       SB_TRY(mark());
-      SB_TRY((launch_apply<2, false>(ctx, op, r, t, EpiYYandYX{}, PublishFinal<BiOmegaFinal>{BiOmegaFinal{rec}, blk}, done)));
+      SB_TRY((stepwise_apply<2, false>(r, t, EpiYYandYX{}, PublishFinal<BiOmegaFinal>{BiOmegaFinal{rec}, blk}, kFinalBiOmega)));
       SB_TRY(mark());
-      SB_TRY((launch_ew<2>(ctx, n, BiEndBody{st, x, r, p, t, rt}, PublishFinal<BiEndFinal>{BiEndFinal{rec}, blk}, done)));
+      SB_TRY((stepwise_ew<2>(BiEndBody{st, x, r, p, t, rt}, nullptr, PublishFinal<BiEndFinal>{BiEndFinal{rec}, blk}, kFinalBiEnd)));
     }
     SB_TRY(mark());
     return SB_OK;
@@ -296,6 +393,20 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
     S.rt = ctx->work[2], S.t = ctx->work[3], S.v = ctx->work[4];
   }
   S.folded = opts->schedule == SB_SCHEDULE_FOLDED;
+  // tuning of the stepwise schedule (include/stormb200.h: SB_TUNE_*); 0 = the defaults
+  const uint32_t tuning = opts->tuning == 0 ? kDefaultTuning : (opts->tuning & ~SB_TUNE_OFF);
+  struct TuningScope { // the launch helpers read the bits from the context while this solve is in progress
+    sb_ctx* c;
+    ~TuningScope() { c->tuning = 0; }
+  } tuning_scope{ctx};
+  ctx->tuning = tuning;
+  const bool p2p = ctx->comm.world > 1 && ctx->comm.mode == SB_COMM_P2P && op->distributed && !(ctx->debug & 2);
+  S.push = p2p && (tuning & SB_TUNE_PUSH_ON_PRODUCE) && op->halo.n_nbr > 0 && op->halo.push_ptr != nullptr && !S.folded;
+  S.no_ack = p2p && (tuning & SB_TUNE_NO_ACK);
+  S.pdl_final = (tuning & SB_TUNE_PDL_FINAL) != 0 && !(ctx->comm.world > 1 && ctx->comm.mode == SB_COMM_NCCL);
+  S.pdl_after = (tuning & SB_TUNE_PDL_AFTER_FINAL) != 0 && !(ctx->comm.world > 1 && ctx->comm.mode == SB_COMM_NCCL);
+  S.in_kernel = (tuning & SB_TUNE_IN_KERNEL_REDUCER) != 0 && !(ctx->comm.world > 1 && (ctx->comm.mode == SB_COMM_NCCL || !op->distributed));
+  S.pdl_apply = (tuning & SB_TUNE_PDL_APPLY) != 0 && !(ctx->comm.world > 1 && ctx->comm.mode == SB_COMM_NCCL);
   SolveGuard guard;
   const int64_t launches0 = ctx->launches;
   SB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -306,8 +417,8 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   std::vector<cudaEvent_t>& prof_events = guard.events; // profile events are appended behind ev_mid / evs
   const int per_iter = (kind == Kind::Cg) ? 3 : 5;       // profiled kernel slots
   size_t prof_first = 0;
-  const int64_t tl_words = profile ? (int64_t) per_iter * opts->num_iterations : 0;
-  if (tl_words > 0) { // in-kernel waits of the profiled run: one word per kernel slot and iteration
+  const int64_t tl_words = profile ? 2 * (int64_t) per_iter * opts->num_iterations : 0;
+  if (tl_words > 0) { // in-kernel waits of the profiled run: two words per kernel slot and iteration
     if (tl_words > ctx->timeline_cap) {
       SB_CUDA(cudaStreamSynchronize(ctx->stream));
       cudaFree(ctx->d_timeline);
@@ -354,7 +465,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
         SB_CUDA(cudaGraphInstantiate(&guard.graph_exec, guard.graph, 0));
       }
     }
-    const int launches_per_iter = S.folded ? per_iter : ((kind == Kind::Cg) ? 5 : 8); // unfolded: + one-CTA final stages
+    const int launches_per_iter = (S.folded || S.in_kernel) ? per_iter : ((kind == Kind::Cg) ? 5 : 8); // + one-CTA final stages
 
     // Convergence polling: a flag copy is queued every `check` iterations and examined one batch later,
     // so the host never drains the stream while it still has work to enqueue.
@@ -408,7 +519,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   report->n_kernel_slots = persistent ? 0 : per_iter;
   report->schedule = persistent ? SB_SCHEDULE_PERSISTENT : (S.folded ? SB_SCHEDULE_FOLDED : SB_SCHEDULE_STEPWISE);
   for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->kernel_ms[k] = 0.0;
-  for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->wait_ms[k] = 0.0;
+  for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->wait_ms[k] = report->ar_wait_ms[k] = 0.0;
   if (profile && !persistent) {
     // events come in groups of per_iter + 1 per iteration
     const size_t group = (size_t) per_iter + 1;
@@ -421,7 +532,10 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
     if (tl_words > 0) { // longest in-kernel wait per launch, summed per slot
       std::vector<unsigned long long> tl((size_t) tl_words);
       SB_CUDA(cudaMemcpy(tl.data(), ctx->d_timeline, sizeof(unsigned long long) * tl_words, cudaMemcpyDeviceToHost));
-      for (int64_t q = 0; q < S.tl_pos && q < tl_words; ++q) report->wait_ms[q % per_iter] += 1e-6 * (double) tl[(size_t) q];
+      for (int64_t q = 0; q + 1 < S.tl_pos && q + 1 < tl_words; q += 2) {
+        report->wait_ms[(q / 2) % per_iter] += 1e-6 * (double) tl[(size_t) q];
+        report->ar_wait_ms[(q / 2) % per_iter] += 1e-6 * (double) tl[(size_t) q + 1];
+      }
     }
   }
   // a device-side spin wait that gave up (lost peer, rank skew beyond SB_SPIN_TIMEOUT_S): values are meaningless

@@ -220,21 +220,36 @@ def run_gpu(dist, rank, world, mode_name):
             # and the persistent whole-solve kernel (in-kernel halo push, grid barriers, mailbox all-reduce; P2P only),
             # alternating on one context so that the sequence numbers of the two protocols have to stay in step
             oracle_op = cpu if form == sb.FORM_FAITHFUL else orc.RowsOp(n, *cpu.rows_coef())
+            # (schedule, graph replay, tuning bits): every combination must produce the same bits
+            T = capi
             if form == sb.FORM_FAITHFUL:
-                variants = [(capi.SCHEDULE_AUTO, False), (capi.SCHEDULE_AUTO, True)]
+                variants = [(capi.SCHEDULE_AUTO, False, 0), (capi.SCHEDULE_AUTO, True, 0)]
+                if mode == capi.COMM_P2P:
+                    variants += [(capi.SCHEDULE_STEPWISE, True, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PDL_FINAL),
+                                 (capi.SCHEDULE_STEPWISE, True, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_IN_KERNEL_REDUCER)]
             elif mode == capi.COMM_P2P:
-                variants = [(capi.SCHEDULE_PERSISTENT, False), (capi.SCHEDULE_STEPWISE, True),
-                            (capi.SCHEDULE_PERSISTENT, False), (capi.SCHEDULE_AUTO, False)]
+                variants = [(capi.SCHEDULE_PERSISTENT, False, 0), (capi.SCHEDULE_STEPWISE, True, T.TUNE_OFF),
+                            (capi.SCHEDULE_STEPWISE, True, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_STREAM_OPERATOR),
+                            (capi.SCHEDULE_PERSISTENT, False, 0), (capi.SCHEDULE_AUTO, False, 0),
+                            (capi.SCHEDULE_STEPWISE, False, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PDL_FINAL | T.TUNE_PDL_AFTER_FINAL),
+                            (capi.SCHEDULE_FOLDED, True, 0),
+                            (capi.SCHEDULE_STEPWISE, True, T.TUNE_IN_KERNEL_REDUCER),
+                            (capi.SCHEDULE_STEPWISE, False, T.TUNE_IN_KERNEL_REDUCER | T.TUNE_PUSH_ON_PRODUCE),
+                            (capi.SCHEDULE_STEPWISE, True, T.TUNE_IN_KERNEL_REDUCER | T.TUNE_PUSH_ON_PRODUCE | T.TUNE_STREAM_OPERATOR
+                             | T.TUNE_PDL_AFTER_FINAL | T.TUNE_PDL_APPLY),
+                            (capi.SCHEDULE_STEPWISE, True, T.TUNE_NO_ACK | T.TUNE_PDL_APPLY | T.TUNE_PDL_FINAL | T.TUNE_PDL_AFTER_FINAL),
+                            (capi.SCHEDULE_STEPWISE, True, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PDL_APPLY | T.TUNE_PDL_FINAL
+                             | T.TUNE_PDL_AFTER_FINAL | T.TUNE_STREAM_OPERATOR)]
             else:
-                variants = [(capi.SCHEDULE_STEPWISE, True)]
+                variants = [(capi.SCHEDULE_STEPWISE, True, 0)]
             for name, Solver in (("cg", sb.CgSolver), ("bicgstab", sb.BiCgStabSolver)):
                 w = orc.solve(name, oracle_op, bg[order], num_iterations=60, abs_tol=0.0, rel_tol=1e-9, mode=orc.RED_TREE_SEG)
-                for schedule, use_graph in variants:
+                for schedule, use_graph, tuning in variants:
                     s = Solver(num_iterations=60, absolute_error_tolerance=0.0, relative_error_tolerance=1e-9,
-                               use_graph=use_graph, check_every=7, schedule=schedule)
+                               use_graph=use_graph, check_every=7, schedule=schedule, tuning=tuning)
                     xs = ctx.zeros(loc.n_owned)
                     conv = s.solve(xs, ctx.vector(bg[loc.owned_global]), op)
-                    tag = f"{name} form {form} schedule {schedule}->{s.schedule_used}"
+                    tag = f"{name} form {form} schedule {schedule}->{s.schedule_used} tuning {tuning:#x}"
                     if form == sb.FORM_COEF and mode == capi.COMM_P2P and schedule == capi.SCHEDULE_PERSISTENT:
                         assert s.schedule_used == capi.SCHEDULE_PERSISTENT, tag
                     assert conv == w.converged and s.iteration == w.iterations, (tag, conv, s.iteration, w.iterations)

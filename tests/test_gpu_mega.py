@@ -70,8 +70,21 @@ def test_persistent_schedule_bit_identical_to_oracle_and_to_stepwise(ctx, name, 
     step = run(ctx, gpu, solver, b, STEP, iters, use_graph=True)
     assert step[0].schedule_used == STEP and same(pers, step)
     # one launch for the whole loop: initialisation (apply + final stage + copy) + 1; the stepwise schedule: 3 (CG) or
-    # 5 (BiCGStab) launches per iteration, nothing in between
-    assert pers[0].launches <= 4 < step[0].launches <= (3 if solver == "cg" else 5) * (iters + 1) + 6
+    # 5 (BiCGStab) kernels per iteration + a one-CTA final stage per reduction (2 / 3); folded: nothing in between
+    assert pers[0].launches <= 4 < step[0].launches <= (5 if solver == "cg" else 8) * (iters + 1) + 6
+    fold = run(ctx, gpu, solver, b, capi.SCHEDULE_FOLDED, iters, use_graph=True)
+    assert fold[0].schedule_used == capi.SCHEDULE_FOLDED and same(pers, fold)
+    assert fold[0].launches <= (3 if solver == "cg" else 5) * (iters + 1) + 6
+    # the tuning bits of the stepwise schedule change how kernels are launched and what the L2 keeps, never the bits
+    for tuning in (capi.TUNE_OFF, capi.TUNE_STREAM_OPERATOR, capi.TUNE_PDL_FINAL | capi.TUNE_PDL_AFTER_FINAL,
+                   capi.TUNE_STREAM_OPERATOR | capi.TUNE_PDL_FINAL | capi.TUNE_PDL_AFTER_FINAL | capi.TUNE_PDL_APPLY,
+                   capi.TUNE_IN_KERNEL_REDUCER,
+                   capi.TUNE_IN_KERNEL_REDUCER | capi.TUNE_STREAM_OPERATOR | capi.TUNE_PDL_AFTER_FINAL | capi.TUNE_PDL_APPLY):
+        for graph in (True, False):
+            got = run(ctx, gpu, solver, b, STEP, iters, use_graph=graph, tuning=tuning)
+            assert same(pers, got), (tuning, graph)
+            if tuning & capi.TUNE_IN_KERNEL_REDUCER:   # no one-CTA kernels between the steps
+                assert got[0].launches <= (3 if solver == "cg" else 5) * (iters + 1) + 6
     # stops in the middle of the loop, on the relative tolerance: same iterate as the stepwise schedule, and again
     # when the two schedules alternate on one context (the all-reduce mailbox parity carries over)
     rel = want.hist / want.hist[0]
