@@ -124,6 +124,17 @@ print("   stepwise slots us", {k: round(1e3 * v, 1) for k, v in d["stepwise"]["k
 PY
     done
     ;;
+  i)
+    # tuning bits of the stepwise schedule on one GPU: the whole GPU suite (incl. two ranks sharing the GPU: push-on-produce,
+    # in-kernel reducer, PDL), then the A/B at the per-rank sizes of 8 / 4 / 1 GPUs
+    export SB_SPIN_TIMEOUT_S=30
+    timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 > "$out/pytest_gpu.log"; tail -8 "$out/pytest_gpu.log"
+    unset SB_SPIN_TIMEOUT_S
+    for ax in 59 75 119; do
+      timeout 600 python scripts/scale_ab.py --axis $ax --out "$out/ab_n1_axis$ax.json" > "$out/ab_n1_axis$ax.jsonl" 2> "$out/ab_n1_axis$ax.log"
+      grep "^\[ab\]" "$out/ab_n1_axis$ax.log"
+    done
+    ;;
   g)
     # two GPUs: the distributed tests with a GPU per rank, the strong-scaling point, config 3 and config 5 at N = 2
     export SB_SPIN_TIMEOUT_S=60
