@@ -259,6 +259,15 @@ def phase_times(timeline, solver):
     return out
 
 
+def SCHEDULES(capi):
+    return {"auto": capi.SCHEDULE_AUTO, "stepwise": capi.SCHEDULE_STEPWISE, "persistent": capi.SCHEDULE_PERSISTENT,
+            "folded": capi.SCHEDULE_FOLDED}
+
+
+def schedule_name(capi, used):
+    return {capi.SCHEDULE_PERSISTENT: "persistent", capi.SCHEDULE_STEPWISE: "stepwise", capi.SCHEDULE_FOLDED: "folded"}[used]
+
+
 SLOTS = {"bicgstab": ["direction", "apply+dot", "half_update", "apply+2dots", "final_update+2dots"],
          "cg": ["apply+dot", "update+dot", "direction"]}
 KERNEL_NAME = {"bicgstab": "sb::krylov_persistent_kernel<BiCgStab, W> (the whole iteration loop, ONE cooperative launch)",
@@ -284,7 +293,7 @@ def run_own_arm(args):
     xs = ctx.vector(x_star)
     b = ctx.zeros(n)
     op.mul(b, xs)                                   # b = A x*
-    schedule = {"auto": capi.SCHEDULE_AUTO, "stepwise": capi.SCHEDULE_STEPWISE, "persistent": capi.SCHEDULE_PERSISTENT}[args.schedule]
+    schedule = SCHEDULES(capi)[args.schedule]
     peak, peak_src = peaks()
     alg_apply = op.info.algorithmic_bytes_per_apply
 
@@ -302,22 +311,23 @@ def run_own_arm(args):
             assert s.iteration == iters, (s.iteration, iters)
             return s, x
 
-        solve(max(args.warmup, 3), use_graph=True, schedule=schedule)            # warm-up (untimed)
-        s, x = solve(args.steps, use_graph=True, schedule=schedule)              # timed: exactly K iterations
+        solve(max(args.warmup, 3), use_graph=True, schedule=schedule, tuning=args.tuning)   # warm-up (untimed)
+        s, x = solve(args.steps, use_graph=True, schedule=schedule, tuning=args.tuning)     # timed: exactly K iterations
         value = args.steps / (s.iter_ms * 1e-3)
         alg_iter = applies_per_it * alg_apply + passes_per_it * 8 * n
         out = {"solver": solver, "s": s, "x": x, "value": value, "ms_per_step": s.iter_ms / args.steps,
                "alg_iter": alg_iter, "applies_per_it": applies_per_it,
-               "schedule": {capi.SCHEDULE_PERSISTENT: "persistent", capi.SCHEDULE_STEPWISE: "stepwise"}[s.schedule_used],
+               "schedule": schedule_name(capi, s.schedule_used),
                "iteration_roofline": {"algorithmic_bytes_per_iteration": int(alg_iter),
                                       "achieved_gbs": alg_iter * value / 1e9,
                                       "frac_of_measured_peak": alg_iter * value / 1e9 / peak,
                                       "frac_of_nominal_8TBs": alg_iter * value / 8e12}}
         if s.schedule_used == capi.SCHEDULE_PERSISTENT:
-            st, _ = solve(min(args.steps, 64), schedule=schedule, timeline_iters=min(args.steps, 64))
+            st, _ = solve(min(args.steps, 64), schedule=schedule, timeline_iters=min(args.steps, 64), tuning=args.tuning)
             out["phases"] = phase_times(st.timeline, solver)
         # per-kernel breakdown of the same K iterations in the stepwise schedule (events around every launch, no graph)
-        sp, _ = solve(args.steps, profile=True)
+        sp, _ = solve(args.steps, profile=True, schedule=capi.SCHEDULE_FOLDED if s.schedule_used == capi.SCHEDULE_FOLDED else capi.SCHEDULE_STEPWISE,
+                      tuning=args.tuning)
         kms = list(sp.kernel_ms)
         slots = SLOTS[solver]
         apply_slots = [k for k, nm in enumerate(slots) if nm.startswith("apply")]
@@ -352,12 +362,13 @@ def run_own_arm(args):
     hx = torch.zeros(n, dtype=torch.float64).pin_memory()
     hb = torch.from_numpy(b.numpy()).pin_memory()
     hxn, hbn = hx.numpy(), hb.numpy()
-    sb.solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=3, abs_tol=0.0, rel_tol=0.0, use_graph=True, schedule=schedule)
+    sb.solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=3, abs_tol=0.0, rel_tol=0.0, use_graph=True, schedule=schedule,
+                  tuning=args.tuning)
     hxn[:] = 0.0
     ctx.sync()
     t = time.perf_counter()
     rep = sb.solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=args.steps, abs_tol=0.0, rel_tol=0.0,
-                        use_graph=True, schedule=schedule)
+                        use_graph=True, schedule=schedule, tuning=args.tuning)
     e2e_s = time.perf_counter() - t
     assert rep.iterations == args.steps
     e2e_value = args.steps / e2e_s
@@ -442,9 +453,10 @@ def main():
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: halo exchange + reductions by in-kernel NVLink peer stores (p2p) or NCCL send/recv + allreduce")
     ap.add_argument("--partition", default="metis", choices=["metis", "slab"], help="N>1: METIS k-way or contiguous RCM slabs")
-    ap.add_argument("--schedule", default="auto", choices=["auto", "stepwise", "persistent"],
-                    help="fused-solver schedule of the timed run (auto = stepwise: one kernel per step, reductions folded "
-                         "into their consumers, graph replay)")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "stepwise", "persistent", "folded"],
+                    help="fused-solver schedule of the timed run (auto = stepwise: one kernel per step, graph replay)")
+    ap.add_argument("--tuning", type=lambda v: int(v, 0), default=0,
+                    help="SB_TUNE_* bits of the stepwise schedule (include/stormb200.h); 0 = the library's defaults")
     ap.add_argument("--single-solver", action="store_true", help="skip the leg of the other target solver (cg <-> bicgstab)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -276,7 +276,8 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
     local_rank = local_device()
     mode = capi.COMM_NCCL if args.comm == "nccl" else capi.COMM_P2P
     method = capi.PART_SLAB if args.partition == "slab" else capi.PART_METIS
-    schedule = {"auto": capi.SCHEDULE_AUTO, "stepwise": capi.SCHEDULE_STEPWISE, "persistent": capi.SCHEDULE_PERSISTENT}[args.schedule]
+    schedule = bench_mod.SCHEDULES(capi)[args.schedule]
+    tuning = int(getattr(args, "tuning", 0))
     mesh, x_star = build_problem(args)
     part = partition_mesh(mesh, world, method)
     loc = part.local(rank)
@@ -303,8 +304,8 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
         assert s.iteration == iters, (s.iteration, iters)
         return s, x
 
-    solve(max(args.warmup, 3), use_graph=True, schedule=schedule)
-    s, x = solve(args.steps, use_graph=True, schedule=schedule)
+    solve(max(args.warmup, 3), use_graph=True, schedule=schedule, tuning=tuning)
+    s, x = solve(args.steps, use_graph=True, schedule=schedule, tuning=tuning)
     iter_ms = max_over_ranks(s.iter_ms)
     launches = int(sum_over_ranks(s.launches))
     value = args.steps / (iter_ms * 1e-3)
@@ -312,16 +313,18 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
     phases = None
     if persistent:   # the kernel's own timeline, per rank (rank 0's is printed; the waits are maxima over the ranks)
         k = min(args.steps, 64)
-        st, _ = solve(k, schedule=schedule, timeline_iters=k)
+        st, _ = solve(k, schedule=schedule, timeline_iters=k, tuning=tuning)
         phases = bench_mod.phase_times(st.timeline, args.solver)
         if phases is not None:
             for key in ("us_in_barrier_cta0", "us_wait_for_other_ranks"):
                 phases[key + "_max_over_ranks"] = {nm: max_over_ranks(v) for nm, v in phases[key].items()}
             phases["us_halo_wait_max_over_ranks"] = [max_over_ranks(v) for v in phases["us_halo_wait_max"]]
             phases["us_per_iteration_max_over_ranks"] = max_over_ranks(phases["us_per_iteration"])
-    sp, _ = solve(args.steps, profile=True)
+    sp, _ = solve(args.steps, profile=True, tuning=tuning,
+                  schedule=capi.SCHEDULE_FOLDED if s.schedule_used == capi.SCHEDULE_FOLDED else capi.SCHEDULE_STEPWISE)
     kms = [max_over_ranks(v) for v in sp.kernel_ms]
     wms = [max_over_ranks(v) for v in sp.wait_ms]
+    ams = [max_over_ranks(v) for v in sp.ar_wait_ms]
     xg = gather_global(loc, x.numpy(), mesh.n_cells)
     err = float(np.linalg.norm(xg - x_star) / np.linalg.norm(x_star))
 
@@ -329,13 +332,14 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
     hx = torch.zeros(n, dtype=torch.float64).pin_memory()
     hb = torch.from_numpy(b.numpy()).pin_memory()
     hxn, hbn = hx.numpy(), hb.numpy()
-    solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=3, abs_tol=0.0, rel_tol=0.0, use_graph=True, schedule=schedule)
+    solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=3, abs_tol=0.0, rel_tol=0.0, use_graph=True, schedule=schedule,
+               tuning=tuning)
     hxn[:] = 0.0
     ctx.sync()
     dist.barrier()
     t = time.perf_counter()
     rep = solve_host(ctx, op, args.solver, hxn, hbn, num_iterations=args.steps, abs_tol=0.0, rel_tol=0.0, use_graph=True,
-                     schedule=schedule)
+                     schedule=schedule, tuning=tuning)
     dist.barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t)
     assert rep.iterations == args.steps
@@ -356,7 +360,7 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
         cfg = workload_config(args, mesh)
         cfg.update({"partition": args.partition, "comm": args.comm, "edge_cut": int(pinfo.edge_cut),
                     "cells_per_rank": [int(pinfo.min_owned), int(pinfo.max_owned)], "max_halo": int(pinfo.max_halo),
-                    "schedule": "persistent" if persistent else "stepwise"})
+                    "schedule": bench_mod.schedule_name(capi, s.schedule_used), "tuning": tuning})
         line = {
             "metric": "krylov_iterations_per_sec", "value": value, "unit": "it/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": iter_ms / args.steps,
@@ -377,10 +381,12 @@ def bench_main(args, build_problem, workload_config, peaks, ClockSampler):
             "phases": phases,
             "stepwise": {"kernel_ms_per_iteration": {nm: kms[k] / args.steps for k, nm in enumerate(slots)},
                          "in_kernel_wait_ms_per_iteration": {nm: wms[k] / args.steps for k, nm in enumerate(slots)},
+                         "allreduce_wait_ms_per_iteration": {nm: ams[k] / args.steps for k, nm in enumerate(slots)},
                          "apply_avg_launch_ms": apply_ms,
-                         "note": "profiled run (events around every launch, no graph), maxima over the ranks; waits: apply "
-                                 "slots = a boundary CTA waiting for a neighbour's halo values, other slots = CTA 0 "
-                                 "waiting for the other ranks' partial sums of the reduction it folds"},
+                         "note": "profiled run (events around every launch, no graph), maxima over the ranks; in-kernel "
+                                 "wait: apply slots = a boundary CTA waiting for a neighbour's halo values; all-reduce wait "
+                                 "= the reducer of the slot waiting for the other ranks' sums (rank skew + one NVLink "
+                                 "crossing)"},
             "applies_per_sec": applies_per_it * value,
             "cpu_baseline": None,
             "e2e": {"value": args.steps / e2e_s, "unit": "it/s", "h2d_bytes_per_step": 16 * n_glob / args.steps,
