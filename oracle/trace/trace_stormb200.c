@@ -97,6 +97,11 @@ API int sb_eval(sb_ctx* ctx, double* y, size_t n, int assign_op, const sb_expr* 
     if (used[k]) off += snprintf(line + off, sizeof line - (size_t) off, " %d", id_of(e->vec[k]));
   snprintf(line + off, sizeof line - (size_t) off, "\n");
   put(line);
+  if (getenv("SBTRACE_OPS") != NULL) { /* debugging aid: the postfix program itself */
+    fprintf(stderr, "[sbtrace] eval ops:");
+    for (int k = 0; k < e->n_ops; ++k) fprintf(stderr, " %d", e->ops[k]);
+    fprintf(stderr, "\n");
+  }
   return SB_OK;
 }
 /* group n_reads r... n_writes w... n_dots : one launch; reads = distinct vectors read before the group wrote them

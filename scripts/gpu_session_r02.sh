@@ -136,14 +136,17 @@ PY
     done
     ;;
   g)
-    # two GPUs: the distributed tests with a GPU per rank, the strong-scaling point, config 3 and config 5 at N = 2
+    # two GPUs: the distributed tests with a GPU per rank, the tuning A/B on the strong-scaling problem, the bench line,
+    # config 3 and config 5 at N = 2
     export SB_SPIN_TIMEOUT_S=60
     timeout 900 python -m pytest tests/test_multigpu.py -m gpu -q 2>&1 | tail -15 > "$out/pytest_multigpu_n2.log"; cat "$out/pytest_multigpu_n2.log"
     unset SB_SPIN_TIMEOUT_S
-    $TR --nproc-per-node 2 --master-port 29541 bench.py --gpus 2 --steps 200 --warmup 20 > "$out/bench_n2_bicgstab.json" 2> "$out/bench_n2.err"
-    $TR --nproc-per-node 2 --master-port 29542 bench.py --gpus 2 --steps 200 --warmup 20 --solver cg > "$out/bench_n2_cg.json" 2>> "$out/bench_n2.err"
-    $TR --nproc-per-node 2 --master-port 29543 bench.py --gpus 2 --steps 200 --warmup 20 --schedule persistent > "$out/bench_n2_bicgstab_persistent.json" 2>> "$out/bench_n2.err"
-    for f in bench_n2_bicgstab bench_n2_cg bench_n2_bicgstab_persistent; do python - "$out/$f.json" <<'PY'
+    timeout 900 $TR --nproc-per-node 2 --master-port 29540 scripts/scale_ab.py --axis 119 --out "$out/ab_n2_axis119.json" \
+        --variants off,stream,noack,push,push+stream,red,red+stream,red+noack,red+push,red+push+stream,pdlfa,push+stream+pdlfa,folded,persistent \
+        > "$out/ab_n2_axis119.jsonl" 2> "$out/ab_n2_axis119.log"
+    grep "^\[ab\]" "$out/ab_n2_axis119.log"
+    timeout 600 $TR --nproc-per-node 2 --master-port 29541 bench.py --gpus 2 --steps 200 --warmup 20 > "$out/bench_n2_bicgstab.json" 2> "$out/bench_n2.err"
+    for f in bench_n2_bicgstab; do python - "$out/$f.json" <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print(sys.argv[1], round(d["value"]), "it/s", round(1e3 * d["ms_per_step"], 1), "us", d["config"]["schedule"], "e2e", round(d["e2e"]["value"]))
@@ -151,36 +154,40 @@ print("   slots us", {k: round(1e3 * v, 1) for k, v in d["stepwise"]["kernel_ms_
 print("   waits us", {k: round(1e3 * v, 1) for k, v in d["stepwise"]["in_kernel_wait_ms_per_iteration"].items()})
 PY
     done
-    $TR --nproc-per-node 2 --master-port 29544 scripts/config3_gmres.py --axis 119 --steps 100 > "$out/config3_gmres_fused_10M_n2.json" 2> "$out/config3.err"
-    $TR --nproc-per-node 2 --master-port 29545 scripts/config3_gmres.py --axis 119 --steps 100 --solver fgmres --path generic --precond jacobi > "$out/config3_fgmres_jacobi_generic_10M_n2.json" 2>> "$out/config3.err"
-    tail -c 400 "$out/config3_gmres_fused_10M_n2.json"; tail -c 400 "$out/config3_fgmres_jacobi_generic_10M_n2.json"
-    $TR --nproc-per-node 2 --master-port 29546 scripts/apply_sweep.py --cells tet,hex --sizes 1e6,1e7,3e7 --out "$out/apply_sweep_n2.json" > "$out/config5_n2.log" 2>&1
+    timeout 600 $TR --nproc-per-node 2 --master-port 29544 scripts/config3_gmres.py --axis 119 --steps 100 > "$out/config3_gmres_fused_10M_n2.json" 2> "$out/config3.err"
+    timeout 600 $TR --nproc-per-node 2 --master-port 29545 scripts/config3_gmres.py --axis 119 --steps 100 --solver fgmres --path generic --precond jacobi > "$out/config3_fgmres_jacobi_generic_10M_n2.json" 2>> "$out/config3.err"
+    tail -c 400 "$out/config3_gmres_fused_10M_n2.json"; tail -c 400 "$out/config3_fgmres_jacobi_generic_10M_n2.json"; tail -3 "$out/config3.err"
+    timeout 900 $TR --nproc-per-node 2 --master-port 29546 scripts/apply_sweep.py --cells tet,hex --sizes 1e6,1e7,3e7 --out "$out/apply_sweep_n2.json" > "$out/config5_n2.log" 2>&1
     tail -6 "$out/config5_n2.log"
     ;;
   h)
-    # eight GPUs (charged 8x: keep it short). Order = value: scaling points first, then the bit-exactness logs, config 4, 3, 5
+    # eight GPUs (charged 8x: keep it short). Order = value: the tuning A/B on the strong-scaling problem (slot times, halo
+    # and all-reduce waits, maxima over the ranks), the bit-exactness logs, config 4 at full size, N = 4, configs 3 and 5
     N=${2:-8}
-    $TR --nproc-per-node $N --master-port 29551 bench.py --gpus $N --steps 200 --warmup 20 > "$out/bench_n${N}_bicgstab.json" 2> "$out/bench_n$N.err"
-    $TR --nproc-per-node $N --master-port 29552 bench.py --gpus $N --steps 200 --warmup 20 --solver cg > "$out/bench_n${N}_cg.json" 2>> "$out/bench_n$N.err"
-    $TR --nproc-per-node 4 --master-port 29553 bench.py --gpus 4 --steps 200 --warmup 20 > "$out/bench_n4_bicgstab.json" 2>> "$out/bench_n$N.err"
-    for f in bench_n${N}_bicgstab bench_n${N}_cg bench_n4_bicgstab; do python - "$out/$f.json" <<'PY'
-import json, sys
-d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print(sys.argv[1], round(d["value"]), "it/s", round(1e3 * d["ms_per_step"], 1), "us", d["config"]["schedule"], "e2e", round(d["e2e"]["value"]))
-print("   slots us", {k: round(1e3 * v, 1) for k, v in d["stepwise"]["kernel_ms_per_iteration"].items()})
-print("   waits us", {k: round(1e3 * v, 1) for k, v in d["stepwise"]["in_kernel_wait_ms_per_iteration"].items()})
-PY
-    done
+    AB="off,stream,stream+noack,push+stream,red+stream,stream+pdlfa,folded,folded+stream,persistent"
+    timeout 300 $TR --nproc-per-node $N --master-port 29550 scripts/scale_ab.py --axis 119 --out "$out/ab_n${N}_axis119.json" --variants $AB \
+        > "$out/ab_n${N}_axis119.jsonl" 2> "$out/ab_n${N}_axis119.log"
+    grep "^\[ab\]" "$out/ab_n${N}_axis119.log"
     export SB_SPIN_TIMEOUT_S=60
-    ( time timeout 600 $TR --nproc-per-node $N --master-port 29554 tests/_dist_worker.py p2p ) > "$out/dist_worker_p2p_n$N.log" 2>&1; tail -3 "$out/dist_worker_p2p_n$N.log"
-    ( time timeout 600 $TR --nproc-per-node 4 --master-port 29555 tests/_dist_worker.py p2p ) > "$out/dist_worker_p2p_n4.log" 2>&1; tail -3 "$out/dist_worker_p2p_n4.log"
+    timeout 400 python -m pytest tests/test_multigpu.py -m gpu -q -rA 2>&1 | tail -15 > "$out/pytest_multigpu_n$N.log"; cat "$out/pytest_multigpu_n$N.log"
+    ( time timeout 200 $TR --nproc-per-node 4 --master-port 29555 tests/_dist_worker.py p2p ) > "$out/dist_worker_p2p_n4.log" 2>&1; tail -4 "$out/dist_worker_p2p_n4.log"
     unset SB_SPIN_TIMEOUT_S
-    $TR --nproc-per-node $N --master-port 29556 scripts/config4_projection.py --axis 368 --lattice --steps 10 > "$out/config4_368_n${N}_lattice.json" 2> "$out/config4.err"
-    tail -c 1200 "$out/config4_368_n${N}_lattice.json"
-    $TR --nproc-per-node 4 --master-port 29557 scripts/config3_gmres.py --axis 119 --steps 100 > "$out/config3_gmres_fused_10M_n4.json" 2> "$out/config3.err"
-    $TR --nproc-per-node $N --master-port 29558 scripts/config3_gmres.py --axis 119 --steps 100 > "$out/config3_gmres_fused_10M_n$N.json" 2>> "$out/config3.err"
+    timeout 240 $TR --nproc-per-node 4 --master-port 29551 scripts/scale_ab.py --axis 119 --out "$out/ab_n4_axis119.json" --variants off,stream,persistent \
+        > "$out/ab_n4_axis119.jsonl" 2> "$out/ab_n4_axis119.log"
+    grep "^\[ab\]" "$out/ab_n4_axis119.log"
+    timeout 240 $TR --nproc-per-node $N --master-port 29552 scripts/scale_ab.py --axis 119 --partition slab --out "$out/ab_n${N}_axis119_slab.json" --variants off,stream,persistent \
+        > "$out/ab_n${N}_axis119_slab.jsonl" 2> "$out/ab_n${N}_axis119_slab.log"
+    grep "^\[ab\]" "$out/ab_n${N}_axis119_slab.log"
+    ;;
+  h2)
+    # eight GPUs, second call: config 4 at full size, configs 3 and 5
+    N=${2:-8}
+    timeout 300 $TR --nproc-per-node $N --master-port 29556 scripts/config4_projection.py --axis 368 --lattice --steps 10 > "$out/config4_368_n${N}_lattice.json" 2> "$out/config4.err"
+    tail -c 1200 "$out/config4_368_n${N}_lattice.json"; tail -3 "$out/config4.err"
+    timeout 300 $TR --nproc-per-node $N --master-port 29558 scripts/config3_gmres.py --axis 119 --steps 100 > "$out/config3_gmres_fused_10M_n$N.json" 2>> "$out/config3.err"
+    timeout 300 $TR --nproc-per-node 4 --master-port 29557 scripts/config3_gmres.py --axis 119 --steps 100 > "$out/config3_gmres_fused_10M_n4.json" 2> "$out/config3.err"
     tail -c 300 "$out/config3_gmres_fused_10M_n4.json"; tail -c 300 "$out/config3_gmres_fused_10M_n$N.json"
-    $TR --nproc-per-node $N --master-port 29559 scripts/apply_sweep.py --cells hexlat --sizes 1e7,1e8,2e8 --out "$out/apply_sweep_hexlat_n$N.json" > "$out/config5_n$N.log" 2>&1
+    timeout 400 $TR --nproc-per-node $N --master-port 29559 scripts/apply_sweep.py --cells hexlat --sizes 1e7,1e8,2e8 --out "$out/apply_sweep_hexlat_n$N.json" > "$out/config5_n$N.log" 2>&1
     tail -4 "$out/config5_n$N.log"
     ;;
 esac

@@ -55,7 +55,9 @@ VARIANTS = {
     "red+push+stream+pdlall": (T.SCHEDULE_STEPWISE, T.TUNE_IN_KERNEL_REDUCER | T.TUNE_PUSH_ON_PRODUCE | T.TUNE_STREAM_OPERATOR
                                | T.TUNE_PDL_AFTER_FINAL | T.TUNE_PDL_APPLY),
     "red+noack": (T.SCHEDULE_STEPWISE, T.TUNE_IN_KERNEL_REDUCER | T.TUNE_NO_ACK),
-    "folded": (T.SCHEDULE_FOLDED, 0),
+    "stream+noack": (T.SCHEDULE_STEPWISE, T.TUNE_STREAM_OPERATOR | T.TUNE_NO_ACK),
+    "folded": (T.SCHEDULE_FOLDED, T.TUNE_OFF),
+    "folded+stream": (T.SCHEDULE_FOLDED, T.TUNE_STREAM_OPERATOR),
     "persistent": (T.SCHEDULE_PERSISTENT, 0),
 }
 SLOTS = {"bicgstab": ["direction", "apply+dot", "half_update", "apply+2dots", "final_update+2dots"],

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <unordered_map>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/stormb200.h"

@@ -422,6 +422,45 @@ __device__ __forceinline__ double eval_prog(const Prog& P, const double (&in)[NV
   return s0;
 }
 
+// The same stack machine for a RUN-TIME program, on both elements of a 128-bit pair at once: a rolled loop over the
+// program with real branches (the opcode sits in the kernel parameters, so every branch is warp-uniform). The
+// unrolled form above folds away with a StaticProg, but with a run-time program ptxas predicates all 24 steps --
+// every step then issues both divisions' slow paths whatever the opcode: 760 us for a 3-vector statement at 10.1 M
+// cells, where the static kernels need 50 (profiles/r02_launches_cgs_10M_runtime_program_summary.txt).
+template<int NV>
+__device__ __forceinline__ double2 eval_prog_pair(const RuntimeProg& P, const double2 (&in)[NV],
+                                                  const double (&sc)[SB_EXPR_MAX_SCAL]) {
+  double2 s0 = {0.0, 0.0}, s1 = s0, s2 = s0, s3 = s0, s4 = s0, s5 = s0;
+#pragma unroll 1
+  for (int k = 0; k < P.n; ++k) {
+    const int op = P.code[k];
+    if (op < SB_OP_ADD) {
+      double2 v;
+      if (op < SB_OP_SCAL0) {
+        v = in[0];
+        if constexpr (NV > 1) v = (op == 1) ? in[1] : v;
+        if constexpr (NV > 2) v = (op == 2) ? in[2] : v;
+        if constexpr (NV > 3) v = (op == 3) ? in[3] : v;
+      } else {
+        const int q = op - SB_OP_SCAL0;
+        const double c = (q == 0) ? sc[0] : (q == 1) ? sc[1] : (q == 2) ? sc[2] : sc[3];
+        v = {c, c};
+      }
+      s5 = s4, s4 = s3, s3 = s2, s2 = s1, s1 = s0, s0 = v;
+    } else if (op == SB_OP_NEG) {
+      s0 = {-s0.x, -s0.y};
+    } else {
+      double2 v;
+      if (op == SB_OP_ADD) v = {__dadd_rn(s1.x, s0.x), __dadd_rn(s1.y, s0.y)};
+      else if (op == SB_OP_SUB) v = {__dsub_rn(s1.x, s0.x), __dsub_rn(s1.y, s0.y)};
+      else if (op == SB_OP_MUL) v = {__dmul_rn(s1.x, s0.x), __dmul_rn(s1.y, s0.y)};
+      else v = {__ddiv_rn(s1.x, s0.x), __ddiv_rn(s1.y, s0.y)};
+      s0 = v, s1 = s2, s2 = s3, s3 = s4, s4 = s5;
+    }
+  }
+  return s0;
+}
+
 template<int AOP>
 __device__ __forceinline__ double apply_assign(double y, double v) {
   if constexpr (AOP == SB_ASSIGN) return v;
@@ -447,12 +486,18 @@ struct EvalBody {
     if constexpr (AOP != SB_ASSIGN) r.y = ld2(y, e0);
   }
   __device__ __forceinline__ void run(int64_t e0, int64_t, Regs& r, double (&)[1]) const {
-    double a[NV], b[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) a[k] = r.in[k].x, b[k] = r.in[k].y;
     double2 out;
-    out.x = apply_assign<AOP>(r.y.x, eval_prog<NV>(prog, a, sc));
-    out.y = apply_assign<AOP>(r.y.y, eval_prog<NV>(prog, b, sc));
+    if constexpr (std::is_same_v<Prog, RuntimeProg>) {
+      const double2 v = eval_prog_pair<NV>(prog, r.in, sc);
+      out.x = apply_assign<AOP>(r.y.x, v.x);
+      out.y = apply_assign<AOP>(r.y.y, v.y);
+    } else {
+      double a[NV], b[NV];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) a[k] = r.in[k].x, b[k] = r.in[k].y;
+      out.x = apply_assign<AOP>(r.y.x, eval_prog<NV>(prog, a, sc));
+      out.y = apply_assign<AOP>(r.y.y, eval_prog<NV>(prog, b, sc));
+    }
     st2(y, e0, out);
   }
 };

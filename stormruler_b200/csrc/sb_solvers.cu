@@ -124,7 +124,9 @@ static int check_vector(sb_ctx* ctx, const double* v, int64_t n, const char* wha
 }
 
 // What sb_solver_opts::tuning == 0 selects (measured on 1, 2 and 8 GPUs).
-constexpr uint32_t kDefaultTuning = 0;
+// STREAM_OPERATOR: 1 GPU 1.23 M / 2.5 M / 10.1 M cells BiCGStab +9 % / +10 % / +-0, CG +5 % / +15 % / +-0; 2 GPUs, 10.1 M cells
+// +4 % / +7 % (profiles/r02_ab_*). Every other bit measured slower or equal on one and two GPUs.
+constexpr uint32_t kDefaultTuning = SB_TUNE_STREAM_OPERATOR;
 
 struct Solve {
   sb_ctx* ctx;
