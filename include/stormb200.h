@@ -435,6 +435,9 @@ typedef struct sb_solver_opts {
                                          all-reduce over the ranks and the scalar update; no one-CTA kernels between
                                          the steps (3 / 5 launches per CG / BiCGStab iteration), nobody waits in-kernel */
 #define SB_TUNE_PDL_APPLY 32u /* the apply kernels too (they follow an element-wise kernel; slice prefetch under its tail) */
+#define SB_TUNE_PUSH_LAZY 128u /* with PUSH_ON_PRODUCE: the producer only issues the peer stores (posted writes that drain
+                                  while the rest of it runs; its completion performs them); the flags are raised by the
+                                  first CTA of the consuming apply: no fence, ticket or flag in the producer */
 #define SB_TUNE_OFF 0x80000000u
 
 /* Schedules of the fused CG / BiCGStab solvers (bit-identical results; measurements: DESIGN.md 5d):

@@ -135,6 +135,19 @@ PY
       grep "^\[ab\]" "$out/ab_n1_axis$ax.log"
     done
     ;;
+  j)
+    # one GPU: lazy halo push (two ranks sharing the GPU: protocol + bits), batched in-kernel reducer, rolled run-time
+    # expression interpreter; A/B at the per-rank size of 8 GPUs and at full size; CGS through the reference template
+    export SB_SPIN_TIMEOUT_S=30
+    timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 > "$out/pytest_gpu.log"; tail -8 "$out/pytest_gpu.log"
+    unset SB_SPIN_TIMEOUT_S
+    for ax in 59 119; do
+      timeout 600 python scripts/scale_ab.py --axis $ax --variants off,stream,red,red+stream,stream+pdlfa --out "$out/ab_n1_axis$ax.json" > "$out/ab_n1_axis$ax.jsonl" 2> "$out/ab_n1_axis$ax.log"
+      grep "^\[ab\]" "$out/ab_n1_axis$ax.log"
+    done
+    python scripts/solver_sweep.py --solvers cgs,bicgstab,tfqmr --out "$out/solver_sweep_cgs.json" > "$out/solver_sweep_cgs.log" 2>&1
+    tail -4 "$out/solver_sweep_cgs.log"
+    ;;
   g)
     # two GPUs: the distributed tests with a GPU per rank, the tuning A/B on the strong-scaling problem, the bench line,
     # config 3 and config 5 at N = 2

@@ -56,6 +56,11 @@ VARIANTS = {
                                | T.TUNE_PDL_AFTER_FINAL | T.TUNE_PDL_APPLY),
     "red+noack": (T.SCHEDULE_STEPWISE, T.TUNE_IN_KERNEL_REDUCER | T.TUNE_NO_ACK),
     "stream+noack": (T.SCHEDULE_STEPWISE, T.TUNE_STREAM_OPERATOR | T.TUNE_NO_ACK),
+    "lazy": (T.SCHEDULE_STEPWISE, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PUSH_LAZY),
+    "lazy+stream": (T.SCHEDULE_STEPWISE, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PUSH_LAZY | T.TUNE_STREAM_OPERATOR),
+    "lazy+stream+red": (T.SCHEDULE_STEPWISE, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PUSH_LAZY | T.TUNE_STREAM_OPERATOR | T.TUNE_IN_KERNEL_REDUCER),
+    "lazy+stream+pdlfa": (T.SCHEDULE_STEPWISE, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PUSH_LAZY | T.TUNE_STREAM_OPERATOR | T.TUNE_PDL_FINAL
+                          | T.TUNE_PDL_AFTER_FINAL),
     "folded": (T.SCHEDULE_FOLDED, T.TUNE_OFF),
     "folded+stream": (T.SCHEDULE_FOLDED, T.TUNE_STREAM_OPERATOR),
     "persistent": (T.SCHEDULE_PERSISTENT, 0),

@@ -18,6 +18,7 @@ COMM_NCCL, COMM_P2P = 0, 1
 SCHEDULE_AUTO, SCHEDULE_STEPWISE, SCHEDULE_PERSISTENT, SCHEDULE_FOLDED = 0, 1, 2, 3
 TIMELINE_WORDS = 20
 TUNE_PUSH_ON_PRODUCE, TUNE_NO_ACK, TUNE_STREAM_OPERATOR, TUNE_PDL_FINAL, TUNE_PDL_AFTER_FINAL, TUNE_PDL_APPLY, TUNE_IN_KERNEL_REDUCER, TUNE_OFF = 1, 2, 4, 8, 16, 32, 64, 0x80000000
+TUNE_PUSH_LAZY = 128
 COMM_BLOB_BYTES = 256
 ASSIGN, ADD_ASSIGN, SUB_ASSIGN, MUL_ASSIGN, DIV_ASSIGN = range(5)
 OP_VEC0, OP_SCAL0 = 0, 8

@@ -160,8 +160,15 @@ __device__ __forceinline__ void halo_pack_role(const CommDev& comm, const HaloDe
 // kernel, the kernel boundary and the apply's interior tiles run; the apply itself has no pack CTAs and its boundary
 // tiles normally find the flags up. No ack round: a producer runs behind an all-reduce to which every neighbour
 // contributed only after its previous apply of this vector had completed (sb_op.cuh: ApplyDist::no_ack).
+//
+// `lazy` (SB_TUNE_PUSH_LAZY): the CTA only issues the peer stores -- no fence, no ticket, no flag. The stores are posted
+// writes that drain while the rest of the producer runs (boundary tiles come first), the producer's completion is
+// what makes them performed, and the flags are raised by the first CTA of the CONSUMING apply (halo_post_flags) as
+// soon as that kernel starts. Measured at 8 GPUs the fence + ticket + fence + flag chain of the eager form doubled
+// the producer kernels (10 -> 20 us), and the same chain inside the apply's pack CTAs arrived 10 us after the boundary
+// tiles needed it (profiles/r02_ab_n8_10M.txt).
 __device__ __forceinline__ void halo_push_tile(const CommDev& comm, const HaloDev& halo, const double* y, int64_t y_off,
-                                               int64_t tile) {
+                                               int64_t tile, bool lazy) {
   __syncthreads(); // the tile's stores to y are visible to the whole CTA
   CommCtrl* me = comm.ctrl(comm.rank);
   const int q = (int) (tile - halo.first_boundary_tile);
@@ -173,6 +180,7 @@ __device__ __forceinline__ void halo_push_tile(const CommDev& comm, const HaloDe
     double* dst = reinterpret_cast<double*>(comm.base[halo.nbr_rank[k]] + y_off) + en.y;
     *dst = v;
   }
+  if (lazy) return;
   __threadfence_system(); // my peer stores are performed before the ticket below is taken
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -184,6 +192,18 @@ __device__ __forceinline__ void halo_push_tile(const CommDev& comm, const HaloDe
       for (int k = 0; k < halo.n_nbr; ++k)
         st_relaxed_sys(&comm.ctrl(halo.nbr_rank[k])->halo_flag[comm.rank], seq);
     }
+  }
+}
+
+// Lazy push, consumer side: the kernel that produced x has completed (stream order; griddepcontrol.wait has returned),
+// so its peer stores are performed; one system fence makes that cumulative, then the flags go out as posted stores.
+// Called by the first CTA of the apply, before anything else.
+__device__ __forceinline__ void halo_post_flags(const CommDev& comm, const HaloDev& halo) {
+  if (threadIdx.x < halo.n_nbr) {
+    CommCtrl* me = comm.ctrl(comm.rank);
+    const unsigned long long seq = ld_acquire_sys(&me->apply_seq) + 1; // this apply's number
+    __threadfence_system();
+    st_relaxed_sys(&comm.ctrl(halo.nbr_rank[threadIdx.x])->halo_flag[comm.rank], seq);
   }
 }
 

@@ -7,6 +7,8 @@
 
 namespace sb {
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ double safe_divide(double x, double y) {
   // Crow/MathUtils.hpp:49-52
   return (y == 0.0) ? 0.0 : __ddiv_rn(x, y);
@@ -160,25 +162,63 @@ static __device__ __noinline__ void reducer_role(const ReducerArgs& ra) {
   __shared__ double s_w[kMaxDots][kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned long long t_begin = globaltimer_ns();
+  if (threadIdx.x < 2) prefetch_l1(reinterpret_cast<const unsigned char*>(ra.rec.st) + 128 * threadIdx.x); // the scalar update's state
   bool gave_up = false;
   double sums[kMaxDots];
-  for (int d = 0; d < ra.nd; ++d) {
-    double s = 0.0;
-    unsigned long long* part = reinterpret_cast<unsigned long long*>(ra.slots + (int64_t) d * ra.cap_tiles);
-    for (int64_t q = threadIdx.x; q < ra.n_tiles; q += kThreads) {
-      unsigned long long v = ld_relaxed_gpu(part + q);
-      unsigned spins = 0;
-      while (v == kArSentinel && !gave_up) {
-        __nanosleep(32);
-        v = ld_relaxed_gpu(part + q);
-        // a tile CTA that never deposits (it cannot happen short of a device fault) must not hang the device
-        if ((++spins & 1023u) == 0 && globaltimer_ns() - t_begin > ra.comm.timeout_ns + 20000000000ull) gave_up = true;
+  // Thread t takes partial[t], partial[t + 256], ... of every sum, in that order (final_stage's order). The loads of a
+  // batch -- all sums, four slots each -- are issued together: one L2 round trip for everything that has already been
+  // deposited; only a slot that still holds the sentinel is polled. (The first version polled slot by slot: six
+  // dependent round trips per thread for two sums at 617 tiles, 4-9 us behind the last tile CTA, more than the one-CTA
+  // kernel it replaced: profiles/r02_ab_n8_10M.txt, variant red+stream.)
+  constexpr int kBatch = 4;
+  double s[kMaxDots];
+#pragma unroll
+  for (int d = 0; d < kMaxDots; ++d) s[d] = 0.0;
+  for (int64_t q0 = threadIdx.x; q0 < ra.n_tiles; q0 += (int64_t) kBatch * kThreads) {
+    unsigned long long v[kMaxDots][kBatch];
+#pragma unroll
+    for (int d = 0; d < kMaxDots; ++d)
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b)
+        v[d][b] = (d < ra.nd && q0 + (int64_t) b * kThreads < ra.n_tiles) ? kArSentinel : 0ull;
+    unsigned spins = 0;
+    for (;;) { // every pass re-reads ALL slots of the batch that are still missing, independently of each other
+      bool missing = false;
+#pragma unroll
+      for (int d = 0; d < kMaxDots; ++d) {
+        const unsigned long long* part = reinterpret_cast<const unsigned long long*>(ra.slots + (int64_t) d * ra.cap_tiles);
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b)
+          if (v[d][b] == kArSentinel) v[d][b] = ld_relaxed_gpu(part + q0 + (int64_t) b * kThreads);
       }
-      part[q] = kArSentinel;
-      s = __dadd_rn(s, __longlong_as_double((long long) v));
+#pragma unroll
+      for (int d = 0; d < kMaxDots; ++d)
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) missing |= v[d][b] == kArSentinel;
+      if (!missing || gave_up) break;
+      __nanosleep(20);
+      // a tile CTA that never deposits (it cannot happen short of a device fault) must not hang the device
+      if ((++spins & 1023u) == 0 && globaltimer_ns() - t_begin > ra.comm.timeout_ns + 20000000000ull) gave_up = true;
     }
-    const double w = warp_butterfly(s);
-    if (lane == 0) s_w[d][warp] = w;
+#pragma unroll
+    for (int d = 0; d < kMaxDots; ++d) {
+      unsigned long long* part = reinterpret_cast<unsigned long long*>(ra.slots + (int64_t) d * ra.cap_tiles);
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int64_t q = q0 + (int64_t) b * kThreads;
+        if (d < ra.nd && q < ra.n_tiles) {
+          part[q] = kArSentinel;
+          s[d] = __dadd_rn(s[d], __longlong_as_double((long long) v[d][b]));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < kMaxDots; ++d) {
+    if (d < ra.nd) {
+      const double w = warp_butterfly(s[d]);
+      if (lane == 0) s_w[d][warp] = w;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {

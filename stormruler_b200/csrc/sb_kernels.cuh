@@ -120,6 +120,16 @@ __device__ __forceinline__ void final_stage(int64_t n_tiles, const RedPtrs& red,
   }
 }
 
+// The solver state a Final functor updates (PublishFinal<...>), or null (StoreFinal, NoFinal).
+template<class F>
+__device__ __forceinline__ auto final_state_of(const F& f, int) -> decltype((const void*) f.inner.rec.st) {
+  return f.inner.rec.st;
+}
+template<class F>
+__device__ __forceinline__ const void* final_state_of(const F&, long) {
+  return nullptr;
+}
+
 // The one-CTA kernel behind every reducing kernel of the one-kernel-per-step schedule. `fin(sums)` runs on one
 // thread: that is where the solver scalars (alpha, beta, residual, stop flag) are updated.
 template<int ND, class Final>
@@ -129,6 +139,9 @@ __global__ void __launch_bounds__(kThreads) final_reduce_kernel(int64_t n_tiles,
   pdl_trigger();
   pdl_wait();
   if (is_done(done)) return;
+  // the scalar update's state: on its way into L1 while the partial sums are read and the ranks exchange theirs
+  if (const void* st = final_state_of(fin, 0); st != nullptr && threadIdx.x < 2)
+    prefetch_l1(reinterpret_cast<const unsigned char*>(st) + 128 * threadIdx.x);
   __shared__ double s_w[kMaxDots][kWarps];
   double sums[ND];
   final_stage<ND>(n_tiles, red, s_w, sums);

@@ -38,6 +38,7 @@ struct ApplyDist {
                                // contributes to it only after its earlier apply has completed
   int32_t pre_pushed = 0;      // 1: the kernel that produced x has already pushed the boundary values (halo_push_tile):
                                // no pack CTAs (n_pack == 0), the boundary tiles only acquire the flags
+  int32_t post_flags = 0;      // 1 (with pre_pushed): the push was lazy -- this kernel's first CTA raises the flags
   unsigned long long* wait_ns = nullptr; // optional: longest halo-flag wait of any boundary CTA (atomicMax)
 };
 
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double*
   }
   const int64_t tile = (int64_t) blockIdx.x - ad.n_pack;
   const int coh = ad.coherent_gather && tile >= ad.halo.first_boundary_tile;
+  if (ad.post_flags && blockIdx.x == 0) halo_post_flags(ad.comm, ad.halo); // lazy push: the producer has completed
   apply_halo_wait(ad, tile);
   double acc[ND > 0 ? ND : 1];
 #pragma unroll
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(kThreads, StageLayout<W>::min_ctas) apply_kern
   // The epilogue's third vector (r~ or b) is read with plain coalesced loads, all four sub-iterations up
   // front so they are in flight under the pipeline: measured 10 % faster than staging it as a third bulk
   // copy per stage (apply + <r~,v> at 10.1 M cells: 138 us against 152 us), and 512 B less ring per stage.
+  if (ad.post_flags && blockIdx.x == 0) halo_post_flags(ad.comm, ad.halo); // lazy push: the producer has completed
   typename Epi::Regs er[kSub];
 #pragma unroll
   for (int j = 0; j < kSub; ++j) epi.load(row0 + j * 64 + 2 * lane, er[j]);
@@ -455,6 +458,7 @@ struct PushArgs {
   int64_t y_off = 0;         // its byte offset inside the slab (the same on every rank)
   int64_t n_tiles = 0;
   int32_t push = 0;
+  int32_t lazy = 0;          // 1: stores only; the consuming apply raises the flags (halo_post_flags)
 };
 
 template<int ND, class Body>
@@ -478,7 +482,7 @@ __global__ void __launch_bounds__(kThreads) ew_solver_kernel(int64_t n, Body bod
 #pragma unroll
   for (int j = 0; j < kSub; ++j) body.run(lane_elem(tile, j), n, r[j], acc);
   if constexpr (ND > 0) block_reduce_partials<ND>(acc, red, tile);
-  if (pa.push && tile >= pa.halo.first_boundary_tile) halo_push_tile(pa.comm, pa.halo, pa.y, pa.y_off, tile);
+  if (pa.push && tile >= pa.halo.first_boundary_tile) halo_push_tile(pa.comm, pa.halo, pa.y, pa.y_off, tile, pa.lazy != 0);
 }
 
 // y = x / diag (Jacobi). The diagonal lives inside the blocked slice records (or in OpDev::diag for the v1 layout).
@@ -535,7 +539,8 @@ struct ApplyOpts {
                                    // it (sb_kernels.cuh: Fold) instead of a one-CTA final stage behind this launch
   int halo_mode = 0;               // distributed operator, P2P: 0 = pack CTAs inside the apply + ack round (any caller);
                                    // 1 = pack CTAs, no ack round (fused solvers: ApplyDist::no_ack); 2 = the producer of
-                                   // x has pushed the boundary values already (halo_push_tile), no pack CTAs
+                                   // x has pushed the boundary values already (halo_push_tile), no pack CTAs; 3 = the
+                                   // same, lazily: stores only, this kernel's first CTA raises the flags
   unsigned long long* halo_wait_ns = nullptr; // optional timeline: longest halo-flag wait of a boundary CTA
   unsigned long long* ar_wait_ns = nullptr;   // optional timeline: the final stage's wait for the other ranks' sums
   bool pdl = false, pdl_final = false;        // programmatic-serialization attribute on the apply / on its final stage
@@ -564,8 +569,8 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
     if (ctx->comm.mode == SB_COMM_P2P && exchange) {
       ad.comm = ctx->comm, ad.halo = op->halo, ad.x_off = x_off;
       const int64_t total = op->halo.send_ptr[op->halo.n_nbr];
-      if (ao.halo_mode == 2) {
-        ad.n_pack = 0, ad.pre_pushed = 1;
+      if (ao.halo_mode >= 2) {
+        ad.n_pack = 0, ad.pre_pushed = 1, ad.post_flags = ao.halo_mode == 3 ? 1 : 0;
       } else {
         ad.n_pack = (int32_t) std::max<int64_t>(1, std::min<int64_t>(64, (total + 2 * kThreads - 1) / (2 * kThreads)));
         ad.no_ack = (ao.fold_later || ao.halo_mode == 1) ? 1 : 0;

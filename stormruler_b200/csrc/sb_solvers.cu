@@ -53,7 +53,7 @@ int launch_ew_solver(sb_ctx* ctx, const sb_op* op, int64_t n, const Body& body, 
   PushArgs pa;
   pa.n_tiles = num_tiles(n);
   if (push_y != nullptr) {
-    pa.comm = ctx->comm, pa.halo = op->halo, pa.y = push_y, pa.push = 1;
+    pa.comm = ctx->comm, pa.halo = op->halo, pa.y = push_y, pa.push = 1, pa.lazy = (ctx->tuning & SB_TUNE_PUSH_LAZY) ? 1 : 0;
     pa.y_off = (int64_t) (reinterpret_cast<const unsigned char*>(push_y) - ctx->slab);
   }
   {
@@ -278,7 +278,7 @@ struct Solve {
   template<int ND, bool RESID, class Epi, class Final>
   int stepwise_apply(const double* in, double* out, const Epi& epi, const Final& fin, FinalKind kind) {
     ApplyOpts ao;
-    ao.halo_mode = push ? 2 : (no_ack ? 1 : 0);
+    ao.halo_mode = push ? ((ctx->tuning & SB_TUNE_PUSH_LAZY) ? 3 : 2) : (no_ack ? 1 : 0);
     ao.pdl = pdl_apply, ao.pdl_final = pdl_final;
     const WaitPair w = wait_slot();
     ao.halo_wait_ns = w.own, ao.ar_wait_ns = w.ar;

@@ -225,7 +225,8 @@ def run_gpu(dist, rank, world, mode_name):
             if form == sb.FORM_FAITHFUL:
                 variants = [(capi.SCHEDULE_AUTO, False, 0), (capi.SCHEDULE_AUTO, True, 0)]
                 if mode == capi.COMM_P2P:
-                    variants += [(capi.SCHEDULE_STEPWISE, True, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PDL_FINAL),
+                    variants += [(capi.SCHEDULE_STEPWISE, True, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PUSH_LAZY),
+                                 (capi.SCHEDULE_STEPWISE, True, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PDL_FINAL),
                                  (capi.SCHEDULE_STEPWISE, True, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_IN_KERNEL_REDUCER)]
             elif mode == capi.COMM_P2P:
                 variants = [(capi.SCHEDULE_PERSISTENT, False, 0), (capi.SCHEDULE_STEPWISE, True, T.TUNE_OFF),
@@ -233,6 +234,10 @@ def run_gpu(dist, rank, world, mode_name):
                             (capi.SCHEDULE_PERSISTENT, False, 0), (capi.SCHEDULE_AUTO, False, 0),
                             (capi.SCHEDULE_STEPWISE, False, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PDL_FINAL | T.TUNE_PDL_AFTER_FINAL),
                             (capi.SCHEDULE_FOLDED, True, 0),
+                            (capi.SCHEDULE_STEPWISE, True, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PUSH_LAZY | T.TUNE_STREAM_OPERATOR),
+                            (capi.SCHEDULE_STEPWISE, False, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PUSH_LAZY | T.TUNE_IN_KERNEL_REDUCER),
+                            (capi.SCHEDULE_STEPWISE, True, T.TUNE_PUSH_ON_PRODUCE | T.TUNE_PUSH_LAZY | T.TUNE_IN_KERNEL_REDUCER
+                             | T.TUNE_STREAM_OPERATOR | T.TUNE_PDL_AFTER_FINAL | T.TUNE_PDL_APPLY),
                             (capi.SCHEDULE_STEPWISE, True, T.TUNE_IN_KERNEL_REDUCER),
                             (capi.SCHEDULE_STEPWISE, False, T.TUNE_IN_KERNEL_REDUCER | T.TUNE_PUSH_ON_PRODUCE),
                             (capi.SCHEDULE_STEPWISE, True, T.TUNE_IN_KERNEL_REDUCER | T.TUNE_PUSH_ON_PRODUCE | T.TUNE_STREAM_OPERATOR
