@@ -270,6 +270,7 @@ def schedule_name(capi, used):
 
 SLOTS = {"bicgstab": ["direction", "apply+dot", "half_update", "apply+2dots", "final_update+2dots"],
          "cg": ["apply+dot", "update+dot", "direction"]}
+APPLY_EPILOGUE = {"bicgstab": {"apply+dot": "EpiUY", "apply+2dots": "EpiYYandYX"}, "cg": {"apply+dot": "EpiXY"}}
 KERNEL_NAME = {"bicgstab": "sb::krylov_persistent_kernel<BiCgStab, W> (the whole iteration loop, ONE cooperative launch)",
                "cg": "sb::krylov_persistent_kernel<Cg, W> (the whole iteration loop, ONE cooperative launch)"}
 
@@ -329,16 +330,33 @@ def run_own_arm(args):
         sp, _ = solve(args.steps, profile=True, schedule=capi.SCHEDULE_FOLDED if s.schedule_used == capi.SCHEDULE_FOLDED else capi.SCHEDULE_STEPWISE,
                       tuning=args.tuning)
         kms = list(sp.kernel_ms)
+        fms = list(sp.final_ms)                       # the one-CTA final stage behind a reducing kernel (its own event)
         slots = SLOTS[solver]
         apply_slots = [k for k, nm in enumerate(slots) if nm.startswith("apply")]
-        apply_ms = sum(kms[k] for k in apply_slots) / (len(apply_slots) * args.steps)   # avg per launch
+        # every apply variant against ITS OWN algorithmic bytes: the <r~,v> epilogue reads a third vector (+ 8 N)
+        variants = []
+        for k in apply_slots:
+            epi = APPLY_EPILOGUE[solver][slots[k]]
+            bytes_k = alg_apply + (8 * n if epi == "EpiUY" else 0)
+            ms_k = (kms[k] - fms[k]) / args.steps     # the apply kernel alone
+            variants.append({"slot": slots[k], "kernel": f"sb::apply_kernel_tma<W, ., ., {epi}>",
+                             "algorithmic_bytes_per_launch": int(bytes_k), "avg_launch_ms": ms_k,
+                             "final_stage_ms": fms[k] / args.steps,
+                             "achieved": bytes_k / (ms_k * 1e-3) / 1e9, "frac": bytes_k / (ms_k * 1e-3) / 1e9 / peak})
+        tot_bytes = sum(v["algorithmic_bytes_per_launch"] for v in variants)
+        tot_ms = sum(v["avg_launch_ms"] for v in variants)
         out["stepwise"] = {"kernel_ms_per_iteration": {nm: kms[k] / args.steps for k, nm in enumerate(slots)},
+                           "final_stage_ms_per_iteration": {nm: fms[k] / args.steps for k, nm in enumerate(slots)},
                            "in_kernel_wait_ms_per_iteration": {nm: sp.wait_ms[k] / args.steps for k, nm in enumerate(slots)},
-                           "apply_kernel": {"kernel": "sb::apply_kernel_tma + one-CTA final stage (stepwise schedule, profiled)",
-                                            "algorithmic_bytes_per_launch": int(alg_apply), "avg_launch_ms": apply_ms,
-                                            "achieved": alg_apply / (apply_ms * 1e-3) / 1e9,
-                                            "frac": alg_apply / (apply_ms * 1e-3) / 1e9 / peak,
-                                            "share_of_step": sum(kms[k] for k in apply_slots) / sum(kms[:len(slots)])}}
+                           "apply_kernel": {"kernel": "sb::apply_kernel_tma (stepwise schedule, profiled: CUDA events around every "
+                                                      "launch; the one-CTA final stage behind it is timed separately)",
+                                            "algorithmic_bytes_per_launch": tot_bytes / len(variants),
+                                            "avg_launch_ms": tot_ms / len(variants),
+                                            "achieved": tot_bytes / (tot_ms * 1e-3) / 1e9,
+                                            "frac": tot_bytes / (tot_ms * 1e-3) / 1e9 / peak,
+                                            "share_of_step": sum(kms[k] - fms[k] for k in apply_slots) / sum(kms[:len(slots)]),
+                                            "launches_timed": len(variants) * args.steps,
+                                            "variants": variants}}
         return out
 
     main = measure(args.solver)
@@ -347,13 +365,18 @@ def run_own_arm(args):
         other = measure("cg" if args.solver == "bicgstab" else "bicgstab")   # the other target solver, same problem
     s, x = main["s"], main["x"]
     err = np.linalg.norm(x.numpy() - x_star) / np.linalg.norm(x_star)
+    # DRAM bytes per launch of the same kernels from the committed `ncu --set full` capture (per apply variant; only
+    # valid for the workload it was captured on), averaged over the variants like `achieved`
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "persistent_traffic.json")
-    if os.path.exists(tpath):
+    tpath = os.path.join(ROOT, "profiles", "apply_traffic.json")
+    if main["schedule"] != "persistent" and os.path.exists(tpath):
         try:
-            t = json.load(open(tpath))[args.solver]
-            # dram bytes per iteration of the same kernel from the committed ncu --set full capture, scaled to K
-            traffic, traffic_src = t["dram_bytes_per_iteration"] * args.steps, t["source"]
+            t = json.load(open(tpath))
+            if t.get("workload") == {"cell": args.cell, "axis": args.n}:
+                per = [t["variants"][APPLY_EPILOGUE[args.solver][v["slot"]]] for v in main["stepwise"]["apply_kernel"]["variants"]]
+                for v, b_ in zip(main["stepwise"]["apply_kernel"]["variants"], per):
+                    v["traffic"] = b_
+                traffic, traffic_src = sum(per) / len(per), t["source"]
         except Exception:
             traffic = None
 
@@ -403,7 +426,7 @@ def run_own_arm(args):
             cpu_all = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     persistent = main["schedule"] == "persistent"
-    alg_launch = main["alg_iter"] * args.steps if persistent else alg_apply
+    alg_launch = main["alg_iter"] * args.steps if persistent else main["stepwise"]["apply_kernel"]["algorithmic_bytes_per_launch"]
     launch_ms = s.iter_ms if persistent else main["stepwise"]["apply_kernel"]["avg_launch_ms"]
     achieved = alg_launch / (launch_ms * 1e-3) / 1e9
     line = {
@@ -416,7 +439,8 @@ def run_own_arm(args):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_launch), "avg_launch_ms": launch_ms,
-                     "launches_timed": 1 if persistent else 2 * args.steps,
+                     "launches_timed": 1 if persistent else main["stepwise"]["apply_kernel"]["launches_timed"],
+                     "variants": None if persistent else main["stepwise"]["apply_kernel"]["variants"],
                      "share_of_step": 1.0 if persistent else main["stepwise"]["apply_kernel"]["share_of_step"],
                      "note": "persistent schedule: one launch = K iterations = K x (applies x (24 N + 12 entries) + passes x 8 N) "
                              "algorithmic bytes, timed by CUDA events around the launch" if persistent else None},

@@ -488,6 +488,9 @@ typedef struct sb_solver_report {
   double ar_wait_ms[SB_MAX_KERNEL_SLOTS]; /* profile=1, STEPWISE on several GPUs: per kernel slot, how long the one-CTA
                                             final stage behind the slot waited for the other ranks' sums after posting
                                             its own (rank skew + one NVLink crossing), summed over the iterations */
+  double final_ms[SB_MAX_KERNEL_SLOTS];  /* profile=1, STEPWISE with one-CTA final stages: the part of kernel_ms[k] that
+                                            is the final stage behind the slot's kernel (from an event recorded between
+                                            the two launches): kernel_ms[k] - final_ms[k] is the reducing kernel alone */
 } sb_solver_report;
 
 SB_API int sb_cg_solve(sb_ctx* ctx, const sb_op* op, double* x, const double* b,

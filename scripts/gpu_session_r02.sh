@@ -192,6 +192,27 @@ PY
         > "$out/ab_n${N}_axis119_slab.jsonl" 2> "$out/ab_n${N}_axis119_slab.log"
     grep "^\[ab\]" "$out/ab_n${N}_axis119_slab.log"
     ;;
+  h3)
+    # eight GPUs, second session: lazy halo push against the best of the first session, METIS and slab partitions; the
+    # bit-exactness worker at 8 ranks (it runs the lazy variants too); then config 4 at full size, configs 3 and 5
+    N=${2:-8}
+    timeout 300 $TR --nproc-per-node $N --master-port 29550 scripts/scale_ab.py --axis 119 --out "$out/ab_n${N}_axis119.json" \
+        --variants stream+noack,lazy+stream,lazy+stream+pdlfa,lazy+stream+red,lazy,persistent > "$out/ab_n${N}_axis119.jsonl" 2> "$out/ab_n${N}_axis119.log"
+    grep "^\[ab\]" "$out/ab_n${N}_axis119.log"
+    timeout 240 $TR --nproc-per-node $N --master-port 29552 scripts/scale_ab.py --axis 119 --partition slab --out "$out/ab_n${N}_axis119_slab.json" \
+        --variants stream,lazy+stream > "$out/ab_n${N}_axis119_slab.jsonl" 2> "$out/ab_n${N}_axis119_slab.log"
+    grep "^\[ab\]" "$out/ab_n${N}_axis119_slab.log"
+    export SB_SPIN_TIMEOUT_S=60
+    ( time timeout 200 $TR --nproc-per-node $N --master-port 29555 tests/_dist_worker.py p2p ) > "$out/dist_worker_p2p_n$N.log" 2>&1; tail -4 "$out/dist_worker_p2p_n$N.log"
+    unset SB_SPIN_TIMEOUT_S
+    timeout 300 $TR --nproc-per-node $N --master-port 29556 scripts/config4_projection.py --axis 368 --lattice --steps 10 > "$out/config4_368_n${N}_lattice.json" 2> "$out/config4.err"
+    tail -c 1500 "$out/config4_368_n${N}_lattice.json"; tail -3 "$out/config4.err"
+    timeout 300 $TR --nproc-per-node $N --master-port 29558 scripts/config3_gmres.py --axis 119 --steps 100 > "$out/config3_gmres_fused_10M_n$N.json" 2> "$out/config3.err"
+    timeout 300 $TR --nproc-per-node 4 --master-port 29557 scripts/config3_gmres.py --axis 119 --steps 100 > "$out/config3_gmres_fused_10M_n4.json" 2>> "$out/config3.err"
+    tail -c 300 "$out/config3_gmres_fused_10M_n4.json"; tail -c 300 "$out/config3_gmres_fused_10M_n$N.json"; tail -3 "$out/config3.err"
+    timeout 400 $TR --nproc-per-node $N --master-port 29559 scripts/apply_sweep.py --cells hexlat --sizes 1e7,1e8,2e8 --out "$out/apply_sweep_hexlat_n$N.json" > "$out/config5_n$N.log" 2>&1
+    tail -4 "$out/config5_n$N.log"
+    ;;
   h2)
     # eight GPUs, second call: config 4 at full size, configs 3 and 5
     N=${2:-8}

@@ -346,6 +346,7 @@ class _FusedSolver:
     kernel_ms: tuple = ()
     wait_ms: tuple = ()
     ar_wait_ms: tuple = ()
+    final_ms: tuple = ()
     launches: int = 0
     schedule_used: int = 0
     _entry = ""
@@ -373,6 +374,7 @@ class _FusedSolver:
         self.kernel_ms = tuple(rep.kernel_ms[k] for k in range(rep.n_kernel_slots))
         self.wait_ms = tuple(rep.wait_ms[k] for k in range(rep.n_kernel_slots))
         self.ar_wait_ms = tuple(rep.ar_wait_ms[k] for k in range(rep.n_kernel_slots))
+        self.final_ms = tuple(rep.final_ms[k] for k in range(rep.n_kernel_slots))
         self.schedule_used = int(rep.schedule)
         self.timeline = tl[:min(int(self.timeline_iters), self.iteration)] if rep.schedule == capi.SCHEDULE_PERSISTENT else tl[:0]
         return bool(rep.converged)

@@ -99,7 +99,8 @@ class SolverReport(C.Structure):
                 ("abs_err", C.c_double), ("rel_err", C.c_double), ("n_hist", C.c_int64),
                 ("n_trace", C.c_int64), ("solve_ms", C.c_double), ("iter_ms", C.c_double),
                 ("launches", C.c_int64), ("n_kernel_slots", C.c_int32), ("kernel_ms", C.c_double * 8),
-                ("schedule", C.c_int32), ("wait_ms", C.c_double * 8), ("ar_wait_ms", C.c_double * 8)]
+                ("schedule", C.c_int32), ("wait_ms", C.c_double * 8), ("ar_wait_ms", C.c_double * 8),
+                ("final_ms", C.c_double * 8)]
 
 
 # name -> (restype, argtypes); the keys are exactly the SB_API symbols of include/stormb200.h

@@ -150,6 +150,7 @@ struct sb_ctx {
   double* d_trace = nullptr;
   int64_t trace_cap = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t>* prof_mid = nullptr; // profiled solve: launch_final records an event in front of every final stage
   // fused GMRES (sb_gmres.cu): cached Krylov basis, device scalars (H records, betas), pinned mirror
   std::vector<double*> basis;
   size_t basis_n = 0;

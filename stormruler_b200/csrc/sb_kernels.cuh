@@ -199,6 +199,12 @@ inline int launch_final(sb_ctx* ctx, int64_t n, const Final& fin, const int* don
     ctx->launches += 2;
     return SB_OK;
   }
+  if (ctx->prof_mid != nullptr) { // profiled solve: where the reducing kernel ends and its final stage begins
+    cudaEvent_t e;
+    SB_CUDA(cudaEventCreate(&e));
+    ctx->prof_mid->push_back(e); // owned by the solve's guard from here on
+    SB_CUDA(cudaEventRecord(e, ctx->stream));
+  }
   PdlScope pdl_scope(ctx, pdl);
   SB_CUDA(launch_kernel(ctx, final_reduce_kernel<ND, Final>, 1, kThreads, 0, num_tiles(n), red, fin, ctx->comm, bump, done, ar_wait_ns));
   ctx->launches++;

@@ -332,7 +332,11 @@ struct SolveGuard {
     events.push_back(*e);
     return SB_OK;
   }
+  std::vector<cudaEvent_t> mid_events; // profiled solve: one in front of every one-CTA final stage
+  sb_ctx* ctx = nullptr;
   ~SolveGuard() {
+    if (ctx != nullptr) ctx->prof_mid = nullptr;
+    for (cudaEvent_t e : mid_events) cudaEventDestroy(e);
     for (cudaEvent_t e : events) cudaEventDestroy(e);
     if (graph_exec != nullptr) cudaGraphExecDestroy(graph_exec);
     if (graph != nullptr) cudaGraphDestroy(graph);
@@ -489,7 +493,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
           ctx->launches += launches_per_iter * its_per_graph;
           it += its_per_graph;
         } else {
-          if (profile) S.prof = &prof_events;
+          if (profile) S.prof = &prof_events, guard.ctx = ctx, ctx->prof_mid = &guard.mid_events;
           SB_TRY(S.iterate(kind));
           ++it;
         }
@@ -505,7 +509,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
       }
       slot ^= 1;
     }
-    S.prof = nullptr;
+    S.prof = nullptr, ctx->prof_mid = nullptr;
     if (S.folded) SB_TRY(S.finish_folded(kind));
   }
   SB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -521,7 +525,7 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   report->n_kernel_slots = persistent ? 0 : per_iter;
   report->schedule = persistent ? SB_SCHEDULE_PERSISTENT : (S.folded ? SB_SCHEDULE_FOLDED : SB_SCHEDULE_STEPWISE);
   for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->kernel_ms[k] = 0.0;
-  for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->wait_ms[k] = report->ar_wait_ms[k] = 0.0;
+  for (int k = 0; k < SB_MAX_KERNEL_SLOTS; ++k) report->wait_ms[k] = report->ar_wait_ms[k] = report->final_ms[k] = 0.0;
   if (profile && !persistent) {
     // events come in groups of per_iter + 1 per iteration
     const size_t group = (size_t) per_iter + 1;
@@ -531,6 +535,18 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
         cudaEventElapsedTime(&dt, prof_events[g + k], prof_events[g + k + 1]);
         report->kernel_ms[k] += dt;
       }
+    // one event per final stage: CG slots 0, 1; BiCGStab slots 1, 3, 4 (none when the reductions end in-kernel)
+    const int cg_slots[2] = {0, 1}, bi_slots[3] = {1, 3, 4};
+    const int nf = kind == Kind::Cg ? 2 : 3;
+    const int* fslot = kind == Kind::Cg ? cg_slots : bi_slots;
+    const size_t iters_profiled = (prof_events.size() - prof_first) / group;
+    if (guard.mid_events.size() == iters_profiled * (size_t) nf)
+      for (size_t i = 0; i < iters_profiled; ++i)
+        for (int j = 0; j < nf; ++j) {
+          float dt = 0.f;
+          cudaEventElapsedTime(&dt, guard.mid_events[i * nf + j], prof_events[prof_first + i * group + fslot[j] + 1]);
+          report->final_ms[fslot[j]] += dt;
+        }
     if (tl_words > 0) { // longest in-kernel wait per launch, summed per slot
       std::vector<unsigned long long> tl((size_t) tl_words);
       SB_CUDA(cudaMemcpy(tl.data(), ctx->d_timeline, sizeof(unsigned long long) * tl_words, cudaMemcpyDeviceToHost));
