@@ -148,6 +148,27 @@ PY
     python scripts/solver_sweep.py --solvers cgs,bicgstab,tfqmr --out "$out/solver_sweep_cgs.json" > "$out/solver_sweep_cgs.log" 2>&1
     tail -4 "$out/solver_sweep_cgs.log"
     ;;
+  k)
+    # one GPU, the round's record: the whole GPU suite, smoke, the bench line, the ncu launch list of the same command,
+    # one `ncu --set full` capture of the apply kernels, time to solution against the reference CPU solve, every solver
+    export SB_SPIN_TIMEOUT_S=30
+    timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -30 > "$out/pytest_gpu.log"; tail -5 "$out/pytest_gpu.log"
+    unset SB_SPIN_TIMEOUT_S
+    python -c "import __graft_entry__ as g; g.smoke()" > "$out/smoke.log" 2>&1; tail -4 "$out/smoke.log"
+    python bench.py --steps 200 --warmup 20 > "$out/bench_n1.json" 2> "$out/bench_n1.err"; tail -c 600 "$out/bench_n1.json"; tail -2 "$out/bench_n1.err"
+    python bench.py --impl reference --steps 20 --warmup 3 > "$out/bench_reference_arm.json" 2> "$out/bench_reference_arm.err"; tail -c 400 "$out/bench_reference_arm.json"
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/launches_bench.csv" \
+        python bench.py --steps 2 --warmup 1 --no-cpu-baseline > "$out/ncu_launches.log" 2>&1
+    python scripts/summarize_ncu.py launches "$out/launches_bench.csv" "$out/launches_bench" "bench.py --steps 2 --warmup 1 (BiCGStab + CG legs, 10.1 M tets, stepwise schedule)" > /dev/null 2>&1
+    head -16 "$out/launches_bench_summary.txt"
+    ncu --set full --clock-control none --import-source on -k regex:apply_kernel_tma -c 8 -o "$out/apply_full" \
+        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --single-solver > "$out/ncu_full.log" 2>&1
+    ls -la "$out"/apply_full* 2>&1 | tail -2
+    timeout 900 python scripts/time_to_solution.py --cpu --out "$out/time_to_solution_10M.json" > "$out/tts.jsonl" 2> "$out/tts.err"; tail -3 "$out/tts.err"; cut -c1-400 "$out/tts.jsonl"
+    python scripts/solver_sweep.py --solvers cg,bicgstab,cgs,bicgstabl,tfqmr,tfqmr1,idrs,gmres,fgmres,richardson,grouped_idrs,grouped_bicgstabl \
+        --out "$out/solver_sweep_default.json" > "$out/solver_sweep.log" 2>&1
+    tail -3 "$out/solver_sweep.log" | cut -c1-300
+    ;;
   g)
     # two GPUs: the distributed tests with a GPU per rank, the tuning A/B on the strong-scaling problem, the bench line,
     # config 3 and config 5 at N = 2
@@ -212,6 +233,23 @@ PY
     tail -c 300 "$out/config3_gmres_fused_10M_n4.json"; tail -c 300 "$out/config3_gmres_fused_10M_n$N.json"; tail -3 "$out/config3.err"
     timeout 400 $TR --nproc-per-node $N --master-port 29559 scripts/apply_sweep.py --cells hexlat --sizes 1e7,1e8,2e8 --out "$out/apply_sweep_hexlat_n$N.json" > "$out/config5_n$N.log" 2>&1
     tail -4 "$out/config5_n$N.log"
+    ;;
+  h4)
+    # eight GPUs, third session: lazy push with the batched forwarding loop; the communication-free floor of the same
+    # partition (SB_DEBUG=6: no halo exchange, rank-local sums -- numbers only, the iterates are meaningless); N = 4
+    N=${2:-8}
+    timeout 300 $TR --nproc-per-node $N --master-port 29550 scripts/scale_ab.py --axis 119 --out "$out/ab_n${N}_axis119.json" \
+        --variants stream+noack,lazy+stream > "$out/ab_n${N}_axis119.jsonl" 2> "$out/ab_n${N}_axis119.log"
+    grep "^\[ab\]" "$out/ab_n${N}_axis119.log"
+    SB_DEBUG=6 timeout 300 $TR --nproc-per-node $N --master-port 29551 scripts/scale_ab.py --axis 119 --out "$out/ab_n${N}_axis119_nocomm.json" \
+        --variants off,stream > "$out/ab_n${N}_axis119_nocomm.jsonl" 2> "$out/ab_n${N}_axis119_nocomm.log"
+    grep "^\[ab\]" "$out/ab_n${N}_axis119_nocomm.log"
+    timeout 240 $TR --nproc-per-node $N --master-port 29552 scripts/scale_ab.py --axis 119 --partition slab --out "$out/ab_n${N}_axis119_slab.json" \
+        --variants lazy+stream > "$out/ab_n${N}_axis119_slab.jsonl" 2> "$out/ab_n${N}_axis119_slab.log"
+    grep "^\[ab\]" "$out/ab_n${N}_axis119_slab.log"
+    timeout 240 $TR --nproc-per-node 4 --master-port 29553 scripts/scale_ab.py --axis 119 --out "$out/ab_n4_axis119.json" \
+        --variants stream,lazy+stream > "$out/ab_n4_axis119.jsonl" 2> "$out/ab_n4_axis119.log"
+    grep "^\[ab\]" "$out/ab_n4_axis119.log"
     ;;
   h2)
     # eight GPUs, second call: config 4 at full size, configs 3 and 5

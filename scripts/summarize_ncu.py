@@ -2,7 +2,7 @@
 """Turn the ncu artefacts a gpurun call brought back into the tracked summaries under profiles/.
 
     python scripts/summarize_ncu.py launches gpurun_out/launches_v3.csv profiles/r01_launches_bench_v3 "<note>"
-    python scripts/summarize_ncu.py full gpurun_out/apply_v3_full.ncu-rep profiles/r01_apply_v3_full "<note>"
+    python scripts/summarize_ncu.py full gpurun_out/apply_v3_full.ncu-rep profiles/r01_apply_v3_full "<note>" [tet:119]
 
 `launches`: copies the per-launch csv (gpu__time_duration.sum, --clock-control none) and writes a
 per-kernel share table. `full`: extracts the metrics the roofline argument uses from a
@@ -71,11 +71,18 @@ def full(src, dst, note):
         traffic.append({"kernel": r[i_name][:120], "dram_bytes": rd + wr,
                         "duration_us": float(vals["gpu__time_duration.sum"][0].replace(",", ""))})
     open(dst + "_raw.txt", "w").write("\n".join(lines) + "\n")
-    mean = sum(t["dram_bytes"] for t in traffic) / len(traffic)
-    json.dump({"dram_bytes_per_launch": mean, "launches": traffic, "source": os.path.basename(dst) + "_raw.txt",
-               "note": note}, open(os.path.join(os.path.dirname(dst), "apply_traffic.json"), "w"), indent=1)
+    # per apply variant (the epilogue is part of the kernel name): what bench.py reports as roofline.traffic
+    variants = {}
+    for epi in ("EpiUY", "EpiYYandYX", "EpiXY", "NoEpi", "EpiResidual"):
+        v = [t["dram_bytes"] for t in traffic if "apply_kernel_tma" in t["kernel"] and epi + ">" in t["kernel"]]
+        if v:
+            variants[epi] = sum(v) / len(v)
+    cell, axis = (sys.argv[5].split(":") + ["119"])[:2] if len(sys.argv) > 5 else ("tet", "119")
+    json.dump({"workload": {"cell": cell, "axis": int(axis)}, "variants": variants, "source": os.path.basename(dst) + "_raw.txt",
+               "note": note + "; dram__bytes_read.sum + dram__bytes_write.sum per launch", "launches": traffic},
+              open(os.path.join(os.path.dirname(dst), "apply_traffic.json"), "w"), indent=1)
     print("\n".join(lines))
-    print("mean dram bytes per launch:", mean)
+    print("dram bytes per launch, per apply variant:", variants)
 
 
 if __name__ == "__main__":

@@ -173,12 +173,29 @@ __device__ __forceinline__ void halo_push_tile(const CommDev& comm, const HaloDe
   CommCtrl* me = comm.ctrl(comm.rank);
   const int q = (int) (tile - halo.first_boundary_tile);
   const int32_t beg = halo.push_ptr[q], end = halo.push_ptr[q + 1];
-  for (int32_t i = beg + (int32_t) threadIdx.x; i < end; i += kThreads) {
-    const int2 en = halo.push_entry[i];
-    const int k = (int) ((uint32_t) en.x >> 28);
-    const double v = __ldcg(y + (en.x & 0x0fffffff));
-    double* dst = reinterpret_cast<double*>(comm.base[halo.nbr_rank[k]] + y_off) + en.y;
-    *dst = v;
+  // four entries per thread and pass, every load of a pass issued before its first store: a boundary tile forwards
+  // ~2 000 values, and one entry at a time (entry -> value -> store, ~1.5 us of dependent latency each) kept the
+  // pushing CTAs alive 6 us beyond the tile's own work (direction kernel 10.8 -> 16.7 us at 8 GPUs,
+  // profiles/r02_ab_n8_10M_lazy.txt)
+  constexpr int kPush = 4;
+  for (int32_t i0 = beg + (int32_t) threadIdx.x; i0 < end; i0 += kPush * kThreads) {
+    int2 en[kPush];
+    double v[kPush];
+#pragma unroll
+    for (int u = 0; u < kPush; ++u) {
+      const int32_t i = i0 + u * kThreads;
+      en[u] = i < end ? halo.push_entry[i] : make_int2(0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < kPush; ++u) v[u] = (i0 + u * kThreads < end) ? __ldcg(y + (en[u].x & 0x0fffffff)) : 0.0;
+#pragma unroll
+    for (int u = 0; u < kPush; ++u) {
+      if (i0 + u * kThreads < end) {
+        const int k = (int) ((uint32_t) en[u].x >> 28);
+        double* dst = reinterpret_cast<double*>(comm.base[halo.nbr_rank[k]] + y_off) + en[u].y;
+        *dst = v[u];
+      }
+    }
   }
   if (lazy) return;
   __threadfence_system(); // my peer stores are performed before the ticket below is taken
