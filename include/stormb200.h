@@ -408,8 +408,10 @@ typedef struct sb_solver_opts {
                              the all-reduce included); [11+b] reducing barriers: ns the CTA that ran the reduction
                              waited for the other ranks' sums after posting its own; [16+k] longest wait of any
                              warp of this rank for a neighbour's halo values in apply k */
-  uint32_t tuning;        /* stepwise schedule: SB_TUNE_* bits, 0 = the defaults (what SB_TUNE_DEFAULT names). Results
-                             are bit-identical whatever the bits; they exist so that one process can A/B them */
+  uint32_t tuning;        /* stepwise schedule: SB_TUNE_* bits, 0 = the library's choice (STREAM_OPERATOR | NO_ACK, plus
+                             PUSH_ON_PRODUCE | PUSH_LAZY when a rank's apply kernel is at most ~two waves of tiles:
+                             DESIGN.md 5d / 6). Results are bit-identical whatever the bits; they exist so that one
+                             process can A/B them */
 } sb_solver_opts;
 
 /* Tuning bits of the stepwise schedule (sb_solver_opts::tuning; measurements: DESIGN.md 6):
@@ -420,7 +422,8 @@ typedef struct sb_solver_opts {
  *   NO_ACK           multi-GPU: the in-apply halo push skips the ack round (valid inside the fused solvers: between two
  *                    applies that write the same halo tail there is always an all-reduce);
  *   STREAM_OPERATOR  the apply kernel's bulk copies of the operator slices carry an L2 evict-first policy, so that a
- *                    rank whose vectors fit the 126 MB L2 (<= ~1.3 M cells) keeps them there between the kernels;
+ *                    rank whose vectors fit the 126 MB L2 (<= ~1.3 M cells) keeps them there between the kernels
+ *                    (outside the fused solvers -- sb_apply, sb_gmres_solve, the generic path -- it is always on);
  *   PDL_FINAL        the one-CTA final stages are launched with programmatic stream serialization (resident while
  *                    the producer drains); PDL_AFTER_FINAL: so are the kernels that follow a final stage (resident,
  *                    operator slices prefetched, while the one-CTA stage runs on an otherwise idle machine);

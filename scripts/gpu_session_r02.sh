@@ -168,6 +168,16 @@ PY
     python scripts/solver_sweep.py --solvers cg,bicgstab,cgs,bicgstabl,tfqmr,tfqmr1,idrs,gmres,fgmres,richardson,grouped_idrs,grouped_bicgstabl \
         --out "$out/solver_sweep_default.json" > "$out/solver_sweep.log" 2>&1
     tail -3 "$out/solver_sweep.log" | cut -c1-300
+    # the strong-scaling reference point of a 30 M-cell problem (its 8-GPU leg: block h5)
+    python bench.py --axis 171 --steps 100 --warmup 10 --no-cpu-baseline > "$out/bench_n1_30M.json" 2> "$out/bench_n1_30M.err"; tail -c 300 "$out/bench_n1_30M.json"
+    ;;
+  h5)
+    # eight GPUs: the bench line with the library's defaults (what the driver runs), then the same at 30 M cells
+    N=${2:-8}
+    timeout 300 $TR --nproc-per-node $N --master-port 29561 bench.py --gpus $N --steps 200 --warmup 20 > "$out/bench_n${N}_bicgstab.json" 2> "$out/bench_n$N.err"
+    tail -c 500 "$out/bench_n${N}_bicgstab.json"; tail -2 "$out/bench_n$N.err"
+    timeout 400 $TR --nproc-per-node $N --master-port 29562 bench.py --gpus $N --axis 171 --steps 200 --warmup 20 > "$out/bench_n${N}_bicgstab_30M.json" 2> "$out/bench_n${N}_30M.err"
+    tail -c 500 "$out/bench_n${N}_bicgstab_30M.json"; tail -2 "$out/bench_n${N}_30M.err"
     ;;
   g)
     # two GPUs: the distributed tests with a GPU per rank, the tuning A/B on the strong-scaling problem, the bench line,

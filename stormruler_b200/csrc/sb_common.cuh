@@ -178,6 +178,8 @@ struct sb_ctx {
   int64_t sendbuf_cap = 0;
   // experiments only (SB_DEBUG env): bit1 = skip the halo exchange, bit2 = skip the cross-rank all-reduce
   // (results are wrong on purpose; used to attribute multi-GPU time, never set in tests or bench lines)
+  int stream_operator = 1; // apply kernels fetch the operator slices with an L2 evict-first policy (SB_TUNE_STREAM_OPERATOR;
+                           // a fused solve sets it from its tuning bits and restores it)
   int debug = 0;
   // persistent whole-solve kernel (sb_mega.cu): grid barrier / mailbox block, timeline scratch
   struct sb::MegaCtrl* d_mega = nullptr;

@@ -552,7 +552,7 @@ template<int ND, bool RESID, class Epi, class Final>
 int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const Epi& epi, const Final& fin,
                  const int* done, const ApplyOpts& ao = ApplyOpts{}) {
   OpDev d = ao.per_call != nullptr ? *ao.per_call : op->d;
-  d.stream_hint = (ctx->tuning & SB_TUNE_STREAM_OPERATOR) ? 1 : 0;
+  d.stream_hint = ctx->stream_operator;
   if constexpr (ND > 0) {
     SB_TRY(ensure_red_scratch(ctx, d.n));
   }

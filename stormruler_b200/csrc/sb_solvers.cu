@@ -123,10 +123,22 @@ static int check_vector(sb_ctx* ctx, const double* v, int64_t n, const char* wha
   return SB_ERR_INVALID;
 }
 
-// What sb_solver_opts::tuning == 0 selects (measured on 1, 2 and 8 GPUs).
-// STREAM_OPERATOR: 1 GPU 1.23 M / 2.5 M / 10.1 M cells BiCGStab +9 % / +10 % / +-0, CG +5 % / +15 % / +-0; 2 GPUs, 10.1 M cells
-// +4 % / +7 % (profiles/r02_ab_*). Every other bit measured slower or equal on one and two GPUs.
-constexpr uint32_t kDefaultTuning = SB_TUNE_STREAM_OPERATOR;
+// What sb_solver_opts::tuning == 0 selects (profiles/r02_ab_*):
+//  * STREAM_OPERATOR always: one GPU, 1.23 M / 2.5 M / 10.1 M cells: BiCGStab +9 % / +10 % / +-0, CG +5 % / +15 % / +-0;
+//    10.1 M cells on 2 / 4 / 8 GPUs: BiCGStab +4 % / +17 % / +12 %;
+//  * NO_ACK always (it only concerns the distributed apply inside a fused solve): 8 GPUs +5 %, 2 GPUs +-0;
+//  * PUSH_ON_PRODUCE | PUSH_LAZY when the rank's apply kernel is at most ~two waves of tiles: there the pack chain
+//    of the apply (stores, fence, ticket, fence, flags) lands 7-10 us after the boundary tiles need it (8 GPUs, 617
+//    tiles per rank: +10 % on top of the two above), while with several waves in front of the boundary tiles it is
+//    hidden anyway and the pushing producers only cost (4 GPUs, 1 235 tiles: 7 138 against 7 171 it/s).
+// Every other bit (eager push, in-kernel reducer, programmatic dependent launch) measured slower or equal everywhere.
+constexpr int64_t kLazyPushMaxTiles = 1024;
+static uint32_t default_tuning(const sb_ctx* ctx, const sb_op* op) {
+  uint32_t t = SB_TUNE_STREAM_OPERATOR | SB_TUNE_NO_ACK;
+  if (ctx->comm.world > 1 && ctx->comm.mode == SB_COMM_P2P && op->distributed && num_tiles(op->d.n) <= kLazyPushMaxTiles)
+    t |= SB_TUNE_PUSH_ON_PRODUCE | SB_TUNE_PUSH_LAZY;
+  return t;
+}
 
 struct Solve {
   sb_ctx* ctx;
@@ -400,12 +412,12 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
   }
   S.folded = opts->schedule == SB_SCHEDULE_FOLDED;
   // tuning of the stepwise schedule (include/stormb200.h: SB_TUNE_*); 0 = the defaults
-  const uint32_t tuning = opts->tuning == 0 ? kDefaultTuning : (opts->tuning & ~SB_TUNE_OFF);
+  const uint32_t tuning = opts->tuning == 0 ? default_tuning(ctx, op) : (opts->tuning & ~SB_TUNE_OFF);
   struct TuningScope { // the launch helpers read the bits from the context while this solve is in progress
     sb_ctx* c;
-    ~TuningScope() { c->tuning = 0; }
+    ~TuningScope() { c->tuning = 0, c->stream_operator = 1; }
   } tuning_scope{ctx};
-  ctx->tuning = tuning;
+  ctx->tuning = tuning, ctx->stream_operator = (tuning & SB_TUNE_STREAM_OPERATOR) ? 1 : 0;
   const bool p2p = ctx->comm.world > 1 && ctx->comm.mode == SB_COMM_P2P && op->distributed && !(ctx->debug & 2);
   S.push = p2p && (tuning & SB_TUNE_PUSH_ON_PRODUCE) && op->halo.n_nbr > 0 && op->halo.push_ptr != nullptr && !S.folded;
   S.no_ack = p2p && (tuning & SB_TUNE_NO_ACK);
