@@ -171,13 +171,27 @@ PY
     # the strong-scaling reference point of a 30 M-cell problem (its 8-GPU leg: block h5)
     python bench.py --axis 171 --steps 100 --warmup 10 --no-cpu-baseline > "$out/bench_n1_30M.json" 2> "$out/bench_n1_30M.err"; tail -c 300 "$out/bench_n1_30M.json"
     ;;
+  k2)
+    # one GPU: the files of block k once more (that call's directory exceeded the transfer limit because of a 73 MB ncu
+    # report and nothing came back): the bench line, a SMALL `ncu --set full` capture of the two BiCGStab apply kernels
+    # (raw page exported on the box, the report itself dropped when it is large), the single-GPU point of the 20 M-cell
+    # strong-scaling pair
+    python bench.py --steps 200 --warmup 20 > "$out/bench_n1.json" 2> "$out/bench_n1.err"; tail -c 300 "$out/bench_n1.json"; tail -2 "$out/bench_n1.err"
+    ncu --set full --clock-control none -k regex:apply_kernel_tma --launch-skip 2 -c 4 -o "$out/apply_full" \
+        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --single-solver > "$out/ncu_full.log" 2>&1
+    ncu -i "$out/apply_full.ncu-rep" --page raw --csv > "$out/apply_full_raw.csv" 2> /dev/null
+    ls -la "$out"/apply_full* | tail -3
+    if [ "$(stat -c %s "$out/apply_full.ncu-rep" 2>/dev/null || echo 0)" -gt 30000000 ]; then rm -f "$out/apply_full.ncu-rep"; fi
+    timeout 300 python scripts/scale_ab.py --axis 150 --variants default,off --no-profile --out "$out/ab_n1_axis150.json" > "$out/ab_n1_axis150.jsonl" 2> "$out/ab_n1_axis150.log"
+    grep "^\[ab\]" "$out/ab_n1_axis150.log"
+    du -sh "$out"
+    ;;
   h5)
-    # eight GPUs: the bench line with the library's defaults (what the driver runs), then the same at 30 M cells
+    # eight GPUs: the 20 M-cell strong-scaling point with the library's defaults (2.53 M cells per rank)
     N=${2:-8}
-    timeout 300 $TR --nproc-per-node $N --master-port 29561 bench.py --gpus $N --steps 200 --warmup 20 > "$out/bench_n${N}_bicgstab.json" 2> "$out/bench_n$N.err"
-    tail -c 500 "$out/bench_n${N}_bicgstab.json"; tail -2 "$out/bench_n$N.err"
-    timeout 400 $TR --nproc-per-node $N --master-port 29562 bench.py --gpus $N --axis 171 --steps 200 --warmup 20 > "$out/bench_n${N}_bicgstab_30M.json" 2> "$out/bench_n${N}_30M.err"
-    tail -c 500 "$out/bench_n${N}_bicgstab_30M.json"; tail -2 "$out/bench_n${N}_30M.err"
+    timeout 400 $TR --nproc-per-node $N --master-port 29561 scripts/scale_ab.py --axis 150 --variants default --no-profile \
+        --out "$out/ab_n${N}_axis150.json" > "$out/ab_n${N}_axis150.jsonl" 2> "$out/ab_n${N}_axis150.log"
+    grep "^\[ab\]" "$out/ab_n${N}_axis150.log"
     ;;
   g)
     # two GPUs: the distributed tests with a GPU per rank, the tuning A/B on the strong-scaling problem, the bench line,

@@ -114,6 +114,13 @@ def test_reference_2d_meshes_three_ctas(ctx, square_nb, solver):
         assert np.array_equal(s2.history, s.history) and np.array_equal(s2.trace, s.trace) and np.array_equal(x2, x)
         if kw.get("profile"):
             assert len(s2.kernel_ms) in (3, 5) and min(s2.kernel_ms) > 0 and min(s2.wait_ms) >= 0.0
+            # the one-CTA final stage behind every reducing kernel has an event of its own: part of its slot, never all
+            reducing = (0, 1) if solver == "cg" else (1, 3, 4)
+            for k in range(len(s2.kernel_ms)):
+                if k in reducing:
+                    assert 0.0 < s2.final_ms[k] < s2.kernel_ms[k], (k, s2.final_ms, s2.kernel_ms)
+                else:
+                    assert s2.final_ms[k] == 0.0
 
 
 def test_stopping_rules_persistent(ctx, square_nb):
