@@ -418,6 +418,23 @@ def run_own_arm(args):
             parity[label] = history_parity(sg.history, ref_hist)
             del o, xg
 
+    # the other target solver's history against the reference too (a shorter sample: CG's whole history is expected to
+    # stay within the bar, BiCGStab's is not -- SURVEY.md F8)
+    parity_other = None
+    if not args.no_cpu_baseline and other is not None:
+        try:
+            o_solver = other["solver"]
+            _, kind_o, iters_o, _, ref_hist_o = cpu_reference_rate(mesh, x_star, o_solver, budget_s=args.cpu_budget / 4)
+            OSolver = sb.BiCgStabSolver if o_solver == "bicgstab" else sb.CgSolver
+            sg = OSolver(num_iterations=iters_o, absolute_error_tolerance=0.0, relative_error_tolerance=0.0, record=True)
+            xg = ctx.zeros(n)
+            sg.solve(xg, b, op)
+            parity_other = {"solver": o_solver, "against": f"{kind_o}: first {iters_o} iterations of the same problem, sequential sums",
+                            "measured_path_coef_rows": history_parity(sg.history, ref_hist_o)}
+            del xg
+        except Exception as e:  # noqa: BLE001 -- an extra, never allowed to take the bench line down
+            parity_other = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
     cpu_all = None
     if not args.no_cpu_baseline:
         try:   # an extra, never allowed to take the bench line down
@@ -453,6 +470,7 @@ def run_own_arm(args):
         "cpu_baseline": cpu,
         "cpu_baseline_all_cores": cpu_all,
         "parity": parity,
+        "parity_other_solver": parity_other,
         "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": 16 * n / args.steps,
                 "d2h_bytes_per_step": 8 * n / args.steps,
                 "note": f"one sb_solve_host call = H2D(x0,b) + init + {args.steps} iterations + D2H(x), pinned host buffers"},

@@ -193,6 +193,22 @@ PY
         --out "$out/ab_n${N}_axis150.json" > "$out/ab_n${N}_axis150.jsonl" 2> "$out/ab_n${N}_axis150.log"
     grep "^\[ab\]" "$out/ab_n${N}_axis150.log"
     ;;
+  ab)
+    # one GPU: the TMA apply kernel compiled for 72 registers (__launch_bounds__(256, 3), the tree's build) against 64
+    # registers (__launch_bounds__(256, 4): what ptxas chose in round 1), same source otherwise (ab/libstormb200_regs64.so,
+    # built with -DSB_TMA_REG_CTAS3=4); two problem sizes, slot times included
+    for ax in 119 59; do
+      timeout 300 python scripts/scale_ab.py --axis $ax --variants default,off --out "$out/ab_regs72_axis$ax.json" > "$out/ab_regs72_axis$ax.jsonl" 2> "$out/ab_regs72_axis$ax.log"
+      echo "72 registers, axis $ax"; grep "^\[ab\]" "$out/ab_regs72_axis$ax.log"
+    done
+    cp stormruler_b200/libstormb200.so /tmp/libstormb200_tree.so
+    cp ab/libstormb200_regs64.so stormruler_b200/libstormb200.so
+    for ax in 119 59; do
+      timeout 300 python scripts/scale_ab.py --axis $ax --variants default,off --out "$out/ab_regs64_axis$ax.json" > "$out/ab_regs64_axis$ax.jsonl" 2> "$out/ab_regs64_axis$ax.log"
+      echo "64 registers, axis $ax"; grep "^\[ab\]" "$out/ab_regs64_axis$ax.log"
+    done
+    cp /tmp/libstormb200_tree.so stormruler_b200/libstormb200.so
+    ;;
   g)
     # two GPUs: the distributed tests with a GPU per rank, the tuning A/B on the strong-scaling problem, the bench line,
     # config 3 and config 5 at N = 2

@@ -53,7 +53,10 @@ def launches(src, dst, note):
 
 
 def full(src, dst, note):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # src: the report, or its raw page already exported on the GPU box (`ncu -i rep --page raw --csv > raw.csv`: the
+    # report itself can exceed what a gpurun call brings back)
+    out = open(src).read() if src.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     i_name = hdr.index("Kernel Name")

@@ -179,7 +179,10 @@ struct StageLayout {
   // ptxas through __launch_bounds__ so that it uses the registers that occupancy leaves free anyway (85 at three CTAs)
   // instead of spilling down to 64
   static constexpr int fit = (227 * 1024) / (cta_bytes + 2048);
-  static constexpr int min_ctas = fit >= 3 ? 3 : (fit >= 1 ? fit : 1);
+#ifndef SB_TMA_REG_CTAS3 // A/B hook (scripts/gpu_session_r02.sh ab): the register budget when three CTAs fit
+#define SB_TMA_REG_CTAS3 3
+#endif
+  static constexpr int min_ctas = fit >= 3 ? SB_TMA_REG_CTAS3 : (fit >= 1 ? fit : 1);
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
