@@ -209,6 +209,27 @@ PY
     done
     cp /tmp/libstormb200_tree.so stormruler_b200/libstormb200.so
     ;;
+  ab2)
+    # one GPU: the tree's library against A/B builds of the same source (ab/libstormb200_<X>.so; C = the TMA apply without
+    # the out-of-line reducer call, D = C without the policy branch in the refill path), 10.1 M cells, slot times included
+    cp stormruler_b200/libstormb200.so /tmp/libstormb200_tree.so
+    for v in tree C D tree; do
+      if [ $v = tree ]; then cp /tmp/libstormb200_tree.so stormruler_b200/libstormb200.so; else cp ab/libstormb200_$v.so stormruler_b200/libstormb200.so; fi
+      timeout 300 python scripts/scale_ab.py --axis 119 --variants default,off --out "$out/ab_lib_${v}_axis119.json" > "$out/ab_lib_${v}.jsonl" 2> "$out/ab_lib_$v.log"
+      echo "library $v"; grep "^\[ab\]" "$out/ab_lib_$v.log"
+    done
+    cp /tmp/libstormb200_tree.so stormruler_b200/libstormb200.so
+    ;;
+  k3)
+    # one GPU, after the reducer role left the apply kernels and the default element-wise kernels: the whole GPU suite
+    # (the in-kernel-reducer variants run in the mega and the two-ranks-on-one-GPU tests), the bench line, a quick A/B
+    export SB_SPIN_TIMEOUT_S=30
+    timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 > "$out/pytest_gpu.log"; tail -5 "$out/pytest_gpu.log"
+    unset SB_SPIN_TIMEOUT_S
+    python bench.py --steps 200 --warmup 20 > "$out/bench_n1.json" 2> "$out/bench_n1.err"; tail -c 300 "$out/bench_n1.json"; tail -2 "$out/bench_n1.err"
+    timeout 300 python scripts/scale_ab.py --axis 59 --variants default,off,red+stream --out "$out/ab_n1_axis59.json" > "$out/ab_n1_axis59.jsonl" 2> "$out/ab_n1_axis59.log"
+    grep "^\[ab\]" "$out/ab_n1_axis59.log"
+    ;;
   g)
     # two GPUs: the distributed tests with a GPU per rank, the tuning A/B on the strong-scaling problem, the bench line,
     # config 3 and config 5 at N = 2

@@ -109,15 +109,10 @@ struct EpiResidual {
 template<int FORM, int W, int ND, bool RESID, class Epi>
 __global__ void __launch_bounds__(kThreads) apply_kernel(OpDev op, const double* __restrict__ x, double* __restrict__ y,
                                                          Epi epi, RedPtrs red, ApplyDist ad,
-                                                         const int* __restrict__ done,
-                                                         const __grid_constant__ ReducerArgs ra) {
+                                                         const int* __restrict__ done) {
   pdl_trigger();
   pdl_wait();
   if (is_done(done)) return;
-  if (ra.kind != kFinalNone && blockIdx.x == gridDim.x - 1) { // the in-kernel reducer (sb_finals.cuh) owns no tile
-    reducer_role(ra);
-    return;
-  }
   if (ad.n_pack > 0 && (int) blockIdx.x < ad.n_pack) {
     halo_pack_role(ad.comm, ad.halo, x, ad.x_off, ad.n_pack, ad.no_ack != 0);
     return;
@@ -179,10 +174,9 @@ struct StageLayout {
   // ptxas through __launch_bounds__ so that it uses the registers that occupancy leaves free anyway (85 at three CTAs)
   // instead of spilling down to 64
   static constexpr int fit = (227 * 1024) / (cta_bytes + 2048);
-#ifndef SB_TMA_REG_CTAS3 // A/B hook (scripts/gpu_session_r02.sh ab): the register budget when three CTAs fit
-#define SB_TMA_REG_CTAS3 3
-#endif
-  static constexpr int min_ctas = fit >= 3 ? SB_TMA_REG_CTAS3 : (fit >= 1 ? fit : 1);
+  // (64 against 72 registers at W = 4 -- __launch_bounds__(256, 4) against (256, 3) -- measured equal: 2 233-2 238 against
+  // 2 252-2 260 it/s, profiles/r02_ab_apply_registers.txt)
+  static constexpr int min_ctas = fit >= 3 ? 3 : (fit >= 1 ? fit : 1);
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -226,17 +220,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 template<int W, int ND, bool RESID, class Epi>
 __global__ void __launch_bounds__(kThreads, StageLayout<W>::min_ctas) apply_kernel_tma(OpDev op, const double* __restrict__ x,
                                                             double* __restrict__ y, Epi epi, RedPtrs red,
-                                                            ApplyDist ad, const int* __restrict__ done,
-                                                            const __grid_constant__ ReducerArgs ra) {
+                                                            ApplyDist ad, const int* __restrict__ done) {
   using L = StageLayout<W>;
   extern __shared__ __align__(128) unsigned char sb_smem[];
   __shared__ __align__(8) uint64_t bars[kWarps][kStages];
   pdl_trigger();
-  if (ra.kind != kFinalNone && blockIdx.x == gridDim.x - 1) { // the in-kernel reducer (sb_finals.cuh) owns no tile
-    pdl_wait();
-    if (!is_done(done)) reducer_role(ra);
-    return;
-  }
+  // (No in-kernel reducer role here, unlike ew_solver_kernel: merely CARRYING the out-of-line call -- a stack frame and
+  // 640 B more static shared memory, never executed without SB_TUNE_IN_KERNEL_REDUCER -- cost this kernel 6 % at 10.1 M
+  // cells: 153.9 against 143.8 us per apply + dot slot, BiCGStab 2 198 against 2 323 it/s on the same box,
+  // profiles/r02_ab_apply_without_reducer_call.txt. An apply's reduction always ends in the one-CTA final stage.)
   if (ad.n_pack > 0 && (int) blockIdx.x < ad.n_pack) { // halo-pack CTAs: scheduled first, overlap the interior tiles
     pdl_wait();
     if (!is_done(done)) halo_pack_role(ad.comm, ad.halo, x, ad.x_off, ad.n_pack, ad.no_ack != 0);
@@ -464,16 +456,20 @@ struct PushArgs {
   int32_t lazy = 0;          // 1: stores only; the consuming apply raises the flags (halo_post_flags)
 };
 
-template<int ND, class Body>
+// RED: the instantiation that carries the reducer role. The default path (RED = false) does not even contain the
+// out-of-line call: carrying it cost the apply kernel 6 % (see apply_kernel_tma).
+template<int ND, class Body, bool RED>
 __global__ void __launch_bounds__(kThreads) ew_solver_kernel(int64_t n, Body body, RedPtrs red, const int* __restrict__ done,
                                                              const __grid_constant__ PushArgs pa,
                                                              const __grid_constant__ ReducerArgs ra) {
   pdl_trigger();
   pdl_wait();
   if (is_done(done)) return;
-  if (ra.kind != kFinalNone && blockIdx.x == gridDim.x - 1) {
-    reducer_role(ra);
-    return;
+  if constexpr (RED) {
+    if (ra.kind != kFinalNone && blockIdx.x == gridDim.x - 1) {
+      reducer_role(ra);
+      return;
+    }
   }
   const int64_t tile = pa.push ? pa.n_tiles - 1 - (int64_t) blockIdx.x : (int64_t) blockIdx.x;
   typename Body::Regs r[kSub];
@@ -547,8 +543,6 @@ struct ApplyOpts {
   unsigned long long* halo_wait_ns = nullptr; // optional timeline: longest halo-flag wait of a boundary CTA
   unsigned long long* ar_wait_ns = nullptr;   // optional timeline: the final stage's wait for the other ranks' sums
   bool pdl = false, pdl_final = false;        // programmatic-serialization attribute on the apply / on its final stage
-  const ReducerArgs* reducer = nullptr;       // the reduction is finished by the last CTA of the apply kernel itself
-                                              // (sb_finals.cuh) instead of a one-CTA final stage behind this launch
 };
 
 template<int ND, bool RESID, class Epi, class Final>
@@ -559,9 +553,7 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
   if constexpr (ND > 0) {
     SB_TRY(ensure_red_scratch(ctx, d.n));
   }
-  ReducerArgs ra;
-  if (ao.reducer != nullptr) ra = *ao.reducer;
-  const RedPtrs red = ra.kind != kFinalNone ? RedPtrs{ra.slots, ra.cap_tiles} : RedPtrs{ctx->red.partials, ctx->red.cap_tiles};
+  const RedPtrs red{ctx->red.partials, ctx->red.cap_tiles};
   ApplyDist ad;
   CommCtrl* bump = nullptr;
   if (op->distributed && ctx->comm.world > 1) {
@@ -586,12 +578,11 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
     // neighbours) are compared against the same counter, which therefore has to advance in lockstep on all ranks.
     if (ctx->comm.mode == SB_COMM_P2P && !(ctx->debug & 2)) bump = ctx->comm.ctrl(ctx->comm.rank);
   }
-  if (ra.kind != kFinalNone) ra.bump = bump, ra.n_tiles = num_tiles(d.n);
-  const unsigned grid = (unsigned) (num_tiles(d.n) + ad.n_pack + (ra.kind != kFinalNone ? 1 : 0));
+  const unsigned grid = (unsigned) (num_tiles(d.n) + ad.n_pack);
   {
   PdlScope pdl_scope(ctx, ao.pdl);
 #define SB_LAUNCH(FORM, W) \
-  SB_CUDA(launch_kernel(ctx, apply_kernel<FORM, W, ND, RESID, Epi>, grid, kThreads, 0, d, x, y, epi, red, ad, done, ra))
+  SB_CUDA(launch_kernel(ctx, apply_kernel<FORM, W, ND, RESID, Epi>, grid, kThreads, 0, d, x, y, epi, red, ad, done))
 #define SB_WIDTHS(FORM)                   \
   switch (d.width) {                      \
     case 0: case 1: SB_LAUNCH(FORM, 1); break; \
@@ -622,7 +613,7 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
       SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
       configured.fetch_or(bit, std::memory_order_release);                                                      \
     }                                                                                                           \
-    SB_CUDA(launch_kernel(ctx, kern, grid, kThreads, smem, d, x, y, epi, red, ad, done, ra));                   \
+    SB_CUDA(launch_kernel(ctx, kern, grid, kThreads, smem, d, x, y, epi, red, ad, done));                       \
   }
     switch (d.width) {
       case 0: case 1: SB_LAUNCH_TMA(1) break;
@@ -651,7 +642,7 @@ int launch_apply(sb_ctx* ctx, const sb_op* op, const double* x, double* y, const
 #undef SB_LAUNCH
   }
   ctx->launches++;
-  if (ao.fold_later || ra.kind != kFinalNone) return SB_OK;
+  if (ao.fold_later) return SB_OK;
   if constexpr (ND > 0) return launch_final<ND>(ctx, d.n, fin, done, bump, ao.ar_wait_ns, ao.pdl_final);
   if (bump != nullptr) {
     SB_CUDA(launch_kernel(ctx, seq_bump_kernel, 1, 1, 0, bump, done));

@@ -58,8 +58,10 @@ int launch_ew_solver(sb_ctx* ctx, const sb_op* op, int64_t n, const Body& body, 
   }
   {
     PdlScope pdl_scope(ctx, pdl);
-    SB_CUDA(launch_kernel(ctx, ew_solver_kernel<ND, Body>, (unsigned) (num_tiles(n) + (in_kernel ? 1 : 0)), kThreads, 0, n, body,
-                          red, done, pa, ra));
+    if (in_kernel)
+      SB_CUDA(launch_kernel(ctx, ew_solver_kernel<ND, Body, true>, (unsigned) (num_tiles(n) + 1), kThreads, 0, n, body, red, done, pa, ra));
+    else
+      SB_CUDA(launch_kernel(ctx, ew_solver_kernel<ND, Body, false>, (unsigned) num_tiles(n), kThreads, 0, n, body, red, done, pa, ra));
   }
   ctx->launches++;
   if constexpr (ND > 0) {
@@ -294,8 +296,7 @@ struct Solve {
     ao.pdl = pdl_apply, ao.pdl_final = pdl_final;
     const WaitPair w = wait_slot();
     ao.halo_wait_ns = w.own, ao.ar_wait_ns = w.ar;
-    const ReducerArgs ra = reducer(kind, ND, w.ar);
-    if (in_kernel) ao.reducer = &ra;
+    (void) kind; // an apply's reduction always ends in the one-CTA final stage (sb_op.cuh: apply_kernel_tma)
     return launch_apply<ND, RESID>(ctx, op, in, out, epi, fin, done, ao);
   }
 
@@ -483,7 +484,8 @@ static int run_solver(sb_ctx* ctx, const sb_op* op, Kind kind, double* x, const 
         SB_CUDA(cudaGraphInstantiate(&guard.graph_exec, guard.graph, 0));
       }
     }
-    const int launches_per_iter = (S.folded || S.in_kernel) ? per_iter : ((kind == Kind::Cg) ? 5 : 8); // + one-CTA final stages
+    // + the one-CTA final stages (with the in-kernel reducer only those behind the applies remain)
+    const int launches_per_iter = S.folded ? per_iter : (S.in_kernel ? per_iter + ((kind == Kind::Cg) ? 1 : 2) : ((kind == Kind::Cg) ? 5 : 8));
 
     // Convergence polling: a flag copy is queued every `check` iterations and examined one batch later,
     // so the host never drains the stream while it still has work to enqueue.
