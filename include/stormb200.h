@@ -433,10 +433,12 @@ typedef struct sb_solver_opts {
 #define SB_TUNE_STREAM_OPERATOR 4u
 #define SB_TUNE_PDL_FINAL 8u
 #define SB_TUNE_PDL_AFTER_FINAL 16u
-#define SB_TUNE_IN_KERNEL_REDUCER 64u /* every reduction is finished by the LAST CTA of the kernel that produces it: it
-                                         takes the tile partials as they appear (the value is the flag), runs the
-                                         all-reduce over the ranks and the scalar update; no one-CTA kernels between
-                                         the steps (3 / 5 launches per CG / BiCGStab iteration), nobody waits in-kernel */
+#define SB_TUNE_IN_KERNEL_REDUCER 64u /* the reductions of the ELEMENT-WISE steps are finished by the last CTA of the
+                                         kernel that produces them: it takes the tile partials as they appear (the
+                                         value is the flag), runs the all-reduce over the ranks and the scalar update;
+                                         nobody waits in-kernel. An apply's reduction keeps its one-CTA final stage
+                                         (4 / 7 launches per CG / BiCGStab iteration): carrying the role cost the apply
+                                         kernel 6 % whether used or not */
 #define SB_TUNE_PDL_APPLY 32u /* the apply kernels too (they follow an element-wise kernel; slice prefetch under its tail) */
 #define SB_TUNE_PUSH_LAZY 128u /* with PUSH_ON_PRODUCE: the producer only issues the peer stores (posted writes that drain
                                   while the rest of it runs; its completion performs them); the flags are raised by the

@@ -230,6 +230,13 @@ PY
     timeout 300 python scripts/scale_ab.py --axis 59 --variants default,off,red+stream --out "$out/ab_n1_axis59.json" > "$out/ab_n1_axis59.jsonl" 2> "$out/ab_n1_axis59.log"
     grep "^\[ab\]" "$out/ab_n1_axis59.log"
     ;;
+  k4)
+    # one GPU: the whole GPU suite on the round's last code state
+    export SB_SPIN_TIMEOUT_S=30
+    timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -30 > "$out/pytest_gpu.log"; tail -5 "$out/pytest_gpu.log"
+    unset SB_SPIN_TIMEOUT_S
+    python -c "import __graft_entry__ as g; g.smoke()" > "$out/smoke.log" 2>&1; tail -4 "$out/smoke.log"
+    ;;
   g)
     # two GPUs: the distributed tests with a GPU per rank, the tuning A/B on the strong-scaling problem, the bench line,
     # config 3 and config 5 at N = 2

@@ -83,8 +83,8 @@ def test_persistent_schedule_bit_identical_to_oracle_and_to_stepwise(ctx, name, 
         for graph in (True, False):
             got = run(ctx, gpu, solver, b, STEP, iters, use_graph=graph, tuning=tuning)
             assert same(pers, got), (tuning, graph)
-            if tuning & capi.TUNE_IN_KERNEL_REDUCER:   # no one-CTA kernels between the steps
-                assert got[0].launches <= (3 if solver == "cg" else 5) * (iters + 1) + 6
+            if tuning & capi.TUNE_IN_KERNEL_REDUCER:   # one-CTA kernels only behind the applies (1 / 2 per iteration)
+                assert got[0].launches <= (4 if solver == "cg" else 7) * (iters + 1) + 6
     # stops in the middle of the loop, on the relative tolerance: same iterate as the stepwise schedule, and again
     # when the two schedules alternate on one context (the all-reduce mailbox parity carries over)
     rel = want.hist / want.hist[0]
