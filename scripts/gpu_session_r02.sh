@@ -187,11 +187,13 @@ PY
     du -sh "$out"
     ;;
   h5)
-    # eight GPUs: the 20 M-cell strong-scaling point with the library's defaults (2.53 M cells per rank)
+    # N GPUs: a larger strong-scaling point with the library's defaults (axis 161 = 25.0 M cells, 3.13 M per rank at N = 8);
+    # `h5 1 161` is its single-GPU reference
     N=${2:-8}
-    timeout 400 $TR --nproc-per-node $N --master-port 29561 scripts/scale_ab.py --axis 150 --variants default --no-profile \
-        --out "$out/ab_n${N}_axis150.json" > "$out/ab_n${N}_axis150.jsonl" 2> "$out/ab_n${N}_axis150.log"
-    grep "^\[ab\]" "$out/ab_n${N}_axis150.log"
+    AX=${3:-161}
+    timeout 200 $TR --nproc-per-node $N --master-port 29561 scripts/scale_ab.py --axis $AX --variants default --no-profile \
+        --out "$out/ab_n${N}_axis$AX.json" > "$out/ab_n${N}_axis$AX.jsonl" 2> "$out/ab_n${N}_axis$AX.log"
+    grep "^\[ab\]" "$out/ab_n${N}_axis$AX.log"
     ;;
   ab)
     # one GPU: the TMA apply kernel compiled for 72 registers (__launch_bounds__(256, 3), the tree's build) against 64
