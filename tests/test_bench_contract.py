@@ -81,3 +81,35 @@ def test_reference_arm_never_maps_the_cuda_library():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "MAPS False True True" in out.stdout, out.stdout[-500:]
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """The round's bench line as measured on the B200 (profiles/r02_bench_n1.json): every key the measurement contract
+    names, with the meaning it names (roofline per launch of the dominant kernel, CPU baseline beside it, end-to-end
+    number with its copy volumes, clock record, parity of both solvers at full size)."""
+    import json
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in line, k
+    assert line["metric"] == "krylov_iterations_per_sec" and line["unit"] == "it/s" and line["dtype"] == "f64"
+    assert line["vs_baseline"] is None and line["higher_is_better"] is True and "workload" in line["config"]
+    r = line["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["avg_launch_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    # per variant: its own bytes (the <r~,v> epilogue reads a third vector), never more than the measured copy bandwidth
+    n = line["config"]["cells"]
+    uy, yy = r["variants"]
+    assert uy["algorithmic_bytes_per_launch"] - yy["algorithmic_bytes_per_launch"] == 8 * n
+    assert all(0.5 < v["frac"] < 1.0 and 0.0 < v["final_stage_ms"] < v["avg_launch_ms"] for v in r["variants"])
+    assert 0.9 < r["traffic"] / r["algorithmic_bytes_per_launch"] < 1.1          # no wasted re-reads
+    c = line["cpu_baseline"]
+    assert c["kind"] == "reference" and c["cores"] == 1 and c["unit"] == "it/s" and c["value"] > 0 and c["sample"]
+    e = line["e2e"]
+    assert e["unit"] == "it/s" and 0 < e["value"] < line["value"] and e["h2d_bytes_per_step"] == 16 * n / line["steps"]
+    assert line["gpu_launches"] >= 8 * line["steps"]                             # 5 steps + 3 final stages per iteration
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(line["clocks"]["reasons"])
+    # parity at full size: BiCGStab leaves the 1e-10 bar early (reduction order), CG stays inside it
+    assert line["parity"]["measured_path_coef_rows"]["first_iteration_over_1e-10"] >= 5
+    assert line["parity_other_solver"]["measured_path_coef_rows"]["first_iteration_over_1e-10"] is None
