@@ -196,6 +196,8 @@ PY
     grep "^\[ab\]" "$out/ab_n${N}_axis$AX.log"
     ;;
   ab)
+    # (record of a finished experiment: the -D hooks and the ab/ libraries were removed once it was decided;
+    #  results: profiles/r02_ab_apply_registers.txt, r02_ab_apply_without_reducer_call.txt)
     # one GPU: the TMA apply kernel compiled for 72 registers (__launch_bounds__(256, 3), the tree's build) against 64
     # registers (__launch_bounds__(256, 4): what ptxas chose in round 1), same source otherwise (ab/libstormb200_regs64.so,
     # built with -DSB_TMA_REG_CTAS3=4); two problem sizes, slot times included
